@@ -1,0 +1,164 @@
+/*
+ * gcnb.h -- C ABI of libgcn_b200.so, the Blackwell (sm_100a) GCN training kernels.
+ *
+ * This is the drop-in boundary of the hot path: plain pointers and sizes, no C++/torch types.  The
+ * reference (davide-gurrieri/parallel-GCN) has no FFI of its own; each entry point below replaces the CUDA
+ * kernel(s) behind one method of the reference's C++ module API and cites it (paths relative to the
+ * reference repo).  The C++ classes in parallel-gcn_b200/host/ (same names/signatures as the reference:
+ * Variable, Dropout, SparseMatmul, GraphSum, ReLU, Matmul, CrossEntropyLoss, Adam, GCN, Parser) call ONLY
+ * these functions; tests and bench.py call them through ctypes.
+ *
+ * Conventions
+ *   - every `d_*` pointer is a device pointer; tensors are fp32 row-major, indices uint32 (the reference's
+ *     `natural`), labels/truth int32, sizes int64;
+ *   - every launch is asynchronous on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream);
+ *   - return value: 0 on success, otherwise a cudaError_t (or GCNB_E_* below); gcnb_error_string() explains;
+ *   - no hidden global state: per-graph metadata lives in an explicit plan object; all reductions are
+ *     fixed-order (no floating-point atomics), so results are bit-reproducible run to run;
+ *   - there is NO CPU fallback: every function fails (cudaErrorNoDevice / cudaErrorInsufficientDriver ...)
+ *     when no sm_100 device is usable.
+ */
+#ifndef GCNB_H
+#define GCNB_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GCNB_API __attribute__((visibility("default")))
+#define GCNB_E_BADARG 10001
+#define GCNB_E_UNSUPPORTED 10002
+
+typedef void *gcnb_stream_t; /* cudaStream_t */
+
+GCNB_API const char *gcnb_error_string(int code);
+GCNB_API int gcnb_version(void);
+/* device sanity: fails unless the current device is compute capability 10.x; fills SM count. */
+GCNB_API int gcnb_device_check(int *sm_count);
+
+/* ---------------------------------------------------------------------------------------------------
+ * CSR x dense plan.  One plan per sparse index (graph adjacency, feature matrix, or the transposed
+ * feature matrix); built once, reused by every launch.  Holds the load-balancing metadata the reference
+ * does not have: rows are cut into segments of <= seg_nnz entries, segments are grouped into per-SM queues of
+ * equal nnz (contiguous rows per SM => neighbour rows are re-used from that SM's L1), long rows are combined
+ * in a fixed order from per-segment partials.  Replaces the launch-shape knobs CudaParams::N_BLOCKS/N_THREADS
+ * (include/utils.cuh:17-23, src/module.cu:71-72 pattern).
+ * The plan BORROWS d_indptr/d_indices (they must outlive it), exactly like DevSparseIndex users do
+ * (include/sparse.cuh:21-29).
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct gcnb_spmm_plan gcnb_spmm_plan;
+GCNB_API int gcnb_spmm_plan_create(const uint32_t *d_indptr, const uint32_t *d_indices, int64_t n_rows,
+                                   int64_t n_cols, int seg_nnz /*0 = default*/, gcnb_stream_t stream,
+                                   gcnb_spmm_plan **out);
+GCNB_API int gcnb_spmm_plan_destroy(gcnb_spmm_plan *plan);
+/* number of segments / split rows / queues (introspection for tests & DESIGN numbers) */
+GCNB_API int gcnb_spmm_plan_info(const gcnb_spmm_plan *plan, int64_t out[8]);
+
+/* C[n_rows x dim] = A_csr * B[n_cols x dim],  A_csr values = d_values[e] (or d_values[d_perm[e]] if d_perm).
+ *   GraphSum::forward/backward + graphsum_kernel            src/module.cu:172-210  (values = graph_value)
+ *   SparseMatmul::forward + sparse_matmul_kernel_forward     src/module.cu:108-132  (values = input Variable)
+ * Fully overwrites C.  Summation: fixed order (segment-local lane tree, then ascending segments). */
+GCNB_API int gcnb_spmm_f32(gcnb_spmm_plan *plan, const float *d_values, const uint32_t *d_perm, const float *d_B,
+                           float *d_C, int dim, gcnb_stream_t stream);
+
+/* Transposed-CSR companion for SparseMatmul::backward (src/module.cu:136-163; atomicAdd there, fixed-order here):
+ * builds on the device the CSC of a CSR (column pointers, row ids, and the permutation into the CSR value array
+ * so that dropped-out input values are picked up without rebuilding).  Outputs are allocated by the call and
+ * owned by the returned handle. */
+typedef struct gcnb_csc gcnb_csc;
+GCNB_API int gcnb_csc_create(const uint32_t *d_indptr, const uint32_t *d_indices, int64_t n_rows, int64_t n_cols,
+                             gcnb_stream_t stream, gcnb_csc **out);
+GCNB_API int gcnb_csc_destroy(gcnb_csc *csc);
+GCNB_API int gcnb_csc_arrays(const gcnb_csc *csc, const uint32_t **d_colptr, const uint32_t **d_rowidx,
+                             const uint32_t **d_perm, int *is_dense /* every row holds columns 0..n_cols-1 */);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Dense tall-skinny products (Matmul module, src/module.cu:270-472).  Row-major fp32, FFMA (no TF32: the
+ * parity bar is 1e-5).  `ws` = caller workspace for the split-K partials of the TN product
+ * (gcnb_matmul_tn_workspace() bytes); fixed-order second pass => deterministic (reference: atomicAdd :389).
+ *   NN: C[m x p]  = A[m x n]   * B[n x p]      Matmul::forward            :319-328
+ *   NT: dA[m x n] = dC[m x p]  * B[n x p]^T    matmul_kernel_backward_1   :332-374
+ *   TN: dB[n x p] = A[m x n]^T * dC[m x p]     matmul_kernel_backward_2   :377-391
+ * ------------------------------------------------------------------------------------------------- */
+GCNB_API int gcnb_matmul_nn_f32(const float *d_A, const float *d_B, float *d_C, int64_t m, int n, int p,
+                                gcnb_stream_t stream);
+GCNB_API int gcnb_matmul_nt_f32(const float *d_dC, const float *d_B, float *d_dA, int64_t m, int n, int p,
+                                gcnb_stream_t stream);
+GCNB_API int64_t gcnb_matmul_tn_workspace(int64_t m, int n, int p);
+GCNB_API int gcnb_matmul_tn_f32(const float *d_A, const float *d_dC, float *d_dB, int64_t m, int n, int p,
+                                void *d_ws, int64_t ws_bytes, gcnb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Elementwise / RNG.
+ * Stateless Philox4x32-10 reproducing the reference's cuRAND streams with no state array:
+ * element 4g+k of an RNG op = lane k of Philox(ctr=(t,0,g,0), key=(seed,0)), t = number of earlier RNG ops that
+ * covered state g (src/variable.cu:5-11,44-61; src/module.cu:16-63).  The caller describes "earlier ops" by
+ * up to GCNB_MAX_RNG_HIST (n_groups, count) pairs: t(g) = sum(count_i for n_groups_i > g).
+ * ------------------------------------------------------------------------------------------------- */
+#define GCNB_MAX_RNG_HIST 8
+typedef struct {
+  uint32_t seed;
+  int n_hist;
+  uint32_t hist_groups[GCNB_MAX_RNG_HIST]; /* ceil(size/4) of an earlier RNG consumer */
+  uint32_t hist_count[GCNB_MAX_RNG_HIST];  /* how many times it has run */
+} gcnb_rng_t;
+
+/* Variable::glorot (src/variable.cu:44-83): w = (u - 0.5) * 2*sqrtf(6/(rows+cols)), double arithmetic. */
+GCNB_API int gcnb_glorot_f32(float *d_w, int64_t size, uint32_t rows, uint32_t cols, const gcnb_rng_t *rng,
+                             gcnb_stream_t stream);
+/* Dropout::forward (src/module.cu:16-76): x *= (u >= p) ? scale : 0 in place; d_mask (1 byte/element) optional.
+ * If d_ext_mask != NULL the keep decisions are READ from it instead of drawn (injected masks). */
+GCNB_API int gcnb_dropout_fwd_f32(float *d_x, uint8_t *d_mask, const uint8_t *d_ext_mask, int64_t size, float p,
+                                  const gcnb_rng_t *rng, gcnb_stream_t stream);
+/* Dropout::backward (src/module.cu:80-99): g *= mask ? scale : 0. */
+GCNB_API int gcnb_dropout_bwd_f32(float *d_g, const uint8_t *d_mask, int64_t size, float p, gcnb_stream_t stream);
+/* ReLU::forward/backward (src/module.cu:222-265); mask written only when training. */
+GCNB_API int gcnb_relu_fwd_f32(float *d_x, uint8_t *d_mask, int64_t size, int training, gcnb_stream_t stream);
+GCNB_API int gcnb_relu_bwd_f32(float *d_g, const uint8_t *d_mask, int64_t size, gcnb_stream_t stream);
+/* Fused pair used by the GCN driver: ReLU then Dropout in one pass, one packed mask byte per element
+ * (bit0 = relu keep, bit1 = dropout keep); backward applies dropout-bwd then relu-bwd like the module chain. */
+GCNB_API int gcnb_relu_dropout_fwd_f32(float *d_x, uint8_t *d_mask, const uint8_t *d_ext_mask, int64_t size, float p,
+                                       int training, const gcnb_rng_t *rng, gcnb_stream_t stream);
+GCNB_API int gcnb_relu_dropout_bwd_f32(float *d_g, const uint8_t *d_mask, int64_t size, float p, gcnb_stream_t stream);
+/* GCN::set_truth (src/gcn.cu:204-226). */
+GCNB_API int gcnb_set_truth(int32_t *d_truth, const uint32_t *d_split, const int32_t *d_label, int64_t n,
+                            uint32_t current_split, gcnb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * CrossEntropyLoss::forward (src/module.cu:484-541) + GCN::get_accuracy (src/gcn.cu:264-289) in one pass.
+ * In-place logits -= rowmax for rows with truth >= 0 (API-visible side effect kept); if training:
+ * grad = softmax/num_samples, grad[truth] -= 1.0/num_samples (double), rows with truth < 0 get grad 0.
+ * d_result[0] = un-normalised loss sum (float), d_result[1] = bit pattern of the uint32 wrong count,
+ * d_result[2] = bit pattern of the uint32 labelled-row count.  Deterministic two-level reduction.
+ * d_ws: gcnb_ce_workspace(n) bytes.
+ * ------------------------------------------------------------------------------------------------- */
+GCNB_API int64_t gcnb_ce_workspace(int64_t n);
+GCNB_API int gcnb_softmax_ce_f32(float *d_logits, float *d_grad, const int32_t *d_truth, int64_t n, int num_classes,
+                                 uint32_t num_samples, int training, float *d_result, void *d_ws,
+                                 gcnb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Adam::step (src/optim.cu:42-95) for up to GCNB_MAX_TENSORS weights in ONE launch, and
+ * GCN::get_l2_penalty (src/gcn.cu:230-260) as a fixed-order sum of squares.
+ * ------------------------------------------------------------------------------------------------- */
+#define GCNB_MAX_TENSORS 16
+typedef struct {
+  int n_tensors;
+  float *w[GCNB_MAX_TENSORS];
+  const float *g[GCNB_MAX_TENSORS];
+  float *m[GCNB_MAX_TENSORS];
+  float *v[GCNB_MAX_TENSORS];
+  int64_t size[GCNB_MAX_TENSORS];
+  int decay[GCNB_MAX_TENSORS];
+} gcnb_adam_tensors_t;
+GCNB_API int gcnb_adam_step_f32(const gcnb_adam_tensors_t *t, float weight_decay, float beta1, float beta2, float eps,
+                                float step_size, gcnb_stream_t stream);
+/* d_out[0] = sum_i w[i]^2 (ascending fixed tree).  d_ws: gcnb_sumsq_workspace(n) bytes. */
+GCNB_API int64_t gcnb_sumsq_workspace(int64_t n);
+GCNB_API int gcnb_sumsq_f32(const float *d_w, int64_t n, float *d_out, void *d_ws, gcnb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GCNB_H */

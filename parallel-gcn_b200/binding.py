@@ -1,0 +1,263 @@
+"""ctypes binding of libgcn_b200.so (the C ABI declared in include/gcnb.h).
+
+PyTorch is used only as plumbing: device memory (tensor.data_ptr()) and the current CUDA stream.  There is no
+CPU / eager fallback: importing this module without the built library, or calling any kernel without a usable
+sm_100 device, raises.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libgcn_b200.so")
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        "libgcn_b200.so is not built (%s). Run `python -c 'import __graft_entry__ as g; g.build()'` "
+        "or `python parallel-gcn_b200/build.py`; there is no fallback path." % LIB_PATH)
+
+lib = C.CDLL(LIB_PATH)
+P, I64, I32, U32, F32 = C.c_void_p, C.c_int64, C.c_int, C.c_uint32, C.c_float
+
+MAX_RNG_HIST = 8
+MAX_TENSORS = 16
+
+
+class RngT(C.Structure):
+    _fields_ = [("seed", U32), ("n_hist", I32), ("hist_groups", U32 * MAX_RNG_HIST), ("hist_count", U32 * MAX_RNG_HIST)]
+
+
+class AdamTensorsT(C.Structure):
+    _fields_ = [("n_tensors", I32), ("w", P * MAX_TENSORS), ("g", P * MAX_TENSORS), ("m", P * MAX_TENSORS),
+                ("v", P * MAX_TENSORS), ("size", I64 * MAX_TENSORS), ("decay", I32 * MAX_TENSORS)]
+
+
+def _sig(name, res, args):
+    fn = getattr(lib, name)
+    fn.restype = res
+    fn.argtypes = args
+    return fn
+
+
+_sig("gcnb_error_string", C.c_char_p, [I32])
+_sig("gcnb_version", I32, [])
+_sig("gcnb_device_check", I32, [P])
+_sig("gcnb_spmm_plan_create", I32, [P, P, I64, I64, I32, P, P])
+_sig("gcnb_spmm_plan_destroy", I32, [P])
+_sig("gcnb_spmm_plan_info", I32, [P, P])
+_sig("gcnb_spmm_f32", I32, [P, P, P, P, P, I32, P])
+_sig("gcnb_csc_create", I32, [P, P, I64, I64, P, P])
+_sig("gcnb_csc_destroy", I32, [P])
+_sig("gcnb_csc_arrays", I32, [P, P, P, P, P])
+_sig("gcnb_matmul_nn_f32", I32, [P, P, P, I64, I32, I32, P])
+_sig("gcnb_matmul_nt_f32", I32, [P, P, P, I64, I32, I32, P])
+_sig("gcnb_matmul_tn_workspace", I64, [I64, I32, I32])
+_sig("gcnb_matmul_tn_f32", I32, [P, P, P, I64, I32, I32, P, I64, P])
+_sig("gcnb_glorot_f32", I32, [P, I64, U32, U32, P, P])
+_sig("gcnb_dropout_fwd_f32", I32, [P, P, P, I64, F32, P, P])
+_sig("gcnb_dropout_bwd_f32", I32, [P, P, I64, F32, P])
+_sig("gcnb_relu_fwd_f32", I32, [P, P, I64, I32, P])
+_sig("gcnb_relu_bwd_f32", I32, [P, P, I64, P])
+_sig("gcnb_relu_dropout_fwd_f32", I32, [P, P, P, I64, F32, I32, P, P])
+_sig("gcnb_relu_dropout_bwd_f32", I32, [P, P, I64, F32, P])
+_sig("gcnb_set_truth", I32, [P, P, P, I64, U32, P])
+_sig("gcnb_ce_workspace", I64, [I64])
+_sig("gcnb_softmax_ce_f32", I32, [P, P, P, I64, I32, U32, I32, P, P, P])
+_sig("gcnb_adam_step_f32", I32, [P, F32, F32, F32, F32, F32, P])
+_sig("gcnb_sumsq_workspace", I64, [I64])
+_sig("gcnb_sumsq_f32", I32, [P, I64, P, P, P])
+
+
+class GcnbError(RuntimeError):
+    pass
+
+
+def check(code):
+    if code != 0:
+        raise GcnbError("libgcn_b200: error %d: %s" % (code, lib.gcnb_error_string(code).decode()))
+
+
+def ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def device_check():
+    n = C.c_int(0)
+    check(lib.gcnb_device_check(C.byref(n)))
+    return n.value
+
+
+def make_rng(seed, history=()):
+    """history: iterable of (n_elements_of_an_earlier_rng_op, times_it_ran)."""
+    r = RngT()
+    r.seed = int(seed) & 0xFFFFFFFF
+    merged = {}
+    for size, count in history:
+        g = (int(size) + 3) // 4
+        merged[g] = merged.get(g, 0) + int(count)
+    items = [(g, c) for g, c in merged.items() if c > 0]
+    if len(items) > MAX_RNG_HIST:
+        raise ValueError("too many distinct RNG consumers")
+    r.n_hist = len(items)
+    for i, (g, c) in enumerate(items):
+        r.hist_groups[i] = g
+        r.hist_count[i] = c
+    return r
+
+
+class SpmmPlan:
+    """gcnb_spmm_plan: load-balancing metadata of one CSR index (borrowed device arrays)."""
+
+    def __init__(self, indptr, indices, n_cols, seg_nnz=0):
+        self.indptr, self.indices = indptr, indices  # keep alive: the plan borrows them
+        self.n_rows = indptr.numel() - 1
+        self.n_cols = int(n_cols)
+        h = C.c_void_p()
+        check(lib.gcnb_spmm_plan_create(ptr(indptr), ptr(indices), self.n_rows, self.n_cols, int(seg_nnz), stream(),
+                                        C.byref(h)))
+        self.h = h
+
+    def info(self):
+        out = (I64 * 8)()
+        check(lib.gcnb_spmm_plan_info(self.h, out))
+        keys = ("n_rows", "nnz", "n_seg", "n_split_rows", "n_slots", "n_queues", "seg_nnz", "max_deg")
+        return dict(zip(keys, [int(x) for x in out]))
+
+    def spmm(self, values, B, C_out, dim, perm=None):
+        check(lib.gcnb_spmm_f32(self.h, ptr(values), ptr(perm), ptr(B), ptr(C_out), int(dim), stream()))
+        return C_out
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib.gcnb_spmm_plan_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+
+class Csc:
+    """gcnb_csc: transposed view (column pointers, row ids, permutation into the CSR value array)."""
+
+    def __init__(self, indptr, indices, n_cols):
+        import torch
+        self.n_rows, self.n_cols = indptr.numel() - 1, int(n_cols)
+        h = C.c_void_p()
+        check(lib.gcnb_csc_create(ptr(indptr), ptr(indices), self.n_rows, self.n_cols, stream(), C.byref(h)))
+        self.h = h
+        cp, ri, pm, dense = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_int(0)
+        check(lib.gcnb_csc_arrays(h, C.byref(cp), C.byref(ri), C.byref(pm), C.byref(dense)))
+        self.is_dense = bool(dense.value)
+        self.colptr_ptr, self.rowidx_ptr, self.perm_ptr = cp, ri, pm
+        self.nnz = int(indices.numel())
+        self.plan = None
+        if not self.is_dense:
+            # wrap the library-owned arrays as torch tensors without copying (for plan creation)
+            self.colptr = _wrap_u32(cp.value, self.n_cols + 1, indptr.device)
+            self.rowidx = _wrap_u32(ri.value, max(self.nnz, 1), indptr.device)[: self.nnz]
+            self.perm = _wrap_u32(pm.value, max(self.nnz, 1), indptr.device)[: self.nnz]
+            self.plan = SpmmPlan(self.colptr, self.rowidx, self.n_rows)
+
+    def close(self):
+        if self.plan is not None:
+            self.plan.close()
+            self.plan = None
+        if getattr(self, "h", None):
+            lib.gcnb_csc_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+
+def _wrap_u32(addr, n, device):
+    """torch view (int32 storage) over library-owned device memory."""
+    import torch
+
+    class _Holder:
+        pass
+
+    h = _Holder()
+    h.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (addr, False), "version": 2}
+    return torch.as_tensor(h, device=device)
+
+
+def matmul_nn(A, B, Cout, m, n, p):
+    check(lib.gcnb_matmul_nn_f32(ptr(A), ptr(B), ptr(Cout), m, n, p, stream()))
+    return Cout
+
+
+def matmul_nt(dC, B, dA, m, n, p):
+    check(lib.gcnb_matmul_nt_f32(ptr(dC), ptr(B), ptr(dA), m, n, p, stream()))
+    return dA
+
+
+def matmul_tn(A, dC, dB, m, n, p, ws=None):
+    import torch
+    need = lib.gcnb_matmul_tn_workspace(m, n, p)
+    if ws is None or ws.numel() * ws.element_size() < need:
+        ws = torch.empty((need + 3) // 4, dtype=torch.float32, device=A.device)
+    check(lib.gcnb_matmul_tn_f32(ptr(A), ptr(dC), ptr(dB), m, n, p, ptr(ws), ws.numel() * ws.element_size(), stream()))
+    return dB
+
+
+def glorot(w, rows, cols, rng):
+    check(lib.gcnb_glorot_f32(ptr(w), w.numel(), rows, cols, C.byref(rng), stream()))
+    return w
+
+
+def dropout_fwd(x, mask, p, rng=None, ext_mask=None):
+    check(lib.gcnb_dropout_fwd_f32(ptr(x), ptr(mask), ptr(ext_mask), x.numel(), p,
+                                   C.byref(rng) if rng is not None else None, stream()))
+
+
+def dropout_bwd(g, mask, p):
+    check(lib.gcnb_dropout_bwd_f32(ptr(g), ptr(mask), g.numel(), p, stream()))
+
+
+def relu_fwd(x, mask, training):
+    check(lib.gcnb_relu_fwd_f32(ptr(x), ptr(mask), x.numel(), int(training), stream()))
+
+
+def relu_bwd(g, mask):
+    check(lib.gcnb_relu_bwd_f32(ptr(g), ptr(mask), g.numel(), stream()))
+
+
+def relu_dropout_fwd(x, mask, p, training, rng=None, ext_mask=None):
+    check(lib.gcnb_relu_dropout_fwd_f32(ptr(x), ptr(mask), ptr(ext_mask), x.numel(), p, int(training),
+                                        C.byref(rng) if rng is not None else None, stream()))
+
+
+def relu_dropout_bwd(g, mask, p):
+    check(lib.gcnb_relu_dropout_bwd_f32(ptr(g), ptr(mask), g.numel(), p, stream()))
+
+
+def set_truth(truth, split, label, cur):
+    check(lib.gcnb_set_truth(ptr(truth), ptr(split), ptr(label), truth.numel(), cur, stream()))
+
+
+def zeroed_workspace(nbytes, device):
+    import torch
+    return torch.zeros((int(nbytes) + 3) // 4, dtype=torch.int32, device=device)
+
+
+def softmax_ce(logits, grad, truth, n, num_classes, num_samples, training, result, ws):
+    check(lib.gcnb_softmax_ce_f32(ptr(logits), ptr(grad), ptr(truth), n, num_classes, num_samples, int(training),
+                                  ptr(result), ptr(ws), stream()))
+
+
+def adam_step(tensors, weight_decay, beta1, beta2, eps, step_size):
+    """tensors: list of (w, g, m, v, decay)."""
+    t = AdamTensorsT()
+    t.n_tensors = len(tensors)
+    for i, (w, g, m, v, decay) in enumerate(tensors):
+        t.w[i], t.g[i], t.m[i], t.v[i] = w.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr()
+        t.size[i] = w.numel()
+        t.decay[i] = int(bool(decay))
+    check(lib.gcnb_adam_step_f32(C.byref(t), weight_decay, beta1, beta2, eps, step_size, stream()))
+
+
+def sumsq(w, out, ws):
+    check(lib.gcnb_sumsq_f32(ptr(w), w.numel(), ptr(out), ptr(ws), stream()))

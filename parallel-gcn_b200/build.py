@@ -1,0 +1,67 @@
+"""Builds libgcn_b200.so (hand-written sm_100a kernels + C++ host mirror of the reference API) in-tree.
+
+nvcc cross-compiles without a GPU; the .so is git-ignored but travels to the GPU box with gpurun.
+"""
+import glob
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "libgcn_b200.so")
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--shared",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-Xcompiler", "-pthread",
+]
+
+
+def sources():
+    return sorted(glob.glob(os.path.join(HERE, "csrc", "*.cu")) + glob.glob(os.path.join(HERE, "host", "src", "*.cpp"))
+                  + glob.glob(os.path.join(HERE, "host", "src", "*.cu")))
+
+
+def headers():
+    root = os.path.dirname(HERE)
+    return sorted(glob.glob(os.path.join(HERE, "csrc", "*.cuh")) + glob.glob(os.path.join(HERE, "host", "include", "*"))
+                  + glob.glob(os.path.join(root, "include", "*.h")))
+
+
+def stale():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(f) > t for f in sources() + headers() + [os.path.abspath(__file__)])
+
+
+def build(force=False, verbose=False):
+    if not force and not stale():
+        return LIB
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    objs = []
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    procs = []
+    for src in sources():
+        obj = os.path.join(objdir, os.path.basename(src) + ".o")
+        objs.append(obj)
+        deps = headers() + [src, os.path.abspath(__file__)]
+        if not force and os.path.exists(obj) and all(os.path.getmtime(obj) >= os.path.getmtime(d) for d in deps):
+            continue
+        cmd = [nvcc] + [f for f in NVCC_FLAGS if f != "--shared"] + ["-x", "cu", "-c", src, "-o", obj,
+                                                                      "-I", os.path.join(HERE, "host", "include")]
+        if verbose:
+            cmd += ["-Xptxas", "-v"]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for src, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            sys.stderr.write(out)
+            raise RuntimeError("nvcc failed on %s" % src)
+        if verbose:
+            sys.stderr.write(out)
+    subprocess.check_call([nvcc, "--shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,300 @@
+// elementwise.cu -- Dropout / ReLU / Glorot / set_truth / Adam / L2 kernels for sm_100a.
+// Replaces dropout_kernel_forward/backward, relu_kernel_forward/backward (src/module.cu:16-99,222-265),
+// glorot_kernel + initialize_var_random_kernel (src/variable.cu:5-83), set_truth_kernel (src/gcn.cu:204-210),
+// adam_step_kernel (src/optim.cu:42-55) and get_l2_penalty_kernel (src/gcn.cu:230-243).
+// All are HBM-streaming: 16-byte vector accesses, grid sized to the SM count, no RNG state array (stateless
+// Philox, philox.cuh), fixed-order reductions instead of the reference's atomicAdd.
+#include <algorithm>
+
+#include "common.cuh"
+#include "philox.cuh"
+
+using namespace gcnb;
+
+namespace {
+
+constexpr int kT = 256;
+
+inline int grid_for(int64_t work_items) {
+  const int sm = std::max(1, device_info().sm_count);
+  const int64_t blocks = (work_items + kT - 1) / kT;
+  return (int)std::max<int64_t>(1, std::min<int64_t>(blocks, (int64_t)sm * 8));
+}
+
+// ---------------- Glorot -------------------------------------------------------------------------------
+__global__ void glorot_kernel(float *__restrict__ w, int64_t size, int64_t groups, double scale, gcnb_rng_t rng) {
+  for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < groups; g += (int64_t)gridDim.x * blockDim.x) {
+    float u[4];
+    rng_uniform4(rng, (uint32_t)g, u);
+    const int64_t j = g * 4;
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+      if (j + k < size) w[j + k] = (float)((u[k] - 0.5) * scale);  // double arithmetic as src/variable.cu:53-59
+  }
+}
+
+// ---------------- Dropout ------------------------------------------------------------------------------
+// MODE bit0: write mask, bit1: read external mask.  FUSE_RELU: ReLU first (mask bit0 = relu keep, bit1 = dropout keep).
+template <bool FUSE_RELU>
+__global__ void dropout_fwd_kernel(float *__restrict__ x, uint8_t *__restrict__ mask, const uint8_t *__restrict__ ext,
+                                   int64_t size, int64_t groups, float p, float scale, int training, gcnb_rng_t rng) {
+  const bool vec_ok = ((uintptr_t)x % 16 == 0);
+  for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < groups; g += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t j = g * 4;
+    const bool full = (j + 4 <= size);
+    float v[4];
+    if (full && vec_ok) {
+      const float4 t = *reinterpret_cast<const float4 *>(x + j);
+      v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; k++) v[k] = (j + k < size) ? x[j + k] : 0.f;
+    }
+    bool keep[4] = {true, true, true, true};
+    if (training) {
+      if (ext) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) keep[k] = (j + k < size) ? (ext[j + k] != 0) : false;
+      } else {
+        float u[4];
+        rng_uniform4(rng, (uint32_t)g, u);
+#pragma unroll
+        for (int k = 0; k < 4; k++) keep[k] = u[k] >= p;
+      }
+    }
+    uint8_t m[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      if (FUSE_RELU) {
+        const bool rk = v[k] > 0.f;
+        if (!rk) v[k] = 0.f;
+        if (training) v[k] *= keep[k] ? scale : 0.f;
+        m[k] = (uint8_t)((rk ? 1 : 0) | (keep[k] ? 2 : 0));
+      } else {
+        v[k] *= keep[k] ? scale : 0.f;
+        m[k] = keep[k] ? 1 : 0;
+      }
+    }
+    if (full && vec_ok) {
+      *reinterpret_cast<float4 *>(x + j) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+        if (j + k < size) x[j + k] = v[k];
+    }
+    if (mask && training) {
+      if (full && ((uintptr_t)mask % 4 == 0)) {
+        *reinterpret_cast<uchar4 *>(mask + j) = make_uchar4(m[0], m[1], m[2], m[3]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+          if (j + k < size) mask[j + k] = m[k];
+      }
+    }
+  }
+}
+
+// g *= keep ? scale : 0    (FUSED: keep = both bits set, scale only from dropout)
+template <bool FUSED>
+__global__ void mask_bwd_kernel(float *__restrict__ gr, const uint8_t *__restrict__ mask, int64_t size, float scale,
+                                int relu_only) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < size; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint8_t m = mask[i];
+    float v = gr[i];
+    if (FUSED) {
+      v *= (m & 2) ? scale : 0.f;  // Dropout::backward first (reverse module order) ...
+      if (!(m & 1)) v = 0.f;       // ... then ReLU::backward
+    } else if (relu_only) {
+      if (!m) v = 0.f;
+    } else {
+      v *= m ? scale : 0.f;
+    }
+    gr[i] = v;
+  }
+}
+
+__global__ void relu_fwd_kernel(float *__restrict__ x, uint8_t *__restrict__ mask, int64_t size, int training) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < size; i += (int64_t)gridDim.x * blockDim.x) {
+    const bool keep = x[i] > 0.f;
+    if (training) mask[i] = keep;
+    if (!keep) x[i] = 0.f;
+  }
+}
+
+__global__ void set_truth_kernel(int32_t *__restrict__ truth, const uint32_t *__restrict__ split,
+                                 const int32_t *__restrict__ label, int64_t n, uint32_t cur) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    truth[i] = split[i] == cur ? label[i] : -1;
+}
+
+// ---------------- Adam (multi-tensor) ---------------------------------------------------------------------
+struct AdamArgs {
+  gcnb_adam_tensors_t t;
+  int64_t prefix[GCNB_MAX_TENSORS + 1];
+};
+__global__ void adam_kernel(AdamArgs a, float weight_decay, float beta1, float beta2, float eps, float step_size) {
+  const int64_t total = a.prefix[a.t.n_tensors];
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int k = 0;
+    while (i >= a.prefix[k + 1]) k++;
+    const int64_t j = i - a.prefix[k];
+    float *w = a.t.w[k], *m = a.t.m[k], *v = a.t.v[k];
+    float grad = a.t.g[k][j];
+    const float wj = w[j];
+    if (a.t.decay[k]) grad += weight_decay * wj;
+    // (1.0 - beta) is a double expression in the reference (src/optim.cu:51-52): keep the mixed precision
+    const float mj = (float)(beta1 * m[j] + (1.0 - beta1) * grad);
+    const float vj = (float)(beta2 * v[j] + (1.0 - beta2) * grad * grad);
+    m[j] = mj;
+    v[j] = vj;
+    w[j] = wj - step_size * mj / (sqrtf(vj) + eps);
+  }
+}
+
+// ---------------- sum of squares: block partials, last block reduces them in ascending order ----------------
+__global__ void sumsq_kernel(const float *__restrict__ w, int64_t n, float *__restrict__ out, float *__restrict__ partial,
+                             unsigned int *__restrict__ ticket) {
+  __shared__ float sm[kT / 32];
+  __shared__ bool last;
+  float s = 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float x = w[i];
+    s = fmaf(x, x, s);
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float b = 0.f;
+    for (int i = 0; i < kT / 32; i++) b += sm[i];
+    partial[blockIdx.x] = b;
+    __threadfence();
+    const unsigned t = atomicAdd(ticket, 1u);
+    last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    float tot = 0.f;
+    for (unsigned i = 0; i < gridDim.x; i++) tot += ((volatile float *)partial)[i];
+    out[0] = tot;
+    *ticket = 0;  // self-reset for the next launch
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int gcnb_glorot_f32(float *d_w, int64_t size, uint32_t rows, uint32_t cols, const gcnb_rng_t *rng, gcnb_stream_t s) {
+  if (!d_w || !rng || size < 0 || rows + cols == 0) return GCNB_E_BADARG;
+  if (size == 0) return 0;
+  const double range = sqrtf(6.0f / (rows + cols));  // src/variable.cu:75-76
+  const double scale = range * 2;
+  const int64_t groups = (size + 3) / 4;
+  glorot_kernel<<<grid_for(groups), kT, 0, as_stream(s)>>>(d_w, size, groups, scale, *rng);
+  GCNB_LAUNCH_CHECK();
+  return 0;
+}
+
+static inline float dropout_scale(float p) { return (float)(1.0 / (1.0 - p)); }  // src/module.cu:69
+
+int gcnb_dropout_fwd_f32(float *d_x, uint8_t *d_mask, const uint8_t *d_ext_mask, int64_t size, float p,
+                         const gcnb_rng_t *rng, gcnb_stream_t s) {
+  if (!d_x || size < 0 || (!rng && !d_ext_mask)) return GCNB_E_BADARG;
+  if (size == 0) return 0;
+  const int64_t groups = (size + 3) / 4;
+  gcnb_rng_t r = rng ? *rng : gcnb_rng_t{};
+  dropout_fwd_kernel<false><<<grid_for(groups), kT, 0, as_stream(s)>>>(d_x, d_mask, d_ext_mask, size, groups, p,
+                                                                        dropout_scale(p), 1, r);
+  GCNB_LAUNCH_CHECK();
+  return 0;
+}
+
+int gcnb_dropout_bwd_f32(float *d_g, const uint8_t *d_mask, int64_t size, float p, gcnb_stream_t s) {
+  if (!d_g || !d_mask || size < 0) return GCNB_E_BADARG;
+  if (size == 0) return 0;
+  mask_bwd_kernel<false><<<grid_for(size), kT, 0, as_stream(s)>>>(d_g, d_mask, size, dropout_scale(p), 0);
+  GCNB_LAUNCH_CHECK();
+  return 0;
+}
+
+int gcnb_relu_fwd_f32(float *d_x, uint8_t *d_mask, int64_t size, int training, gcnb_stream_t s) {
+  if (!d_x || size < 0 || (training && !d_mask)) return GCNB_E_BADARG;
+  if (size == 0) return 0;
+  relu_fwd_kernel<<<grid_for(size), kT, 0, as_stream(s)>>>(d_x, d_mask, size, training);
+  GCNB_LAUNCH_CHECK();
+  return 0;
+}
+
+int gcnb_relu_bwd_f32(float *d_g, const uint8_t *d_mask, int64_t size, gcnb_stream_t s) {
+  if (!d_g || !d_mask || size < 0) return GCNB_E_BADARG;
+  if (size == 0) return 0;
+  mask_bwd_kernel<false><<<grid_for(size), kT, 0, as_stream(s)>>>(d_g, d_mask, size, 1.f, 1);
+  GCNB_LAUNCH_CHECK();
+  return 0;
+}
+
+int gcnb_relu_dropout_fwd_f32(float *d_x, uint8_t *d_mask, const uint8_t *d_ext_mask, int64_t size, float p,
+                              int training, const gcnb_rng_t *rng, gcnb_stream_t s) {
+  if (!d_x || size < 0 || (training && !d_mask) || (training && !rng && !d_ext_mask)) return GCNB_E_BADARG;
+  if (size == 0) return 0;
+  const int64_t groups = (size + 3) / 4;
+  gcnb_rng_t r = rng ? *rng : gcnb_rng_t{};
+  dropout_fwd_kernel<true><<<grid_for(groups), kT, 0, as_stream(s)>>>(d_x, d_mask, d_ext_mask, size, groups, p,
+                                                                       dropout_scale(p), training, r);
+  GCNB_LAUNCH_CHECK();
+  return 0;
+}
+
+int gcnb_relu_dropout_bwd_f32(float *d_g, const uint8_t *d_mask, int64_t size, float p, gcnb_stream_t s) {
+  if (!d_g || !d_mask || size < 0) return GCNB_E_BADARG;
+  if (size == 0) return 0;
+  mask_bwd_kernel<true><<<grid_for(size), kT, 0, as_stream(s)>>>(d_g, d_mask, size, dropout_scale(p), 0);
+  GCNB_LAUNCH_CHECK();
+  return 0;
+}
+
+int gcnb_set_truth(int32_t *d_truth, const uint32_t *d_split, const int32_t *d_label, int64_t n, uint32_t cur,
+                   gcnb_stream_t s) {
+  if (!d_truth || !d_split || !d_label || n < 0) return GCNB_E_BADARG;
+  if (n == 0) return 0;
+  set_truth_kernel<<<grid_for(n), kT, 0, as_stream(s)>>>(d_truth, d_split, d_label, n, cur);
+  GCNB_LAUNCH_CHECK();
+  return 0;
+}
+
+int gcnb_adam_step_f32(const gcnb_adam_tensors_t *t, float weight_decay, float beta1, float beta2, float eps,
+                       float step_size, gcnb_stream_t s) {
+  if (!t || t->n_tensors < 0 || t->n_tensors > GCNB_MAX_TENSORS) return GCNB_E_BADARG;
+  if (t->n_tensors == 0) return 0;
+  AdamArgs a;
+  a.t = *t;
+  a.prefix[0] = 0;
+  for (int k = 0; k < t->n_tensors; k++) {
+    if (!t->w[k] || !t->g[k] || !t->m[k] || !t->v[k] || t->size[k] < 0) return GCNB_E_BADARG;
+    a.prefix[k + 1] = a.prefix[k] + t->size[k];
+  }
+  for (int k = t->n_tensors; k < GCNB_MAX_TENSORS; k++) a.prefix[k + 1] = a.prefix[t->n_tensors];
+  if (a.prefix[t->n_tensors] == 0) return 0;
+  adam_kernel<<<grid_for(a.prefix[t->n_tensors]), kT, 0, as_stream(s)>>>(a, weight_decay, beta1, beta2, eps, step_size);
+  GCNB_LAUNCH_CHECK();
+  return 0;
+}
+
+static int sumsq_blocks(int64_t n) {
+  return (int)std::max<int64_t>(1, std::min<int64_t>((n + kT * 4 - 1) / (kT * 4), 1024));
+}
+int64_t gcnb_sumsq_workspace(int64_t n) { return (int64_t)(sumsq_blocks(n) + 1) * 4 + 16; }
+
+int gcnb_sumsq_f32(const float *d_w, int64_t n, float *d_out, void *d_ws, gcnb_stream_t s) {
+  if (!d_w || !d_out || !d_ws || n < 0) return GCNB_E_BADARG;
+  // ws layout: [ticket (zeroed once by the caller via cudaMemset; self-resetting afterwards)] [partials...]
+  unsigned int *ticket = (unsigned int *)d_ws;
+  float *partial = (float *)d_ws + 4;
+  sumsq_kernel<<<sumsq_blocks(n), kT, 0, as_stream(s)>>>(d_w, n, d_out, partial, ticket);
+  GCNB_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,502 @@
+// spmm.cu -- CSR x dense product for sm_100a: GraphSum (normalised adjacency x activations, forward and
+// backward) and SparseMatmul forward (svmlight features x W0), plus the transposed (CSC) view used by
+// SparseMatmul backward.  Replaces graphsum_kernel / sparse_matmul_kernel_forward / _backward of the reference
+// (src/module.cu:108-186), which run one thread per OUTPUT ELEMENT with no load balancing and fp32 atomics.
+//
+// Design (B200): HBM streams (indices, values) are read exactly once with L1::no_allocate; the gathered
+// neighbour rows go through L1/L2.  Work unit = row segment of <= seg_nnz entries handled by one warp:
+// the 32 lanes are LPR lanes across the feature dimension (VEC floats each, float4 when dim % 4 == 0) times
+// G = 32/LPR neighbours in flight; a 32-entry chunk of indices/values is loaded coalesced, one per lane, and
+// broadcast with shuffles.  Segments are dealt to per-SM queues holding CONTIGUOUS rows with equal nnz, so an
+// SM's gathers concentrate on one neighbourhood (L1 reuse on community-ordered graphs) and degree skew is
+// absorbed by segment granularity; idle SMs steal from the other queues.  Rows longer than one segment are
+// combined from per-segment partials in ascending order by a second tiny kernel: no floating-point atomics.
+#include <algorithm>
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+
+#include "common.cuh"
+
+namespace gcnb {
+
+const DeviceInfo &device_info() {
+  static DeviceInfo info = [] {
+    DeviceInfo d;
+    int dev = 0;
+    cudaDeviceProp p;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&p, dev) == cudaSuccess) {
+      d.sm_count = p.multiProcessorCount;
+      d.cc_major = p.major;
+      d.ok = 1;
+    }
+    return d;
+  }();
+  return info;
+}
+
+}  // namespace gcnb
+
+using namespace gcnb;
+
+struct gcnb_spmm_plan {
+  const uint32_t *d_indptr = nullptr;
+  const uint32_t *d_indices = nullptr;
+  int64_t n_rows = 0, n_cols = 0, nnz = 0;
+  int seg_nnz = 0;
+  int64_t n_seg = 0, n_split_rows = 0, n_slots = 0;
+  int n_queues = 0;
+  uint4 *d_segs = nullptr;         // (row, begin, end, slot or 0xffffffff)
+  uint32_t *d_queue_begin = nullptr;  // n_queues + 1
+  uint32_t *d_counters = nullptr;     // n_queues (+1 done counter)
+  uint32_t *d_split_row = nullptr;    // n_split_rows
+  uint32_t *d_split_slot = nullptr;   // n_split_rows + 1
+  float *d_scratch = nullptr;
+  int64_t scratch_dim = 0;
+  int64_t max_deg = 0;
+};
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr uint32_t kNoSlot = 0xffffffffu;
+
+template <int VEC>
+struct Acc {
+  float v[VEC];
+};
+
+template <int VEC>
+__device__ __forceinline__ void gather_fma(Acc<VEC> &acc, const float *__restrict__ p, float a) {
+  if constexpr (VEC == 4) {
+    const float4 x = __ldg(reinterpret_cast<const float4 *>(p));
+    acc.v[0] = fmaf(a, x.x, acc.v[0]);
+    acc.v[1] = fmaf(a, x.y, acc.v[1]);
+    acc.v[2] = fmaf(a, x.z, acc.v[2]);
+    acc.v[3] = fmaf(a, x.w, acc.v[3]);
+  } else {
+    acc.v[0] = fmaf(a, __ldg(p), acc.v[0]);
+  }
+}
+
+// One warp per claimed segment.  KT = column tiles held per lane (dim <= VEC*LPR*KT handled in one pass).
+template <int VEC, int LPR, int KT>
+struct SegArgs {
+  const uint4 *__restrict__ segs;
+  const uint32_t *__restrict__ indices;
+  const float *__restrict__ values;
+  const uint32_t *__restrict__ perm;
+  const float *__restrict__ B;
+  float *__restrict__ C;
+  float *__restrict__ scratch;
+  int dim;
+};
+
+template <int VEC, int LPR, int KT>
+__device__ __forceinline__ void run_segment(const SegArgs<VEC, LPR, KT> &A, const uint4 sg, const int lane) {
+  constexpr int G = 32 / LPR;
+  constexpr int W = VEC * LPR;
+  const int g = lane / LPR, l = lane % LPR;
+  const int dim = A.dim;
+  const uint32_t row = sg.x, beg = sg.y, end = sg.z, slot = sg.w;
+
+  Acc<VEC> acc[KT];
+#pragma unroll
+  for (int t = 0; t < KT; t++)
+#pragma unroll
+    for (int i = 0; i < VEC; i++) acc[t].v[i] = 0.f;
+
+  // software-pipelined chunk loads: indices/values of the next 32 entries are in flight while the current
+  // chunk's rows are gathered
+  uint32_t idx_n = 0;
+  float val_n = 0.f;
+  {
+    const uint32_t e = beg + lane;
+    if (e < end) {
+      idx_n = ld_stream_u32(A.indices + e);
+      val_n = A.perm ? __ldg(A.values + __ldg(A.perm + e)) : ld_stream_f32(A.values + e);
+    }
+  }
+  for (uint32_t base = beg; base < end; base += 32) {
+    const uint32_t idx = idx_n;
+    const float val = val_n;
+    {
+      const uint32_t e = base + 32 + lane;
+      idx_n = 0;
+      val_n = 0.f;
+      if (e < end) {
+        idx_n = ld_stream_u32(A.indices + e);
+        val_n = A.perm ? __ldg(A.values + __ldg(A.perm + e)) : ld_stream_f32(A.values + e);
+      }
+    }
+    const int cnt = min(32u, end - base);
+#pragma unroll
+    for (int k = 0; k < 32; k += G) {
+      if (k >= cnt) break;  // warp-uniform
+      const int j = k + g;
+      const uint32_t c = __shfl_sync(0xffffffffu, idx, j);
+      const float a = __shfl_sync(0xffffffffu, val, j);
+      if (j < cnt) {
+        const float *brow = A.B + (size_t)c * dim + l * VEC;
+#pragma unroll
+        for (int t = 0; t < KT; t++)
+          if (t * W + l * VEC < dim) gather_fma<VEC>(acc[t], brow + t * W, a);
+      }
+    }
+  }
+  // fixed-order tree over the G neighbour groups
+#pragma unroll
+  for (int t = 0; t < KT; t++)
+#pragma unroll
+    for (int i = 0; i < VEC; i++)
+#pragma unroll
+      for (int o = 16; o >= LPR; o >>= 1) acc[t].v[i] += __shfl_xor_sync(0xffffffffu, acc[t].v[i], o);
+  if (g == 0) {
+    float *dst = (slot == kNoSlot) ? A.C + (size_t)row * dim : A.scratch + (size_t)slot * dim;
+#pragma unroll
+    for (int t = 0; t < KT; t++) {
+      const int col = t * W + l * VEC;
+      if (col < dim) {
+        if constexpr (VEC == 4) {
+          *reinterpret_cast<float4 *>(dst + col) = make_float4(acc[t].v[0], acc[t].v[1], acc[t].v[2], acc[t].v[3]);
+        } else {
+          dst[col] = acc[t].v[0];
+        }
+      }
+    }
+  }
+}
+
+template <int VEC, int LPR, int KT>
+__device__ __forceinline__ void drain_queue(const SegArgs<VEC, LPR, KT> &A, const uint32_t *__restrict__ queue_begin,
+                                            uint32_t *__restrict__ counters, int q, int lane) {
+  const uint32_t qb = __ldg(queue_begin + q), qn = __ldg(queue_begin + q + 1) - qb;
+  for (;;) {
+    uint32_t ticket = 0;
+    if (lane == 0) ticket = atomicAdd(counters + q, 1u);
+    ticket = __shfl_sync(0xffffffffu, ticket, 0);
+    if (ticket >= qn) break;
+    run_segment<VEC, LPR, KT>(A, __ldg(A.segs + qb + ticket), lane);
+  }
+}
+
+template <int VEC, int LPR, int KT>
+__global__ void __launch_bounds__(kThreads)
+spmm_seg_kernel(const uint4 *__restrict__ segs, const uint32_t *__restrict__ queue_begin,
+                uint32_t *__restrict__ counters, int n_queues, const uint32_t *__restrict__ indices,
+                const float *__restrict__ values, const uint32_t *__restrict__ perm, const float *__restrict__ B,
+                float *__restrict__ C, float *__restrict__ scratch, int dim) {
+  const SegArgs<VEC, LPR, KT> A{segs, indices, values, perm, B, C, scratch, dim};
+  const int lane = threadIdx.x & 31;
+  uint32_t smid;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+  const int q0 = (int)(smid % (uint32_t)n_queues);
+  // 1) this SM's own queue (contiguous rows => L1 reuse of gathered neighbour rows)
+  drain_queue<VEC, LPR, KT>(A, queue_begin, counters, q0, lane);
+  // 2) steal: probe 32 queues at a time, drain the ones that still hold segments
+  for (int base = 1; base < n_queues; base += 32) {
+    const int off = base + lane;
+    bool has = false;
+    int q = 0;
+    if (off < n_queues) {
+      q = (q0 + off) % n_queues;
+      const uint32_t taken = *((volatile uint32_t *)(counters + q));
+      has = taken < __ldg(queue_begin + q + 1) - __ldg(queue_begin + q);
+    }
+    uint32_t mask = __ballot_sync(0xffffffffu, has);
+    while (mask) {
+      const int src = __ffs(mask) - 1;
+      mask &= mask - 1;
+      drain_queue<VEC, LPR, KT>(A, queue_begin, counters, __shfl_sync(0xffffffffu, q, src), lane);
+    }
+  }
+}
+
+// rows cut into several segments: out[row] = partial[s0] + partial[s0+1] + ... in ascending order
+__global__ void spmm_combine_kernel(const uint32_t *__restrict__ split_row, const uint32_t *__restrict__ split_slot,
+                                    const float *__restrict__ scratch, float *__restrict__ C, int64_t n_split,
+                                    int dim) {
+  const int64_t total = n_split * dim;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / dim;
+    const int c = (int)(i - r * dim);
+    const uint32_t s0 = __ldg(split_slot + r), s1 = __ldg(split_slot + r + 1);
+    float sum = 0.f;
+    for (uint32_t s = s0; s < s1; s++) sum += __ldg(scratch + (size_t)s * dim + c);
+    C[(size_t)__ldg(split_row + r) * dim + c] = sum;
+  }
+}
+
+using KernelFn = void (*)(const uint4 *, const uint32_t *, uint32_t *, int, const uint32_t *, const float *,
+                          const uint32_t *, const float *, float *, float *, int);
+
+template <int VEC, int LPR, int KT>
+KernelFn kfn() {
+  return spmm_seg_kernel<VEC, LPR, KT>;
+}
+
+template <int VEC>
+KernelFn pick_kernel(int dim) {
+  const int chunks = (dim + VEC - 1) / VEC;  // lanes needed across the feature dimension
+  if (chunks <= 1) return kfn<VEC, 1, 1>();
+  if (chunks <= 2) return kfn<VEC, 2, 1>();
+  if (chunks <= 4) return kfn<VEC, 4, 1>();
+  if (chunks <= 8) return kfn<VEC, 8, 1>();
+  if (chunks <= 16) return kfn<VEC, 16, 1>();
+  if (chunks <= 32) return kfn<VEC, 32, 1>();
+  if (chunks <= 64) return kfn<VEC, 32, 2>();
+  if (chunks <= 128) return kfn<VEC, 32, 4>();
+  if (chunks <= 256) return kfn<VEC, 32, 8>();
+  return nullptr;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gcnb_spmm_plan_create(const uint32_t *d_indptr, const uint32_t *d_indices, int64_t n_rows, int64_t n_cols,
+                          int seg_nnz, gcnb_stream_t stream_, gcnb_spmm_plan **out) {
+  if (!d_indptr || !out || n_rows < 0) return GCNB_E_BADARG;
+  const DeviceInfo &di = device_info();
+  if (!di.ok) return (int)cudaErrorNoDevice;
+  cudaStream_t stream = as_stream(stream_);
+  if (seg_nnz <= 0) seg_nnz = 512;
+  std::vector<uint32_t> indptr((size_t)n_rows + 1);
+  GCNB_CHECK(cudaMemcpyAsync(indptr.data(), d_indptr, indptr.size() * 4, cudaMemcpyDeviceToHost, stream));
+  GCNB_CHECK(cudaStreamSynchronize(stream));
+
+  auto *p = new gcnb_spmm_plan();
+  p->d_indptr = d_indptr;
+  p->d_indices = d_indices;
+  p->n_rows = n_rows;
+  p->n_cols = n_cols;
+  p->nnz = n_rows ? indptr[n_rows] : 0;
+  p->seg_nnz = seg_nnz;
+
+  std::vector<uint4> segs;
+  segs.reserve((size_t)n_rows + (size_t)(p->nnz / seg_nnz) + 1);
+  std::vector<uint32_t> split_row, split_slot;
+  uint32_t slots = 0;
+  for (int64_t r = 0; r < n_rows; r++) {
+    const uint32_t b = indptr[r], e = indptr[r + 1];
+    const uint32_t deg = e - b;
+    p->max_deg = std::max<int64_t>(p->max_deg, deg);
+    if (deg <= (uint32_t)seg_nnz) {
+      segs.push_back(make_uint4((uint32_t)r, b, e, kNoSlot));
+    } else {
+      // equal pieces (not seg_nnz + remainder) so that the last piece is not a straggler
+      const uint32_t pieces = (deg + seg_nnz - 1) / seg_nnz;
+      split_row.push_back((uint32_t)r);
+      split_slot.push_back(slots);
+      for (uint32_t k = 0; k < pieces; k++) {
+        const uint32_t sb = b + (uint32_t)((uint64_t)deg * k / pieces);
+        const uint32_t se = b + (uint32_t)((uint64_t)deg * (k + 1) / pieces);
+        segs.push_back(make_uint4((uint32_t)r, sb, se, slots++));
+      }
+    }
+  }
+  split_slot.push_back(slots);
+  p->n_seg = (int64_t)segs.size();
+  p->n_split_rows = (int64_t)split_row.size();
+  p->n_slots = slots;
+
+  // per-SM queues: contiguous segments, equal cost (nnz + fixed per-segment overhead)
+  p->n_queues = std::max(1, di.sm_count);
+  std::vector<uint32_t> qbeg((size_t)p->n_queues + 1, 0);
+  {
+    const double seg_overhead = 24.0;
+    double total = 0;
+    for (auto &s : segs) total += (s.z - s.y) + seg_overhead;
+    double acc = 0;
+    int q = 1;
+    for (size_t i = 0; i < segs.size() && q < p->n_queues; i++) {
+      acc += (segs[i].z - segs[i].y) + seg_overhead;
+      while (q < p->n_queues && acc >= total * q / p->n_queues) qbeg[q++] = (uint32_t)(i + 1);
+    }
+    for (; q <= p->n_queues; q++) qbeg[q] = (uint32_t)segs.size();
+    qbeg[p->n_queues] = (uint32_t)segs.size();
+  }
+
+  auto upload = [&](void **dst, const void *src, size_t bytes) -> int {
+    if (bytes == 0) bytes = 4;
+    GCNB_CHECK(cudaMalloc(dst, bytes));
+    if (src) GCNB_CHECK(cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, stream));
+    return 0;
+  };
+  int rc = 0;
+  if (!rc) rc = upload((void **)&p->d_segs, segs.empty() ? nullptr : segs.data(), segs.size() * sizeof(uint4));
+  if (!rc) rc = upload((void **)&p->d_queue_begin, qbeg.data(), qbeg.size() * 4);
+  if (!rc) rc = upload((void **)&p->d_counters, nullptr, ((size_t)p->n_queues + 1) * 4);
+  if (!rc) rc = upload((void **)&p->d_split_row, split_row.empty() ? nullptr : split_row.data(), split_row.size() * 4);
+  if (!rc) rc = upload((void **)&p->d_split_slot, split_slot.data(), split_slot.size() * 4);
+  if (!rc) rc = (int)cudaStreamSynchronize(stream);
+  if (rc) {
+    gcnb_spmm_plan_destroy(p);
+    return rc;
+  }
+  *out = p;
+  return 0;
+}
+
+int gcnb_spmm_plan_destroy(gcnb_spmm_plan *p) {
+  if (!p) return 0;
+  cudaFree(p->d_segs);
+  cudaFree(p->d_queue_begin);
+  cudaFree(p->d_counters);
+  cudaFree(p->d_split_row);
+  cudaFree(p->d_split_slot);
+  cudaFree(p->d_scratch);
+  delete p;
+  return 0;
+}
+
+int gcnb_spmm_plan_info(const gcnb_spmm_plan *p, int64_t out[8]) {
+  if (!p || !out) return GCNB_E_BADARG;
+  out[0] = p->n_rows; out[1] = p->nnz; out[2] = p->n_seg; out[3] = p->n_split_rows;
+  out[4] = p->n_slots; out[5] = p->n_queues; out[6] = p->seg_nnz; out[7] = p->max_deg;
+  return 0;
+}
+
+int gcnb_spmm_f32(gcnb_spmm_plan *p, const float *d_values, const uint32_t *d_perm, const float *d_B, float *d_C,
+                  int dim, gcnb_stream_t stream_) {
+  if (!p || !d_values || !d_B || !d_C || dim <= 0) return GCNB_E_BADARG;
+  if (p->n_rows == 0) return 0;
+  cudaStream_t stream = as_stream(stream_);
+  const bool vec4 = (dim % 4 == 0) && (((uintptr_t)d_B | (uintptr_t)d_C) % 16 == 0);
+  KernelFn fn = vec4 ? pick_kernel<4>(dim) : pick_kernel<1>(dim);
+  if (!fn) return GCNB_E_UNSUPPORTED;
+  if (p->n_slots > 0 && p->scratch_dim < dim) {
+    // grows once per new (larger) feature width; steady-state launches never allocate
+    GCNB_CHECK(cudaStreamSynchronize(stream));
+    cudaFree(p->d_scratch);
+    p->d_scratch = nullptr;
+    GCNB_CHECK(cudaMalloc((void **)&p->d_scratch, (size_t)p->n_slots * dim * sizeof(float)));
+    p->scratch_dim = dim;
+  }
+  if (p->n_slots > 0 && (uintptr_t)p->d_scratch % 16 != 0) return GCNB_E_UNSUPPORTED;
+  int blocks_per_sm = 0;
+  {
+    static std::mutex mu;
+    static std::unordered_map<const void *, int> cache;  // occupancy query costs microseconds: once per kernel
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find((const void *)fn);
+    if (it == cache.end()) {
+      GCNB_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, fn, kThreads, 0));
+      if (blocks_per_sm < 1) blocks_per_sm = 1;
+      cache[(const void *)fn] = blocks_per_sm;
+    } else {
+      blocks_per_sm = it->second;
+    }
+  }
+  const int64_t warps_needed = p->n_seg;
+  int64_t grid = (int64_t)p->n_queues * blocks_per_sm;
+  const int64_t min_grid = (warps_needed + (kThreads / 32) - 1) / (kThreads / 32);
+  if (grid > min_grid) grid = std::max<int64_t>(1, min_grid);
+  GCNB_CHECK(cudaMemsetAsync(p->d_counters, 0, ((size_t)p->n_queues + 1) * 4, stream));
+  fn<<<(unsigned)grid, kThreads, 0, stream>>>(p->d_segs, p->d_queue_begin, p->d_counters, p->n_queues, p->d_indices,
+                                              d_values, d_perm, d_B, d_C, p->d_scratch, dim);
+  GCNB_LAUNCH_CHECK();
+  if (p->n_split_rows > 0) {
+    const int64_t total = p->n_split_rows * dim;
+    const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)p->n_queues * 8);
+    spmm_combine_kernel<<<blocks, 256, 0, stream>>>(p->d_split_row, p->d_split_slot, p->d_scratch, d_C,
+                                                    p->n_split_rows, dim);
+    GCNB_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+// ---- CSC companion -----------------------------------------------------------------------------------
+struct gcnb_csc {
+  uint32_t *d_colptr = nullptr, *d_rowidx = nullptr, *d_perm = nullptr;
+  int is_dense = 0;
+  int64_t n_rows = 0, n_cols = 0, nnz = 0;
+};
+
+int gcnb_csc_create(const uint32_t *d_indptr, const uint32_t *d_indices, int64_t n_rows, int64_t n_cols,
+                    gcnb_stream_t stream_, gcnb_csc **out) {
+  if (!d_indptr || !out) return GCNB_E_BADARG;
+  cudaStream_t stream = as_stream(stream_);
+  std::vector<uint32_t> indptr((size_t)n_rows + 1);
+  GCNB_CHECK(cudaMemcpyAsync(indptr.data(), d_indptr, indptr.size() * 4, cudaMemcpyDeviceToHost, stream));
+  GCNB_CHECK(cudaStreamSynchronize(stream));
+  const int64_t nnz = n_rows ? indptr[n_rows] : 0;
+  auto *c = new gcnb_csc();
+  c->n_rows = n_rows;
+  c->n_cols = n_cols;
+  c->nnz = nnz;
+  // dense detection needs only indptr first: every row must hold exactly n_cols entries
+  bool dense = n_cols > 0 && nnz == n_rows * n_cols;
+  for (int64_t r = 0; dense && r < n_rows; r++) dense = (indptr[r + 1] - indptr[r]) == (uint32_t)n_cols;
+  std::vector<uint32_t> indices((size_t)nnz);
+  if (nnz) {
+    GCNB_CHECK(cudaMemcpyAsync(indices.data(), d_indices, (size_t)nnz * 4, cudaMemcpyDeviceToHost, stream));
+    GCNB_CHECK(cudaStreamSynchronize(stream));
+  }
+  if (dense)
+    for (int64_t e = 0; dense && e < nnz; e++) dense = indices[e] == (uint32_t)(e % n_cols);
+  c->is_dense = dense ? 1 : 0;
+  if (!dense) {
+    // stable counting sort by column: entries of a column stay in ascending row order => fixed summation order
+    std::vector<uint32_t> colptr((size_t)n_cols + 1, 0), rowidx((size_t)nnz), perm((size_t)nnz);
+    for (int64_t e = 0; e < nnz; e++) colptr[indices[e] + 1]++;
+    for (int64_t j = 0; j < n_cols; j++) colptr[j + 1] += colptr[j];
+    std::vector<uint32_t> cur(colptr.begin(), colptr.end() - 1);
+    for (int64_t r = 0; r < n_rows; r++)
+      for (uint32_t e = indptr[r]; e < indptr[r + 1]; e++) {
+        const uint32_t pos = cur[indices[e]]++;
+        rowidx[pos] = (uint32_t)r;
+        perm[pos] = e;
+      }
+    GCNB_CHECK(cudaMalloc((void **)&c->d_colptr, colptr.size() * 4));
+    GCNB_CHECK(cudaMalloc((void **)&c->d_rowidx, std::max<size_t>(4, rowidx.size() * 4)));
+    GCNB_CHECK(cudaMalloc((void **)&c->d_perm, std::max<size_t>(4, perm.size() * 4)));
+    GCNB_CHECK(cudaMemcpyAsync(c->d_colptr, colptr.data(), colptr.size() * 4, cudaMemcpyHostToDevice, stream));
+    if (nnz) {
+      GCNB_CHECK(cudaMemcpyAsync(c->d_rowidx, rowidx.data(), rowidx.size() * 4, cudaMemcpyHostToDevice, stream));
+      GCNB_CHECK(cudaMemcpyAsync(c->d_perm, perm.data(), perm.size() * 4, cudaMemcpyHostToDevice, stream));
+    }
+    GCNB_CHECK(cudaStreamSynchronize(stream));
+  }
+  *out = c;
+  return 0;
+}
+
+int gcnb_csc_destroy(gcnb_csc *c) {
+  if (!c) return 0;
+  cudaFree(c->d_colptr);
+  cudaFree(c->d_rowidx);
+  cudaFree(c->d_perm);
+  delete c;
+  return 0;
+}
+
+int gcnb_csc_arrays(const gcnb_csc *c, const uint32_t **d_colptr, const uint32_t **d_rowidx, const uint32_t **d_perm,
+                    int *is_dense) {
+  if (!c) return GCNB_E_BADARG;
+  if (d_colptr) *d_colptr = c->d_colptr;
+  if (d_rowidx) *d_rowidx = c->d_rowidx;
+  if (d_perm) *d_perm = c->d_perm;
+  if (is_dense) *is_dense = c->is_dense;
+  return 0;
+}
+
+const char *gcnb_error_string(int code) {
+  if (code == 0) return "success";
+  if (code == GCNB_E_BADARG) return "gcnb: bad argument";
+  if (code == GCNB_E_UNSUPPORTED) return "gcnb: unsupported shape/alignment";
+  return cudaGetErrorString((cudaError_t)code);
+}
+int gcnb_version(void) { return 100; }
+int gcnb_device_check(int *sm_count) {
+  int n = 0;
+  GCNB_CHECK(cudaGetDeviceCount(&n));
+  if (n == 0) return (int)cudaErrorNoDevice;
+  const DeviceInfo &di = device_info();
+  if (!di.ok) return (int)cudaErrorNoDevice;
+  if (sm_count) *sm_count = di.sm_count;
+  if (di.cc_major != 10) return (int)cudaErrorInvalidDevice;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,69 @@
+"""Quick GraphSum probe on a Reddit-shape random CSR (device-generated; perf only, not parity)."""
+import json
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, ".")
+import __graft_entry__ as ge
+
+ge.load_package()
+from parallel_gcn_b200 import binding as gcnb
+
+dev = torch.device("cuda:0")
+gcnb.device_check()
+N, MEAN, BLOCKS = 232965, 492, 50
+
+
+def make(intra, seed=0, sort=True):
+    g = torch.Generator(device=dev).manual_seed(seed)
+    deg = torch.exp(torch.randn(N, device=dev, generator=g) * 1.2)
+    deg = (deg * (MEAN / deg.mean())).clamp(1, 21657)
+    deg = (deg * (MEAN / deg.mean())).clamp(1, 21657).round().long()
+    indptr = torch.zeros(N + 1, dtype=torch.int64, device=dev)
+    indptr[1:] = torch.cumsum(deg, 0)
+    nnz = int(indptr[-1])
+    rows = torch.repeat_interleave(torch.arange(N, device=dev), deg)
+    bs = (N + BLOCKS - 1) // BLOCKS
+    local = (rows // bs) * bs + torch.randint(0, bs, (nnz,), device=dev, generator=g)
+    local = local.clamp(max=N - 1)
+    glob = torch.randint(0, N, (nnz,), device=dev, generator=g)
+    pick = torch.rand(nnz, device=dev, generator=g) < intra
+    cols = torch.where(pick, local, glob)
+    if sort:
+        key = rows * N + cols
+        key, _ = torch.sort(key)
+        cols = key % N
+    vals = torch.rand(nnz, device=dev, generator=g)
+    return indptr.int(), cols.int(), vals, nnz
+
+
+def bench(plan, vals, x, out, dim, iters=20):
+    for _ in range(3):
+        plan.spmm(vals, x, out, dim)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        plan.spmm(vals, x, out, dim)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters * 1e3  # us
+
+
+res = []
+for intra in (0.8, 0.0):
+    indptr, cols, vals, nnz = make(intra)
+    for dim in (16, 41, 64):
+        x = torch.randn(N, dim, device=dev)
+        out = torch.empty(N, dim, device=dev)
+        for seg in (256, 512, 1024):
+            plan = gcnb.SpmmPlan(indptr, cols, N, seg)
+            us = bench(plan, vals, x, out, dim)
+            alg = 4 * (N + 1) + 8 * nnz + 8 * N * dim
+            r = dict(intra=intra, dim=dim, seg=seg, nnz=nnz, us=round(us, 1), alg_GBs=round(alg / us / 1e3, 1), info=plan.info())
+            print(json.dumps(r), flush=True)
+            res.append(r)
+            plan.close()
+json.dump(res, open("gpurun_out/probe_graphsum.json", "w"), indent=1)

@@ -1,0 +1,286 @@
+"""GPU parity of every C-ABI kernel against the oracle (gcn_oracle.c) on seeded inputs.
+
+Tolerances: integer / mask / index results bit-exact; fp32 results within 1e-5 relative (north_star), with an
+absolute floor of 1e-6 x max|want| where sums cancel.  All calls go through the C ABI (ctypes)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from tests.util import assert_close, random_csr, to_dev, to_np
+
+pytestmark = pytest.mark.gpu
+f32, u32, i32, u8 = np.float32, np.uint32, np.int32, np.uint8
+
+
+def _graphsum_check(O, gcnb, dev, indptr, indices, values, dim, seg_nnz=0, n_cols=None):
+    import torch
+    n = len(indptr) - 1
+    n_cols = n if n_cols is None else n_cols
+    rng = np.random.default_rng(dim * 1000 + n)
+    x = rng.standard_normal((n_cols, dim)).astype(f32)
+    want = np.empty((n, dim), f32)
+    O.lib.orc_spmm(n, dim, O._p(indptr), O._p(indices), O._p(values), O._p(x), O._p(want))
+    d_ip, d_ix, d_v, d_x = (to_dev(a, dev) for a in (indptr, indices, values, x))
+    out = torch.full((n, dim), float("nan"), device=dev)
+    plan = gcnb.SpmmPlan(d_ip, d_ix, n_cols, seg_nnz)
+    plan.spmm(d_v, d_x, out, dim)
+    torch.cuda.synchronize()
+    assert_close(to_np(out), want, what="spmm dim=%d" % dim)
+    # determinism: bit-identical on a second launch
+    out2 = torch.empty_like(out)
+    plan.spmm(d_v, d_x, out2, dim)
+    assert torch.equal(out, out2)
+    info = plan.info()
+    plan.close()
+    return info
+
+
+@pytest.mark.parametrize("name", ["cora", "citeseer"])
+@pytest.mark.parametrize("dim", [16, 7, 41, 3, 64, 600])
+def test_graphsum_datasets(O, gcnb, dev, datasets, name, dim):
+    ds = datasets[name]
+    _graphsum_check(O, gcnb, dev, ds.g_indptr, ds.g_indices, ds.graph_values(), dim)
+
+
+@pytest.mark.parametrize("dim", [16, 41, 128, 5])
+def test_graphsum_skewed_split_rows(O, gcnb, dev, dim):
+    """rows far longer than a segment (multi-segment combine), empty rows, tiny segments."""
+    rng = np.random.default_rng(7)
+    n = 3000
+    indptr, indices = random_csr(rng, n, n, 12, heavy_rows=[(5, 20000), (6, 513), (2999, 7777)], empty_rows=[0, 17, 2998])
+    values = rng.standard_normal(len(indices)).astype(f32)
+    info = _graphsum_check(O, gcnb, dev, indptr, indices, values, dim, seg_nnz=64)
+    assert info["n_split_rows"] >= 3 and info["max_deg"] == 20000
+
+
+def test_graphsum_ref_cpu_flavour(O, gcnb, dev, datasets):
+    """the ref-CPU GraphSum recomputes coef per edge (module.cpp:86-90); hoisted values give the same bits."""
+    ds = datasets["cora"]
+    n, dim = ds.num_nodes, 16
+    x = np.random.default_rng(0).standard_normal((n, dim)).astype(f32)
+    a, b = np.empty((n, dim), f32), np.empty((n, dim), f32)
+    O.lib.orc_graphsum(n, dim, O._p(ds.g_indptr), O._p(ds.g_indices), None, O._p(x), O._p(a))
+    O.lib.orc_graphsum(n, dim, O._p(ds.g_indptr), O._p(ds.g_indices), O._p(ds.graph_values()), O._p(x), O._p(b))
+    assert (a == b).all()
+
+
+@pytest.mark.parametrize("name,p", [("cora", 16), ("citeseer", 16), ("cora", 72)])
+def test_sparse_matmul_fwd_bwd(O, gcnb, dev, datasets, name, p):
+    import torch
+    ds = datasets[name]
+    n, F = ds.num_nodes, ds.input_dim
+    rng = np.random.default_rng(3)
+    w = rng.standard_normal((F, p)).astype(f32)
+    vals = (ds.f_value * rng.integers(0, 2, len(ds.f_value)) * 2).astype(f32)  # as after dropout
+    cg = rng.standard_normal((n, p)).astype(f32)
+    want_c, want_g = np.empty((n, p), f32), np.empty((F, p), f32)
+    O.lib.orc_spmm(n, p, O._p(ds.f_indptr), O._p(ds.f_indices), O._p(vals), O._p(w), O._p(want_c))
+    O.lib.orc_spmm_bwd(n, F, p, O._p(ds.f_indptr), O._p(ds.f_indices), O._p(vals), O._p(cg), O._p(want_g))
+    d_ip, d_ix, d_v, d_w, d_cg = (to_dev(a, dev) for a in (ds.f_indptr, ds.f_indices, vals, w, cg))
+    plan = gcnb.SpmmPlan(d_ip, d_ix, F)
+    c = torch.empty((n, p), device=dev)
+    plan.spmm(d_v, d_w, c, p)
+    assert_close(to_np(c), want_c, what="sparse_matmul fwd")
+    csc = gcnb.Csc(d_ip, d_ix, F)
+    assert not csc.is_dense
+    g = torch.full((F, p), float("nan"), device=dev)
+    csc.plan.spmm(d_v, d_cg, g, p, perm=csc.perm)
+    torch.cuda.synchronize()
+    assert_close(to_np(g), want_g, what="sparse_matmul bwd")
+    # CSC bit-exactness against a host transpose
+    colptr = to_np(csc.colptr, u32)
+    rowidx = to_np(csc.rowidx, u32)
+    order = np.argsort(ds.f_indices, kind="stable")
+    rows = np.repeat(np.arange(n, dtype=u32), np.diff(ds.f_indptr.astype(np.int64)))
+    assert (rowidx == rows[order]).all() and (to_np(csc.perm, u32) == order.astype(u32)).all()
+    assert (colptr == np.concatenate([[0], np.cumsum(np.bincount(ds.f_indices, minlength=F))]).astype(u32)).all()
+    csc.close(); plan.close()
+
+
+def test_csc_dense_detection(gcnb, dev):
+    n, F = 37, 12
+    indptr = (np.arange(n + 1) * F).astype(u32)
+    indices = np.tile(np.arange(F, dtype=u32), n)
+    csc = gcnb.Csc(to_dev(indptr, dev), to_dev(indices, dev), F)
+    assert csc.is_dense
+    csc.close()
+
+
+@pytest.mark.parametrize("m,n,p", [(2708, 16, 7), (3327, 16, 6), (5000, 16, 41), (1000, 72, 7), (777, 602, 16),
+                                   (513, 600, 41), (300, 130, 70), (1, 16, 41), (129, 1, 1)])
+def test_matmul_nn_nt_tn(O, gcnb, dev, m, n, p):
+    import torch
+    rng = np.random.default_rng(m + n + p)
+    a = rng.standard_normal((m, n)).astype(f32)
+    b = rng.standard_normal((n, p)).astype(f32)
+    cg = rng.standard_normal((m, p)).astype(f32)
+    want_c, want_ag, want_bg = np.empty((m, p), f32), np.empty((m, n), f32), np.empty((n, p), f32)
+    O.lib.orc_matmul(m, n, p, O._p(a), O._p(b), O._p(want_c))
+    O.lib.orc_matmul_bwd(m, n, p, O._p(a), O._p(b), O._p(cg), O._p(want_ag), O._p(want_bg))
+    d_a, d_b, d_cg = (to_dev(x, dev) for x in (a, b, cg))
+    c = torch.full((m, p), float("nan"), device=dev)
+    ag = torch.full((m, n), float("nan"), device=dev)
+    bg = torch.full((n, p), float("nan"), device=dev)
+    gcnb.matmul_nn(d_a, d_b, c, m, n, p)
+    gcnb.matmul_nt(d_cg, d_b, ag, m, n, p)
+    gcnb.matmul_tn(d_a, d_cg, bg, m, n, p)
+    torch.cuda.synchronize()
+    assert_close(to_np(c), want_c, what="matmul nn")
+    assert_close(to_np(ag), want_ag, what="matmul nt")
+    assert_close(to_np(bg), want_bg, rtol=2e-5, what="matmul tn")
+    bg2 = torch.empty_like(bg)
+    gcnb.matmul_tn(d_a, d_cg, bg2, m, n, p)
+    assert torch.equal(bg, bg2), "weight gradient must be deterministic"
+
+
+def _oracle_draws(history, size):
+    g = (size + 3) // 4
+    d = np.zeros(g, u32)
+    for s, c in history:
+        d[: min(g, (s + 3) // 4)] += c
+    return d
+
+
+@pytest.mark.parametrize("size,rows,cols,hist", [(1433 * 16, 1433, 16, []), (16 * 7, 16, 7, [(1433 * 16, 1)]),
+                                                 (10, 3, 3, [(5, 2), (100, 1)])])
+def test_glorot_bit_exact(O, gcnb, dev, size, rows, cols, hist):
+    import torch
+    seed = 19990304
+    want = np.empty(size, f32)
+    O.lib.orc_glorot_philox(size, rows, cols, seed, O._p(_oracle_draws(hist, size)), 1, O._p(want))
+    w = torch.empty(size, device=dev)
+    gcnb.glorot(w, rows, cols, gcnb.make_rng(seed, hist))
+    assert (to_np(w).view(u32) == want.view(u32)).all()
+
+
+@pytest.mark.parametrize("size,p,hist", [(49216, 0.5, [(22928, 1), (112, 1)]), (43328, 0.5, [(49216, 3), (22928, 1), (112, 1), (43328, 2)]),
+                                         (1001, 0.6, []), (7, 0.0, []), (4096, 0.1, [(10, 1)])])
+def test_dropout_philox_bit_exact(O, gcnb, dev, size, p, hist):
+    import torch
+    seed = 311288059
+    rng = np.random.default_rng(size)
+    x = rng.standard_normal(size).astype(f32)
+    mask_want = np.empty(size, u8)
+    O.lib.orc_dropout_mask_philox(size, p, seed, O._p(_oracle_draws(hist, size)), 1, O._p(mask_want))
+    want = x.copy()
+    O.lib.orc_dropout_apply(size, O._p(want), O._p(mask_want), O.lib.orc_dropout_scale(p, 1))
+    d_x = to_dev(x, dev)
+    d_m = torch.zeros(size, dtype=torch.uint8, device=dev)
+    gcnb.dropout_fwd(d_x, d_m, p, rng=gcnb.make_rng(seed, hist))
+    assert (to_np(d_m) == mask_want).all()
+    assert (to_np(d_x).view(u32) == want.view(u32)).all()
+    # no-mask variant (input Variable has no grad) and injected masks
+    d_x2 = to_dev(x, dev)
+    gcnb.dropout_fwd(d_x2, None, p, rng=gcnb.make_rng(seed, hist))
+    assert torch.equal(d_x, d_x2)
+    d_x3 = to_dev(x, dev)
+    gcnb.dropout_fwd(d_x3, None, p, ext_mask=to_dev(mask_want, dev))
+    assert torch.equal(d_x, d_x3)
+    # backward
+    g = rng.standard_normal(size).astype(f32)
+    gw = g.copy()
+    O.lib.orc_dropout_apply(size, O._p(gw), O._p(mask_want), O.lib.orc_dropout_scale(p, 1))
+    d_g = to_dev(g, dev)
+    gcnb.dropout_bwd(d_g, d_m, p)
+    assert (to_np(d_g).view(u32) == gw.view(u32)).all()
+
+
+@pytest.mark.parametrize("size", [1, 43328, 100003])
+def test_relu_and_fused_relu_dropout(O, gcnb, dev, size):
+    import torch
+    rng = np.random.default_rng(size)
+    x = rng.standard_normal(size).astype(f32)
+    x[::7] = 0.0
+    g = rng.standard_normal(size).astype(f32)
+    p, seed = 0.5, 123
+    xw, rm = x.copy(), np.zeros(size, u8)
+    O.lib.orc_relu_fwd(size, O._p(xw), O._p(rm), 1)
+    d_x, d_m = to_dev(x, dev), torch.zeros(size, dtype=torch.uint8, device=dev)
+    gcnb.relu_fwd(d_x, d_m, True)
+    assert (to_np(d_x) == xw).all() and (to_np(d_m) == rm).all()
+    gw = g.copy(); O.lib.orc_relu_bwd(size, O._p(gw), O._p(rm))
+    d_g = to_dev(g, dev); gcnb.relu_bwd(d_g, d_m)
+    assert (to_np(d_g) == gw).all()
+    # eval mode leaves the mask untouched
+    d_m2 = torch.full((size,), 9, dtype=torch.uint8, device=dev)
+    gcnb.relu_fwd(to_dev(x, dev), d_m2, False)
+    assert (to_np(d_m2) == 9).all()
+    # fused ReLU+Dropout == the two modules chained
+    dm = np.empty(size, u8)
+    O.lib.orc_dropout_mask_philox(size, p, seed, None, 1, O._p(dm))
+    O.lib.orc_dropout_apply(size, O._p(xw), O._p(dm), 2.0)
+    d_x, d_mm = to_dev(x, dev), torch.zeros(size, dtype=torch.uint8, device=dev)
+    gcnb.relu_dropout_fwd(d_x, d_mm, p, True, rng=gcnb.make_rng(seed))
+    assert (to_np(d_x).view(u32) == xw.view(u32)).all()
+    assert (to_np(d_mm) == (rm | (dm << 1))).all()
+    gw = g.copy(); O.lib.orc_dropout_apply(size, O._p(gw), O._p(dm), 2.0); O.lib.orc_relu_bwd(size, O._p(gw), O._p(rm))
+    d_g = to_dev(g, dev); gcnb.relu_dropout_bwd(d_g, d_mm, p)
+    assert (to_np(d_g).view(u32) == gw.view(u32)).all()
+    # fused eval: relu only
+    d_x = to_dev(x, dev); gcnb.relu_dropout_fwd(d_x, None, p, False)
+    xe = x.copy(); O.lib.orc_relu_fwd(size, O._p(xe), O._p(rm), 0)
+    assert (to_np(d_x) == xe).all()
+
+
+@pytest.mark.parametrize("n,C,training", [(2708, 7, 1), (3327, 6, 1), (5000, 41, 1), (5000, 41, 0), (100, 172, 1), (3, 2, 1)])
+def test_softmax_ce(O, gcnb, dev, n, C, training):
+    import torch
+    rng = np.random.default_rng(n * C)
+    logits = (rng.standard_normal((n, C)) * 3).astype(f32)
+    truth = rng.integers(-1, C, n).astype(i32)
+    truth[rng.random(n) < 0.4] = -1
+    ns = int((truth >= 0).sum()) + 5  # split count may exceed labelled rows (citeseer)
+    lw, gw = logits.copy(), np.empty((n, C), f32)
+    cnt = np.zeros(1, np.int64)
+    loss_want = O.lib.orc_cross_entropy(n, C, O._p(lw), O._p(truth), O._p(gw) if training else None, ns, training, O._p(cnt))
+    wrong_want = O.lib.orc_wrong_count(n, C, O._p(lw), O._p(truth), None)
+    d_l, d_t = to_dev(logits, dev), to_dev(truth, dev)
+    d_g = torch.full((n, C), float("nan"), device=dev) if training else None
+    res = torch.zeros(4, device=dev)
+    ws = gcnb.zeroed_workspace(gcnb.lib.gcnb_ce_workspace(n), dev)
+    for _ in range(2):  # second launch checks the self-resetting ticket
+        d_l.copy_(to_dev(logits, dev))
+        gcnb.softmax_ce(d_l, d_g, d_t, n, C, ns, training, res, ws)
+    r = to_np(res)
+    assert_close(r[0], loss_want, rtol=1e-5, what="loss sum")
+    assert int(r.view(u32)[1]) == wrong_want and int(r.view(u32)[2]) == int(cnt[0])
+    assert_close(to_np(d_l), lw, rtol=1e-6, atol=1e-6, what="shifted logits")
+    if training:
+        assert_close(to_np(d_g), gw, rtol=1e-5, atol=1e-9, what="ce grad")
+
+
+def test_adam_and_sumsq(O, gcnb, dev):
+    import torch
+    rng = np.random.default_rng(5)
+    sizes, decays = [1433 * 16, 16 * 7, 5], [True, False, True]
+    ws = [rng.standard_normal(s).astype(f32) * 0.1 for s in sizes]
+    ms = [np.zeros(s, f32) for s in sizes]
+    vs = [np.zeros(s, f32) for s in sizes]
+    d = [[to_dev(a, dev) for a in (w, m, v)] for w, m, v in zip(ws, ms, vs)]
+    for step in range(1, 4):
+        gs = [rng.standard_normal(s).astype(f32) * 0.01 for s in sizes]
+        ss = O.lib.orc_adam_step_size(0.01, 0.9, 0.999, step)
+        for w, g, m, v, dec in zip(ws, gs, ms, vs, decays):
+            O.lib.orc_adam_step(w.size, O._p(w), O._p(g), O._p(m), O._p(v), int(dec), 5e-4, 0.9, 0.999, 1e-8, ss)
+        gcnb.adam_step([(dw, to_dev(g, dev), dm, dv, dec) for (dw, dm, dv), g, dec in zip(d, gs, decays)], 5e-4, 0.9, 0.999, 1e-8, ss)
+    for (dw, dm, dv), w, m, v in zip(d, ws, ms, vs):
+        assert_close(to_np(dw), w, rtol=1e-6, what="adam w")
+        assert_close(to_np(dm), m, rtol=1e-6, what="adam m")
+        assert_close(to_np(dv), v, rtol=1e-6, what="adam v")
+    out = torch.zeros(1, device=dev)
+    wsb = gcnb.zeroed_workspace(gcnb.lib.gcnb_sumsq_workspace(sizes[0]), dev)
+    for _ in range(2):
+        gcnb.sumsq(d[0][0], out, wsb)
+    assert_close(to_np(out)[0], O.lib.orc_sumsq(sizes[0], O._p(ws[0])), rtol=1e-5, what="sumsq")
+
+
+def test_set_truth(O, gcnb, dev, datasets):
+    import torch
+    ds = datasets["citeseer"]
+    for cur in (1, 2, 3):
+        want = np.empty(ds.num_nodes, i32)
+        O.lib.orc_set_truth(ds.num_nodes, O._p(ds.split), O._p(ds.label), cur, O._p(want))
+        t = torch.empty(ds.num_nodes, dtype=torch.int32, device=dev)
+        gcnb.set_truth(t, to_dev(ds.split, dev), to_dev(ds.label, dev), cur)
+        assert (to_np(t) == want).all()
