@@ -96,7 +96,7 @@ GCNB_API int gcnb_matmul_tn_f32(const float *d_A, const float *d_dC, float *d_dB
  * covered state g (src/variable.cu:5-11,44-61; src/module.cu:16-63).  The caller describes "earlier ops" by
  * up to GCNB_MAX_RNG_HIST (n_groups, count) pairs: t(g) = sum(count_i for n_groups_i > g).
  * ------------------------------------------------------------------------------------------------- */
-#define GCNB_MAX_RNG_HIST 8
+#define GCNB_MAX_RNG_HIST 16
 typedef struct {
   uint32_t seed;
   int n_hist;
@@ -111,6 +111,10 @@ GCNB_API int gcnb_glorot_f32(float *d_w, int64_t size, uint32_t rows, uint32_t c
  * If d_ext_mask != NULL the keep decisions are READ from it instead of drawn (injected masks). */
 GCNB_API int gcnb_dropout_fwd_f32(float *d_x, uint8_t *d_mask, const uint8_t *d_ext_mask, int64_t size, float p,
                                   const gcnb_rng_t *rng, gcnb_stream_t stream);
+/* Same, out of place (d_src is left intact): lets the GCN driver keep the feature values pristine instead of the
+ * reference's in-place drop + set_input restore copy every eval (src/gcn.cu:181-200). */
+GCNB_API int gcnb_dropout_fwd_oop_f32(const float *d_src, float *d_dst, uint8_t *d_mask, const uint8_t *d_ext_mask,
+                                      int64_t size, float p, const gcnb_rng_t *rng, gcnb_stream_t stream);
 /* Dropout::backward (src/module.cu:80-99): g *= mask ? scale : 0. */
 GCNB_API int gcnb_dropout_bwd_f32(float *d_g, const uint8_t *d_mask, int64_t size, float p, gcnb_stream_t stream);
 /* ReLU::forward/backward (src/module.cu:222-265); mask written only when training. */
@@ -131,7 +135,8 @@ GCNB_API int gcnb_set_truth(int32_t *d_truth, const uint32_t *d_split, const int
  * grad = softmax/num_samples, grad[truth] -= 1.0/num_samples (double), rows with truth < 0 get grad 0.
  * d_result[0] = un-normalised loss sum (float), d_result[1] = bit pattern of the uint32 wrong count,
  * d_result[2] = bit pattern of the uint32 labelled-row count.  Deterministic two-level reduction.
- * d_ws: gcnb_ce_workspace(n) bytes.
+ * d_ws: gcnb_ce_workspace(n) bytes, zero-filled ONCE by the caller (cudaMemset) before the first launch; the
+ *       kernel leaves it ready for the next launch (same rule for gcnb_sumsq_f32).
  * ------------------------------------------------------------------------------------------------- */
 GCNB_API int64_t gcnb_ce_workspace(int64_t n);
 GCNB_API int gcnb_softmax_ce_f32(float *d_logits, float *d_grad, const int32_t *d_truth, int64_t n, int num_classes,

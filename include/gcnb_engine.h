@@ -1,0 +1,96 @@
+/*
+ * gcnb_engine.h -- engine-level C ABI of libgcn_b200.so: the reference's *driver* surface (Parser, GCN ctor,
+ * GCN::run / train_epoch / eval) behind plain C, taking HOST buffers.  This is what a foreign-language caller (or
+ * bench.py's end-to-end leg) binds; include/gcnb.h is the kernel-level ABI underneath it.
+ *
+ *   Parser(GCNParams*, GCNData*, name).parse()         include/parser.h:12-19, src/parser.cpp:189-209
+ *   GCN(GCNParams const*, AdamParams const*, GCNData const*)   include/gcn.cuh:114-121, src/gcn.cu:146-177
+ *   GCN::run()                                          src/gcn.cu:347-436
+ *   GCN::train_epoch() / eval(split)  (private there)   src/gcn.cu:293-343
+ *
+ * All functions return 0 on success or a cudaError_t / GCNB_E_* code; unrecoverable CUDA failures inside the C++
+ * classes follow the reference's convention (message on stderr, exit).  Host pointers are read during the call
+ * only (the engine uploads them; pinned memory makes that upload run at full PCIe speed).
+ */
+#ifndef GCNB_ENGINE_H
+#define GCNB_ENGINE_H
+#include "gcnb.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct {
+  int64_t num_nodes, input_dim, output_dim;
+  int32_t n_layers;
+  const uint32_t *hidden_dims; /* n_layers - 1 entries */
+  const float *dropouts;       /* n_layers entries     */
+  uint32_t epochs, early_stopping;
+  float learning_rate, beta1, beta2, eps, weight_decay;
+  uint32_t seed;    /* CudaParams::SEED */
+  int32_t quiet;    /* runtime form of -DNO_OUTPUT */
+  int32_t reorder;  /* 1: allow (A*a)*W when in_dim < out_dim; 0: always the module chain's A*(a*W) */
+} gcnb_gcn_config;
+
+typedef struct {
+  const uint32_t *graph_indptr, *graph_indices; /* [num_nodes+1], [graph_nnz]; row i starts with i (self) */
+  int64_t graph_nnz;
+  const float *graph_value;                     /* [graph_nnz] or NULL => 1/sqrtf(deg*deg) computed */
+  const uint32_t *feat_indptr, *feat_indices;   /* [num_nodes+1], [feat_nnz] */
+  const float *feat_value;                      /* [feat_nnz] */
+  int64_t feat_nnz;
+  const int32_t *label;                         /* [num_nodes], -1 = unlabelled */
+  const uint32_t *split;                        /* [num_nodes], 1 train / 2 val / 3 test */
+} gcnb_gcn_data;
+
+/* ---- datasets (Parser) ---- */
+typedef struct gcnb_dataset gcnb_dataset;
+/* reads <root>/data/<name>.{graph,split,svmlight}; NULL in *out + nonzero return if a file is missing */
+GCNB_API int gcnb_dataset_parse(const char *root, const char *name, int no_feature, gcnb_dataset **out);
+/* dims: num_nodes, graph_nnz, feat_rows, feat_nnz, input_dim, output_dim, n_split, train_dim, val_dim, test_dim */
+GCNB_API int gcnb_dataset_dims(const gcnb_dataset *d, int64_t dims[10]);
+/* which: 0 graph_indptr 1 graph_indices 2 feat_indptr 3 feat_indices 4 feat_value 5 label 6 split 7 graph_value */
+GCNB_API int gcnb_dataset_copy(const gcnb_dataset *d, int which, void *dst);
+GCNB_API int gcnb_dataset_free(gcnb_dataset *d);
+
+/* ---- model (GCN) ---- */
+typedef struct gcnb_gcn gcnb_gcn;
+GCNB_API int gcnb_gcn_create(const gcnb_gcn_config *cfg, const gcnb_gcn_data *data, gcnb_gcn **out);
+GCNB_API int gcnb_gcn_create_from_dataset(const gcnb_gcn_config *cfg, const gcnb_dataset *d, gcnb_gcn **out);
+GCNB_API int gcnb_gcn_destroy(gcnb_gcn *g);
+GCNB_API int gcnb_gcn_train_epoch(gcnb_gcn *g, float out_loss_acc[2]);
+GCNB_API int gcnb_gcn_eval(gcnb_gcn *g, int split, float out_loss_acc[2]);
+/* GCN::run(): out[0] = avg_epoch_time (ms, reference's TMR_TRAIN/(epochs+1)), out[1] = total_time (s),
+ * out[2] = last_val_accuracy, out[3] = epochs actually run */
+GCNB_API int gcnb_gcn_run(gcnb_gcn *g, float out[4]);
+GCNB_API int64_t gcnb_gcn_weight_size(const gcnb_gcn *g, int layer);
+GCNB_API int gcnb_gcn_get_weight(const gcnb_gcn *g, int layer, float *host_dst);
+GCNB_API int gcnb_gcn_set_weight(gcnb_gcn *g, int layer, const float *host_src);
+GCNB_API int gcnb_gcn_get_weight_grad(const gcnb_gcn *g, int layer, float *host_dst);
+GCNB_API int gcnb_gcn_get_logits(const gcnb_gcn *g, float *host_dst); /* [num_nodes x output_dim], CE-shifted */
+/* injected keep-masks (1 byte/element) for the following training passes; site 0 = input features
+ * ([feat_nnz]), site l = hidden layer l-1 ([num_nodes x hidden_dims[l-1]]); NULL = back to Philox */
+GCNB_API int gcnb_gcn_set_mask(gcnb_gcn *g, int site, const uint8_t *host_mask);
+GCNB_API int64_t gcnb_gcn_launches_per_epoch(const gcnb_gcn *g);
+
+/* ---- synthetic workloads (BASELINE.json configs 3-5; deterministic in seed, independent of thread count) ----
+ * Symmetric simple graph with `n_blocks` contiguous planted communities: undirected edges are drawn with endpoint
+ * probability proportional to a lognormal(sigma) weight (expected-degree model, weights clipped so that no expected
+ * degree exceeds max_deg); with probability `intra` the second endpoint comes from the first one's community.
+ * Output is the parser's CSR convention (row i = [i, sorted neighbours]); arrays are malloc'ed, free with
+ * gcnb_host_free.  n_undirected_edges is met exactly. */
+GCNB_API int gcnb_synth_graph(int64_t n, int64_t n_undirected_edges, int n_blocks, double intra, double sigma,
+                              int64_t max_deg, uint64_t seed, uint32_t **indptr_out, uint32_t **indices_out,
+                              int64_t *nnz_out);
+GCNB_API void gcnb_host_free(void *p);
+/* dense feature CSR (every row holds columns 0..f-1, as svmlight-Reddit parses), values ~ N(0,1) */
+GCNB_API int gcnb_synth_dense_features(int64_t n, int f, uint64_t seed, uint32_t *indptr, uint32_t *indices,
+                                       float *values);
+/* uniform labels in [0, classes), split 1/2/3 with the given train/val fractions (rest = test) */
+GCNB_API int gcnb_synth_labels(int64_t n, int classes, double frac_train, double frac_val, uint64_t seed,
+                               int32_t *label, uint32_t *split);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GCNB_ENGINE_H */

@@ -18,7 +18,7 @@ if not os.path.exists(LIB_PATH):
 lib = C.CDLL(LIB_PATH)
 P, I64, I32, U32, F32 = C.c_void_p, C.c_int64, C.c_int, C.c_uint32, C.c_float
 
-MAX_RNG_HIST = 8
+MAX_RNG_HIST = 16
 MAX_TENSORS = 16
 
 

@@ -9,10 +9,12 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "libgcn_b200.so")
-NVCC_FLAGS = [
-    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--shared",
-    "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-Xcompiler", "-pthread",
-]
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ARCH + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread"]
+# kernels + C ABI: only the GCNB_API symbols are exported
+KERNEL_FLAGS = COMMON + ["-Xcompiler", "-fvisibility=hidden"]
+# C++ mirror of the reference API (Variable, Module..., GCN, Parser): must be linkable by user code
+HOST_FLAGS = COMMON
 
 
 def sources():
@@ -47,8 +49,8 @@ def build(force=False, verbose=False):
         deps = headers() + [src, os.path.abspath(__file__)]
         if not force and os.path.exists(obj) and all(os.path.getmtime(obj) >= os.path.getmtime(d) for d in deps):
             continue
-        cmd = [nvcc] + [f for f in NVCC_FLAGS if f != "--shared"] + ["-x", "cu", "-c", src, "-o", obj,
-                                                                      "-I", os.path.join(HERE, "host", "include")]
+        flags = HOST_FLAGS if (os.sep + "host" + os.sep) in src else KERNEL_FLAGS
+        cmd = [nvcc] + flags + ["-x", "cu", "-c", src, "-o", obj, "-I", os.path.join(HERE, "host", "include")]
         if verbose:
             cmd += ["-Xptxas", "-v"]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -59,7 +61,7 @@ def build(force=False, verbose=False):
             raise RuntimeError("nvcc failed on %s" % src)
         if verbose:
             sys.stderr.write(out)
-    subprocess.check_call([nvcc, "--shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs)
+    subprocess.check_call([nvcc, "--shared"] + ARCH + ["-o", LIB] + objs)
     return LIB
 
 

@@ -36,19 +36,22 @@ __global__ void glorot_kernel(float *__restrict__ w, int64_t size, int64_t group
 // ---------------- Dropout ------------------------------------------------------------------------------
 // MODE bit0: write mask, bit1: read external mask.  FUSE_RELU: ReLU first (mask bit0 = relu keep, bit1 = dropout keep).
 template <bool FUSE_RELU>
-__global__ void dropout_fwd_kernel(float *__restrict__ x, uint8_t *__restrict__ mask, const uint8_t *__restrict__ ext,
-                                   int64_t size, int64_t groups, float p, float scale, int training, gcnb_rng_t rng) {
-  const bool vec_ok = ((uintptr_t)x % 16 == 0);
+__global__ void dropout_fwd_kernel(const float *src, float *x, uint8_t *__restrict__ mask,
+                                   const uint8_t *__restrict__ ext, int64_t size, int64_t groups, float p, float scale,
+                                   int training, gcnb_rng_t rng) {
+  // src == x for the in-place module semantics; src != x keeps the source intact (GCN driver: features are never
+  // overwritten, so no set_input restore copy is needed)
+  const bool vec_ok = (((uintptr_t)x | (uintptr_t)src) % 16 == 0);
   for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < groups; g += (int64_t)gridDim.x * blockDim.x) {
     const int64_t j = g * 4;
     const bool full = (j + 4 <= size);
     float v[4];
     if (full && vec_ok) {
-      const float4 t = *reinterpret_cast<const float4 *>(x + j);
+      const float4 t = *reinterpret_cast<const float4 *>(src + j);
       v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
     } else {
 #pragma unroll
-      for (int k = 0; k < 4; k++) v[k] = (j + k < size) ? x[j + k] : 0.f;
+      for (int k = 0; k < 4; k++) v[k] = (j + k < size) ? src[j + k] : 0.f;
     }
     bool keep[4] = {true, true, true, true};
     if (training) {
@@ -199,16 +202,21 @@ int gcnb_glorot_f32(float *d_w, int64_t size, uint32_t rows, uint32_t cols, cons
 
 static inline float dropout_scale(float p) { return (float)(1.0 / (1.0 - p)); }  // src/module.cu:69
 
-int gcnb_dropout_fwd_f32(float *d_x, uint8_t *d_mask, const uint8_t *d_ext_mask, int64_t size, float p,
-                         const gcnb_rng_t *rng, gcnb_stream_t s) {
-  if (!d_x || size < 0 || (!rng && !d_ext_mask)) return GCNB_E_BADARG;
+int gcnb_dropout_fwd_oop_f32(const float *d_src, float *d_dst, uint8_t *d_mask, const uint8_t *d_ext_mask,
+                             int64_t size, float p, const gcnb_rng_t *rng, gcnb_stream_t s) {
+  if (!d_src || !d_dst || size < 0 || (!rng && !d_ext_mask)) return GCNB_E_BADARG;
   if (size == 0) return 0;
   const int64_t groups = (size + 3) / 4;
   gcnb_rng_t r = rng ? *rng : gcnb_rng_t{};
-  dropout_fwd_kernel<false><<<grid_for(groups), kT, 0, as_stream(s)>>>(d_x, d_mask, d_ext_mask, size, groups, p,
-                                                                        dropout_scale(p), 1, r);
+  dropout_fwd_kernel<false><<<grid_for(groups), kT, 0, as_stream(s)>>>(d_src, d_dst, d_mask, d_ext_mask, size, groups,
+                                                                        p, dropout_scale(p), 1, r);
   GCNB_LAUNCH_CHECK();
   return 0;
+}
+
+int gcnb_dropout_fwd_f32(float *d_x, uint8_t *d_mask, const uint8_t *d_ext_mask, int64_t size, float p,
+                         const gcnb_rng_t *rng, gcnb_stream_t s) {
+  return gcnb_dropout_fwd_oop_f32(d_x, d_x, d_mask, d_ext_mask, size, p, rng, s);
 }
 
 int gcnb_dropout_bwd_f32(float *d_g, const uint8_t *d_mask, int64_t size, float p, gcnb_stream_t s) {
@@ -241,7 +249,7 @@ int gcnb_relu_dropout_fwd_f32(float *d_x, uint8_t *d_mask, const uint8_t *d_ext_
   if (size == 0) return 0;
   const int64_t groups = (size + 3) / 4;
   gcnb_rng_t r = rng ? *rng : gcnb_rng_t{};
-  dropout_fwd_kernel<true><<<grid_for(groups), kT, 0, as_stream(s)>>>(d_x, d_mask, d_ext_mask, size, groups, p,
+  dropout_fwd_kernel<true><<<grid_for(groups), kT, 0, as_stream(s)>>>(d_x, d_x, d_mask, d_ext_mask, size, groups, p,
                                                                        dropout_scale(p), training, r);
   GCNB_LAUNCH_CHECK();
   return 0;

@@ -62,25 +62,39 @@ constexpr int kThreads = 256;
 constexpr uint32_t kNoSlot = 0xffffffffu;
 
 template <int VEC>
-struct Acc {
-  float v[VEC];
+struct Vec;
+template <>
+struct Vec<4> {
+  float4 v;
+  __device__ __forceinline__ void zero() { v = make_float4(0.f, 0.f, 0.f, 0.f); }
+  __device__ __forceinline__ void load(const char *p) { v = __ldg(reinterpret_cast<const float4 *>(p)); }
+  __device__ __forceinline__ void fma(float a, const Vec<4> &x) {
+    v.x = fmaf(a, x.v.x, v.x);
+    v.y = fmaf(a, x.v.y, v.y);
+    v.z = fmaf(a, x.v.z, v.z);
+    v.w = fmaf(a, x.v.w, v.w);
+  }
+  __device__ __forceinline__ void xor_add(int o) {
+    v.x += __shfl_xor_sync(0xffffffffu, v.x, o);
+    v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
+    v.z += __shfl_xor_sync(0xffffffffu, v.z, o);
+    v.w += __shfl_xor_sync(0xffffffffu, v.w, o);
+  }
+  __device__ __forceinline__ void store(float *p) const { *reinterpret_cast<float4 *>(p) = v; }
+};
+template <>
+struct Vec<1> {
+  float v;
+  __device__ __forceinline__ void zero() { v = 0.f; }
+  __device__ __forceinline__ void load(const char *p) { v = __ldg(reinterpret_cast<const float *>(p)); }
+  __device__ __forceinline__ void fma(float a, const Vec<1> &x) { v = fmaf(a, x.v, v); }
+  __device__ __forceinline__ void xor_add(int o) { v += __shfl_xor_sync(0xffffffffu, v, o); }
+  __device__ __forceinline__ void store(float *p) const { *p = v; }
 };
 
-template <int VEC>
-__device__ __forceinline__ void gather_fma(Acc<VEC> &acc, const float *__restrict__ p, float a) {
-  if constexpr (VEC == 4) {
-    const float4 x = __ldg(reinterpret_cast<const float4 *>(p));
-    acc.v[0] = fmaf(a, x.x, acc.v[0]);
-    acc.v[1] = fmaf(a, x.y, acc.v[1]);
-    acc.v[2] = fmaf(a, x.z, acc.v[2]);
-    acc.v[3] = fmaf(a, x.w, acc.v[3]);
-  } else {
-    acc.v[0] = fmaf(a, __ldg(p), acc.v[0]);
-  }
-}
-
-// One warp per claimed segment.  KT = column tiles held per lane (dim <= VEC*LPR*KT handled in one pass).
-template <int VEC, int LPR, int KT>
+// One warp per claimed segment.  KT = column tiles held per lane (dim <= VEC*LPR*KT handled in one pass);
+// EXACT: dim == VEC*LPR*KT, so no column predicate is needed.
+template <int VEC, int LPR, int KT, bool EXACT>
 struct SegArgs {
   const uint4 *__restrict__ segs;
   const uint32_t *__restrict__ indices;
@@ -92,22 +106,60 @@ struct SegArgs {
   int dim;
 };
 
-template <int VEC, int LPR, int KT>
-__device__ __forceinline__ void run_segment(const SegArgs<VEC, LPR, KT> &A, const uint4 sg, const int lane) {
+// gathers + FMAs of one 32-entry chunk held one-per-lane in (idx, val).  Loads are issued in batches of UB
+// independent gathers before any FMA consumes them (memory-level parallelism); TAIL chunks predicate the loads
+// (never multiply a foreign row by a padding zero: 0 * inf would poison the sum).
+template <int VEC, int LPR, int KT, bool EXACT, bool TAIL>
+__device__ __forceinline__ void chunk_fma(Vec<VEC> (&acc)[KT], const char *__restrict__ Bl, uint32_t row_bytes,
+                                          uint32_t idx, float val, int cnt, int g, const bool (&colok)[KT]) {
   constexpr int G = 32 / LPR;
+  constexpr int U = 32 / G;  // gather steps per chunk == LPR
+  constexpr int W = VEC * LPR;
+  constexpr int UB0 = 32 / (VEC * KT);
+  constexpr int UB = UB0 < 1 ? 1 : (UB0 > 8 ? (U < 8 ? U : 8) : (UB0 > U ? U : UB0));
+#pragma unroll
+  for (int u0 = 0; u0 < U; u0 += UB) {
+    if (TAIL && u0 * G >= cnt) break;  // warp-uniform
+    float a[UB];
+    Vec<VEC> x[UB][KT];
+#pragma unroll
+    for (int u = 0; u < UB; u++) {
+      const int j = (u0 + u) * G + g;
+      const uint32_t c = __shfl_sync(0xffffffffu, idx, j);
+      a[u] = __shfl_sync(0xffffffffu, val, j);
+      const bool ok = !TAIL || j < cnt;
+      const char *p = Bl + (uint64_t)c * row_bytes;
+#pragma unroll
+      for (int t = 0; t < KT; t++) {
+        x[u][t].zero();
+        if (ok && (EXACT || colok[t])) x[u][t].load(p + (size_t)t * W * sizeof(float));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UB; u++)
+#pragma unroll
+      for (int t = 0; t < KT; t++) acc[t].fma(a[u], x[u][t]);
+  }
+}
+
+template <int VEC, int LPR, int KT, bool EXACT>
+__device__ __forceinline__ void run_segment(const SegArgs<VEC, LPR, KT, EXACT> &A, const uint4 sg, const int lane) {
   constexpr int W = VEC * LPR;
   const int g = lane / LPR, l = lane % LPR;
   const int dim = A.dim;
   const uint32_t row = sg.x, beg = sg.y, end = sg.z, slot = sg.w;
-
-  Acc<VEC> acc[KT];
+  const char *Bl = reinterpret_cast<const char *>(A.B + l * VEC);
+  const uint32_t row_bytes = (uint32_t)dim * (uint32_t)sizeof(float);
+  bool colok[KT];
 #pragma unroll
-  for (int t = 0; t < KT; t++)
-#pragma unroll
-    for (int i = 0; i < VEC; i++) acc[t].v[i] = 0.f;
+  for (int t = 0; t < KT; t++) colok[t] = EXACT || (t * W + l * VEC < dim);
 
-  // software-pipelined chunk loads: indices/values of the next 32 entries are in flight while the current
-  // chunk's rows are gathered
+  Vec<VEC> acc[KT];
+#pragma unroll
+  for (int t = 0; t < KT; t++) acc[t].zero();
+
+  // software pipeline: indices/values of the next 32 entries are in flight while the current chunk's rows
+  // are gathered
   uint32_t idx_n = 0;
   float val_n = 0.f;
   {
@@ -117,7 +169,8 @@ __device__ __forceinline__ void run_segment(const SegArgs<VEC, LPR, KT> &A, cons
       val_n = A.perm ? __ldg(A.values + __ldg(A.perm + e)) : ld_stream_f32(A.values + e);
     }
   }
-  for (uint32_t base = beg; base < end; base += 32) {
+  uint32_t base = beg;
+  for (; base + 32 <= end; base += 32) {
     const uint32_t idx = idx_n;
     const float val = val_n;
     {
@@ -129,46 +182,25 @@ __device__ __forceinline__ void run_segment(const SegArgs<VEC, LPR, KT> &A, cons
         val_n = A.perm ? __ldg(A.values + __ldg(A.perm + e)) : ld_stream_f32(A.values + e);
       }
     }
-    const int cnt = min(32u, end - base);
-#pragma unroll
-    for (int k = 0; k < 32; k += G) {
-      if (k >= cnt) break;  // warp-uniform
-      const int j = k + g;
-      const uint32_t c = __shfl_sync(0xffffffffu, idx, j);
-      const float a = __shfl_sync(0xffffffffu, val, j);
-      if (j < cnt) {
-        const float *brow = A.B + (size_t)c * dim + l * VEC;
-#pragma unroll
-        for (int t = 0; t < KT; t++)
-          if (t * W + l * VEC < dim) gather_fma<VEC>(acc[t], brow + t * W, a);
-      }
-    }
+    chunk_fma<VEC, LPR, KT, EXACT, false>(acc, Bl, row_bytes, idx, val, 32, g, colok);
   }
+  if (base < end) chunk_fma<VEC, LPR, KT, EXACT, true>(acc, Bl, row_bytes, idx_n, val_n, (int)(end - base), g, colok);
+
   // fixed-order tree over the G neighbour groups
 #pragma unroll
   for (int t = 0; t < KT; t++)
 #pragma unroll
-    for (int i = 0; i < VEC; i++)
-#pragma unroll
-      for (int o = 16; o >= LPR; o >>= 1) acc[t].v[i] += __shfl_xor_sync(0xffffffffu, acc[t].v[i], o);
+    for (int o = 16; o >= LPR; o >>= 1) acc[t].xor_add(o);
   if (g == 0) {
     float *dst = (slot == kNoSlot) ? A.C + (size_t)row * dim : A.scratch + (size_t)slot * dim;
 #pragma unroll
-    for (int t = 0; t < KT; t++) {
-      const int col = t * W + l * VEC;
-      if (col < dim) {
-        if constexpr (VEC == 4) {
-          *reinterpret_cast<float4 *>(dst + col) = make_float4(acc[t].v[0], acc[t].v[1], acc[t].v[2], acc[t].v[3]);
-        } else {
-          dst[col] = acc[t].v[0];
-        }
-      }
-    }
+    for (int t = 0; t < KT; t++)
+      if (colok[t]) acc[t].store(dst + t * W + l * VEC);
   }
 }
 
-template <int VEC, int LPR, int KT>
-__device__ __forceinline__ void drain_queue(const SegArgs<VEC, LPR, KT> &A, const uint32_t *__restrict__ queue_begin,
+template <int VEC, int LPR, int KT, bool EXACT>
+__device__ __forceinline__ void drain_queue(const SegArgs<VEC, LPR, KT, EXACT> &A, const uint32_t *__restrict__ queue_begin,
                                             uint32_t *__restrict__ counters, int q, int lane) {
   const uint32_t qb = __ldg(queue_begin + q), qn = __ldg(queue_begin + q + 1) - qb;
   for (;;) {
@@ -176,23 +208,23 @@ __device__ __forceinline__ void drain_queue(const SegArgs<VEC, LPR, KT> &A, cons
     if (lane == 0) ticket = atomicAdd(counters + q, 1u);
     ticket = __shfl_sync(0xffffffffu, ticket, 0);
     if (ticket >= qn) break;
-    run_segment<VEC, LPR, KT>(A, __ldg(A.segs + qb + ticket), lane);
+    run_segment<VEC, LPR, KT, EXACT>(A, __ldg(A.segs + qb + ticket), lane);
   }
 }
 
-template <int VEC, int LPR, int KT>
-__global__ void __launch_bounds__(kThreads)
+template <int VEC, int LPR, int KT, bool EXACT>
+__global__ void __launch_bounds__(kThreads, 4)
 spmm_seg_kernel(const uint4 *__restrict__ segs, const uint32_t *__restrict__ queue_begin,
                 uint32_t *__restrict__ counters, int n_queues, const uint32_t *__restrict__ indices,
                 const float *__restrict__ values, const uint32_t *__restrict__ perm, const float *__restrict__ B,
                 float *__restrict__ C, float *__restrict__ scratch, int dim) {
-  const SegArgs<VEC, LPR, KT> A{segs, indices, values, perm, B, C, scratch, dim};
+  const SegArgs<VEC, LPR, KT, EXACT> A{segs, indices, values, perm, B, C, scratch, dim};
   const int lane = threadIdx.x & 31;
   uint32_t smid;
   asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
   const int q0 = (int)(smid % (uint32_t)n_queues);
   // 1) this SM's own queue (contiguous rows => L1 reuse of gathered neighbour rows)
-  drain_queue<VEC, LPR, KT>(A, queue_begin, counters, q0, lane);
+  drain_queue<VEC, LPR, KT, EXACT>(A, queue_begin, counters, q0, lane);
   // 2) steal: probe 32 queues at a time, drain the ones that still hold segments
   for (int base = 1; base < n_queues; base += 32) {
     const int off = base + lane;
@@ -207,7 +239,7 @@ spmm_seg_kernel(const uint4 *__restrict__ segs, const uint32_t *__restrict__ que
     while (mask) {
       const int src = __ffs(mask) - 1;
       mask &= mask - 1;
-      drain_queue<VEC, LPR, KT>(A, queue_begin, counters, __shfl_sync(0xffffffffu, q, src), lane);
+      drain_queue<VEC, LPR, KT, EXACT>(A, queue_begin, counters, __shfl_sync(0xffffffffu, q, src), lane);
     }
   }
 }
@@ -231,22 +263,23 @@ using KernelFn = void (*)(const uint4 *, const uint32_t *, uint32_t *, int, cons
                           const uint32_t *, const float *, float *, float *, int);
 
 template <int VEC, int LPR, int KT>
-KernelFn kfn() {
-  return spmm_seg_kernel<VEC, LPR, KT>;
+KernelFn kfn(int dim) {
+  if (dim == VEC * LPR * KT) return spmm_seg_kernel<VEC, LPR, KT, true>;
+  return spmm_seg_kernel<VEC, LPR, KT, false>;
 }
 
 template <int VEC>
 KernelFn pick_kernel(int dim) {
   const int chunks = (dim + VEC - 1) / VEC;  // lanes needed across the feature dimension
-  if (chunks <= 1) return kfn<VEC, 1, 1>();
-  if (chunks <= 2) return kfn<VEC, 2, 1>();
-  if (chunks <= 4) return kfn<VEC, 4, 1>();
-  if (chunks <= 8) return kfn<VEC, 8, 1>();
-  if (chunks <= 16) return kfn<VEC, 16, 1>();
-  if (chunks <= 32) return kfn<VEC, 32, 1>();
-  if (chunks <= 64) return kfn<VEC, 32, 2>();
-  if (chunks <= 128) return kfn<VEC, 32, 4>();
-  if (chunks <= 256) return kfn<VEC, 32, 8>();
+  if (chunks <= 1) return kfn<VEC, 1, 1>(dim);
+  if (chunks <= 2) return kfn<VEC, 2, 1>(dim);
+  if (chunks <= 4) return kfn<VEC, 4, 1>(dim);
+  if (chunks <= 8) return kfn<VEC, 8, 1>(dim);
+  if (chunks <= 16) return kfn<VEC, 16, 1>(dim);
+  if (chunks <= 32) return kfn<VEC, 32, 1>(dim);
+  if (chunks <= 64) return kfn<VEC, 32, 2>(dim);
+  if (chunks <= 128) return kfn<VEC, 32, 4>(dim);
+  if (chunks <= 256) return kfn<VEC, 32, 8>(dim);
   return nullptr;
 }
 
@@ -260,7 +293,7 @@ int gcnb_spmm_plan_create(const uint32_t *d_indptr, const uint32_t *d_indices, i
   const DeviceInfo &di = device_info();
   if (!di.ok) return (int)cudaErrorNoDevice;
   cudaStream_t stream = as_stream(stream_);
-  if (seg_nnz <= 0) seg_nnz = 512;
+  if (seg_nnz <= 0) seg_nnz = 1024;
   std::vector<uint32_t> indptr((size_t)n_rows + 1);
   GCNB_CHECK(cudaMemcpyAsync(indptr.data(), d_indptr, indptr.size() * 4, cudaMemcpyDeviceToHost, stream));
   GCNB_CHECK(cudaStreamSynchronize(stream));

@@ -1,0 +1,206 @@
+"""ctypes binding of the engine-level C ABI (include/gcnb_engine.h): Parser, GCN, synthetic workloads.
+
+Host-side only plumbing: numpy arrays in, numpy arrays / floats out.  The compute is libgcn_b200.so's CUDA path; there
+is no fallback -- creating a GCN without a usable sm_100 GPU raises GcnbError.
+"""
+import ctypes as C
+
+import numpy as np
+
+from .binding import GcnbError, check, lib
+
+P, I64, I32, U32, F32 = C.c_void_p, C.c_int64, C.c_int32, C.c_uint32, C.c_float
+
+
+class GcnConfig(C.Structure):
+    _fields_ = [("num_nodes", I64), ("input_dim", I64), ("output_dim", I64), ("n_layers", I32), ("hidden_dims", P),
+                ("dropouts", P), ("epochs", U32), ("early_stopping", U32), ("learning_rate", F32), ("beta1", F32),
+                ("beta2", F32), ("eps", F32), ("weight_decay", F32), ("seed", U32), ("quiet", I32), ("reorder", I32)]
+
+
+class GcnData(C.Structure):
+    _fields_ = [("graph_indptr", P), ("graph_indices", P), ("graph_nnz", I64), ("graph_value", P), ("feat_indptr", P),
+                ("feat_indices", P), ("feat_value", P), ("feat_nnz", I64), ("label", P), ("split", P)]
+
+
+def _sig(name, res, args):
+    fn = getattr(lib, name)
+    fn.restype = res
+    fn.argtypes = args
+
+
+_sig("gcnb_dataset_parse", I32, [C.c_char_p, C.c_char_p, I32, P])
+_sig("gcnb_dataset_dims", I32, [P, P])
+_sig("gcnb_dataset_copy", I32, [P, I32, P])
+_sig("gcnb_dataset_free", I32, [P])
+_sig("gcnb_gcn_create", I32, [P, P, P])
+_sig("gcnb_gcn_create_from_dataset", I32, [P, P, P])
+_sig("gcnb_gcn_destroy", I32, [P])
+_sig("gcnb_gcn_train_epoch", I32, [P, P])
+_sig("gcnb_gcn_eval", I32, [P, I32, P])
+_sig("gcnb_gcn_run", I32, [P, P])
+_sig("gcnb_gcn_weight_size", I64, [P, I32])
+_sig("gcnb_gcn_get_weight", I32, [P, I32, P])
+_sig("gcnb_gcn_set_weight", I32, [P, I32, P])
+_sig("gcnb_gcn_get_weight_grad", I32, [P, I32, P])
+_sig("gcnb_gcn_get_logits", I32, [P, P])
+_sig("gcnb_gcn_set_mask", I32, [P, I32, P])
+_sig("gcnb_gcn_launches_per_epoch", I64, [P])
+_sig("gcnb_synth_graph", I32, [I64, I64, I32, C.c_double, C.c_double, I64, C.c_uint64, P, P, P])
+_sig("gcnb_host_free", None, [P])
+_sig("gcnb_synth_dense_features", I32, [I64, I32, C.c_uint64, P, P, P])
+_sig("gcnb_synth_labels", I32, [I64, I32, C.c_double, C.c_double, C.c_uint64, P, P])
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(P)
+
+
+class HostDataset:
+    """Host CSR of one dataset (uint32 indices, int32 labels) -- the content of the reference's GCNData."""
+
+    FIELDS = ("g_indptr", "g_indices", "f_indptr", "f_indices", "f_value", "label", "split", "graph_value")
+
+    def __init__(self, **kw):
+        self.graph_value = None
+        self.__dict__.update(kw)
+
+    @property
+    def num_nodes(self):
+        return len(self.g_indptr) - 1
+
+    def nbytes(self):
+        return sum(getattr(self, k).nbytes for k in self.FIELDS if getattr(self, k) is not None)
+
+
+def parse_dataset(root, name, no_feature=False):
+    """Parser(params, data, name).parse() run from `root` (expects root/data/<name>.graph|.split|.svmlight)."""
+    h = P()
+    rc = lib.gcnb_dataset_parse(str(root).encode(), name.encode(), int(no_feature), C.byref(h))
+    if rc != 0:
+        return None
+    dims = (I64 * 10)()
+    check(lib.gcnb_dataset_dims(h, dims))
+    n, gnnz, frows, fnnz, in_dim, out_dim, nsplit, tr, va, te = (int(x) for x in dims)
+    arrs = [np.empty(n + 1, np.uint32), np.empty(gnnz, np.uint32), np.empty(frows + 1, np.uint32),
+            np.empty(fnnz, np.uint32), np.empty(fnnz, np.float32), np.empty(frows, np.int32),
+            np.empty(nsplit, np.uint32), np.empty(gnnz, np.float32)]
+    for k, a in enumerate(arrs):
+        check(lib.gcnb_dataset_copy(h, k, _p(a)))
+    lib.gcnb_dataset_free(h)
+    return HostDataset(**dict(zip(HostDataset.FIELDS, arrs)), input_dim=in_dim, output_dim=out_dim,
+                       split_counts=(tr, va, te))
+
+
+def synth_graph(n, n_undirected_edges, n_blocks=50, intra=0.8, sigma=1.2, max_deg=21657, seed=19990304):
+    ip, ix, nnz = P(), P(), I64(0)
+    check(lib.gcnb_synth_graph(n, n_undirected_edges, n_blocks, intra, sigma, max_deg, seed, C.byref(ip), C.byref(ix),
+                               C.byref(nnz)))
+    indptr = np.ctypeslib.as_array(C.cast(ip, C.POINTER(C.c_uint32)), shape=(n + 1,)).copy()
+    indices = np.ctypeslib.as_array(C.cast(ix, C.POINTER(C.c_uint32)), shape=(nnz.value,)).copy()
+    lib.gcnb_host_free(ip)
+    lib.gcnb_host_free(ix)
+    return indptr, indices
+
+
+def synth_dataset(n, n_undirected_edges, n_features, n_classes, n_blocks=50, intra=0.8, sigma=1.2, max_deg=21657,
+                  frac_train=0.66, frac_val=0.10, seed=19990304, pinned=False):
+    """Reddit-shape style synthetic dataset (BASELINE.json config 3): planted-community graph, dense N(0,1) features
+    stored as an all-columns CSR (how svmlight-Reddit parses), uniform labels, 66/10/24 split."""
+    g_indptr, g_indices = synth_graph(n, n_undirected_edges, n_blocks, intra, sigma, max_deg, seed)
+
+    def alloc(shape, dtype):
+        if pinned:
+            import torch
+            t = torch.empty(shape, dtype={np.uint32: torch.int32, np.float32: torch.float32, np.int32: torch.int32}[dtype],
+                            pin_memory=True)
+            return t.numpy().view(dtype), t
+        return np.empty(shape, dtype), None
+
+    keep = []
+    f_indptr, t = alloc(n + 1, np.uint32); keep.append(t)
+    f_indices, t = alloc(n * n_features, np.uint32); keep.append(t)
+    f_value, t = alloc(n * n_features, np.float32); keep.append(t)
+    check(lib.gcnb_synth_dense_features(n, n_features, seed, _p(f_indptr), _p(f_indices), _p(f_value)))
+    label, split = np.empty(n, np.int32), np.empty(n, np.uint32)
+    check(lib.gcnb_synth_labels(n, n_classes, frac_train, frac_val, seed, _p(label), _p(split)))
+    if pinned:
+        gi, t = alloc(g_indptr.shape, np.uint32); gi[:] = g_indptr; keep.append(t); g_indptr = gi
+        gx, t = alloc(g_indices.shape, np.uint32); gx[:] = g_indices; keep.append(t); g_indices = gx
+    ds = HostDataset(g_indptr=g_indptr, g_indices=g_indices, f_indptr=f_indptr, f_indices=f_indices, f_value=f_value,
+                     label=label, split=split, input_dim=n_features, output_dim=n_classes,
+                     split_counts=tuple(int((split == s).sum()) for s in (1, 2, 3)))
+    ds._pinned_keepalive = keep
+    return ds
+
+
+class GCN:
+    """The reference's GCN driver (GCN(params, adam_params, data); run(); private train_epoch/eval exposed)."""
+
+    def __init__(self, ds, hidden_dims=(16,), dropouts=(0.5, 0.5), epochs=100, early_stopping=0, lr=0.01, beta1=0.9,
+                 beta2=0.999, eps=1e-8, weight_decay=5e-4, seed=19990304, quiet=True, reorder=True):
+        self.ds = ds
+        self.n_layers = len(hidden_dims) + 1
+        assert len(dropouts) == self.n_layers
+        self._hd = np.asarray(hidden_dims, np.uint32)
+        self._dp = np.asarray(dropouts, np.float32)
+        cfg = GcnConfig(ds.num_nodes, ds.input_dim, ds.output_dim, self.n_layers, _p(self._hd) if len(self._hd) else None,
+                        _p(self._dp), epochs, early_stopping, lr, beta1, beta2, eps, weight_decay, seed, int(quiet),
+                        int(reorder))
+        gv = getattr(ds, "graph_value", None)
+        data = GcnData(_p(ds.g_indptr), _p(ds.g_indices), len(ds.g_indices), _p(gv), _p(ds.f_indptr), _p(ds.f_indices),
+                       _p(ds.f_value), len(ds.f_indices), _p(ds.label), _p(ds.split))
+        h = P()
+        check(lib.gcnb_gcn_create(C.byref(cfg), C.byref(data), C.byref(h)))
+        self.h = h
+        self.dims = [ds.input_dim] + [int(x) for x in hidden_dims] + [ds.output_dim]
+
+    def _pair(self, fn, *a):
+        out = (F32 * 2)()
+        check(fn(self.h, *a, out))
+        return float(out[0]), float(out[1])
+
+    def train_epoch(self):
+        return self._pair(lib.gcnb_gcn_train_epoch)
+
+    def eval(self, split):
+        return self._pair(lib.gcnb_gcn_eval, int(split))
+
+    def run(self):
+        out = (F32 * 4)()
+        check(lib.gcnb_gcn_run(self.h, out))
+        return dict(avg_epoch_ms=float(out[0]), total_s=float(out[1]), last_val_acc=float(out[2]), epochs=int(out[3]))
+
+    def weight(self, l):
+        w = np.empty(lib.gcnb_gcn_weight_size(self.h, l), np.float32)
+        check(lib.gcnb_gcn_get_weight(self.h, l, _p(w)))
+        return w
+
+    def weight_grad(self, l):
+        w = np.empty(lib.gcnb_gcn_weight_size(self.h, l), np.float32)
+        check(lib.gcnb_gcn_get_weight_grad(self.h, l, _p(w)))
+        return w
+
+    def set_weight(self, l, w):
+        w = np.ascontiguousarray(w, np.float32).ravel()
+        assert w.size == lib.gcnb_gcn_weight_size(self.h, l)
+        check(lib.gcnb_gcn_set_weight(self.h, l, _p(w)))
+
+    def logits(self):
+        out = np.empty((self.ds.num_nodes, self.ds.output_dim), np.float32)
+        check(lib.gcnb_gcn_get_logits(self.h, _p(out)))
+        return out
+
+    def set_mask(self, site, mask):
+        m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+        check(lib.gcnb_gcn_set_mask(self.h, site, _p(m)))
+
+    def launches_per_epoch(self):
+        return int(lib.gcnb_gcn_launches_per_epoch(self.h))
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib.gcnb_gcn_destroy(self.h)
+            self.h = None
+
+    __del__ = close

@@ -1,0 +1,143 @@
+// gcn.cuh -- model driver, mirror of include/gcn.cuh:23-122 (GCNSmartObjects, GCNParams, GCNData, DevGCNData, GCN
+// with the same constructor, run() and public result fields).  The private part is a B200-first redesign:
+//   * one stream, no per-module event choreography; the per-epoch launch sequence is fixed, so small datasets can
+//     be replayed from a CUDA graph (launch-bound regime);
+//   * the feature matrix is never overwritten: input dropout writes a second buffer (no set_input restore copy,
+//     src/gcn.cu:181-200), and an all-columns-present feature CSR (Reddit) is routed to the dense kernels;
+//   * per layer the cheaper association is used: (A_hat * a) * W when in_dim < out_dim (GraphSum runs at the
+//     narrower width), A_hat * (a * W) otherwise -- same math as the module chain, different rounding order;
+//   * ReLU+Dropout fused, loss + accuracy fused, multi-tensor Adam, fixed-order reductions.
+#ifndef GCN_CUH
+#define GCN_CUH
+#include <cuda_runtime.h>
+#include <memory>
+#include <string>
+#include <utility>
+#include <vector>
+#include "../include/module.cuh"
+#include "../include/optim.cuh"
+#include "../include/reduction.cuh"
+#include "../include/shared_ptr.cuh"
+#include "../include/smart_object.cuh"
+#include "../include/sparse.cuh"
+#include "../include/utils.cuh"
+#include "../include/variable.cuh"
+
+using std::shared_ptr;
+using std::unique_ptr;
+
+class GCNSmartObjects {
+ public:
+  smart_stream forward_training_stream;
+  smart_stream forward_evaluation_stream;
+  std::vector<smart_stream> backward_streams;  // 2
+  smart_event start_backward;
+  smart_event start_set_input;
+  std::vector<smart_event> start_matmul_backward;  // L - 1
+  std::vector<smart_event> start_matmul_forward;   // L
+  explicit GCNSmartObjects(const natural n_layers);
+};
+
+struct GCNParams {
+  natural num_nodes, input_dim, output_dim;
+  std::vector<natural> hidden_dims = {16};
+  std::vector<real> dropouts = {0.5, 0.5};
+  natural epochs{100}, early_stopping{0};
+  natural train_dim{0}, val_dim{0}, test_dim{0};
+  natural n_layers{2};
+  void print_info() const;
+};
+
+struct GCNData {
+  SparseIndex feature_index, graph;
+  std::vector<natural> split;
+  std::vector<integer> label;
+  std::vector<real> graph_value;
+  std::vector<real> feature_value;
+};
+
+// extension: non-owning view of the same data as raw host arrays (C ABI / synthetic graphs)
+struct GCNDataView {
+  const natural *graph_indptr, *graph_indices;
+  size_t graph_nnz;
+  const real *graph_value;  // may be nullptr: computed as 1./sqrtf(deg_src*deg_dst)
+  const natural *feat_indptr, *feat_indices;
+  const real *feat_value;
+  size_t feat_nnz;
+  const integer *label;
+  const natural *split;
+  size_t num_nodes;
+};
+
+class DevGCNData {
+ public:
+  DevSparseIndex dev_graph_index;    // adjacency matrix
+  DevSparseIndex dev_feature_index;  // feature
+  dev_shared_ptr<real> dev_feature_value;
+  dev_shared_ptr<real> dev_graph_value;
+  dev_shared_ptr<natural> dev_split;
+  dev_shared_ptr<integer> dev_label;
+  natural label_size;
+  DevGCNData(const GCNData &gcn_data);
+  DevGCNData(const GCNDataView &view);
+};
+
+struct GCNEngineState;  // plans, workspaces, captured graphs (src/gcn.cpp)
+
+class GCN {
+  GCNSmartObjects smart_objects;
+  natural L;
+  const GCNData *data;
+  DevGCNData dev_data;
+  std::vector<shared_ptr<Variable>> variables;
+  shared_ptr<Variable> input, output;
+  std::vector<shared_ptr<Variable>> weights;
+  std::vector<bool> decays;
+  Adam optimizer;
+  dev_shared_ptr<integer> dev_truth;
+  std::string variables_info;
+  shared_ptr<GCNEngineState> st;
+
+  void set_truth(const natural current_split, cudaStream_t stream) const;
+  void forward_pass(bool training, natural split, cudaStream_t stream);
+  void backward_pass(cudaStream_t stream);
+  std::pair<real, real> finalize(cudaStream_t stream) const;
+  void print_variable_info() const;
+  void init(bool quiet);
+
+ public:
+  real avg_epoch_time;
+  real total_time;
+  real last_val_accuracy;
+  const GCNParams *params;
+  const AdamParams *adam_params;
+  // The reference silences its output at compile time (-DNO_OUTPUT, Makefile:40-63).  The library is compiled once,
+  // so the flag is sampled in the including translation unit and passed down.
+#ifdef NO_OUTPUT
+  GCN(GCNParams const *params_, AdamParams const *adam_params_, GCNData const *data_)
+      : GCN(params_, adam_params_, data_, true) {}
+#else
+  GCN(GCNParams const *params_, AdamParams const *adam_params_, GCNData const *data_)
+      : GCN(params_, adam_params_, data_, false) {}
+#endif
+  GCN(GCNParams const *params_, AdamParams const *adam_params_, GCNData const *data_, bool quiet);
+  GCN(GCNParams const *params_, AdamParams const *adam_params_, const GCNDataView &view, bool quiet);
+  ~GCN();
+  void run();
+
+  // ---- extensions (not in the reference's public surface; used by the C ABI engine, tests and bench) ----
+  std::pair<real, real> train_epoch();                       // reference: private, src/gcn.cu:307-343
+  std::pair<real, real> eval(const natural current_split);   // reference: private, src/gcn.cu:293-303
+  natural n_layers() const { return L; }
+  const shared_ptr<Variable> &weight(natural l) const { return weights[l]; }
+  const shared_ptr<Variable> &logits() const { return output; }
+  // injected randomness for parity against the reference CPU implementation: keep-masks (1 byte per element)
+  // for the next training pass, one per dropout site (0 = input, l = hidden layer l-1); nullptr = draw with Philox
+  void set_external_masks(const std::vector<const unsigned char *> &host_masks);
+  void set_quiet(bool q);
+  void set_use_cuda_graph(bool on);
+  void set_reorder(bool on);  // allow the (A*a)*W association (default on)
+  size_t launches_per_epoch() const;
+  natural epochs_run() const;
+};
+#endif

@@ -1,0 +1,221 @@
+// engine.cpp -- engine-level C ABI (include/gcnb_engine.h): Parser + GCN behind plain C with host buffers.
+#include <cstring>
+#include <memory>
+#include "../../../include/gcnb_engine.h"
+#include "../include/gcn.cuh"
+#include "../include/parser.h"
+#include <unistd.h>
+
+struct gcnb_dataset {
+  GCNParams params;
+  GCNData data;
+};
+
+struct gcnb_gcn {
+  GCNParams params;
+  AdamParams adam;
+  std::unique_ptr<GCN> gcn;
+  std::vector<std::vector<unsigned char>> unused;
+  std::vector<const unsigned char *> masks;
+};
+
+extern "C" {
+
+int gcnb_dataset_parse(const char *root, const char *name, int no_feature, gcnb_dataset **out) {
+  if (!root || !name || !out) return GCNB_E_BADARG;
+  *out = nullptr;
+  char cwd[4096];
+  if (!getcwd(cwd, sizeof cwd)) return GCNB_E_BADARG;
+  if (chdir(root) != 0) return GCNB_E_BADARG;  // Parser opens data/<name>.* relative to the CWD (src/parser.cpp:3-9)
+  auto d = std::make_unique<gcnb_dataset>();
+  bool ok;
+  {
+    Parser parser(&d->params, &d->data, name, no_feature != 0, true);
+    ok = parser.parse();
+  }
+  if (chdir(cwd) != 0) ok = false;
+  if (!ok) return GCNB_E_BADARG;
+  *out = d.release();
+  return 0;
+}
+
+int gcnb_dataset_dims(const gcnb_dataset *d, int64_t dims[10]) {
+  if (!d || !dims) return GCNB_E_BADARG;
+  dims[0] = d->params.num_nodes;
+  dims[1] = (int64_t)d->data.graph.indices.size();
+  dims[2] = (int64_t)d->data.feature_index.indptr.size() - 1;
+  dims[3] = (int64_t)d->data.feature_index.indices.size();
+  dims[4] = d->params.input_dim;
+  dims[5] = d->params.output_dim;
+  dims[6] = (int64_t)d->data.split.size();
+  dims[7] = d->params.train_dim;
+  dims[8] = d->params.val_dim;
+  dims[9] = d->params.test_dim;
+  return 0;
+}
+
+int gcnb_dataset_copy(const gcnb_dataset *d, int which, void *dst) {
+  if (!d || !dst) return GCNB_E_BADARG;
+  auto cp = [&](const void *src, size_t bytes) { std::memcpy(dst, src, bytes); };
+  switch (which) {
+    case 0: cp(d->data.graph.indptr.data(), d->data.graph.indptr.size() * 4); break;
+    case 1: cp(d->data.graph.indices.data(), d->data.graph.indices.size() * 4); break;
+    case 2: cp(d->data.feature_index.indptr.data(), d->data.feature_index.indptr.size() * 4); break;
+    case 3: cp(d->data.feature_index.indices.data(), d->data.feature_index.indices.size() * 4); break;
+    case 4: cp(d->data.feature_value.data(), d->data.feature_value.size() * 4); break;
+    case 5: cp(d->data.label.data(), d->data.label.size() * 4); break;
+    case 6: cp(d->data.split.data(), d->data.split.size() * 4); break;
+    case 7: cp(d->data.graph_value.data(), d->data.graph_value.size() * 4); break;
+    default: return GCNB_E_BADARG;
+  }
+  return 0;
+}
+
+int gcnb_dataset_free(gcnb_dataset *d) {
+  delete d;
+  return 0;
+}
+
+static int fill_params(const gcnb_gcn_config *cfg, gcnb_gcn *g) {
+  if (cfg->n_layers < 1 || (cfg->n_layers > 1 && !cfg->hidden_dims) || !cfg->dropouts) return GCNB_E_BADARG;
+  g->params.num_nodes = (natural)cfg->num_nodes;
+  g->params.input_dim = (natural)cfg->input_dim;
+  g->params.output_dim = (natural)cfg->output_dim;
+  g->params.n_layers = (natural)cfg->n_layers;
+  g->params.hidden_dims.assign(cfg->hidden_dims, cfg->hidden_dims + (cfg->n_layers - 1));
+  g->params.dropouts.assign(cfg->dropouts, cfg->dropouts + cfg->n_layers);
+  g->params.epochs = cfg->epochs;
+  g->params.early_stopping = cfg->early_stopping;
+  g->adam.learning_rate = cfg->learning_rate;
+  g->adam.beta1 = cfg->beta1;
+  g->adam.beta2 = cfg->beta2;
+  g->adam.eps = cfg->eps;
+  g->adam.weight_decay = cfg->weight_decay;
+  CudaParams::SEED = cfg->seed;
+  return 0;
+}
+
+int gcnb_gcn_create(const gcnb_gcn_config *cfg, const gcnb_gcn_data *data, gcnb_gcn **out) {
+  if (!cfg || !data || !out) return GCNB_E_BADARG;
+  int sm = 0;
+  const int dc = gcnb_device_check(&sm);
+  if (dc) return dc;  // no GPU => error, never a CPU path
+  auto g = std::make_unique<gcnb_gcn>();
+  const int rc = fill_params(cfg, g.get());
+  if (rc) return rc;
+  const size_t n = (size_t)cfg->num_nodes;
+  for (size_t i = 0; i < n; i++) {
+    if (data->split[i] == 1) g->params.train_dim++;
+    else if (data->split[i] == 2) g->params.val_dim++;
+    else if (data->split[i] == 3) g->params.test_dim++;
+  }
+  GCNDataView v{};
+  v.graph_indptr = data->graph_indptr;
+  v.graph_indices = data->graph_indices;
+  v.graph_nnz = (size_t)data->graph_nnz;
+  v.graph_value = data->graph_value;
+  v.feat_indptr = data->feat_indptr;
+  v.feat_indices = data->feat_indices;
+  v.feat_value = data->feat_value;
+  v.feat_nnz = (size_t)data->feat_nnz;
+  v.label = data->label;
+  v.split = data->split;
+  v.num_nodes = n;
+  g->gcn = std::make_unique<GCN>(&g->params, &g->adam, v, cfg->quiet != 0);
+  if (!cfg->reorder) g->gcn->set_reorder(false);
+  g->masks.assign(g->params.n_layers, nullptr);
+  *out = g.release();
+  return 0;
+}
+
+int gcnb_gcn_create_from_dataset(const gcnb_gcn_config *cfg, const gcnb_dataset *d, gcnb_gcn **out) {
+  if (!cfg || !d || !out) return GCNB_E_BADARG;
+  gcnb_gcn_config c = *cfg;
+  c.num_nodes = d->params.num_nodes;
+  c.input_dim = d->params.input_dim;
+  c.output_dim = d->params.output_dim;
+  gcnb_gcn_data gd{};
+  gd.graph_indptr = d->data.graph.indptr.data();
+  gd.graph_indices = d->data.graph.indices.data();
+  gd.graph_nnz = (int64_t)d->data.graph.indices.size();
+  gd.graph_value = d->data.graph_value.data();
+  gd.feat_indptr = d->data.feature_index.indptr.data();
+  gd.feat_indices = d->data.feature_index.indices.data();
+  gd.feat_value = d->data.feature_value.data();
+  gd.feat_nnz = (int64_t)d->data.feature_index.indices.size();
+  gd.label = d->data.label.data();
+  gd.split = d->data.split.data();
+  return gcnb_gcn_create(&c, &gd, out);
+}
+
+int gcnb_gcn_destroy(gcnb_gcn *g) {
+  delete g;
+  return 0;
+}
+
+int gcnb_gcn_train_epoch(gcnb_gcn *g, float out[2]) {
+  if (!g || !out) return GCNB_E_BADARG;
+  auto r = g->gcn->train_epoch();
+  out[0] = r.first;
+  out[1] = r.second;
+  return 0;
+}
+
+int gcnb_gcn_eval(gcnb_gcn *g, int split, float out[2]) {
+  if (!g || !out || split < 1 || split > 3) return GCNB_E_BADARG;
+  auto r = g->gcn->eval((natural)split);
+  out[0] = r.first;
+  out[1] = r.second;
+  return 0;
+}
+
+int gcnb_gcn_run(gcnb_gcn *g, float out[4]) {
+  if (!g) return GCNB_E_BADARG;
+  reset_timer();
+  g->gcn->run();
+  if (out) {
+    out[0] = g->gcn->avg_epoch_time;
+    out[1] = g->gcn->total_time;
+    out[2] = g->gcn->last_val_accuracy;
+    out[3] = (float)g->gcn->epochs_run();
+  }
+  return 0;
+}
+
+int64_t gcnb_gcn_weight_size(const gcnb_gcn *g, int layer) {
+  if (!g || layer < 0 || layer >= (int)g->gcn->n_layers()) return -1;
+  return g->gcn->weight(layer)->size;
+}
+int gcnb_gcn_get_weight(const gcnb_gcn *g, int layer, float *dst) {
+  if (!g || !dst || layer < 0 || layer >= (int)g->gcn->n_layers()) return GCNB_E_BADARG;
+  CHECK_CUDA_ERROR(cudaDeviceSynchronize());
+  g->gcn->weight(layer)->dev_data.copy_to_host(dst);
+  return 0;
+}
+int gcnb_gcn_set_weight(gcnb_gcn *g, int layer, const float *src) {
+  if (!g || !src || layer < 0 || layer >= (int)g->gcn->n_layers()) return GCNB_E_BADARG;
+  CHECK_CUDA_ERROR(cudaDeviceSynchronize());
+  g->gcn->weight(layer)->dev_data.copy_to_device(src);
+  return 0;
+}
+int gcnb_gcn_get_weight_grad(const gcnb_gcn *g, int layer, float *dst) {
+  if (!g || !dst || layer < 0 || layer >= (int)g->gcn->n_layers()) return GCNB_E_BADARG;
+  CHECK_CUDA_ERROR(cudaDeviceSynchronize());
+  g->gcn->weight(layer)->dev_grad.copy_to_host(dst);
+  return 0;
+}
+int gcnb_gcn_get_logits(const gcnb_gcn *g, float *dst) {
+  if (!g || !dst) return GCNB_E_BADARG;
+  CHECK_CUDA_ERROR(cudaDeviceSynchronize());
+  g->gcn->logits()->dev_data.copy_to_host(dst);
+  return 0;
+}
+int gcnb_gcn_set_mask(gcnb_gcn *g, int site, const uint8_t *host_mask) {
+  if (!g || site < 0 || site >= (int)g->gcn->n_layers()) return GCNB_E_BADARG;
+  g->masks[site] = host_mask;
+  g->gcn->set_external_masks(g->masks);  // uploads now; the host buffer is not referenced afterwards
+  return 0;
+}
+int64_t gcnb_gcn_launches_per_epoch(const gcnb_gcn *g) { return g ? (int64_t)g->gcn->launches_per_epoch() : -1; }
+
+}  // extern "C"

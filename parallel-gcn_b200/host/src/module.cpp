@@ -1,0 +1,161 @@
+// module.cpp -- Dropout / SparseMatmul / GraphSum / ReLU / Matmul / CrossEntropyLoss of the reference's module API
+// (src/module.cu) as thin calls into the C ABI.  Stream/event choreography mirrors the reference so that hand-built
+// module chains keep their ordering; the kernels underneath are the sm_100a ones of csrc/.
+#include "../include/module.cuh"
+#include <map>
+
+// ---- shared SpMM plans -------------------------------------------------------------------------------------
+struct SpmmPlanCache {
+  dev_shared_ptr<natural> indptr, indices;  // keep the device arrays alive while a plan borrows them
+  natural n_rows = 0, n_cols = 0;
+  gcnb_spmm_plan *plan = nullptr;
+  gcnb_csc *csc = nullptr;
+  gcnb_spmm_plan *csc_plan = nullptr;
+  const uint32_t *csc_perm = nullptr;
+  int csc_dense = 0;
+  bool csc_ready = false;
+  dev_shared_ptr<real> tn_workspace;
+  ~SpmmPlanCache() {
+    if (csc_plan) gcnb_spmm_plan_destroy(csc_plan);
+    if (csc) gcnb_csc_destroy(csc);
+    if (plan) gcnb_spmm_plan_destroy(plan);
+  }
+  void ensure_csc(cudaStream_t s) {
+    if (csc_ready) return;
+    GCNB_CALL(gcnb_csc_create(indptr.get(), indices.get(), n_rows, n_cols, s, &csc));
+    const uint32_t *colptr = nullptr, *rowidx = nullptr;
+    GCNB_CALL(gcnb_csc_arrays(csc, &colptr, &rowidx, &csc_perm, &csc_dense));
+    if (!csc_dense) GCNB_CALL(gcnb_spmm_plan_create(colptr, rowidx, n_cols, n_rows, 0, s, &csc_plan));
+    csc_ready = true;
+  }
+};
+
+static shared_ptr<SpmmPlanCache> plan_for(DevSparseIndex *sp, natural n_cols) {
+  static std::map<std::pair<const void *, const void *>, std::weak_ptr<SpmmPlanCache>> registry;
+  const auto key = std::make_pair((const void *)sp->dev_indptr.get(), (const void *)sp->dev_indices.get());
+  auto it = registry.find(key);
+  if (it != registry.end())
+    if (auto alive = it->second.lock()) return alive;
+  auto c = std::make_shared<SpmmPlanCache>();
+  c->indptr = sp->dev_indptr;
+  c->indices = sp->dev_indices;
+  c->n_rows = sp->indptr_size - 1;
+  c->n_cols = n_cols;
+  GCNB_CALL(gcnb_spmm_plan_create(c->indptr.get(), c->indices.get(), c->n_rows, n_cols, 0, nullptr, &c->plan));
+  registry[key] = c;
+  return c;
+}
+
+// ---- Dropout (src/module.cu:6-99) -----------------------------------------------------------------------------
+Dropout::Dropout(shared_ptr<Variable> in_, real p_) : in(in_), p(p_) {
+  dev_mask = in->dev_grad.get() ? dev_shared_ptr<bool>(in->size) : dev_shared_ptr<bool>();
+}
+void Dropout::forward(bool training, const smart_stream &stream) const {
+  if (!training) return;
+  const gcnb_rng_t rng = Variable::rng_descriptor();
+  GCNB_CALL(gcnb_dropout_fwd_f32(in->dev_data.get(), reinterpret_cast<uint8_t *>(dev_mask.get()), nullptr, in->size, p,
+                                 &rng, stream.get()));
+  Variable::rng_consume(in->size);
+}
+void Dropout::backward(const smart_stream &backward_stream) const {
+  if (!dev_mask.get()) return;
+  GCNB_CALL(gcnb_dropout_bwd_f32(in->dev_grad.get(), reinterpret_cast<const uint8_t *>(dev_mask.get()), in->size, p,
+                                 backward_stream.get()));
+}
+
+// ---- SparseMatmul (src/module.cu:104-163) -----------------------------------------------------------------------
+SparseMatmul::SparseMatmul(shared_ptr<Variable> a_, shared_ptr<Variable> b_, shared_ptr<Variable> c_,
+                           DevSparseIndex *sp_, natural m_, natural n_, natural p_,
+                           smart_event &start_matmul_forward_, smart_event &start_set_input_)
+    : a(a_), b(b_), c(c_), sp(sp_), m(m_), n(n_), p(p_), start_matmul_forward(start_matmul_forward_),
+      start_set_input(start_set_input_), plans(plan_for(sp_, n_)) {}
+
+void SparseMatmul::forward(bool, const smart_stream &stream) const {
+  CHECK_CUDA_ERROR(cudaStreamWaitEvent(stream.get(), start_matmul_forward.get()));
+  GCNB_CALL(gcnb_spmm_f32(plans->plan, a->dev_data.get(), nullptr, b->dev_data.get(), c->dev_data.get(), p, stream.get()));
+}
+void SparseMatmul::backward(const smart_stream &backward_stream) const {
+  // b.grad = A^T * c.grad, fully overwritten (the reference zeroes then atomically accumulates, :154-163)
+  cudaStream_t s = backward_stream.get();
+  plans->ensure_csc(s);
+  if (plans->csc_dense) {
+    const int64_t need = gcnb_matmul_tn_workspace(m, n, p);
+    if ((int64_t)plans->tn_workspace.get_n_elements() * 4 < need) plans->tn_workspace = dev_shared_ptr<real>((need + 3) / 4);
+    GCNB_CALL(gcnb_matmul_tn_f32(a->dev_data.get(), c->dev_grad.get(), b->dev_grad.get(), m, n, p,
+                                 plans->tn_workspace.get(), need, s));
+  } else {
+    GCNB_CALL(gcnb_spmm_f32(plans->csc_plan, a->dev_data.get(), plans->csc_perm, c->dev_grad.get(), b->dev_grad.get(), p, s));
+  }
+  CHECK_CUDA_ERROR(cudaEventRecord(start_set_input.get(), s));
+}
+
+// ---- GraphSum (src/module.cu:168-210) ---------------------------------------------------------------------------
+GraphSum::GraphSum(shared_ptr<Variable> in_, shared_ptr<Variable> out_, DevSparseIndex *graph_,
+                   dev_shared_ptr<real> dev_graph_value_, natural dim_, bool generate_event_,
+                   smart_event &start_matmul_backward_)
+    : in(in_), out(out_), graph(graph_), dev_graph_value(dev_graph_value_), dim(dim_), generate_event(generate_event_),
+      start_matmul_backward(start_matmul_backward_), plans(plan_for(graph_, graph_->indptr_size - 1)) {}
+
+void GraphSum::forward(bool, const smart_stream &stream) const {
+  GCNB_CALL(gcnb_spmm_f32(plans->plan, dev_graph_value.get(), nullptr, in->dev_data.get(), out->dev_data.get(), dim,
+                          stream.get()));
+}
+void GraphSum::backward(const smart_stream &backward_stream) const {
+  // same index (symmetric normalised adjacency), gradients flow out.grad -> in.grad (src/module.cu:200-210)
+  GCNB_CALL(gcnb_spmm_f32(plans->plan, dev_graph_value.get(), nullptr, out->dev_grad.get(), in->dev_grad.get(), dim,
+                          backward_stream.get()));
+  if (generate_event) CHECK_CUDA_ERROR(cudaEventRecord(start_matmul_backward.get(), backward_stream.get()));
+}
+
+// ---- ReLU (src/module.cu:215-265) -------------------------------------------------------------------------------
+ReLU::ReLU(shared_ptr<Variable> in_) : in(in_) { dev_mask = dev_shared_ptr<bool>(in->size); }
+void ReLU::forward(bool training, const smart_stream &stream) const {
+  GCNB_CALL(gcnb_relu_fwd_f32(in->dev_data.get(), reinterpret_cast<uint8_t *>(dev_mask.get()), in->size, training,
+                              stream.get()));
+}
+void ReLU::backward(const smart_stream &backward_stream) const {
+  GCNB_CALL(gcnb_relu_bwd_f32(in->dev_grad.get(), reinterpret_cast<const uint8_t *>(dev_mask.get()), in->size,
+                              backward_stream.get()));
+}
+
+// ---- Matmul (src/module.cu:270-472) -------------------------------------------------------------------------------
+Matmul::Matmul(shared_ptr<Variable> a_, shared_ptr<Variable> b_, shared_ptr<Variable> c_, natural m_, natural n_,
+               natural p_, smart_event &event_forward_, smart_event &event_backward_, const smart_stream &stream_)
+    : a(a_), b(b_), c(c_), m(m_), n(n_), p(p_), event_forward(event_forward_), event_backward(event_backward_),
+      my_stream(stream_) {
+  workspace = dev_shared_ptr<real>((gcnb_matmul_tn_workspace(m, n, p) + 3) / 4);
+}
+void Matmul::forward(bool, const smart_stream &stream) const {
+  CHECK_CUDA_ERROR(cudaStreamWaitEvent(stream.get(), event_forward.get()));
+  GCNB_CALL(gcnb_matmul_nn_f32(a->dev_data.get(), b->dev_data.get(), c->dev_data.get(), m, n, p, stream.get()));
+}
+void Matmul::backward(const smart_stream &backward_stream) const {
+  GCNB_CALL(gcnb_matmul_nt_f32(c->dev_grad.get(), b->dev_data.get(), a->dev_grad.get(), m, n, p, backward_stream.get()));
+  CHECK_CUDA_ERROR(cudaStreamWaitEvent(my_stream.get(), event_backward.get()));
+  GCNB_CALL(gcnb_matmul_tn_f32(a->dev_data.get(), c->dev_grad.get(), b->dev_grad.get(), m, n, p, workspace.get(),
+                               (int64_t)workspace.get_n_elements() * 4, my_stream.get()));
+}
+
+// ---- CrossEntropyLoss (src/module.cu:477-562) ------------------------------------------------------------------------
+CrossEntropyLoss::CrossEntropyLoss(shared_ptr<Variable> logits_, dev_shared_ptr<integer> dev_truth_,
+                                   pinned_host_ptr<real> loss_, natural num_classes_, smart_event &event)
+    : logits(logits_), dev_truth(dev_truth_), loss(loss_), num_classes(num_classes_), start_backward(event),
+      num_samples(0) {
+  dev_loss_res = dev_shared_ptr<real>(4);
+  const natural n = logits->size / num_classes;
+  workspace = dev_shared_ptr<natural>((gcnb_ce_workspace(n) + 3) / 4);
+  CHECK_CUDA_ERROR(cudaMemset(workspace.get(), 0, workspace.get_n_elements() * sizeof(natural)));
+}
+void CrossEntropyLoss::forward(bool training, const smart_stream &stream) const {
+  const natural n = logits->size / num_classes;
+  GCNB_CALL(gcnb_softmax_ce_f32(logits->dev_data.get(), logits->dev_grad.get(), dev_truth.get(), n, num_classes,
+                                num_samples, training, dev_loss_res.get(), workspace.get(), stream.get()));
+  if (training) CHECK_CUDA_ERROR(cudaEventRecord(start_backward.get(), stream.get()));
+  // un-normalised loss sum -> pinned host (src/module.cu:540); GCN::finalize divides after the stream sync
+  CHECK_CUDA_ERROR(cudaMemcpyAsync(loss.get(), dev_loss_res.get(), sizeof(real), cudaMemcpyDeviceToHost, stream.get()));
+}
+void CrossEntropyLoss::backward(const smart_stream &backward_stream) const {
+  CHECK_CUDA_ERROR(cudaStreamWaitEvent(backward_stream.get(), start_backward.get()));
+}
+void CrossEntropyLoss::set_num_samples(natural num_samples_) { num_samples = num_samples_; }
+natural CrossEntropyLoss::get_num_samples() const { return num_samples; }

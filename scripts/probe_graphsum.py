@@ -52,18 +52,26 @@ def bench(plan, vals, x, out, dim, iters=20):
     return e0.elapsed_time(e1) / iters * 1e3  # us
 
 
+import argparse
+ap = argparse.ArgumentParser()
+ap.add_argument("--intra", type=float, nargs="*", default=[0.8, 0.0])
+ap.add_argument("--dim", type=int, nargs="*", default=[16, 41, 64])
+ap.add_argument("--seg", type=int, nargs="*", default=[256, 512, 1024])
+ap.add_argument("--iters", type=int, default=20)
+ap.add_argument("--out", default="gpurun_out/probe_graphsum.json")
+args = ap.parse_args()
 res = []
-for intra in (0.8, 0.0):
+for intra in args.intra:
     indptr, cols, vals, nnz = make(intra)
-    for dim in (16, 41, 64):
+    for dim in args.dim:
         x = torch.randn(N, dim, device=dev)
         out = torch.empty(N, dim, device=dev)
-        for seg in (256, 512, 1024):
+        for seg in args.seg:
             plan = gcnb.SpmmPlan(indptr, cols, N, seg)
-            us = bench(plan, vals, x, out, dim)
+            us = bench(plan, vals, x, out, dim, args.iters)
             alg = 4 * (N + 1) + 8 * nnz + 8 * N * dim
             r = dict(intra=intra, dim=dim, seg=seg, nnz=nnz, us=round(us, 1), alg_GBs=round(alg / us / 1e3, 1), info=plan.info())
             print(json.dumps(r), flush=True)
             res.append(r)
             plan.close()
-json.dump(res, open("gpurun_out/probe_graphsum.json", "w"), indent=1)
+json.dump(res, open(args.out, "w"), indent=1)
