@@ -1,0 +1,282 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 GCN engine (contract: see the task description / DESIGN.md).
+
+  python bench.py --gpus N --steps K --warmup W                 our arm   (N>1: launched by torchrun, one rank per GPU)
+  python bench.py --impl reference --gpus N --steps K --warmup W  the reference's own CPU implementation (rank 0 only)
+
+metric  : GCN train ms/epoch on the Reddit-shape synthetic graph (BASELINE.json configs[2]): 232,965 nodes,
+          114,848,857 CSR entries, 602 dense features, 41 classes, 2-layer GCN hidden 16, dropout 0.5/0.5, Adam.
+          A "step" is one epoch as the reference times it (TMR_TRAIN, src/gcn.cu:363-375): train_epoch (forward +
+          backward + Adam, loss/L2/accuracy) followed by the validation forward pass eval(2).
+value   : device time per step, inputs resident in HBM (CUDA events on the engine's stream, max over ranks).
+e2e     : the same metric through the engine C ABI with HOST (pinned) buffers: dataset upload + plan build + K steps,
+          every step reading its loss/accuracy back to the host; wall clock / K.
+roofline: GraphSum SpMM (d=16) algorithmic bytes / mean launch duration (event pair per launch inside the timed steps)
+          against the measured HBM copy bandwidth in MEASURED_PEAKS.json.
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+REDDIT = dict(n=232965, m=57307946, f=602, c=41, blocks=50, intra=0.8, sigma=1.2, max_deg=21657, seed=19990304)
+MODEL = dict(hidden=(16,), dropouts=(0.5, 0.5), lr=0.01, weight_decay=5e-4)
+METRIC, UNIT = "gcn_train_ms_per_epoch_reddit_shape", "ms/epoch"
+PUBLISHED = {"ref_gpu_T4_real_reddit_ms_per_epoch": 231.518, "ref_cpu_colab_xeon_real_reddit_ms_per_epoch": 9826.111,
+             "source": "reference report.pdf Table 3 (other hardware, real Reddit; not this synthetic graph)"}
+
+
+def workload_config(scale=1):
+    w = dict(REDDIT)
+    if scale > 1:
+        w["n"] = REDDIT["n"] // scale
+        w["m"] = REDDIT["m"] // scale
+        w["blocks"] = max(1, REDDIT["blocks"] // scale)
+        w["max_deg"] = min(REDDIT["max_deg"], w["n"] // 4)
+    return w
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md): in-process NVML polling every few
+    ms (the timed region is tens of ms, too short for `nvidia-smi -lms`), nvidia-smi one-shot as fallback."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
+    def __init__(self, index=0):
+        self.index, self.sm, self.mask, self.max_mhz, self._stop, self._t = index, [], 0, None, False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _poll(self):
+        while not self._stop:
+            try:
+                self.sm.append(float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+                self.mask |= int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def start(self):
+        if self.nv is not None:
+            self._t = threading.Thread(target=self._poll, daemon=True)
+            self._t.start()
+        return self
+
+    def stop(self):
+        self._stop = True
+        if self._t is not None:
+            self._t.join()
+        if not self.sm:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=clocks.sm,clocks.max.sm",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=20).stdout
+                a, b = [float(x) for x in out.strip().split(",")]
+                self.sm, self.max_mhz = [a], b
+            except Exception:
+                pass
+        reasons = sorted(name for bit, name in self.REASONS.items() if self.mask & bit)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(self.sm)}
+
+
+def make_dataset(eng, scale=1, pinned=True):
+    w = workload_config(scale)
+    t0 = time.time()
+    ds = eng.synth_dataset(w["n"], w["m"], w["f"], w["c"], n_blocks=w["blocks"], intra=w["intra"], sigma=w["sigma"],
+                           max_deg=w["max_deg"], seed=w["seed"], pinned=pinned)
+    return ds, w, time.time() - t0
+
+
+def graphsum_alg_bytes(n, nnz, d):
+    # 4(N+1) indptr + 4 nnz indices + 4 nnz values + 4 N d read + 4 N d write
+    return 4 * (n + 1) + 8 * nnz + 8 * n * d
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_reference_step_ms(steps, warmup, scale):
+    """The reference's own CPU implementation (oracle/_ref = hpdga-spring23 compiled in place) on a 1/scale Reddit-shape
+    sample; falls back to the oracle port when _ref did not travel.  Returns (ms per full-size step, kind, sample, cores)."""
+    import __graft_entry__ as ge
+    ge.load_package()
+    eng = importlib.import_module("parallel_gcn_b200.engine")  # generator only (host code)
+    from oracle import oracle as O
+    ds, w, _ = make_dataset(eng, scale, pinned=False)
+    sample = ("1/%d-scale Reddit-shape graph from the same generator (%d nodes, %d CSR entries, %d dense features, %d "
+              "classes), one train epoch + validation forward per step, time x%d (linear in nnz and N*F; small-graph "
+              "cache residency makes this favour the CPU)" % (scale, ds.num_nodes, len(ds.g_indices), w["f"], w["c"], scale))
+    ods = O.Dataset(g_indptr=ds.g_indptr, g_indices=ds.g_indices, f_indptr=ds.f_indptr, f_indices=ds.f_indices,
+                    f_value=ds.f_value, label=ds.label, split=ds.split, input_dim=w["f"], output_dim=w["c"])
+    times = []
+    if O.ref is not None:
+        kind = "reference"
+        h = O.ref_dataset_from(ods)
+        O.ref.ref_srand(1)
+        g = O.ref.ref_gcn_create(h, MODEL["hidden"][0], MODEL["dropouts"][0], MODEL["lr"], MODEL["weight_decay"], 100, 0)
+        out = np.zeros(2, np.float32)
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            O.ref.ref_gcn_train_epoch(g, O._p(out))
+            O.ref.ref_gcn_eval(g, 2, O._p(out))
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+        O.ref.ref_gcn_free(g)
+        O.ref.ref_dataset_free(h)
+    else:
+        kind = "port"
+        og = O.OracleGCN(ods, hidden_dims=MODEL["hidden"], dropouts=MODEL["dropouts"], flavour="ref_cpu", libc_seed=1)
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            og.train_epoch()
+            og.eval(2)
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    return float(np.mean(times)) * 1e3 * scale, kind, sample, 1
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    scale = 16
+    ms, kind, sample, cores = cpu_reference_step_ms(args.steps, args.warmup, scale)
+    w = workload_config(1)
+    line = {"impl": "reference", "metric": METRIC, "value": ms, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "reddit_shape_synthetic n=%d nnz=%d f=%d c=%d; 2-layer GCN hidden 16 dropout 0.5/0.5 Adam; "
+                                   "step = train_epoch + eval(2)" % (w["n"], 2 * w["m"] + w["n"], w["f"], w["c"]),
+                       "host_cpu": cpu_name(), "host_cores_total": os.cpu_count()},
+            "cpu_baseline": {"value": ms, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": ms, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def cpu_name():
+    try:
+        for l in open("/proc/cpuinfo"):
+            if l.startswith("model name"):
+                return l.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import __graft_entry__ as ge
+    ge.load_package()
+    gcnb = importlib.import_module("parallel_gcn_b200.binding")
+    eng = importlib.import_module("parallel_gcn_b200.engine")
+    torch.cuda.set_device(local_rank)
+    gcnb.device_check()
+    if world > 1:
+        dist_mod = importlib.import_module("parallel_gcn_b200.dist")
+        return dist_mod.bench_main(args, rank, world, local_rank, sys.modules[__name__])
+
+    ds, w, gen_s = make_dataset(eng, args.scale, pinned=True)
+    n, nnz = ds.num_nodes, len(ds.g_indices)
+    # warm the CUDA context / module loading on a throw-away tiny problem (not part of any timed region)
+    tiny = eng.synth_dataset(2000, 20000, 32, 7, n_blocks=4, seed=1)
+    tg = eng.GCN(tiny)
+    tg.train_epoch(); tg.eval(2); tg.close()
+    torch.cuda.synchronize()
+
+    # ---- e2e: host buffers -> engine (upload + plans) -> K steps with per-pass D2H of loss/accuracy; wall clock
+    t0 = time.perf_counter()
+    g = eng.GCN(ds, hidden_dims=MODEL["hidden"], dropouts=MODEL["dropouts"], lr=MODEL["lr"], weight_decay=MODEL["weight_decay"],
+                seed=w["seed"])
+    t_create = time.perf_counter() - t0
+    last = None
+    for _ in range(args.steps):
+        tl = g.train_epoch()
+        vl = g.eval(2)
+        last = (tl, vl)
+    torch.cuda.synchronize()
+    e2e_total = time.perf_counter() - t0
+    h2d = ds.nbytes() - (0 if ds.graph_value is None else 0)
+    e2e = {"value": e2e_total * 1e3 / args.steps, "unit": UNIT, "h2d_bytes_per_step": int(h2d / args.steps),
+           "d2h_bytes_per_step": 2 * 32, "setup_ms": t_create * 1e3,
+           "steady_ms_per_step": (e2e_total - t_create) * 1e3 / args.steps,
+           "note": "wall clock of gcnb_gcn_create (pinned-host upload of the whole dataset, %d bytes, + plan build) plus K "
+                   "steps, divided by K; every pass copies its 32-byte result block back" % h2d}
+
+    # ---- device-timed steps (inputs resident), GraphSum launches timed individually for the roofline
+    for _ in range(args.warmup):
+        g.train_epoch(); g.eval(2)
+    clocks = ClockSampler(local_rank).start()
+    r = g.timed_epochs(args.steps, with_eval=True, time_graphsum=True)
+    clk = clocks.stop()
+    ms_per_step = r["ms"] / args.steps
+    gs_us = r["graphsum_ms"] * 1e3 / max(1, r["graphsum_calls"])
+    d = MODEL["hidden"][0]
+    alg = graphsum_alg_bytes(n, nnz, d)
+    peak, peak_src = peaks()
+    achieved = alg / (gs_us * 1e-6) / 1e9
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "graphsum_d16_summary.json")
+    if os.path.exists(prof):
+        traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+    roofline = {"bound": "hbm", "kernel": "spmm_seg_kernel<4,4,1> (GraphSum, d=%d)" % d, "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg, "mean_launch_us": gs_us, "launches_timed": r["graphsum_calls"],
+                "graphsum_share_of_step": r["graphsum_ms"] / r["ms"], "frac_of_nominal_8TBs": achieved / 8000.0}
+    line = {"metric": METRIC, "value": ms_per_step, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "reddit_shape_synthetic n=%d nnz=%d f=%d (dense, stored as all-columns CSR) c=%d, %d planted "
+                                   "communities %.0f%% intra, lognormal(%.1f) degrees; 2-layer GCN hidden %d dropout %.1f/%.1f "
+                                   "Adam lr %.2g wd %.0e; step = train_epoch + eval(2) (reference TMR_TRAIN)" %
+                                   (n, nnz, w["f"], w["c"], w["blocks"], 100 * w["intra"], w["sigma"], d, MODEL["dropouts"][0],
+                                    MODEL["dropouts"][1], MODEL["lr"], MODEL["weight_decay"]),
+                       "l2_policy": "inputs larger than L2 (each GraphSum streams %.0f MB, features 561 MB; L2 is 126 MB)" % (alg / 1e6),
+                       "parallelism": "single GPU", "dataset_gen_s": round(gen_s, 1), "scale": args.scale,
+                       "final_train_loss": last[0][0], "final_val_acc": last[1][1], "published_other_hw": PUBLISHED},
+            "clocks": clk, "e2e": e2e, "gpu_launches": r["launches"], "roofline": roofline}
+    g.close()
+    if not args.no_cpu_baseline:
+        ms, kind, sample, cores = cpu_reference_step_ms(2, 0, 16)
+        line["cpu_baseline"] = {"value": ms, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
+                                "host_cpu": cpu_name(), "host_cores_total": os.cpu_count()}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scale", type=int, default=1, help="debug: 1/scale-size workload (numbers are then not the metric)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+    return run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -259,6 +259,16 @@ __global__ void spmm_combine_kernel(const uint32_t *__restrict__ split_row, cons
   }
 }
 
+// all-columns-present check of a feature CSR (Reddit: every row holds columns 0..n_cols-1), done on the device so
+// that 4*nnz bytes of indices are not pulled back over PCIe just to be scanned
+__global__ void dense_check_kernel(const uint32_t *__restrict__ indices, int64_t nnz, uint32_t n_cols,
+                                   unsigned int *__restrict__ mismatch) {
+  bool bad = false;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < nnz; e += (int64_t)gridDim.x * blockDim.x)
+    bad |= __ldg(indices + e) != (uint32_t)(e % n_cols);
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(mismatch, 1u);
+}
+
 using KernelFn = void (*)(const uint4 *, const uint32_t *, uint32_t *, int, const uint32_t *, const float *,
                           const uint32_t *, const float *, float *, float *, int);
 
@@ -461,15 +471,24 @@ int gcnb_csc_create(const uint32_t *d_indptr, const uint32_t *d_indices, int64_t
   // dense detection needs only indptr first: every row must hold exactly n_cols entries
   bool dense = n_cols > 0 && nnz == n_rows * n_cols;
   for (int64_t r = 0; dense && r < n_rows; r++) dense = (indptr[r + 1] - indptr[r]) == (uint32_t)n_cols;
-  std::vector<uint32_t> indices((size_t)nnz);
-  if (nnz) {
-    GCNB_CHECK(cudaMemcpyAsync(indices.data(), d_indices, (size_t)nnz * 4, cudaMemcpyDeviceToHost, stream));
+  if (dense && nnz) {
+    unsigned int *d_flag = nullptr, h_flag = 0;
+    GCNB_CHECK(cudaMalloc((void **)&d_flag, 4));
+    GCNB_CHECK(cudaMemsetAsync(d_flag, 0, 4, stream));
+    const int blocks = (int)std::min<int64_t>((nnz + 255) / 256, (int64_t)std::max(1, device_info().sm_count) * 16);
+    dense_check_kernel<<<blocks, 256, 0, stream>>>(d_indices, nnz, (uint32_t)n_cols, d_flag);
+    GCNB_CHECK(cudaMemcpyAsync(&h_flag, d_flag, 4, cudaMemcpyDeviceToHost, stream));
     GCNB_CHECK(cudaStreamSynchronize(stream));
+    cudaFree(d_flag);
+    dense = (h_flag == 0);
   }
-  if (dense)
-    for (int64_t e = 0; dense && e < nnz; e++) dense = indices[e] == (uint32_t)(e % n_cols);
   c->is_dense = dense ? 1 : 0;
   if (!dense) {
+    std::vector<uint32_t> indices((size_t)nnz);
+    if (nnz) {
+      GCNB_CHECK(cudaMemcpyAsync(indices.data(), d_indices, (size_t)nnz * 4, cudaMemcpyDeviceToHost, stream));
+      GCNB_CHECK(cudaStreamSynchronize(stream));
+    }
     // stable counting sort by column: entries of a column stay in ascending row order => fixed summation order
     std::vector<uint32_t> colptr((size_t)n_cols + 1, 0), rowidx((size_t)nnz), perm((size_t)nnz);
     for (int64_t e = 0; e < nnz; e++) colptr[indices[e] + 1]++;

@@ -138,6 +138,10 @@ class GCN {
   void set_use_cuda_graph(bool on);
   void set_reorder(bool on);  // allow the (A*a)*W association (default on)
   size_t launches_per_epoch() const;
+  size_t launches_total() const;
+  void set_time_graphsum(bool on);                        // event pair around every GraphSum launch
+  void graphsum_timing(double *ms_total, size_t *calls) const;
+  float timed_epochs(natural n_epochs, bool with_eval);   // ms between CUDA events on the engine stream
   natural epochs_run() const;
 };
 #endif

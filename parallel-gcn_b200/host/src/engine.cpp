@@ -217,5 +217,20 @@ int gcnb_gcn_set_mask(gcnb_gcn *g, int site, const uint8_t *host_mask) {
   return 0;
 }
 int64_t gcnb_gcn_launches_per_epoch(const gcnb_gcn *g) { return g ? (int64_t)g->gcn->launches_per_epoch() : -1; }
+int64_t gcnb_gcn_launches_total(const gcnb_gcn *g) { return g ? (int64_t)g->gcn->launches_total() : -1; }
+int gcnb_gcn_timed_epochs(gcnb_gcn *g, int n_epochs, int with_eval, int time_graphsum, float out[4]) {
+  if (!g || !out || n_epochs < 0) return GCNB_E_BADARG;
+  g->gcn->set_time_graphsum(time_graphsum != 0);
+  const size_t l0 = g->gcn->launches_total();
+  out[0] = g->gcn->timed_epochs((natural)n_epochs, with_eval != 0);
+  double ms = 0;
+  size_t calls = 0;
+  g->gcn->graphsum_timing(&ms, &calls);
+  out[1] = (float)ms;
+  out[2] = (float)calls;
+  out[3] = (float)(g->gcn->launches_total() - l0);
+  g->gcn->set_time_graphsum(false);
+  return 0;
+}
 
 }  // extern "C"

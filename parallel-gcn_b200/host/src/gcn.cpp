@@ -98,9 +98,43 @@ struct GCNEngineState {
   natural cur_num_samples = 0;
   std::vector<dev_shared_ptr<unsigned char>> ext_masks;  // injected keep-masks per dropout site (may be null)
   bool quiet = false, use_graph = false, allow_reorder = true;
-  size_t launches = 0, launches_last_epoch = 0;
+  size_t launches = 0, launches_last_epoch = 0;  // CUDA kernels launched (memsets / copies not counted)
   natural epochs_run = 0;
+  int graph_spmm_kernels = 1, feat_spmm_kernels = 1, feat_csc_kernels = 1;  // 1 + combine kernel when rows are split
+  // optional per-launch timing of the GraphSum SpMM (bench.py roofline): event pairs on the engine stream
+  bool time_graphsum = false;
+  std::vector<cudaEvent_t> gs_events;
+  size_t gs_used = 0;
+  double gs_ms_total = 0;
+  size_t gs_calls = 0;
+  void graphsum(const real *gv, const real *in, real *out, natural dim) {
+    if (time_graphsum) {
+      if (gs_used + 2 > gs_events.size())
+        for (int i = 0; i < 2; i++) {
+          cudaEvent_t e;
+          CHECK_CUDA_ERROR(cudaEventCreate(&e));
+          gs_events.push_back(e);
+        }
+      CHECK_CUDA_ERROR(cudaEventRecord(gs_events[gs_used], stream));
+    }
+    GCNB_CALL(gcnb_spmm_f32(graph_plan, gv, nullptr, in, out, dim, stream));
+    if (time_graphsum) {
+      CHECK_CUDA_ERROR(cudaEventRecord(gs_events[gs_used + 1], stream));
+      gs_used += 2;
+    }
+    launches += graph_spmm_kernels;
+  }
+  void collect_graphsum_times() {  // after a stream sync
+    for (size_t i = 0; i + 1 < gs_used; i += 2) {
+      float ms = 0;
+      CHECK_CUDA_ERROR(cudaEventElapsedTime(&ms, gs_events[i], gs_events[i + 1]));
+      gs_ms_total += ms;
+      gs_calls++;
+    }
+    gs_used = 0;
+  }
   ~GCNEngineState() {
+    for (auto e : gs_events) cudaEventDestroy(e);
     if (feat_csc_plan) gcnb_spmm_plan_destroy(feat_csc_plan);
     if (feat_csc) gcnb_csc_destroy(feat_csc);
     if (feat_plan) gcnb_spmm_plan_destroy(feat_plan);
@@ -149,6 +183,18 @@ void GCN::init(bool quiet) {
     GCNB_CALL(gcnb_spmm_plan_create(dev_data.dev_feature_index.dev_indptr.get(),
                                     dev_data.dev_feature_index.dev_indices.get(), N, F, 0, st->stream, &st->feat_plan));
     GCNB_CALL(gcnb_spmm_plan_create(colptr, rowidx, F, N, 0, st->stream, &st->feat_csc_plan));
+  }
+
+  {
+    int64_t info[8];
+    GCNB_CALL(gcnb_spmm_plan_info(st->graph_plan, info));
+    st->graph_spmm_kernels = 1 + (info[3] > 0);
+    if (st->feat_plan) {
+      GCNB_CALL(gcnb_spmm_plan_info(st->feat_plan, info));
+      st->feat_spmm_kernels = 1 + (info[3] > 0);
+      GCNB_CALL(gcnb_spmm_plan_info(st->feat_csc_plan, info));
+      st->feat_csc_kernels = 1 + (info[3] > 0);
+    }
   }
 
   // variables, in the reference's order: input, {layer_var1, weight, layer_var2} per layer (src/gcn.cu:47-142)
@@ -218,6 +264,35 @@ void GCN::set_reorder(bool on) {
   }
 }
 size_t GCN::launches_per_epoch() const { return st->launches_last_epoch; }
+size_t GCN::launches_total() const { return st->launches; }
+void GCN::set_time_graphsum(bool on) {
+  st->time_graphsum = on;
+  st->gs_ms_total = 0;
+  st->gs_calls = 0;
+}
+void GCN::graphsum_timing(double *ms_total, size_t *calls) const {
+  *ms_total = st->gs_ms_total;
+  *calls = st->gs_calls;
+}
+float GCN::timed_epochs(natural n_epochs, bool with_eval) {
+  // K epochs bracketed by CUDA events on the engine's own stream (bench.py: device time, not wall clock)
+  cudaEvent_t e0, e1;
+  CHECK_CUDA_ERROR(cudaEventCreate(&e0));
+  CHECK_CUDA_ERROR(cudaEventCreate(&e1));
+  CHECK_CUDA_ERROR(cudaStreamSynchronize(st->stream));
+  CHECK_CUDA_ERROR(cudaEventRecord(e0, st->stream));
+  for (natural i = 0; i < n_epochs; i++) {
+    train_epoch();
+    if (with_eval) eval(2);
+  }
+  CHECK_CUDA_ERROR(cudaEventRecord(e1, st->stream));
+  CHECK_CUDA_ERROR(cudaEventSynchronize(e1));
+  float ms = 0;
+  CHECK_CUDA_ERROR(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return ms;
+}
 natural GCN::epochs_run() const { return st->epochs_run; }
 
 void GCN::set_external_masks(const std::vector<const unsigned char *> &host_masks) {
@@ -263,30 +338,29 @@ void GCN::forward_pass(bool training, natural split, cudaStream_t s) {
   }
   {
     GCNLayer &l0 = st->layers[0];
-    if (st->feat_dense)
+    if (st->feat_dense) {
       GCNB_CALL(gcnb_matmul_nn_f32(xvals, weights[0]->dev_data.get(), l0.pre->dev_data.get(), N, F, l0.out_dim, s));
-    else
+      st->launches += 1;
+    } else {
       GCNB_CALL(gcnb_spmm_f32(st->feat_plan, xvals, nullptr, weights[0]->dev_data.get(), l0.pre->dev_data.get(),
                               l0.out_dim, s));
-    GCNB_CALL(gcnb_spmm_f32(st->graph_plan, dev_data.dev_graph_value.get(), nullptr, l0.pre->dev_data.get(),
-                            l0.z->dev_data.get(), l0.out_dim, s));
-    st->launches += 2 + 2;  // + plan counter reset / combine nodes are counted as part of the spmm call
+      st->launches += st->feat_spmm_kernels;
+    }
+    st->graphsum(dev_data.dev_graph_value.get(), l0.pre->dev_data.get(), l0.z->dev_data.get(), l0.out_dim);
   }
   for (natural l = 0; l < L; l++) {
     GCNLayer &ly = st->layers[l];
     if (l > 0) {
       const real *a = st->layers[l - 1].z->dev_data.get();
       if (ly.reorder) {
-        GCNB_CALL(gcnb_spmm_f32(st->graph_plan, dev_data.dev_graph_value.get(), nullptr, a, ly.pre->dev_data.get(),
-                                ly.in_dim, s));
+        st->graphsum(dev_data.dev_graph_value.get(), a, ly.pre->dev_data.get(), ly.in_dim);
         GCNB_CALL(gcnb_matmul_nn_f32(ly.pre->dev_data.get(), weights[l]->dev_data.get(), ly.z->dev_data.get(), N,
                                      ly.in_dim, ly.out_dim, s));
       } else {
         GCNB_CALL(gcnb_matmul_nn_f32(a, weights[l]->dev_data.get(), ly.pre->dev_data.get(), N, ly.in_dim, ly.out_dim, s));
-        GCNB_CALL(gcnb_spmm_f32(st->graph_plan, dev_data.dev_graph_value.get(), nullptr, ly.pre->dev_data.get(),
-                                ly.z->dev_data.get(), ly.out_dim, s));
+        st->graphsum(dev_data.dev_graph_value.get(), ly.pre->dev_data.get(), ly.z->dev_data.get(), ly.out_dim);
       }
-      st->launches += 3;
+      st->launches += 1;
     }
     if (l + 1 < L) {
       const real p = params->dropouts[l + 1];
@@ -317,32 +391,35 @@ void GCN::backward_pass(cudaStream_t s) {
       GCNB_CALL(gcnb_matmul_tn_f32(ly.pre->dev_data.get(), g, weights[l]->dev_grad.get(), N, ly.in_dim, ly.out_dim,
                                    st->tn_ws.get(), st->tn_ws_bytes, s));
       GCNB_CALL(gcnb_matmul_nt_f32(g, weights[l]->dev_data.get(), ly.pre->dev_grad.get(), N, ly.in_dim, ly.out_dim, s));
-      GCNB_CALL(gcnb_spmm_f32(st->graph_plan, gv, nullptr, ly.pre->dev_grad.get(), prev.z->dev_grad.get(), ly.in_dim, s));
+      st->graphsum(gv, ly.pre->dev_grad.get(), prev.z->dev_grad.get(), ly.in_dim);
     } else {
       // z = A_hat h, h = a W  =>  dh = A_hat g ; dW = a^T dh ; da = dh W^T   (src/module.cu:200-210, :456-472)
-      GCNB_CALL(gcnb_spmm_f32(st->graph_plan, gv, nullptr, g, ly.pre->dev_grad.get(), ly.out_dim, s));
+      st->graphsum(gv, g, ly.pre->dev_grad.get(), ly.out_dim);
       GCNB_CALL(gcnb_matmul_tn_f32(prev.z->dev_data.get(), ly.pre->dev_grad.get(), weights[l]->dev_grad.get(), N,
                                    ly.in_dim, ly.out_dim, st->tn_ws.get(), st->tn_ws_bytes, s));
       GCNB_CALL(gcnb_matmul_nt_f32(ly.pre->dev_grad.get(), weights[l]->dev_data.get(), prev.z->dev_grad.get(), N,
                                    ly.in_dim, ly.out_dim, s));
     }
     GCNB_CALL(gcnb_relu_dropout_bwd_f32(prev.z->dev_grad.get(), prev.mask.get(), prev.z->size, params->dropouts[l], s));
-    st->launches += 6;
+    st->launches += 2 + 1 + 1;  // split-K weight gradient (2 kernels), dA product, mask kernel
     g = prev.z->dev_grad.get();
   }
   GCNLayer &l0 = st->layers[0];
-  GCNB_CALL(gcnb_spmm_f32(st->graph_plan, gv, nullptr, g, l0.pre->dev_grad.get(), l0.out_dim, s));
-  if (st->feat_dense)
+  st->graphsum(gv, g, l0.pre->dev_grad.get(), l0.out_dim);
+  if (st->feat_dense) {
     GCNB_CALL(gcnb_matmul_tn_f32(st->x_train_vals, l0.pre->dev_grad.get(), weights[0]->dev_grad.get(), N, F, l0.out_dim,
                                  st->tn_ws.get(), st->tn_ws_bytes, s));
-  else
+    st->launches += 2;
+  } else {
     GCNB_CALL(gcnb_spmm_f32(st->feat_csc_plan, st->x_train_vals, st->feat_perm, l0.pre->dev_grad.get(),
                             weights[0]->dev_grad.get(), l0.out_dim, s));
-  st->launches += 4;
+    st->launches += st->feat_csc_kernels;
+  }
 }
 
 std::pair<real, real> GCN::finalize(cudaStream_t s) const {
   CHECK_CUDA_ERROR(cudaStreamSynchronize(s));  // the one host sync per pass (src/gcn.cu:443)
+  if (st->time_graphsum) st->collect_graphsum_times();
   const real *r = st->host_result.get();
   const natural total = st->cur_num_samples;
   natural wrong;
