@@ -99,6 +99,8 @@ GCNB_API int gcnb_matmul_tn_f32(const float *d_A, const float *d_dC, float *d_dB
 #define GCNB_MAX_RNG_HIST 16
 typedef struct {
   uint32_t seed;
+  uint32_t group_offset; /* row-partitioned ranks: a local slab whose element 0 is GLOBAL element e0 passes        */
+  uint32_t elem_lead;    /* group_offset = e0 / 4 and elem_lead = e0 % 4 (masks then do not depend on the partition) */
   int n_hist;
   uint32_t hist_groups[GCNB_MAX_RNG_HIST]; /* ceil(size/4) of an earlier RNG consumer */
   uint32_t hist_count[GCNB_MAX_RNG_HIST];  /* how many times it has run */

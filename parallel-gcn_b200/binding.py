@@ -23,7 +23,7 @@ MAX_TENSORS = 16
 
 
 class RngT(C.Structure):
-    _fields_ = [("seed", U32), ("n_hist", I32), ("hist_groups", U32 * MAX_RNG_HIST), ("hist_count", U32 * MAX_RNG_HIST)]
+    _fields_ = [("seed", U32), ("group_offset", U32), ("elem_lead", U32), ("n_hist", I32), ("hist_groups", U32 * MAX_RNG_HIST), ("hist_count", U32 * MAX_RNG_HIST)]
 
 
 class AdamTensorsT(C.Structure):
@@ -54,6 +54,7 @@ _sig("gcnb_matmul_tn_workspace", I64, [I64, I32, I32])
 _sig("gcnb_matmul_tn_f32", I32, [P, P, P, I64, I32, I32, P, I64, P])
 _sig("gcnb_glorot_f32", I32, [P, I64, U32, U32, P, P])
 _sig("gcnb_dropout_fwd_f32", I32, [P, P, P, I64, F32, P, P])
+_sig("gcnb_dropout_fwd_oop_f32", I32, [P, P, P, P, I64, F32, P, P])
 _sig("gcnb_dropout_bwd_f32", I32, [P, P, I64, F32, P])
 _sig("gcnb_relu_fwd_f32", I32, [P, P, I64, I32, P])
 _sig("gcnb_relu_bwd_f32", I32, [P, P, I64, P])
@@ -91,10 +92,11 @@ def device_check():
     return n.value
 
 
-def make_rng(seed, history=()):
-    """history: iterable of (n_elements_of_an_earlier_rng_op, times_it_ran)."""
+def make_rng(seed, history=(), elem_offset=0):
+    """history: iterable of (n_elements_of_an_earlier_rng_op, times_it_ran); elem_offset: global index of local element 0."""
     r = RngT()
     r.seed = int(seed) & 0xFFFFFFFF
+    r.group_offset, r.elem_lead = elem_offset // 4, elem_offset % 4
     merged = {}
     for size, count in history:
         g = (int(size) + 3) // 4
@@ -132,7 +134,7 @@ class SpmmPlan:
         return C_out
 
     def close(self):
-        if getattr(self, "h", None):
+        if getattr(self, "h", None) and lib is not None:
             lib.gcnb_spmm_plan_destroy(self.h)
             self.h = None
 
@@ -165,7 +167,7 @@ class Csc:
         if self.plan is not None:
             self.plan.close()
             self.plan = None
-        if getattr(self, "h", None):
+        if getattr(self, "h", None) and lib is not None:
             lib.gcnb_csc_destroy(self.h)
             self.h = None
 

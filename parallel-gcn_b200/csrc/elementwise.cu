@@ -41,24 +41,26 @@ __global__ void dropout_fwd_kernel(const float *src, float *x, uint8_t *__restri
                                    int training, gcnb_rng_t rng) {
   // src == x for the in-place module semantics; src != x keeps the source intact (GCN driver: features are never
   // overwritten, so no set_input restore copy is needed)
-  const bool vec_ok = (((uintptr_t)x | (uintptr_t)src) % 16 == 0);
+  // a rank's slab may start inside a Philox group (elem_lead = global index of local element 0, mod 4)
+  const int lead = (int)rng.elem_lead;
+  const bool vec_ok = lead == 0 && (((uintptr_t)x | (uintptr_t)src) % 16 == 0);
   for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < groups; g += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t j = g * 4;
-    const bool full = (j + 4 <= size);
+    const int64_t j = g * 4 - lead;
+    const bool full = (j >= 0 && j + 4 <= size);
     float v[4];
     if (full && vec_ok) {
       const float4 t = *reinterpret_cast<const float4 *>(src + j);
       v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
     } else {
 #pragma unroll
-      for (int k = 0; k < 4; k++) v[k] = (j + k < size) ? src[j + k] : 0.f;
+      for (int k = 0; k < 4; k++) v[k] = (j + k >= 0 && j + k < size) ? src[j + k] : 0.f;
     }
     bool keep[4] = {true, true, true, true};
     if (training) {
       if (ext) {
 #pragma unroll
-        for (int k = 0; k < 4; k++) keep[k] = (j + k < size) ? (ext[j + k] != 0) : false;
-      } else {
+        for (int k = 0; k < 4; k++) keep[k] = (j + k >= 0 && j + k < size) ? (ext[j + k] != 0) : false;
+      } else if (p > 0.f) {  // p == 0 keeps everything (u is in (0,1]); the caller still accounts the draw
         float u[4];
         rng_uniform4(rng, (uint32_t)g, u);
 #pragma unroll
@@ -83,15 +85,15 @@ __global__ void dropout_fwd_kernel(const float *src, float *x, uint8_t *__restri
     } else {
 #pragma unroll
       for (int k = 0; k < 4; k++)
-        if (j + k < size) x[j + k] = v[k];
+        if (j + k >= 0 && j + k < size) x[j + k] = v[k];
     }
     if (mask && training) {
-      if (full && ((uintptr_t)mask % 4 == 0)) {
+      if (full && lead == 0 && ((uintptr_t)mask % 4 == 0)) {
         *reinterpret_cast<uchar4 *>(mask + j) = make_uchar4(m[0], m[1], m[2], m[3]);
       } else {
 #pragma unroll
         for (int k = 0; k < 4; k++)
-          if (j + k < size) mask[j + k] = m[k];
+          if (j + k >= 0 && j + k < size) mask[j + k] = m[k];
       }
     }
   }
@@ -206,8 +208,9 @@ int gcnb_dropout_fwd_oop_f32(const float *d_src, float *d_dst, uint8_t *d_mask, 
                              int64_t size, float p, const gcnb_rng_t *rng, gcnb_stream_t s) {
   if (!d_src || !d_dst || size < 0 || (!rng && !d_ext_mask)) return GCNB_E_BADARG;
   if (size == 0) return 0;
-  const int64_t groups = (size + 3) / 4;
   gcnb_rng_t r = rng ? *rng : gcnb_rng_t{};
+  if (r.elem_lead > 3) return GCNB_E_BADARG;
+  const int64_t groups = (size + r.elem_lead + 3) / 4;
   dropout_fwd_kernel<false><<<grid_for(groups), kT, 0, as_stream(s)>>>(d_src, d_dst, d_mask, d_ext_mask, size, groups,
                                                                         p, dropout_scale(p), 1, r);
   GCNB_LAUNCH_CHECK();
@@ -247,8 +250,9 @@ int gcnb_relu_dropout_fwd_f32(float *d_x, uint8_t *d_mask, const uint8_t *d_ext_
                               int training, const gcnb_rng_t *rng, gcnb_stream_t s) {
   if (!d_x || size < 0 || (training && !d_mask) || (training && !rng && !d_ext_mask)) return GCNB_E_BADARG;
   if (size == 0) return 0;
-  const int64_t groups = (size + 3) / 4;
   gcnb_rng_t r = rng ? *rng : gcnb_rng_t{};
+  if (r.elem_lead > 3) return GCNB_E_BADARG;
+  const int64_t groups = (size + r.elem_lead + 3) / 4;
   dropout_fwd_kernel<true><<<grid_for(groups), kT, 0, as_stream(s)>>>(d_x, d_x, d_mask, d_ext_mask, size, groups, p,
                                                                        dropout_scale(p), training, r);
   GCNB_LAUNCH_CHECK();

@@ -37,7 +37,8 @@ __device__ __forceinline__ uint32_t rng_draw_index(const gcnb_rng_t &rng, uint32
 
 // four uniforms in (0,1] for element group g; same expression as cuRAND's _curand_uniform so nvcc contracts it
 // to the same single FMA.
-__device__ __forceinline__ void rng_uniform4(const gcnb_rng_t &rng, uint32_t g, float u[4]) {
+__device__ __forceinline__ void rng_uniform4(const gcnb_rng_t &rng, uint32_t g_local, float u[4]) {
+  const uint32_t g = g_local + rng.group_offset;  // global element group (independent of the row partition)
   uint32_t x[4];
   philox4x32_10(rng_draw_index(rng, g), 0u, g, 0u, rng.seed, 0u, x);
 #pragma unroll

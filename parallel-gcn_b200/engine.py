@@ -206,7 +206,7 @@ class GCN:
         return int(lib.gcnb_gcn_launches_per_epoch(self.h))
 
     def close(self):
-        if getattr(self, "h", None):
+        if getattr(self, "h", None) and lib is not None:
             lib.gcnb_gcn_destroy(self.h)
             self.h = None
 

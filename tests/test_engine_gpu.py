@@ -179,3 +179,24 @@ def test_dense_feature_path_matches_sparse_path(O, eng):
         assert abs(te[0] - to[0]) <= 2e-5 * (1 + ep) * abs(to[0]) and abs(ve[0] - vo[0]) <= 2e-5 * (1 + ep) * abs(vo[0])
     assert_close(g.weight(0), og.W[0], rtol=1e-4, atol=1e-6, what="W0 dense path")
     g.close()
+
+
+def test_dist_driver_single_rank_matches_engine(O, eng, gcnb, dev, datasets):
+    """the multi-GPU driver (parallel_gcn_b200.dist.DistGCN, CUDA backend) at world size 1 reproduces the C++ engine:
+    same kernels, same Philox bookkeeping.  (world > 1 choreography: tests/test_dist_cpu.py with gloo; N-GPU run:
+    scripts/dist_check.py under torchrun.)"""
+    import importlib
+    dmod = importlib.import_module("parallel_gcn_b200.dist")
+    for name in ("cora", "citeseer"):
+        ds = eng.parse_dataset(ROOT, name)
+        part = dmod.partition_dataset(ds, 0, 1)
+        dg = dmod.DistGCN(part, dmod.CudaOps(gcnb, dev), dmod.Comm(None, 0, 1))
+        g = eng.GCN(ds)
+        for ep in range(4):
+            a, b = dg.train_epoch(), g.train_epoch()
+            va, vb = dg.eval(2), g.eval(2)
+            assert abs(a[0] - b[0]) <= 1e-6 * abs(b[0]) and a[1] == pytest.approx(b[1], abs=1e-7), (name, ep, a, b)
+            assert abs(va[0] - vb[0]) <= 1e-6 * abs(vb[0]) and va[1] == pytest.approx(vb[1], abs=1e-7)
+        for l in range(2):
+            assert_close(to_np(dg.W[l]), g.weight(l), rtol=1e-6, atol=1e-7, what="dist W%d" % l)
+        g.close()
