@@ -132,6 +132,29 @@ GCNB_API int gcnb_set_truth(int32_t *d_truth, const uint32_t *d_split, const int
                             uint32_t current_split, gcnb_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------
+ * First layer on a DENSE feature matrix (every svmlight row lists all F columns, e.g. Reddit's 602): the
+ * SparseMatmul::forward/backward products (src/module.cu:108-163) with Dropout(input) (src/module.cu:16-76) applied
+ * on the fly from a 1-bit/element keep mask -- X is streamed once per product, never rewritten, never restored
+ * (src/gcn.cu:181-200 copies it back before every eval).  d_bits == NULL means "no dropout" (eval).
+ * Supported when gcnb_dense_feat_supported(F, P): P in {8,16,32}, F <= 1024; otherwise use the generic products.
+ * ------------------------------------------------------------------------------------------------- */
+GCNB_API int gcnb_dense_feat_supported(int f, int p);
+/* Keep decisions (u >= p) of the n_rows*f elements, same Philox stream and lane order as gcnb_dropout_fwd_f32, stored
+ * 1 bit per element in the row-tile layout the two products bulk-copy: rows in tiles of 32, element (r, k) is bit
+ * (r % 32) * f + k of tile r / 32, every tile padded to a multiple of 16 bytes (gcnb_dropout_maskbits_words words). */
+GCNB_API int64_t gcnb_dropout_maskbits_words(int64_t n_rows, int f);
+GCNB_API int gcnb_dropout_maskbits(uint32_t *d_bits, int64_t n_rows, int f, float p, const gcnb_rng_t *rng,
+                                   gcnb_stream_t stream);
+/* out[n x p] = (X .* keep/(1-p_drop))[n x f] * W[f x p] */
+GCNB_API int gcnb_dense_feat_fwd_f32(const float *d_X, const uint32_t *d_bits, float p_drop, const float *d_W,
+                                     float *d_out, int64_t n, int f, int p, gcnb_stream_t stream);
+/* dW[f x p] = (X .* keep/(1-p_drop))^T * dH[n x p]; per-CTA row-slab partials in d_ws, reduced in slab order */
+GCNB_API int64_t gcnb_dense_feat_tn_workspace(int64_t n, int f, int p);
+GCNB_API int gcnb_dense_feat_tn_f32(const float *d_X, const uint32_t *d_bits, float p_drop, const float *d_dH,
+                                    float *d_dW, int64_t n, int f, int p, void *d_ws, int64_t ws_bytes,
+                                    gcnb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------
  * CrossEntropyLoss::forward (src/module.cu:484-541) + GCN::get_accuracy (src/gcn.cu:264-289) in one pass.
  * In-place logits -= rowmax for rows with truth >= 0 (API-visible side effect kept); if training:
  * grad = softmax/num_samples, grad[truth] -= 1.0/num_samples (double), rows with truth < 0 get grad 0.

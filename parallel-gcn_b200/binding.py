@@ -52,6 +52,12 @@ _sig("gcnb_matmul_nn_f32", I32, [P, P, P, I64, I32, I32, P])
 _sig("gcnb_matmul_nt_f32", I32, [P, P, P, I64, I32, I32, P])
 _sig("gcnb_matmul_tn_workspace", I64, [I64, I32, I32])
 _sig("gcnb_matmul_tn_f32", I32, [P, P, P, I64, I32, I32, P, I64, P])
+_sig("gcnb_dense_feat_supported", I32, [I32, I32])
+_sig("gcnb_dropout_maskbits_words", I64, [I64, I32])
+_sig("gcnb_dropout_maskbits", I32, [P, I64, I32, F32, P, P])
+_sig("gcnb_dense_feat_fwd_f32", I32, [P, P, F32, P, P, I64, I32, I32, P])
+_sig("gcnb_dense_feat_tn_workspace", I64, [I64, I32, I32])
+_sig("gcnb_dense_feat_tn_f32", I32, [P, P, F32, P, P, I64, I32, I32, P, I64, P])
 _sig("gcnb_glorot_f32", I32, [P, I64, U32, U32, P, P])
 _sig("gcnb_dropout_fwd_f32", I32, [P, P, P, I64, F32, P, P])
 _sig("gcnb_dropout_fwd_oop_f32", I32, [P, P, P, P, I64, F32, P, P])
@@ -203,6 +209,23 @@ def matmul_tn(A, dC, dB, m, n, p, ws=None):
         ws = torch.empty((need + 3) // 4, dtype=torch.float32, device=A.device)
     check(lib.gcnb_matmul_tn_f32(ptr(A), ptr(dC), ptr(dB), m, n, p, ptr(ws), ws.numel() * ws.element_size(), stream()))
     return dB
+
+
+def dropout_maskbits(bits, n_rows, f, p, rng):
+    check(lib.gcnb_dropout_maskbits(ptr(bits), n_rows, f, p, C.byref(rng), stream()))
+
+
+def dense_feat_fwd(X, bits, p_drop, W, out, n, f, p):
+    check(lib.gcnb_dense_feat_fwd_f32(ptr(X), ptr(bits), p_drop, ptr(W), ptr(out), n, f, p, stream()))
+
+
+def dense_feat_tn(X, bits, p_drop, dH, dW, n, f, p, ws=None):
+    import torch
+    need = lib.gcnb_dense_feat_tn_workspace(n, f, p)
+    if ws is None or ws.numel() * ws.element_size() < need:
+        ws = torch.empty((need + 3) // 4, dtype=torch.float32, device=X.device)
+    check(lib.gcnb_dense_feat_tn_f32(ptr(X), ptr(bits), p_drop, ptr(dH), ptr(dW), n, f, p, ptr(ws),
+                                     ws.numel() * ws.element_size(), stream()))
 
 
 def glorot(w, rows, cols, rng):

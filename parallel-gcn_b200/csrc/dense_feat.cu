@@ -1,0 +1,420 @@
+// dense_feat.cu -- the first layer when the feature matrix is dense (every svmlight row lists all F columns, as
+// Reddit's 602 do): X[N x F] * W0[F x P] and its weight gradient X^T * dH, with the input dropout applied on the fly
+// from a 1-bit/element keep mask instead of materialising a dropped copy of X.
+//
+// Reference path being replaced (per training epoch, Reddit): Dropout::forward rewrites the 561 MB input in place and
+// pulls 2.2 GB of Philox state through HBM (src/module.cu:16-76), SparseMatmul::forward re-reads values + 561 MB of
+// column indices (src/module.cu:108-132), SparseMatmul::backward issues Fnnz*H atomicAdds (src/module.cu:136-152), and
+// every eval first restores the input with a 1.1 GB copy (src/gcn.cu:181-200).  Here: one Philox pass writes 17.5 MB of
+// mask bits; forward and backward each stream X exactly once (561 MB, the HBM roofline of these two kernels).
+//
+//   dropout_maskbits_kernel : bit j of the mask = keep decision of element j (same Philox stream/lanes as Dropout)
+//   dense_feat_fwd_kernel   : warp = R rows x all P columns, lanes stride over k; W0 staged in shared memory (padded
+//                             rows: conflict-free LDS.128); 64 accumulators per lane, transposing butterfly reduction
+//   dense_feat_tn_kernel    : thread = FPT features x P columns, CTAs own row slabs; partials reduced in slab order
+//                             (deterministic, no atomics)
+#include <algorithm>
+
+#include "common.cuh"
+#include "philox.cuh"
+
+using namespace gcnb;
+
+namespace {
+
+constexpr int kT = 256;
+
+constexpr int TR = 32;  // rows per tile (8 warps x 4 rows in the forward kernel)
+
+// ---- 1 bit per element keep mask, in the tile layout the two products consume ----------------------------------------
+// Rows are grouped in tiles of TR = 32; inside a tile element (r, k) is bit idx = (r % 32) * F + k, i.e. the tile's
+// elements in memory order, and every tile starts on a 16-byte boundary (WPT words per tile, padded) so that a tile's
+// mask is one bulk copy.  Global element of (tile, idx) = tile * 32 * F + idx.
+__host__ __device__ inline int64_t mask_words_per_tile(int F) { return ((((int64_t)TR * F + 31) / 32) + 3) & ~(int64_t)3; }
+
+__global__ void dropout_maskbits_kernel(uint32_t *__restrict__ bits, int64_t size, int F, int64_t wpt, int64_t total_words,
+                                        float p, gcnb_rng_t rng) {
+  const int64_t tile_elems = (int64_t)TR * F;
+  const uint32_t lead = rng.elem_lead;
+  for (int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; w < total_words; w += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t tile = w / wpt;
+    const int64_t idx0 = (w - tile * wpt) * 32;            // first bit of this word inside the tile
+    int64_t nvalid = min((int64_t)32, tile_elems - idx0);  // padding words / bits stay zero
+    const int64_t e0 = tile * tile_elems + idx0;           // local element index of bit 0
+    nvalid = min(nvalid, size - e0);
+    uint32_t out = 0;
+    if (nvalid > 0) {
+      const uint64_t pos0 = (uint64_t)e0 + lead;  // position counted from the first global group of this call
+      const uint32_t g0 = (uint32_t)(pos0 >> 2);
+      const int shift = (int)(pos0 & 3);          // bit b of the word is lane (b + shift) & 3 of group g0 + (b + shift) / 4
+#pragma unroll 1
+      for (int gi = 0; gi < 9; gi++) {
+        const int b_first = gi * 4 - shift;       // word bit of lane 0 of this group
+        if (b_first >= nvalid) break;
+        float u[4];
+        rng_uniform4(rng, g0 + gi, u);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const int b = b_first + k;
+          if (b >= 0 && b < nvalid && u[k] >= p) out |= 1u << b;
+        }
+      }
+    }
+    bits[w] = out;
+  }
+}
+
+// keep-test on a tile's mask staged in shared memory (idx = position of the element inside the tile)
+__device__ __forceinline__ float masked(float x, const uint32_t *sbits, int idx, float scale) {
+  if (sbits == nullptr) return x;
+  return ((sbits[idx >> 5] >> (idx & 31)) & 1u) ? x * scale : 0.f;  // Dropout: x *= keep ? scale : 0
+}
+
+// ---- TMA bulk-copy plumbing (cp.async.bulk + mbarrier): a tile of TR consecutive rows of X is ONE contiguous block
+// of HBM, so each stage is a single bulk copy of up to 77 KB issued by one thread -- 150 KB in flight per SM, which
+// is what it takes to stream at HBM speed (per-lane LDG streams from 16 warps keep ~8 KB in flight and crawl).
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra.uni WAIT_DONE;\n"
+      "bra.uni WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// thread 0: start the copy of rows [r0, r0+nrows) of a row-major [.. x F] matrix into `dst`; the 16-byte-multiple
+// prefix goes through the bulk engine, a possible 4/8/12-byte tail by plain stores (visible after the next barrier)
+__device__ __forceinline__ void issue_tile(float *dst, const float *__restrict__ src, int64_t r0, int nrows, int F,
+                                           uint64_t *bar) {
+  const size_t bytes = (size_t)nrows * F * sizeof(float);
+  const uint32_t bulk = (uint32_t)(bytes & ~(size_t)15);
+  const float *g = src + (size_t)r0 * F;
+  mbar_expect_tx(bar, bulk);
+  if (bulk) bulk_g2s(dst, g, bulk, bar);
+  for (size_t i = bulk / 4; i < bytes / 4; i++) dst[i] = __ldg(g + i);
+}
+
+// ---- forward: out[N x P] = (X .* mask*scale)[N x F] * W[F x P] ---------------------------------------------------
+// persistent CTA (1 per SM): W0 resident in shared memory (padded rows: conflict-free LDS.128), X tiles double-buffered
+// by bulk copies; each warp owns R = 64/P... here TR/8 = 4 rows of the tile and all P columns, lanes stride over k.
+template <int P>
+__global__ void __launch_bounds__(kT, 1)
+dense_feat_fwd_kernel(const float *__restrict__ X, const uint32_t *__restrict__ bits, float scale,
+                      const float *__restrict__ W, float *__restrict__ out, int64_t N, int F) {
+  constexpr int R = TR / (kT / 32);  // rows per warp per tile
+  constexpr int WP = P + 4;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float *tile0 = reinterpret_cast<float *>(smem_raw);
+  float *tile1 = tile0 + (size_t)TR * F;
+  float *Ws = tile1 + (size_t)TR * F;
+  const int wpt = (int)mask_words_per_tile(F);
+  uint32_t *mb0 = reinterpret_cast<uint32_t *>(Ws + (((size_t)F * WP + 3) & ~(size_t)3));
+  uint32_t *mb1 = mb0 + wpt;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(mb1 + wpt);
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t ntiles = (N + TR - 1) / TR;
+  const int64_t first = blockIdx.x, stride = gridDim.x;
+  const int nbar = bits ? 2 : 1;  // arrivals per stage: X tile (+ mask tile)
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], nbar);
+    mbar_init(&bars[1], nbar);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto issue = [&](int s, int64_t t) {
+    issue_tile(s ? tile1 : tile0, X, t * TR, (int)min((int64_t)TR, N - t * TR), F, &bars[s]);
+    if (bits) {
+      mbar_expect_tx(&bars[s], (uint32_t)wpt * 4);
+      bulk_g2s(s ? mb1 : mb0, bits + t * wpt, (uint32_t)wpt * 4, &bars[s]);
+    }
+  };
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 2; s++) {
+      const int64_t t = first + s * stride;
+      if (t < ntiles) issue(s, t);
+    }
+  }
+  for (int i = threadIdx.x; i < F * P; i += kT) Ws[(i / P) * WP + (i % P)] = __ldg(W + i);
+  __syncthreads();
+  int it = 0;
+  for (int64_t t = first; t < ntiles; t += stride, it++) {
+    const int s = it & 1;
+    const float *tile = s ? tile1 : tile0;
+    const uint32_t *sbits = bits ? (s ? mb1 : mb0) : nullptr;
+    mbar_wait(&bars[s], (uint32_t)((it >> 1) & 1));
+    const int64_t r0 = t * TR + wib * R;
+    float acc[R * P];
+#pragma unroll
+    for (int i = 0; i < R * P; i++) acc[i] = 0.f;
+    const float *xrow = tile + (size_t)(wib * R) * F;
+#pragma unroll 2
+    for (int k = lane; k < F; k += 32) {
+      float x[R];
+#pragma unroll
+      for (int q = 0; q < R; q++) {
+        const int64_t r = r0 + q;
+        x[q] = (r < N) ? masked(xrow[(size_t)q * F + k], sbits, (wib * R + q) * F + k, scale) : 0.f;
+      }
+      const float4 *wr = reinterpret_cast<const float4 *>(Ws + k * WP);
+#pragma unroll
+      for (int c4 = 0; c4 < P / 4; c4++) {
+        const float4 w = wr[c4];
+#pragma unroll
+        for (int q = 0; q < R; q++) {
+          acc[q * P + c4 * 4 + 0] = fmaf(x[q], w.x, acc[q * P + c4 * 4 + 0]);
+          acc[q * P + c4 * 4 + 1] = fmaf(x[q], w.y, acc[q * P + c4 * 4 + 1]);
+          acc[q * P + c4 * 4 + 2] = fmaf(x[q], w.z, acc[q * P + c4 * 4 + 2]);
+          acc[q * P + c4 * 4 + 3] = fmaf(x[q], w.w, acc[q * P + c4 * 4 + 3]);
+        }
+      }
+    }
+    // transposing butterfly: R*P partial sums per lane -> every lane ends with R*P/32 complete outputs
+    constexpr int V = R * P;  // 64 for P=16, 128 for P=32, 32 for P=8
+#pragma unroll
+    for (int m = 16, n = V; m >= 1; m >>= 1, n >>= 1) {
+      const bool up = (lane & m) != 0;
+#pragma unroll
+      for (int i = 0; i < n / 2; i++) {
+        const float lo = acc[i], hi = acc[i + n / 2];
+        const float send = up ? lo : hi;
+        const float keep = up ? hi : lo;
+        acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+      }
+    }
+    constexpr int PER = V / 32;  // contiguous outputs per lane: indices lane*PER .. lane*PER+PER-1 (= q*P + c)
+    const int i0 = lane * PER;
+    const int q = i0 / P, c = i0 % P;
+    const int64_t r = r0 + q;
+    if (r < N) {
+#pragma unroll
+      for (int i = 0; i < PER; i++) out[r * P + c + i] = acc[i];
+    }
+    __syncthreads();  // everyone is done with this stage's tile
+    if (threadIdx.x == 0) {
+      const int64_t tn = t + 2 * stride;
+      if (tn < ntiles) issue(s, tn);
+    }
+  }
+}
+
+// ---- weight gradient: dW[F x P] = (X .* mask*scale)^T * dH[N x P] --------------------------------------------------
+// persistent CTA: thread t owns features t, t+256, ... (FPT of them) x all P columns in registers; X and dH tiles of
+// TR rows arrive by bulk copy; per-CTA partial written once at the end, reduced in CTA order by a second kernel.
+template <int P, int FPT>
+__global__ void __launch_bounds__(kT, 1)
+dense_feat_tn_kernel(const float *__restrict__ X, const uint32_t *__restrict__ bits, float scale,
+                     const float *__restrict__ dH, float *__restrict__ ws, int64_t N, int F) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float *tile0 = reinterpret_cast<float *>(smem_raw);
+  float *tile1 = tile0 + (size_t)TR * F;
+  float *dh0 = tile1 + (size_t)TR * F;
+  float *dh1 = dh0 + TR * P;
+  const int wpt = (int)mask_words_per_tile(F);
+  uint32_t *mb0 = reinterpret_cast<uint32_t *>(dh1 + TR * P);
+  uint32_t *mb1 = mb0 + wpt;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(mb1 + wpt);
+  const int tid = threadIdx.x;
+  const int64_t ntiles = (N + TR - 1) / TR;
+  const int64_t first = blockIdx.x, stride = gridDim.x;
+  const int nbar = bits ? 3 : 2;  // expect_tx arrivals per stage: X tile, dH tile (+ mask tile)
+  if (tid == 0) {
+    mbar_init(&bars[0], nbar);
+    mbar_init(&bars[1], nbar);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto issue = [&](int s, int64_t t) {
+    const int nr = (int)min((int64_t)TR, N - t * TR);
+    issue_tile(s ? tile1 : tile0, X, t * TR, nr, F, &bars[s]);
+    issue_tile(s ? dh1 : dh0, dH, t * TR, nr, P, &bars[s]);
+    if (bits) {
+      mbar_expect_tx(&bars[s], (uint32_t)wpt * 4);
+      bulk_g2s(s ? mb1 : mb0, bits + t * wpt, (uint32_t)wpt * 4, &bars[s]);
+    }
+  };
+  if (tid == 0) {
+    for (int s = 0; s < 2; s++) {
+      const int64_t t = first + s * stride;
+      if (t < ntiles) issue(s, t);
+    }
+  }
+  __syncthreads();
+  float acc[FPT][P];
+#pragma unroll
+  for (int f = 0; f < FPT; f++)
+#pragma unroll
+    for (int c = 0; c < P; c++) acc[f][c] = 0.f;
+  int it = 0;
+  for (int64_t t = first; t < ntiles; t += stride, it++) {
+    const int s = it & 1;
+    const float *tile = s ? tile1 : tile0;
+    const float4 *dh = reinterpret_cast<const float4 *>(s ? dh1 : dh0);
+    const uint32_t *sbits = bits ? (s ? mb1 : mb0) : nullptr;
+    mbar_wait(&bars[s], (uint32_t)((it >> 1) & 1));
+    const int nrows = (int)min((int64_t)TR, N - t * TR);
+#pragma unroll 4
+    for (int rr = 0; rr < nrows; rr++) {
+      float x[FPT];
+#pragma unroll
+      for (int f = 0; f < FPT; f++) {
+        const int j = tid + f * kT;
+        x[f] = (j < F) ? masked(tile[(size_t)rr * F + j], sbits, rr * F + j, scale) : 0.f;
+      }
+#pragma unroll
+      for (int c4 = 0; c4 < P / 4; c4++) {
+        const float4 g = dh[rr * (P / 4) + c4];
+#pragma unroll
+        for (int f = 0; f < FPT; f++) {
+          acc[f][c4 * 4 + 0] = fmaf(x[f], g.x, acc[f][c4 * 4 + 0]);
+          acc[f][c4 * 4 + 1] = fmaf(x[f], g.y, acc[f][c4 * 4 + 1]);
+          acc[f][c4 * 4 + 2] = fmaf(x[f], g.z, acc[f][c4 * 4 + 2]);
+          acc[f][c4 * 4 + 3] = fmaf(x[f], g.w, acc[f][c4 * 4 + 3]);
+        }
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      const int64_t tn = t + 2 * stride;
+      if (tn < ntiles) issue(s, tn);
+    }
+  }
+  float *dst = ws + (size_t)blockIdx.x * F * P;
+#pragma unroll
+  for (int f = 0; f < FPT; f++) {
+    const int j = tid + f * kT;
+    if (j < F) {
+#pragma unroll
+      for (int c4 = 0; c4 < P / 4; c4++)
+        *reinterpret_cast<float4 *>(dst + (size_t)j * P + c4 * 4) =
+            make_float4(acc[f][c4 * 4], acc[f][c4 * 4 + 1], acc[f][c4 * 4 + 2], acc[f][c4 * 4 + 3]);
+    }
+  }
+}
+
+__global__ void cta_partial_reduce_kernel(const float *__restrict__ ws, float *__restrict__ out, int64_t elems, int parts) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < elems; i += (int64_t)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int z = 0; z < parts; z++) s += __ldg(ws + (size_t)z * elems + i);  // ascending CTA (= row slab) order
+    out[i] = s;
+  }
+}
+
+int persistent_ctas(int64_t n) {
+  const int sm = std::max(1, device_info().sm_count);
+  return (int)std::max<int64_t>(1, std::min<int64_t>((n + TR - 1) / TR, (int64_t)sm));
+}
+size_t fwd_smem(int f, int p) {
+  return ((size_t)2 * TR * f + (size_t)f * (p + 4) + 4 + 2 * (size_t)mask_words_per_tile(f)) * sizeof(float) + 2 * sizeof(uint64_t) + 16;
+}
+size_t tn_smem(int f, int p) {
+  return ((size_t)2 * TR * f + (size_t)2 * TR * p + 2 * (size_t)mask_words_per_tile(f)) * sizeof(float) + 2 * sizeof(uint64_t) + 16;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gcnb_dense_feat_supported(int f, int p) {
+  return (p == 8 || p == 16 || p == 32) && f >= 1 && f <= 4 * kT && fwd_smem(f, p) <= 227 * 1024 && tn_smem(f, p) <= 227 * 1024;
+}
+
+int64_t gcnb_dropout_maskbits_words(int64_t n_rows, int f) { return ((n_rows + TR - 1) / TR) * mask_words_per_tile(f); }
+
+int gcnb_dropout_maskbits(uint32_t *d_bits, int64_t n_rows, int f, float p, const gcnb_rng_t *rng, gcnb_stream_t s) {
+  if (!d_bits || !rng || n_rows < 0 || f <= 0 || rng->elem_lead > 3) return GCNB_E_BADARG;
+  if (((uintptr_t)d_bits % 16) != 0) return GCNB_E_UNSUPPORTED;
+  if (n_rows == 0) return 0;
+  const int64_t wpt = mask_words_per_tile(f);
+  const int64_t words = ((n_rows + TR - 1) / TR) * wpt;
+  const int sm = std::max(1, device_info().sm_count);
+  const int blocks = (int)std::min<int64_t>((words + kT - 1) / kT, (int64_t)sm * 16);
+  dropout_maskbits_kernel<<<blocks, kT, 0, as_stream(s)>>>(d_bits, n_rows * f, f, wpt, words, p, *rng);
+  GCNB_LAUNCH_CHECK();
+  return 0;
+}
+
+int gcnb_dense_feat_fwd_f32(const float *d_X, const uint32_t *d_bits, float p_drop, const float *d_W, float *d_out,
+                            int64_t n, int f, int p, gcnb_stream_t s) {
+  if (!d_X || !d_W || !d_out || n < 0) return GCNB_E_BADARG;
+  if (!gcnb_dense_feat_supported(f, p) || ((uintptr_t)d_X % 16) != 0) return GCNB_E_UNSUPPORTED;
+  if (n == 0) return 0;
+  const float scale = (float)(1.0 / (1.0 - p_drop));
+  const size_t smem = fwd_smem(f, p);
+  const int blocks = persistent_ctas(n);
+  cudaStream_t st = as_stream(s);
+#define FWD(PP)                                                                                                   \
+  do {                                                                                                            \
+    GCNB_CHECK(cudaFuncSetAttribute(dense_feat_fwd_kernel<PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    dense_feat_fwd_kernel<PP><<<blocks, kT, smem, st>>>(d_X, d_bits, scale, d_W, d_out, n, f);                    \
+  } while (0)
+  if (p == 8) FWD(8);
+  else if (p == 16) FWD(16);
+  else FWD(32);
+#undef FWD
+  GCNB_LAUNCH_CHECK();
+  return 0;
+}
+
+int64_t gcnb_dense_feat_tn_workspace(int64_t n, int f, int p) {
+  return (int64_t)persistent_ctas(n) * f * p * (int64_t)sizeof(float);
+}
+
+int gcnb_dense_feat_tn_f32(const float *d_X, const uint32_t *d_bits, float p_drop, const float *d_dH, float *d_dW,
+                           int64_t n, int f, int p, void *d_ws, int64_t ws_bytes, gcnb_stream_t s) {
+  if (!d_X || !d_dH || !d_dW || n < 0) return GCNB_E_BADARG;
+  if (!gcnb_dense_feat_supported(f, p) || ((uintptr_t)d_dH % 16) != 0 || ((uintptr_t)d_X % 16) != 0)
+    return GCNB_E_UNSUPPORTED;
+  cudaStream_t st = as_stream(s);
+  if (n == 0) {
+    GCNB_CHECK(cudaMemsetAsync(d_dW, 0, (size_t)f * p * 4, st));
+    return 0;
+  }
+  const int ctas = persistent_ctas(n);
+  if (!d_ws || ws_bytes < (int64_t)ctas * f * p * 4 || ((uintptr_t)d_ws % 16) != 0) return GCNB_E_BADARG;
+  const float scale = (float)(1.0 / (1.0 - p_drop));
+  const int fpt = (f + kT - 1) / kT;
+  const size_t smem = tn_smem(f, p);
+#define TN(PP, FF)                                                                                                      \
+  do {                                                                                                                  \
+    GCNB_CHECK(cudaFuncSetAttribute(dense_feat_tn_kernel<PP, FF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    dense_feat_tn_kernel<PP, FF><<<ctas, kT, smem, st>>>(d_X, d_bits, scale, d_dH, (float *)d_ws, n, f);                  \
+  } while (0)
+#define TNP(PP)                 \
+  do {                          \
+    if (fpt == 1) TN(PP, 1);    \
+    else if (fpt == 2) TN(PP, 2); \
+    else if (fpt == 3) TN(PP, 3); \
+    else TN(PP, 4);             \
+  } while (0)
+  if (p == 8) TNP(8);
+  else if (p == 16) TNP(16);
+  else TNP(32);
+#undef TNP
+#undef TN
+  GCNB_LAUNCH_CHECK();
+  const int64_t elems = (int64_t)f * p;
+  cta_partial_reduce_kernel<<<(int)std::min<int64_t>((elems + 255) / 256, 1024), 256, 0, st>>>((const float *)d_ws, d_dW,
+                                                                                                 elems, ctas);
+  GCNB_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

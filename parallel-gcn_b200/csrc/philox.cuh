@@ -29,9 +29,8 @@ __host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1,
 // draw index of state g given the history table (see gcnb_rng_t)
 __device__ __forceinline__ uint32_t rng_draw_index(const gcnb_rng_t &rng, uint32_t g) {
   uint32_t t = 0;
-#pragma unroll
-  for (int i = 0; i < GCNB_MAX_RNG_HIST; i++)
-    if (i < rng.n_hist && rng.hist_groups[i] > g) t += rng.hist_count[i];
+  for (int i = 0; i < rng.n_hist; i++)  // n_hist is 2-4 in practice; the table lives in constant memory
+    if (rng.hist_groups[i] > g) t += rng.hist_count[i];
   return t;
 }
 

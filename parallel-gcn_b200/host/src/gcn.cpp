@@ -90,6 +90,13 @@ struct GCNEngineState {
   int feat_dense = 0;
   std::vector<GCNLayer> layers;
   const real *x_train_vals = nullptr;  // feature values the last training forward used (dropped or pristine)
+  // dense feature matrix: dropout applied on the fly from a bit mask (csrc/dense_feat.cu), X never copied
+  bool dense_fast = false;
+  dev_shared_ptr<natural> x_bits;
+  const natural *x_train_bits = nullptr;
+  real x_train_p = 0.f;
+  dev_shared_ptr<real> dense_tn_ws;
+  int64_t dense_tn_ws_bytes = 0;
   dev_shared_ptr<real> tn_ws;
   int64_t tn_ws_bytes = 0;
   dev_shared_ptr<natural> ce_ws, sumsq_ws;
@@ -227,6 +234,12 @@ void GCN::init(bool quiet) {
     tn_need = std::max(tn_need, gcnb_matmul_tn_workspace(N, ly.in_dim, ly.out_dim));
   }
   output = st->layers.back().z;
+  if (st->feat_dense && gcnb_dense_feat_supported((int)F, (int)dims[1])) {
+    st->dense_fast = true;
+    st->x_bits = dev_shared_ptr<natural>(gcnb_dropout_maskbits_words(N, (int)F));
+    st->dense_tn_ws_bytes = gcnb_dense_feat_tn_workspace(N, (int)F, (int)dims[1]);
+    st->dense_tn_ws = dev_shared_ptr<real>((st->dense_tn_ws_bytes + 3) / 4);
+  }
   st->tn_ws_bytes = tn_need;
   st->tn_ws = dev_shared_ptr<real>((tn_need + 3) / 4);
   st->ce_ws = dev_shared_ptr<natural>((gcnb_ce_workspace(N) + 3) / 4);
@@ -324,9 +337,27 @@ void GCN::forward_pass(bool training, natural split, cudaStream_t s) {
   set_truth(split, s);
   // ---- layer 0: features never overwritten; training writes the dropped copy into `input`
   const real *xvals = dev_data.dev_feature_value.get();
-  if (training) {
+  const natural *xbits = nullptr;
+  real xp = 0.f;
+  if (training && st->dense_fast && !st->ext_masks[0].get()) {
+    // dense features: only the keep bits are generated (17.5 MB for Reddit); X itself is streamed by the products
+    const real p0 = params->dropouts.front();
+    if (p0 > 0.f) {
+      const gcnb_rng_t rng = Variable::rng_descriptor();
+      GCNB_CALL(gcnb_dropout_maskbits(st->x_bits.get(), N, (int)F, p0, &rng, s));
+      st->launches++;
+      xbits = st->x_bits.get();
+      xp = p0;
+    }
+    Variable::rng_consume(input->size);
+    st->x_train_vals = xvals;
+    st->x_train_bits = xbits;
+    st->x_train_p = xp;
+  } else if (training) {
     const real p0 = params->dropouts.front();
     const unsigned char *ext = st->ext_masks[0].get();
+    st->x_train_bits = nullptr;
+    st->x_train_p = 0.f;
     if (p0 > 0.f || ext) {
       const gcnb_rng_t rng = Variable::rng_descriptor();
       GCNB_CALL(gcnb_dropout_fwd_oop_f32(xvals, input->dev_data.get(), nullptr, ext, input->size, p0, &rng, s));
@@ -338,7 +369,11 @@ void GCN::forward_pass(bool training, natural split, cudaStream_t s) {
   }
   {
     GCNLayer &l0 = st->layers[0];
-    if (st->feat_dense) {
+    if (st->dense_fast) {
+      GCNB_CALL(gcnb_dense_feat_fwd_f32(xvals, xbits, xp, weights[0]->dev_data.get(), l0.pre->dev_data.get(), N, (int)F,
+                                        (int)l0.out_dim, s));
+      st->launches += 1;
+    } else if (st->feat_dense) {
       GCNB_CALL(gcnb_matmul_nn_f32(xvals, weights[0]->dev_data.get(), l0.pre->dev_data.get(), N, F, l0.out_dim, s));
       st->launches += 1;
     } else {
@@ -406,7 +441,12 @@ void GCN::backward_pass(cudaStream_t s) {
   }
   GCNLayer &l0 = st->layers[0];
   st->graphsum(gv, g, l0.pre->dev_grad.get(), l0.out_dim);
-  if (st->feat_dense) {
+  if (st->dense_fast) {
+    GCNB_CALL(gcnb_dense_feat_tn_f32(st->x_train_vals, st->x_train_bits, st->x_train_p, l0.pre->dev_grad.get(),
+                                     weights[0]->dev_grad.get(), N, (int)F, (int)l0.out_dim, st->dense_tn_ws.get(),
+                                     st->dense_tn_ws_bytes, s));
+    st->launches += 2;
+  } else if (st->feat_dense) {
     GCNB_CALL(gcnb_matmul_tn_f32(st->x_train_vals, l0.pre->dev_grad.get(), weights[0]->dev_grad.get(), N, F, l0.out_dim,
                                  st->tn_ws.get(), st->tn_ws_bytes, s));
     st->launches += 2;

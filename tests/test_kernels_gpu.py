@@ -284,3 +284,48 @@ def test_set_truth(O, gcnb, dev, datasets):
         t = torch.empty(ds.num_nodes, dtype=torch.int32, device=dev)
         gcnb.set_truth(t, to_dev(ds.split, dev), to_dev(ds.label, dev), cur)
         assert (to_np(t) == want).all()
+
+
+@pytest.mark.parametrize("n,F,P,p,off", [(1003, 602, 16, 0.5, 0), (517, 24, 16, 0.5, 6), (300, 130, 32, 0.2, 0), (65, 640, 8, 0.9, 3),
+                                         (9, 5, 16, 0.0, 0)])
+def test_dense_feature_products_with_bit_mask(O, gcnb, dev, n, F, P, p, off):
+    """mask bits == Dropout's keep decisions (bit-exact); masked X*W and (masked X)^T*dH == oracle on the dropped copy."""
+    import torch
+    seed, hist = 19990304, [(F * P, 1), (n * F + off, 2)]
+    rng = np.random.default_rng(n * F)
+    X = rng.standard_normal((n, F)).astype(f32)
+    W = rng.standard_normal((F, P)).astype(f32)
+    dH = rng.standard_normal((n, P)).astype(f32)
+    size = n * F
+    full_mask = np.empty(off + size, u8)
+    O.lib.orc_dropout_mask_philox(off + size, p, seed, O._p(_oracle_draws(hist, off + size)), 1, O._p(full_mask))
+    mask = np.ascontiguousarray(full_mask[off:])
+    Xd = X.copy().ravel()
+    O.lib.orc_dropout_apply(size, O._p(Xd), O._p(mask), O.lib.orc_dropout_scale(p, 1))
+    want_out, want_dW, dummy = np.empty((n, P), f32), np.empty((F, P), f32), np.empty((n, F), f32)
+    O.lib.orc_matmul(n, F, P, O._p(Xd), O._p(W), O._p(want_out))
+    O.lib.orc_matmul_bwd(n, F, P, O._p(Xd), O._p(W), O._p(dH), O._p(dummy), O._p(want_dW))
+    assert gcnb.lib.gcnb_dense_feat_supported(F, P)
+    d_X, d_W, d_dH = to_dev(X, dev), to_dev(W, dev), to_dev(dH, dev)
+    words = gcnb.lib.gcnb_dropout_maskbits_words(n, F)
+    bits = torch.full((words,), -1, dtype=torch.int32, device=dev)
+    gcnb.dropout_maskbits(bits, n, F, p, gcnb.make_rng(seed, hist, elem_offset=off))
+    # tile layout: 32 rows per tile, tile padded to a multiple of 4 words
+    wpt = words // ((n + 31) // 32)
+    tiles = np.unpackbits(to_np(bits).view(u8), bitorder="little").reshape(-1, wpt * 32)
+    got_bits = tiles[:, : 32 * F].reshape(-1)[:size]
+    assert (got_bits == mask).all()
+    assert (tiles[:, 32 * F:] == 0).all() and (tiles[:, : 32 * F].reshape(-1)[size:] == 0).all()
+    out = torch.full((n, P), float("nan"), device=dev)
+    gcnb.dense_feat_fwd(d_X, bits, p, d_W, out, n, F, P)
+    assert_close(to_np(out), want_out, what="dense_feat_fwd")
+    dW = torch.full((F, P), float("nan"), device=dev)
+    gcnb.dense_feat_tn(d_X, bits, p, d_dH, dW, n, F, P)
+    assert_close(to_np(dW), want_dW, rtol=2e-5, what="dense_feat_tn")
+    dW2 = torch.empty_like(dW)
+    gcnb.dense_feat_tn(d_X, bits, p, d_dH, dW2, n, F, P)
+    assert torch.equal(dW, dW2)
+    # eval form: no mask
+    O.lib.orc_matmul(n, F, P, O._p(X), O._p(W), O._p(want_out))
+    gcnb.dense_feat_fwd(d_X, None, 0.0, d_W, out, n, F, P)
+    assert_close(to_np(out), want_out, what="dense_feat_fwd eval")
