@@ -55,6 +55,38 @@ GCNB_API int gcnb_spmm_plan_destroy(gcnb_spmm_plan *plan);
 /* number of segments / split rows / queues (introspection for tests & DESIGN numbers) */
 GCNB_API int gcnb_spmm_plan_info(const gcnb_spmm_plan *plan, int64_t out[8]);
 
+/* Optional window-staged fast path for a product whose values never change between launches -- GraphSum's
+ * graph_value (src/parser.cpp:164-181, GraphSum::forward/backward src/module.cu:188-210).  Builds (once, on the host,
+ * multi-threaded) a second representation of the index: entries of rows with many neighbours inside one column window
+ * of B (a window = as many rows of B as fit in an SM's shared memory at feature width `dim`) become packed segments
+ * with 16-bit window-local column ids and a copy of their values; the rest stays a (smaller) CSR.  Later
+ * gcnb_spmm_f32 calls with the SAME d_values pointer, this dim and no permutation run the staged kernel + the generic
+ * kernel on the remainder; any other call is unaffected.  h_indptr / h_indices: host copies of the plan's CSR arrays,
+ * or NULL to have them copied back from the device.  Only dim == 16 is staged today (other dims: no-op, returns 0);
+ * graphs without column locality (< 25 % of the entries stageable) are left on the generic kernel.  Calling it again
+ * with a new value array re-gathers the packed values only. */
+GCNB_API int gcnb_spmm_plan_stage(gcnb_spmm_plan *plan, const uint32_t *h_indptr, const uint32_t *h_indices,
+                                  const float *d_values, int dim, gcnb_stream_t stream);
+/* same with the builder's knobs exposed (0 = default): window_rows <= 3072, min_seg = fewest entries of a row inside a
+ * window worth a segment (16), seg_cap = longest segment (512), min_window_nnz = fewest staged entries that justify
+ * copying a window (8 * window_rows) */
+GCNB_API int gcnb_spmm_plan_stage_ex(gcnb_spmm_plan *plan, const uint32_t *h_indptr, const uint32_t *h_indices,
+                                     const float *d_values, int dim, int window_rows, int min_seg, int seg_cap,
+                                     int64_t min_window_nnz, gcnb_stream_t stream);
+/* out = {staged?, window_rows, staged entries, remainder entries, segments, runs, chunks, partial slots} */
+GCNB_API int gcnb_spmm_plan_stage_info(const gcnb_spmm_plan *plan, int64_t out[8]);
+
+/* The staging builder on its own, host memory only, no CUDA call: lets the plan layout be verified on a machine
+ * without a GPU (tests/test_stage_cpu.py).  Arrays are described in parallel-gcn_b200/csrc/spmm_plan.cuh. */
+typedef struct gcnb_stage_host gcnb_stage_host;
+GCNB_API int gcnb_stage_host_build(const uint32_t *h_indptr, const uint32_t *h_indices, int64_t n_rows, int64_t n_cols,
+                                   int dim, int window_rows /*0 = default*/, int min_seg /*0 = default*/,
+                                   int seg_cap /*0 = default*/, int64_t min_window_nnz /*0 = default*/,
+                                   int n_cta /*0 = 148*/, int n_threads /*0 = auto*/, gcnb_stage_host **out);
+GCNB_API int gcnb_stage_host_sizes(const gcnb_stage_host *h, int64_t out[12]);
+GCNB_API int gcnb_stage_host_copy(const gcnb_stage_host *h, int which, void *dst, int64_t bytes);
+GCNB_API int gcnb_stage_host_destroy(gcnb_stage_host *h);
+
 /* C[n_rows x dim] = A_csr * B[n_cols x dim],  A_csr values = d_values[e] (or d_values[d_perm[e]] if d_perm).
  *   GraphSum::forward/backward + graphsum_kernel            src/module.cu:172-210  (values = graph_value)
  *   SparseMatmul::forward + sparse_matmul_kernel_forward     src/module.cu:108-132  (values = input Variable)

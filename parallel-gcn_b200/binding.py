@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libgcn_b200.so")
+LIB_PATH = os.environ.get("GCNB_LIB") or os.path.join(HERE, "libgcn_b200.so")  # GCNB_LIB: tuning builds only
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(
@@ -45,6 +45,13 @@ _sig("gcnb_spmm_plan_create", I32, [P, P, I64, I64, I32, P, P])
 _sig("gcnb_spmm_plan_destroy", I32, [P])
 _sig("gcnb_spmm_plan_info", I32, [P, P])
 _sig("gcnb_spmm_f32", I32, [P, P, P, P, P, I32, P])
+_sig("gcnb_spmm_plan_stage", I32, [P, P, P, P, I32, P])
+_sig("gcnb_spmm_plan_stage_ex", I32, [P, P, P, P, I32, I32, I32, I32, I64, P])
+_sig("gcnb_spmm_plan_stage_info", I32, [P, P])
+_sig("gcnb_stage_host_build", I32, [P, P, I64, I64, I32, I32, I32, I32, I64, I32, I32, P])
+_sig("gcnb_stage_host_sizes", I32, [P, P])
+_sig("gcnb_stage_host_copy", I32, [P, I32, P, I64])
+_sig("gcnb_stage_host_destroy", I32, [P])
 _sig("gcnb_csc_create", I32, [P, P, I64, I64, P, P])
 _sig("gcnb_csc_destroy", I32, [P])
 _sig("gcnb_csc_arrays", I32, [P, P, P, P, P])
@@ -135,6 +142,21 @@ class SpmmPlan:
         keys = ("n_rows", "nnz", "n_seg", "n_split_rows", "n_slots", "n_queues", "seg_nnz", "max_deg")
         return dict(zip(keys, [int(x) for x in out]))
 
+    def stage(self, values, dim, h_indptr=None, h_indices=None, window_rows=0, min_seg=0, seg_cap=0, min_window_nnz=0):
+        """window-staged fast path for a static value array (GraphSum); h_*: optional numpy uint32 host copies."""
+        self._staged_values = values  # keep alive: the staged path is keyed on this pointer
+        hp = h_indptr.ctypes.data_as(C.c_void_p) if h_indptr is not None else None
+        hi = h_indices.ctypes.data_as(C.c_void_p) if h_indices is not None else None
+        check(lib.gcnb_spmm_plan_stage_ex(self.h, hp, hi, ptr(values), int(dim), window_rows, min_seg, seg_cap,
+                                          min_window_nnz, stream()))
+        return self.stage_info()
+
+    def stage_info(self):
+        out = (I64 * 8)()
+        check(lib.gcnb_spmm_plan_stage_info(self.h, out))
+        keys = ("staged", "window_rows", "staged_nnz", "rem_nnz", "n_segs", "n_runs", "n_blocks", "n_slots")
+        return dict(zip(keys, [int(x) for x in out]))
+
     def spmm(self, values, B, C_out, dim, perm=None):
         check(lib.gcnb_spmm_f32(self.h, ptr(values), ptr(perm), ptr(B), ptr(C_out), int(dim), stream()))
         return C_out
@@ -145,6 +167,45 @@ class SpmmPlan:
             self.h = None
 
     __del__ = close
+
+
+def stage_host_build(indptr, indices, n_cols, dim=16, window_rows=0, min_seg=0, seg_cap=0, min_window_nnz=0, n_cta=0,
+                     n_threads=0):
+    """Host-only run of the staging builder (no CUDA): returns the plan arrays as numpy (see csrc/spmm_plan.cuh)."""
+    import numpy as np
+    indptr = np.ascontiguousarray(indptr, np.uint32)
+    indices = np.ascontiguousarray(indices, np.uint32)
+    h = C.c_void_p()
+    check(lib.gcnb_stage_host_build(indptr.ctypes.data_as(C.c_void_p), indices.ctypes.data_as(C.c_void_p),
+                                    len(indptr) - 1, int(n_cols), dim, window_rows, min_seg, seg_cap, min_window_nnz,
+                                    n_cta, n_threads, C.byref(h)))
+    try:
+        sz = (I64 * 12)()
+        check(lib.gcnb_stage_host_sizes(h, sz))
+        keys = ("window_rows", "n_win", "n_cta", "staged_nnz", "n_bundles", "n_runs", "n_blocks", "n_slots", "rem_nnz",
+                "n_rows", "nnz", "n_segs")
+        out = dict(zip(keys, [int(x) for x in sz]))
+        n_rows = out["n_rows"]
+
+        def grab(which, n, dtype):
+            a = np.zeros(n, dtype)
+            if n:
+                check(lib.gcnb_stage_host_copy(h, which, a.ctypes.data_as(C.c_void_p), a.nbytes))
+            return a
+        out["bundles"] = grab(0, out["n_bundles"] * 4, np.uint32).reshape(-1, 4)
+        out["runs"] = grab(1, out["n_runs"] * 4, np.uint32).reshape(-1, 4)
+        out["run_begin"] = grab(2, out["n_cta"] + 1, np.uint32)
+        out["pidx"] = grab(3, out["n_blocks"] * 128, np.uint16)
+        out["pperm"] = grab(4, out["n_blocks"] * 128, np.uint32)
+        out["row_slot"] = grab(5, n_rows + 1, np.uint32)
+        out["r_indptr"] = grab(6, n_rows + 1, np.uint32)
+        out["r_indices"] = grab(7, out["rem_nnz"], np.uint32)
+        out["r_perm"] = grab(8, out["rem_nnz"], np.uint32)
+        out["lens"] = grab(9, out["n_bundles"] * 32, np.uint16)
+        out["lane_slot"] = grab(10, out["n_bundles"] * 32, np.uint32)
+        return out
+    finally:
+        lib.gcnb_stage_host_destroy(h)
 
 
 class Csc:

@@ -17,6 +17,7 @@
 
 #include "common.cuh"
 #include "philox.cuh"
+#include "bulk.cuh"
 
 using namespace gcnb;
 
@@ -73,33 +74,6 @@ __device__ __forceinline__ float masked(float x, const uint32_t *sbits, int idx,
 // ---- TMA bulk-copy plumbing (cp.async.bulk + mbarrier): a tile of TR consecutive rows of X is ONE contiguous block
 // of HBM, so each stage is a single bulk copy of up to 77 KB issued by one thread -- 150 KB in flight per SM, which
 // is what it takes to stream at HBM speed (per-lane LDG streams from 16 warps keep ~8 KB in flight and crawl).
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra.uni WAIT_DONE;\n"
-      "bra.uni WAIT_LOOP;\n"
-      "WAIT_DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst_smem)),
-               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-
 // thread 0: start the copy of rows [r0, r0+nrows) of a row-major [.. x F] matrix into `dst`; the 16-byte-multiple
 // prefix goes through the bulk engine, a possible 4/8/12-byte tail by plain stores (visible after the next barrier)
 __device__ __forceinline__ void issue_tile(float *dst, const float *__restrict__ src, int64_t r0, int nrows, int F,

@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "spmm_plan.cuh"
 
 namespace gcnb {
 
@@ -39,26 +40,13 @@ const DeviceInfo &device_info() {
 
 using namespace gcnb;
 
-struct gcnb_spmm_plan {
-  const uint32_t *d_indptr = nullptr;
-  const uint32_t *d_indices = nullptr;
-  int64_t n_rows = 0, n_cols = 0, nnz = 0;
-  int seg_nnz = 0;
-  int64_t n_seg = 0, n_split_rows = 0, n_slots = 0;
-  int n_queues = 0;
-  uint4 *d_segs = nullptr;         // (row, begin, end, slot or 0xffffffff)
-  uint32_t *d_queue_begin = nullptr;  // n_queues + 1
-  uint32_t *d_counters = nullptr;     // n_queues (+1 done counter)
-  uint32_t *d_split_row = nullptr;    // n_split_rows
-  uint32_t *d_split_slot = nullptr;   // n_split_rows + 1
-  float *d_scratch = nullptr;
-  int64_t scratch_dim = 0;
-  int64_t max_deg = 0;
-};
-
 namespace {
 
 constexpr int kThreads = 256;
+#ifndef GCNB_BLOCKS_NARROW
+#define GCNB_BLOCKS_NARROW 4
+#endif
+constexpr int kBlocksNarrow = GCNB_BLOCKS_NARROW;  // resident CTAs per SM asked of ptxas for the one-tile kernels
 constexpr uint32_t kNoSlot = 0xffffffffu;
 
 template <int VEC>
@@ -142,8 +130,24 @@ __device__ __forceinline__ void chunk_fma(Vec<VEC> (&acc)[KT], const char *__res
   }
 }
 
+// indices / values of entries [e0 + lane] of a segment (zero beyond its end)
 template <int VEC, int LPR, int KT, bool EXACT>
-__device__ __forceinline__ void run_segment(const SegArgs<VEC, LPR, KT, EXACT> &A, const uint4 sg, const int lane) {
+__device__ __forceinline__ void load_chunk(const SegArgs<VEC, LPR, KT, EXACT> &A, uint32_t e, uint32_t end,
+                                           uint32_t &idx, float &val) {
+  idx = 0;
+  val = 0.f;
+  if (e < end) {
+    idx = ld_stream_u32(A.indices + e);
+    val = A.perm ? __ldg(A.values + __ldg(A.perm + e)) : ld_stream_f32(A.values + e);
+  }
+}
+
+// One segment.  (idx_n, val_n) arrive holding the segment's first 32 entries and leave holding the first 32 entries
+// of `next` (the segment this warp runs afterwards, if any): while the last chunk's rows are gathered, the next
+// segment's indices are already in flight -- short rows are otherwise a chain of dependent memory latencies.
+template <int VEC, int LPR, int KT, bool EXACT>
+__device__ __forceinline__ void run_segment(const SegArgs<VEC, LPR, KT, EXACT> &A, const uint4 sg, const int lane,
+                                            uint32_t &idx_n, float &val_n, const bool has_next, const uint4 next) {
   constexpr int W = VEC * LPR;
   const int g = lane / LPR, l = lane % LPR;
   const int dim = A.dim;
@@ -160,31 +164,18 @@ __device__ __forceinline__ void run_segment(const SegArgs<VEC, LPR, KT, EXACT> &
 
   // software pipeline: indices/values of the next 32 entries are in flight while the current chunk's rows
   // are gathered
-  uint32_t idx_n = 0;
-  float val_n = 0.f;
-  {
-    const uint32_t e = beg + lane;
-    if (e < end) {
-      idx_n = ld_stream_u32(A.indices + e);
-      val_n = A.perm ? __ldg(A.values + __ldg(A.perm + e)) : ld_stream_f32(A.values + e);
-    }
-  }
   uint32_t base = beg;
-  for (; base + 32 <= end; base += 32) {
+  if (base >= end && has_next) load_chunk(A, next.y + lane, next.z, idx_n, val_n);
+  while (base < end) {  // warp-uniform
     const uint32_t idx = idx_n;
     const float val = val_n;
-    {
-      const uint32_t e = base + 32 + lane;
-      idx_n = 0;
-      val_n = 0.f;
-      if (e < end) {
-        idx_n = ld_stream_u32(A.indices + e);
-        val_n = A.perm ? __ldg(A.values + __ldg(A.perm + e)) : ld_stream_f32(A.values + e);
-      }
-    }
-    chunk_fma<VEC, LPR, KT, EXACT, false>(acc, Bl, row_bytes, idx, val, 32, g, colok);
+    const uint32_t nb = base + 32;
+    if (nb < end) load_chunk(A, nb + lane, end, idx_n, val_n);
+    else if (has_next) load_chunk(A, next.y + lane, next.z, idx_n, val_n);
+    if (nb <= end) chunk_fma<VEC, LPR, KT, EXACT, false>(acc, Bl, row_bytes, idx, val, 32, g, colok);
+    else chunk_fma<VEC, LPR, KT, EXACT, true>(acc, Bl, row_bytes, idx, val, (int)(end - base), g, colok);
+    base = nb;
   }
-  if (base < end) chunk_fma<VEC, LPR, KT, EXACT, true>(acc, Bl, row_bytes, idx_n, val_n, (int)(end - base), g, colok);
 
   // fixed-order tree over the G neighbour groups
 #pragma unroll
@@ -199,32 +190,92 @@ __device__ __forceinline__ void run_segment(const SegArgs<VEC, LPR, KT, EXACT> &
   }
 }
 
+// Drains one queue.  Two tickets ahead: while segment n runs, the header of segment n+1 is already loaded (its
+// first chunk gets prefetched by run_segment) and the atomic that claims segment n+2 is in flight.
 template <int VEC, int LPR, int KT, bool EXACT>
-__device__ __forceinline__ void drain_queue(const SegArgs<VEC, LPR, KT, EXACT> &A, const uint32_t *__restrict__ queue_begin,
+__device__ __forceinline__ void drain_queue_lookahead(const SegArgs<VEC, LPR, KT, EXACT> &A, const uint32_t *__restrict__ queue_begin,
                                             uint32_t *__restrict__ counters, int q, int lane) {
   const uint32_t qb = __ldg(queue_begin + q), qn = __ldg(queue_begin + q + 1) - qb;
+  if (*((volatile uint32_t *)(counters + q)) >= qn) return;  // already drained: do not pay for an atomic
+  uint32_t t = 0;
+  if (lane == 0) t = atomicAdd(counters + q, 1u);
+  t = __shfl_sync(0xffffffffu, t, 0);
+  if (t >= qn) return;
+  uint4 sg = __ldg(A.segs + qb + t);
+  if (lane == 0) t = atomicAdd(counters + q, 1u);
+  t = __shfl_sync(0xffffffffu, t, 0);
+  bool has_next = t < qn;
+  uint4 sgn = make_uint4(0, 0, 0, 0);
+  if (has_next) sgn = __ldg(A.segs + qb + t);
+  uint32_t idx_n;
+  float val_n;
+  load_chunk(A, sg.y + lane, sg.z, idx_n, val_n);
   for (;;) {
-    uint32_t ticket = 0;
-    if (lane == 0) ticket = atomicAdd(counters + q, 1u);
-    ticket = __shfl_sync(0xffffffffu, ticket, 0);
-    if (ticket >= qn) break;
-    run_segment<VEC, LPR, KT, EXACT>(A, __ldg(A.segs + qb + ticket), lane);
+    uint32_t t2 = 0;
+    if (has_next && lane == 0) t2 = atomicAdd(counters + q, 1u);  // claims the segment after next; used below
+    run_segment<VEC, LPR, KT, EXACT>(A, sg, lane, idx_n, val_n, has_next, sgn);
+    if (!has_next) break;
+    sg = sgn;
+    t2 = __shfl_sync(0xffffffffu, t2, 0);
+    has_next = t2 < qn;
+    if (has_next) sgn = __ldg(A.segs + qb + t2);
+  }
+}
+
+// Short rows: drains one queue in batches of kBatch (<= 32) consecutive segments per atomic ticket: the batch's headers arrive in ONE
+// coalesced load (lane k holds segment k) and the next segment's first chunk is prefetched by run_segment, so the
+// ticket -> header -> indices latency chain is paid once per batch instead of once per (short) row.
+template <int VEC, int LPR, int KT, bool EXACT>
+__device__ __forceinline__ void drain_queue_batched(const SegArgs<VEC, LPR, KT, EXACT> &A, const uint32_t *__restrict__ queue_begin,
+                                            uint32_t *__restrict__ counters, int q, int lane, const uint32_t kBatch) {
+  const uint32_t qb = __ldg(queue_begin + q), qn = __ldg(queue_begin + q + 1) - qb;
+  uint32_t t = 0;
+  if (lane == 0) t = atomicAdd(counters + q, kBatch);
+  t = __shfl_sync(0xffffffffu, t, 0);
+  while (t < qn) {
+    const uint32_t nb = min(kBatch, qn - t);
+    uint4 h = make_uint4(0, 0, 0, 0);
+    if ((uint32_t)lane < nb) h = __ldg(A.segs + qb + t + lane);
+    uint32_t tn = 0;
+    if (lane == 0) tn = atomicAdd(counters + q, kBatch);  // next batch's ticket is in flight during this batch
+    uint4 sg;
+    sg.x = __shfl_sync(0xffffffffu, h.x, 0); sg.y = __shfl_sync(0xffffffffu, h.y, 0);
+    sg.z = __shfl_sync(0xffffffffu, h.z, 0); sg.w = __shfl_sync(0xffffffffu, h.w, 0);
+    uint32_t idx_n;
+    float val_n;
+    load_chunk(A, sg.y + lane, sg.z, idx_n, val_n);
+    for (uint32_t k = 0; k < nb; k++) {
+      const bool has_next = k + 1 < nb;
+      uint4 sgn;
+      sgn.x = __shfl_sync(0xffffffffu, h.x, (int)((k + 1) & 31)); sgn.y = __shfl_sync(0xffffffffu, h.y, (int)((k + 1) & 31));
+      sgn.z = __shfl_sync(0xffffffffu, h.z, (int)((k + 1) & 31)); sgn.w = __shfl_sync(0xffffffffu, h.w, (int)((k + 1) & 31));
+      run_segment<VEC, LPR, KT, EXACT>(A, sg, lane, idx_n, val_n, has_next, sgn);
+      sg = sgn;
+    }
+    t = __shfl_sync(0xffffffffu, tn, 0);
   }
 }
 
 template <int VEC, int LPR, int KT, bool EXACT>
-__global__ void __launch_bounds__(kThreads, 4)
+__device__ __forceinline__ void drain_queue(const SegArgs<VEC, LPR, KT, EXACT> &A, const uint32_t *__restrict__ queue_begin,
+                                            uint32_t *__restrict__ counters, int q, int lane, int batch) {
+  if (batch <= 1) drain_queue_lookahead<VEC, LPR, KT, EXACT>(A, queue_begin, counters, q, lane);
+  else drain_queue_batched<VEC, LPR, KT, EXACT>(A, queue_begin, counters, q, lane, (uint32_t)batch);
+}
+
+template <int VEC, int LPR, int KT, bool EXACT>
+__global__ void __launch_bounds__(kThreads, (KT == 1 ? kBlocksNarrow : 4))
 spmm_seg_kernel(const uint4 *__restrict__ segs, const uint32_t *__restrict__ queue_begin,
                 uint32_t *__restrict__ counters, int n_queues, const uint32_t *__restrict__ indices,
                 const float *__restrict__ values, const uint32_t *__restrict__ perm, const float *__restrict__ B,
-                float *__restrict__ C, float *__restrict__ scratch, int dim) {
+                float *__restrict__ C, float *__restrict__ scratch, int dim, int batch) {
   const SegArgs<VEC, LPR, KT, EXACT> A{segs, indices, values, perm, B, C, scratch, dim};
   const int lane = threadIdx.x & 31;
   uint32_t smid;
   asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
   const int q0 = (int)(smid % (uint32_t)n_queues);
   // 1) this SM's own queue (contiguous rows => L1 reuse of gathered neighbour rows)
-  drain_queue<VEC, LPR, KT, EXACT>(A, queue_begin, counters, q0, lane);
+  drain_queue<VEC, LPR, KT, EXACT>(A, queue_begin, counters, q0, lane, batch);
   // 2) steal: probe 32 queues at a time, drain the ones that still hold segments
   for (int base = 1; base < n_queues; base += 32) {
     const int off = base + lane;
@@ -239,7 +290,7 @@ spmm_seg_kernel(const uint4 *__restrict__ segs, const uint32_t *__restrict__ que
     while (mask) {
       const int src = __ffs(mask) - 1;
       mask &= mask - 1;
-      drain_queue<VEC, LPR, KT, EXACT>(A, queue_begin, counters, __shfl_sync(0xffffffffu, q, src), lane);
+      drain_queue<VEC, LPR, KT, EXACT>(A, queue_begin, counters, __shfl_sync(0xffffffffu, q, src), lane, batch);
     }
   }
 }
@@ -270,7 +321,7 @@ __global__ void dense_check_kernel(const uint32_t *__restrict__ indices, int64_t
 }
 
 using KernelFn = void (*)(const uint4 *, const uint32_t *, uint32_t *, int, const uint32_t *, const float *,
-                          const uint32_t *, const float *, float *, float *, int);
+                          const uint32_t *, const float *, float *, float *, int, int);
 
 template <int VEC, int LPR, int KT>
 KernelFn kfn(int dim) {
@@ -340,6 +391,8 @@ int gcnb_spmm_plan_create(const uint32_t *d_indptr, const uint32_t *d_indices, i
   }
   split_slot.push_back(slots);
   p->n_seg = (int64_t)segs.size();
+  // short rows: several segments per atomic ticket (see drain_queue_batched); long rows: one, with look-ahead
+  p->batch = (int)std::min<int64_t>(8, std::max<int64_t>(1, 384 / std::max<int64_t>(1, p->nnz / std::max<int64_t>(1, p->n_seg))));
   p->n_split_rows = (int64_t)split_row.size();
   p->n_slots = slots;
 
@@ -389,6 +442,7 @@ int gcnb_spmm_plan_destroy(gcnb_spmm_plan *p) {
   cudaFree(p->d_split_row);
   cudaFree(p->d_split_slot);
   cudaFree(p->d_scratch);
+  gcnb::stage_destroy(p->staged);
   delete p;
   return 0;
 }
@@ -405,6 +459,11 @@ int gcnb_spmm_f32(gcnb_spmm_plan *p, const float *d_values, const uint32_t *d_pe
   if (!p || !d_values || !d_B || !d_C || dim <= 0) return GCNB_E_BADARG;
   if (p->n_rows == 0) return 0;
   cudaStream_t stream = as_stream(stream_);
+  if (p->staged) {  // window-staged fast path (static values, dim it was built for), spmm_stage.cu
+    int handled = 0;
+    const int rc = gcnb_stage_try_spmm(p, d_values, d_perm, d_B, d_C, dim, stream, &handled);
+    if (rc || handled) return rc;
+  }
   const bool vec4 = (dim % 4 == 0) && (((uintptr_t)d_B | (uintptr_t)d_C) % 16 == 0);
   KernelFn fn = vec4 ? pick_kernel<4>(dim) : pick_kernel<1>(dim);
   if (!fn) return GCNB_E_UNSUPPORTED;
@@ -437,7 +496,7 @@ int gcnb_spmm_f32(gcnb_spmm_plan *p, const float *d_values, const uint32_t *d_pe
   if (grid > min_grid) grid = std::max<int64_t>(1, min_grid);
   GCNB_CHECK(cudaMemsetAsync(p->d_counters, 0, ((size_t)p->n_queues + 1) * 4, stream));
   fn<<<(unsigned)grid, kThreads, 0, stream>>>(p->d_segs, p->d_queue_begin, p->d_counters, p->n_queues, p->d_indices,
-                                              d_values, d_perm, d_B, d_C, p->d_scratch, dim);
+                                              d_values, d_perm, d_B, d_C, p->d_scratch, dim, p->batch);
   GCNB_LAUNCH_CHECK();
   if (p->n_split_rows > 0) {
     const int64_t total = p->n_split_rows * dim;

@@ -1,0 +1,91 @@
+// spmm_plan.cuh -- the CSR x dense plan object shared by spmm.cu (generic segment kernel) and spmm_stage.cu
+// (window-staged GraphSum kernel).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <vector>
+
+namespace gcnb {
+
+// ---- window staging (spmm_stage.cu) ----------------------------------------------------------------------------
+// The columns (= rows of the dense operand B) are cut into windows of `window_rows` rows, one window fitting in an
+// SM's shared memory.  Entries (i, j) of rows that hold >= min_seg entries inside a window are STAGED: the CTA that
+// owns the window copies it into shared memory once (TMA bulk copy) and gathers the neighbour rows from there with
+// conflict-free LDS.128 -- half an LSU wavefront per neighbour row instead of one L1 wavefront, and 2-byte
+// window-local column indices instead of 4-byte ones.  Everything else (the REMAINDER) stays a plain CSR and goes
+// through the generic kernel.
+struct StageParams {
+  int dim = 16;                  // feature width the plan is built for (window_rows * dim * 4 bytes of shared memory)
+  int window_rows = 0;           // 0 = as many rows as fit (<= 65536: local column ids are 16-bit)
+  int min_seg = 16;              // (row, window) pairs with fewer entries are not worth a segment
+  int seg_cap = 256;            // longer (row, window) runs are cut into pieces of <= seg_cap entries
+  int64_t min_window_nnz = 0;    // 0 = 8 * window_rows: a window must be re-used to pay for its copy
+  int n_cta = 148;               // persistent CTAs (one per SM)
+  int n_threads = 0;             // host threads for the build (0 = hardware concurrency, <= 16)
+  int runs_per_queue = 1;        // > 1 cuts every CTA's share of a window into several runs
+  int min_avg_seg = 32;          // staging is skipped when the average segment is shorter (per-segment work dominates)
+};
+
+constexpr int kStageLanes = 32;                 // segments per bundle (one per lane)
+constexpr int kStageBlock = 4;                  // steps per packed block (one 8-byte id load + one 16-byte value load)
+constexpr uint32_t kStagePad = 0xffffffffu;     // padding marker in the value permutation / unused slot
+
+// Host-side result of the build (pure CPU, unit-tested without a GPU through gcnb_stage_host_*).
+// A SEGMENT is the run of one row's entries inside one window (cut into pieces of <= seg_cap).  Segments of a
+// window are sorted by length and dealt 32 at a time into BUNDLES: lane l of the warp that processes a bundle owns
+// segment l entirely (private accumulators, no cross-lane reduction), step k of the bundle handles entry k of all 32
+// segments (ELL layout, so ids / values of a step are one coalesced load).
+//   bundles[b] = (first block, steps L = longest segment, shortest segment (0 if a lane is unused), 0)
+//   lens[b*32 + l] = entries of lane l's segment
+//   block = 4 steps x 32 lanes: pidx[(block*32 + l)*4 + k%4] = window-local column of entry k of lane l;
+//           pperm (same addressing) = position of that entry in the original CSR value array, kStagePad for padding
+//   entry order inside a segment alternates even/odd local columns, and lanes with bit 2 set start on odd: the two
+//   lanes of a quarter-warp that read the same 16-byte column chunk then always hit opposite bank halves
+//   lane_slot[b*32 + l] = partial slot written by lane l (kStagePad if the lane is unused); the slots of row r are the
+//   contiguous range [row_slot[r], row_slot[r+1]) in ascending (window, piece) order
+//   runs[r] = (window, first bundle, end bundle, 0);  CTA q processes runs [run_begin[q], run_begin[q+1])
+//   r_* : remainder CSR (original entry order inside a row) and its permutation into the original value array
+struct StagedHost {
+  int dim = 0, window_rows = 0, n_win = 0, n_cta = 0;
+  int64_t n_rows = 0, n_cols = 0, nnz = 0, staged_nnz = 0, n_blocks = 0, n_slots = 0, n_segs = 0;
+  std::vector<uint4> bundles, runs;
+  std::vector<uint16_t> lens;
+  std::vector<uint32_t> run_begin;
+  std::vector<uint16_t> pidx;
+  std::vector<uint32_t> pperm;
+  std::vector<uint32_t> row_slot, lane_slot;
+  std::vector<uint32_t> r_indptr, r_indices, r_perm;
+};
+
+int stage_build_host(const uint32_t *indptr, const uint32_t *indices, int64_t n_rows, int64_t n_cols,
+                     const StageParams &params, StagedHost &out);
+
+struct StagedDev;  // device mirror, spmm_stage.cu
+void stage_destroy(StagedDev *s);
+
+}  // namespace gcnb
+
+struct gcnb_spmm_plan {
+  const uint32_t *d_indptr = nullptr;
+  const uint32_t *d_indices = nullptr;
+  int64_t n_rows = 0, n_cols = 0, nnz = 0;
+  int seg_nnz = 0;
+  int64_t n_seg = 0, n_split_rows = 0, n_slots = 0;
+  int n_queues = 0;
+  uint4 *d_segs = nullptr;         // (row, begin, end, slot or 0xffffffff)
+  uint32_t *d_queue_begin = nullptr;  // n_queues + 1
+  uint32_t *d_counters = nullptr;     // n_queues (+1 done counter)
+  uint32_t *d_split_row = nullptr;    // n_split_rows
+  uint32_t *d_split_slot = nullptr;   // n_split_rows + 1
+  float *d_scratch = nullptr;
+  int64_t scratch_dim = 0;
+  int64_t max_deg = 0;
+  int batch = 1;                      // segments claimed per atomic ticket (short-row graphs: > 1)
+  gcnb::StagedDev *staged = nullptr;  // optional window-staged fast path (gcnb_spmm_plan_stage)
+};
+
+// spmm_stage.cu: runs the staged path if it applies to this call (same values pointer, same dim, no permutation) and
+// sets *handled = 1; otherwise *handled = 0 and the caller runs the generic kernel.  Returns 0 or an error code.
+int gcnb_stage_try_spmm(gcnb_spmm_plan *p, const float *d_values, const uint32_t *d_perm, const float *d_B, float *d_C,
+                        int dim, cudaStream_t stream, int *handled);

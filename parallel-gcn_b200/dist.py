@@ -217,6 +217,10 @@ class DistGCN:
         self.label, self.split = o.upload(part["label"]), o.upload(part["split"])
         self.truth = o.i32(max(1, self.nl))
         self.graph_plan = o.plan(self.g_indptr, self.g_indices, self.N)
+        if hasattr(self.graph_plan, "stage") and self.nl and 16 in self.dims[1:]:
+            # static graph_value: window-staged GraphSum at width 16 (csrc/spmm_stage.cu); no-op without locality
+            self.graph_plan.stage(self.g_value, 16, np.ascontiguousarray(part["g_indptr"], np.uint32),
+                                  np.ascontiguousarray(part["g_indices"], np.uint32))
         self.feat_csc = o.csc(self.f_indptr, self.f_indices, self.dims[0])
         self.feat_dense = self.feat_csc.is_dense
         self.feat_plan = None if self.feat_dense else o.plan(self.f_indptr, self.f_indices, self.dims[0])

@@ -103,7 +103,7 @@ class GCN {
   void backward_pass(cudaStream_t stream);
   std::pair<real, real> finalize(cudaStream_t stream) const;
   void print_variable_info() const;
-  void init(bool quiet);
+  void init(bool quiet, const natural *h_graph_indptr = nullptr, const natural *h_graph_indices = nullptr);
 
  public:
   real avg_epoch_time;

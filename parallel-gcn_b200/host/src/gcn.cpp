@@ -108,6 +108,7 @@ struct GCNEngineState {
   size_t launches = 0, launches_last_epoch = 0;  // CUDA kernels launched (memsets / copies not counted)
   natural epochs_run = 0;
   int graph_spmm_kernels = 1, feat_spmm_kernels = 1, feat_csc_kernels = 1;  // 1 + combine kernel when rows are split
+  int graph_staged_dim = -1, graph_staged_kernels = 0;  // window-staged GraphSum: staged + remainder (+combine) + add
   // optional per-launch timing of the GraphSum SpMM (bench.py roofline): event pairs on the engine stream
   bool time_graphsum = false;
   std::vector<cudaEvent_t> gs_events;
@@ -129,7 +130,7 @@ struct GCNEngineState {
       CHECK_CUDA_ERROR(cudaEventRecord(gs_events[gs_used + 1], stream));
       gs_used += 2;
     }
-    launches += graph_spmm_kernels;
+    launches += (dim == graph_staged_dim) ? graph_staged_kernels : graph_spmm_kernels;
   }
   void collect_graphsum_times() {  // after a stream sync
     for (size_t i = 0; i + 1 < gs_used; i += 2) {
@@ -153,16 +154,16 @@ struct GCNEngineState {
 GCN::GCN(GCNParams const *params_, AdamParams const *adam_params_, GCNData const *data_, bool quiet)
     : smart_objects(params_->n_layers), data(data_), dev_data{DevGCNData(*data_)}, params(params_),
       adam_params(adam_params_) {
-  init(quiet);
+  init(quiet, data_->graph.indptr.data(), data_->graph.indices.data());
 }
 
 GCN::GCN(GCNParams const *params_, AdamParams const *adam_params_, const GCNDataView &view, bool quiet)
     : smart_objects(params_->n_layers), data(nullptr), dev_data{DevGCNData(view)}, params(params_),
       adam_params(adam_params_) {
-  init(quiet);
+  init(quiet, view.graph_indptr, view.graph_indices);
 }
 
-void GCN::init(bool quiet) {
+void GCN::init(bool quiet, const natural *h_graph_indptr, const natural *h_graph_indices) {
   int sm = 0;
   GCNB_CALL(gcnb_device_check(&sm));  // no CPU fallback: a missing/unsupported GPU is fatal here
   L = params->n_layers;
@@ -234,6 +235,22 @@ void GCN::init(bool quiet) {
     tn_need = std::max(tn_need, gcnb_matmul_tn_workspace(N, ly.in_dim, ly.out_dim));
   }
   output = st->layers.back().z;
+  {
+    // graph_value never changes: give GraphSum at width 16 the window-staged representation (shared-memory gathers
+    // for the clustered part of the adjacency, see csrc/spmm_stage.cu); a no-op for graphs without column locality
+    bool uses16 = false;
+    for (const GCNLayer &ly : st->layers) uses16 |= (ly.reorder ? ly.in_dim : ly.out_dim) == 16;
+    if (uses16) {
+      GCNB_CALL(gcnb_spmm_plan_stage(st->graph_plan, h_graph_indptr, h_graph_indices, dev_data.dev_graph_value.get(),
+                                     16, st->stream));
+      int64_t sinfo[8];
+      GCNB_CALL(gcnb_spmm_plan_stage_info(st->graph_plan, sinfo));
+      if (sinfo[0]) {
+        st->graph_staged_dim = 16;
+        st->graph_staged_kernels = 3;  // staged + remainder + add (a remainder combine kernel, if any, is not counted)
+      }
+    }
+  }
   if (st->feat_dense && gcnb_dense_feat_supported((int)F, (int)dims[1])) {
     st->dense_fast = true;
     st->x_bits = dev_shared_ptr<natural>(gcnb_dropout_maskbits_words(N, (int)F));

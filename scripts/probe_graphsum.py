@@ -58,6 +58,9 @@ ap.add_argument("--intra", type=float, nargs="*", default=[0.8, 0.0])
 ap.add_argument("--dim", type=int, nargs="*", default=[16, 41, 64])
 ap.add_argument("--seg", type=int, nargs="*", default=[256, 512, 1024])
 ap.add_argument("--iters", type=int, default=20)
+ap.add_argument("--stage", type=int, default=1)
+ap.add_argument("--min-seg", type=int, nargs="*", default=[0])
+ap.add_argument("--seg-cap", type=int, nargs="*", default=[0])
 ap.add_argument("--out", default="gpurun_out/probe_graphsum.json")
 args = ap.parse_args()
 res = []
@@ -67,11 +70,23 @@ for intra in args.intra:
         x = torch.randn(N, dim, device=dev)
         out = torch.empty(N, dim, device=dev)
         for seg in args.seg:
-            plan = gcnb.SpmmPlan(indptr, cols, N, seg)
-            us = bench(plan, vals, x, out, dim, args.iters)
-            alg = 4 * (N + 1) + 8 * nnz + 8 * N * dim
-            r = dict(intra=intra, dim=dim, seg=seg, nnz=nnz, us=round(us, 1), alg_GBs=round(alg / us / 1e3, 1), info=plan.info())
-            print(json.dumps(r), flush=True)
-            res.append(r)
-            plan.close()
+          for min_seg in args.min_seg:
+            for seg_cap in args.seg_cap:
+                plan = gcnb.SpmmPlan(indptr, cols, N, seg)
+                us0 = bench(plan, vals, x, out, dim, args.iters)
+                ref = out.clone()
+                sinfo, build_s = None, None
+                if args.stage and dim == 16:
+                    t0 = time.time()
+                    sinfo = plan.stage(vals, dim, min_seg=min_seg, seg_cap=seg_cap)
+                    build_s = round(time.time() - t0, 2)
+                us = bench(plan, vals, x, out, dim, args.iters)
+                err = float((out - ref).abs().max() / ref.abs().max())
+                alg = 4 * (N + 1) + 8 * nnz + 8 * N * dim
+                r = dict(intra=intra, dim=dim, seg=seg, min_seg=min_seg, seg_cap=seg_cap, nnz=nnz, us_generic=round(us0, 1),
+                         us=round(us, 1), alg_GBs=round(alg / us / 1e3, 1), rel_diff_vs_generic=err, stage=sinfo,
+                         stage_build_s=build_s, info=plan.info())
+                print(json.dumps(r), flush=True)
+                res.append(r)
+                plan.close()
 json.dump(res, open(args.out, "w"), indent=1)
