@@ -237,7 +237,10 @@ def run_ours(args, rank, world, local_rank):
     prof = os.path.join(ROOT, "profiles", "graphsum_d16_summary.json")
     if os.path.exists(prof):
         traffic = json.load(open(prof)).get("dram_bytes_per_launch")
-    roofline = {"bound": "hbm", "kernel": "spmm_seg_kernel<4,4,1> (GraphSum, d=%d)" % d, "achieved": achieved, "peak": peak,
+    staged = bool(r.get("graph_staged"))
+    kname = ("GraphSum d=%d = spmm_staged16_kernel (shared-memory column windows) || spmm_seg_kernel (remainder CSR, 2nd "
+             "stream) + stage_add16_kernel" % d) if staged else "spmm_seg_kernel<4,4,1> (GraphSum, d=%d)" % d
+    roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg, "mean_launch_us": gs_us, "launches_timed": r["graphsum_calls"],
                 "graphsum_share_of_step": r["graphsum_ms"] / r["ms"], "frac_of_nominal_8TBs": achieved / 8000.0}

@@ -72,6 +72,8 @@ GCNB_API int gcnb_gcn_get_logits(const gcnb_gcn *g, float *host_dst); /* [num_no
  * ([feat_nnz]), site l = hidden layer l-1 ([num_nodes x hidden_dims[l-1]]); NULL = back to Philox */
 GCNB_API int gcnb_gcn_set_mask(gcnb_gcn *g, int site, const uint8_t *host_mask);
 GCNB_API int64_t gcnb_gcn_launches_per_epoch(const gcnb_gcn *g);
+/* 1 if GraphSum at feature width 16 uses the window-staged kernels (graph with column locality), else 0 */
+GCNB_API int gcnb_gcn_graph_staged(const gcnb_gcn *g);
 GCNB_API int64_t gcnb_gcn_launches_total(const gcnb_gcn *g);
 /* measurement hook (bench.py): n_epochs x {train_epoch [+ eval(2)]} bracketed by CUDA events on the engine's stream.
  * out[0] = total ms, out[1] = summed ms of the GraphSum SpMM launches (event pair per launch, if time_graphsum),

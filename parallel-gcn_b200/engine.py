@@ -46,6 +46,7 @@ _sig("gcnb_gcn_get_weight_grad", I32, [P, I32, P])
 _sig("gcnb_gcn_get_logits", I32, [P, P])
 _sig("gcnb_gcn_set_mask", I32, [P, I32, P])
 _sig("gcnb_gcn_launches_per_epoch", I64, [P])
+_sig("gcnb_gcn_graph_staged", I32, [P])
 _sig("gcnb_gcn_launches_total", I64, [P])
 _sig("gcnb_gcn_timed_epochs", I32, [P, I32, I32, I32, P])
 _sig("gcnb_synth_graph", I32, [I64, I64, I32, C.c_double, C.c_double, I64, C.c_uint64, P, P, P])
@@ -200,7 +201,8 @@ class GCN:
     def timed_epochs(self, n_epochs, with_eval=True, time_graphsum=False):
         out = (F32 * 4)()
         check(lib.gcnb_gcn_timed_epochs(self.h, int(n_epochs), int(with_eval), int(time_graphsum), out))
-        return dict(ms=float(out[0]), graphsum_ms=float(out[1]), graphsum_calls=int(out[2]), launches=int(out[3]))
+        return dict(ms=float(out[0]), graphsum_ms=float(out[1]), graphsum_calls=int(out[2]), launches=int(out[3]),
+                    graph_staged=int(lib.gcnb_gcn_graph_staged(self.h)))
 
     def launches_per_epoch(self):
         return int(lib.gcnb_gcn_launches_per_epoch(self.h))

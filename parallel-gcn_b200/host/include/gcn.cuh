@@ -138,6 +138,7 @@ class GCN {
   void set_use_cuda_graph(bool on);
   void set_reorder(bool on);  // allow the (A*a)*W association (default on)
   size_t launches_per_epoch() const;
+  bool graph_staged() const;  // GraphSum at width 16 runs the window-staged kernels (csrc/spmm_stage.cu)
   size_t launches_total() const;
   void set_time_graphsum(bool on);                        // event pair around every GraphSum launch
   void graphsum_timing(double *ms_total, size_t *calls) const;

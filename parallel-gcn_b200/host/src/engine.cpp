@@ -217,6 +217,7 @@ int gcnb_gcn_set_mask(gcnb_gcn *g, int site, const uint8_t *host_mask) {
   return 0;
 }
 int64_t gcnb_gcn_launches_per_epoch(const gcnb_gcn *g) { return g ? (int64_t)g->gcn->launches_per_epoch() : -1; }
+int gcnb_gcn_graph_staged(const gcnb_gcn *g) { return g ? (int)g->gcn->graph_staged() : -1; }
 int64_t gcnb_gcn_launches_total(const gcnb_gcn *g) { return g ? (int64_t)g->gcn->launches_total() : -1; }
 int gcnb_gcn_timed_epochs(gcnb_gcn *g, int n_epochs, int with_eval, int time_graphsum, float out[4]) {
   if (!g || !out || n_epochs < 0) return GCNB_E_BADARG;

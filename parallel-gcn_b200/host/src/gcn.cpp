@@ -294,6 +294,7 @@ void GCN::set_reorder(bool on) {
   }
 }
 size_t GCN::launches_per_epoch() const { return st->launches_last_epoch; }
+bool GCN::graph_staged() const { return st->graph_staged_dim > 0; }
 size_t GCN::launches_total() const { return st->launches; }
 void GCN::set_time_graphsum(bool on) {
   st->time_graphsum = on;
