@@ -92,7 +92,19 @@ struct GCNEngineState {
   const real *x_train_vals = nullptr;  // feature values the last training forward used (dropped or pristine)
   // dense feature matrix: dropout applied on the fly from a bit mask (csrc/dense_feat.cu), X never copied
   bool dense_fast = false;
-  dev_shared_ptr<natural> x_bits;
+  dev_shared_ptr<natural> x_bits, x_bits_next;
+  // the keep bits of the NEXT training epoch are generated on the side stream while this epoch runs (the Philox
+  // stream is a pure function of the consumption history, so the descriptor is known as soon as this epoch's
+  // forward has been enqueued); used only if the descriptor still matches when the next epoch starts
+  bool next_bits_valid = false;
+  gcnb_rng_t next_bits_rng{};
+  real next_bits_p = 0.f;
+  // side stream: work that is independent of the main chain (next epoch's dropout bits, weight gradients of the
+  // upper layers) overlaps with the GraphSum / feature products on `stream`
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_bits = nullptr, ev_epoch = nullptr;
+  bool side_pending = false;  // side-stream work of this backward pass not yet joined
+  int use_side = 3;           // bit 0: side stream for weight gradients, bit 1: prefetch next epoch's dropout bits
   const natural *x_train_bits = nullptr;
   real x_train_p = 0.f;
   dev_shared_ptr<real> dense_tn_ws;
@@ -147,6 +159,9 @@ struct GCNEngineState {
     if (feat_csc) gcnb_csc_destroy(feat_csc);
     if (feat_plan) gcnb_spmm_plan_destroy(feat_plan);
     if (graph_plan) gcnb_spmm_plan_destroy(graph_plan);
+    if (side && side != stream) cudaStreamDestroy(side);
+    for (cudaEvent_t e : {ev_fork, ev_join, ev_bits, ev_epoch})
+      if (e) cudaEventDestroy(e);
     if (stream) cudaStreamDestroy(stream);
   }
 };
@@ -175,6 +190,11 @@ void GCN::init(bool quiet, const natural *h_graph_indptr, const natural *h_graph
   st = std::make_shared<GCNEngineState>();
   st->quiet = quiet;
   CHECK_CUDA_ERROR(cudaStreamCreateWithFlags(&st->stream, cudaStreamNonBlocking));
+  if (const char *e = getenv("GCNB_SIDE_STREAM")) st->use_side = atoi(e);  // tuning probe: 0 = single stream
+  if (st->use_side & 1) CHECK_CUDA_ERROR(cudaStreamCreateWithFlags(&st->side, cudaStreamNonBlocking));
+  else st->side = st->stream;
+  for (cudaEvent_t *e : {&st->ev_fork, &st->ev_join, &st->ev_bits, &st->ev_epoch})
+    CHECK_CUDA_ERROR(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
   const natural N = params->num_nodes, F = params->input_dim;
   dev_truth = dev_shared_ptr<integer>(N);
   decays.resize(L, false);  // only W0 is L2-regularised / decayed (src/gcn.cu:157-158)
@@ -254,6 +274,7 @@ void GCN::init(bool quiet, const natural *h_graph_indptr, const natural *h_graph
   if (st->feat_dense && gcnb_dense_feat_supported((int)F, (int)dims[1])) {
     st->dense_fast = true;
     st->x_bits = dev_shared_ptr<natural>(gcnb_dropout_maskbits_words(N, (int)F));
+    st->x_bits_next = dev_shared_ptr<natural>(gcnb_dropout_maskbits_words(N, (int)F));
     st->dense_tn_ws_bytes = gcnb_dense_feat_tn_workspace(N, (int)F, (int)dims[1]);
     st->dense_tn_ws = dev_shared_ptr<real>((st->dense_tn_ws_bytes + 3) / 4);
   }
@@ -362,8 +383,14 @@ void GCN::forward_pass(bool training, natural split, cudaStream_t s) {
     const real p0 = params->dropouts.front();
     if (p0 > 0.f) {
       const gcnb_rng_t rng = Variable::rng_descriptor();
-      GCNB_CALL(gcnb_dropout_maskbits(st->x_bits.get(), N, (int)F, p0, &rng, s));
-      st->launches++;
+      if (st->next_bits_valid && st->next_bits_p == p0 && std::memcmp(&rng, &st->next_bits_rng, sizeof(rng)) == 0) {
+        std::swap(st->x_bits, st->x_bits_next);  // generated on the side stream during the previous epoch
+        CHECK_CUDA_ERROR(cudaStreamWaitEvent(s, st->ev_bits, 0));
+      } else {
+        GCNB_CALL(gcnb_dropout_maskbits(st->x_bits.get(), N, (int)F, p0, &rng, s));
+        st->launches++;
+      }
+      st->next_bits_valid = false;
       xbits = st->x_bits.get();
       xp = p0;
     }
@@ -439,26 +466,40 @@ void GCN::backward_pass(cudaStream_t s) {
   for (natural l = L - 1; l >= 1; l--) {
     GCNLayer &ly = st->layers[l];
     GCNLayer &prev = st->layers[l - 1];
+    // the weight gradient only feeds Adam: it runs on the side stream (the reference uses a second backward stream
+    // for the same product, src/module.cu:456-472) while the main stream carries on with dA and the next GraphSum
     if (ly.reorder) {
       // z = y W, y = A_hat a  =>  dW = y^T g ; dy = g W^T ; da = A_hat dy   (A_hat symmetric)
+      CHECK_CUDA_ERROR(cudaEventRecord(st->ev_fork, s));
+      CHECK_CUDA_ERROR(cudaStreamWaitEvent(st->side, st->ev_fork, 0));
       GCNB_CALL(gcnb_matmul_tn_f32(ly.pre->dev_data.get(), g, weights[l]->dev_grad.get(), N, ly.in_dim, ly.out_dim,
-                                   st->tn_ws.get(), st->tn_ws_bytes, s));
+                                   st->tn_ws.get(), st->tn_ws_bytes, st->side));
       GCNB_CALL(gcnb_matmul_nt_f32(g, weights[l]->dev_data.get(), ly.pre->dev_grad.get(), N, ly.in_dim, ly.out_dim, s));
       st->graphsum(gv, ly.pre->dev_grad.get(), prev.z->dev_grad.get(), ly.in_dim);
     } else {
       // z = A_hat h, h = a W  =>  dh = A_hat g ; dW = a^T dh ; da = dh W^T   (src/module.cu:200-210, :456-472)
       st->graphsum(gv, g, ly.pre->dev_grad.get(), ly.out_dim);
+      CHECK_CUDA_ERROR(cudaEventRecord(st->ev_fork, s));
+      CHECK_CUDA_ERROR(cudaStreamWaitEvent(st->side, st->ev_fork, 0));
       GCNB_CALL(gcnb_matmul_tn_f32(prev.z->dev_data.get(), ly.pre->dev_grad.get(), weights[l]->dev_grad.get(), N,
-                                   ly.in_dim, ly.out_dim, st->tn_ws.get(), st->tn_ws_bytes, s));
+                                   ly.in_dim, ly.out_dim, st->tn_ws.get(), st->tn_ws_bytes, st->side));
       GCNB_CALL(gcnb_matmul_nt_f32(ly.pre->dev_grad.get(), weights[l]->dev_data.get(), prev.z->dev_grad.get(), N,
                                    ly.in_dim, ly.out_dim, s));
     }
+    st->side_pending = true;
     GCNB_CALL(gcnb_relu_dropout_bwd_f32(prev.z->dev_grad.get(), prev.mask.get(), prev.z->size, params->dropouts[l], s));
     st->launches += 2 + 1 + 1;  // split-K weight gradient (2 kernels), dA product, mask kernel
     g = prev.z->dev_grad.get();
   }
   GCNLayer &l0 = st->layers[0];
   st->graphsum(gv, g, l0.pre->dev_grad.get(), l0.out_dim);
+  auto join_side = [&]() {
+    if (!st->side_pending) return;
+    CHECK_CUDA_ERROR(cudaEventRecord(st->ev_join, st->side));
+    CHECK_CUDA_ERROR(cudaStreamWaitEvent(s, st->ev_join, 0));
+    st->side_pending = false;
+  };
+  if (!st->dense_fast && st->feat_dense) join_side();  // that branch re-uses the split-K workspace
   if (st->dense_fast) {
     GCNB_CALL(gcnb_dense_feat_tn_f32(st->x_train_vals, st->x_train_bits, st->x_train_p, l0.pre->dev_grad.get(),
                                      weights[0]->dev_grad.get(), N, (int)F, (int)l0.out_dim, st->dense_tn_ws.get(),
@@ -473,6 +514,7 @@ void GCN::backward_pass(cudaStream_t s) {
                             weights[0]->dev_grad.get(), l0.out_dim, s));
     st->launches += st->feat_csc_kernels;
   }
+  join_side();  // Adam needs every weight gradient
 }
 
 std::pair<real, real> GCN::finalize(cudaStream_t s) const {
@@ -492,7 +534,20 @@ std::pair<real, real> GCN::finalize(cudaStream_t s) const {
 std::pair<real, real> GCN::train_epoch() {
   const size_t before = st->launches;
   cudaStream_t s = st->stream;
+  CHECK_CUDA_ERROR(cudaEventRecord(st->ev_epoch, s));  // everything enqueued so far (previous epoch included)
   forward_pass(true, 1, s);
+  if ((st->use_side & 2) && st->dense_fast && !st->ext_masks[0].get() && params->dropouts.front() > 0.f) {
+    // keep bits of the next epoch's input dropout, on the side stream, into the other buffer (its last reader was
+    // the previous epoch's weight-gradient product, ordered by ev_epoch)
+    st->next_bits_rng = Variable::rng_descriptor();
+    st->next_bits_p = params->dropouts.front();
+    CHECK_CUDA_ERROR(cudaStreamWaitEvent(st->side, st->ev_epoch, 0));
+    GCNB_CALL(gcnb_dropout_maskbits(st->x_bits_next.get(), params->num_nodes, (int)params->input_dim, st->next_bits_p,
+                                    &st->next_bits_rng, st->side));
+    CHECK_CUDA_ERROR(cudaEventRecord(st->ev_bits, st->side));
+    st->launches++;
+    st->next_bits_valid = true;
+  }
   backward_pass(s);
   optimizer.step_on(s);
   st->launches++;
