@@ -190,7 +190,7 @@ def run_ours(args, rank, world, local_rank):
     eng = importlib.import_module("parallel_gcn_b200.engine")
     torch.cuda.set_device(local_rank)
     gcnb.device_check()
-    if world > 1:
+    if world > 1 or os.environ.get("GCNB_FORCE_DIST"):  # GCNB_FORCE_DIST: run the row-partitioned driver on one rank (debug)
         dist_mod = importlib.import_module("parallel_gcn_b200.dist")
         return dist_mod.bench_main(args, rank, world, local_rank, sys.modules[__name__])
 

@@ -748,13 +748,8 @@ int gcnb_spmm_plan_stage_ex(gcnb_spmm_plan *p, const uint32_t *h_indptr, const u
                             int64_t min_window_nnz, gcnb_stream_t stream_) {
   if (!p || !d_values) return GCNB_E_BADARG;
   cudaStream_t stream = as_stream(stream_);
-  if (p->staged && p->staged->dim == dim) return gather_values(p->staged, d_values, stream);  // values changed: re-gather
-  if (p->staged) {
-    GCNB_CHECK(cudaStreamSynchronize(stream));
-    stage_destroy(p->staged);
-    p->staged = nullptr;
-  }
   if (dim != 16 || p->n_rows == 0 || p->nnz == 0) return 0;  // only the dim-16 kernel exists; not an error
+  if (p->staged && p->staged->dim == dim) return gather_values(p->staged, d_values, stream);  // (new) values: re-gather
   std::vector<uint32_t> indptr_copy, indices_copy;
   if (!h_indptr) {
     indptr_copy.resize((size_t)p->n_rows + 1);

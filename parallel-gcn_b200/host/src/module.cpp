@@ -94,7 +94,11 @@ GraphSum::GraphSum(shared_ptr<Variable> in_, shared_ptr<Variable> out_, DevSpars
                    dev_shared_ptr<real> dev_graph_value_, natural dim_, bool generate_event_,
                    smart_event &start_matmul_backward_)
     : in(in_), out(out_), graph(graph_), dev_graph_value(dev_graph_value_), dim(dim_), generate_event(generate_event_),
-      start_matmul_backward(start_matmul_backward_), plans(plan_for(graph_, graph_->indptr_size - 1)) {}
+      start_matmul_backward(start_matmul_backward_), plans(plan_for(graph_, graph_->indptr_size - 1)) {
+  // graph_value is fixed for the life of the module: let the plan build its window-staged form for this width
+  // (no-op unless dim == 16 and the graph has column locality; the CSR is read back from the device once)
+  GCNB_CALL(gcnb_spmm_plan_stage(plans->plan, nullptr, nullptr, dev_graph_value.get(), (int)dim, nullptr));
+}
 
 void GraphSum::forward(bool, const smart_stream &stream) const {
   GCNB_CALL(gcnb_spmm_f32(plans->plan, dev_graph_value.get(), nullptr, in->dev_data.get(), out->dev_data.get(), dim,
