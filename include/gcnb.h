@@ -29,6 +29,7 @@ extern "C" {
 #define GCNB_API __attribute__((visibility("default")))
 #define GCNB_E_BADARG 10001
 #define GCNB_E_UNSUPPORTED 10002
+#define GCNB_E_COMM 10003 /* NCCL missing or a collective failed */
 
 typedef void *gcnb_stream_t; /* cudaStream_t */
 
@@ -219,6 +220,30 @@ GCNB_API int gcnb_adam_step_f32(const gcnb_adam_tensors_t *t, float weight_decay
 /* d_out[0] = sum_i w[i]^2 (ascending fixed tree).  d_ws: gcnb_sumsq_workspace(n) bytes. */
 GCNB_API int64_t gcnb_sumsq_workspace(int64_t n);
 GCNB_API int gcnb_sumsq_f32(const float *d_w, int64_t n, float *d_out, void *d_ws, gcnb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Communicator of the row-partitioned multi-GPU engine (one process per GPU).  The reference has no
+ * distributed path at all (single GPU: SURVEY 5.8), so there is no reference line to cite; the collectives below are
+ * the ones the partitioned epoch needs: all-gather of the [N/R x d] GraphSum input slab, sum all-reduce of the
+ * replicated weight gradients and of the loss / count scalars.  NCCL is loaded at run time (libnccl.so.2).
+ * Bootstrap: rank 0 calls gcnb_comm_unique_id and ships the GCNB_COMM_ID_BYTES to every rank by any side channel
+ * (bench.py: torch.distributed broadcast), then every rank calls gcnb_comm_create with its CUDA device current.
+ * world == 1 needs no id and no NCCL.
+ * ------------------------------------------------------------------------------------------------- */
+#define GCNB_COMM_ID_BYTES 128
+typedef struct gcnb_comm gcnb_comm;
+GCNB_API int gcnb_comm_unique_id(void *out_id /* GCNB_COMM_ID_BYTES */);
+GCNB_API int gcnb_comm_create(int rank, int world, const void *id_bytes, gcnb_comm **out);
+GCNB_API int gcnb_comm_destroy(gcnb_comm *c);
+GCNB_API int gcnb_comm_rank(const gcnb_comm *c);
+GCNB_API int gcnb_comm_world(const gcnb_comm *c);
+/* d_recv[world x count_per_rank] = concatenation of every rank's d_send[count_per_rank], in rank order */
+GCNB_API int gcnb_comm_all_gather_f32(gcnb_comm *c, const float *d_send, float *d_recv, int64_t count_per_rank,
+                                      gcnb_stream_t stream);
+/* in-place sum over ranks of `count` float32 (is_u32 = 0) or uint32 (is_u32 = 1) values */
+GCNB_API int gcnb_comm_all_reduce_sum(gcnb_comm *c, void *d_buf, int64_t count, int is_u32, gcnb_stream_t stream);
+GCNB_API int gcnb_comm_group_start(gcnb_comm *c);
+GCNB_API int gcnb_comm_group_end(gcnb_comm *c);
 
 #ifdef __cplusplus
 }

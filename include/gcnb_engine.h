@@ -53,9 +53,26 @@ GCNB_API int gcnb_dataset_dims(const gcnb_dataset *d, int64_t dims[10]);
 GCNB_API int gcnb_dataset_copy(const gcnb_dataset *d, int which, void *dst);
 GCNB_API int gcnb_dataset_free(gcnb_dataset *d);
 
+/* Row partition of one rank (multi-GPU).  The rank owns the contiguous global rows
+ * [row_offset, row_offset + cfg.num_nodes) of the adjacency, of the features, labels, split and of every activation;
+ * `block` (a multiple of 4, the same on every rank, >= every rank's row count, world * block >= n_global) is the slab
+ * size of the all-gather.  Graph column ids stay GLOBAL; graph_value must be given (it needs global degrees).
+ * cfg.num_nodes is the LOCAL row count; train/val/test sample counts are global and computed by all-reduce. */
+typedef struct {
+  gcnb_comm *comm;         /* from gcnb_comm_create; borrowed, must outlive the model */
+  int64_t n_global;        /* rows of the whole graph */
+  int64_t row_offset;      /* first global row of this rank */
+  int64_t block;           /* all-gather slab rows */
+  int64_t feat_elem_offset;/* global position of this rank's first feature value (sum of earlier ranks' feat_nnz) */
+  int64_t feat_nnz_global; /* feature values of the whole dataset */
+} gcnb_gcn_partition;
+
 /* ---- model (GCN) ---- */
 typedef struct gcnb_gcn gcnb_gcn;
 GCNB_API int gcnb_gcn_create(const gcnb_gcn_config *cfg, const gcnb_gcn_data *data, gcnb_gcn **out);
+/* same on one row block; every rank of the communicator must call it (collectives inside) */
+GCNB_API int gcnb_gcn_create_partitioned(const gcnb_gcn_config *cfg, const gcnb_gcn_data *data,
+                                         const gcnb_gcn_partition *part, gcnb_gcn **out);
 GCNB_API int gcnb_gcn_create_from_dataset(const gcnb_gcn_config *cfg, const gcnb_dataset *d, gcnb_gcn **out);
 GCNB_API int gcnb_gcn_destroy(gcnb_gcn *g);
 GCNB_API int gcnb_gcn_train_epoch(gcnb_gcn *g, float out_loss_acc[2]);

@@ -596,6 +596,7 @@ const char *gcnb_error_string(int code) {
   if (code == 0) return "success";
   if (code == GCNB_E_BADARG) return "gcnb: bad argument";
   if (code == GCNB_E_UNSUPPORTED) return "gcnb: unsupported shape/alignment";
+  if (code == GCNB_E_COMM) return "gcnb: NCCL unavailable or collective failed";
   return cudaGetErrorString((cudaError_t)code);
 }
 int gcnb_version(void) { return 100; }

@@ -23,6 +23,11 @@ class GcnData(C.Structure):
                 ("feat_indices", P), ("feat_value", P), ("feat_nnz", I64), ("label", P), ("split", P)]
 
 
+class GcnPartition(C.Structure):
+    _fields_ = [("comm", P), ("n_global", I64), ("row_offset", I64), ("block", I64), ("feat_elem_offset", I64),
+                ("feat_nnz_global", I64)]
+
+
 def _sig(name, res, args):
     fn = getattr(lib, name)
     fn.restype = res
@@ -35,6 +40,10 @@ _sig("gcnb_dataset_copy", I32, [P, I32, P])
 _sig("gcnb_dataset_free", I32, [P])
 _sig("gcnb_gcn_create", I32, [P, P, P])
 _sig("gcnb_gcn_create_from_dataset", I32, [P, P, P])
+_sig("gcnb_gcn_create_partitioned", I32, [P, P, P, P])
+_sig("gcnb_comm_unique_id", I32, [P])
+_sig("gcnb_comm_create", I32, [I32, I32, P, P])
+_sig("gcnb_comm_destroy", I32, [P])
 _sig("gcnb_gcn_destroy", I32, [P])
 _sig("gcnb_gcn_train_epoch", I32, [P, P])
 _sig("gcnb_gcn_eval", I32, [P, I32, P])
@@ -137,11 +146,48 @@ def synth_dataset(n, n_undirected_edges, n_features, n_classes, n_blocks=50, int
     return ds
 
 
+COMM_ID_BYTES = 128
+
+
+class Comm:
+    """gcnb_comm: the NCCL communicator of the row-partitioned engine.  `id_bytes` (rank 0: Comm.unique_id()) has to
+    reach every rank through a side channel (bench.py / scripts use a torch.distributed broadcast)."""
+
+    @staticmethod
+    def unique_id():
+        buf = (C.c_ubyte * COMM_ID_BYTES)()
+        check(lib.gcnb_comm_unique_id(buf))
+        return bytes(buf)
+
+    def __init__(self, rank, world, id_bytes=None):
+        self.rank, self.world = int(rank), int(world)
+        h = P()
+        buf = None if id_bytes is None else (C.c_ubyte * COMM_ID_BYTES).from_buffer_copy(id_bytes)
+        check(lib.gcnb_comm_create(self.rank, self.world, buf, C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None) and lib is not None:
+            lib.gcnb_comm_destroy(self.h)
+            self.h = None
+
+
+class PartDataset(HostDataset):
+    """row block of a dataset as produced by dist.partition_dataset, in HostDataset clothing (column ids global)."""
+
+    def __init__(self, part):
+        super().__init__(g_indptr=part["g_indptr"], g_indices=part["g_indices"], f_indptr=part["f_indptr"],
+                         f_indices=part["f_indices"], f_value=part["f_value"], label=part["label"], split=part["split"],
+                         graph_value=part["graph_value"], input_dim=part["input_dim"], output_dim=part["output_dim"])
+        self.part = part
+
+
 class GCN:
-    """The reference's GCN driver (GCN(params, adam_params, data); run(); private train_epoch/eval exposed)."""
+    """The reference's GCN driver (GCN(params, adam_params, data); run(); private train_epoch/eval exposed).
+    With `comm` (and ds = PartDataset) the model runs on one row block of a row-partitioned multi-GPU job."""
 
     def __init__(self, ds, hidden_dims=(16,), dropouts=(0.5, 0.5), epochs=100, early_stopping=0, lr=0.01, beta1=0.9,
-                 beta2=0.999, eps=1e-8, weight_decay=5e-4, seed=19990304, quiet=True, reorder=True):
+                 beta2=0.999, eps=1e-8, weight_decay=5e-4, seed=19990304, quiet=True, reorder=True, comm=None):
         self.ds = ds
         self.n_layers = len(hidden_dims) + 1
         assert len(dropouts) == self.n_layers
@@ -154,7 +200,13 @@ class GCN:
         data = GcnData(_p(ds.g_indptr), _p(ds.g_indices), len(ds.g_indices), _p(gv), _p(ds.f_indptr), _p(ds.f_indices),
                        _p(ds.f_value), len(ds.f_indices), _p(ds.label), _p(ds.split))
         h = P()
-        check(lib.gcnb_gcn_create(C.byref(cfg), C.byref(data), C.byref(h)))
+        if comm is None:
+            check(lib.gcnb_gcn_create(C.byref(cfg), C.byref(data), C.byref(h)))
+        else:
+            pt = ds.part
+            self.comm = comm  # keep alive: the model borrows it
+            part = GcnPartition(comm.h, pt["n_global"], pt["r0"], pt["block"], pt["f_elem_offset"], pt["f_nnz_global"])
+            check(lib.gcnb_gcn_create_partitioned(C.byref(cfg), C.byref(data), C.byref(part), C.byref(h)))
         self.h = h
         self.dims = [ds.input_dim] + [int(x) for x in hidden_dims] + [ds.output_dim]
 

@@ -84,6 +84,13 @@ class DevGCNData {
 
 struct GCNEngineState;  // plans, workspaces, captured graphs (src/gcn.cpp)
 
+// extension: row block of one rank in the multi-GPU engine (see gcnb_gcn_partition in include/gcnb_engine.h)
+struct gcnb_comm;
+struct GCNPartition {
+  gcnb_comm *comm = nullptr;
+  size_t n_global = 0, row_offset = 0, block = 0, feat_elem_offset = 0, feat_nnz_global = 0;
+};
+
 class GCN {
   GCNSmartObjects smart_objects;
   natural L;
@@ -103,7 +110,8 @@ class GCN {
   void backward_pass(cudaStream_t stream);
   std::pair<real, real> finalize(cudaStream_t stream) const;
   void print_variable_info() const;
-  void init(bool quiet, const natural *h_graph_indptr = nullptr, const natural *h_graph_indices = nullptr);
+  void init(bool quiet, const natural *h_graph_indptr = nullptr, const natural *h_graph_indices = nullptr,
+            const GCNPartition *part = nullptr);
 
  public:
   real avg_epoch_time;
@@ -122,6 +130,9 @@ class GCN {
 #endif
   GCN(GCNParams const *params_, AdamParams const *adam_params_, GCNData const *data_, bool quiet);
   GCN(GCNParams const *params_, AdamParams const *adam_params_, const GCNDataView &view, bool quiet);
+  // row-partitioned rank: params_->num_nodes = LOCAL rows, train/val/test_dim = GLOBAL counts, view = the row block
+  GCN(GCNParams const *params_, AdamParams const *adam_params_, const GCNDataView &view, const GCNPartition &part,
+      bool quiet);
   ~GCN();
   void run();
 

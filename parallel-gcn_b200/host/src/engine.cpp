@@ -128,6 +128,58 @@ int gcnb_gcn_create(const gcnb_gcn_config *cfg, const gcnb_gcn_data *data, gcnb_
   return 0;
 }
 
+int gcnb_gcn_create_partitioned(const gcnb_gcn_config *cfg, const gcnb_gcn_data *data, const gcnb_gcn_partition *part,
+                                gcnb_gcn **out) {
+  if (!cfg || !data || !part || !part->comm || !out || !data->graph_value) return GCNB_E_BADARG;
+  int sm = 0;
+  const int dc = gcnb_device_check(&sm);
+  if (dc) return dc;
+  auto g = std::make_unique<gcnb_gcn>();
+  int rc = fill_params(cfg, g.get());
+  if (rc) return rc;
+  const size_t n = (size_t)cfg->num_nodes;
+  // global split counts (CE normalisation, src/gcn.cu:214-219): local counts summed over the ranks
+  uint32_t counts[3] = {0, 0, 0};
+  for (size_t i = 0; i < n; i++)
+    if (data->split[i] >= 1 && data->split[i] <= 3) counts[data->split[i] - 1]++;
+  {
+    uint32_t *d = nullptr;
+    if (cudaMalloc((void **)&d, sizeof counts) != cudaSuccess) return (int)cudaGetLastError();
+    cudaMemcpy(d, counts, sizeof counts, cudaMemcpyHostToDevice);
+    rc = gcnb_comm_all_reduce_sum(part->comm, d, 3, 1, nullptr);
+    if (!rc) rc = (int)cudaMemcpy(counts, d, sizeof counts, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (rc) return rc;
+  }
+  g->params.train_dim = counts[0];
+  g->params.val_dim = counts[1];
+  g->params.test_dim = counts[2];
+  GCNDataView v{};
+  v.graph_indptr = data->graph_indptr;
+  v.graph_indices = data->graph_indices;
+  v.graph_nnz = (size_t)data->graph_nnz;
+  v.graph_value = data->graph_value;
+  v.feat_indptr = data->feat_indptr;
+  v.feat_indices = data->feat_indices;
+  v.feat_value = data->feat_value;
+  v.feat_nnz = (size_t)data->feat_nnz;
+  v.label = data->label;
+  v.split = data->split;
+  v.num_nodes = n;
+  GCNPartition p;
+  p.comm = part->comm;
+  p.n_global = (size_t)part->n_global;
+  p.row_offset = (size_t)part->row_offset;
+  p.block = (size_t)part->block;
+  p.feat_elem_offset = (size_t)part->feat_elem_offset;
+  p.feat_nnz_global = (size_t)part->feat_nnz_global;
+  g->gcn = std::make_unique<GCN>(&g->params, &g->adam, v, p, cfg->quiet != 0);
+  if (!cfg->reorder) g->gcn->set_reorder(false);
+  g->masks.assign(g->params.n_layers, nullptr);
+  *out = g.release();
+  return 0;
+}
+
 int gcnb_gcn_create_from_dataset(const gcnb_gcn_config *cfg, const gcnb_dataset *d, gcnb_gcn **out) {
   if (!cfg || !d || !out) return GCNB_E_BADARG;
   gcnb_gcn_config c = *cfg;

@@ -104,6 +104,12 @@ struct GCNEngineState {
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_bits = nullptr, ev_epoch = nullptr;
   bool side_pending = false;  // side-stream work of this backward pass not yet joined
+  // row-partitioned multi-GPU mode: this rank owns global rows [row0, row0 + N); GraphSum inputs are
+  // all-gathered in slabs of `block` rows, weight gradients and the loss / count scalars are sum-all-reduced
+  gcnb_comm *comm = nullptr;
+  bool dist = false;
+  size_t n_global = 0, row0 = 0, block = 0, f_elem_off = 0, f_nnz_global = 0;
+  dev_shared_ptr<real> gather_buf;  // [world * block x max GraphSum width]
   int use_side = 3;           // bit 0: side stream for weight gradients, bit 1: prefetch next epoch's dropout bits
   const natural *x_train_bits = nullptr;
   real x_train_p = 0.f;
@@ -136,6 +142,11 @@ struct GCNEngineState {
           gs_events.push_back(e);
         }
       CHECK_CUDA_ERROR(cudaEventRecord(gs_events[gs_used], stream));
+    }
+    if (dist) {
+      // the slab [block x dim] of every rank, concatenated in rank order, IS the global [N x dim] matrix
+      GCNB_CALL(gcnb_comm_all_gather_f32(comm, in, gather_buf.get(), (int64_t)block * dim, stream));
+      in = gather_buf.get();
     }
     GCNB_CALL(gcnb_spmm_f32(graph_plan, gv, nullptr, in, out, dim, stream));
     if (time_graphsum) {
@@ -178,7 +189,14 @@ GCN::GCN(GCNParams const *params_, AdamParams const *adam_params_, const GCNData
   init(quiet, view.graph_indptr, view.graph_indices);
 }
 
-void GCN::init(bool quiet, const natural *h_graph_indptr, const natural *h_graph_indices) {
+GCN::GCN(GCNParams const *params_, AdamParams const *adam_params_, const GCNDataView &view, const GCNPartition &part,
+         bool quiet)
+    : smart_objects(params_->n_layers), data(nullptr), dev_data{DevGCNData(view)}, params(params_),
+      adam_params(adam_params_) {
+  init(quiet, view.graph_indptr, view.graph_indices, &part);
+}
+
+void GCN::init(bool quiet, const natural *h_graph_indptr, const natural *h_graph_indices, const GCNPartition *part) {
   int sm = 0;
   GCNB_CALL(gcnb_device_check(&sm));  // no CPU fallback: a missing/unsupported GPU is fatal here
   L = params->n_layers;
@@ -189,6 +207,21 @@ void GCN::init(bool quiet, const natural *h_graph_indptr, const natural *h_graph
   avg_epoch_time = total_time = last_val_accuracy = 0;
   st = std::make_shared<GCNEngineState>();
   st->quiet = quiet;
+  if (part) {
+    const size_t world = (size_t)gcnb_comm_world(part->comm);
+    if (!part->comm || part->block % 4 != 0 || part->block < params->num_nodes || world * part->block < part->n_global ||
+        part->row_offset + params->num_nodes > part->n_global || params->num_nodes == 0) {
+      std::cerr << "GCN: inconsistent row partition" << std::endl;
+      exit(1);
+    }
+    st->comm = part->comm;
+    st->dist = true;
+    st->n_global = part->n_global;
+    st->row0 = part->row_offset;
+    st->block = part->block;
+    st->f_elem_off = part->feat_elem_offset;
+    st->f_nnz_global = part->feat_nnz_global;
+  }
   CHECK_CUDA_ERROR(cudaStreamCreateWithFlags(&st->stream, cudaStreamNonBlocking));
   if (const char *e = getenv("GCNB_SIDE_STREAM")) st->use_side = atoi(e);  // tuning probe: 0 = single stream
   if (st->use_side & 1) CHECK_CUDA_ERROR(cudaStreamCreateWithFlags(&st->side, cudaStreamNonBlocking));
@@ -201,8 +234,10 @@ void GCN::init(bool quiet, const natural *h_graph_indptr, const natural *h_graph
   decays.front() = true;
 
   // plans (built once; the reference re-derives its launch shape from CudaParams on every call)
+  // rows of every activation buffer: a partitioned rank allocates whole all-gather slabs (rows beyond N are padding)
+  const size_t rows_alloc = st->dist ? st->block : N;
   GCNB_CALL(gcnb_spmm_plan_create(dev_data.dev_graph_index.dev_indptr.get(), dev_data.dev_graph_index.dev_indices.get(),
-                                  N, N, 0, st->stream, &st->graph_plan));
+                                  N, st->dist ? (int64_t)st->n_global : (int64_t)N, 0, st->stream, &st->graph_plan));
   GCNB_CALL(gcnb_csc_create(dev_data.dev_feature_index.dev_indptr.get(), dev_data.dev_feature_index.dev_indices.get(), N,
                             F, st->stream, &st->feat_csc));
   const uint32_t *colptr = nullptr, *rowidx = nullptr;
@@ -241,20 +276,30 @@ void GCN::init(bool quiet, const natural *h_graph_indptr, const natural *h_graph
     ly.out_dim = dims[l + 1];
     ly.reorder = (l > 0) && st->allow_reorder && (ly.in_dim < ly.out_dim);
     const natural pre_dim = ly.reorder ? ly.in_dim : ly.out_dim;
-    ly.pre = std::make_shared<Variable>(N * pre_dim);
+    ly.pre = std::make_shared<Variable>(rows_alloc * pre_dim);
     variables.push_back(ly.pre);
     variables_info += "layer" + std::to_string(l + 1) + "_var1:   " + std::to_string(ly.pre->size) + "\n";
     auto w = std::make_shared<Variable>(ly.in_dim * ly.out_dim, true, true, ly.in_dim, ly.out_dim);
     variables.push_back(w);
     weights.push_back(w);
     variables_info += "layer" + std::to_string(l + 1) + "_weight: " + std::to_string(w->size) + "\n";
-    ly.z = std::make_shared<Variable>(N * ly.out_dim, true, l + 1 < L);
+    ly.z = std::make_shared<Variable>(rows_alloc * ly.out_dim, true, l + 1 < L);
     variables.push_back(ly.z);
     variables_info += "layer" + std::to_string(l + 1) + "_var2:   " + std::to_string(ly.z->size) + (l + 1 < L ? "\n" : "");
     if (l + 1 < L) ly.mask = dev_shared_ptr<unsigned char>(ly.z->size);
     tn_need = std::max(tn_need, gcnb_matmul_tn_workspace(N, ly.in_dim, ly.out_dim));
   }
   output = st->layers.back().z;
+  if (st->dist) {
+    natural dmax = 0;
+    for (size_t i = 1; i < dims.size(); i++) dmax = std::max(dmax, dims[i]);
+    st->gather_buf = dev_shared_ptr<real>((size_t)gcnb_comm_world(st->comm) * st->block * dmax);
+    for (GCNLayer &ly : st->layers)  // padding rows are shipped by the all-gather: keep them defined
+      for (const shared_ptr<Variable> &v : {ly.pre, ly.z}) {
+        if (v->dev_data.get()) CHECK_CUDA_ERROR(cudaMemset(v->dev_data.get(), 0, (size_t)v->size * sizeof(real)));
+        if (v->dev_grad.get()) CHECK_CUDA_ERROR(cudaMemset(v->dev_grad.get(), 0, (size_t)v->size * sizeof(real)));
+      }
+  }
   {
     // graph_value never changes: give GraphSum at width 16 the window-staged representation (shared-memory gathers
     // for the clustered part of the adjacency, see csrc/spmm_stage.cu); a no-op for graphs without column locality
@@ -305,13 +350,17 @@ void GCN::set_quiet(bool q) { st->quiet = q; }
 void GCN::set_use_cuda_graph(bool on) { st->use_graph = on; }
 void GCN::set_reorder(bool on) {
   st->allow_reorder = on;
-  const natural N = params->num_nodes;
+  const size_t N = st->dist ? st->block : params->num_nodes;
   for (natural l = 1; l < L; l++) {
     GCNLayer &ly = st->layers[l];
     const bool want = on && (ly.in_dim < ly.out_dim);
     if (want == ly.reorder) continue;
     ly.reorder = want;
     *ly.pre = Variable(N * (want ? ly.in_dim : ly.out_dim));
+    if (st->dist) {
+      CHECK_CUDA_ERROR(cudaMemset(ly.pre->dev_data.get(), 0, (size_t)ly.pre->size * sizeof(real)));
+      if (ly.pre->dev_grad.get()) CHECK_CUDA_ERROR(cudaMemset(ly.pre->dev_grad.get(), 0, (size_t)ly.pre->size * sizeof(real)));
+    }
   }
 }
 size_t GCN::launches_per_epoch() const { return st->launches_last_epoch; }
@@ -371,8 +420,19 @@ void GCN::set_truth(const natural current_split, cudaStream_t stream) const {
   st->launches++;
 }
 
+// Philox descriptor for an op whose local element 0 is GLOBAL element e0 (partition-independent masks)
+static gcnb_rng_t rng_at(size_t e0) {
+  gcnb_rng_t r = Variable::rng_descriptor();
+  r.group_offset = (uint32_t)(e0 / 4);
+  r.elem_lead = (uint32_t)(e0 % 4);
+  return r;
+}
+
 void GCN::forward_pass(bool training, natural split, cudaStream_t s) {
   const natural N = params->num_nodes, F = params->input_dim;
+  // RNG consumption is counted in GLOBAL elements so that every rank walks the same Philox streams
+  const size_t input_elems = st->dist ? st->f_nnz_global : (size_t)input->size;
+  const size_t rows_global = st->dist ? st->n_global : (size_t)N;
   set_truth(split, s);
   // ---- layer 0: features never overwritten; training writes the dropped copy into `input`
   const real *xvals = dev_data.dev_feature_value.get();
@@ -382,7 +442,7 @@ void GCN::forward_pass(bool training, natural split, cudaStream_t s) {
     // dense features: only the keep bits are generated (17.5 MB for Reddit); X itself is streamed by the products
     const real p0 = params->dropouts.front();
     if (p0 > 0.f) {
-      const gcnb_rng_t rng = Variable::rng_descriptor();
+      const gcnb_rng_t rng = rng_at(st->f_elem_off);
       if (st->next_bits_valid && st->next_bits_p == p0 && std::memcmp(&rng, &st->next_bits_rng, sizeof(rng)) == 0) {
         std::swap(st->x_bits, st->x_bits_next);  // generated on the side stream during the previous epoch
         CHECK_CUDA_ERROR(cudaStreamWaitEvent(s, st->ev_bits, 0));
@@ -394,7 +454,7 @@ void GCN::forward_pass(bool training, natural split, cudaStream_t s) {
       xbits = st->x_bits.get();
       xp = p0;
     }
-    Variable::rng_consume(input->size);
+    Variable::rng_consume(input_elems);
     st->x_train_vals = xvals;
     st->x_train_bits = xbits;
     st->x_train_p = xp;
@@ -404,12 +464,12 @@ void GCN::forward_pass(bool training, natural split, cudaStream_t s) {
     st->x_train_bits = nullptr;
     st->x_train_p = 0.f;
     if (p0 > 0.f || ext) {
-      const gcnb_rng_t rng = Variable::rng_descriptor();
+      const gcnb_rng_t rng = rng_at(st->f_elem_off);
       GCNB_CALL(gcnb_dropout_fwd_oop_f32(xvals, input->dev_data.get(), nullptr, ext, input->size, p0, &rng, s));
       st->launches++;
       xvals = input->dev_data.get();
     }
-    Variable::rng_consume(input->size);  // the reference draws even when p == 0
+    Variable::rng_consume(input_elems);  // the reference draws even when p == 0
     st->x_train_vals = xvals;
   }
   {
@@ -444,16 +504,22 @@ void GCN::forward_pass(bool training, natural split, cudaStream_t s) {
     }
     if (l + 1 < L) {
       const real p = params->dropouts[l + 1];
-      const gcnb_rng_t rng = Variable::rng_descriptor();
-      GCNB_CALL(gcnb_relu_dropout_fwd_f32(ly.z->dev_data.get(), ly.mask.get(), st->ext_masks[l + 1].get(), ly.z->size, p,
-                                          training, &rng, s));
+      const gcnb_rng_t rng = rng_at(st->row0 * ly.out_dim);
+      GCNB_CALL(gcnb_relu_dropout_fwd_f32(ly.z->dev_data.get(), ly.mask.get(), st->ext_masks[l + 1].get(),
+                                          (size_t)N * ly.out_dim, p, training, &rng, s));
       st->launches++;
-      if (training) Variable::rng_consume(ly.z->size);
+      if (training) Variable::rng_consume(rows_global * ly.out_dim);
     }
   }
   // ---- loss + accuracy (one kernel) and the L2 term of the decayed weights
   GCNB_CALL(gcnb_softmax_ce_f32(output->dev_data.get(), output->dev_grad.get(), dev_truth.get(), N, params->output_dim,
                                 st->cur_num_samples, training, st->dev_result.get(), st->ce_ws.get(), s));
+  if (st->dist) {  // loss sum (float) and wrong / labelled counts (uint32 bit patterns) over all row blocks
+    GCNB_CALL(gcnb_comm_group_start(st->comm));
+    GCNB_CALL(gcnb_comm_all_reduce_sum(st->comm, st->dev_result.get(), 1, 0, s));
+    GCNB_CALL(gcnb_comm_all_reduce_sum(st->comm, st->dev_result.get() + 1, 2, 1, s));
+    GCNB_CALL(gcnb_comm_group_end(st->comm));
+  }
   GCNB_CALL(gcnb_sumsq_f32(weights[0]->dev_data.get(), weights[0]->size, st->dev_result.get() + 4, st->sumsq_ws.get(), s));
   CHECK_CUDA_ERROR(cudaMemcpyAsync(st->host_result.get(), st->dev_result.get(), 8 * sizeof(real), cudaMemcpyDeviceToHost, s));
   st->launches += 2;
@@ -487,7 +553,8 @@ void GCN::backward_pass(cudaStream_t s) {
                                    ly.in_dim, ly.out_dim, s));
     }
     st->side_pending = true;
-    GCNB_CALL(gcnb_relu_dropout_bwd_f32(prev.z->dev_grad.get(), prev.mask.get(), prev.z->size, params->dropouts[l], s));
+    GCNB_CALL(gcnb_relu_dropout_bwd_f32(prev.z->dev_grad.get(), prev.mask.get(), (size_t)N * prev.out_dim,
+                                        params->dropouts[l], s));
     st->launches += 2 + 1 + 1;  // split-K weight gradient (2 kernels), dA product, mask kernel
     g = prev.z->dev_grad.get();
   }
@@ -515,6 +582,12 @@ void GCN::backward_pass(cudaStream_t s) {
     st->launches += st->feat_csc_kernels;
   }
   join_side();  // Adam needs every weight gradient
+  if (st->dist) {   // replicated weights: sum the row blocks' contributions (one grouped call for all layers)
+    GCNB_CALL(gcnb_comm_group_start(st->comm));
+    for (natural l = 0; l < L; l++)
+      GCNB_CALL(gcnb_comm_all_reduce_sum(st->comm, weights[l]->dev_grad.get(), (int64_t)weights[l]->size, 0, s));
+    GCNB_CALL(gcnb_comm_group_end(st->comm));
+  }
 }
 
 std::pair<real, real> GCN::finalize(cudaStream_t s) const {
@@ -539,7 +612,7 @@ std::pair<real, real> GCN::train_epoch() {
   if ((st->use_side & 2) && st->dense_fast && !st->ext_masks[0].get() && params->dropouts.front() > 0.f) {
     // keep bits of the next epoch's input dropout, on the side stream, into the other buffer (its last reader was
     // the previous epoch's weight-gradient product, ordered by ev_epoch)
-    st->next_bits_rng = Variable::rng_descriptor();
+    st->next_bits_rng = rng_at(st->f_elem_off);
     st->next_bits_p = params->dropouts.front();
     CHECK_CUDA_ERROR(cudaStreamWaitEvent(st->side, st->ev_epoch, 0));
     GCNB_CALL(gcnb_dropout_maskbits(st->x_bits_next.get(), params->num_nodes, (int)params->input_dim, st->next_bits_p,

@@ -200,3 +200,23 @@ def test_dist_driver_single_rank_matches_engine(O, eng, gcnb, dev, datasets):
         for l in range(2):
             assert_close(to_np(dg.W[l]), g.weight(l), rtol=1e-6, atol=1e-7, what="dist W%d" % l)
         g.close()
+
+
+def test_native_partitioned_engine_single_rank_matches_engine(eng, datasets):
+    """the row-partitioned native engine (gcnb_gcn_create_partitioned, csrc/comm.cu) on ONE rank: slab-padded buffers,
+    global RNG offsets and the (degenerate) collectives must reproduce the plain engine bit for bit; the N-rank case is
+    scripts/dist_check_native.py (needs N GPUs)."""
+    import importlib
+    dmod = importlib.import_module("parallel_gcn_b200.dist")
+    ds = eng.parse_dataset(ROOT, "citeseer")
+    comm = eng.Comm(0, 1)
+    g = eng.GCN(eng.PartDataset(dmod.partition_dataset(ds, 0, 1)), comm=comm)
+    h = eng.GCN(ds)
+    for _ in range(3):
+        assert g.train_epoch() == h.train_epoch()
+        assert g.eval(2) == h.eval(2)
+    for l in range(2):
+        assert np.array_equal(g.weight(l), h.weight(l))
+    g.close()
+    h.close()
+    comm.close()
