@@ -61,14 +61,19 @@ ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--stage", type=int, default=1)
 ap.add_argument("--min-seg", type=int, nargs="*", default=[0])
 ap.add_argument("--seg-cap", type=int, nargs="*", default=[0])
+ap.add_argument("--rows-div", type=int, nargs="*", default=[1], help="keep only the first N/div rows (a rank's row block)")
 ap.add_argument("--out", default="gpurun_out/probe_graphsum.json")
 args = ap.parse_args()
 res = []
-for intra in args.intra:
+for intra, div in [(a, b) for a in args.intra for b in args.rows_div]:
     indptr, cols, vals, nnz = make(intra)
+    nrows = N // div
+    if div > 1:
+        nnz = int(indptr[nrows])
+        indptr, cols, vals = indptr[: nrows + 1].contiguous(), cols[:nnz].contiguous(), vals[:nnz].contiguous()
     for dim in args.dim:
         x = torch.randn(N, dim, device=dev)
-        out = torch.empty(N, dim, device=dev)
+        out = torch.empty(nrows, dim, device=dev)
         for seg in args.seg:
           for min_seg in args.min_seg:
             for seg_cap in args.seg_cap:
@@ -82,8 +87,8 @@ for intra in args.intra:
                     build_s = round(time.time() - t0, 2)
                 us = bench(plan, vals, x, out, dim, args.iters)
                 err = float((out - ref).abs().max() / ref.abs().max())
-                alg = 4 * (N + 1) + 8 * nnz + 8 * N * dim
-                r = dict(intra=intra, dim=dim, seg=seg, min_seg=min_seg, seg_cap=seg_cap, nnz=nnz, us_generic=round(us0, 1),
+                alg = 4 * (nrows + 1) + 8 * nnz + 4 * (N + nrows) * dim
+                r = dict(rows_div=div, intra=intra, dim=dim, seg=seg, min_seg=min_seg, seg_cap=seg_cap, nnz=nnz, us_generic=round(us0, 1),
                          us=round(us, 1), alg_GBs=round(alg / us / 1e3, 1), rel_diff_vs_generic=err, stage=sinfo,
                          stage_build_s=build_s, info=plan.info())
                 print(json.dumps(r), flush=True)
