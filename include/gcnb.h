@@ -242,6 +242,16 @@ GCNB_API int gcnb_comm_all_gather_f32(gcnb_comm *c, const float *d_send, float *
                                       gcnb_stream_t stream);
 /* in-place sum over ranks of `count` float32 (is_u32 = 0) or uint32 (is_u32 = 1) values */
 GCNB_API int gcnb_comm_all_reduce_sum(gcnb_comm *c, void *d_buf, int64_t count, int is_u32, gcnb_stream_t stream);
+/* Slab gather for the row-partitioned GraphSum (the all-gather of the [N/R x d] input slab) over NVLink
+ * peer memory: gcnb_comm_gather_setup (collective, once) allocates two gather buffers of `gather_floats` per rank and
+ * opens every peer's through CUDA IPC; gcnb_comm_gather_slabs_f32 then stores this rank's slab into slot `rank` of
+ * every rank's buffer and waits for the peers' flags (falls back to ncclAllGather, collectively, when peer memory is
+ * unavailable).  *d_full_out (owned by the communicator, valid until the next-but-one gather) holds the world slabs
+ * in rank order.  gcnb_comm_gather_mode: 0 single rank, 1 NCCL all-gather, 2 peer-memory push. */
+GCNB_API int gcnb_comm_gather_setup(gcnb_comm *c, int64_t gather_floats);
+GCNB_API int gcnb_comm_gather_slabs_f32(gcnb_comm *c, const float *d_slab, int64_t count_per_rank,
+                                        const float **d_full_out, gcnb_stream_t stream);
+GCNB_API int gcnb_comm_gather_mode(const gcnb_comm *c);
 GCNB_API int gcnb_comm_group_start(gcnb_comm *c);
 GCNB_API int gcnb_comm_group_end(gcnb_comm *c);
 

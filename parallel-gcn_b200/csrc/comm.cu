@@ -7,9 +7,12 @@
 #include <dlfcn.h>
 #include <nccl.h>  // types and enums only; no symbol of libnccl is linked
 
+#include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 #include "common.cuh"
 
@@ -61,10 +64,69 @@ int nccl_rc(ncclResult_t r) {
 
 }  // namespace
 
+constexpr int kMaxWorld = 16;
+
+// peer-memory slab exchange (NVLink / NVSwitch): every rank owns two gather buffers and a flag word per peer, opened
+// in every other process through CUDA IPC
+struct P2PPeers {
+  float *gather[2][kMaxWorld];
+  uint32_t *flags[kMaxWorld];
+  int world, rank;
+};
+
 struct gcnb_comm {
   ncclComm_t comm = nullptr;
   int rank = 0, world = 1;
+  // slab gather state
+  float *gather_local[2] = {nullptr, nullptr};
+  uint32_t *flags_local = nullptr;
+  unsigned int *d_ticket = nullptr;
+  int64_t gather_floats = 0;
+  bool p2p = false;
+  P2PPeers peers{};
+  void *opened[3 * kMaxWorld] = {nullptr};
+  int n_opened = 0;
+  uint32_t epoch = 0;
 };
+
+namespace {
+
+// rank r's slab -> slot r of EVERY rank's gather buffer (its own included), then one flag per peer: "slab `epoch` of
+// rank r has landed".  The last CTA to finish publishes the flags (system-scope fence before, release stores).
+__global__ void __launch_bounds__(256)
+p2p_push_kernel(const float4 *__restrict__ slab, int64_t n4, P2PPeers peers, int buf, int64_t slot_off4, uint32_t epoch,
+                unsigned int *__restrict__ ticket) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(slab + i);
+    for (int p = 0; p < peers.world; p++) reinterpret_cast<float4 *>(peers.gather[buf][p])[slot_off4 + i] = v;
+  }
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool last;
+  if (threadIdx.x == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (last) {
+    __threadfence_system();
+    if (threadIdx.x < peers.world) {
+      uint32_t *f = peers.flags[threadIdx.x] + peers.rank;
+      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(epoch) : "memory");
+    }
+    if (threadIdx.x == 0) *ticket = 0;
+  }
+}
+
+// wait until every rank's slab `epoch` has landed in this rank's buffer
+__global__ void p2p_wait_kernel(const uint32_t *__restrict__ flags, int world, uint32_t epoch) {
+  if (threadIdx.x < world) {
+    uint32_t v;
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + threadIdx.x) : "memory");
+    } while ((int32_t)(v - epoch) < 0);
+  }
+  __threadfence_system();
+}
+
+}  // namespace
 
 extern "C" {
 
@@ -109,8 +171,131 @@ int gcnb_comm_create(int rank, int world, const void *id_bytes, gcnb_comm **out)
 
 int gcnb_comm_destroy(gcnb_comm *c) {
   if (!c) return 0;
+  cudaDeviceSynchronize();
+  for (int i = 0; i < c->n_opened; i++) cudaIpcCloseMemHandle(c->opened[i]);
+  cudaFree(c->gather_local[0]);
+  cudaFree(c->gather_local[1]);
+  cudaFree(c->flags_local);
+  cudaFree(c->d_ticket);
   if (c->comm) nccl().CommDestroy(c->comm);
   delete c;
+  return 0;
+}
+
+// Allocates the slab-gather buffers (two, `gather_floats` each) and tries to open every peer's buffers through CUDA
+// IPC.  If any rank cannot (no peer access, IPC unavailable), ALL ranks fall back to ncclAllGather into the local
+// buffer -- still a device collective, decided collectively so that no rank waits for a push that never comes.
+int gcnb_comm_gather_setup(gcnb_comm *c, int64_t gather_floats) {
+  if (!c || gather_floats <= 0) return GCNB_E_BADARG;
+  if (c->gather_local[0] && c->gather_floats >= gather_floats) return 0;
+  if (c->gather_local[0]) {
+    // a later, larger model on the same communicator: start over (every rank takes this branch -- sizes are equal on
+    // all ranks -- and the handle exchange below is a barrier; nobody pushes for the finished model any more)
+    GCNB_CHECK(cudaDeviceSynchronize());
+    for (int i = 0; i < c->n_opened; i++) cudaIpcCloseMemHandle(c->opened[i]);
+    c->n_opened = 0;
+    cudaFree(c->gather_local[0]);
+    cudaFree(c->gather_local[1]);
+    cudaFree(c->flags_local);
+    cudaFree(c->d_ticket);
+    c->gather_local[0] = c->gather_local[1] = nullptr;
+    c->flags_local = nullptr;
+    c->d_ticket = nullptr;
+    c->p2p = false;
+    c->epoch = 0;
+  }
+  c->gather_floats = gather_floats;
+  for (int b = 0; b < 2; b++) {
+    GCNB_CHECK(cudaMalloc((void **)&c->gather_local[b], (size_t)gather_floats * 4));
+    GCNB_CHECK(cudaMemset(c->gather_local[b], 0, (size_t)gather_floats * 4));
+  }
+  GCNB_CHECK(cudaMalloc((void **)&c->flags_local, kMaxWorld * 4));
+  GCNB_CHECK(cudaMemset(c->flags_local, 0, kMaxWorld * 4));
+  GCNB_CHECK(cudaMalloc((void **)&c->d_ticket, 4));
+  GCNB_CHECK(cudaMemset(c->d_ticket, 0, 4));
+  c->peers.world = c->world;
+  c->peers.rank = c->rank;
+  if (c->world == 1) return 0;
+  const char *env = getenv("GCNB_P2P");  // GCNB_P2P=0: force the NCCL all-gather (A/B measurements)
+  int ok = (c->world <= kMaxWorld) && !(env && atoi(env) == 0);
+  // exchange the IPC handles (3 per rank) with one all-gather of raw bytes
+  struct Handles {
+    cudaIpcMemHandle_t h[3];
+  };
+  static_assert(sizeof(Handles) % 4 == 0, "handles travel as float words");
+  Handles mine{};
+  if (ok) {
+    ok = cudaIpcGetMemHandle(&mine.h[0], c->gather_local[0]) == cudaSuccess &&
+         cudaIpcGetMemHandle(&mine.h[1], c->gather_local[1]) == cudaSuccess &&
+         cudaIpcGetMemHandle(&mine.h[2], c->flags_local) == cudaSuccess;
+    if (!ok) cudaGetLastError();
+  }
+  Handles *d_all = nullptr;
+  GCNB_CHECK(cudaMalloc((void **)&d_all, sizeof(Handles) * c->world));
+  GCNB_CHECK(cudaMemcpy(d_all + c->rank, &mine, sizeof(Handles), cudaMemcpyHostToDevice));
+  int rc = nccl_rc(nccl().AllGather(d_all + c->rank, d_all, sizeof(Handles) / 4, ncclFloat, c->comm, nullptr));
+  std::vector<Handles> all((size_t)c->world);
+  if (!rc) rc = (int)cudaMemcpy(all.data(), d_all, sizeof(Handles) * c->world, cudaMemcpyDeviceToHost);
+  cudaFree(d_all);
+  if (rc) return rc;
+  for (int p = 0; p < c->world && ok; p++) {
+    if (p == c->rank) {
+      c->peers.gather[0][p] = c->gather_local[0];
+      c->peers.gather[1][p] = c->gather_local[1];
+      c->peers.flags[p] = c->flags_local;
+      continue;
+    }
+    void *ptr[3] = {nullptr, nullptr, nullptr};
+    for (int k = 0; k < 3 && ok; k++) {
+      ok = cudaIpcOpenMemHandle(&ptr[k], all[p].h[k], cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+      if (ok) c->opened[c->n_opened++] = ptr[k];
+      else cudaGetLastError();
+    }
+    c->peers.gather[0][p] = (float *)ptr[0];
+    c->peers.gather[1][p] = (float *)ptr[1];
+    c->peers.flags[p] = (uint32_t *)ptr[2];
+  }
+  // collective decision: everybody pushes or nobody does
+  uint32_t *d_ok = nullptr;
+  uint32_t h_ok = ok ? 1u : 0u;
+  GCNB_CHECK(cudaMalloc((void **)&d_ok, 4));
+  GCNB_CHECK(cudaMemcpy(d_ok, &h_ok, 4, cudaMemcpyHostToDevice));
+  rc = nccl_rc(nccl().AllReduce(d_ok, d_ok, 1, ncclUint32, ncclSum, c->comm, nullptr));
+  if (!rc) rc = (int)cudaMemcpy(&h_ok, d_ok, 4, cudaMemcpyDeviceToHost);
+  cudaFree(d_ok);
+  if (rc) return rc;
+  c->p2p = h_ok == (uint32_t)c->world;
+  return 0;
+}
+
+int gcnb_comm_gather_mode(const gcnb_comm *c) { return c ? (c->world == 1 ? 0 : (c->p2p ? 2 : 1)) : 0; }
+
+// *d_full_out = [world x count_per_rank] floats: slab of rank r at r * count_per_rank.  Peer-memory mode: this rank's
+// slab is stored straight into every rank's buffer over NVLink and a flag per (writer, reader) pair tells the reader
+// when it has landed -- one copy kernel + one wait kernel, no ring / tree schedule.  Two buffers alternate: a rank can
+// be at most one exchange ahead of a peer (it needed that peer's previous slab to get there), so the buffer it
+// overwrites has been consumed.
+int gcnb_comm_gather_slabs_f32(gcnb_comm *c, const float *d_slab, int64_t count_per_rank, const float **d_full_out,
+                               gcnb_stream_t s) {
+  if (!c || !d_slab || !d_full_out || count_per_rank <= 0 || !c->gather_local[0]) return GCNB_E_BADARG;
+  if (count_per_rank * c->world > c->gather_floats || count_per_rank % 4 || ((uintptr_t)d_slab % 16)) return GCNB_E_BADARG;
+  cudaStream_t st = as_stream(s);
+  const uint32_t epoch = ++c->epoch;
+  const int buf = (int)(epoch & 1u);
+  float *full = c->gather_local[buf];
+  *d_full_out = full;
+  if (c->world == 1) {
+    GCNB_CHECK(cudaMemcpyAsync(full, d_slab, (size_t)count_per_rank * 4, cudaMemcpyDeviceToDevice, st));
+    return 0;
+  }
+  if (!c->p2p) return nccl_rc(nccl().AllGather(d_slab, full, (size_t)count_per_rank, ncclFloat, c->comm, st));
+  const int64_t n4 = count_per_rank / 4;
+  const int blocks = (int)std::min<int64_t>((n4 + 255) / 256, (int64_t)std::max(1, gcnb::device_info().sm_count) * 2);
+  p2p_push_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float4 *>(d_slab), n4, c->peers, buf,
+                                          (int64_t)c->rank * n4, epoch, c->d_ticket);
+  GCNB_LAUNCH_CHECK();
+  p2p_wait_kernel<<<1, 32, 0, st>>>(c->flags_local, c->world, epoch);
+  GCNB_LAUNCH_CHECK();
   return 0;
 }
 

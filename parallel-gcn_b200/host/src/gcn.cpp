@@ -109,7 +109,6 @@ struct GCNEngineState {
   gcnb_comm *comm = nullptr;
   bool dist = false;
   size_t n_global = 0, row0 = 0, block = 0, f_elem_off = 0, f_nnz_global = 0;
-  dev_shared_ptr<real> gather_buf;  // [world * block x max GraphSum width]
   int use_side = 3;           // bit 0: side stream for weight gradients, bit 1: prefetch next epoch's dropout bits
   const natural *x_train_bits = nullptr;
   real x_train_p = 0.f;
@@ -145,8 +144,7 @@ struct GCNEngineState {
     }
     if (dist) {
       // the slab [block x dim] of every rank, concatenated in rank order, IS the global [N x dim] matrix
-      GCNB_CALL(gcnb_comm_all_gather_f32(comm, in, gather_buf.get(), (int64_t)block * dim, stream));
-      in = gather_buf.get();
+      GCNB_CALL(gcnb_comm_gather_slabs_f32(comm, in, (int64_t)block * dim, &in, stream));
     }
     GCNB_CALL(gcnb_spmm_f32(graph_plan, gv, nullptr, in, out, dim, stream));
     if (time_graphsum) {
@@ -293,7 +291,7 @@ void GCN::init(bool quiet, const natural *h_graph_indptr, const natural *h_graph
   if (st->dist) {
     natural dmax = 0;
     for (size_t i = 1; i < dims.size(); i++) dmax = std::max(dmax, dims[i]);
-    st->gather_buf = dev_shared_ptr<real>((size_t)gcnb_comm_world(st->comm) * st->block * dmax);
+    GCNB_CALL(gcnb_comm_gather_setup(st->comm, (int64_t)gcnb_comm_world(st->comm) * st->block * dmax));
     for (GCNLayer &ly : st->layers)  // padding rows are shipped by the all-gather: keep them defined
       for (const shared_ptr<Variable> &v : {ly.pre, ly.z}) {
         if (v->dev_data.get()) CHECK_CUDA_ERROR(cudaMemset(v->dev_data.get(), 0, (size_t)v->size * sizeof(real)));
