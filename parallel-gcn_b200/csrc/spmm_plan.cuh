@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cstdlib>
 #include <vector>
 
 namespace gcnb {
@@ -25,6 +26,34 @@ struct StageParams {
   int n_threads = 0;             // host threads for the build (0 = hardware concurrency, <= 16)
   int runs_per_queue = 1;        // > 1 cuts every CTA's share of a window into several runs
   int min_avg_seg = 32;          // staging is skipped when the average segment is shorter (per-segment work dominates)
+};
+
+// large plan arrays: malloc'ed and NOT value-initialised (a std::vector would zero-fill ~1 GB on one thread before the
+// builder's threads overwrite it; the builder touches every element it needs itself, in parallel)
+template <class T>
+struct HostArray {
+  T *p = nullptr;
+  size_t n = 0;
+  HostArray() = default;
+  HostArray(const HostArray &) = delete;
+  HostArray &operator=(const HostArray &) = delete;
+  HostArray(HostArray &&o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+  HostArray &operator=(HostArray &&o) noexcept {
+    if (this != &o) { free(p); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+    return *this;
+  }
+  ~HostArray() { free(p); }
+  void alloc(size_t count) {
+    free(p);
+    n = count;
+    p = count ? static_cast<T *>(malloc(count * sizeof(T))) : nullptr;
+  }
+  T *data() { return p; }
+  const T *data() const { return p; }
+  size_t size() const { return n; }
+  bool empty() const { return n == 0; }
+  T &operator[](size_t i) { return p[i]; }
+  const T &operator[](size_t i) const { return p[i]; }
 };
 
 constexpr int kStageLanes = 32;                 // segments per bundle (one per lane)
@@ -52,10 +81,11 @@ struct StagedHost {
   std::vector<uint4> bundles, runs;
   std::vector<uint16_t> lens;
   std::vector<uint32_t> run_begin;
-  std::vector<uint16_t> pidx;
-  std::vector<uint32_t> pperm;
+  HostArray<uint16_t> pidx;
+  HostArray<uint32_t> pperm;
   std::vector<uint32_t> row_slot, lane_slot;
-  std::vector<uint32_t> r_indptr, r_indices, r_perm;
+  std::vector<uint32_t> r_indptr;
+  HostArray<uint32_t> r_indices, r_perm;
 };
 
 int stage_build_host(const uint32_t *indptr, const uint32_t *indices, int64_t n_rows, int64_t n_cols,

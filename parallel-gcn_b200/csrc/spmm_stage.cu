@@ -21,6 +21,8 @@
 // row, every lane re-reading the row's indices).
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <numeric>
@@ -81,6 +83,14 @@ int stage_build_host(const uint32_t *indptr, const uint32_t *indices, int64_t n_
   if (nnz < (1 << 16)) T = 1;
   const WinDiv win_of((uint32_t)wc);
 
+  const bool verbose = getenv("GCNB_STAGE_VERBOSE") != nullptr;
+  auto t_last = std::chrono::steady_clock::now();
+  auto lap = [&](const char *what) {
+    if (!verbose) return;
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[stage] %-28s %7.1f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+    t_last = now;
+  };
   H = StagedHost();
   H.dim = P.dim;
   H.window_rows = wc;
@@ -116,6 +126,7 @@ int stage_build_host(const uint32_t *indptr, const uint32_t *indices, int64_t n_
       }
     }
   });
+  lap("pass A (window totals)");
   std::vector<uint8_t> enabled((size_t)n_win, 0);
   bool any = false;
   for (int w = 0; w < n_win; w++) {
@@ -157,6 +168,7 @@ int stage_build_host(const uint32_t *indptr, const uint32_t *indices, int64_t n_
       H.r_indptr[(size_t)r + 1] = deg - staged;
     }
   });
+  lap("pass B (sizes)");
   for (int64_t r = 0; r < n_rows; r++) {
     H.row_slot[(size_t)r + 1] += H.row_slot[(size_t)r];
     H.r_indptr[(size_t)r + 1] += H.r_indptr[(size_t)r];
@@ -181,12 +193,16 @@ int stage_build_host(const uint32_t *indptr, const uint32_t *indices, int64_t n_
     }
     win_seg_begin[n_win] = (uint32_t)so;
   }
-  std::vector<TmpSeg> tseg((size_t)H.n_segs);
-  std::vector<uint16_t> tcol((size_t)H.staged_nnz);
-  std::vector<uint32_t> tent((size_t)H.staged_nnz);
-  H.r_indices.assign((size_t)rem_nnz, 0);
-  H.r_perm.assign((size_t)rem_nnz, 0);
+  HostArray<TmpSeg> tseg;
+  HostArray<uint16_t> tcol;
+  HostArray<uint32_t> tent;
+  tseg.alloc((size_t)H.n_segs);
+  tcol.alloc((size_t)H.staged_nnz);
+  tent.alloc((size_t)H.staged_nnz);
+  H.r_indices.alloc((size_t)rem_nnz);
+  H.r_perm.alloc((size_t)rem_nnz);
 
+  lap("alloc temporaries");
   // ---- pass C: segments (entries in even/odd alternating order) + remainder CSR -------------------------------------
   run_threads(T, [&](int t) {
     std::vector<uint32_t> cnt((size_t)n_win, 0), start((size_t)n_win, 0), touched, staged_w;
@@ -261,6 +277,7 @@ int stage_build_host(const uint32_t *indptr, const uint32_t *indices, int64_t n_
     }
   });
 
+  lap("pass C (segments+remainder)");
   // ---- phase 2a: per window, sort segments by length and count bundles / blocks --------------------------------------
   std::vector<uint32_t> order((size_t)H.n_segs);
   std::iota(order.begin(), order.end(), 0u);
@@ -288,6 +305,7 @@ int stage_build_host(const uint32_t *indptr, const uint32_t *indices, int64_t n_
     win_bundles[w + 1] += win_bundles[w];
     win_blocks[w + 1] += win_blocks[w];
   }
+  lap("phase 2a (sort)");
   const uint64_t n_bundles = win_bundles[n_win];
   H.n_blocks = (int64_t)win_blocks[n_win];
   if ((uint64_t)H.n_blocks > 0xfffffff0ull || n_bundles * kStageLanes > 0xfffffff0ull) return GCNB_E_UNSUPPORTED;
@@ -295,9 +313,10 @@ int stage_build_host(const uint32_t *indptr, const uint32_t *indices, int64_t n_
   H.bundles.assign((size_t)n_bundles, make_uint4(0, 0, 0, 0));
   H.lens.assign((size_t)n_bundles * kStageLanes, 0);
   H.lane_slot.assign((size_t)n_bundles * kStageLanes, kStagePad);
-  H.pidx.assign((size_t)H.n_blocks * kStageLanes * kStageBlock, 0);
-  H.pperm.assign((size_t)H.n_blocks * kStageLanes * kStageBlock, kStagePad);
+  H.pidx.alloc((size_t)H.n_blocks * kStageLanes * kStageBlock);   // padding written per bundle in phase 2b
+  H.pperm.alloc((size_t)H.n_blocks * kStageLanes * kStageBlock);
 
+  lap("alloc outputs");
   // ---- phase 2b: fill bundles -----------------------------------------------------------------------------------------
   {
     std::atomic<int> next(0);
@@ -313,6 +332,12 @@ int stage_build_host(const uint32_t *indptr, const uint32_t *indices, int64_t n_
           const uint32_t L = tseg[order[i0]].len;
           const uint32_t minL = nl == kStageLanes ? tseg[order[i0 + nl - 1]].len : 0;
           H.bundles[bundle] = make_uint4((uint32_t)blk, L, minL, 0);
+          {
+            const size_t b0 = (size_t)blk * kStageLanes * kStageBlock;
+            const size_t cnt = (size_t)((L + kStageBlock - 1) / kStageBlock) * kStageLanes * kStageBlock;
+            std::fill(H.pidx.data() + b0, H.pidx.data() + b0 + cnt, (uint16_t)0);
+            std::fill(H.pperm.data() + b0, H.pperm.data() + b0 + cnt, kStagePad);
+          }
           // lane assignment: lanes l and l + 4 of a quarter-warp read the same 16-byte column chunk, so they should
           // fetch rows of opposite parity.  Inside a segment entries alternate even/odd (pass C) and lanes with bit 2
           // set start on odd; the unpaired tail of a segment is all-even or all-odd, so segments with an even surplus
@@ -359,6 +384,7 @@ int stage_build_host(const uint32_t *indptr, const uint32_t *indices, int64_t n_
     });
   }
 
+  lap("phase 2b (fill bundles)");
   // ---- runs and per-CTA queues: contiguous, equal estimated cycles ---------------------------------------------------
   {
     const double c_step = 18.0, c_bundle = 80.0, c_load = 6000.0;
@@ -664,6 +690,14 @@ __global__ void stage_gather_values_kernel(const uint32_t *__restrict__ perm, co
     const uint32_t e = __ldg(perm + i);
     out[i] = e == kStagePad ? 0.f : __ldg(values + e);
   }
+}
+
+template <class T>
+int upload_vec(T **dst, const HostArray<T> &v, cudaStream_t stream) {
+  const size_t bytes = std::max<size_t>(16, v.size() * sizeof(T));
+  GCNB_CHECK(cudaMalloc((void **)dst, bytes));
+  if (!v.empty()) GCNB_CHECK(cudaMemcpyAsync(*dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, stream));
+  return 0;
 }
 
 template <class T>
