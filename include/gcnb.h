@@ -76,6 +76,10 @@ GCNB_API int gcnb_spmm_plan_stage_ex(gcnb_spmm_plan *plan, const uint32_t *h_ind
                                      int64_t min_window_nnz, gcnb_stream_t stream);
 /* out = {staged?, window_rows, staged entries, remainder entries, segments, runs, chunks, partial slots} */
 GCNB_API int gcnb_spmm_plan_stage_info(const gcnb_spmm_plan *plan, int64_t out[8]);
+/* number of 16-column slabs a product of width `dim` runs as through the staged kernels (0: generic kernel).  Widths
+ * 16 and >= 64 are staged; each slab launches the staged kernel, the remainder kernel and the merge kernel (+ one
+ * packing kernel when B is not 16 floats wide). */
+GCNB_API int gcnb_spmm_plan_stage_slabs(const gcnb_spmm_plan *plan, int dim);
 
 /* The staging builder on its own, host memory only, no CUDA call: lets the plan layout be verified on a machine
  * without a GPU (tests/test_stage_cpu.py).  Arrays are described in parallel-gcn_b200/csrc/spmm_plan.cuh. */
@@ -94,6 +98,13 @@ GCNB_API int gcnb_stage_host_destroy(gcnb_stage_host *h);
  * Fully overwrites C.  Summation: fixed order (segment-local lane tree, then ascending segments). */
 GCNB_API int gcnb_spmm_f32(gcnb_spmm_plan *plan, const float *d_values, const uint32_t *d_perm, const float *d_B,
                            float *d_C, int dim, gcnb_stream_t stream);
+/* Same product on COLUMN SLABS of wider row-major matrices: B has row stride ldb floats, C row stride ldc floats
+ * (both >= dim); only columns [0, dim) of the two pointers are read / written.  This is how a wide GraphSum
+ * (hidden 600, parameters/parameters_reddit.txt:5) runs: 16 columns at a time, so that the window-staged kernels apply
+ * and the slab of B being gathered stays on chip.  A staged plan does this slab loop by itself for any
+ * dim >= 64, and the generic kernel cuts operands much larger than L2 into L2-sized slabs. */
+GCNB_API int gcnb_spmm_ld_f32(gcnb_spmm_plan *plan, const float *d_values, const uint32_t *d_perm, const float *d_B,
+                              int64_t ldb, float *d_C, int64_t ldc, int dim, gcnb_stream_t stream);
 
 /* Transposed-CSR companion for SparseMatmul::backward (src/module.cu:136-163; atomicAdd there, fixed-order here):
  * builds on the device the CSC of a CSR (column pointers, row ids, and the permutation into the CSR value array

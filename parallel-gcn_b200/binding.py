@@ -45,9 +45,11 @@ _sig("gcnb_spmm_plan_create", I32, [P, P, I64, I64, I32, P, P])
 _sig("gcnb_spmm_plan_destroy", I32, [P])
 _sig("gcnb_spmm_plan_info", I32, [P, P])
 _sig("gcnb_spmm_f32", I32, [P, P, P, P, P, I32, P])
+_sig("gcnb_spmm_ld_f32", I32, [P, P, P, P, I64, P, I64, I32, P])
 _sig("gcnb_spmm_plan_stage", I32, [P, P, P, P, I32, P])
 _sig("gcnb_spmm_plan_stage_ex", I32, [P, P, P, P, I32, I32, I32, I32, I64, P])
 _sig("gcnb_spmm_plan_stage_info", I32, [P, P])
+_sig("gcnb_spmm_plan_stage_slabs", I32, [P, I32])
 _sig("gcnb_stage_host_build", I32, [P, P, I64, I64, I32, I32, I32, I32, I64, I32, I32, P])
 _sig("gcnb_stage_host_sizes", I32, [P, P])
 _sig("gcnb_stage_host_copy", I32, [P, I32, P, I64])
@@ -159,6 +161,12 @@ class SpmmPlan:
 
     def spmm(self, values, B, C_out, dim, perm=None):
         check(lib.gcnb_spmm_f32(self.h, ptr(values), ptr(perm), ptr(B), ptr(C_out), int(dim), stream()))
+        return C_out
+
+    def spmm_ld(self, values, B, ldb, C_out, ldc, dim, perm=None, b_off=0, c_off=0):
+        """product on the column slab [off, off + dim) of wider row-major matrices (row strides ldb / ldc floats)"""
+        check(lib.gcnb_spmm_ld_f32(self.h, ptr(values), ptr(perm), C.c_void_p(B.data_ptr() + 4 * int(b_off)), int(ldb),
+                                   C.c_void_p(C_out.data_ptr() + 4 * int(c_off)), int(ldc), int(dim), stream()))
         return C_out
 
     def close(self):

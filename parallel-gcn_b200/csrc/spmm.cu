@@ -92,6 +92,7 @@ struct SegArgs {
   float *__restrict__ C;
   float *__restrict__ scratch;
   int dim;
+  int ldb, ldc;  // row strides of B and C in floats (>= dim): a column slab of a wider matrix is a valid operand
 };
 
 // gathers + FMAs of one 32-entry chunk held one-per-lane in (idx, val).  Loads are issued in batches of UB
@@ -153,7 +154,7 @@ __device__ __forceinline__ void run_segment(const SegArgs<VEC, LPR, KT, EXACT> &
   const int dim = A.dim;
   const uint32_t row = sg.x, beg = sg.y, end = sg.z, slot = sg.w;
   const char *Bl = reinterpret_cast<const char *>(A.B + l * VEC);
-  const uint32_t row_bytes = (uint32_t)dim * (uint32_t)sizeof(float);
+  const uint32_t row_bytes = (uint32_t)A.ldb * (uint32_t)sizeof(float);
   bool colok[KT];
 #pragma unroll
   for (int t = 0; t < KT; t++) colok[t] = EXACT || (t * W + l * VEC < dim);
@@ -183,7 +184,7 @@ __device__ __forceinline__ void run_segment(const SegArgs<VEC, LPR, KT, EXACT> &
 #pragma unroll
     for (int o = 16; o >= LPR; o >>= 1) acc[t].xor_add(o);
   if (g == 0) {
-    float *dst = (slot == kNoSlot) ? A.C + (size_t)row * dim : A.scratch + (size_t)slot * dim;
+    float *dst = (slot == kNoSlot) ? A.C + (size_t)row * A.ldc : A.scratch + (size_t)slot * dim;
 #pragma unroll
     for (int t = 0; t < KT; t++)
       if (colok[t]) acc[t].store(dst + t * W + l * VEC);
@@ -268,8 +269,8 @@ __global__ void __launch_bounds__(kThreads, (KT == 1 ? kBlocksNarrow : 4))
 spmm_seg_kernel(const uint4 *__restrict__ segs, const uint32_t *__restrict__ queue_begin,
                 uint32_t *__restrict__ counters, int n_queues, const uint32_t *__restrict__ indices,
                 const float *__restrict__ values, const uint32_t *__restrict__ perm, const float *__restrict__ B,
-                float *__restrict__ C, float *__restrict__ scratch, int dim, int batch) {
-  const SegArgs<VEC, LPR, KT, EXACT> A{segs, indices, values, perm, B, C, scratch, dim};
+                float *__restrict__ C, float *__restrict__ scratch, int dim, int ldb, int ldc, int batch) {
+  const SegArgs<VEC, LPR, KT, EXACT> A{segs, indices, values, perm, B, C, scratch, dim, ldb, ldc};
   const int lane = threadIdx.x & 31;
   uint32_t smid;
   asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
@@ -298,7 +299,7 @@ spmm_seg_kernel(const uint4 *__restrict__ segs, const uint32_t *__restrict__ que
 // rows cut into several segments: out[row] = partial[s0] + partial[s0+1] + ... in ascending order
 __global__ void spmm_combine_kernel(const uint32_t *__restrict__ split_row, const uint32_t *__restrict__ split_slot,
                                     const float *__restrict__ scratch, float *__restrict__ C, int64_t n_split,
-                                    int dim) {
+                                    int dim, int ldc) {
   const int64_t total = n_split * dim;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / dim;
@@ -306,7 +307,7 @@ __global__ void spmm_combine_kernel(const uint32_t *__restrict__ split_row, cons
     const uint32_t s0 = __ldg(split_slot + r), s1 = __ldg(split_slot + r + 1);
     float sum = 0.f;
     for (uint32_t s = s0; s < s1; s++) sum += __ldg(scratch + (size_t)s * dim + c);
-    C[(size_t)__ldg(split_row + r) * dim + c] = sum;
+    C[(size_t)__ldg(split_row + r) * ldc + c] = sum;
   }
 }
 
@@ -321,7 +322,7 @@ __global__ void dense_check_kernel(const uint32_t *__restrict__ indices, int64_t
 }
 
 using KernelFn = void (*)(const uint4 *, const uint32_t *, uint32_t *, int, const uint32_t *, const float *,
-                          const uint32_t *, const float *, float *, float *, int, int);
+                          const uint32_t *, const float *, float *, float *, int, int, int, int);
 
 template <int VEC, int LPR, int KT>
 KernelFn kfn(int dim) {
@@ -456,15 +457,50 @@ int gcnb_spmm_plan_info(const gcnb_spmm_plan *p, int64_t out[8]) {
 
 int gcnb_spmm_f32(gcnb_spmm_plan *p, const float *d_values, const uint32_t *d_perm, const float *d_B, float *d_C,
                   int dim, gcnb_stream_t stream_) {
-  if (!p || !d_values || !d_B || !d_C || dim <= 0) return GCNB_E_BADARG;
+  return gcnb_spmm_ld_f32(p, d_values, d_perm, d_B, dim, d_C, dim, dim, stream_);
+}
+
+int gcnb_spmm_ld_f32(gcnb_spmm_plan *p, const float *d_values, const uint32_t *d_perm, const float *d_B, int64_t ldb_,
+                     float *d_C, int64_t ldc_, int dim, gcnb_stream_t stream_) {
+  if (!p || !d_values || !d_B || !d_C || dim <= 0 || ldb_ < dim || ldc_ < dim || ldb_ > (1 << 28) || ldc_ > (1 << 28))
+    return GCNB_E_BADARG;
   if (p->n_rows == 0) return 0;
+  const int ldb = (int)ldb_, ldc = (int)ldc_;
   cudaStream_t stream = as_stream(stream_);
-  if (p->staged) {  // window-staged fast path (static values, dim it was built for), spmm_stage.cu
+  if (p->staged) {  // window-staged fast path (static values, 16-column slabs), spmm_stage.cu
     int handled = 0;
-    const int rc = gcnb_stage_try_spmm(p, d_values, d_perm, d_B, d_C, dim, stream, &handled);
+    const int rc = gcnb_stage_try_spmm(p, d_values, d_perm, d_B, ldb, d_C, ldc, dim, stream, &handled);
     if (rc || handled) return rc;
   }
-  const bool vec4 = (dim % 4 == 0) && (((uintptr_t)d_B | (uintptr_t)d_C) % 16 == 0);
+  // Column slabs: (1) the kernel holds at most 256 column chunks per row (1024 floats vectorised, 256 otherwise);
+  // (2) a dense operand much larger than L2 is gathered from HBM at sector granularity, while a slab that fits in L2
+  // is gathered on chip and re-streaming the index (8 bytes per entry per slab) is cheap next to row gathers of
+  // 4 * width bytes per entry -- Reddit-shape GraphSum at width 600: 75 ms as one pass, ~4x less in 32-column slabs.
+  const bool vec4 = (dim % 4 == 0) && (ldb % 4 == 0) && (ldc % 4 == 0) && (((uintptr_t)d_B | (uintptr_t)d_C) % 16 == 0);
+  int width = std::min(dim, vec4 ? 1024 : 256);
+  static const int64_t l2_budget = [] {
+    const char *e = getenv("GCNB_SPMM_SLAB_BYTES");  // tuning probe; 0 disables the L2 slabs
+    return e ? atoll(e) : (int64_t)32 << 20;
+  }();
+  if (l2_budget > 0 && dim > 32 && p->n_cols * (int64_t)dim * 4 > 2 * l2_budget) {
+    int64_t w = l2_budget / (p->n_cols * 4);
+    w = std::max<int64_t>(16, w / 16 * 16);
+    width = (int)std::min<int64_t>(width, w);
+  }
+  for (int c0 = 0; c0 < dim; c0 += width) {
+    const int w = std::min(width, dim - c0);
+    const int rc = spmm_generic_launch(p, d_values, d_perm, d_B + c0, ldb, d_C + c0, ldc, w, stream);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+}  // extern "C"
+
+int gcnb::spmm_generic_launch(gcnb_spmm_plan *p, const float *d_values, const uint32_t *d_perm, const float *d_B, int ldb,
+                              float *d_C, int ldc, int dim, cudaStream_t stream) {
+  if (p->n_rows == 0) return 0;
+  const bool vec4 = (dim % 4 == 0) && (ldb % 4 == 0) && (ldc % 4 == 0) && (((uintptr_t)d_B | (uintptr_t)d_C) % 16 == 0);
   KernelFn fn = vec4 ? pick_kernel<4>(dim) : pick_kernel<1>(dim);
   if (!fn) return GCNB_E_UNSUPPORTED;
   if (p->n_slots > 0 && p->scratch_dim < dim) {
@@ -496,17 +532,19 @@ int gcnb_spmm_f32(gcnb_spmm_plan *p, const float *d_values, const uint32_t *d_pe
   if (grid > min_grid) grid = std::max<int64_t>(1, min_grid);
   GCNB_CHECK(cudaMemsetAsync(p->d_counters, 0, ((size_t)p->n_queues + 1) * 4, stream));
   fn<<<(unsigned)grid, kThreads, 0, stream>>>(p->d_segs, p->d_queue_begin, p->d_counters, p->n_queues, p->d_indices,
-                                              d_values, d_perm, d_B, d_C, p->d_scratch, dim, p->batch);
+                                              d_values, d_perm, d_B, d_C, p->d_scratch, dim, ldb, ldc, p->batch);
   GCNB_LAUNCH_CHECK();
   if (p->n_split_rows > 0) {
     const int64_t total = p->n_split_rows * dim;
     const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)p->n_queues * 8);
     spmm_combine_kernel<<<blocks, 256, 0, stream>>>(p->d_split_row, p->d_split_slot, p->d_scratch, d_C,
-                                                    p->n_split_rows, dim);
+                                                    p->n_split_rows, dim, ldc);
     GCNB_LAUNCH_CHECK();
   }
   return 0;
 }
+
+extern "C" {
 
 // ---- CSC companion -----------------------------------------------------------------------------------
 struct gcnb_csc {

@@ -117,5 +117,12 @@ struct gcnb_spmm_plan {
 
 // spmm_stage.cu: runs the staged path if it applies to this call (same values pointer, same dim, no permutation) and
 // sets *handled = 1; otherwise *handled = 0 and the caller runs the generic kernel.  Returns 0 or an error code.
-int gcnb_stage_try_spmm(gcnb_spmm_plan *p, const float *d_values, const uint32_t *d_perm, const float *d_B, float *d_C,
-                        int dim, cudaStream_t stream, int *handled);
+// generic segment kernel on any plan (never the staged path), spmm.cu
+namespace gcnb {
+int spmm_generic_launch(gcnb_spmm_plan *p, const float *d_values, const uint32_t *d_perm, const float *d_B, int ldb,
+                        float *d_C, int ldc, int dim, cudaStream_t stream);
+}
+// B and C may be column slabs of wider matrices (row strides ldb / ldc floats); dims that are multiples of the staged
+// width run slab by slab.
+int gcnb_stage_try_spmm(gcnb_spmm_plan *p, const float *d_values, const uint32_t *d_perm, const float *d_B, int ldb,
+                        float *d_C, int ldc, int dim, cudaStream_t stream, int *handled);

@@ -455,6 +455,10 @@ struct StagedDev {
   cudaStream_t aux = nullptr;         // the remainder product runs here, concurrently with the staged kernel
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   const float *values_src = nullptr;  // the value array the packed copies were gathered from
+  // column-slab mode (operands wider than the staged width): one 16-column slab of B packed contiguously (so that the
+  // window copy stays one bulk copy and the remainder's random gathers hit a 15 MB L2-resident matrix instead of a
+  // strided one in HBM), and the remainder product of the slab before it is merged into the strided C
+  float *d_pack = nullptr, *d_remout = nullptr;
 };
 
 void stage_destroy(StagedDev *s) {
@@ -462,6 +466,7 @@ void stage_destroy(StagedDev *s) {
   cudaFree(s->d_bundles); cudaFree(s->d_runs); cudaFree(s->d_lens); cudaFree(s->d_run_begin); cudaFree(s->d_row_slot);
   cudaFree(s->d_lane_slot); cudaFree(s->d_counters); cudaFree(s->d_pidx); cudaFree(s->d_pperm); cudaFree(s->d_pval); cudaFree(s->d_partial);
   cudaFree(s->d_r_indptr); cudaFree(s->d_r_indices); cudaFree(s->d_r_perm); cudaFree(s->d_r_val);
+  cudaFree(s->d_pack); cudaFree(s->d_remout);
   if (s->rem) gcnb_spmm_plan_destroy(s->rem);
   if (s->aux) cudaStreamDestroy(s->aux);
   if (s->ev_fork) cudaEventDestroy(s->ev_fork);
@@ -652,19 +657,27 @@ spmm_staged16_kernel(const uint4 *__restrict__ runs, const uint32_t *__restrict_
   }
 }
 
-// C[row] += partial[slot] over the row's slots [row_slot[r], row_slot[r+1]) in ascending order (C already holds the
-// remainder product).  Thread = (row, 16-byte chunk): consecutive threads read consecutive 16-byte pieces; the loads
-// of four slots are issued together, the additions stay in slot order.
+// C[row] = R[row] + partial[slot] over the row's slots [row_slot[r], row_slot[r+1]) in ascending order, R = the remainder
+// product (in place in C when R == nullptr, else a contiguous [n_rows x 16] buffer and C is a 16-column slab with row
+// stride ldc).  Thread = (row, 16-byte chunk): consecutive threads read consecutive 16-byte pieces; the loads of four
+// slots are issued together, the additions stay in slot order.  VW = widest aligned access to C (4, 2 or 1 floats).
+template <int VW>
 __global__ void __launch_bounds__(256)
-stage_add16_kernel(const uint32_t *__restrict__ row_slot, const float *__restrict__ partial, float *__restrict__ C,
-                   int64_t n_rows) {
+stage_add16_kernel(const uint32_t *__restrict__ row_slot, const float *__restrict__ partial, const float *__restrict__ R,
+                   float *__restrict__ C, int64_t n_rows, int64_t ldc) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n_rows * 4) return;
   const int64_t r = i >> 2;
   const int c = (int)(i & 3);
   const uint32_t s0 = __ldg(row_slot + r), s1 = __ldg(row_slot + r + 1);
-  if (s0 == s1) return;
-  float4 acc = *reinterpret_cast<const float4 *>(C + r * 16 + c * 4);
+  float *dst = C + r * ldc + c * 4;
+  float4 acc;
+  if (R) {
+    acc = __ldg(reinterpret_cast<const float4 *>(R + r * 16 + c * 4));
+  } else {
+    if (s0 == s1) return;
+    acc = *reinterpret_cast<const float4 *>(dst);  // in-place mode is only used with ldc == 16 (VW == 4)
+  }
   const float4 *p = reinterpret_cast<const float4 *>(partial + (size_t)s0 * 16 + c * 4);
   for (uint32_t sl = s0; sl < s1; sl += 4, p += 16) {
     float4 v[4];
@@ -681,7 +694,30 @@ stage_add16_kernel(const uint32_t *__restrict__ row_slot, const float *__restric
       acc.w += v[u].w;
     }
   }
-  *reinterpret_cast<float4 *>(C + r * 16 + c * 4) = acc;
+  if (VW == 4) {
+    *reinterpret_cast<float4 *>(dst) = acc;
+  } else if (VW == 2) {
+    *reinterpret_cast<float2 *>(dst) = make_float2(acc.x, acc.y);
+    *reinterpret_cast<float2 *>(dst + 2) = make_float2(acc.z, acc.w);
+  } else {
+    dst[0] = acc.x; dst[1] = acc.y; dst[2] = acc.z; dst[3] = acc.w;
+  }
+}
+
+// one 16-column slab of a wider row-major matrix, packed contiguously: out[r][0..16) = B[r * ldb + 0..16)
+template <int VW>
+__global__ void __launch_bounds__(256)
+stage_pack16_kernel(const float *__restrict__ B, int64_t ldb, float *__restrict__ out, int64_t n_rows) {
+  constexpr int PER = 16 / VW;  // pieces per row
+  const int64_t total = n_rows * PER;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / PER;
+    const int c = (int)(i - r * PER) * VW;
+    const float *src = B + r * ldb + c;
+    if (VW == 4) *reinterpret_cast<float4 *>(out + r * 16 + c) = __ldg(reinterpret_cast<const float4 *>(src));
+    else if (VW == 2) *reinterpret_cast<float2 *>(out + r * 16 + c) = __ldg(reinterpret_cast<const float2 *>(src));
+    else out[r * 16 + c] = __ldg(src);
+  }
 }
 
 __global__ void stage_gather_values_kernel(const uint32_t *__restrict__ perm, const float *__restrict__ values,
@@ -721,12 +757,34 @@ int gather_values(StagedDev *s, const float *d_values, cudaStream_t stream) {
 
 }  // namespace
 
-int gcnb_stage_try_spmm(gcnb_spmm_plan *p, const float *d_values, const uint32_t *d_perm, const float *d_B, float *d_C,
-                        int dim, cudaStream_t stream, int *handled) {
-  *handled = 0;
-  StagedDev *s = p->staged;
-  if (!s || d_perm || dim != s->dim || d_values != s->values_src) return 0;
-  if ((((uintptr_t)d_B | (uintptr_t)d_C) % 16) != 0) return 0;
+namespace {
+
+// widest vector access (floats) valid for every row of a slab that starts at `p` with row stride `ld`
+int slab_vec_width(const void *p, int64_t ld) {
+  if ((uintptr_t)p % 16 == 0 && ld % 4 == 0) return 4;
+  if ((uintptr_t)p % 8 == 0 && ld % 2 == 0) return 2;
+  return 1;
+}
+
+// C[:, 0..16) (row stride ldc) = A * B[:, 0..16) (row stride ldb) through the staged representation
+int staged_slab16(StagedDev *s, const float *d_B, int64_t ldb, float *d_C, int64_t ldc, cudaStream_t stream) {
+  const int sms = std::max(1, device_info().sm_count);
+  if (ldb != 16 || (uintptr_t)d_B % 16 != 0) {
+    if (!s->d_pack) GCNB_CHECK(cudaMalloc((void **)&s->d_pack, std::max<size_t>(16, (size_t)s->n_cols * 16 * sizeof(float))));
+    const int vw = slab_vec_width(d_B, ldb);
+    const int blocks = (int)std::min<int64_t>((s->n_cols * (16 / vw) + 255) / 256, (int64_t)sms * 16);
+    if (vw == 4) stage_pack16_kernel<4><<<blocks, 256, 0, stream>>>(d_B, ldb, s->d_pack, s->n_cols);
+    else if (vw == 2) stage_pack16_kernel<2><<<blocks, 256, 0, stream>>>(d_B, ldb, s->d_pack, s->n_cols);
+    else stage_pack16_kernel<1><<<blocks, 256, 0, stream>>>(d_B, ldb, s->d_pack, s->n_cols);
+    GCNB_LAUNCH_CHECK();
+    d_B = s->d_pack;
+  }
+  const bool in_place = ldc == 16 && (uintptr_t)d_C % 16 == 0;
+  float *rem_out = d_C;
+  if (!in_place) {
+    if (!s->d_remout) GCNB_CHECK(cudaMalloc((void **)&s->d_remout, std::max<size_t>(16, (size_t)s->n_rows * 16 * sizeof(float))));
+    rem_out = s->d_remout;
+  }
   const size_t smem = (size_t)s->window_rows * s->dim * sizeof(float) + 32;
   static const int nt = [] {
     const char *e = getenv("GCNB_STAGE_THREADS");  // tuning probe
@@ -737,7 +795,7 @@ int gcnb_stage_try_spmm(gcnb_spmm_plan *p, const float *d_values, const uint32_t
     return e ? atoi(e) : 1;
   }();
   // The remainder product (latency-bound L2 gathers) runs on the plan's second stream while the staged kernel
-  // (LSU-bound shared-memory gathers, 1 CTA of 256 threads per SM) runs here: the two co-reside on every SM.
+  // (LSU-bound shared-memory gathers, one persistent CTA per SM) runs here: the two co-reside on every SM.
   cudaStream_t rs = stream;
   if (concurrent) {
     GCNB_CHECK(cudaEventRecord(s->ev_fork, stream));
@@ -757,15 +815,51 @@ int gcnb_stage_try_spmm(gcnb_spmm_plan *p, const float *d_values, const uint32_t
   else GCNB_STAGE_LAUNCH(256, 1);
 #undef GCNB_STAGE_LAUNCH
   GCNB_LAUNCH_CHECK();
-  int rc = gcnb_spmm_f32(s->rem, s->d_r_val, nullptr, d_B, d_C, dim, (gcnb_stream_t)rs);
+  int rc = spmm_generic_launch(s->rem, s->d_r_val, nullptr, d_B, 16, rem_out, 16, 16, rs);
   if (rc) return rc;
   if (concurrent) {
     GCNB_CHECK(cudaEventRecord(s->ev_join, s->aux));
     GCNB_CHECK(cudaStreamWaitEvent(stream, s->ev_join, 0));
   }
   const int64_t total = s->n_rows * 4;
-  stage_add16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(s->d_row_slot, s->d_partial, d_C, s->n_rows);
+  const unsigned blocks = (unsigned)((total + 255) / 256);
+  if (in_place) {
+    stage_add16_kernel<4><<<blocks, 256, 0, stream>>>(s->d_row_slot, s->d_partial, nullptr, d_C, s->n_rows, 16);
+  } else {
+    const int vw = slab_vec_width(d_C, ldc);
+    if (vw == 4) stage_add16_kernel<4><<<blocks, 256, 0, stream>>>(s->d_row_slot, s->d_partial, rem_out, d_C, s->n_rows, ldc);
+    else if (vw == 2) stage_add16_kernel<2><<<blocks, 256, 0, stream>>>(s->d_row_slot, s->d_partial, rem_out, d_C, s->n_rows, ldc);
+    else stage_add16_kernel<1><<<blocks, 256, 0, stream>>>(s->d_row_slot, s->d_partial, rem_out, d_C, s->n_rows, ldc);
+  }
   GCNB_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace
+
+// Smallest operand width (other than the staged width itself) that is cut into 16-column slabs; narrower products stay
+// on the generic kernel, which reads the index once for all columns.
+static int stage_slab_min_dim() {
+  static const int v = [] {
+    const char *e = getenv("GCNB_STAGE_SLAB_MIN");  // tuning probe
+    return e ? atoi(e) : 64;
+  }();
+  return v;
+}
+
+int gcnb_stage_try_spmm(gcnb_spmm_plan *p, const float *d_values, const uint32_t *d_perm, const float *d_B, int ldb,
+                        float *d_C, int ldc, int dim, cudaStream_t stream, int *handled) {
+  *handled = 0;
+  StagedDev *s = p->staged;
+  if (!s || d_perm || s->dim != 16 || d_values != s->values_src) return 0;
+  if (dim != 16 && dim < stage_slab_min_dim()) return 0;
+  // slabs of 16 columns; the last one is shifted left to end at `dim` (its overlap with the previous slab is computed
+  // twice with identical results) so that every slab takes the staged path
+  for (int c0 = 0; c0 < dim; c0 += 16) {
+    const int c = std::min(c0, dim - 16);
+    const int rc = staged_slab16(s, d_B + c, ldb, d_C + c, ldc, stream);
+    if (rc) return rc;
+  }
   *handled = 1;
   return 0;
 }
@@ -862,6 +956,12 @@ int gcnb_spmm_plan_stage_ex(gcnb_spmm_plan *p, const uint32_t *h_indptr, const u
   if ((rc = (int)cudaStreamSynchronize(stream))) return fail(rc);
   p->staged = s;
   return 0;
+}
+
+int gcnb_spmm_plan_stage_slabs(const gcnb_spmm_plan *p, int dim) {
+  const StagedDev *s = p ? p->staged : nullptr;
+  if (!s || s->dim != 16 || (dim != 16 && dim < stage_slab_min_dim())) return 0;
+  return (dim + 15) / 16;
 }
 
 int gcnb_spmm_plan_stage_info(const gcnb_spmm_plan *p, int64_t out[8]) {

@@ -114,6 +114,10 @@ struct GCNEngineState {
   real x_train_p = 0.f;
   dev_shared_ptr<real> dense_tn_ws;
   int64_t dense_tn_ws_bytes = 0;
+  // evaluation passes read pristine features, and both A_hat and X are constants: layer 0 of an evaluation forward is
+  // (A_hat X) W0 with P = A_hat X computed once (first evaluation), instead of A_hat (X W0) -- one GraphSum less per pass
+  dev_shared_ptr<real> ax;
+  bool ax_tried = false, ax_ready = false;
   dev_shared_ptr<real> tn_ws;
   int64_t tn_ws_bytes = 0;
   dev_shared_ptr<natural> ce_ws, sumsq_ws;
@@ -125,7 +129,7 @@ struct GCNEngineState {
   size_t launches = 0, launches_last_epoch = 0;  // CUDA kernels launched (memsets / copies not counted)
   natural epochs_run = 0;
   int graph_spmm_kernels = 1, feat_spmm_kernels = 1, feat_csc_kernels = 1;  // 1 + combine kernel when rows are split
-  int graph_staged_dim = -1, graph_staged_kernels = 0;  // window-staged GraphSum: staged + remainder (+combine) + add
+  bool graph_staged = false;  // window-staged GraphSum (csrc/spmm_stage.cu) for widths 16 and >= 64
   // optional per-launch timing of the GraphSum SpMM (bench.py roofline): event pairs on the engine stream
   bool time_graphsum = false;
   std::vector<cudaEvent_t> gs_events;
@@ -151,7 +155,14 @@ struct GCNEngineState {
       CHECK_CUDA_ERROR(cudaEventRecord(gs_events[gs_used + 1], stream));
       gs_used += 2;
     }
-    launches += (dim == graph_staged_dim) ? graph_staged_kernels : graph_spmm_kernels;
+    launches += graphsum_launches(dim);
+  }
+  size_t graphsum_launches(natural dim) const {
+    // staged: per 16-column slab the staged kernel, the remainder kernel and the merge kernel (+ the slab packing kernel
+    // when the operand is wider than a slab); a remainder combine kernel, if any, is not counted
+    const int slabs = graph_staged ? gcnb_spmm_plan_stage_slabs(graph_plan, (int)dim) : 0;
+    if (slabs > 0) return (size_t)slabs * (dim == 16 ? 3 : 4);
+    return (size_t)graph_spmm_kernels;
   }
   void collect_graphsum_times() {  // after a stream sync
     for (size_t i = 0; i + 1 < gs_used; i += 2) {
@@ -301,17 +312,18 @@ void GCN::init(bool quiet, const natural *h_graph_indptr, const natural *h_graph
   {
     // graph_value never changes: give GraphSum at width 16 the window-staged representation (shared-memory gathers
     // for the clustered part of the adjacency, see csrc/spmm_stage.cu); a no-op for graphs without column locality
-    bool uses16 = false;
-    for (const GCNLayer &ly : st->layers) uses16 |= (ly.reorder ? ly.in_dim : ly.out_dim) == 16;
-    if (uses16) {
+    // (wider GraphSums run through the same kernels 16 columns at a time)
+    bool wanted = false;
+    for (const GCNLayer &ly : st->layers) {
+      const natural d = ly.reorder ? ly.in_dim : ly.out_dim;
+      wanted |= d == 16 || d >= 64;
+    }
+    if (wanted) {
       GCNB_CALL(gcnb_spmm_plan_stage(st->graph_plan, h_graph_indptr, h_graph_indices, dev_data.dev_graph_value.get(),
                                      16, st->stream));
       int64_t sinfo[8];
       GCNB_CALL(gcnb_spmm_plan_stage_info(st->graph_plan, sinfo));
-      if (sinfo[0]) {
-        st->graph_staged_dim = 16;
-        st->graph_staged_kernels = 3;  // staged + remainder + add (a remainder combine kernel, if any, is not counted)
-      }
+      st->graph_staged = sinfo[0] != 0;
     }
   }
   if (st->feat_dense && gcnb_dense_feat_supported((int)F, (int)dims[1])) {
@@ -362,7 +374,7 @@ void GCN::set_reorder(bool on) {
   }
 }
 size_t GCN::launches_per_epoch() const { return st->launches_last_epoch; }
-bool GCN::graph_staged() const { return st->graph_staged_dim > 0; }
+bool GCN::graph_staged() const { return st->graph_staged; }
 size_t GCN::launches_total() const { return st->launches; }
 void GCN::set_time_graphsum(bool on) {
   st->time_graphsum = on;
@@ -470,7 +482,24 @@ void GCN::forward_pass(bool training, natural split, cudaStream_t s) {
     Variable::rng_consume(input_elems);  // the reference draws even when p == 0
     st->x_train_vals = xvals;
   }
-  {
+  if (!training && st->dense_fast && !st->dist && st->allow_reorder && !st->ax_tried) {
+    st->ax_tried = true;
+    const char *e = getenv("GCNB_PROPAGATE");  // tuning probe: 0 keeps the module chain's A_hat (X W0) in evaluation
+    size_t free_b = 0, total_b = 0;
+    CHECK_CUDA_ERROR(cudaMemGetInfo(&free_b, &total_b));
+    const size_t bytes = (size_t)N * F * sizeof(real);
+    if (!(e && atoi(e) == 0) && free_b > bytes + (size_t(4) << 30)) {
+      st->ax = dev_shared_ptr<real>((size_t)N * F);
+      GCNB_CALL(gcnb_spmm_ld_f32(st->graph_plan, dev_data.dev_graph_value.get(), nullptr, xvals, F, st->ax.get(), F, (int)F, s));
+      st->ax_ready = true;
+    }
+  }
+  if (!training && st->ax_ready && st->allow_reorder) {
+    GCNLayer &l0 = st->layers[0];
+    GCNB_CALL(gcnb_dense_feat_fwd_f32(st->ax.get(), nullptr, 0.f, weights[0]->dev_data.get(), l0.z->dev_data.get(), N, (int)F,
+                                      (int)l0.out_dim, s));
+    st->launches += 1;
+  } else {
     GCNLayer &l0 = st->layers[0];
     if (st->dense_fast) {
       GCNB_CALL(gcnb_dense_feat_fwd_f32(xvals, xbits, xp, weights[0]->dev_data.get(), l0.pre->dev_data.get(), N, (int)F,

@@ -108,6 +108,62 @@ def test_graphsum_window_staged(O, gcnb, dev, cfg):
     plan2.close()
 
 
+@pytest.mark.parametrize("dim,ldb,ldc,b_off,c_off", [(16, 40, 24, 8, 4), (7, 9, 11, 2, 3), (64, 64, 96, 0, 32), (10, 602, 602, 592, 592)])
+def test_graphsum_column_slabs_generic(O, gcnb, dev, dim, ldb, ldc, b_off, c_off):
+    """gcnb_spmm_ld_f32: B and C are column slabs of wider matrices; columns outside the slab are neither read nor
+    written."""
+    import torch
+    rng = np.random.default_rng(5)
+    n = 2500
+    indptr, indices = random_csr(rng, n, n, 20, heavy_rows=[(9, 5000)], empty_rows=[0, 1234])
+    values = rng.standard_normal(len(indices)).astype(f32)
+    xw = rng.standard_normal((n, ldb)).astype(f32)
+    x = np.ascontiguousarray(xw[:, b_off:b_off + dim])
+    want = np.empty((n, dim), f32)
+    O.lib.orc_spmm(n, dim, O._p(indptr), O._p(indices), O._p(values), O._p(x), O._p(want))
+    d_ip, d_ix, d_v, d_x = (to_dev(a, dev) for a in (indptr, indices, values, xw))
+    plan = gcnb.SpmmPlan(d_ip, d_ix, n, 64)
+    out = torch.full((n, ldc), -7.0, device=dev)
+    plan.spmm_ld(d_v, d_x, ldb, out, ldc, dim, b_off=b_off, c_off=c_off)
+    torch.cuda.synchronize()
+    got = to_np(out)
+    assert_close(got[:, c_off:c_off + dim], want, what="slab spmm")
+    mask = np.ones(ldc, bool)
+    mask[c_off:c_off + dim] = False
+    assert (got[:, mask] == -7.0).all()
+    plan.close()
+
+
+@pytest.mark.parametrize("dim,ld", [(64, 64), (600, 600), (41, 41), (602, 602), (32, 50)])
+def test_graphsum_window_staged_wide(O, gcnb, dev, dim, ld, monkeypatch):
+    """operands wider than the staged width run as 16-column slabs through the staged kernels (last slab shifted left to
+    end at dim): same product as the oracle, other columns of a wider C untouched, bit-identical between launches."""
+    import torch
+    from tests.test_stage_cpu import community_csr
+    rng = np.random.default_rng(33)
+    n = 6000
+    indptr, indices = community_csr(rng, n, 4, 80, 0.8, ((5, 2500),))
+    values = rng.standard_normal(len(indices)).astype(f32)
+    xw = rng.standard_normal((n, ld)).astype(f32)
+    x = np.ascontiguousarray(xw[:, :dim])
+    want = np.empty((n, dim), f32)
+    O.lib.orc_spmm(n, dim, O._p(indptr), O._p(indices), O._p(values), O._p(x), O._p(want))
+    d_ip, d_ix, d_v, d_x = (to_dev(a, dev) for a in (indptr, indices, values, xw))
+    plan = gcnb.SpmmPlan(d_ip, d_ix, n)
+    info = plan.stage(d_v, 16, None, None, 1024, 8, 64, 1)
+    assert info["staged"] == 1
+    out = torch.full((n, ld), -7.0, device=dev)
+    plan.spmm_ld(d_v, d_x, ld, out, ld, dim)
+    torch.cuda.synchronize()
+    got = to_np(out)
+    assert_close(got[:, :dim], want, what="staged slab spmm dim=%d" % dim)
+    assert (got[:, dim:] == -7.0).all()
+    out2 = torch.full((n, ld), -7.0, device=dev)
+    plan.spmm_ld(d_v, d_x, ld, out2, ld, dim)
+    assert torch.equal(out, out2)
+    plan.close()
+
+
 def test_graphsum_ref_cpu_flavour(O, gcnb, dev, datasets):
     """the ref-CPU GraphSum recomputes coef per edge (module.cpp:86-90); hoisted values give the same bits."""
     ds = datasets["cora"]
