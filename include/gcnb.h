@@ -80,6 +80,16 @@ GCNB_API int gcnb_spmm_plan_stage_info(const gcnb_spmm_plan *plan, int64_t out[8
  * 16 and >= 64 are staged; each slab launches the staged kernel, the remainder kernel and the merge kernel (+ one
  * packing kernel when B is not 16 floats wide). */
 GCNB_API int gcnb_spmm_plan_stage_slabs(const gcnb_spmm_plan *plan, int dim);
+/* Row-partitioned GraphSum (one rank = one row block of A, B = the slabs of all ranks gathered over NVLink): columns
+ * [col0, col1) of A -- rows of B -- are the rank's OWN slab, which exists before the exchange.  Call before
+ * gcnb_spmm_plan_stage: staged column windows that lie entirely inside the range get their own run list.  Then, per
+ * product, gcnb_spmm_stage_own_f32 launches those runs from the rank's slab (d_B_own = its first row, 16 floats per row)
+ * while the exchange is still in flight, and the following gcnb_spmm_f32 call on the gathered matrix does the rest
+ * (other windows, remainder entries, merge).  *launched = 0 means nothing was launched (no staged plan, no window inside
+ * the range, other dim / value array): the gcnb_spmm_f32 call then does everything, as without this call. */
+GCNB_API int gcnb_spmm_plan_set_own_cols(gcnb_spmm_plan *plan, int64_t col0, int64_t col1);
+GCNB_API int gcnb_spmm_stage_own_f32(gcnb_spmm_plan *plan, const float *d_values, const float *d_B_own, int dim,
+                                     gcnb_stream_t stream, int *launched);
 
 /* The staging builder on its own, host memory only, no CUDA call: lets the plan layout be verified on a machine
  * without a GPU (tests/test_stage_cpu.py).  Arrays are described in parallel-gcn_b200/csrc/spmm_plan.cuh. */
@@ -88,7 +98,11 @@ GCNB_API int gcnb_stage_host_build(const uint32_t *h_indptr, const uint32_t *h_i
                                    int dim, int window_rows /*0 = default*/, int min_seg /*0 = default*/,
                                    int seg_cap /*0 = default*/, int64_t min_window_nnz /*0 = default*/,
                                    int n_cta /*0 = 148*/, int n_threads /*0 = auto*/, gcnb_stage_host **out);
-GCNB_API int gcnb_stage_host_sizes(const gcnb_stage_host *h, int64_t out[12]);
+/* same, with the own column range of a row-partitioned product (gcnb_spmm_plan_set_own_cols) */
+GCNB_API int gcnb_stage_host_build_own(const uint32_t *h_indptr, const uint32_t *h_indices, int64_t n_rows, int64_t n_cols,
+                                       int dim, int window_rows, int min_seg, int seg_cap, int64_t min_window_nnz, int n_cta,
+                                       int n_threads, int64_t own_col0, int64_t own_col1, gcnb_stage_host **out);
+GCNB_API int gcnb_stage_host_sizes(const gcnb_stage_host *h, int64_t out[13]);
 GCNB_API int gcnb_stage_host_copy(const gcnb_stage_host *h, int which, void *dst, int64_t bytes);
 GCNB_API int gcnb_stage_host_destroy(gcnb_stage_host *h);
 

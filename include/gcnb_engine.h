@@ -114,6 +114,23 @@ GCNB_API int gcnb_synth_dense_features(int64_t n, int f, uint64_t seed, uint32_t
 GCNB_API int gcnb_synth_labels(int64_t n, int classes, double frac_train, double frac_val, uint64_t seed,
                                int32_t *label, uint32_t *split);
 
+/* Row-local symmetric generator for the scale-out workloads (BASELINE.json config 5): rows [row0, row0 + rows) of a
+ * symmetric simple graph on n nodes whose edge {i, j} is a pure function of (seed, min, max) -- every rank of a
+ * row-partitioned job generates only its block, and the blocks of all ranks form one consistent symmetric graph.
+ * Communities are contiguous blocks of block_size nodes (every pair inside is a candidate, expected mean_intra
+ * neighbours); across communities node i's candidates are its images under n_reflect fixed reflections (c_k - i) mod n
+ * (expected mean_inter neighbours); degrees are skewed by lognormal(sigma) weights.  Column ids are global; row i =
+ * [i, sorted neighbours] (the parser's convention).  Arrays are malloc'ed: gcnb_host_free. */
+GCNB_API int gcnb_synth_sym_rows(int64_t n, int64_t row0, int64_t rows, int64_t block_size, double mean_intra,
+                                 double mean_inter, int n_reflect, double sigma, uint64_t seed, uint32_t **indptr_out,
+                                 uint32_t **indices_out, int64_t *nnz_out);
+/* graph_value of a row block from the GLOBAL degree array (Parser::calculateGraphValues arithmetic, src/parser.cpp:164-181) */
+GCNB_API int gcnb_synth_graph_values(const uint32_t *indptr, const uint32_t *indices, int64_t rows, int64_t row0,
+                                     const uint32_t *deg_global, float *out);
+/* dense feature CSR with cheap uniform(-sqrt 3, sqrt 3) values; elem_offset = global position of the block's first value */
+GCNB_API int gcnb_synth_dense_features_uniform(int64_t n, int f, uint64_t seed, uint64_t elem_offset, uint32_t *indptr,
+                                               uint32_t *indices, float *values);
+
 #ifdef __cplusplus
 }
 #endif

@@ -51,6 +51,9 @@ _sig("gcnb_spmm_plan_stage_ex", I32, [P, P, P, P, I32, I32, I32, I32, I64, P])
 _sig("gcnb_spmm_plan_stage_info", I32, [P, P])
 _sig("gcnb_spmm_plan_stage_slabs", I32, [P, I32])
 _sig("gcnb_stage_host_build", I32, [P, P, I64, I64, I32, I32, I32, I32, I64, I32, I32, P])
+_sig("gcnb_stage_host_build_own", I32, [P, P, I64, I64, I32, I32, I32, I32, I64, I32, I32, I64, I64, P])
+_sig("gcnb_spmm_plan_set_own_cols", I32, [P, I64, I64])
+_sig("gcnb_spmm_stage_own_f32", I32, [P, P, P, I32, P, P])
 _sig("gcnb_stage_host_sizes", I32, [P, P])
 _sig("gcnb_stage_host_copy", I32, [P, I32, P, I64])
 _sig("gcnb_stage_host_destroy", I32, [P])
@@ -163,6 +166,16 @@ class SpmmPlan:
         check(lib.gcnb_spmm_f32(self.h, ptr(values), ptr(perm), ptr(B), ptr(C_out), int(dim), stream()))
         return C_out
 
+    def set_own_cols(self, col0, col1):
+        """row-partitioned product: columns [col0, col1) are this rank's own slab of B (call before stage())"""
+        check(lib.gcnb_spmm_plan_set_own_cols(self.h, int(col0), int(col1)))
+
+    def stage_own(self, values, B_own, dim=16):
+        """launch the staged runs whose windows lie inside the own slab, from that slab; True if anything was launched"""
+        launched = C.c_int(0)
+        check(lib.gcnb_spmm_stage_own_f32(self.h, ptr(values), ptr(B_own), int(dim), stream(), C.byref(launched)))
+        return bool(launched.value)
+
     def spmm_ld(self, values, B, ldb, C_out, ldc, dim, perm=None, b_off=0, c_off=0):
         """product on the column slab [off, off + dim) of wider row-major matrices (row strides ldb / ldc floats)"""
         check(lib.gcnb_spmm_ld_f32(self.h, ptr(values), ptr(perm), C.c_void_p(B.data_ptr() + 4 * int(b_off)), int(ldb),
@@ -178,20 +191,20 @@ class SpmmPlan:
 
 
 def stage_host_build(indptr, indices, n_cols, dim=16, window_rows=0, min_seg=0, seg_cap=0, min_window_nnz=0, n_cta=0,
-                     n_threads=0):
+                     n_threads=0, own_cols=(0, 0)):
     """Host-only run of the staging builder (no CUDA): returns the plan arrays as numpy (see csrc/spmm_plan.cuh)."""
     import numpy as np
     indptr = np.ascontiguousarray(indptr, np.uint32)
     indices = np.ascontiguousarray(indices, np.uint32)
     h = C.c_void_p()
-    check(lib.gcnb_stage_host_build(indptr.ctypes.data_as(C.c_void_p), indices.ctypes.data_as(C.c_void_p),
-                                    len(indptr) - 1, int(n_cols), dim, window_rows, min_seg, seg_cap, min_window_nnz,
-                                    n_cta, n_threads, C.byref(h)))
+    check(lib.gcnb_stage_host_build_own(indptr.ctypes.data_as(C.c_void_p), indices.ctypes.data_as(C.c_void_p),
+                                        len(indptr) - 1, int(n_cols), dim, window_rows, min_seg, seg_cap, min_window_nnz,
+                                        n_cta, n_threads, int(own_cols[0]), int(own_cols[1]), C.byref(h)))
     try:
-        sz = (I64 * 12)()
+        sz = (I64 * 13)()
         check(lib.gcnb_stage_host_sizes(h, sz))
         keys = ("window_rows", "n_win", "n_cta", "staged_nnz", "n_bundles", "n_runs", "n_blocks", "n_slots", "rem_nnz",
-                "n_rows", "nnz", "n_segs")
+                "n_rows", "nnz", "n_segs", "n_own_runs")
         out = dict(zip(keys, [int(x) for x in sz]))
         n_rows = out["n_rows"]
 
@@ -211,6 +224,8 @@ def stage_host_build(indptr, indices, n_cols, dim=16, window_rows=0, min_seg=0, 
         out["r_perm"] = grab(8, out["rem_nnz"], np.uint32)
         out["lens"] = grab(9, out["n_bundles"] * 32, np.uint16)
         out["lane_slot"] = grab(10, out["n_bundles"] * 32, np.uint32)
+        out["own_runs"] = grab(11, out["n_own_runs"] * 4, np.uint32).reshape(-1, 4)
+        out["own_run_begin"] = grab(12, out["n_cta"] + 1, np.uint32)
         return out
     finally:
         lib.gcnb_stage_host_destroy(h)

@@ -26,6 +26,9 @@ struct StageParams {
   int n_threads = 0;             // host threads for the build (0 = hardware concurrency, <= 16)
   int runs_per_queue = 1;        // > 1 cuts every CTA's share of a window into several runs
   int min_avg_seg = 32;          // staging is skipped when the average segment is shorter (per-segment work dominates)
+  // row-partitioned products: columns [own_col0, own_col1) are the rank's own slab of B; windows entirely inside go to
+  // a second run list (own_runs) that can be processed before the peers' slabs have arrived
+  int64_t own_col0 = 0, own_col1 = 0;
 };
 
 // large plan arrays: malloc'ed and NOT value-initialised (a std::vector would zero-fill ~1 GB on one thread before the
@@ -78,9 +81,9 @@ constexpr uint32_t kStagePad = 0xffffffffu;     // padding marker in the value p
 struct StagedHost {
   int dim = 0, window_rows = 0, n_win = 0, n_cta = 0;
   int64_t n_rows = 0, n_cols = 0, nnz = 0, staged_nnz = 0, n_blocks = 0, n_slots = 0, n_segs = 0;
-  std::vector<uint4> bundles, runs;
+  std::vector<uint4> bundles, runs, own_runs;
   std::vector<uint16_t> lens;
-  std::vector<uint32_t> run_begin;
+  std::vector<uint32_t> run_begin, own_run_begin;
   HostArray<uint16_t> pidx;
   HostArray<uint32_t> pperm;
   std::vector<uint32_t> row_slot, lane_slot;
@@ -113,6 +116,7 @@ struct gcnb_spmm_plan {
   int64_t max_deg = 0;
   int batch = 1;                      // segments claimed per atomic ticket (short-row graphs: > 1)
   gcnb::StagedDev *staged = nullptr;  // optional window-staged fast path (gcnb_spmm_plan_stage)
+  int64_t own_col0 = 0, own_col1 = 0;  // gcnb_spmm_plan_set_own_cols (before staging)
 };
 
 // spmm_stage.cu: runs the staged path if it applies to this call (same values pointer, same dim, no permutation) and

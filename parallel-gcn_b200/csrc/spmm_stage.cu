@@ -386,13 +386,21 @@ int stage_build_host(const uint32_t *indptr, const uint32_t *indices, int64_t n_
 
   lap("phase 2b (fill bundles)");
   // ---- runs and per-CTA queues: contiguous, equal estimated cycles ---------------------------------------------------
-  {
+  // Two classes of windows when the caller names an OWN column range (row-partitioned GraphSum: the rank's own slab of B
+  // is available before the slabs of its peers have arrived): windows entirely inside it form a second run list that
+  // can be processed while the exchange is still in flight.
+  auto build_runs = [&](bool own_class, std::vector<uint4> &runs, std::vector<uint32_t> &run_begin) {
     const double c_step = 18.0, c_bundle = 80.0, c_load = 6000.0;
     auto bundle_cost = [&](const uint4 &b) { return c_bundle + c_step * b.y; };
+    auto in_class = [&](int w) {
+      const int64_t c0 = (int64_t)w * wc, c1 = std::min<int64_t>(n_cols, c0 + wc);
+      const bool own = P.own_col1 > P.own_col0 && c0 >= P.own_col0 && c1 <= P.own_col1;
+      return own == own_class;
+    };
     double total = 0;
     int n_used = 0;
     for (int w = 0; w < n_win; w++) {
-      if (win_bundles[w + 1] == win_bundles[w]) continue;
+      if (win_bundles[w + 1] == win_bundles[w] || !in_class(w)) continue;
       n_used++;
       for (uint32_t i = win_bundles[w]; i < win_bundles[w + 1]; i++) total += bundle_cost(H.bundles[i]);
     }
@@ -400,13 +408,14 @@ int stage_build_host(const uint32_t *indptr, const uint32_t *indices, int64_t n_
     total += c_load * (n_used + Q);
     // a queue is cut into ~kRunsPerQueue runs so that a CTA that finishes early can take over whole runs of another
     const double max_run = std::max(4.0 * c_load, total / Q / std::max(1, P.runs_per_queue));
-    H.run_begin.assign((size_t)Q + 1, 0);
+    runs.clear();
+    run_begin.assign((size_t)Q + 1, 0);
     int q = 0;
     double acc = 0;
     for (int w = 0; w < n_win; w++) {
       uint32_t sb = win_bundles[w];
       const uint32_t se = win_bundles[w + 1];
-      if (sb == se) continue;
+      if (sb == se || !in_class(w)) continue;
       acc += c_load;
       double run_acc = 0;
       for (uint32_t i = sb; i < se; i++) {
@@ -415,20 +424,22 @@ int stage_build_host(const uint32_t *indptr, const uint32_t *indices, int64_t n_
         run_acc += c;
         const bool cut_queue = q < Q - 1 && acc >= total * (q + 1) / Q && i + 1 < se;
         if (cut_queue || (run_acc >= max_run && i + 1 < se)) {
-          H.runs.push_back(make_uint4((uint32_t)w, sb, i + 1, 0));
+          runs.push_back(make_uint4((uint32_t)w, sb, i + 1, 0));
           sb = i + 1;
           run_acc = 0;
           if (cut_queue) {
-            H.run_begin[++q] = (uint32_t)H.runs.size();
+            run_begin[++q] = (uint32_t)runs.size();
             acc += c_load;
           }
         }
       }
-      H.runs.push_back(make_uint4((uint32_t)w, sb, se, 0));
-      if (q < Q - 1 && acc >= total * (q + 1) / Q) H.run_begin[++q] = (uint32_t)H.runs.size();
+      runs.push_back(make_uint4((uint32_t)w, sb, se, 0));
+      if (q < Q - 1 && acc >= total * (q + 1) / Q) run_begin[++q] = (uint32_t)runs.size();
     }
-    while (q < Q) H.run_begin[++q] = (uint32_t)H.runs.size();
-  }
+    while (q < Q) run_begin[++q] = (uint32_t)runs.size();
+  };
+  build_runs(false, H.runs, H.run_begin);
+  build_runs(true, H.own_runs, H.own_run_begin);
   return 0;
 }
 
@@ -442,7 +453,10 @@ namespace gcnb {
 struct StagedDev {
   int dim = 0, window_rows = 0, n_cta = 0;
   int64_t n_rows = 0, n_cols = 0, n_blocks = 0, n_slots = 0, n_runs = 0, staged_nnz = 0, rem_nnz = 0, n_segs = 0;
-  uint4 *d_bundles = nullptr, *d_runs = nullptr;
+  uint4 *d_bundles = nullptr, *d_runs = nullptr, *d_own_runs = nullptr;
+  uint32_t *d_own_run_begin = nullptr;
+  int64_t n_own_runs = 0, own_col0 = 0;
+  bool own_pending = false;  // the own-window runs of the next product have already been launched (gcnb_spmm_stage_own_f32)
   uint16_t *d_lens = nullptr;
   uint32_t *d_run_begin = nullptr, *d_row_slot = nullptr, *d_lane_slot = nullptr, *d_counters = nullptr;
   uint16_t *d_pidx = nullptr;
@@ -466,7 +480,7 @@ void stage_destroy(StagedDev *s) {
   cudaFree(s->d_bundles); cudaFree(s->d_runs); cudaFree(s->d_lens); cudaFree(s->d_run_begin); cudaFree(s->d_row_slot);
   cudaFree(s->d_lane_slot); cudaFree(s->d_counters); cudaFree(s->d_pidx); cudaFree(s->d_pperm); cudaFree(s->d_pval); cudaFree(s->d_partial);
   cudaFree(s->d_r_indptr); cudaFree(s->d_r_indices); cudaFree(s->d_r_perm); cudaFree(s->d_r_val);
-  cudaFree(s->d_pack); cudaFree(s->d_remout);
+  cudaFree(s->d_pack); cudaFree(s->d_remout); cudaFree(s->d_own_runs); cudaFree(s->d_own_run_begin);
   if (s->rem) gcnb_spmm_plan_destroy(s->rem);
   if (s->aux) cudaStreamDestroy(s->aux);
   if (s->ev_fork) cudaEventDestroy(s->ev_fork);
@@ -766,6 +780,30 @@ int slab_vec_width(const void *p, int64_t ld) {
   return 1;
 }
 
+// one launch of the persistent staged kernel over a run list (`counters`: n_cta tickets, zeroed here)
+int launch_staged_runs(StagedDev *s, const uint4 *d_runs, const uint32_t *d_run_begin, uint32_t *counters, const float *d_B,
+                       cudaStream_t stream) {
+  const size_t smem = (size_t)s->window_rows * s->dim * sizeof(float) + 32;
+  static const int nt = [] {
+    const char *e = getenv("GCNB_STAGE_THREADS");  // tuning probe
+    return e ? atoi(e) : 564;
+  }();
+  GCNB_CHECK(cudaMemsetAsync(counters, 0, (size_t)s->n_cta * 4, stream));
+#define GCNB_STAGE_LAUNCH(NT, MINB)                                                                                    \
+  spmm_staged16_kernel<NT, MINB><<<s->n_cta, NT, smem, stream>>>(                                                      \
+      d_runs, d_run_begin, counters, s->n_cta, s->d_bundles, s->d_lens, s->d_lane_slot,                                \
+      reinterpret_cast<const uint2 *>(s->d_pidx), reinterpret_cast<const float4 *>(s->d_pval), d_B, s->d_partial,     \
+      s->window_rows, s->n_cols)
+  if (nt == 1024) GCNB_STAGE_LAUNCH(1024, 1);
+  else if (nt == 512) GCNB_STAGE_LAUNCH(512, 1);
+  else if (nt == 564) GCNB_STAGE_LAUNCH(512, 2);  // 512 threads capped at 64 registers
+  else if (nt == 384) GCNB_STAGE_LAUNCH(384, 1);
+  else GCNB_STAGE_LAUNCH(256, 1);
+#undef GCNB_STAGE_LAUNCH
+  GCNB_LAUNCH_CHECK();
+  return 0;
+}
+
 // C[:, 0..16) (row stride ldc) = A * B[:, 0..16) (row stride ldb) through the staged representation
 int staged_slab16(StagedDev *s, const float *d_B, int64_t ldb, float *d_C, int64_t ldc, cudaStream_t stream) {
   const int sms = std::max(1, device_info().sm_count);
@@ -785,11 +823,6 @@ int staged_slab16(StagedDev *s, const float *d_B, int64_t ldb, float *d_C, int64
     if (!s->d_remout) GCNB_CHECK(cudaMalloc((void **)&s->d_remout, std::max<size_t>(16, (size_t)s->n_rows * 16 * sizeof(float))));
     rem_out = s->d_remout;
   }
-  const size_t smem = (size_t)s->window_rows * s->dim * sizeof(float) + 32;
-  static const int nt = [] {
-    const char *e = getenv("GCNB_STAGE_THREADS");  // tuning probe
-    return e ? atoi(e) : 564;
-  }();
   static const int concurrent = [] {
     const char *e = getenv("GCNB_STAGE_CONCURRENT");  // tuning probe
     return e ? atoi(e) : 1;
@@ -802,19 +835,16 @@ int staged_slab16(StagedDev *s, const float *d_B, int64_t ldb, float *d_C, int64
     GCNB_CHECK(cudaStreamWaitEvent(s->aux, s->ev_fork, 0));
     rs = s->aux;
   }
-  GCNB_CHECK(cudaMemsetAsync(s->d_counters, 0, (size_t)s->n_cta * 4, stream));
-#define GCNB_STAGE_LAUNCH(NT, MINB)                                                                                    \
-  spmm_staged16_kernel<NT, MINB><<<s->n_cta, NT, smem, stream>>>(                                                      \
-      s->d_runs, s->d_run_begin, s->d_counters, s->n_cta, s->d_bundles, s->d_lens, s->d_lane_slot,                     \
-      reinterpret_cast<const uint2 *>(s->d_pidx), reinterpret_cast<const float4 *>(s->d_pval), d_B, s->d_partial,     \
-      s->window_rows, s->n_cols)
-  if (nt == 1024) GCNB_STAGE_LAUNCH(1024, 1);
-  else if (nt == 512) GCNB_STAGE_LAUNCH(512, 1);
-  else if (nt == 564) GCNB_STAGE_LAUNCH(512, 2);  // 512 threads capped at 64 registers
-  else if (nt == 384) GCNB_STAGE_LAUNCH(384, 1);
-  else GCNB_STAGE_LAUNCH(256, 1);
-#undef GCNB_STAGE_LAUNCH
-  GCNB_LAUNCH_CHECK();
+  const bool own_done = s->own_pending;  // launched ahead of the exchange from the rank's own slab
+  s->own_pending = false;
+  if (s->n_runs > 0) {
+    const int rc = launch_staged_runs(s, s->d_runs, s->d_run_begin, s->d_counters, d_B, stream);
+    if (rc) return rc;
+  }
+  if (!own_done && s->n_own_runs > 0) {
+    const int rc = launch_staged_runs(s, s->d_own_runs, s->d_own_run_begin, s->d_counters + s->n_cta, d_B, stream);
+    if (rc) return rc;
+  }
   int rc = spmm_generic_launch(s->rem, s->d_r_val, nullptr, d_B, 16, rem_out, 16, 16, rs);
   if (rc) return rc;
   if (concurrent) {
@@ -898,6 +928,8 @@ int gcnb_spmm_plan_stage_ex(gcnb_spmm_plan *p, const uint32_t *h_indptr, const u
   if (seg_cap > 0) P.seg_cap = seg_cap;
   P.min_window_nnz = min_window_nnz;
   if (window_rows > 0) P.min_avg_seg = 1;  // explicit knobs (tests): stage whatever qualifies
+  P.own_col0 = p->own_col0;
+  P.own_col1 = p->own_col1;
   StagedHost H;
   int rc = stage_build_host(h_indptr, h_indices, p->n_rows, p->n_cols, P, H);
   if (rc == GCNB_E_UNSUPPORTED) return 0;  // too many windows / too large: stay on the generic kernel
@@ -923,6 +955,8 @@ int gcnb_spmm_plan_stage_ex(gcnb_spmm_plan *p, const uint32_t *h_indptr, const u
   s->n_blocks = H.n_blocks;
   s->n_slots = H.n_slots;
   s->n_runs = (int64_t)H.runs.size();
+  s->n_own_runs = (int64_t)H.own_runs.size();
+  s->own_col0 = P.own_col0;
   s->n_segs = H.n_segs;
   s->staged_nnz = H.staged_nnz;
   s->rem_nnz = H.nnz - H.staged_nnz;
@@ -934,9 +968,11 @@ int gcnb_spmm_plan_stage_ex(gcnb_spmm_plan *p, const uint32_t *h_indptr, const u
   if ((rc = upload_vec(&s->d_runs, H.runs, stream))) return fail(rc);
   if ((rc = upload_vec(&s->d_lens, H.lens, stream))) return fail(rc);
   if ((rc = upload_vec(&s->d_run_begin, H.run_begin, stream))) return fail(rc);
+  if ((rc = upload_vec(&s->d_own_runs, H.own_runs, stream))) return fail(rc);
+  if ((rc = upload_vec(&s->d_own_run_begin, H.own_run_begin, stream))) return fail(rc);
   if ((rc = upload_vec(&s->d_row_slot, H.row_slot, stream))) return fail(rc);
   if ((rc = upload_vec(&s->d_lane_slot, H.lane_slot, stream))) return fail(rc);
-  if ((rc = (int)cudaMalloc((void **)&s->d_counters, (size_t)H.n_cta * 4))) return fail(rc);
+  if ((rc = (int)cudaMalloc((void **)&s->d_counters, (size_t)H.n_cta * 2 * 4))) return fail(rc);
   if ((rc = (int)cudaStreamCreateWithFlags(&s->aux, cudaStreamNonBlocking))) return fail(rc);
   if ((rc = (int)cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming))) return fail(rc);
   if ((rc = (int)cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming))) return fail(rc);
@@ -958,6 +994,29 @@ int gcnb_spmm_plan_stage_ex(gcnb_spmm_plan *p, const uint32_t *h_indptr, const u
   return 0;
 }
 
+int gcnb_spmm_plan_set_own_cols(gcnb_spmm_plan *p, int64_t col0, int64_t col1) {
+  if (!p || col0 < 0 || col1 < col0 || col1 > p->n_cols) return GCNB_E_BADARG;
+  p->own_col0 = col0;
+  p->own_col1 = col1;
+  return 0;
+}
+
+int gcnb_spmm_stage_own_f32(gcnb_spmm_plan *p, const float *d_values, const float *d_B_own, int dim, gcnb_stream_t stream_,
+                            int *launched) {
+  if (!p || !d_values || !d_B_own || !launched) return GCNB_E_BADARG;
+  *launched = 0;
+  StagedDev *s = p->staged;
+  if (!s || dim != 16 || s->dim != 16 || d_values != s->values_src || s->n_own_runs == 0 || (uintptr_t)d_B_own % 16 != 0)
+    return 0;
+  // the own-window runs only touch rows [own_col0, own_col1) of B: address them through the slab
+  const float *base = d_B_own - s->own_col0 * 16;
+  const int rc = launch_staged_runs(s, s->d_own_runs, s->d_own_run_begin, s->d_counters + s->n_cta, base, as_stream(stream_));
+  if (rc) return rc;
+  s->own_pending = true;
+  *launched = 1;
+  return 0;
+}
+
 int gcnb_spmm_plan_stage_slabs(const gcnb_spmm_plan *p, int dim) {
   const StagedDev *s = p ? p->staged : nullptr;
   if (!s || s->dim != 16 || (dim != 16 && dim < stage_slab_min_dim())) return 0;
@@ -970,7 +1029,7 @@ int gcnb_spmm_plan_stage_info(const gcnb_spmm_plan *p, int64_t out[8]) {
   const StagedDev *s = p->staged;
   if (!s) return 0;
   out[0] = 1; out[1] = s->window_rows; out[2] = s->staged_nnz; out[3] = s->rem_nnz;
-  out[4] = s->n_segs; out[5] = s->n_runs; out[6] = s->n_blocks; out[7] = s->n_slots;
+  out[4] = s->n_segs; out[5] = s->n_runs + s->n_own_runs; out[6] = s->n_blocks; out[7] = s->n_slots;
   return 0;
 }
 
@@ -982,6 +1041,13 @@ struct gcnb_stage_host {
 int gcnb_stage_host_build(const uint32_t *h_indptr, const uint32_t *h_indices, int64_t n_rows, int64_t n_cols, int dim,
                           int window_rows, int min_seg, int seg_cap, int64_t min_window_nnz, int n_cta, int n_threads,
                           gcnb_stage_host **out) {
+  return gcnb_stage_host_build_own(h_indptr, h_indices, n_rows, n_cols, dim, window_rows, min_seg, seg_cap, min_window_nnz,
+                                   n_cta, n_threads, 0, 0, out);
+}
+
+int gcnb_stage_host_build_own(const uint32_t *h_indptr, const uint32_t *h_indices, int64_t n_rows, int64_t n_cols, int dim,
+                              int window_rows, int min_seg, int seg_cap, int64_t min_window_nnz, int n_cta, int n_threads,
+                              int64_t own_col0, int64_t own_col1, gcnb_stage_host **out) {
   if (!out) return GCNB_E_BADARG;
   StageParams P;
   P.dim = dim;
@@ -991,6 +1057,8 @@ int gcnb_stage_host_build(const uint32_t *h_indptr, const uint32_t *h_indices, i
   P.min_window_nnz = min_window_nnz;
   if (n_cta > 0) P.n_cta = n_cta;
   P.n_threads = n_threads;
+  P.own_col0 = own_col0;
+  P.own_col1 = own_col1;
   auto *h = new gcnb_stage_host();
   const int rc = stage_build_host(h_indptr, h_indices, n_rows, n_cols, P, h->H);
   if (rc) {
@@ -1001,12 +1069,13 @@ int gcnb_stage_host_build(const uint32_t *h_indptr, const uint32_t *h_indices, i
   return 0;
 }
 
-int gcnb_stage_host_sizes(const gcnb_stage_host *h, int64_t out[12]) {
+int gcnb_stage_host_sizes(const gcnb_stage_host *h, int64_t out[13]) {
   if (!h || !out) return GCNB_E_BADARG;
   const StagedHost &H = h->H;
   out[0] = H.window_rows; out[1] = H.n_win; out[2] = H.n_cta; out[3] = H.staged_nnz;
   out[4] = (int64_t)H.bundles.size(); out[5] = (int64_t)H.runs.size(); out[6] = H.n_blocks; out[7] = H.n_slots;
   out[8] = (int64_t)H.r_indices.size(); out[9] = H.n_rows; out[10] = H.nnz; out[11] = H.n_segs;
+  out[12] = (int64_t)H.own_runs.size();
   return 0;
 }
 
@@ -1029,6 +1098,8 @@ int gcnb_stage_host_copy(const gcnb_stage_host *h, int which, void *dst, int64_t
     case 8: src = H.r_perm.data(); n = H.r_perm.size() * 4; break;
     case 9: src = H.lens.data(); n = H.lens.size() * 2; break;
     case 10: src = H.lane_slot.data(); n = H.lane_slot.size() * 4; break;
+    case 11: src = H.own_runs.data(); n = H.own_runs.size() * sizeof(uint4); break;
+    case 12: src = H.own_run_begin.data(); n = H.own_run_begin.size() * 4; break;
     default: return GCNB_E_BADARG;
   }
   memcpy(dst, src, std::min<size_t>(n, (size_t)bytes));

@@ -62,6 +62,9 @@ _sig("gcnb_synth_graph", I32, [I64, I64, I32, C.c_double, C.c_double, I64, C.c_u
 _sig("gcnb_host_free", None, [P])
 _sig("gcnb_synth_dense_features", I32, [I64, I32, C.c_uint64, P, P, P])
 _sig("gcnb_synth_labels", I32, [I64, I32, C.c_double, C.c_double, C.c_uint64, P, P])
+_sig("gcnb_synth_sym_rows", I32, [I64, I64, I64, I64, C.c_double, C.c_double, I32, C.c_double, C.c_uint64, P, P, P])
+_sig("gcnb_synth_graph_values", I32, [P, P, I64, I64, P, P])
+_sig("gcnb_synth_dense_features_uniform", I32, [I64, I32, C.c_uint64, C.c_uint64, P, P, P])
 
 
 def _p(a):
@@ -144,6 +147,47 @@ def synth_dataset(n, n_undirected_edges, n_features, n_classes, n_blocks=50, int
                      split_counts=tuple(int((split == s).sum()) for s in (1, 2, 3)))
     ds._pinned_keepalive = keep
     return ds
+
+
+def _adopt(ptr_, ctype, n):
+    """numpy view of a malloc'ed array returned by the library; freed (gcnb_host_free) when the array is collected"""
+    import weakref
+    if n == 0:
+        lib.gcnb_host_free(ptr_)
+        return np.empty(0, np.dtype(ctype))
+    a = np.ctypeslib.as_array(C.cast(ptr_, C.POINTER(ctype)), shape=(n,))
+    weakref.finalize(a, lib.gcnb_host_free, C.c_void_p(ptr_.value))
+    return a
+
+
+def synth_sym_rows(n, row0, rows, block_size=4000, mean_intra=200.0, mean_inter=50.0, n_reflect=2048, sigma=1.0,
+                   seed=19990304):
+    """rows [row0, row0 + rows) of the row-local symmetric community graph (gcnb_synth_sym_rows); global column ids"""
+    ip, ix, nnz = P(), P(), I64(0)
+    check(lib.gcnb_synth_sym_rows(n, row0, rows, block_size, mean_intra, mean_inter, n_reflect, sigma, seed, C.byref(ip),
+                                  C.byref(ix), C.byref(nnz)))
+    return _adopt(ip, C.c_uint32, rows + 1), _adopt(ix, C.c_uint32, nnz.value)
+
+
+def synth_graph_values(indptr, indices, row0, deg_global):
+    out = np.empty(len(indices), np.float32)
+    deg_global = np.ascontiguousarray(deg_global, np.uint32)
+    check(lib.gcnb_synth_graph_values(_p(indptr), _p(indices), len(indptr) - 1, row0, _p(deg_global), _p(out)))
+    return out
+
+
+def synth_dense_features_uniform(rows, n_features, seed, elem_offset=0):
+    f_indptr = np.empty(rows + 1, np.uint32)
+    f_indices = np.empty(rows * n_features, np.uint32)
+    f_value = np.empty(rows * n_features, np.float32)
+    check(lib.gcnb_synth_dense_features_uniform(rows, n_features, seed, elem_offset, _p(f_indptr), _p(f_indices), _p(f_value)))
+    return f_indptr, f_indices, f_value
+
+
+def synth_labels(n, n_classes, frac_train=0.66, frac_val=0.10, seed=19990304):
+    label, split = np.empty(n, np.int32), np.empty(n, np.uint32)
+    check(lib.gcnb_synth_labels(n, n_classes, frac_train, frac_val, seed, _p(label), _p(split)))
+    return label, split
 
 
 COMM_ID_BYTES = 128

@@ -103,6 +103,9 @@ struct GCNEngineState {
   // upper layers) overlaps with the GraphSum / feature products on `stream`
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_bits = nullptr, ev_epoch = nullptr;
+  cudaStream_t comm_stream = nullptr;  // slab exchange of the partitioned GraphSum, overlapped with own-slab windows
+  cudaEvent_t ev_cfork = nullptr, ev_gather = nullptr;
+  bool overlap_gather = false;
   bool side_pending = false;  // side-stream work of this backward pass not yet joined
   // row-partitioned multi-GPU mode: this rank owns global rows [row0, row0 + N); GraphSum inputs are
   // all-gathered in slabs of `block` rows, weight gradients and the loss / count scalars are sum-all-reduced
@@ -117,7 +120,7 @@ struct GCNEngineState {
   // evaluation passes read pristine features, and both A_hat and X are constants: layer 0 of an evaluation forward is
   // (A_hat X) W0 with P = A_hat X computed once (first evaluation), instead of A_hat (X W0) -- one GraphSum less per pass
   dev_shared_ptr<real> ax;
-  bool ax_tried = false, ax_ready = false;
+  bool ax_tried = false, ax_ready = false, ax_planned = false;
   dev_shared_ptr<real> tn_ws;
   int64_t tn_ws_bytes = 0;
   dev_shared_ptr<natural> ce_ws, sumsq_ws;
@@ -146,7 +149,19 @@ struct GCNEngineState {
         }
       CHECK_CUDA_ERROR(cudaEventRecord(gs_events[gs_used], stream));
     }
-    if (dist) {
+    if (dist && overlap_gather && graph_staged && dim == 16) {
+      // the exchange runs on its own stream while the staged windows that lie inside this rank's own slab are already
+      // being processed from `in`; everything that needs a peer's rows waits for ev_gather
+      CHECK_CUDA_ERROR(cudaEventRecord(ev_cfork, stream));
+      CHECK_CUDA_ERROR(cudaStreamWaitEvent(comm_stream, ev_cfork, 0));
+      const real *full = nullptr;
+      GCNB_CALL(gcnb_comm_gather_slabs_f32(comm, in, (int64_t)block * dim, &full, comm_stream));
+      CHECK_CUDA_ERROR(cudaEventRecord(ev_gather, comm_stream));
+      int launched = 0;
+      GCNB_CALL(gcnb_spmm_stage_own_f32(graph_plan, gv, in, (int)dim, stream, &launched));
+      CHECK_CUDA_ERROR(cudaStreamWaitEvent(stream, ev_gather, 0));
+      in = full;
+    } else if (dist) {
       // the slab [block x dim] of every rank, concatenated in rank order, IS the global [N x dim] matrix
       GCNB_CALL(gcnb_comm_gather_slabs_f32(comm, in, (int64_t)block * dim, &in, stream));
     }
@@ -180,8 +195,9 @@ struct GCNEngineState {
     if (feat_plan) gcnb_spmm_plan_destroy(feat_plan);
     if (graph_plan) gcnb_spmm_plan_destroy(graph_plan);
     if (side && side != stream) cudaStreamDestroy(side);
-    for (cudaEvent_t e : {ev_fork, ev_join, ev_bits, ev_epoch})
+    for (cudaEvent_t e : {ev_fork, ev_join, ev_bits, ev_epoch, ev_cfork, ev_gather})
       if (e) cudaEventDestroy(e);
+    if (comm_stream) cudaStreamDestroy(comm_stream);
     if (stream) cudaStreamDestroy(stream);
   }
 };
@@ -235,8 +251,13 @@ void GCN::init(bool quiet, const natural *h_graph_indptr, const natural *h_graph
   if (const char *e = getenv("GCNB_SIDE_STREAM")) st->use_side = atoi(e);  // tuning probe: 0 = single stream
   if (st->use_side & 1) CHECK_CUDA_ERROR(cudaStreamCreateWithFlags(&st->side, cudaStreamNonBlocking));
   else st->side = st->stream;
-  for (cudaEvent_t *e : {&st->ev_fork, &st->ev_join, &st->ev_bits, &st->ev_epoch})
+  for (cudaEvent_t *e : {&st->ev_fork, &st->ev_join, &st->ev_bits, &st->ev_epoch, &st->ev_cfork, &st->ev_gather})
     CHECK_CUDA_ERROR(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+  if (st->dist) {
+    const char *e = getenv("GCNB_DIST_OVERLAP");  // tuning probe: 0 = exchange and product strictly in sequence
+    st->overlap_gather = !(e && atoi(e) == 0);
+    if (st->overlap_gather) CHECK_CUDA_ERROR(cudaStreamCreateWithFlags(&st->comm_stream, cudaStreamNonBlocking));
+  }
   const natural N = params->num_nodes, F = params->input_dim;
   dev_truth = dev_shared_ptr<integer>(N);
   decays.resize(L, false);  // only W0 is L2-regularised / decayed (src/gcn.cu:157-158)
@@ -302,6 +323,15 @@ void GCN::init(bool quiet, const natural *h_graph_indptr, const natural *h_graph
   if (st->dist) {
     natural dmax = 0;
     for (size_t i = 1; i < dims.size(); i++) dmax = std::max(dmax, dims[i]);
+    // feature propagation (see ax): the whole feature matrix goes through the slab gather once, if it is small enough.
+    // The criterion depends only on global sizes, so every rank decides alike (the gather is collective).
+    {
+      const char *e = getenv("GCNB_PROPAGATE");
+      const double gather_bytes = 2.0 * (double)gcnb_comm_world(st->comm) * (double)st->block * (double)F * sizeof(real);
+      st->ax_planned = !(e && atoi(e) == 0) && gather_bytes < 24e9 && gcnb_dense_feat_supported((int)F, (int)dims[1]) &&
+                       st->f_nnz_global == st->n_global * (size_t)F;  // all-columns features on every rank
+      if (st->ax_planned) dmax = std::max(dmax, F);
+    }
     GCNB_CALL(gcnb_comm_gather_setup(st->comm, (int64_t)gcnb_comm_world(st->comm) * st->block * dmax));
     for (GCNLayer &ly : st->layers)  // padding rows are shipped by the all-gather: keep them defined
       for (const shared_ptr<Variable> &v : {ly.pre, ly.z}) {
@@ -318,6 +348,7 @@ void GCN::init(bool quiet, const natural *h_graph_indptr, const natural *h_graph
       const natural d = ly.reorder ? ly.in_dim : ly.out_dim;
       wanted |= d == 16 || d >= 64;
     }
+    if (wanted && st->dist) GCNB_CALL(gcnb_spmm_plan_set_own_cols(st->graph_plan, (int64_t)st->row0, (int64_t)(st->row0 + N)));
     if (wanted) {
       GCNB_CALL(gcnb_spmm_plan_stage(st->graph_plan, h_graph_indptr, h_graph_indices, dev_data.dev_graph_value.get(),
                                      16, st->stream));
@@ -482,16 +513,30 @@ void GCN::forward_pass(bool training, natural split, cudaStream_t s) {
     Variable::rng_consume(input_elems);  // the reference draws even when p == 0
     st->x_train_vals = xvals;
   }
-  if (!training && st->dense_fast && !st->dist && st->allow_reorder && !st->ax_tried) {
+  if (!training && st->dense_fast && st->allow_reorder && !st->ax_tried) {
     st->ax_tried = true;
-    const char *e = getenv("GCNB_PROPAGATE");  // tuning probe: 0 keeps the module chain's A_hat (X W0) in evaluation
-    size_t free_b = 0, total_b = 0;
-    CHECK_CUDA_ERROR(cudaMemGetInfo(&free_b, &total_b));
-    const size_t bytes = (size_t)N * F * sizeof(real);
-    if (!(e && atoi(e) == 0) && free_b > bytes + (size_t(4) << 30)) {
-      st->ax = dev_shared_ptr<real>((size_t)N * F);
-      GCNB_CALL(gcnb_spmm_ld_f32(st->graph_plan, dev_data.dev_graph_value.get(), nullptr, xvals, F, st->ax.get(), F, (int)F, s));
-      st->ax_ready = true;
+    if (st->dist) {
+      if (st->ax_planned) {  // collective: every rank takes this branch (ax_planned depends on global sizes only)
+        dev_shared_ptr<real> xpad((size_t)st->block * F);
+        CHECK_CUDA_ERROR(cudaMemsetAsync(xpad.get(), 0, (size_t)st->block * F * sizeof(real), s));
+        CHECK_CUDA_ERROR(cudaMemcpyAsync(xpad.get(), xvals, (size_t)N * F * sizeof(real), cudaMemcpyDeviceToDevice, s));
+        const real *xfull = nullptr;
+        GCNB_CALL(gcnb_comm_gather_slabs_f32(st->comm, xpad.get(), (int64_t)st->block * F, &xfull, s));
+        st->ax = dev_shared_ptr<real>((size_t)N * F);
+        GCNB_CALL(gcnb_spmm_ld_f32(st->graph_plan, dev_data.dev_graph_value.get(), nullptr, xfull, F, st->ax.get(), F, (int)F, s));
+        CHECK_CUDA_ERROR(cudaStreamSynchronize(s));  // xpad is released here
+        st->ax_ready = true;
+      }
+    } else {
+      const char *e = getenv("GCNB_PROPAGATE");  // tuning probe: 0 keeps the module chain's A_hat (X W0) in evaluation
+      size_t free_b = 0, total_b = 0;
+      CHECK_CUDA_ERROR(cudaMemGetInfo(&free_b, &total_b));
+      const size_t bytes = (size_t)N * F * sizeof(real);
+      if (!(e && atoi(e) == 0) && free_b > bytes + (size_t(4) << 30)) {
+        st->ax = dev_shared_ptr<real>((size_t)N * F);
+        GCNB_CALL(gcnb_spmm_ld_f32(st->graph_plan, dev_data.dev_graph_value.get(), nullptr, xvals, F, st->ax.get(), F, (int)F, s));
+        st->ax_ready = true;
+      }
     }
   }
   if (!training && st->ax_ready && st->allow_reorder) {

@@ -198,4 +198,119 @@ int gcnb_synth_labels(int64_t n, int classes, double frac_train, double frac_val
   return 0;
 }
 
+// ---- row-local symmetric generator (scale-out workloads: every rank builds ONLY its row block) -------------------------
+// Whether the undirected edge {i, j} exists is a pure function of (seed, min(i,j), max(i,j)), so any row can be
+// generated without looking at any other row and the union of all rows is a symmetric simple graph:
+//   * inside a community (contiguous blocks of `block_size` nodes) every pair is a candidate, accepted with
+//     probability p_in * w_i * w_j;
+//   * across communities the candidates of node i are its images under `n_reflect` fixed reflections
+//     j = (c_k - i) mod n (an involution: i is then the k-th candidate of j), accepted with p_out * w_i * w_j;
+//   * w = lognormal(sigma) expected-degree weights with mean ~1, clipped so that no probability exceeds 1.
+int gcnb_synth_sym_rows(int64_t n, int64_t row0, int64_t rows, int64_t block_size, double mean_intra, double mean_inter,
+                        int n_reflect, double sigma, uint64_t seed, uint32_t **indptr_out, uint32_t **indices_out,
+                        int64_t *nnz_out) {
+  if (n <= 1 || n > 0xffffffffll || row0 < 0 || rows < 0 || row0 + rows > n || block_size < 2 || n_reflect < 0 ||
+      mean_intra < 0 || mean_inter < 0 || !indptr_out || !indices_out || !nnz_out)
+    return GCNB_E_BADARG;
+  const double p_in = std::min(1.0, mean_intra / (double)block_size);
+  const double p_out = n_reflect > 0 ? std::min(1.0, mean_inter / (double)n_reflect) : 0.0;
+  const double w_max = std::sqrt(1.0 / std::max({p_in, p_out, 1e-12}));
+  std::vector<float> w((size_t)n);
+  parallel_for(n, [&](int64_t a, int64_t b) {
+    for (int64_t i = a; i < b; i++)
+      w[i] = (float)std::min(w_max, std::exp(sigma * normal(seed, 11, (uint64_t)i) - 0.5 * sigma * sigma));
+  });
+  std::vector<int64_t> refl((size_t)n_reflect);
+  for (int k = 0; k < n_reflect; k++) refl[k] = (int64_t)(rnd(seed, 12, (uint64_t)k) % (uint64_t)n);
+  const uint64_t pair_seed = mix64(seed ^ 0x5eed5eedull);
+  auto accept = [&](uint64_t i, uint64_t j, double p) {
+    const uint64_t lo = std::min(i, j), hi = std::max(i, j);
+    return u01(mix64(pair_seed ^ ((lo << 32) | hi))) < p * (double)w[lo] * (double)w[hi];
+  };
+  const unsigned nt = rows < 1024 ? 1 : n_threads();
+  std::vector<std::vector<uint32_t>> t_idx(nt);
+  std::vector<uint32_t> deg((size_t)rows, 0);
+  std::vector<std::thread> th;
+  for (unsigned t = 0; t < nt; t++)
+    th.emplace_back([&, t] {
+      std::vector<uint32_t> &out = t_idx[t];
+      std::vector<uint32_t> row;
+      for (int64_t r = rows * t / nt; r < rows * (t + 1) / nt; r++) {
+        const int64_t i = row0 + r;
+        const int64_t b0 = (i / block_size) * block_size, b1 = std::min(n, b0 + block_size);
+        row.clear();
+        for (int64_t j = b0; j < b1; j++)
+          if (j != i && accept((uint64_t)i, (uint64_t)j, p_in)) row.push_back((uint32_t)j);
+        const size_t n_in = row.size();
+        for (int k = 0; k < n_reflect; k++) {
+          int64_t j = refl[k] - i;
+          if (j < 0) j += n;
+          if (j == i || (j >= b0 && j < b1)) continue;
+          if (accept((uint64_t)i, (uint64_t)j, p_out)) row.push_back((uint32_t)j);
+        }
+        std::sort(row.begin() + n_in, row.end());
+        row.erase(std::unique(row.begin() + n_in, row.end()), row.end());
+        std::inplace_merge(row.begin(), row.begin() + n_in, row.end());
+        deg[r] = (uint32_t)row.size() + 1;
+        out.push_back((uint32_t)i);
+        out.insert(out.end(), row.begin(), row.end());
+      }
+    });
+  for (auto &x : th) x.join();
+  uint64_t nnz = 0;
+  for (auto &v : t_idx) nnz += v.size();
+  if (nnz > 0xfffffff0ull) return GCNB_E_UNSUPPORTED;
+  uint32_t *indptr = (uint32_t *)std::malloc(((size_t)rows + 1) * 4);
+  uint32_t *indices = (uint32_t *)std::malloc(std::max<size_t>(4, (size_t)nnz * 4));
+  if (!indptr || !indices) return GCNB_E_UNSUPPORTED;
+  indptr[0] = 0;
+  for (int64_t r = 0; r < rows; r++) indptr[r + 1] = indptr[r] + deg[r];
+  th.clear();
+  for (unsigned t = 0; t < nt; t++)
+    th.emplace_back([&, t] {
+      if (!t_idx[t].empty()) std::memcpy(indices + indptr[rows * t / nt], t_idx[t].data(), t_idx[t].size() * 4);
+    });
+  for (auto &x : th) x.join();
+  *indptr_out = indptr;
+  *indices_out = indices;
+  *nnz_out = (int64_t)nnz;
+  return 0;
+}
+
+// graph_value of a row block from GLOBAL degrees, the reference's arithmetic (src/parser.cpp:164-181):
+// 1. / sqrtf(unsigned(deg_src * deg_dst)), the divide in double, then rounded to fp32
+int gcnb_synth_graph_values(const uint32_t *indptr, const uint32_t *indices, int64_t rows, int64_t row0,
+                            const uint32_t *deg_global, float *out) {
+  if (!indptr || !indices || !deg_global || !out || rows < 0) return GCNB_E_BADARG;
+  parallel_for(rows, [&](int64_t a, int64_t b) {
+    for (int64_t r = a; r < b; r++) {
+      const uint32_t ds = deg_global[row0 + r];
+      for (uint32_t e = indptr[r]; e < indptr[r + 1]; e++) out[e] = (float)(1. / sqrtf((float)(ds * deg_global[indices[e]])));
+    }
+  });
+  return 0;
+}
+
+// cheap dense features for the large workloads: uniform on [-sqrt(3), sqrt(3)) (unit variance), one hash per two values
+int gcnb_synth_dense_features_uniform(int64_t n, int f, uint64_t seed, uint64_t elem_offset, uint32_t *indptr,
+                                      uint32_t *indices, float *values) {
+  if (n < 0 || f <= 0 || !indptr || !indices || !values) return GCNB_E_BADARG;
+  if ((uint64_t)n * (uint64_t)f > 0xffffffffull) return GCNB_E_UNSUPPORTED;
+  parallel_for(n, [&](int64_t a, int64_t b) {
+    for (int64_t i = a; i < b; i++) {
+      indptr[i] = (uint32_t)(i * f);
+      for (int j = 0; j < f; j++) {
+        const size_t e = (size_t)i * f + j;
+        const uint64_t g = elem_offset + e;
+        const uint64_t h = rnd(seed, 13, g >> 1);
+        const uint32_t bits = (g & 1) ? (uint32_t)(h >> 32) : (uint32_t)h;
+        indices[e] = (uint32_t)j;
+        values[e] = ((float)(bits >> 8) * (1.0f / 16777216.0f) - 0.5f) * 3.4641016f;
+      }
+    }
+  });
+  indptr[n] = (uint32_t)(n * f);
+  return 0;
+}
+
 }  // extern "C"

@@ -164,6 +164,42 @@ def test_graphsum_window_staged_wide(O, gcnb, dev, dim, ld, monkeypatch):
     plan.close()
 
 
+def test_graphsum_window_staged_own_slab_first(O, gcnb, dev):
+    """row-partitioned GraphSum: the staged windows inside the rank's own column range are launched from the own slab
+    before the gathered matrix exists (gcnb_spmm_stage_own_f32), the rest afterwards -- same product, bit-identical to
+    the one-call form."""
+    import torch
+    from tests.test_stage_cpu import community_csr
+    rng = np.random.default_rng(17)
+    n_rows, n_cols, dim = 2000, 6000, 16   # a row block [2000, 4000) of a 6000-node graph
+    own = (2000, 4000)
+    ip, ix = community_csr(rng, n_cols, 6, 60, 0.8)
+    indptr = (ip[own[0]:own[1] + 1] - ip[own[0]]).astype(u32)
+    indices = np.ascontiguousarray(ix[ip[own[0]]:ip[own[1]]])
+    values = rng.standard_normal(len(indices)).astype(f32)
+    x = rng.standard_normal((n_cols, dim)).astype(f32)
+    want = np.empty((n_rows, dim), f32)
+    O.lib.orc_spmm(n_rows, dim, O._p(indptr), O._p(indices), O._p(values), O._p(x), O._p(want))
+    d_ip, d_ix, d_v, d_x = (to_dev(a, dev) for a in (indptr, indices, values, x))
+    plan = gcnb.SpmmPlan(d_ip, d_ix, n_cols)
+    plan.set_own_cols(*own)
+    info = plan.stage(d_v, dim, None, None, 512, 8, 64, 1)
+    assert info["staged"] == 1
+    one = torch.full((n_rows, dim), float("nan"), device=dev)
+    plan.spmm(d_v, d_x, one, dim)            # everything from the full matrix
+    torch.cuda.synchronize()
+    assert_close(to_np(one), want, what="staged spmm, own + remote runs in one call")
+    own_slab = d_x[own[0]:own[1]].clone()    # only the rank's rows exist at this point
+    full_late = torch.full_like(d_x, float("nan"))
+    assert plan.stage_own(d_v, own_slab, dim)
+    full_late.copy_(d_x)                     # "the exchange completes"
+    two = torch.full((n_rows, dim), float("nan"), device=dev)
+    plan.spmm(d_v, full_late, two, dim)
+    torch.cuda.synchronize()
+    assert torch.equal(one, two)
+    plan.close()
+
+
 def test_graphsum_ref_cpu_flavour(O, gcnb, dev, datasets):
     """the ref-CPU GraphSum recomputes coef per edge (module.cpp:86-90); hoisted values give the same bits."""
     ds = datasets["cora"]

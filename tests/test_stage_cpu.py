@@ -167,3 +167,28 @@ def test_stage_plan_queues_are_balanced(gcnb):
             # the builder's cycle model: window copy + per-bundle overhead + steps
             cost[q] += 6000 + 80 * (se - sb) + 18.0 * plan["bundles"][sb:se, 1].astype(np.int64).sum()
     assert cost.min() > 0 and cost.max() / cost.mean() < 1.15, cost
+
+
+def test_stage_plan_own_column_range_splits_runs(gcnb):
+    """row-partitioned GraphSum: windows entirely inside the rank's own column range go to a second run list; the two
+    lists together cover every bundle exactly once and reproduce the product."""
+    rng = np.random.default_rng(13)
+    n = 6000
+    indptr, indices = community_csr(rng, n, 6, 50, 0.8)
+    values = rng.standard_normal(indices.size).astype(np.float32)
+    B = rng.standard_normal((n, 16)).astype(np.float32)
+    own = (1900, 4100)
+    plan = gcnb.stage_host_build(indptr, indices, n, 16, 512, 8, 64, 1, 7, 2, own_cols=own)
+    assert plan["n_own_runs"] > 0 and plan["n_runs"] > 0
+    for w, sb, se, _ in plan["own_runs"]:
+        assert w * 512 >= own[0] and min(n, (w + 1) * 512) <= own[1] and sb < se
+    for w, sb, se, _ in plan["runs"]:
+        assert not (w * 512 >= own[0] and min(n, (w + 1) * 512) <= own[1])
+    assert plan["own_run_begin"][0] == 0 and plan["own_run_begin"][-1] == plan["n_own_runs"]
+    base = gcnb.stage_host_build(indptr, indices, n, 16, 512, 8, 64, 1, 7, 2)
+    assert base["n_own_runs"] == 0 and np.array_equal(base["bundles"], plan["bundles"])
+    merged = dict(plan)
+    merged["runs"] = np.concatenate([plan["runs"], plan["own_runs"]])
+    merged["run_begin"] = np.array([0] * 7 + [len(merged["runs"])], np.uint32)
+    got = emulate(merged, indptr, indices, values, B)
+    assert_close(got, reference(indptr, indices, values, B), rtol=1e-9, what="own + remote runs")
