@@ -276,6 +276,10 @@ GCNB_API int gcnb_comm_all_reduce_sum(gcnb_comm *c, void *d_buf, int64_t count, 
 GCNB_API int gcnb_comm_gather_setup(gcnb_comm *c, int64_t gather_floats);
 GCNB_API int gcnb_comm_gather_slabs_f32(gcnb_comm *c, const float *d_slab, int64_t count_per_rank,
                                         const float **d_full_out, gcnb_stream_t stream);
+/* same; overlapped != 0 tells the communicator that the caller computes on another stream meanwhile: large slabs then
+ * travel through the copy engines (peer cudaMemcpyAsync + a flag kernel) instead of the SM push kernel */
+GCNB_API int gcnb_comm_gather_slabs_ex_f32(gcnb_comm *c, const float *d_slab, int64_t count_per_rank,
+                                           const float **d_full_out, int overlapped, gcnb_stream_t stream);
 GCNB_API int gcnb_comm_gather_mode(const gcnb_comm *c);
 GCNB_API int gcnb_comm_group_start(gcnb_comm *c);
 GCNB_API int gcnb_comm_group_end(gcnb_comm *c);

@@ -115,6 +115,16 @@ p2p_push_kernel(const float4 *__restrict__ slab, int64_t n4, P2PPeers peers, int
   }
 }
 
+// copy-engine variant of the push: the slabs travel as peer cudaMemcpyAsync calls (no SM, no LSU traffic -- the SMs are
+// busy with the staged windows of the rank's own slab meanwhile); this kernel, next in stream order, publishes the flags
+__global__ void p2p_flag_kernel(P2PPeers peers, uint32_t epoch) {
+  __threadfence_system();
+  if (threadIdx.x < peers.world) {
+    uint32_t *f = peers.flags[threadIdx.x] + peers.rank;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(epoch) : "memory");
+  }
+}
+
 // wait until every rank's slab `epoch` has landed in this rank's buffer
 __global__ void p2p_wait_kernel(const uint32_t *__restrict__ flags, int world, uint32_t epoch) {
   if (threadIdx.x < world) {
@@ -277,6 +287,11 @@ int gcnb_comm_gather_mode(const gcnb_comm *c) { return c ? (c->world == 1 ? 0 : 
 // overwrites has been consumed.
 int gcnb_comm_gather_slabs_f32(gcnb_comm *c, const float *d_slab, int64_t count_per_rank, const float **d_full_out,
                                gcnb_stream_t s) {
+  return gcnb_comm_gather_slabs_ex_f32(c, d_slab, count_per_rank, d_full_out, 0, s);
+}
+
+int gcnb_comm_gather_slabs_ex_f32(gcnb_comm *c, const float *d_slab, int64_t count_per_rank, const float **d_full_out,
+                                  int overlapped, gcnb_stream_t s) {
   if (!c || !d_slab || !d_full_out || count_per_rank <= 0 || !c->gather_local[0]) return GCNB_E_BADARG;
   if (count_per_rank * c->world > c->gather_floats || count_per_rank % 4 || ((uintptr_t)d_slab % 16)) return GCNB_E_BADARG;
   cudaStream_t st = as_stream(s);
@@ -289,6 +304,24 @@ int gcnb_comm_gather_slabs_f32(gcnb_comm *c, const float *d_slab, int64_t count_
     return 0;
   }
   if (!c->p2p) return nccl_rc(nccl().AllGather(d_slab, full, (size_t)count_per_rank, ncclFloat, c->comm, st));
+  // exchange overlapped with compute on another stream and large enough to amortise 1 + world API calls: copy engines
+  static const int dma_env = [] {
+    const char *e = getenv("GCNB_P2P_DMA");  // tuning probe: 0 never, 1 always, unset = overlapped exchanges >= 4 MB
+    return e ? atoi(e) : -1;
+  }();
+  const bool dma = dma_env == 1 || (dma_env < 0 && overlapped && count_per_rank * 4 >= (4 << 20));
+  if (dma) {
+    for (int k = 0; k < c->world; k++) {
+      const int p = (c->rank + 1 + k) % c->world;  // start with the next rank: no two ranks target one peer at once
+      GCNB_CHECK(cudaMemcpyAsync(c->peers.gather[buf][p] + (size_t)c->rank * count_per_rank, d_slab,
+                                 (size_t)count_per_rank * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    p2p_flag_kernel<<<1, 32, 0, st>>>(c->peers, epoch);
+    GCNB_LAUNCH_CHECK();
+    p2p_wait_kernel<<<1, 32, 0, st>>>(c->flags_local, c->world, epoch);
+    GCNB_LAUNCH_CHECK();
+    return 0;
+  }
   const int64_t n4 = count_per_rank / 4;
   const int blocks = (int)std::min<int64_t>((n4 + 255) / 256, (int64_t)std::max(1, gcnb::device_info().sm_count) * 2);
   p2p_push_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float4 *>(d_slab), n4, c->peers, buf,

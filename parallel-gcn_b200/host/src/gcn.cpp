@@ -155,7 +155,7 @@ struct GCNEngineState {
       CHECK_CUDA_ERROR(cudaEventRecord(ev_cfork, stream));
       CHECK_CUDA_ERROR(cudaStreamWaitEvent(comm_stream, ev_cfork, 0));
       const real *full = nullptr;
-      GCNB_CALL(gcnb_comm_gather_slabs_f32(comm, in, (int64_t)block * dim, &full, comm_stream));
+      GCNB_CALL(gcnb_comm_gather_slabs_ex_f32(comm, in, (int64_t)block * dim, &full, 1, comm_stream));
       CHECK_CUDA_ERROR(cudaEventRecord(ev_gather, comm_stream));
       int launched = 0;
       GCNB_CALL(gcnb_spmm_stage_own_f32(graph_plan, gv, in, (int)dim, stream, &launched));
