@@ -185,6 +185,11 @@ GCNB_API int gcnb_relu_bwd_f32(float *d_g, const uint8_t *d_mask, int64_t size, 
 GCNB_API int gcnb_relu_dropout_fwd_f32(float *d_x, uint8_t *d_mask, const uint8_t *d_ext_mask, int64_t size, float p,
                                        int training, const gcnb_rng_t *rng, gcnb_stream_t stream);
 GCNB_API int gcnb_relu_dropout_bwd_f32(float *d_g, const uint8_t *d_mask, int64_t size, float p, gcnb_stream_t stream);
+/* Parser::calculateGraphValues (src/parser.cpp:164-181) on the device: d_out[e] = 1. / sqrtf(deg(src) * deg(dst)) with
+ * the reference's arithmetic (unsigned product -> float -> sqrtf -> double divide -> fp32), bit-identical to the host
+ * loop.  Square graphs only (degrees of both endpoints come from d_indptr). */
+GCNB_API int gcnb_graph_values_f32(const uint32_t *d_indptr, const uint32_t *d_indices, int64_t n_rows, float *d_out,
+                                   gcnb_stream_t stream);
 /* GCN::set_truth (src/gcn.cu:204-226). */
 GCNB_API int gcnb_set_truth(int32_t *d_truth, const uint32_t *d_split, const int32_t *d_label, int64_t n,
                             uint32_t current_split, gcnb_stream_t stream);

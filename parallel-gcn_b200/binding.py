@@ -79,6 +79,7 @@ _sig("gcnb_relu_bwd_f32", I32, [P, P, I64, P])
 _sig("gcnb_relu_dropout_fwd_f32", I32, [P, P, P, I64, F32, I32, P, P])
 _sig("gcnb_relu_dropout_bwd_f32", I32, [P, P, I64, F32, P])
 _sig("gcnb_set_truth", I32, [P, P, P, I64, U32, P])
+_sig("gcnb_graph_values_f32", I32, [P, P, I64, P, P])
 _sig("gcnb_ce_workspace", I64, [I64])
 _sig("gcnb_softmax_ce_f32", I32, [P, P, P, I64, I32, U32, I32, P, P, P])
 _sig("gcnb_adam_step_f32", I32, [P, F32, F32, F32, F32, F32, P])

@@ -283,6 +283,287 @@ dense_feat_tn_kernel(const float *__restrict__ X, const uint32_t *__restrict__ b
   }
 }
 
+// =====================================================================================================================
+// Tensor-core variants for P = 16 (hidden 16, the Part-1 model): mma.sync m16n8k8 TF32 with the 3xTF32 split
+// (x = hi + lo, hi = tf32(x), lo = tf32(x - hi);  x*w ~= lo*w_hi + hi*w_lo + hi*w_hi, fp32 accumulation), which keeps
+// fp32-level accuracy (relative error of a product ~2^-21 before accumulation).  Why: the FMA kernels above are
+// issue-bound -- 16 FFMA per element of X plus mask and address work, ~0.9-1.3 warp instructions per element at 2 warps
+// per scheduler (ncu: 200-375 us for 561 MB, 0.23-0.44 of the HBM roofline); one mma replaces 32 FFMA warp
+// instructions, so the instruction stream shrinks ~3x and the kernels approach the copy rate of X.
+// X streams through shared memory in half-tiles of 16 rows (one bulk copy each, kStages deep); a mask tile (32 rows)
+// is fetched with each of its two half-tiles.
+constexpr int HR = 16;       // rows per half-tile = m (forward) / 2 k-steps (weight gradient)
+constexpr int kStages = 3;
+
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return u;
+}
+__device__ __forceinline__ void split_tf32(float x, uint32_t &hi, uint32_t &lo) {
+  hi = to_tf32(x);
+  lo = to_tf32(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// keep-test of elements idx and idx + 4 of a mask tile (both inside one 64-bit window)
+__device__ __forceinline__ uint32_t mask_window(const uint32_t *sbits, int idx) {
+  const int w = idx >> 5;
+  return __funnelshift_r(sbits[w], sbits[w + 1], idx & 31);  // bit 0 = element idx, bit 4 = element idx + 4
+}
+
+// forward, P = 16: out[N x 16] = (X .* mask*scale) * W.  8 warps split K (F padded to a multiple of 8) of one 16-row
+// half-tile; the 8 partial 16x16 results are added in warp order through shared memory (double-buffered: one
+// __syncthreads per half-tile).  W is split once into hi / lo TF32 halves, stored with an XOR swizzle so that the
+// B-fragment loads (4 k x 8 n per instruction) are bank-conflict-free.
+template <bool MASK>
+__global__ void __launch_bounds__(kT, 1)
+dense_feat_fwd_mma_kernel(const float *__restrict__ X, const uint32_t *__restrict__ bits, float scale,
+                          const float *__restrict__ W, float *__restrict__ out, int64_t N, int F) {
+  constexpr int P = 16;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int KP = (F + 7) & ~7;
+  const int wpt = (int)mask_words_per_tile(F);
+  const size_t tile_floats = ((size_t)HR * F + 3) & ~(size_t)3;
+  float *tiles = reinterpret_cast<float *>(smem_raw);
+  uint32_t *Whi = reinterpret_cast<uint32_t *>(tiles + kStages * tile_floats);
+  uint32_t *Wlo = Whi + (size_t)KP * P;
+  uint32_t *mbits = Wlo + (size_t)KP * P;                 // kStages x (wpt + 4): one spare word for the 64-bit window
+  float *red = reinterpret_cast<float *>(mbits + (size_t)kStages * (wpt + 4));  // 2 x 8 warps x 256
+  uint64_t *bars = reinterpret_cast<uint64_t *>(red + 2 * 8 * 256);
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const int64_t nht = (N + HR - 1) / HR;
+  const int64_t first = blockIdx.x, stride = gridDim.x;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; s++) mbar_init(&bars[s], MASK ? 2 : 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto issue = [&](int s, int64_t ht) {
+    issue_tile(tiles + s * tile_floats, X, ht * HR, (int)min((int64_t)HR, N - ht * HR), F, &bars[s]);
+    if (MASK) {
+      mbar_expect_tx(&bars[s], (uint32_t)wpt * 4);
+      bulk_g2s(mbits + (size_t)s * (wpt + 4), bits + (ht >> 1) * wpt, (uint32_t)wpt * 4, &bars[s]);
+    }
+  };
+  if (threadIdx.x == 0)
+    for (int s = 0; s < kStages; s++) {
+      const int64_t ht = first + s * stride;
+      if (ht < nht) issue(s, ht);
+    }
+  for (int i = threadIdx.x; i < KP * P; i += kT) {
+    const int k = i / P, n = i % P;
+    const float w = k < F ? __ldg(W + (size_t)k * P + n) : 0.f;
+    uint32_t hi, lo;
+    split_tf32(w, hi, lo);
+    const int at = k * P + (n ^ (((k >> 1) & 1) << 3));
+    Whi[at] = hi;
+    Wlo[at] = lo;
+  }
+  if (MASK && threadIdx.x < kStages * 4) mbits[(size_t)(threadIdx.x / 4) * (wpt + 4) + wpt + (threadIdx.x & 3)] = 0;
+  __syncthreads();
+  const int nks = KP / 8, ks_per = (nks + 7) / 8;
+  const int ks0 = wib * ks_per, ks1 = min(nks, ks0 + ks_per);
+  const int swz = ((t >> 1) & 1) << 3;  // (k >> 1) & 1 of k = k0 + t and k0 + t + 4 (k0 a multiple of 8)
+  int it = 0;
+  for (int64_t ht = first; ht < nht; ht += stride, it++) {
+    const int s = it % kStages;
+    const float *tile = tiles + s * tile_floats;
+    const uint32_t *sb = mbits + (size_t)s * (wpt + 4);
+    mbar_wait(&bars[s], (uint32_t)((it / kStages) & 1));
+    const int nrows = (int)min((int64_t)HR, N - ht * HR);
+    const bool r0ok = g < nrows, r1ok = g + 8 < nrows;
+    const int mrow = (int)(ht & 1) * HR;  // position of this half-tile inside its 32-row mask tile
+    float c[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    for (int ks = ks0; ks < ks1; ks++) {
+      const int ka = ks * 8 + t, kb = ka + 4;
+      float x[4];
+      x[0] = (r0ok && ka < F) ? tile[(size_t)g * F + ka] : 0.f;
+      x[1] = (r1ok && ka < F) ? tile[(size_t)(g + 8) * F + ka] : 0.f;
+      x[2] = (r0ok && kb < F) ? tile[(size_t)g * F + kb] : 0.f;
+      x[3] = (r1ok && kb < F) ? tile[(size_t)(g + 8) * F + kb] : 0.f;
+      if (MASK) {
+        const uint32_t m0 = mask_window(sb, (mrow + g) * F + ka), m1 = mask_window(sb, (mrow + g + 8) * F + ka);
+        x[0] = (m0 & 1u) ? x[0] * scale : 0.f;
+        x[1] = (m1 & 1u) ? x[1] * scale : 0.f;
+        x[2] = (m0 & 16u) ? x[2] * scale : 0.f;
+        x[3] = (m1 & 16u) ? x[3] * scale : 0.f;
+      }
+      uint32_t ah[4], al[4];
+#pragma unroll
+      for (int q = 0; q < 4; q++) split_tf32(x[q], ah[q], al[q]);
+#pragma unroll
+      for (int j = 0; j < 2; j++) {
+        const int n = (j * 8 + g) ^ swz;
+        const uint32_t bh0 = Whi[ka * P + n], bh1 = Whi[kb * P + n], bl0 = Wlo[ka * P + n], bl1 = Wlo[kb * P + n];
+        mma_tf32(c[j], al, bh0, bh1);
+        mma_tf32(c[j], ah, bl0, bl1);
+        mma_tf32(c[j], ah, bh0, bh1);
+      }
+    }
+    float *my = red + ((size_t)(it & 1) * 8 + wib) * 256;
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+      *reinterpret_cast<float2 *>(my + g * P + j * 8 + 2 * t) = make_float2(c[j][0], c[j][1]);
+      *reinterpret_cast<float2 *>(my + (g + 8) * P + j * 8 + 2 * t) = make_float2(c[j][2], c[j][3]);
+    }
+    __syncthreads();  // partials visible; every warp is done with this stage's tile
+    if (threadIdx.x == 0) {
+      const int64_t hn = ht + (int64_t)kStages * stride;
+      if (hn < nht) issue(s, hn);
+    }
+    {
+      const float *r = red + (size_t)(it & 1) * 8 * 256 + threadIdx.x;
+      float sum = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; w++) sum += r[w * 256];  // ascending k ranges: fixed order
+      const int row = threadIdx.x / P;
+      if (row < nrows) out[(ht * HR + row) * P + (threadIdx.x % P)] = sum;
+    }
+  }
+}
+
+// weight gradient, P = 16: dW[F x 16] = (X .* mask*scale)^T * dH.  m = features (warp w owns the 16-feature tiles
+// w, w + 8, ... in registers for the whole kernel), k = rows (2 k-steps per half-tile), n = 16 columns.
+template <bool MASK, int MT>
+__global__ void __launch_bounds__(kT, 1)
+dense_feat_tn_mma_kernel(const float *__restrict__ X, const uint32_t *__restrict__ bits, float scale,
+                         const float *__restrict__ dH, float *__restrict__ ws, int64_t N, int F) {
+  constexpr int P = 16;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int wpt = (int)mask_words_per_tile(F);
+  const size_t tile_floats = ((size_t)HR * F + 3) & ~(size_t)3;
+  float *tiles = reinterpret_cast<float *>(smem_raw);
+  float *dhs = tiles + kStages * tile_floats;              // kStages x 16 x 16
+  uint32_t *mbits = reinterpret_cast<uint32_t *>(dhs + kStages * HR * P);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(mbits + (size_t)kStages * (wpt + 4));
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const int64_t nht = (N + HR - 1) / HR;
+  const int64_t first = blockIdx.x, stride = gridDim.x;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; s++) mbar_init(&bars[s], MASK ? 3 : 2);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto issue = [&](int s, int64_t ht) {
+    const int nr = (int)min((int64_t)HR, N - ht * HR);
+    issue_tile(tiles + s * tile_floats, X, ht * HR, nr, F, &bars[s]);
+    issue_tile(dhs + s * HR * P, dH, ht * HR, nr, P, &bars[s]);
+    if (MASK) {
+      mbar_expect_tx(&bars[s], (uint32_t)wpt * 4);
+      bulk_g2s(mbits + (size_t)s * (wpt + 4), bits + (ht >> 1) * wpt, (uint32_t)wpt * 4, &bars[s]);
+    }
+  };
+  if (threadIdx.x == 0)
+    for (int s = 0; s < kStages; s++) {
+      const int64_t ht = first + s * stride;
+      if (ht < nht) issue(s, ht);
+    }
+  if (MASK && threadIdx.x < kStages * 4) mbits[(size_t)(threadIdx.x / 4) * (wpt + 4) + wpt + (threadIdx.x & 3)] = 0;
+  __syncthreads();
+  const int n_mt = (F + 15) / 16;
+  float c[MT][2][4];
+#pragma unroll
+  for (int m = 0; m < MT; m++)
+#pragma unroll
+    for (int j = 0; j < 2; j++)
+#pragma unroll
+      for (int q = 0; q < 4; q++) c[m][j][q] = 0.f;
+  int it = 0;
+  for (int64_t ht = first; ht < nht; ht += stride, it++) {
+    const int s = it % kStages;
+    const float *tile = tiles + s * tile_floats;
+    const float *dh = dhs + s * HR * P;
+    const uint32_t *sb = mbits + (size_t)s * (wpt + 4);
+    mbar_wait(&bars[s], (uint32_t)((it / kStages) & 1));
+    const int nrows = (int)min((int64_t)HR, N - ht * HR);
+    const int mrow = (int)(ht & 1) * HR;
+#pragma unroll
+    for (int ks = 0; ks < 2; ks++) {
+      const int ra = ks * 8 + t, rb = ra + 4;  // rows (k) of this lane's fragment elements
+      const bool raok = ra < nrows, rbok = rb < nrows;
+      // B fragments: dH rows ra / rb, columns j*8 + g
+      uint32_t bh[2][2], bl[2][2];
+#pragma unroll
+      for (int j = 0; j < 2; j++) {
+        split_tf32(raok ? dh[ra * P + j * 8 + g] : 0.f, bh[j][0], bl[j][0]);
+        split_tf32(rbok ? dh[rb * P + j * 8 + g] : 0.f, bh[j][1], bl[j][1]);
+      }
+#pragma unroll
+      for (int m = 0; m < MT; m++) {
+        const int mt = wib + m * 8;
+        if (mt < n_mt) {  // warp-uniform
+          const int fa = mt * 16 + g, fb = fa + 8;  // features (m) of this lane's fragment elements
+          float x[4];
+          x[0] = (raok && fa < F) ? tile[(size_t)ra * F + fa] : 0.f;
+          x[1] = (raok && fb < F) ? tile[(size_t)ra * F + fb] : 0.f;
+          x[2] = (rbok && fa < F) ? tile[(size_t)rb * F + fa] : 0.f;
+          x[3] = (rbok && fb < F) ? tile[(size_t)rb * F + fb] : 0.f;
+          if (MASK) {
+            // elements (row, fa) and (row, fb = fa + 8): bits idx and idx + 8 of the row
+            const int ia = (mrow + ra) * F + fa, ib = (mrow + rb) * F + fa;
+            const uint32_t wa = __funnelshift_r(sb[ia >> 5], sb[(ia >> 5) + 1], ia & 31);
+            const uint32_t wb = __funnelshift_r(sb[ib >> 5], sb[(ib >> 5) + 1], ib & 31);
+            x[0] = (wa & 1u) ? x[0] * scale : 0.f;
+            x[1] = (wa & 256u) ? x[1] * scale : 0.f;
+            x[2] = (wb & 1u) ? x[2] * scale : 0.f;
+            x[3] = (wb & 256u) ? x[3] * scale : 0.f;
+          }
+          uint32_t ah[4], al[4];
+#pragma unroll
+          for (int q = 0; q < 4; q++) split_tf32(x[q], ah[q], al[q]);
+#pragma unroll
+          for (int j = 0; j < 2; j++) {
+            mma_tf32(c[m][j], al, bh[j][0], bh[j][1]);
+            mma_tf32(c[m][j], ah, bl[j][0], bl[j][1]);
+            mma_tf32(c[m][j], ah, bh[j][0], bh[j][1]);
+          }
+        }
+      }
+    }
+    __syncthreads();  // every warp is done with this stage
+    if (threadIdx.x == 0) {
+      const int64_t hn = ht + (int64_t)kStages * stride;
+      if (hn < nht) issue(s, hn);
+    }
+  }
+  float *dst = ws + (size_t)blockIdx.x * F * P;
+#pragma unroll
+  for (int m = 0; m < MT; m++) {
+    const int mt = wib + m * 8;
+    if (mt >= n_mt) continue;
+    const int fa = mt * 16 + g, fb = fa + 8;
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+      if (fa < F) *reinterpret_cast<float2 *>(dst + (size_t)fa * P + j * 8 + 2 * t) = make_float2(c[m][j][0], c[m][j][1]);
+      if (fb < F) *reinterpret_cast<float2 *>(dst + (size_t)fb * P + j * 8 + 2 * t) = make_float2(c[m][j][2], c[m][j][3]);
+    }
+  }
+}
+
+size_t fwd_mma_smem(int f) {
+  const size_t tile_floats = ((size_t)HR * f + 3) & ~(size_t)3;
+  const size_t kp = (size_t)((f + 7) & ~7);
+  return (kStages * tile_floats + 2 * kp * 16 + kStages * (mask_words_per_tile(f) + 4) + 2 * 8 * 256) * 4 + kStages * 8 + 16;
+}
+size_t tn_mma_smem(int f) {
+  const size_t tile_floats = ((size_t)HR * f + 3) & ~(size_t)3;
+  return (kStages * tile_floats + kStages * HR * 16 + kStages * (mask_words_per_tile(f) + 4)) * 4 + kStages * 8 + 16;
+}
+// the tensor-core kernels cover hidden 16 with up to 1024 features (MT <= 8 feature tiles per warp); GCNB_DENSE_MMA=0
+// keeps the FMA kernels (A/B measurements)
+bool use_mma(int f, int p) {
+  static const bool on = [] {
+    const char *e = getenv("GCNB_DENSE_MMA");
+    return !(e && atoi(e) == 0);
+  }();
+  return on && p == 16 && f >= 8 && f <= 1024 && fwd_mma_smem(f) <= 227 * 1024 && tn_mma_smem(f) <= 227 * 1024;
+}
+
 __global__ void cta_partial_reduce_kernel(const float *__restrict__ ws, float *__restrict__ out, int64_t elems, int parts) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < elems; i += (int64_t)gridDim.x * blockDim.x) {
     float s = 0.f;
@@ -331,9 +612,21 @@ int gcnb_dense_feat_fwd_f32(const float *d_X, const uint32_t *d_bits, float p_dr
   if (!gcnb_dense_feat_supported(f, p) || ((uintptr_t)d_X % 16) != 0) return GCNB_E_UNSUPPORTED;
   if (n == 0) return 0;
   const float scale = (float)(1.0 / (1.0 - p_drop));
-  const size_t smem = fwd_smem(f, p);
   const int blocks = persistent_ctas(n);
   cudaStream_t st = as_stream(s);
+  if (use_mma(f, p)) {
+    const size_t sm = fwd_mma_smem(f);
+    if (d_bits) {
+      GCNB_CHECK(cudaFuncSetAttribute(dense_feat_fwd_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      dense_feat_fwd_mma_kernel<true><<<blocks, kT, sm, st>>>(d_X, d_bits, scale, d_W, d_out, n, f);
+    } else {
+      GCNB_CHECK(cudaFuncSetAttribute(dense_feat_fwd_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      dense_feat_fwd_mma_kernel<false><<<blocks, kT, sm, st>>>(d_X, d_bits, scale, d_W, d_out, n, f);
+    }
+    GCNB_LAUNCH_CHECK();
+    return 0;
+  }
+  const size_t smem = fwd_smem(f, p);
 #define FWD(PP)                                                                                                   \
   do {                                                                                                            \
     GCNB_CHECK(cudaFuncSetAttribute(dense_feat_fwd_kernel<PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
@@ -364,6 +657,33 @@ int gcnb_dense_feat_tn_f32(const float *d_X, const uint32_t *d_bits, float p_dro
   const int ctas = persistent_ctas(n);
   if (!d_ws || ws_bytes < (int64_t)ctas * f * p * 4 || ((uintptr_t)d_ws % 16) != 0) return GCNB_E_BADARG;
   const float scale = (float)(1.0 / (1.0 - p_drop));
+  if (use_mma(f, p)) {
+    const size_t sm = tn_mma_smem(f);
+    const int mt = ((f + 15) / 16 + 7) / 8;  // 16-feature tiles per warp
+#define TNM(MASKED, MTT)                                                                                                    \
+  do {                                                                                                                      \
+    GCNB_CHECK(cudaFuncSetAttribute(dense_feat_tn_mma_kernel<MASKED, MTT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
+    dense_feat_tn_mma_kernel<MASKED, MTT><<<ctas, kT, sm, st>>>(d_X, d_bits, scale, d_dH, (float *)d_ws, n, f);              \
+  } while (0)
+#define TNMM(MTT)                    \
+  do {                               \
+    if (d_bits) TNM(true, MTT);      \
+    else TNM(false, MTT);            \
+  } while (0)
+    if (mt <= 1) TNMM(1);
+    else if (mt <= 2) TNMM(2);
+    else if (mt <= 3) TNMM(3);
+    else if (mt <= 5) TNMM(5);
+    else TNMM(8);
+#undef TNMM
+#undef TNM
+    GCNB_LAUNCH_CHECK();
+    const int64_t elems = (int64_t)f * p;
+    cta_partial_reduce_kernel<<<(int)std::min<int64_t>((elems + 255) / 256, 1024), 256, 0, st>>>((const float *)d_ws, d_dW,
+                                                                                                   elems, ctas);
+    GCNB_LAUNCH_CHECK();
+    return 0;
+  }
   const int fpt = (f + kT - 1) / kT;
   const size_t smem = tn_smem(f, p);
 #define TN(PP, FF)                                                                                                      \

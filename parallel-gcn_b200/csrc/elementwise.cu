@@ -189,6 +189,27 @@ __global__ void sumsq_kernel(const float *__restrict__ w, int64_t n, float *__re
 
 }  // namespace
 
+namespace {
+// Parser::calculateGraphValues (src/parser.cpp:164-181): value(e) = 1. / sqrtf(deg(src) * deg(dst)) -- unsigned product,
+// converted to float, sqrtf (IEEE round-to-nearest on the device as on the host), the divide in double, rounded to fp32:
+// bit-identical to the host loop.  One warp per row, lanes stride over its entries.
+__global__ void __launch_bounds__(256)
+graph_values_kernel(const uint32_t *__restrict__ indptr, const uint32_t *__restrict__ indices, int64_t n_rows,
+                    float *__restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < n_rows; r += nwarps) {
+    const uint32_t b = __ldg(indptr + r), e = __ldg(indptr + r + 1);
+    const uint32_t ds = e - b;
+    for (uint32_t k = b + lane; k < e; k += 32) {
+      const uint32_t c = __ldg(indices + k);
+      const uint32_t dd = __ldg(indptr + c + 1) - __ldg(indptr + c);
+      out[k] = (float)(1. / (double)__fsqrt_rn((float)(ds * dd)));
+    }
+  }
+}
+}  // namespace
+
 extern "C" {
 
 int gcnb_glorot_f32(float *d_w, int64_t size, uint32_t rows, uint32_t cols, const gcnb_rng_t *rng, gcnb_stream_t s) {
@@ -272,6 +293,17 @@ int gcnb_set_truth(int32_t *d_truth, const uint32_t *d_split, const int32_t *d_l
   if (!d_truth || !d_split || !d_label || n < 0) return GCNB_E_BADARG;
   if (n == 0) return 0;
   set_truth_kernel<<<grid_for(n), kT, 0, as_stream(s)>>>(d_truth, d_split, d_label, n, cur);
+  GCNB_LAUNCH_CHECK();
+  return 0;
+}
+
+int gcnb_graph_values_f32(const uint32_t *d_indptr, const uint32_t *d_indices, int64_t n_rows, float *d_out,
+                          gcnb_stream_t s) {
+  if (!d_indptr || !d_indices || !d_out || n_rows < 0) return GCNB_E_BADARG;
+  if (n_rows == 0) return 0;
+  const int64_t warps = n_rows;
+  const int blocks = (int)std::min<int64_t>((warps * 32 + kT - 1) / kT, (int64_t)std::max(1, device_info().sm_count) * 32);
+  graph_values_kernel<<<blocks, kT, 0, as_stream(s)>>>(d_indptr, d_indices, n_rows, d_out);
   GCNB_LAUNCH_CHECK();
   return 0;
 }

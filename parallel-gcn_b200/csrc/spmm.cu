@@ -394,6 +394,7 @@ int gcnb_spmm_plan_create(const uint32_t *d_indptr, const uint32_t *d_indices, i
   p->n_seg = (int64_t)segs.size();
   // short rows: several segments per atomic ticket (see drain_queue_batched); long rows: one, with look-ahead
   p->batch = (int)std::min<int64_t>(8, std::max<int64_t>(1, 384 / std::max<int64_t>(1, p->nnz / std::max<int64_t>(1, p->n_seg))));
+  if (const char *e = getenv("GCNB_SPMM_BATCH")) p->batch = std::max(1, std::min(32, atoi(e)));  // tuning probe
   p->n_split_rows = (int64_t)split_row.size();
   p->n_slots = slots;
 

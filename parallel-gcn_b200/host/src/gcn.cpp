@@ -3,9 +3,12 @@
 // then eval(3)); the private epoch pipeline is the B200 redesign described in gcn.cuh.
 #include "../include/gcn.cuh"
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <memory>
+#include <thread>
 #include <tuple>
 #include "../../../include/gcnb.h"
 
@@ -29,6 +32,16 @@ void GCNParams::print_info() const {
   std::cout << std::endl;
 }
 
+// GCNB_SETUP_VERBOSE=1: wall-clock laps of the constructor phases on stderr (the e2e figure of bench.py is mostly setup)
+static void setup_lap(const char *what) {
+  static const bool on = getenv("GCNB_SETUP_VERBOSE") != nullptr;
+  static auto last = std::chrono::steady_clock::now();
+  if (!on) return;
+  const auto now = std::chrono::steady_clock::now();
+  if (what) fprintf(stderr, "[setup] %-34s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(now - last).count());
+  last = now;
+}
+
 static GCNDataView view_of(const GCNData &d) {
   GCNDataView v{};
   v.graph_indptr = d.graph.indptr.data();
@@ -50,27 +63,26 @@ DevGCNData::DevGCNData(const GCNData &gcn_data) : DevGCNData(view_of(gcn_data)) 
 DevGCNData::DevGCNData(const GCNDataView &v)
     : dev_graph_index(v.graph_indptr, v.num_nodes + 1, v.graph_indices, v.graph_nnz),
       dev_feature_index(v.feat_indptr, v.num_nodes + 1, v.feat_indices, v.feat_nnz) {
+  setup_lap("upload graph + feature index");
   label_size = static_cast<natural>(v.num_nodes);
   dev_feature_value = dev_shared_ptr<real>(v.feat_nnz);
   dev_graph_value = dev_shared_ptr<real>(v.graph_nnz);
   dev_split = dev_shared_ptr<natural>(label_size);
   dev_label = dev_shared_ptr<integer>(label_size);
   dev_feature_value.copy_to_device(v.feat_value);
+  setup_lap("upload feature values");
   if (v.graph_value) {
     dev_graph_value.copy_to_device(v.graph_value);
   } else {
-    // callers that fill the data by hand may skip Parser::calculateGraphValues (src/parser.cpp:164-181)
-    std::vector<real> gv(v.graph_nnz);
-    for (size_t src = 0; src < v.num_nodes; src++)
-      for (natural e = v.graph_indptr[src]; e < v.graph_indptr[src + 1]; e++) {
-        const natural dst = v.graph_indices[e];
-        gv[e] = 1. / sqrtf((v.graph_indptr[src + 1] - v.graph_indptr[src]) *
-                           (v.graph_indptr[dst + 1] - v.graph_indptr[dst]));
-      }
-    dev_graph_value.copy_to_device(gv.data());
+    // callers that fill the data by hand may skip Parser::calculateGraphValues (src/parser.cpp:164-181): computed on
+    // the device from the uploaded CSR, bit-identical to the host loop (csrc/elementwise.cu)
+    GCNB_CALL(gcnb_graph_values_f32(dev_graph_index.dev_indptr.get(), dev_graph_index.dev_indices.get(),
+                                    (int64_t)v.num_nodes, dev_graph_value.get(), nullptr));
+    CHECK_CUDA_ERROR(cudaDeviceSynchronize());
   }
   dev_split.copy_to_device(v.split);
   dev_label.copy_to_device(v.label);
+  setup_lap("graph values + labels");
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -224,6 +236,7 @@ GCN::GCN(GCNParams const *params_, AdamParams const *adam_params_, const GCNData
 void GCN::init(bool quiet, const natural *h_graph_indptr, const natural *h_graph_indices, const GCNPartition *part) {
   int sm = 0;
   GCNB_CALL(gcnb_device_check(&sm));  // no CPU fallback: a missing/unsupported GPU is fatal here
+  setup_lap(nullptr);
   L = params->n_layers;
   if (L < 1 || params->hidden_dims.size() != L - 1 || params->dropouts.size() != L) {
     std::cerr << "GCN: n_layers / hidden_dims / dropouts are inconsistent" << std::endl;
@@ -278,6 +291,7 @@ void GCN::init(bool quiet, const natural *h_graph_indptr, const natural *h_graph
     GCNB_CALL(gcnb_spmm_plan_create(colptr, rowidx, F, N, 0, st->stream, &st->feat_csc_plan));
   }
 
+  setup_lap("plans (graph, feature csc)");
   {
     int64_t info[8];
     GCNB_CALL(gcnb_spmm_plan_info(st->graph_plan, info));
@@ -357,6 +371,7 @@ void GCN::init(bool quiet, const natural *h_graph_indptr, const natural *h_graph
       st->graph_staged = sinfo[0] != 0;
     }
   }
+  setup_lap("variables + staged GraphSum plan");
   if (st->feat_dense && gcnb_dense_feat_supported((int)F, (int)dims[1])) {
     st->dense_fast = true;
     st->x_bits = dev_shared_ptr<natural>(gcnb_dropout_maskbits_words(N, (int)F));
@@ -381,6 +396,7 @@ void GCN::init(bool quiet, const natural *h_graph_indptr, const natural *h_graph
   CHECK_CUDA_ERROR(cudaDeviceSynchronize());  // glorot ran on the default stream (as in the reference)
   optimizer = Adam(weights, decays, adam_params, smart_objects.backward_streams, smart_objects.start_matmul_forward,
                    smart_objects.forward_training_stream);
+  setup_lap("workspaces, glorot, Adam state");
 }
 
 GCN::~GCN() {

@@ -200,6 +200,29 @@ def test_graphsum_window_staged_own_slab_first(O, gcnb, dev):
     plan.close()
 
 
+@pytest.mark.parametrize("name", ["cora", "citeseer", "synthetic"])
+def test_graph_values_on_device_bit_exact(O, gcnb, dev, datasets, name):
+    """Parser::calculateGraphValues on the device equals the parser's host values bit for bit (sqrtf and the double
+    divide are IEEE on both sides)."""
+    import torch
+    if name == "synthetic":
+        rng = np.random.default_rng(2)
+        n = 5000
+        indptr, indices = random_csr(rng, n, n, 30, heavy_rows=[(3, 4000), (77, 65000 // 8)], empty_rows=[])
+        deg = np.diff(indptr.astype(np.int64)).astype(np.uint32)
+        rows = np.repeat(np.arange(n), deg)
+        prod = (deg[rows] * deg[indices]).astype(f32)
+        want = (1.0 / np.sqrt(prod, dtype=f32).astype(np.float64)).astype(f32)
+    else:
+        ds = datasets[name]
+        indptr, indices, want = ds.g_indptr, ds.g_indices, ds.graph_values()
+    d_ip, d_ix = to_dev(indptr, dev), to_dev(indices, dev)
+    out = torch.empty(len(indices), device=dev)
+    gcnb.check(gcnb.lib.gcnb_graph_values_f32(gcnb.ptr(d_ip), gcnb.ptr(d_ix), len(indptr) - 1, gcnb.ptr(out), gcnb.stream()))
+    torch.cuda.synchronize()
+    assert np.array_equal(to_np(out).view(u32), np.asarray(want, f32).view(u32))
+
+
 def test_graphsum_ref_cpu_flavour(O, gcnb, dev, datasets):
     """the ref-CPU GraphSum recomputes coef per edge (module.cpp:86-90); hoisted values give the same bits."""
     ds = datasets["cora"]
@@ -433,7 +456,7 @@ def test_set_truth(O, gcnb, dev, datasets):
 
 
 @pytest.mark.parametrize("n,F,P,p,off", [(1003, 602, 16, 0.5, 0), (517, 24, 16, 0.5, 6), (300, 130, 32, 0.2, 0), (65, 640, 8, 0.9, 3),
-                                         (9, 5, 16, 0.0, 0)])
+                                         (9, 5, 16, 0.0, 0), (5000, 128, 16, 0.5, 2), (2049, 301, 16, 0.3, 1), (16, 8, 16, 0.5, 0)])
 def test_dense_feature_products_with_bit_mask(O, gcnb, dev, n, F, P, p, off):
     """mask bits == Dropout's keep decisions (bit-exact); masked X*W and (masked X)^T*dH == oracle on the dropped copy."""
     import torch
