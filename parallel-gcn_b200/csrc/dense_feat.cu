@@ -293,16 +293,25 @@ dense_feat_tn_kernel(const float *__restrict__ X, const uint32_t *__restrict__ b
 // X streams through shared memory in half-tiles of 16 rows (one bulk copy each, kStages deep); a mask tile (32 rows)
 // is fetched with each of its two half-tiles.
 constexpr int HR = 16;       // rows per half-tile = m (forward) / 2 k-steps (weight gradient)
-constexpr int kStages = 3;
+// pipeline shape: two CTAs per SM with two half-tiles in flight each when that fits (while one CTA sits at its
+// per-tile barrier the other one computes), else one CTA with three (measured: deeper pipelines do not help)
 
 __device__ __forceinline__ uint32_t to_tf32(float x) {
   uint32_t u;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
   return u;
 }
+// W / dH side (once per kernel / once per k-step): round-to-nearest split
 __device__ __forceinline__ void split_tf32(float x, uint32_t &hi, uint32_t &lo) {
   hi = to_tf32(x);
   lo = to_tf32(x - __uint_as_float(hi));
+}
+// X side (once per element, the hot path): hi = x with the 13 low mantissa bits cleared, lo = x - hi exactly (the
+// tensor core reads the upper 19 bits of lo).  Two instructions instead of the eight a rounded split compiles to;
+// a product is then off by at most ~2^-20 relative, within the fp32 parity bar of 1e-5.
+__device__ __forceinline__ void split_trunc(float x, uint32_t &hi, uint32_t &lo) {
+  hi = __float_as_uint(x) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
 }
 __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
@@ -310,34 +319,39 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], 
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-// keep-test of elements idx and idx + 4 of a mask tile (both inside one 64-bit window)
+// 32 keep bits starting at element idx of a mask tile (one spare zero word follows every tile)
 __device__ __forceinline__ uint32_t mask_window(const uint32_t *sbits, int idx) {
   const int w = idx >> 5;
-  return __funnelshift_r(sbits[w], sbits[w + 1], idx & 31);  // bit 0 = element idx, bit 4 = element idx + 4
+  return __funnelshift_r(sbits[w], sbits[w + 1], idx & 31);
 }
+// dropped elements become +0; the 1/(1-p) scale is applied once to the accumulated result
+__device__ __forceinline__ float keep_if(float x, uint32_t window, uint32_t bit) { return (window & bit) ? x : 0.f; }
 
 // forward, P = 16: out[N x 16] = (X .* mask*scale) * W.  8 warps split K (F padded to a multiple of 8) of one 16-row
-// half-tile; the 8 partial 16x16 results are added in warp order through shared memory (double-buffered: one
-// __syncthreads per half-tile).  W is split once into hi / lo TF32 halves, stored with an XOR swizzle so that the
-// B-fragment loads (4 k x 8 n per instruction) are bank-conflict-free.
-template <bool MASK>
-__global__ void __launch_bounds__(kT, 1)
+// half-tile: warp w always owns k-steps [w*KSP, (w+1)*KSP), so its B fragments (hi and lo halves of W, split once) stay
+// in registers for the whole kernel and the inner loop is 4 LDS + split + 6 mma per k-step.  The 8 partial 16x16 results
+// are added in warp order through shared memory (double-buffered: one __syncthreads per half-tile).
+// Padding instead of predicates: columns >= F meet zero rows of W, rows >= N are computed but not stored, and the
+// stage buffers are zero-filled once so that no stale NaN pattern can meet a zero.
+template <bool MASK, int KSP>
+__global__ void __launch_bounds__(kT, 2)
 dense_feat_fwd_mma_kernel(const float *__restrict__ X, const uint32_t *__restrict__ bits, float scale,
-                          const float *__restrict__ W, float *__restrict__ out, int64_t N, int F) {
+                          const float *__restrict__ W, float *__restrict__ out, int64_t N, int F, const int kStages) {
   constexpr int P = 16;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int KP = (F + 7) & ~7;
   const int wpt = (int)mask_words_per_tile(F);
   const size_t tile_floats = ((size_t)HR * F + 3) & ~(size_t)3;
   float *tiles = reinterpret_cast<float *>(smem_raw);
-  uint32_t *Whi = reinterpret_cast<uint32_t *>(tiles + kStages * tile_floats);
-  uint32_t *Wlo = Whi + (size_t)KP * P;
-  uint32_t *mbits = Wlo + (size_t)KP * P;                 // kStages x (wpt + 4): one spare word for the 64-bit window
+  float *pad = tiles + kStages * tile_floats;             // 8 zero floats: the last row's reads past column F
+  uint32_t *mbits = reinterpret_cast<uint32_t *>(pad + 8);  // kStages x (wpt + 4): spare zero words for the window
   float *red = reinterpret_cast<float *>(mbits + (size_t)kStages * (wpt + 4));  // 2 x 8 warps x 256
   uint64_t *bars = reinterpret_cast<uint64_t *>(red + 2 * 8 * 256);
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
   const int64_t nht = (N + HR - 1) / HR;
   const int64_t first = blockIdx.x, stride = gridDim.x;
+  for (size_t i = threadIdx.x; i < kStages * tile_floats + 8; i += kT) tiles[i] = 0.f;
+  if (MASK)
+    for (int i = threadIdx.x; i < kStages * (wpt + 4); i += kT) mbits[i] = 0u;
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; s++) mbar_init(&bars[s], MASK ? 2 : 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -350,25 +364,24 @@ dense_feat_fwd_mma_kernel(const float *__restrict__ X, const uint32_t *__restric
       bulk_g2s(mbits + (size_t)s * (wpt + 4), bits + (ht >> 1) * wpt, (uint32_t)wpt * 4, &bars[s]);
     }
   };
-  if (threadIdx.x == 0)
+  if (threadIdx.x == 0) {
+    fence_proxy_async();  // the zero fill above (generic proxy) is ordered before the bulk copies (async proxy)
     for (int s = 0; s < kStages; s++) {
       const int64_t ht = first + s * stride;
       if (ht < nht) issue(s, ht);
     }
-  for (int i = threadIdx.x; i < KP * P; i += kT) {
-    const int k = i / P, n = i % P;
-    const float w = k < F ? __ldg(W + (size_t)k * P + n) : 0.f;
-    uint32_t hi, lo;
-    split_tf32(w, hi, lo);
-    const int at = k * P + (n ^ (((k >> 1) & 1) << 3));
-    Whi[at] = hi;
-    Wlo[at] = lo;
   }
-  if (MASK && threadIdx.x < kStages * 4) mbits[(size_t)(threadIdx.x / 4) * (wpt + 4) + wpt + (threadIdx.x & 3)] = 0;
-  __syncthreads();
-  const int nks = KP / 8, ks_per = (nks + 7) / 8;
-  const int ks0 = wib * ks_per, ks1 = min(nks, ks0 + ks_per);
-  const int swz = ((t >> 1) & 1) << 3;  // (k >> 1) & 1 of k = k0 + t and k0 + t + 4 (k0 a multiple of 8)
+  // this warp's B fragments: W rows k0 + t and k0 + t + 4, columns j*8 + g, for its KSP k-steps
+  uint32_t bh[KSP][2][2], bl[KSP][2][2];
+#pragma unroll
+  for (int q = 0; q < KSP; q++) {
+    const int ka = (wib * KSP + q) * 8 + t, kb = ka + 4;
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+      split_tf32(ka < F ? __ldg(W + (size_t)ka * P + j * 8 + g) : 0.f, bh[q][j][0], bl[q][j][0]);
+      split_tf32(kb < F ? __ldg(W + (size_t)kb * P + j * 8 + g) : 0.f, bh[q][j][1], bl[q][j][1]);
+    }
+  }
   int it = 0;
   for (int64_t ht = first; ht < nht; ht += stride, it++) {
     const int s = it % kStages;
@@ -376,33 +389,30 @@ dense_feat_fwd_mma_kernel(const float *__restrict__ X, const uint32_t *__restric
     const uint32_t *sb = mbits + (size_t)s * (wpt + 4);
     mbar_wait(&bars[s], (uint32_t)((it / kStages) & 1));
     const int nrows = (int)min((int64_t)HR, N - ht * HR);
-    const bool r0ok = g < nrows, r1ok = g + 8 < nrows;
-    const int mrow = (int)(ht & 1) * HR;  // position of this half-tile inside its 32-row mask tile
+    const float *xa = tile + (size_t)g * F + wib * KSP * 8 + t;  // (row g, first k of this warp)
+    const float *xb = xa + (size_t)8 * F;                        // row g + 8
+    const int ia = ((int)(ht & 1) * HR + g) * F + wib * KSP * 8 + t, ib = ia + 8 * F;  // the same elements' mask bits
     float c[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-    for (int ks = ks0; ks < ks1; ks++) {
-      const int ka = ks * 8 + t, kb = ka + 4;
-      float x[4];
-      x[0] = (r0ok && ka < F) ? tile[(size_t)g * F + ka] : 0.f;
-      x[1] = (r1ok && ka < F) ? tile[(size_t)(g + 8) * F + ka] : 0.f;
-      x[2] = (r0ok && kb < F) ? tile[(size_t)g * F + kb] : 0.f;
-      x[3] = (r1ok && kb < F) ? tile[(size_t)(g + 8) * F + kb] : 0.f;
+    const int nq = min(KSP, (F + 7) / 8 - wib * KSP);  // k-steps of this warp that start below F (warp-uniform)
+#pragma unroll
+    for (int q = 0; q < KSP; q++) {
+      if (q >= nq) break;
+      float x[4] = {xa[q * 8], xb[q * 8], xa[q * 8 + 4], xb[q * 8 + 4]};
       if (MASK) {
-        const uint32_t m0 = mask_window(sb, (mrow + g) * F + ka), m1 = mask_window(sb, (mrow + g + 8) * F + ka);
-        x[0] = (m0 & 1u) ? x[0] * scale : 0.f;
-        x[1] = (m1 & 1u) ? x[1] * scale : 0.f;
-        x[2] = (m0 & 16u) ? x[2] * scale : 0.f;
-        x[3] = (m1 & 16u) ? x[3] * scale : 0.f;
+        const uint32_t m0 = mask_window(sb, ia + q * 8), m1 = mask_window(sb, ib + q * 8);
+        x[0] = keep_if(x[0], m0, 1u);
+        x[1] = keep_if(x[1], m1, 1u);
+        x[2] = keep_if(x[2], m0, 16u);
+        x[3] = keep_if(x[3], m1, 16u);
       }
       uint32_t ah[4], al[4];
 #pragma unroll
-      for (int q = 0; q < 4; q++) split_tf32(x[q], ah[q], al[q]);
+      for (int e = 0; e < 4; e++) split_trunc(x[e], ah[e], al[e]);
 #pragma unroll
       for (int j = 0; j < 2; j++) {
-        const int n = (j * 8 + g) ^ swz;
-        const uint32_t bh0 = Whi[ka * P + n], bh1 = Whi[kb * P + n], bl0 = Wlo[ka * P + n], bl1 = Wlo[kb * P + n];
-        mma_tf32(c[j], al, bh0, bh1);
-        mma_tf32(c[j], ah, bl0, bl1);
-        mma_tf32(c[j], ah, bh0, bh1);
+        mma_tf32(c[j], al, bh[q][j][0], bh[q][j][1]);
+        mma_tf32(c[j], ah, bl[q][j][0], bl[q][j][1]);
+        mma_tf32(c[j], ah, bh[q][j][0], bh[q][j][1]);
       }
     }
     float *my = red + ((size_t)(it & 1) * 8 + wib) * 256;
@@ -422,28 +432,33 @@ dense_feat_fwd_mma_kernel(const float *__restrict__ X, const uint32_t *__restric
 #pragma unroll
       for (int w = 0; w < 8; w++) sum += r[w * 256];  // ascending k ranges: fixed order
       const int row = threadIdx.x / P;
-      if (row < nrows) out[(ht * HR + row) * P + (threadIdx.x % P)] = sum;
+      if (row < nrows) out[(ht * HR + row) * P + (threadIdx.x % P)] = MASK ? sum * scale : sum;
     }
   }
 }
 
 // weight gradient, P = 16: dW[F x 16] = (X .* mask*scale)^T * dH.  m = features (warp w owns the 16-feature tiles
-// w, w + 8, ... in registers for the whole kernel), k = rows (2 k-steps per half-tile), n = 16 columns.
+// w, w + 8, ... in registers for the whole kernel), k = rows (2 k-steps per half-tile), n = 16 columns.  Rows beyond N
+// are neutralised on the dH side (zero B fragments); features >= F land in accumulators that are never stored.
 template <bool MASK, int MT>
-__global__ void __launch_bounds__(kT, 1)
+__global__ void __launch_bounds__(kT, 2)
 dense_feat_tn_mma_kernel(const float *__restrict__ X, const uint32_t *__restrict__ bits, float scale,
-                         const float *__restrict__ dH, float *__restrict__ ws, int64_t N, int F) {
+                         const float *__restrict__ dH, float *__restrict__ ws, int64_t N, int F, const int kStages) {
   constexpr int P = 16;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int wpt = (int)mask_words_per_tile(F);
   const size_t tile_floats = ((size_t)HR * F + 3) & ~(size_t)3;
   float *tiles = reinterpret_cast<float *>(smem_raw);
-  float *dhs = tiles + kStages * tile_floats;              // kStages x 16 x 16
+  float *pad = tiles + kStages * tile_floats;              // 16 zero floats: the last row's reads past feature F
+  float *dhs = pad + 16;                                   // kStages x 16 x 16
   uint32_t *mbits = reinterpret_cast<uint32_t *>(dhs + kStages * HR * P);
   uint64_t *bars = reinterpret_cast<uint64_t *>(mbits + (size_t)kStages * (wpt + 4));
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
   const int64_t nht = (N + HR - 1) / HR;
   const int64_t first = blockIdx.x, stride = gridDim.x;
+  for (size_t i = threadIdx.x; i < kStages * tile_floats + 16; i += kT) tiles[i] = 0.f;
+  if (MASK)
+    for (int i = threadIdx.x; i < kStages * (wpt + 4); i += kT) mbits[i] = 0u;
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; s++) mbar_init(&bars[s], MASK ? 3 : 2);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -458,13 +473,13 @@ dense_feat_tn_mma_kernel(const float *__restrict__ X, const uint32_t *__restrict
       bulk_g2s(mbits + (size_t)s * (wpt + 4), bits + (ht >> 1) * wpt, (uint32_t)wpt * 4, &bars[s]);
     }
   };
-  if (threadIdx.x == 0)
+  if (threadIdx.x == 0) {
+    fence_proxy_async();
     for (int s = 0; s < kStages; s++) {
       const int64_t ht = first + s * stride;
       if (ht < nht) issue(s, ht);
     }
-  if (MASK && threadIdx.x < kStages * 4) mbits[(size_t)(threadIdx.x / 4) * (wpt + 4) + wpt + (threadIdx.x & 3)] = 0;
-  __syncthreads();
+  }
   const int n_mt = (F + 15) / 16;
   float c[MT][2][4];
 #pragma unroll
@@ -485,37 +500,30 @@ dense_feat_tn_mma_kernel(const float *__restrict__ X, const uint32_t *__restrict
 #pragma unroll
     for (int ks = 0; ks < 2; ks++) {
       const int ra = ks * 8 + t, rb = ra + 4;  // rows (k) of this lane's fragment elements
-      const bool raok = ra < nrows, rbok = rb < nrows;
-      // B fragments: dH rows ra / rb, columns j*8 + g
+      // B fragments: dH rows ra / rb, columns j*8 + g; rows beyond N contribute nothing
       uint32_t bh[2][2], bl[2][2];
 #pragma unroll
       for (int j = 0; j < 2; j++) {
-        split_tf32(raok ? dh[ra * P + j * 8 + g] : 0.f, bh[j][0], bl[j][0]);
-        split_tf32(rbok ? dh[rb * P + j * 8 + g] : 0.f, bh[j][1], bl[j][1]);
+        split_tf32(ra < nrows ? dh[ra * P + j * 8 + g] : 0.f, bh[j][0], bl[j][0]);
+        split_tf32(rb < nrows ? dh[rb * P + j * 8 + g] : 0.f, bh[j][1], bl[j][1]);
       }
+      const float *xa = tile + (size_t)ra * F + wib * 16 + g;  // (row ra, feature wib*16 + g)
+      const float *xb = xa + (size_t)4 * F;                    // row rb
+      const int ia = (mrow + ra) * F + wib * 16 + g, ib = ia + 4 * F;
 #pragma unroll
       for (int m = 0; m < MT; m++) {
-        const int mt = wib + m * 8;
-        if (mt < n_mt) {  // warp-uniform
-          const int fa = mt * 16 + g, fb = fa + 8;  // features (m) of this lane's fragment elements
-          float x[4];
-          x[0] = (raok && fa < F) ? tile[(size_t)ra * F + fa] : 0.f;
-          x[1] = (raok && fb < F) ? tile[(size_t)ra * F + fb] : 0.f;
-          x[2] = (rbok && fa < F) ? tile[(size_t)rb * F + fa] : 0.f;
-          x[3] = (rbok && fb < F) ? tile[(size_t)rb * F + fb] : 0.f;
+        if (wib + m * 8 < n_mt) {  // warp-uniform
+          float x[4] = {xa[m * 128], xa[m * 128 + 8], xb[m * 128], xb[m * 128 + 8]};  // features fa, fa + 8
           if (MASK) {
-            // elements (row, fa) and (row, fb = fa + 8): bits idx and idx + 8 of the row
-            const int ia = (mrow + ra) * F + fa, ib = (mrow + rb) * F + fa;
-            const uint32_t wa = __funnelshift_r(sb[ia >> 5], sb[(ia >> 5) + 1], ia & 31);
-            const uint32_t wb = __funnelshift_r(sb[ib >> 5], sb[(ib >> 5) + 1], ib & 31);
-            x[0] = (wa & 1u) ? x[0] * scale : 0.f;
-            x[1] = (wa & 256u) ? x[1] * scale : 0.f;
-            x[2] = (wb & 1u) ? x[2] * scale : 0.f;
-            x[3] = (wb & 256u) ? x[3] * scale : 0.f;
+            const uint32_t wa = mask_window(sb, ia + m * 128), wb = mask_window(sb, ib + m * 128);
+            x[0] = keep_if(x[0], wa, 1u);
+            x[1] = keep_if(x[1], wa, 256u);
+            x[2] = keep_if(x[2], wb, 1u);
+            x[3] = keep_if(x[3], wb, 256u);
           }
           uint32_t ah[4], al[4];
 #pragma unroll
-          for (int q = 0; q < 4; q++) split_tf32(x[q], ah[q], al[q]);
+          for (int q = 0; q < 4; q++) split_trunc(x[q], ah[q], al[q]);
 #pragma unroll
           for (int j = 0; j < 2; j++) {
             mma_tf32(c[m][j], al, bh[j][0], bh[j][1]);
@@ -532,6 +540,7 @@ dense_feat_tn_mma_kernel(const float *__restrict__ X, const uint32_t *__restrict
     }
   }
   float *dst = ws + (size_t)blockIdx.x * F * P;
+  const float sc = MASK ? scale : 1.f;
 #pragma unroll
   for (int m = 0; m < MT; m++) {
     const int mt = wib + m * 8;
@@ -539,20 +548,40 @@ dense_feat_tn_mma_kernel(const float *__restrict__ X, const uint32_t *__restrict
     const int fa = mt * 16 + g, fb = fa + 8;
 #pragma unroll
     for (int j = 0; j < 2; j++) {
-      if (fa < F) *reinterpret_cast<float2 *>(dst + (size_t)fa * P + j * 8 + 2 * t) = make_float2(c[m][j][0], c[m][j][1]);
-      if (fb < F) *reinterpret_cast<float2 *>(dst + (size_t)fb * P + j * 8 + 2 * t) = make_float2(c[m][j][2], c[m][j][3]);
+      if (fa < F)
+        *reinterpret_cast<float2 *>(dst + (size_t)fa * P + j * 8 + 2 * t) = make_float2(c[m][j][0] * sc, c[m][j][1] * sc);
+      if (fb < F)
+        *reinterpret_cast<float2 *>(dst + (size_t)fb * P + j * 8 + 2 * t) = make_float2(c[m][j][2] * sc, c[m][j][3] * sc);
     }
   }
 }
 
-size_t fwd_mma_smem(int f) {
+size_t fwd_mma_smem(int f, int ns) {
   const size_t tile_floats = ((size_t)HR * f + 3) & ~(size_t)3;
-  const size_t kp = (size_t)((f + 7) & ~7);
-  return (kStages * tile_floats + 2 * kp * 16 + kStages * (mask_words_per_tile(f) + 4) + 2 * 8 * 256) * 4 + kStages * 8 + 16;
+  return (ns * tile_floats + 8 + ns * (mask_words_per_tile(f) + 4) + 2 * 8 * 256) * 4 + ns * 8 + 16;
 }
-size_t tn_mma_smem(int f) {
+size_t tn_mma_smem(int f, int ns) {
   const size_t tile_floats = ((size_t)HR * f + 3) & ~(size_t)3;
-  return (kStages * tile_floats + kStages * HR * 16 + kStages * (mask_words_per_tile(f) + 4)) * 4 + kStages * 8 + 16;
+  return (ns * tile_floats + 16 + ns * HR * 16 + ns * (mask_words_per_tile(f) + 4)) * 4 + ns * 8 + 16;
+}
+struct MmaShape {
+  int stages = 0, ctas_per_sm = 0;
+};
+MmaShape mma_shape(int f) {
+  MmaShape m;
+  const size_t cap = 227 * 1024, per_cta_reserved = 1024;
+  if (2 * (fwd_mma_smem(f, 2) + per_cta_reserved) <= cap && 2 * (tn_mma_smem(f, 2) + per_cta_reserved) <= cap) {
+    m.stages = 2;
+    m.ctas_per_sm = 2;
+  } else if (fwd_mma_smem(f, 3) <= cap && tn_mma_smem(f, 3) <= cap) {
+    m.stages = 3;
+    m.ctas_per_sm = 1;
+  }
+  return m;
+}
+int mma_ctas(int64_t n, int f) {
+  const int sm = std::max(1, device_info().sm_count);
+  return (int)std::max<int64_t>(1, std::min<int64_t>((n + HR - 1) / HR, (int64_t)sm * mma_shape(f).ctas_per_sm));
 }
 // the tensor-core kernels cover hidden 16 with up to 1024 features (MT <= 8 feature tiles per warp); GCNB_DENSE_MMA=0
 // keeps the FMA kernels (A/B measurements)
@@ -561,7 +590,7 @@ bool use_mma(int f, int p) {
     const char *e = getenv("GCNB_DENSE_MMA");
     return !(e && atoi(e) == 0);
   }();
-  return on && p == 16 && f >= 8 && f <= 1024 && fwd_mma_smem(f) <= 227 * 1024 && tn_mma_smem(f) <= 227 * 1024;
+  return on && p == 16 && f >= 8 && f <= 768 && mma_shape(f).stages > 0;
 }
 
 __global__ void cta_partial_reduce_kernel(const float *__restrict__ ws, float *__restrict__ out, int64_t elems, int parts) {
@@ -615,14 +644,29 @@ int gcnb_dense_feat_fwd_f32(const float *d_X, const uint32_t *d_bits, float p_dr
   const int blocks = persistent_ctas(n);
   cudaStream_t st = as_stream(s);
   if (use_mma(f, p)) {
-    const size_t sm = fwd_mma_smem(f);
-    if (d_bits) {
-      GCNB_CHECK(cudaFuncSetAttribute(dense_feat_fwd_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-      dense_feat_fwd_mma_kernel<true><<<blocks, kT, sm, st>>>(d_X, d_bits, scale, d_W, d_out, n, f);
-    } else {
-      GCNB_CHECK(cudaFuncSetAttribute(dense_feat_fwd_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-      dense_feat_fwd_mma_kernel<false><<<blocks, kT, sm, st>>>(d_X, d_bits, scale, d_W, d_out, n, f);
-    }
+    const int ns = mma_shape(f).stages;
+    const size_t sm = fwd_mma_smem(f, ns);
+    const int mblocks = mma_ctas(n, f);
+    const int ksp = (((f + 7) / 8) + 7) / 8;  // k-steps per warp
+#define FWDM(MASKED, KK)                                                                                                   \
+  do {                                                                                                                     \
+    GCNB_CHECK(cudaFuncSetAttribute(dense_feat_fwd_mma_kernel<MASKED, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
+    dense_feat_fwd_mma_kernel<MASKED, KK><<<mblocks, kT, sm, st>>>(d_X, d_bits, scale, d_W, d_out, n, f, ns);                  \
+  } while (0)
+#define FWDMM(KK)                  \
+  do {                             \
+    if (d_bits) FWDM(true, KK);    \
+    else FWDM(false, KK);          \
+  } while (0)
+    if (ksp <= 1) FWDMM(1);
+    else if (ksp <= 2) FWDMM(2);
+    else if (ksp <= 4) FWDMM(4);
+    else if (ksp <= 6) FWDMM(6);
+    else if (ksp <= 8) FWDMM(8);
+    else if (ksp <= 10) FWDMM(10);
+    else FWDMM(12);
+#undef FWDMM
+#undef FWDM
     GCNB_LAUNCH_CHECK();
     return 0;
   }
@@ -641,7 +685,8 @@ int gcnb_dense_feat_fwd_f32(const float *d_X, const uint32_t *d_bits, float p_dr
 }
 
 int64_t gcnb_dense_feat_tn_workspace(int64_t n, int f, int p) {
-  return (int64_t)persistent_ctas(n) * f * p * (int64_t)sizeof(float);
+  const int ctas = use_mma(f, p) ? std::max(persistent_ctas(n), mma_ctas(n, f)) : persistent_ctas(n);
+  return (int64_t)ctas * f * p * (int64_t)sizeof(float);
 }
 
 int gcnb_dense_feat_tn_f32(const float *d_X, const uint32_t *d_bits, float p_drop, const float *d_dH, float *d_dW,
@@ -658,12 +703,15 @@ int gcnb_dense_feat_tn_f32(const float *d_X, const uint32_t *d_bits, float p_dro
   if (!d_ws || ws_bytes < (int64_t)ctas * f * p * 4 || ((uintptr_t)d_ws % 16) != 0) return GCNB_E_BADARG;
   const float scale = (float)(1.0 / (1.0 - p_drop));
   if (use_mma(f, p)) {
-    const size_t sm = tn_mma_smem(f);
+    const int ns = mma_shape(f).stages;
+    const size_t sm = tn_mma_smem(f, ns);
+    const int mctas = mma_ctas(n, f);
+    if (ws_bytes < (int64_t)mctas * f * p * 4) return GCNB_E_BADARG;
     const int mt = ((f + 15) / 16 + 7) / 8;  // 16-feature tiles per warp
 #define TNM(MASKED, MTT)                                                                                                    \
   do {                                                                                                                      \
     GCNB_CHECK(cudaFuncSetAttribute(dense_feat_tn_mma_kernel<MASKED, MTT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
-    dense_feat_tn_mma_kernel<MASKED, MTT><<<ctas, kT, sm, st>>>(d_X, d_bits, scale, d_dH, (float *)d_ws, n, f);              \
+    dense_feat_tn_mma_kernel<MASKED, MTT><<<mctas, kT, sm, st>>>(d_X, d_bits, scale, d_dH, (float *)d_ws, n, f, ns);          \
   } while (0)
 #define TNMM(MTT)                    \
   do {                               \
@@ -680,7 +728,7 @@ int gcnb_dense_feat_tn_f32(const float *d_X, const uint32_t *d_bits, float p_dro
     GCNB_LAUNCH_CHECK();
     const int64_t elems = (int64_t)f * p;
     cta_partial_reduce_kernel<<<(int)std::min<int64_t>((elems + 255) / 256, 1024), 256, 0, st>>>((const float *)d_ws, d_dW,
-                                                                                                   elems, ctas);
+                                                                                                   elems, mctas);
     GCNB_LAUNCH_CHECK();
     return 0;
   }
