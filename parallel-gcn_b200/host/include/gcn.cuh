@@ -146,10 +146,9 @@ class GCN {
   // for the next training pass, one per dropout site (0 = input, l = hidden layer l-1); nullptr = draw with Philox
   void set_external_masks(const std::vector<const unsigned char *> &host_masks);
   void set_quiet(bool q);
-  void set_use_cuda_graph(bool on);
   void set_reorder(bool on);  // allow the (A*a)*W association (default on)
   size_t launches_per_epoch() const;
-  bool graph_staged() const;  // GraphSum at width 16 runs the window-staged kernels (csrc/spmm_stage.cu)
+  bool graph_staged() const;  // GraphSum at widths 16 / >= 64 runs the window-staged kernels (csrc/spmm_stage.cu)
   size_t launches_total() const;
   void set_time_graphsum(bool on);                        // event pair around every GraphSum launch
   void graphsum_timing(double *ms_total, size_t *calls) const;

@@ -140,7 +140,7 @@ struct GCNEngineState {
   pinned_host_ptr<real> host_result;   // same 8 floats
   natural cur_num_samples = 0;
   std::vector<dev_shared_ptr<unsigned char>> ext_masks;  // injected keep-masks per dropout site (may be null)
-  bool quiet = false, use_graph = false, allow_reorder = true;
+  bool quiet = false, allow_reorder = true;
   size_t launches = 0, launches_last_epoch = 0;  // CUDA kernels launched (memsets / copies not counted)
   natural epochs_run = 0;
   int graph_spmm_kernels = 1, feat_spmm_kernels = 1, feat_csc_kernels = 1;  // 1 + combine kernel when rows are split
@@ -404,7 +404,6 @@ GCN::~GCN() {
 }
 
 void GCN::set_quiet(bool q) { st->quiet = q; }
-void GCN::set_use_cuda_graph(bool on) { st->use_graph = on; }
 void GCN::set_reorder(bool on) {
   st->allow_reorder = on;
   const size_t N = st->dist ? st->block : params->num_nodes;
