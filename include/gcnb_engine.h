@@ -131,6 +131,19 @@ GCNB_API int gcnb_synth_graph_values(const uint32_t *indptr, const uint32_t *ind
 GCNB_API int gcnb_synth_dense_features_uniform(int64_t n, int f, uint64_t seed, uint64_t elem_offset, uint32_t *indptr,
                                                uint32_t *indices, float *values);
 
+/* ---- locality reordering (host side, multi-threaded, deterministic) ----
+ * Communities by synchronous label propagation (ties broken by a hash, at most max_sweeps sweeps, 0 = 8), nodes
+ * renumbered community by community: new_of_old[i] = new id of node i.  The window-staged GraphSum needs the nodes of a
+ * community next to each other; datasets rarely come that way.  The renumbered dataset (gcnb_permute_csr for the
+ * graph, gcnb_permute_rows for features / labels / split) is an ordinary dataset for everything downstream;
+ * gcnb_unpermute_rows maps per-node outputs (logits) back to the original numbering. */
+GCNB_API int gcnb_reorder_communities(int64_t n, const uint32_t *indptr, const uint32_t *indices, int max_sweeps,
+                                      uint64_t seed, uint32_t *new_of_old, int64_t *n_communities);
+GCNB_API int gcnb_permute_csr(int64_t n, const uint32_t *indptr, const uint32_t *indices, const uint32_t *new_of_old,
+                              uint32_t *out_indptr, uint32_t *out_indices);
+GCNB_API int gcnb_permute_rows(int64_t n, int64_t row_bytes, const uint32_t *new_of_old, const void *in, void *out);
+GCNB_API int gcnb_unpermute_rows(int64_t n, int64_t row_bytes, const uint32_t *new_of_old, const void *in, void *out);
+
 #ifdef __cplusplus
 }
 #endif

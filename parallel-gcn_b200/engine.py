@@ -62,6 +62,10 @@ _sig("gcnb_synth_graph", I32, [I64, I64, I32, C.c_double, C.c_double, I64, C.c_u
 _sig("gcnb_host_free", None, [P])
 _sig("gcnb_synth_dense_features", I32, [I64, I32, C.c_uint64, P, P, P])
 _sig("gcnb_synth_labels", I32, [I64, I32, C.c_double, C.c_double, C.c_uint64, P, P])
+_sig("gcnb_reorder_communities", I32, [I64, P, P, I32, C.c_uint64, P, P])
+_sig("gcnb_permute_csr", I32, [I64, P, P, P, P, P])
+_sig("gcnb_permute_rows", I32, [I64, I64, P, P, P])
+_sig("gcnb_unpermute_rows", I32, [I64, I64, P, P, P])
 _sig("gcnb_synth_sym_rows", I32, [I64, I64, I64, I64, C.c_double, C.c_double, I32, C.c_double, C.c_uint64, P, P, P])
 _sig("gcnb_synth_graph_values", I32, [P, P, I64, I64, P, P])
 _sig("gcnb_synth_dense_features_uniform", I32, [I64, I32, C.c_uint64, C.c_uint64, P, P, P])
@@ -188,6 +192,50 @@ def synth_labels(n, n_classes, frac_train=0.66, frac_val=0.10, seed=19990304):
     label, split = np.empty(n, np.int32), np.empty(n, np.uint32)
     check(lib.gcnb_synth_labels(n, n_classes, frac_train, frac_val, seed, _p(label), _p(split)))
     return label, split
+
+
+def reorder_communities(indptr, indices, max_sweeps=0, seed=1):
+    """new_of_old permutation that makes label-propagation communities contiguous; returns (new_of_old, n_communities)"""
+    n = len(indptr) - 1
+    new_of_old, nc = np.empty(n, np.uint32), I64(0)
+    check(lib.gcnb_reorder_communities(n, _p(indptr), _p(indices), int(max_sweeps), int(seed), _p(new_of_old), C.byref(nc)))
+    return new_of_old, int(nc.value)
+
+
+def permute_rows(a, new_of_old, inverse=False):
+    """rows of `a` moved to their new positions (inverse: back to the original numbering)"""
+    a = np.ascontiguousarray(a)
+    out = np.empty_like(a)
+    row_bytes = a.nbytes // max(1, a.shape[0])
+    fn = lib.gcnb_unpermute_rows if inverse else lib.gcnb_permute_rows
+    check(fn(a.shape[0], row_bytes, _p(new_of_old), _p(a), _p(out)))
+    return out
+
+
+def permute_dataset(ds, new_of_old):
+    """the dataset renumbered by new_of_old (all-columns / fixed-width feature rows or general CSR features)"""
+    n = ds.num_nodes
+    g_indptr, g_indices = np.empty(n + 1, np.uint32), np.empty(len(ds.g_indices), np.uint32)
+    check(lib.gcnb_permute_csr(n, _p(ds.g_indptr), _p(ds.g_indices), _p(new_of_old), _p(g_indptr), _p(g_indices)))
+    flen = np.diff(ds.f_indptr.astype(np.int64))
+    if len(flen) and (flen == flen[0]).all() and flen[0] > 0:   # fixed-width rows: one row permutation
+        w = int(flen[0])
+        f_indices = permute_rows(ds.f_indices.reshape(n, w), new_of_old).reshape(-1)
+        f_value = permute_rows(ds.f_value.reshape(n, w), new_of_old).reshape(-1)
+        f_indptr = ds.f_indptr.copy()
+    else:
+        old_of_new = np.empty(n, np.int64)
+        old_of_new[new_of_old] = np.arange(n)
+        f_indptr = np.zeros(n + 1, np.uint32)
+        f_indptr[1:] = np.cumsum(flen[old_of_new])
+        src = np.concatenate([np.arange(ds.f_indptr[i], ds.f_indptr[i + 1]) for i in old_of_new]) if n else np.empty(0, np.int64)
+        f_indices, f_value = ds.f_indices[src], ds.f_value[src]
+    out = HostDataset(g_indptr=g_indptr, g_indices=g_indices, f_indptr=f_indptr, f_indices=np.ascontiguousarray(f_indices),
+                      f_value=np.ascontiguousarray(f_value), label=permute_rows(ds.label, new_of_old),
+                      split=permute_rows(ds.split, new_of_old), input_dim=ds.input_dim, output_dim=ds.output_dim)
+    if getattr(ds, "split_counts", None) is not None:
+        out.split_counts = ds.split_counts
+    return out
 
 
 COMM_ID_BYTES = 128

@@ -224,3 +224,31 @@ def test_native_partitioned_engine_single_rank_matches_engine(eng, datasets):
     assert got == want
     for a, b in zip(gw, hw):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("name", ["cora", "synthetic"])
+def test_renumbered_dataset_is_the_same_model(eng, datasets, name):
+    """locality reordering (host/src/reorder.cpp): a dataset renumbered by gcnb_reorder_communities is the same learning
+    problem -- with the same weights, evaluation loss / accuracy agree and the logits, mapped back with
+    gcnb_unpermute_rows, are the original ones (fp32 summation order inside a row changes: 1e-5)."""
+    if name == "cora":
+        ds = eng.parse_dataset(ROOT, "cora")
+    else:
+        ds = eng.synth_dataset(30000, 30000 * 25, 32, 6, n_blocks=8, seed=11)
+    perm, n_comm = eng.reorder_communities(ds.g_indptr, ds.g_indices)
+    assert n_comm >= 1 and np.array_equal(np.sort(perm), np.arange(ds.num_nodes, dtype=np.uint32))
+    pds = eng.permute_dataset(ds, perm)
+    g = eng.GCN(ds)
+    w = [g.weight(l) for l in range(2)]
+    ev = [g.eval(s) for s in (1, 2, 3)]
+    logits = g.logits()
+    g.close()
+    h = eng.GCN(pds)
+    for l in range(2):
+        h.set_weight(l, w[l])
+    evp = [h.eval(s) for s in (1, 2, 3)]
+    plogits = h.logits()
+    h.close()
+    for a, b in zip(ev, evp):
+        assert abs(a[0] - b[0]) <= 1e-5 * abs(a[0]) and abs(a[1] - b[1]) <= 1e-6
+    assert_close(eng.permute_rows(plogits, perm, inverse=True), logits, rtol=1e-5, what="un-permuted logits")
