@@ -52,6 +52,10 @@ GCNB_API int gcnb_dataset_dims(const gcnb_dataset *d, int64_t dims[10]);
 /* which: 0 graph_indptr 1 graph_indices 2 feat_indptr 3 feat_indices 4 feat_value 5 label 6 split 7 graph_value */
 GCNB_API int gcnb_dataset_copy(const gcnb_dataset *d, int which, void *dst);
 GCNB_API int gcnb_dataset_free(gcnb_dataset *d);
+/* binary container of a parsed dataset (a 128-byte header + the eight arrays of gcnb_dataset_copy, 64-byte aligned):
+ * written once, loading it back (mmap + copy) is bit-identical to parsing the text files again and takes milliseconds */
+GCNB_API int gcnb_dataset_save(const gcnb_dataset *d, const char *path);
+GCNB_API int gcnb_dataset_load(const char *path, gcnb_dataset **out);
 
 /* Row partition of one rank (multi-GPU).  The rank owns the contiguous global rows
  * [row_offset, row_offset + cfg.num_nodes) of the adjacency, of the features, labels, split and of every activation;

@@ -38,6 +38,8 @@ _sig("gcnb_dataset_parse", I32, [C.c_char_p, C.c_char_p, I32, P])
 _sig("gcnb_dataset_dims", I32, [P, P])
 _sig("gcnb_dataset_copy", I32, [P, I32, P])
 _sig("gcnb_dataset_free", I32, [P])
+_sig("gcnb_dataset_save", I32, [P, C.c_char_p])
+_sig("gcnb_dataset_load", I32, [C.c_char_p, P])
 _sig("gcnb_gcn_create", I32, [P, P, P])
 _sig("gcnb_gcn_create_from_dataset", I32, [P, P, P])
 _sig("gcnb_gcn_create_partitioned", I32, [P, P, P, P])
@@ -92,12 +94,27 @@ class HostDataset:
         return sum(getattr(self, k).nbytes for k in self.FIELDS if getattr(self, k) is not None)
 
 
-def parse_dataset(root, name, no_feature=False):
-    """Parser(params, data, name).parse() run from `root` (expects root/data/<name>.graph|.split|.svmlight)."""
+def parse_dataset(root, name, no_feature=False, save_to=None):
+    """Parser(params, data, name).parse() run from `root` (expects root/data/<name>.graph|.split|.svmlight);
+    save_to: also store the parsed dataset in the binary container (gcnb_dataset_save)"""
     h = P()
     rc = lib.gcnb_dataset_parse(str(root).encode(), name.encode(), int(no_feature), C.byref(h))
     if rc != 0:
         return None
+    if save_to is not None:
+        check(lib.gcnb_dataset_save(h, str(save_to).encode()))
+    return _dataset_from_handle(h)
+
+
+def load_dataset(path):
+    """a dataset stored by gcnb_dataset_save: bit-identical to parsing the text files again"""
+    h = P()
+    if lib.gcnb_dataset_load(str(path).encode(), C.byref(h)) != 0:
+        return None
+    return _dataset_from_handle(h)
+
+
+def _dataset_from_handle(h):
     dims = (I64 * 10)()
     check(lib.gcnb_dataset_dims(h, dims))
     n, gnnz, frows, fnnz, in_dim, out_dim, nsplit, tr, va, te = (int(x) for x in dims)

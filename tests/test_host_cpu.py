@@ -289,3 +289,28 @@ def test_reference_main_compiles_against_product_headers(tmp_path):
                "-Wl,-rpath," + os.path.join(ROOT, "parallel-gcn_b200")]
         r = subprocess.run(cmd, capture_output=True, text=True)
         assert r.returncode == 0, r.stderr[-3000:]
+
+
+def test_binary_container_roundtrip_is_bit_identical(tmp_path):
+    """gcnb_dataset_save / gcnb_dataset_load (SURVEY 8f-1): the stored dataset equals the parsed one byte for byte;
+    truncated or foreign files are rejected."""
+    import importlib
+    import __graft_entry__ as ge
+    ge.load_package()
+    eng = importlib.import_module("parallel_gcn_b200.engine")
+    for name in ("cora", "citeseer"):
+        path = tmp_path / (name + ".gcnb")
+        ds = eng.parse_dataset(ROOT, name, save_to=path)
+        back = eng.load_dataset(path)
+        assert back is not None
+        for k in eng.HostDataset.FIELDS:
+            a, b = getattr(ds, k), getattr(back, k)
+            assert a.dtype == b.dtype and np.array_equal(a.view(np.uint32), b.view(np.uint32)), (name, k)
+        assert (ds.input_dim, ds.output_dim, ds.split_counts) == (back.input_dim, back.output_dim, back.split_counts)
+        raw = path.read_bytes()
+        assert len(raw) % 64 == 0 and raw[:7] == b"GCNBDS1"
+        (tmp_path / "cut.gcnb").write_bytes(raw[: len(raw) // 2])
+        assert eng.load_dataset(tmp_path / "cut.gcnb") is None
+    (tmp_path / "junk.gcnb").write_bytes(b"x" * 4096)
+    assert eng.load_dataset(tmp_path / "junk.gcnb") is None
+    assert eng.load_dataset(tmp_path / "missing.gcnb") is None
