@@ -34,6 +34,7 @@ extern "C" {
 typedef void *gcnb_stream_t; /* cudaStream_t */
 
 GCNB_API const char *gcnb_error_string(int code);
+
 GCNB_API int gcnb_version(void);
 /* device sanity: fails unless the current device is compute capability 10.x; fills SM count. */
 GCNB_API int gcnb_device_check(int *sm_count);
@@ -247,6 +248,12 @@ typedef struct {
 } gcnb_adam_tensors_t;
 GCNB_API int gcnb_adam_step_f32(const gcnb_adam_tensors_t *t, float weight_decay, float beta1, float beta2, float eps,
                                 float step_size, gcnb_stream_t stream);
+/* CUDA-graph replay: `node` is a kernel node of a captured graph that was produced by one of the library's calls whose
+ * arguments change from epoch to epoch -- the dropout family (gcnb_dropout_fwd[_oop]_f32, gcnb_relu_dropout_fwd_f32,
+ * gcnb_dropout_maskbits: the Philox descriptor) and gcnb_adam_step_f32 (step_size).  Rewrites that argument of the node
+ * inside the instantiated graph `exec` (cudaGraphExec_t / cudaGraphNode_t passed as void*), so an epoch captured once
+ * is replayed with the next epoch's randomness.  GCNB_E_UNSUPPORTED if the node is not such a kernel. */
+GCNB_API int gcnb_graph_patch_node(void *exec, void *node, const gcnb_rng_t *rng, const float *step_size);
 /* d_out[0] = sum_i w[i]^2 (ascending fixed tree).  d_ws: gcnb_sumsq_workspace(n) bytes. */
 GCNB_API int64_t gcnb_sumsq_workspace(int64_t n);
 GCNB_API int gcnb_sumsq_f32(const float *d_w, int64_t n, float *d_out, void *d_ws, gcnb_stream_t stream);

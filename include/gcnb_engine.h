@@ -96,6 +96,12 @@ GCNB_API int64_t gcnb_gcn_launches_per_epoch(const gcnb_gcn *g);
 /* 1 if GraphSum at feature width 16 uses the window-staged kernels (graph with column locality), else 0 */
 GCNB_API int gcnb_gcn_graph_staged(const gcnb_gcn *g);
 GCNB_API int64_t gcnb_gcn_launches_total(const gcnb_gcn *g);
+/* CUDA-graph replay of the training epoch and of the evaluation passes (small datasets are launch-bound).  Default: on
+ * when graph + feature entries <= 8 Mi (GCNB_CUDA_GRAPH=0/1 overrides); never used by a partitioned model, with injected
+ * masks, or while GraphSum launches are being timed.  Results are bit-identical to eager launches.
+ * gcnb_gcn_uses_cuda_graph: 1 if the next passes may be replayed. */
+GCNB_API int gcnb_gcn_set_cuda_graph(gcnb_gcn *g, int on);
+GCNB_API int gcnb_gcn_uses_cuda_graph(const gcnb_gcn *g);
 /* measurement hook (bench.py): n_epochs x {train_epoch [+ eval(2)]} bracketed by CUDA events on the engine's stream.
  * out[0] = total ms, out[1] = summed ms of the GraphSum SpMM launches (event pair per launch, if time_graphsum),
  * out[2] = number of GraphSum launches, out[3] = CUDA kernels launched in the region */

@@ -30,6 +30,12 @@ struct DeviceInfo {
 };
 const DeviceInfo &device_info();
 
+// Kernels whose arguments change from epoch to epoch (the Philox descriptor of the dropout kernels, Adam's step size) are
+// registered with the index of that argument, so that a captured epoch (CUDA graph) can be replayed with the node's
+// arguments patched in place (gcnb_graph_patch_node, spmm.cu) instead of being captured again.
+void register_patchable(const void *kernel, int rng_arg, int step_arg);
+bool lookup_patchable(const void *kernel, int *rng_arg, int *step_arg);
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

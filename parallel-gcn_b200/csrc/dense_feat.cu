@@ -21,6 +21,17 @@
 
 using namespace gcnb;
 
+// opt a kernel in to `bytes` of dynamic shared memory, once per (kernel, larger size): steady-state launches make no
+// attribute call (and none inside a CUDA-graph capture)
+#define GCNB_SMEM_OPT_IN(bytes, ...)                                                                                 \
+  do {                                                                                                               \
+    static size_t opted_in = 0;                                                                                      \
+    if ((size_t)(bytes) > opted_in) {                                                                                \
+      GCNB_CHECK(cudaFuncSetAttribute(__VA_ARGS__, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));      \
+      opted_in = (size_t)(bytes);                                                                                    \
+    }                                                                                                                \
+  } while (0)
+
 namespace {
 
 constexpr int kT = 256;
@@ -614,6 +625,13 @@ size_t tn_smem(int f, int p) {
 
 }  // namespace
 
+namespace {
+const int patchables_registered = [] {
+  register_patchable((const void *)dropout_maskbits_kernel, 6, -1);
+  return 0;
+}();
+}  // namespace
+
 extern "C" {
 
 int gcnb_dense_feat_supported(int f, int p) {
@@ -650,7 +668,7 @@ int gcnb_dense_feat_fwd_f32(const float *d_X, const uint32_t *d_bits, float p_dr
     const int ksp = (((f + 7) / 8) + 7) / 8;  // k-steps per warp
 #define FWDM(MASKED, KK)                                                                                                   \
   do {                                                                                                                     \
-    GCNB_CHECK(cudaFuncSetAttribute(dense_feat_fwd_mma_kernel<MASKED, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
+    GCNB_SMEM_OPT_IN(sm, dense_feat_fwd_mma_kernel<MASKED, KK>); \
     dense_feat_fwd_mma_kernel<MASKED, KK><<<mblocks, kT, sm, st>>>(d_X, d_bits, scale, d_W, d_out, n, f, ns);                  \
   } while (0)
 #define FWDMM(KK)                  \
@@ -673,7 +691,7 @@ int gcnb_dense_feat_fwd_f32(const float *d_X, const uint32_t *d_bits, float p_dr
   const size_t smem = fwd_smem(f, p);
 #define FWD(PP)                                                                                                   \
   do {                                                                                                            \
-    GCNB_CHECK(cudaFuncSetAttribute(dense_feat_fwd_kernel<PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    GCNB_SMEM_OPT_IN(smem, dense_feat_fwd_kernel<PP>); \
     dense_feat_fwd_kernel<PP><<<blocks, kT, smem, st>>>(d_X, d_bits, scale, d_W, d_out, n, f);                    \
   } while (0)
   if (p == 8) FWD(8);
@@ -710,7 +728,7 @@ int gcnb_dense_feat_tn_f32(const float *d_X, const uint32_t *d_bits, float p_dro
     const int mt = ((f + 15) / 16 + 7) / 8;  // 16-feature tiles per warp
 #define TNM(MASKED, MTT)                                                                                                    \
   do {                                                                                                                      \
-    GCNB_CHECK(cudaFuncSetAttribute(dense_feat_tn_mma_kernel<MASKED, MTT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
+    GCNB_SMEM_OPT_IN(sm, dense_feat_tn_mma_kernel<MASKED, MTT>); \
     dense_feat_tn_mma_kernel<MASKED, MTT><<<mctas, kT, sm, st>>>(d_X, d_bits, scale, d_dH, (float *)d_ws, n, f, ns);          \
   } while (0)
 #define TNMM(MTT)                    \
@@ -736,7 +754,7 @@ int gcnb_dense_feat_tn_f32(const float *d_X, const uint32_t *d_bits, float p_dro
   const size_t smem = tn_smem(f, p);
 #define TN(PP, FF)                                                                                                      \
   do {                                                                                                                  \
-    GCNB_CHECK(cudaFuncSetAttribute(dense_feat_tn_kernel<PP, FF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    GCNB_SMEM_OPT_IN(smem, dense_feat_tn_kernel<PP, FF>); \
     dense_feat_tn_kernel<PP, FF><<<ctas, kT, smem, st>>>(d_X, d_bits, scale, d_dH, (float *)d_ws, n, f);                  \
   } while (0)
 #define TNP(PP)                 \

@@ -210,6 +210,16 @@ graph_values_kernel(const uint32_t *__restrict__ indptr, const uint32_t *__restr
 }
 }  // namespace
 
+namespace {
+// arguments that change from epoch to epoch (CUDA-graph replay, gcnb_graph_patch_node): always the last argument
+const int patchables_registered = [] {
+  register_patchable((const void *)dropout_fwd_kernel<false>, 9, -1);
+  register_patchable((const void *)dropout_fwd_kernel<true>, 9, -1);
+  register_patchable((const void *)adam_kernel, -1, 5);
+  return 0;
+}();
+}  // namespace
+
 extern "C" {
 
 int gcnb_glorot_f32(float *d_w, int64_t size, uint32_t rows, uint32_t cols, const gcnb_rng_t *rng, gcnb_stream_t s) {

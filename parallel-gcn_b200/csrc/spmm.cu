@@ -36,6 +36,26 @@ const DeviceInfo &device_info() {
   return info;
 }
 
+struct Patchable {
+  const void *kernel;
+  int rng_arg, step_arg;
+};
+static std::vector<Patchable> &patch_table() {
+  static std::vector<Patchable> t;
+  return t;
+}
+
+void register_patchable(const void *kernel, int rng_arg, int step_arg) { patch_table().push_back({kernel, rng_arg, step_arg}); }
+bool lookup_patchable(const void *kernel, int *rng_arg, int *step_arg) {
+  for (const Patchable &p : patch_table())
+    if (p.kernel == kernel) {
+      *rng_arg = p.rng_arg;
+      *step_arg = p.step_arg;
+      return true;
+    }
+  return false;
+}
+
 }  // namespace gcnb
 
 using namespace gcnb;
@@ -294,6 +314,17 @@ spmm_seg_kernel(const uint4 *__restrict__ segs, const uint32_t *__restrict__ que
       drain_queue<VEC, LPR, KT, EXACT>(A, queue_begin, counters, __shfl_sync(0xffffffffu, q, src), lane, batch);
     }
   }
+  // the last CTA to finish leaves the tickets zeroed for the next launch (no memset per launch: on small graphs a
+  // memset node costs as much as the product itself).  Every other CTA has left its work loops when it counts itself
+  // done, so nobody reads the tickets any more.
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(counters + n_queues, 1u) == gridDim.x - 1) {
+      for (int q = 0; q <= n_queues; q++) counters[q] = 0u;
+      __threadfence();
+    }
+  }
 }
 
 // rows cut into several segments: out[row] = partial[s0] + partial[s0+1] + ... in ascending order
@@ -425,6 +456,7 @@ int gcnb_spmm_plan_create(const uint32_t *d_indptr, const uint32_t *d_indices, i
   if (!rc) rc = upload((void **)&p->d_segs, segs.empty() ? nullptr : segs.data(), segs.size() * sizeof(uint4));
   if (!rc) rc = upload((void **)&p->d_queue_begin, qbeg.data(), qbeg.size() * 4);
   if (!rc) rc = upload((void **)&p->d_counters, nullptr, ((size_t)p->n_queues + 1) * 4);
+  if (!rc) rc = (int)cudaMemsetAsync(p->d_counters, 0, ((size_t)p->n_queues + 1) * 4, stream);  // kernels re-zero them
   if (!rc) rc = upload((void **)&p->d_split_row, split_row.empty() ? nullptr : split_row.data(), split_row.size() * 4);
   if (!rc) rc = upload((void **)&p->d_split_slot, split_slot.data(), split_slot.size() * 4);
   if (!rc) rc = (int)cudaStreamSynchronize(stream);
@@ -531,7 +563,6 @@ int gcnb::spmm_generic_launch(gcnb_spmm_plan *p, const float *d_values, const ui
   int64_t grid = (int64_t)p->n_queues * blocks_per_sm;
   const int64_t min_grid = (warps_needed + (kThreads / 32) - 1) / (kThreads / 32);
   if (grid > min_grid) grid = std::max<int64_t>(1, min_grid);
-  GCNB_CHECK(cudaMemsetAsync(p->d_counters, 0, ((size_t)p->n_queues + 1) * 4, stream));
   fn<<<(unsigned)grid, kThreads, 0, stream>>>(p->d_segs, p->d_queue_begin, p->d_counters, p->n_queues, p->d_indices,
                                               d_values, d_perm, d_B, d_C, p->d_scratch, dim, ldb, ldc, p->batch);
   GCNB_LAUNCH_CHECK();
@@ -628,6 +659,35 @@ int gcnb_csc_arrays(const gcnb_csc *c, const uint32_t **d_colptr, const uint32_t
   if (d_rowidx) *d_rowidx = c->d_rowidx;
   if (d_perm) *d_perm = c->d_perm;
   if (is_dense) *is_dense = c->is_dense;
+  return 0;
+}
+
+// ---- CUDA-graph replay support -------------------------------------------------------------------------------------------
+int gcnb_graph_patch_node(void *exec_, void *node_, const gcnb_rng_t *rng, const float *step_size) {
+  if (!exec_ || !node_ || (!rng && !step_size)) return GCNB_E_BADARG;
+  cudaGraphExec_t exec = (cudaGraphExec_t)exec_;
+  cudaGraphNode_t node = (cudaGraphNode_t)node_;
+  cudaKernelNodeParams kp{};
+  GCNB_CHECK(cudaGraphKernelNodeGetParams(node, &kp));
+  int rng_arg = -1, step_arg = -1;
+  if (!gcnb::lookup_patchable(kp.func, &rng_arg, &step_arg)) return GCNB_E_UNSUPPORTED;
+  const int n_args = std::max(rng_arg, step_arg) + 1;
+  if ((rng && rng_arg < 0) || (step_size && step_arg < 0) || !kp.kernelParams || n_args > 16) return GCNB_E_BADARG;
+  void *args[16];
+  for (int i = 0; i < n_args; i++) args[i] = kp.kernelParams[i];
+  gcnb_rng_t r;
+  float st;
+  if (rng) {
+    r = *rng;
+    args[rng_arg] = &r;
+  }
+  if (step_size) {
+    st = *step_size;
+    args[step_arg] = &st;
+  }
+  // every patchable kernel keeps the patched argument LAST, so the first n_args pointers are its complete argument list
+  kp.kernelParams = args;
+  GCNB_CHECK(cudaGraphExecKernelNodeSetParams(exec, node, &kp));
   return 0;
 }
 

@@ -58,6 +58,8 @@ _sig("gcnb_gcn_get_logits", I32, [P, P])
 _sig("gcnb_gcn_set_mask", I32, [P, I32, P])
 _sig("gcnb_gcn_launches_per_epoch", I64, [P])
 _sig("gcnb_gcn_graph_staged", I32, [P])
+_sig("gcnb_gcn_set_cuda_graph", I32, [P, I32])
+_sig("gcnb_gcn_uses_cuda_graph", I32, [P])
 _sig("gcnb_gcn_launches_total", I64, [P])
 _sig("gcnb_gcn_timed_epochs", I32, [P, I32, I32, I32, P])
 _sig("gcnb_synth_graph", I32, [I64, I64, I32, C.c_double, C.c_double, I64, C.c_uint64, P, P, P])
@@ -367,6 +369,12 @@ class GCN:
 
     def launches_per_epoch(self):
         return int(lib.gcnb_gcn_launches_per_epoch(self.h))
+
+    def set_cuda_graph(self, on):
+        check(lib.gcnb_gcn_set_cuda_graph(self.h, int(on)))
+
+    def uses_cuda_graph(self):
+        return bool(lib.gcnb_gcn_uses_cuda_graph(self.h))
 
     def close(self):
         if getattr(self, "h", None) and lib is not None:

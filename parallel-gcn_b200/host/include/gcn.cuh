@@ -107,8 +107,11 @@ class GCN {
 
   void set_truth(const natural current_split, cudaStream_t stream) const;
   void forward_pass(bool training, natural split, cudaStream_t stream);
+  void train_body(cudaStream_t stream);
   void backward_pass(cudaStream_t stream);
-  std::pair<real, real> finalize(cudaStream_t stream) const;
+  std::pair<real, real> finalize(cudaStream_t stream, int slot) const;
+  std::pair<real, real> read_result(int slot) const;
+  void train_and_eval(natural split, std::pair<real, real> &train, std::pair<real, real> &val);
   void print_variable_info() const;
   void init(bool quiet, const natural *h_graph_indptr = nullptr, const natural *h_graph_indices = nullptr,
             const GCNPartition *part = nullptr);
@@ -147,6 +150,10 @@ class GCN {
   void set_external_masks(const std::vector<const unsigned char *> &host_masks);
   void set_quiet(bool q);
   void set_reorder(bool on);  // allow the (A*a)*W association (default on)
+  // replay captured epochs as CUDA graphs (default: on for small datasets, which are launch-bound); results are
+  // bit-identical to eager launches
+  void set_use_cuda_graph(bool on);
+  bool uses_cuda_graph() const;
   size_t launches_per_epoch() const;
   bool graph_staged() const;  // GraphSum at widths 16 / >= 64 runs the window-staged kernels (csrc/spmm_stage.cu)
   size_t launches_total() const;

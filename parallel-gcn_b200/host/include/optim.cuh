@@ -43,6 +43,10 @@ class Adam {
   void step();
   // extension used by the fused GCN driver: the whole step on one caller-chosen stream, no events
   void step_on(cudaStream_t stream);
+  // the two halves of step_on, for CUDA-graph replay: advance the step counter and return this step's step size; launch
+  // the update with a given step size
+  real advance();
+  void launch_on(cudaStream_t stream, real step_size);
   natural steps() const { return step_count; }
 };
 #endif

@@ -377,6 +377,12 @@ int gcnb_gcn_set_mask(gcnb_gcn *g, int site, const uint8_t *host_mask) {
   return 0;
 }
 int64_t gcnb_gcn_launches_per_epoch(const gcnb_gcn *g) { return g ? (int64_t)g->gcn->launches_per_epoch() : -1; }
+int gcnb_gcn_set_cuda_graph(gcnb_gcn *g, int on) {
+  if (!g) return GCNB_E_BADARG;
+  g->gcn->set_use_cuda_graph(on != 0);
+  return 0;
+}
+int gcnb_gcn_uses_cuda_graph(const gcnb_gcn *g) { return g ? (int)g->gcn->uses_cuda_graph() : -1; }
 int gcnb_gcn_graph_staged(const gcnb_gcn *g) { return g ? (int)g->gcn->graph_staged() : -1; }
 int64_t gcnb_gcn_launches_total(const gcnb_gcn *g) { return g ? (int64_t)g->gcn->launches_total() : -1; }
 int gcnb_gcn_timed_epochs(gcnb_gcn *g, int n_epochs, int with_eval, int time_graphsum, float out[4]) {

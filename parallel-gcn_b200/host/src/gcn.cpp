@@ -137,10 +137,69 @@ struct GCNEngineState {
   int64_t tn_ws_bytes = 0;
   dev_shared_ptr<natural> ce_ws, sumsq_ws;
   dev_shared_ptr<real> dev_result;     // [loss_sum, wrong, labelled, pad, l2_sumsq, pad..]
-  pinned_host_ptr<real> host_result;   // same 8 floats
+  pinned_host_ptr<real> host_result;   // 2 x the same 8 floats: slot 0 training passes, slot 1 evaluation passes
+  natural result_total[2] = {0, 0};    // num_samples of the pass whose result sits in each slot
   natural cur_num_samples = 0;
   std::vector<dev_shared_ptr<unsigned char>> ext_masks;  // injected keep-masks per dropout site (may be null)
   bool quiet = false, allow_reorder = true;
+  // CUDA-graph replay (small datasets are launch-bound: ~40 launches of a few microseconds per pass).  An epoch is
+  // captured once; afterwards only the arguments that change from epoch to epoch -- the Philox descriptors of the dropout
+  // kernels and Adam's step size -- are patched into the instantiated graph (gcnb_graph_patch_node) and the graph is
+  // launched.  The host-side bookkeeping (RNG consumption history, Adam step count) runs in every phase, so eager, captured
+  // and replayed epochs are interchangeable and produce identical bits.
+  enum Phase { Eager, Capture, Replay };
+  Phase phase = Eager;
+  bool graph_enabled = false;
+  cudaGraphExec_t train_exec = nullptr, eval_exec[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaGraph_t train_graph = nullptr, eval_graph[4] = {nullptr, nullptr, nullptr, nullptr};
+  std::vector<cudaGraphNode_t> train_sites;  // kernel nodes with per-epoch arguments, in issue order
+  size_t site_cursor = 0;
+  size_t backward_launches = 0;
+  natural eager_train_epochs = 0, eager_evals[4] = {0, 0, 0, 0};
+  bool live() const { return phase != Replay; }  // kernels are issued (eagerly or into a capture)
+  cudaGraphNode_t last_captured_node() const {
+    cudaStreamCaptureStatus status;
+    const cudaGraphNode_t *deps = nullptr;
+    size_t n = 0;
+    CHECK_CUDA_ERROR(cudaStreamGetCaptureInfo(stream, &status, nullptr, nullptr, &deps, &n));
+    if (status != cudaStreamCaptureStatusActive || n != 1) {
+      std::cerr << "GCN: unexpected capture state while recording a patchable kernel node" << std::endl;
+      exit(EXIT_FAILURE);
+    }
+    return deps[0];
+  }
+  // a library call that takes this epoch's Philox descriptor: issued (and its node remembered when capturing), or, in a
+  // replay, patched into the captured node
+  template <class F>
+  void rng_site(const gcnb_rng_t &rng, F issue) {
+    if (phase == Replay) {
+      GCNB_CALL(gcnb_graph_patch_node(train_exec, train_sites[site_cursor++], &rng, nullptr));
+      return;
+    }
+    issue();
+    if (phase == Capture) train_sites.push_back(last_captured_node());
+  }
+  void drop_graphs() {
+    if (train_exec) cudaGraphExecDestroy(train_exec);
+    if (train_graph) cudaGraphDestroy(train_graph);
+    train_exec = nullptr;
+    train_graph = nullptr;
+    train_sites.clear();
+    for (int i = 0; i < 4; i++) {
+      if (eval_exec[i]) cudaGraphExecDestroy(eval_exec[i]);
+      if (eval_graph[i]) cudaGraphDestroy(eval_graph[i]);
+      eval_exec[i] = nullptr;
+      eval_graph[i] = nullptr;
+      eager_evals[i] = 0;
+    }
+    eager_train_epochs = 0;
+  }
+  bool graphs_usable() const {
+    if (!graph_enabled || dist || time_graphsum) return false;
+    for (const auto &m : ext_masks)
+      if (m.get()) return false;
+    return true;
+  }
   size_t launches = 0, launches_last_epoch = 0;  // CUDA kernels launched (memsets / copies not counted)
   natural epochs_run = 0;
   int graph_spmm_kernels = 1, feat_spmm_kernels = 1, feat_csc_kernels = 1;  // 1 + combine kernel when rows are split
@@ -152,6 +211,10 @@ struct GCNEngineState {
   double gs_ms_total = 0;
   size_t gs_calls = 0;
   void graphsum(const real *gv, const real *in, real *out, natural dim) {
+    if (!live()) {  // replay: the captured graph holds these launches
+      launches += graphsum_launches(dim);
+      return;
+    }
     if (time_graphsum) {
       if (gs_used + 2 > gs_events.size())
         for (int i = 0; i < 2; i++) {
@@ -201,6 +264,7 @@ struct GCNEngineState {
     gs_used = 0;
   }
   ~GCNEngineState() {
+    drop_graphs();
     for (auto e : gs_events) cudaEventDestroy(e);
     if (feat_csc_plan) gcnb_spmm_plan_destroy(feat_csc_plan);
     if (feat_csc) gcnb_csc_destroy(feat_csc);
@@ -387,7 +451,7 @@ void GCN::init(bool quiet, const natural *h_graph_indptr, const natural *h_graph
   CHECK_CUDA_ERROR(cudaMemset(st->sumsq_ws.get(), 0, st->sumsq_ws.get_n_elements() * 4));
   st->dev_result = dev_shared_ptr<real>(8);
   CHECK_CUDA_ERROR(cudaMemset(st->dev_result.get(), 0, 8 * sizeof(real)));
-  st->host_result = pinned_host_ptr<real>(8);
+  st->host_result = pinned_host_ptr<real>(16);
   st->ext_masks.resize(L);
 
   if (!st->quiet) print_variable_info();
@@ -397,6 +461,12 @@ void GCN::init(bool quiet, const natural *h_graph_indptr, const natural *h_graph
   optimizer = Adam(weights, decays, adam_params, smart_objects.backward_streams, smart_objects.start_matmul_forward,
                    smart_objects.forward_training_stream);
   setup_lap("workspaces, glorot, Adam state");
+  {
+    // small datasets are launch-bound: replay captured epochs (GCNB_CUDA_GRAPH=0 / 1 forces it off / on)
+    const char *e = getenv("GCNB_CUDA_GRAPH");
+    const size_t entries = dev_data.dev_graph_index.indices_size + dev_data.dev_feature_index.indices_size;
+    st->graph_enabled = e ? atoi(e) != 0 : entries <= (size_t(8) << 20);
+  }
 }
 
 GCN::~GCN() {
@@ -404,7 +474,13 @@ GCN::~GCN() {
 }
 
 void GCN::set_quiet(bool q) { st->quiet = q; }
+void GCN::set_use_cuda_graph(bool on) {
+  if (!on) st->drop_graphs();
+  st->graph_enabled = on;
+}
+bool GCN::uses_cuda_graph() const { return st->graphs_usable(); }
 void GCN::set_reorder(bool on) {
+  st->drop_graphs();
   st->allow_reorder = on;
   const size_t N = st->dist ? st->block : params->num_nodes;
   for (natural l = 1; l < L; l++) {
@@ -423,6 +499,7 @@ size_t GCN::launches_per_epoch() const { return st->launches_last_epoch; }
 bool GCN::graph_staged() const { return st->graph_staged; }
 size_t GCN::launches_total() const { return st->launches; }
 void GCN::set_time_graphsum(bool on) {
+  st->drop_graphs();
   st->time_graphsum = on;
   st->gs_ms_total = 0;
   st->gs_calls = 0;
@@ -439,8 +516,12 @@ float GCN::timed_epochs(natural n_epochs, bool with_eval) {
   CHECK_CUDA_ERROR(cudaStreamSynchronize(st->stream));
   CHECK_CUDA_ERROR(cudaEventRecord(e0, st->stream));
   for (natural i = 0; i < n_epochs; i++) {
-    train_epoch();
-    if (with_eval) eval(2);
+    if (with_eval) {
+      std::pair<real, real> tr, va;
+      train_and_eval(2, tr, va);  // the loop body of run()
+    } else {
+      train_epoch();
+    }
   }
   CHECK_CUDA_ERROR(cudaEventRecord(e1, st->stream));
   CHECK_CUDA_ERROR(cudaEventSynchronize(e1));
@@ -453,6 +534,7 @@ float GCN::timed_epochs(natural n_epochs, bool with_eval) {
 natural GCN::epochs_run() const { return st->epochs_run; }
 
 void GCN::set_external_masks(const std::vector<const unsigned char *> &host_masks) {
+  st->drop_graphs();
   const natural N = params->num_nodes;
   for (natural site = 0; site < L; site++) {
     const unsigned char *src = site < host_masks.size() ? host_masks[site] : nullptr;
@@ -471,8 +553,9 @@ void GCN::set_truth(const natural current_split, cudaStream_t stream) const {
   if (current_split == 1) st->cur_num_samples = params->train_dim;
   else if (current_split == 2) st->cur_num_samples = params->val_dim;
   else if (current_split == 3) st->cur_num_samples = params->test_dim;
-  GCNB_CALL(gcnb_set_truth(dev_truth.get(), dev_data.dev_split.get(), dev_data.dev_label.get(), params->num_nodes,
-                           current_split, stream));
+  if (st->live())
+    GCNB_CALL(gcnb_set_truth(dev_truth.get(), dev_data.dev_split.get(), dev_data.dev_label.get(), params->num_nodes,
+                             current_split, stream));
   st->launches++;
 }
 
@@ -503,7 +586,7 @@ void GCN::forward_pass(bool training, natural split, cudaStream_t s) {
         std::swap(st->x_bits, st->x_bits_next);  // generated on the side stream during the previous epoch
         CHECK_CUDA_ERROR(cudaStreamWaitEvent(s, st->ev_bits, 0));
       } else {
-        GCNB_CALL(gcnb_dropout_maskbits(st->x_bits.get(), N, (int)F, p0, &rng, s));
+        st->rng_site(rng, [&] { GCNB_CALL(gcnb_dropout_maskbits(st->x_bits.get(), N, (int)F, p0, &rng, s)); });
         st->launches++;
       }
       st->next_bits_valid = false;
@@ -521,7 +604,9 @@ void GCN::forward_pass(bool training, natural split, cudaStream_t s) {
     st->x_train_p = 0.f;
     if (p0 > 0.f || ext) {
       const gcnb_rng_t rng = rng_at(st->f_elem_off);
-      GCNB_CALL(gcnb_dropout_fwd_oop_f32(xvals, input->dev_data.get(), nullptr, ext, input->size, p0, &rng, s));
+      st->rng_site(rng, [&] {
+        GCNB_CALL(gcnb_dropout_fwd_oop_f32(xvals, input->dev_data.get(), nullptr, ext, input->size, p0, &rng, s));
+      });
       st->launches++;
       xvals = input->dev_data.get();
     }
@@ -554,23 +639,27 @@ void GCN::forward_pass(bool training, natural split, cudaStream_t s) {
       }
     }
   }
+  const bool live = st->live();  // false in a graph replay: the captured graph holds every launch below
   if (!training && st->ax_ready && st->allow_reorder) {
     GCNLayer &l0 = st->layers[0];
-    GCNB_CALL(gcnb_dense_feat_fwd_f32(st->ax.get(), nullptr, 0.f, weights[0]->dev_data.get(), l0.z->dev_data.get(), N, (int)F,
-                                      (int)l0.out_dim, s));
+    if (live)
+      GCNB_CALL(gcnb_dense_feat_fwd_f32(st->ax.get(), nullptr, 0.f, weights[0]->dev_data.get(), l0.z->dev_data.get(), N,
+                                        (int)F, (int)l0.out_dim, s));
     st->launches += 1;
   } else {
     GCNLayer &l0 = st->layers[0];
     if (st->dense_fast) {
-      GCNB_CALL(gcnb_dense_feat_fwd_f32(xvals, xbits, xp, weights[0]->dev_data.get(), l0.pre->dev_data.get(), N, (int)F,
-                                        (int)l0.out_dim, s));
+      if (live)
+        GCNB_CALL(gcnb_dense_feat_fwd_f32(xvals, xbits, xp, weights[0]->dev_data.get(), l0.pre->dev_data.get(), N, (int)F,
+                                          (int)l0.out_dim, s));
       st->launches += 1;
     } else if (st->feat_dense) {
-      GCNB_CALL(gcnb_matmul_nn_f32(xvals, weights[0]->dev_data.get(), l0.pre->dev_data.get(), N, F, l0.out_dim, s));
+      if (live) GCNB_CALL(gcnb_matmul_nn_f32(xvals, weights[0]->dev_data.get(), l0.pre->dev_data.get(), N, F, l0.out_dim, s));
       st->launches += 1;
     } else {
-      GCNB_CALL(gcnb_spmm_f32(st->feat_plan, xvals, nullptr, weights[0]->dev_data.get(), l0.pre->dev_data.get(),
-                              l0.out_dim, s));
+      if (live)
+        GCNB_CALL(gcnb_spmm_f32(st->feat_plan, xvals, nullptr, weights[0]->dev_data.get(), l0.pre->dev_data.get(),
+                                l0.out_dim, s));
       st->launches += st->feat_spmm_kernels;
     }
     st->graphsum(dev_data.dev_graph_value.get(), l0.pre->dev_data.get(), l0.z->dev_data.get(), l0.out_dim);
@@ -581,10 +670,12 @@ void GCN::forward_pass(bool training, natural split, cudaStream_t s) {
       const real *a = st->layers[l - 1].z->dev_data.get();
       if (ly.reorder) {
         st->graphsum(dev_data.dev_graph_value.get(), a, ly.pre->dev_data.get(), ly.in_dim);
-        GCNB_CALL(gcnb_matmul_nn_f32(ly.pre->dev_data.get(), weights[l]->dev_data.get(), ly.z->dev_data.get(), N,
-                                     ly.in_dim, ly.out_dim, s));
+        if (live)
+          GCNB_CALL(gcnb_matmul_nn_f32(ly.pre->dev_data.get(), weights[l]->dev_data.get(), ly.z->dev_data.get(), N,
+                                       ly.in_dim, ly.out_dim, s));
       } else {
-        GCNB_CALL(gcnb_matmul_nn_f32(a, weights[l]->dev_data.get(), ly.pre->dev_data.get(), N, ly.in_dim, ly.out_dim, s));
+        if (live)
+          GCNB_CALL(gcnb_matmul_nn_f32(a, weights[l]->dev_data.get(), ly.pre->dev_data.get(), N, ly.in_dim, ly.out_dim, s));
         st->graphsum(dev_data.dev_graph_value.get(), ly.pre->dev_data.get(), ly.z->dev_data.get(), ly.out_dim);
       }
       st->launches += 1;
@@ -592,27 +683,41 @@ void GCN::forward_pass(bool training, natural split, cudaStream_t s) {
     if (l + 1 < L) {
       const real p = params->dropouts[l + 1];
       const gcnb_rng_t rng = rng_at(st->row0 * ly.out_dim);
-      GCNB_CALL(gcnb_relu_dropout_fwd_f32(ly.z->dev_data.get(), ly.mask.get(), st->ext_masks[l + 1].get(),
-                                          (size_t)N * ly.out_dim, p, training, &rng, s));
+      auto issue = [&] {
+        GCNB_CALL(gcnb_relu_dropout_fwd_f32(ly.z->dev_data.get(), ly.mask.get(), st->ext_masks[l + 1].get(),
+                                            (size_t)N * ly.out_dim, p, training, &rng, s));
+      };
+      if (training) st->rng_site(rng, issue);  // evaluation passes draw nothing: a plain launch
+      else if (live) issue();
       st->launches++;
       if (training) Variable::rng_consume(rows_global * ly.out_dim);
     }
   }
   // ---- loss + accuracy (one kernel) and the L2 term of the decayed weights
-  GCNB_CALL(gcnb_softmax_ce_f32(output->dev_data.get(), output->dev_grad.get(), dev_truth.get(), N, params->output_dim,
-                                st->cur_num_samples, training, st->dev_result.get(), st->ce_ws.get(), s));
+  if (live)
+    GCNB_CALL(gcnb_softmax_ce_f32(output->dev_data.get(), output->dev_grad.get(), dev_truth.get(), N, params->output_dim,
+                                  st->cur_num_samples, training, st->dev_result.get(), st->ce_ws.get(), s));
   if (st->dist) {  // loss sum (float) and wrong / labelled counts (uint32 bit patterns) over all row blocks
     GCNB_CALL(gcnb_comm_group_start(st->comm));
     GCNB_CALL(gcnb_comm_all_reduce_sum(st->comm, st->dev_result.get(), 1, 0, s));
     GCNB_CALL(gcnb_comm_all_reduce_sum(st->comm, st->dev_result.get() + 1, 2, 1, s));
     GCNB_CALL(gcnb_comm_group_end(st->comm));
   }
-  GCNB_CALL(gcnb_sumsq_f32(weights[0]->dev_data.get(), weights[0]->size, st->dev_result.get() + 4, st->sumsq_ws.get(), s));
-  CHECK_CUDA_ERROR(cudaMemcpyAsync(st->host_result.get(), st->dev_result.get(), 8 * sizeof(real), cudaMemcpyDeviceToHost, s));
+  if (live) {
+    GCNB_CALL(gcnb_sumsq_f32(weights[0]->dev_data.get(), weights[0]->size, st->dev_result.get() + 4, st->sumsq_ws.get(), s));
+    CHECK_CUDA_ERROR(cudaMemcpyAsync(st->host_result.get() + (training ? 0 : 8), st->dev_result.get(), 8 * sizeof(real),
+                                     cudaMemcpyDeviceToHost, s));
+  }
+  st->result_total[training ? 0 : 1] = st->cur_num_samples;
   st->launches += 2;
 }
 
 void GCN::backward_pass(cudaStream_t s) {
+  if (!st->live()) {  // graph replay: nothing here depends on the epoch; the captured graph holds the launches
+    st->launches += st->backward_launches;
+    return;
+  }
+  const size_t launches_before = st->launches;
   const natural N = params->num_nodes, F = params->input_dim;
   const real *gv = dev_data.dev_graph_value.get();
   const real *g = output->dev_grad.get();
@@ -675,13 +780,18 @@ void GCN::backward_pass(cudaStream_t s) {
       GCNB_CALL(gcnb_comm_all_reduce_sum(st->comm, weights[l]->dev_grad.get(), (int64_t)weights[l]->size, 0, s));
     GCNB_CALL(gcnb_comm_group_end(st->comm));
   }
+  st->backward_launches = st->launches - launches_before;
 }
 
-std::pair<real, real> GCN::finalize(cudaStream_t s) const {
+std::pair<real, real> GCN::finalize(cudaStream_t s, int slot) const {
   CHECK_CUDA_ERROR(cudaStreamSynchronize(s));  // the one host sync per pass (src/gcn.cu:443)
   if (st->time_graphsum) st->collect_graphsum_times();
-  const real *r = st->host_result.get();
-  const natural total = st->cur_num_samples;
+  return read_result(slot);
+}
+
+std::pair<real, real> GCN::read_result(int slot) const {
+  const real *r = st->host_result.get() + 8 * slot;
+  const natural total = st->result_total[slot];
   natural wrong;
   std::memcpy(&wrong, r + 1, sizeof(natural));
   const real loss = r[0] / total;
@@ -691,12 +801,12 @@ std::pair<real, real> GCN::finalize(cudaStream_t s) const {
   return {final_loss, final_accuracy};
 }
 
-std::pair<real, real> GCN::train_epoch() {
-  const size_t before = st->launches;
-  cudaStream_t s = st->stream;
-  CHECK_CUDA_ERROR(cudaEventRecord(st->ev_epoch, s));  // everything enqueued so far (previous epoch included)
+// forward + backward + Adam of one training epoch, in the current phase (issued, captured, or -- replay -- only the
+// host bookkeeping plus the patches of the per-epoch kernel arguments)
+void GCN::train_body(cudaStream_t s) {
   forward_pass(true, 1, s);
-  if ((st->use_side & 2) && st->dense_fast && !st->ext_masks[0].get() && params->dropouts.front() > 0.f) {
+  if (st->phase == GCNEngineState::Eager && (st->use_side & 2) && st->dense_fast && !st->ext_masks[0].get() &&
+      params->dropouts.front() > 0.f && !st->graphs_usable()) {
     // keep bits of the next epoch's input dropout, on the side stream, into the other buffer (its last reader was
     // the previous epoch's weight-gradient product, ordered by ev_epoch)
     st->next_bits_rng = rng_at(st->f_elem_off);
@@ -709,16 +819,89 @@ std::pair<real, real> GCN::train_epoch() {
     st->next_bits_valid = true;
   }
   backward_pass(s);
-  optimizer.step_on(s);
+  const real step_size = optimizer.advance();
+  if (st->phase == GCNEngineState::Replay) {
+    GCNB_CALL(gcnb_graph_patch_node(st->train_exec, st->train_sites[st->site_cursor++], nullptr, &step_size));
+  } else {
+    optimizer.launch_on(s, step_size);
+    if (st->phase == GCNEngineState::Capture) st->train_sites.push_back(st->last_captured_node());
+  }
   st->launches++;
+}
+
+std::pair<real, real> GCN::train_epoch() {
+  const size_t before = st->launches;
+  cudaStream_t s = st->stream;
+  if (st->graphs_usable() && st->train_exec) {
+    st->phase = GCNEngineState::Replay;
+    st->site_cursor = 0;
+    train_body(s);
+    st->phase = GCNEngineState::Eager;
+    CHECK_CUDA_ERROR(cudaGraphLaunch(st->train_exec, s));
+  } else if (st->graphs_usable() && st->eager_train_epochs >= 1) {
+    // the first epoch ran eagerly (lazy allocations, occupancy queries); this one is captured, then launched
+    st->phase = GCNEngineState::Capture;
+    st->train_sites.clear();
+    CHECK_CUDA_ERROR(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    train_body(s);
+    CHECK_CUDA_ERROR(cudaStreamEndCapture(s, &st->train_graph));
+    st->phase = GCNEngineState::Eager;
+    CHECK_CUDA_ERROR(cudaGraphInstantiate(&st->train_exec, st->train_graph, 0));
+    CHECK_CUDA_ERROR(cudaGraphLaunch(st->train_exec, s));
+  } else {
+    CHECK_CUDA_ERROR(cudaEventRecord(st->ev_epoch, s));  // everything enqueued so far (previous epoch included)
+    train_body(s);
+    st->eager_train_epochs++;
+  }
   st->launches_last_epoch = st->launches - before;
-  return finalize(s);
+  return finalize(s, 0);
+}
+
+// train_epoch() followed by eval(split) with ONE host synchronisation when both passes are graph replays (the loop of
+// run(): small datasets spend a visible share of an epoch in the sync round trip); otherwise the two calls
+void GCN::train_and_eval(natural split, std::pair<real, real> &train, std::pair<real, real> &val) {
+  const natural k = split < 4 ? split : 0;
+  if (!(st->graphs_usable() && st->train_exec && k != 0 && st->eval_exec[k])) {
+    train = train_epoch();
+    val = eval(split);
+    return;
+  }
+  const size_t before = st->launches;
+  cudaStream_t s = st->stream;
+  st->phase = GCNEngineState::Replay;
+  st->site_cursor = 0;
+  train_body(s);
+  st->launches_last_epoch = st->launches - before;
+  CHECK_CUDA_ERROR(cudaGraphLaunch(st->train_exec, s));
+  forward_pass(false, split, s);
+  st->phase = GCNEngineState::Eager;
+  CHECK_CUDA_ERROR(cudaGraphLaunch(st->eval_exec[k], s));
+  CHECK_CUDA_ERROR(cudaStreamSynchronize(s));
+  train = read_result(0);
+  val = read_result(1);
 }
 
 std::pair<real, real> GCN::eval(const natural current_split) {
   cudaStream_t s = st->stream;
-  forward_pass(false, current_split, s);
-  return finalize(s);
+  const natural k = current_split < 4 ? current_split : 0;
+  if (st->graphs_usable() && st->eval_exec[k]) {
+    st->phase = GCNEngineState::Replay;  // nothing to patch in an evaluation pass: bookkeeping only
+    forward_pass(false, current_split, s);
+    st->phase = GCNEngineState::Eager;
+    CHECK_CUDA_ERROR(cudaGraphLaunch(st->eval_exec[k], s));
+  } else if (st->graphs_usable() && k != 0 && st->eager_evals[k] >= 1) {
+    st->phase = GCNEngineState::Capture;
+    CHECK_CUDA_ERROR(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    forward_pass(false, current_split, s);
+    CHECK_CUDA_ERROR(cudaStreamEndCapture(s, &st->eval_graph[k]));
+    st->phase = GCNEngineState::Eager;
+    CHECK_CUDA_ERROR(cudaGraphInstantiate(&st->eval_exec[k], st->eval_graph[k], 0));
+    CHECK_CUDA_ERROR(cudaGraphLaunch(st->eval_exec[k], s));
+  } else {
+    forward_pass(false, current_split, s);
+    st->eager_evals[k]++;
+  }
+  return finalize(s, 1);
 }
 
 void GCN::run() {
@@ -731,8 +914,10 @@ void GCN::run() {
   real train_loss{0.f}, train_acc{0.f}, val_loss{0.f}, val_acc{0.f};
   for (; epoch <= params->epochs; epoch++) {
     timer_start(TMR_TRAIN);
-    std::tie(train_loss, train_acc) = train_epoch();
-    std::tie(val_loss, val_acc) = eval(2);
+    std::pair<real, real> tr, va;
+    train_and_eval(2, tr, va);
+    std::tie(train_loss, train_acc) = tr;
+    std::tie(val_loss, val_acc) = va;
     const auto time = timer_stop(TMR_TRAIN);
     if (out)
       printf("epoch=%d train_loss=%.5f train_acc=%.5f val_loss=%.5f val_acc=%.5f time=%.5f\n", epoch, train_loss,

@@ -30,10 +30,12 @@ Adam::Adam(const std::vector<shared_ptr<Variable>> &weights, const std::vector<b
   for (natural i = 0; i < weights.size(); i++) vars.emplace_back(weights[i], decays[i], forward_training_stream);
 }
 
-void Adam::step_on(cudaStream_t stream) {
+real Adam::advance() {
   step_count++;
-  const real step_size =
-      params->learning_rate * sqrtf(1 - powf(params->beta2, step_count)) / (1 - powf(params->beta1, step_count));
+  return params->learning_rate * sqrtf(1 - powf(params->beta2, step_count)) / (1 - powf(params->beta1, step_count));
+}
+
+void Adam::launch_on(cudaStream_t stream, real step_size) {
   gcnb_adam_tensors_t t{};
   t.n_tensors = static_cast<int>(vars.size());
   for (size_t i = 0; i < vars.size(); i++) {
@@ -46,6 +48,8 @@ void Adam::step_on(cudaStream_t stream) {
   }
   GCNB_CALL(gcnb_adam_step_f32(&t, params->weight_decay, params->beta1, params->beta2, params->eps, step_size, stream));
 }
+
+void Adam::step_on(cudaStream_t stream) { launch_on(stream, advance()); }
 
 void Adam::step() {
   // The reference updates W0 on backward_streams[0] and the rest on backward_streams[1] (src/optim.cu:76-92).

@@ -252,3 +252,32 @@ def test_renumbered_dataset_is_the_same_model(eng, datasets, name):
     for a, b in zip(ev, evp):
         assert abs(a[0] - b[0]) <= 1e-5 * abs(a[0]) and abs(a[1] - b[1]) <= 1e-6
     assert_close(eng.permute_rows(plogits, perm, inverse=True), logits, rtol=1e-5, what="un-permuted logits")
+
+
+@pytest.mark.parametrize("name", ["cora", "citeseer", "dense"])
+def test_cuda_graph_replay_is_bit_identical_to_eager(eng, datasets, name):
+    """small datasets replay captured epochs (CUDA graphs) with the per-epoch kernel arguments -- Philox descriptors,
+    Adam step size -- patched into the instantiated graph: every loss, accuracy and weight equals the eager run's bits."""
+    def make():
+        if name == "dense":
+            return eng.synth_dataset(3000, 40000, 24, 5, n_blocks=4, seed=9)
+        return eng.parse_dataset(ROOT, name)
+
+    def run(use_graph):
+        g = eng.GCN(make(), hidden_dims=(16,), dropouts=(0.5, 0.5))
+        g.set_cuda_graph(use_graph)
+        assert g.uses_cuda_graph() == use_graph
+        hist = []
+        for _ in range(6):
+            hist.append((g.train_epoch(), g.eval(2)))
+        hist.append((g.eval(3), g.eval(1)))
+        w = [g.weight(l) for l in range(2)]
+        launches = g.launches_per_epoch()
+        g.close()
+        return hist, w, launches
+
+    eager, graph = run(False), run(True)
+    assert eager[0] == graph[0]
+    for a, b in zip(eager[1], graph[1]):
+        assert np.array_equal(a, b)
+    assert eager[2] == graph[2]
