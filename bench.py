@@ -254,6 +254,9 @@ def run_ours(args, rank, world, local_rank):
                                     MODEL["dropouts"][1], MODEL["lr"], MODEL["weight_decay"]),
                        "l2_policy": "inputs larger than L2 (each GraphSum streams %.0f MB, features 561 MB; L2 is 126 MB)" % (alg / 1e6),
                        "parallelism": "single GPU", "dataset_gen_s": round(gen_s, 1), "scale": args.scale,
+                       "evaluation_layer0": "(A_hat X) W0 with A_hat X computed once at the first evaluation (its 38 GraphSum "
+                                            "slabs are part of e2e and of the warm-up, not of the timed steps): 5 GraphSum "
+                                            "calls per step instead of 6; GCNB_PROPAGATE=0 restores A_hat (X W0)",
                        "final_train_loss": last[0][0], "final_val_acc": last[1][1], "published_other_hw": PUBLISHED},
             "clocks": clk, "e2e": e2e, "gpu_launches": r["launches"], "roofline": roofline}
     g.close()

@@ -59,16 +59,29 @@ __global__ void dropout_maskbits_kernel(uint32_t *__restrict__ bits, int64_t siz
       const uint64_t pos0 = (uint64_t)e0 + lead;  // position counted from the first global group of this call
       const uint32_t g0 = (uint32_t)(pos0 >> 2);
       const int shift = (int)(pos0 & 3);          // bit b of the word is lane (b + shift) & 3 of group g0 + (b + shift) / 4
-#pragma unroll 1
-      for (int gi = 0; gi < 9; gi++) {
-        const int b_first = gi * 4 - shift;       // word bit of lane 0 of this group
-        if (b_first >= nvalid) break;
-        float u[4];
-        rng_uniform4(rng, g0 + gi, u);
+      if (shift == 0 && nvalid == 32) {
+        // the common case (full word on a group boundary): eight independent Philox chains in flight -- a Philox call is
+        // ten dependent multiply rounds, one chain at a time leaves the integer pipes idle
+        float u[8][4];
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-          const int b = b_first + k;
-          if (b >= 0 && b < nvalid && u[k] >= p) out |= 1u << b;
+        for (int gi = 0; gi < 8; gi++) rng_uniform4(rng, g0 + gi, u[gi]);
+#pragma unroll
+        for (int gi = 0; gi < 8; gi++)
+#pragma unroll
+          for (int k = 0; k < 4; k++)
+            if (u[gi][k] >= p) out |= 1u << (gi * 4 + k);
+      } else {
+#pragma unroll 1
+        for (int gi = 0; gi < 9; gi++) {
+          const int b_first = gi * 4 - shift;       // word bit of lane 0 of this group
+          if (b_first >= nvalid) break;
+          float u[4];
+          rng_uniform4(rng, g0 + gi, u);
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const int b = b_first + k;
+            if (b >= 0 && b < nvalid && u[k] >= p) out |= 1u << b;
+          }
         }
       }
     }
