@@ -1,7 +1,9 @@
 // dense.cu -- tall-skinny fp32 products of the Matmul module (and of SparseMatmul when the feature matrix is
 // dense, as Reddit's 602 columns are).  Replaces matmul_kernel_forward / _backward_1 / _backward_2
 // (src/module.cu:274-391): 16x16 one-thread-per-element tiles there and atomicAdd for the weight gradient;
-// here a register-tiled FFMA kernel (fp32 parity bar 1e-5 rules out TF32) and a split-K weight-gradient
+// here a register-tiled FFMA kernel (plain TF32 would miss the fp32 parity bar of 1e-5; a 3xTF32 mma.sync variant of
+// this tiling was measured for the wide model -- DESIGN.md section 8 -- and is not kept: without a cp.async pipeline it
+// is no faster than the FFMA kernel once its accumulation chains are bounded) and a split-K weight-gradient
 // kernel whose slab partials are reduced in ascending order by a second pass (deterministic).
 //
 // One abstract problem  C[M x N] = sum_k A'(i,k) * B'(k,j)  with three operand layouts:
@@ -9,6 +11,7 @@
 //   NT: A'(i,k)=dC[i*K+k]     B'(k,j)=B[j*K+k]   (M=m rows, N=n, K=p)
 //   TN: A'(i,k)=A[k*M+i]      B'(k,j)=dC[k*N+j]  (M=n, N=p, K=m rows, split over slabs of K)
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 

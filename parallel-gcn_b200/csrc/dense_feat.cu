@@ -416,6 +416,9 @@ dense_feat_fwd_mma_kernel(const float *__restrict__ X, const uint32_t *__restric
     const float *xa = tile + (size_t)g * F + wib * KSP * 8 + t;  // (row g, first k of this warp)
     const float *xb = xa + (size_t)8 * F;                        // row g + 8
     const int ia = ((int)(ht & 1) * HR + g) * F + wib * KSP * 8 + t, ib = ia + 8 * F;  // the same elements' mask bits
+    // The tensor core adds into its fp32 accumulator with truncation, so long in-place chains drift.  Here a chain is
+    // at most 3 * KSP = 30 mma (the accumulators restart from zero for every half-tile and the eight warps' partial sums
+    // are added with rounded FADDs below): <= ~2e-6 relative in the worst case, measured well inside the 1e-5 bar.
     float c[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
     const int nq = min(KSP, (F + 7) / 8 - wib * KSP);  // k-steps of this warp that start below F (warp-uniform)
 #pragma unroll
@@ -521,6 +524,15 @@ dense_feat_tn_mma_kernel(const float *__restrict__ X, const uint32_t *__restrict
     mbar_wait(&bars[s], (uint32_t)((it / kStages) & 1));
     const int nrows = (int)min((int64_t)HR, N - ht * HR);
     const int mrow = (int)(ht & 1) * HR;
+    // per half-tile partial sums (six mma per fragment from zero), then one rounded FADD into the running sums: the
+    // tensor core's truncating accumulation would drift over the ~100 half-tiles a CTA walks
+    float part[MT][2][4];
+#pragma unroll
+    for (int m = 0; m < MT; m++)
+#pragma unroll
+      for (int j = 0; j < 2; j++)
+#pragma unroll
+        for (int q = 0; q < 4; q++) part[m][j][q] = 0.f;
 #pragma unroll
     for (int ks = 0; ks < 2; ks++) {
       const int ra = ks * 8 + t, rb = ra + 4;  // rows (k) of this lane's fragment elements
@@ -550,13 +562,19 @@ dense_feat_tn_mma_kernel(const float *__restrict__ X, const uint32_t *__restrict
           for (int q = 0; q < 4; q++) split_trunc(x[q], ah[q], al[q]);
 #pragma unroll
           for (int j = 0; j < 2; j++) {
-            mma_tf32(c[m][j], al, bh[j][0], bh[j][1]);
-            mma_tf32(c[m][j], ah, bl[j][0], bl[j][1]);
-            mma_tf32(c[m][j], ah, bh[j][0], bh[j][1]);
+            mma_tf32(part[m][j], al, bh[j][0], bh[j][1]);
+            mma_tf32(part[m][j], ah, bl[j][0], bl[j][1]);
+            mma_tf32(part[m][j], ah, bh[j][0], bh[j][1]);
           }
         }
       }
     }
+#pragma unroll
+    for (int m = 0; m < MT; m++)
+#pragma unroll
+      for (int j = 0; j < 2; j++)
+#pragma unroll
+        for (int q = 0; q < 4; q++) c[m][j][q] += part[m][j][q];
     __syncthreads();  // every warp is done with this stage
     if (threadIdx.x == 0) {
       const int64_t hn = ht + (int64_t)kStages * stride;
