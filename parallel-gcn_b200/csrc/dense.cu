@@ -105,6 +105,62 @@ sgemm_kernel(const float *__restrict__ A, const float *__restrict__ B, float *__
   }
 }
 
+// Weight gradient of a NARROW layer (n <= 32 inputs, p <= 64 outputs: the 16 -> 41 layer of the Part-1 model), where the
+// 64 x 64 tiles of the kernel above are 16 % full: dB[n x p] = A[m x n]^T * dC[m x p] is an outer product per row, 53 MB of
+// input for 656 outputs.  CTA = 4 groups of 64 threads; thread (grp, j) keeps column j of dB (n sums) in registers and
+// walks the rows r = grp (mod 4) of its CTA's row slab: one LDS for dC[r][j], n/4 broadcast LDS.128 for A[r][*], n FMA.
+// Groups are added in order through shared memory, CTAs by slab_reduce_kernel: fixed order, deterministic.
+template <int NMAX>
+__global__ void __launch_bounds__(256)
+tn_narrow_kernel(const float *__restrict__ A, const float *__restrict__ dC, float *__restrict__ ws, int64_t m, int n, int p,
+                 int64_t rows_per_cta) {
+  constexpr int TR = 64;
+  __shared__ __align__(16) float As[TR][NMAX];
+  __shared__ float Gs[TR][64];
+  __shared__ float red[3][NMAX][64];  // groups 1..3; group 0 adds them to its registers
+  const int tid = threadIdx.x, grp = tid >> 6, j = tid & 63;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta, r1 = min(m, r0 + rows_per_cta);
+  float acc[NMAX];
+#pragma unroll
+  for (int i = 0; i < NMAX; i++) acc[i] = 0.f;
+  for (int64_t base = r0; base < r1; base += TR) {
+    const int nr = (int)min((int64_t)TR, r1 - base);
+    for (int e = tid; e < TR * NMAX; e += 256) {
+      const int r = e / NMAX, i = e % NMAX;
+      As[r][i] = (r < nr && i < n) ? __ldg(A + (size_t)(base + r) * n + i) : 0.f;
+    }
+    for (int e = tid; e < TR * 64; e += 256) {
+      const int r = e >> 6, c = e & 63;
+      Gs[r][c] = (r < nr && c < p) ? __ldg(dC + (size_t)(base + r) * p + c) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int r = grp; r < TR; r += 4) {  // rows beyond nr hold zeros
+      const float gval = Gs[r][j];
+#pragma unroll
+      for (int i4 = 0; i4 < NMAX / 4; i4++) {
+        const float4 a = *reinterpret_cast<const float4 *>(&As[r][i4 * 4]);
+        acc[i4 * 4 + 0] = fmaf(a.x, gval, acc[i4 * 4 + 0]);
+        acc[i4 * 4 + 1] = fmaf(a.y, gval, acc[i4 * 4 + 1]);
+        acc[i4 * 4 + 2] = fmaf(a.z, gval, acc[i4 * 4 + 2]);
+        acc[i4 * 4 + 3] = fmaf(a.w, gval, acc[i4 * 4 + 3]);
+      }
+    }
+    __syncthreads();
+  }
+  if (grp > 0) {
+#pragma unroll
+    for (int i = 0; i < NMAX; i++) red[grp - 1][i][j] = acc[i];
+  }
+  __syncthreads();
+  if (grp == 0 && j < p) {
+    float *dst = ws + (size_t)blockIdx.x * n * p;
+#pragma unroll
+    for (int i = 0; i < NMAX; i++)
+      if (i < n) dst[(size_t)i * p + j] = ((acc[i] + red[0][i][j]) + red[1][i][j]) + red[2][i][j];
+  }
+}
+
 // dB = sum over slabs, ascending (fixed order)
 __global__ void slab_reduce_kernel(const float *__restrict__ ws, float *__restrict__ out, int64_t elems, int slabs) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < elems; i += (int64_t)gridDim.x * blockDim.x) {
@@ -184,6 +240,20 @@ int gcnb_matmul_tn_f32(const float *d_A, const float *d_dC, float *d_dB, int64_t
   }
   const TnShape sh = tn_shape(m, n, p);
   if (!d_ws || ws_bytes < (int64_t)sh.slabs * n * p * 4) return GCNB_E_BADARG;
+  if (n <= 32 && p <= 64 && m >= 4096) {
+    const int sm = std::max(1, device_info().sm_count);
+    const int ctas = (int)std::min<int64_t>(std::min<int64_t>(2 * sm, sh.slabs), (m + 255) / 256);
+    const int64_t rows_per_cta = ((m + ctas - 1) / ctas + 3) / 4 * 4;
+    const int used = (int)((m + rows_per_cta - 1) / rows_per_cta);
+    if (n <= 16) tn_narrow_kernel<16><<<used, 256, 0, stream>>>(d_A, d_dC, (float *)d_ws, m, n, p, rows_per_cta);
+    else tn_narrow_kernel<32><<<used, 256, 0, stream>>>(d_A, d_dC, (float *)d_ws, m, n, p, rows_per_cta);
+    GCNB_LAUNCH_CHECK();
+    const int64_t elems = (int64_t)n * p;
+    slab_reduce_kernel<<<(int)std::min<int64_t>((elems + 255) / 256, 4096), 256, 0, stream>>>((const float *)d_ws, d_dB, elems,
+                                                                                              used);
+    GCNB_LAUNCH_CHECK();
+    return 0;
+  }
   constexpr int BM = 64, BN = 64, BK = 16, TM = 4, TN = 4;
   dim3 grid(sh.tiles_m, sh.tiles_n, sh.slabs);
   sgemm_kernel<BM, BN, BK, TM, TN, MODE_TN><<<grid, 256, 0, stream>>>(d_A, d_dC, (float *)d_ws, n, p, m, sh.k_slab);

@@ -277,7 +277,8 @@ def test_csc_dense_detection(gcnb, dev):
 
 
 @pytest.mark.parametrize("m,n,p", [(2708, 16, 7), (3327, 16, 6), (5000, 16, 41), (1000, 72, 7), (777, 602, 16),
-                                   (513, 600, 41), (300, 130, 70), (1, 16, 41), (129, 1, 1), (1500, 602, 600), (260, 64, 33)])
+                                   (513, 600, 41), (300, 130, 70), (1, 16, 41), (129, 1, 1), (1500, 602, 600), (260, 64, 33),
+                                   (20011, 16, 41), (9000, 30, 64), (4097, 7, 3)])
 def test_matmul_nn_nt_tn(O, gcnb, dev, m, n, p):
     import torch
     rng = np.random.default_rng(m + n + p)
