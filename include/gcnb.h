@@ -64,9 +64,11 @@ GCNB_API int gcnb_spmm_plan_info(const gcnb_spmm_plan *plan, int64_t out[8]);
  * with 16-bit window-local column ids and a copy of their values; the rest stays a (smaller) CSR.  Later
  * gcnb_spmm_f32 calls with the SAME d_values pointer, this dim and no permutation run the staged kernel + the generic
  * kernel on the remainder; any other call is unaffected.  h_indptr / h_indices: host copies of the plan's CSR arrays,
- * or NULL to have them copied back from the device.  Only dim == 16 is staged today (other dims: no-op, returns 0);
- * graphs without column locality (< 25 % of the entries stageable) are left on the generic kernel.  Calling it again
- * with a new value array re-gathers the packed values only. */
+ * or NULL to have them copied back from the device.  The representation is built for dim == 16 (other dims: no-op,
+ * returns 0); products of width 16 and of any width >= 64 then use it (wide operands run as 16-column slabs, see
+ * gcnb_spmm_ld_f32).  Graphs without column locality (< 25 % of the entries stageable) are left on the generic kernel
+ * (gcnb_reorder_communities, include/gcnb_engine.h, renumbers a graph so that its communities become contiguous).
+ * Calling it again with a new value array re-gathers the packed values only. */
 GCNB_API int gcnb_spmm_plan_stage(gcnb_spmm_plan *plan, const uint32_t *h_indptr, const uint32_t *h_indices,
                                   const float *d_values, int dim, gcnb_stream_t stream);
 /* same with the builder's knobs exposed (0 = default): window_rows <= 3072, min_seg = fewest entries of a row inside a
