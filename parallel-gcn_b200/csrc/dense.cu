@@ -242,7 +242,7 @@ int gcnb_matmul_tn_f32(const float *d_A, const float *d_dC, float *d_dB, int64_t
   if (!d_ws || ws_bytes < (int64_t)sh.slabs * n * p * 4) return GCNB_E_BADARG;
   if (n <= 32 && p <= 64 && m >= 4096) {
     const int sm = std::max(1, device_info().sm_count);
-    const int ctas = (int)std::min<int64_t>(std::min<int64_t>(2 * sm, sh.slabs), (m + 255) / 256);
+    const int ctas = (int)std::min<int64_t>(std::min<int64_t>(4 * sm, sh.slabs), (m + 255) / 256);  // 4 per SM: the tile loads are synchronous
     const int64_t rows_per_cta = ((m + ctas - 1) / ctas + 3) / 4 * 4;
     const int used = (int)((m + rows_per_cta - 1) / rows_per_cta);
     if (n <= 16) tn_narrow_kernel<16><<<used, 256, 0, stream>>>(d_A, d_dC, (float *)d_ws, m, n, p, rows_per_cta);
