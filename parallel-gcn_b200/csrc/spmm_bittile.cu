@@ -1,0 +1,815 @@
+// spmm_bittile.cu -- bit-tile GraphSum for sm_100a: the DENSE BLOCKS of the normalised adjacency go through the 5th-gen
+// tensor cores (tcgen05.mma, accumulators in TMEM) as 0/1 bit maps; the rest stays a CSR on the generic kernel.
+//
+// Why: at 16 columns every gather formulation of  C = A_csr * B  is bound by the SM's LSU data pipe (half
+// a wavefront per gathered 64-byte row from shared memory, one from L1), not by HBM: 0.30 of the HBM roofline on the
+// Reddit-shape graph.  GraphSum's values factor: graph_value[i,j] = s_i * s_j with s = 1/sqrt(deg)
+// (src/parser.cpp:164-181), so  C = diag(s) * M * (diag(s) * B)  with M the 0/1 pattern.  Inside a community M is
+// dense enough (8 % on the bench graph) that a BIT MAP is the smaller encoding (1 bit per cell = 12 bits per entry
+// against 48 for a 16-bit id + fp32 value), and a 0/1 operand is exact in bf16, so the product  M * B'  can run on
+// the tensor cores WITHOUT losing fp32 accuracy: B' = s_j * B_j (fp32) is split into three bf16 pieces
+// (8 + 8 + 8 significand bits, hi + mid + lo == B' exactly), every product 1.0 * piece is exact and the sums are
+// accumulated in fp32.  No neighbour row is gathered at all.
+//
+// How: rows are cut into blocks of 128, columns into chunks of 64.  A TILE (row block x chunk) holding at least
+// min_tile_nnz entries that satisfy the factorisation becomes 128 x 64 bits (1 KB); all other entries (sparse tiles,
+// duplicate entries, values that are not s_i * s_j) form the REMAINDER CSR with their original values.  Per launch:
+//   bt_pack_kernel     B' = s_j * B_j split into bf16 hi | mid | lo, stored chunk by chunk as the K-major core-matrix
+//                      image tcgen05.mma reads from shared memory (48 x 16 per k-step, no swizzle); 96 bytes per row of B
+//   bt_mma_kernel      one persistent CTA per SM, warp-specialised:
+//                        warps 0-7   expand bit-map words into bf16 0/1 A operands and write them to TMEM (tcgen05.st):
+//                                    thread = row, 64 bits -> 32 packed registers with 2 integer ops per register
+//                        warp  12    streams the packed chunks of B' into an 8-stage shared-memory ring (cp.async.bulk)
+//                        warp  13    one thread issues tcgen05.mma.kind::f16, M = 128, N = 48 (3 pieces x 16 columns),
+//                                    K = 16, A from TMEM, B from shared memory, D in TMEM; tcgen05.commit frees stages
+//                        warps 8-11  epilogue: tcgen05.ld the accumulators, add pieces small to large, scale by s_i,
+//                                    store the block's partial rows
+//                      Chains are bounded: the tiles of a row block rotate over 4 accumulators that the epilogue adds
+//                      with rounded fp32 adds (the tensor core's accumulate truncates).
+//   generic kernel     remainder CSR on a second stream, concurrently (it lives on the LSU pipe, the MMA path does not)
+//   bt_add_kernel      C = P + R
+// Summation order is fixed by the plan => bit-reproducible run to run.  Relative to the CSR product the result differs
+// by the rounding of s_i * s_j against 1/sqrtf(deg_i * deg_j) and by the summation order (~1e-6 relative; parity bar 1e-5).
+//
+// Reference being replaced: graphsum_kernel, src/module.cu:172-186.
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <queue>
+#include <thread>
+#include <vector>
+
+#include "bulk.cuh"
+#include "common.cuh"
+#include "spmm_plan.cuh"
+
+using namespace gcnb;
+
+namespace gcnb {
+
+constexpr int kBtRows = 128;                 // rows per block = MMA M = TMEM lanes
+constexpr int kBtChunk = 64;                 // columns per tile = 4 MMA k-steps of 16
+constexpr int kBtN = 48;                     // MMA N: 3 bf16 pieces x 16 columns
+constexpr int kBtKStepBytes = kBtN * 16 * 2; // 1536: one 48 x 16 bf16 operand
+constexpr int kBtChunkBytes = 4 * kBtKStepBytes;  // 6144 bytes of packed B' per chunk
+constexpr int kBtBStages = 8;
+constexpr int kBtAStages = 4;                // x 32 TMEM columns
+constexpr int kBtAcc = 4;                    // accumulators per set (x 48 TMEM columns), two sets
+constexpr int kBtAccCol0 = kBtAStages * 32;  // 128
+constexpr int kBtThreads = 14 * 32;
+
+// Host-side plan (pure CPU; unit-tested without a GPU through gcnb_bittile_host_*).
+//   CTA q processes tiles [cta_tile_ptr[q], cta_tile_ptr[q+1]) in order; they belong to its items
+//   [cta_item_ptr[q], cta_item_ptr[q+1]);  items[k] = (row block, end position of the block's tiles RELATIVE to the
+//   CTA's first tile).  tile_chunk[t] = column chunk of tile t; bits[t*128 + r] = the 64 cells of row r of tile t:
+//   low word = columns 0..31, high word = columns 32..63; inside a word column c sits at bit (c >> 1) + 16 * (c & 1),
+//   which lets register q of the expansion (columns 2q, 2q+1 as a bf16 pair) be  (word & (0x00010001 << q)) * (0x3F80 >> q).
+struct BitTileHost {
+  int64_t n_rows = 0, n_cols = 0, nnz = 0, n_blk = 0, n_tiles = 0, tile_nnz = 0;
+  int n_cta = 0, min_tile_nnz = 0;
+  std::vector<uint32_t> tile_chunk, cta_tile_ptr, cta_item_ptr;
+  std::vector<uint2> items;
+  HostArray<uint64_t> bits;
+  std::vector<uint32_t> r_indptr;
+  HostArray<uint32_t> r_indices;
+  HostArray<float> r_values;
+  std::vector<float> row_scale, col_scale;
+};
+
+namespace {
+
+template <class F>
+void bt_run_threads(int T, F f) {
+  std::vector<std::thread> th;
+  for (int t = 1; t < T; t++) th.emplace_back([&f, t] { f(t); });
+  f(0);
+  for (auto &x : th) x.join();
+}
+
+inline int bt_bit_of_col(uint32_t c) {  // c in [0, 64)
+  const uint32_t cc = c & 31u;
+  return (int)((c & 32u) + (cc >> 1) + 16u * (cc & 1u));
+}
+
+struct BlockOut {
+  std::vector<uint32_t> chunks;
+  std::vector<uint64_t> bits;
+  std::vector<uint32_t> ridx;
+  std::vector<float> rval;
+  uint32_t rcount[kBtRows];
+  int64_t tile_nnz = 0;
+};
+
+}  // namespace
+
+int bittile_build_host(const uint32_t *indptr, const uint32_t *indices, const float *values, int64_t n_rows, int64_t n_cols,
+                       const float *row_scale, const float *col_scale, int min_tile_nnz, int n_cta, int n_threads,
+                       BitTileHost &H) {
+  if (!indptr || (!indices && indptr[n_rows] > 0) || (!values && indptr[n_rows] > 0) || n_rows < 0 || n_cols < 0 ||
+      n_rows > 0xfffffff0ll || n_cols > 0xfffffff0ll)
+    return GCNB_E_BADARG;
+  if ((row_scale == nullptr) != (col_scale == nullptr)) return GCNB_E_BADARG;
+  H.n_rows = n_rows;
+  H.n_cols = n_cols;
+  H.nnz = indptr[n_rows];
+  H.n_cta = n_cta > 0 ? n_cta : 148;
+  H.min_tile_nnz = min_tile_nnz > 0 ? min_tile_nnz : 128;
+  H.n_blk = (n_rows + kBtRows - 1) / kBtRows;
+  const int64_t n_chunks = (n_cols + kBtChunk - 1) / kBtChunk;
+  int T = n_threads > 0 ? n_threads : (int)std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency()));
+  T = (int)std::max<int64_t>(1, std::min<int64_t>(T, H.n_blk));
+
+  // scales: given, or the square roots of the diagonal entries (GraphSum: value[i,i] = 1/deg_i, s_i = 1/sqrt(deg_i));
+  // a row without a usable diagonal gets NaN, which fails every factorisation check => its entries stay in the remainder
+  H.row_scale.assign((size_t)n_rows, 0.f);
+  H.col_scale.assign((size_t)n_cols, 0.f);
+  if (row_scale) {
+    std::copy(row_scale, row_scale + n_rows, H.row_scale.begin());
+    std::copy(col_scale, col_scale + n_cols, H.col_scale.begin());
+  } else {
+    const float nan = std::nanf("");
+    std::fill(H.col_scale.begin(), H.col_scale.end(), nan);
+    if (n_rows == n_cols) {
+      bt_run_threads(T, [&](int t) {
+        for (int64_t i = t; i < n_rows; i += T) {
+          float s = nan;
+          for (uint32_t e = indptr[i]; e < indptr[i + 1]; e++)
+            if (indices[e] == (uint32_t)i) {
+              if (values[e] > 0.f) s = sqrtf(values[e]);
+              break;
+            }
+          H.col_scale[(size_t)i] = s;
+        }
+      });
+    }
+    H.row_scale = H.col_scale;
+    H.row_scale.resize((size_t)n_rows, nan);
+  }
+
+  std::vector<BlockOut> blocks((size_t)H.n_blk);
+  std::atomic<int64_t> next{0};
+  const uint32_t thr = (uint32_t)H.min_tile_nnz;
+  bt_run_threads(T, [&](int) {
+    std::vector<uint32_t> cnt((size_t)n_chunks, 0u), touched;
+    std::vector<int32_t> sel((size_t)n_chunks, -1);
+    for (;;) {
+      const int64_t b = next.fetch_add(1);
+      if (b >= H.n_blk) break;
+      BlockOut &o = blocks[(size_t)b];
+      const int64_t r0 = b * kBtRows, r1 = std::min<int64_t>(n_rows, r0 + kBtRows);
+      touched.clear();
+      for (uint32_t e = indptr[r0]; e < indptr[r1]; e++) {
+        const uint32_t c = indices[e] >> 6;
+        if (cnt[c]++ == 0) touched.push_back(c);
+      }
+      std::sort(touched.begin(), touched.end());
+      for (uint32_t c : touched) {
+        if (cnt[c] >= thr) {
+          sel[c] = (int32_t)o.chunks.size();
+          o.chunks.push_back(c);
+        }
+      }
+      o.bits.assign(o.chunks.size() * (size_t)kBtRows, 0ull);
+      for (int64_t i = r0; i < r1; i++) {
+        const int rl = (int)(i - r0);
+        uint32_t rc = 0;
+        const float si = H.row_scale[(size_t)i];
+        for (uint32_t e = indptr[i]; e < indptr[i + 1]; e++) {
+          const uint32_t j = indices[e];
+          const float v = values[e];
+          const int32_t li = sel[j >> 6];
+          bool in_tile = false;
+          if (li >= 0) {
+            const float p = si * H.col_scale[j];
+            if (fabsf(v - p) <= 1e-6f * fabsf(v)) {  // false for NaN scales
+              uint64_t &w = o.bits[(size_t)li * kBtRows + rl];
+              const uint64_t m = 1ull << bt_bit_of_col(j & 63u);
+              if (!(w & m)) {  // a duplicate entry cannot be a second bit: remainder
+                w |= m;
+                in_tile = true;
+              }
+            }
+          }
+          if (in_tile) {
+            o.tile_nnz++;
+          } else {
+            o.ridx.push_back(j);
+            o.rval.push_back(v);
+            rc++;
+          }
+        }
+        o.rcount[rl] = rc;
+      }
+      for (uint32_t c : touched) {
+        cnt[c] = 0;
+        sel[c] = -1;
+      }
+    }
+  });
+
+  // CTA schedule: longest-processing-time greedy over the row blocks that own tiles (cost = tiles + a per-block
+  // constant for the epilogue and the pipeline drain); deterministic
+  std::vector<uint32_t> order;
+  for (int64_t b = 0; b < H.n_blk; b++)
+    if (!blocks[(size_t)b].chunks.empty()) order.push_back((uint32_t)b);
+  std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+    return blocks[a].chunks.size() > blocks[b].chunks.size();
+  });
+  std::vector<std::vector<uint32_t>> per_cta((size_t)H.n_cta);
+  {
+    typedef std::pair<uint64_t, int> Load;  // (load, cta): smallest load first, ties by CTA index
+    std::priority_queue<Load, std::vector<Load>, std::greater<Load>> pq;
+    for (int q = 0; q < H.n_cta; q++) pq.push(Load(0, q));
+    for (uint32_t b : order) {
+      Load l = pq.top();
+      pq.pop();
+      per_cta[(size_t)l.second].push_back(b);
+      l.first += blocks[b].chunks.size() + 6;
+      pq.push(l);
+    }
+  }
+  H.cta_tile_ptr.assign((size_t)H.n_cta + 1, 0u);
+  H.cta_item_ptr.assign((size_t)H.n_cta + 1, 0u);
+  H.items.clear();
+  std::vector<uint64_t> tile_base((size_t)H.n_blk, 0ull);
+  uint64_t tiles = 0;
+  for (int q = 0; q < H.n_cta; q++) {
+    H.cta_tile_ptr[(size_t)q] = (uint32_t)tiles;
+    H.cta_item_ptr[(size_t)q] = (uint32_t)H.items.size();
+    uint32_t pos = 0;
+    for (uint32_t b : per_cta[(size_t)q]) {
+      tile_base[b] = tiles + pos;
+      pos += (uint32_t)blocks[b].chunks.size();
+      H.items.push_back(make_uint2(b, pos));
+    }
+    tiles += pos;
+    if (tiles > 0xfffffff0ull) return GCNB_E_BADARG;
+  }
+  H.cta_tile_ptr[(size_t)H.n_cta] = (uint32_t)tiles;
+  H.cta_item_ptr[(size_t)H.n_cta] = (uint32_t)H.items.size();
+  H.n_tiles = (int64_t)tiles;
+  H.tile_chunk.assign((size_t)tiles, 0u);
+  H.bits.alloc((size_t)tiles * kBtRows);
+
+  // remainder CSR offsets
+  H.r_indptr.assign((size_t)n_rows + 1, 0u);
+  uint64_t racc = 0;
+  H.tile_nnz = 0;
+  for (int64_t b = 0; b < H.n_blk; b++) {
+    const BlockOut &o = blocks[(size_t)b];
+    const int64_t r0 = b * kBtRows, r1 = std::min<int64_t>(n_rows, r0 + kBtRows);
+    for (int64_t i = r0; i < r1; i++) {
+      H.r_indptr[(size_t)i] = (uint32_t)racc;
+      racc += o.rcount[i - r0];
+    }
+    H.tile_nnz += o.tile_nnz;
+  }
+  H.r_indptr[(size_t)n_rows] = (uint32_t)racc;
+  H.r_indices.alloc((size_t)racc);
+  H.r_values.alloc((size_t)racc);
+  next = 0;
+  bt_run_threads(T, [&](int) {
+    for (;;) {
+      const int64_t b = next.fetch_add(1);
+      if (b >= H.n_blk) break;
+      BlockOut &o = blocks[(size_t)b];
+      if (!o.chunks.empty()) {
+        std::copy(o.chunks.begin(), o.chunks.end(), H.tile_chunk.begin() + (ptrdiff_t)tile_base[(size_t)b]);
+        memcpy(H.bits.data() + tile_base[(size_t)b] * kBtRows, o.bits.data(), o.bits.size() * sizeof(uint64_t));
+      }
+      if (!o.ridx.empty()) {
+        const size_t at = H.r_indptr[(size_t)(b * kBtRows)];
+        memcpy(H.r_indices.data() + at, o.ridx.data(), o.ridx.size() * 4);
+        memcpy(H.r_values.data() + at, o.rval.data(), o.rval.size() * 4);
+      }
+      BlockOut().chunks.swap(o.chunks);
+      std::vector<uint64_t>().swap(o.bits);
+      std::vector<uint32_t>().swap(o.ridx);
+      std::vector<float>().swap(o.rval);
+    }
+  });
+  // the kernels multiply by the scales unconditionally: rows / columns without a usable scale own no bit, give them 0
+  for (float &x : H.row_scale)
+    if (!(fabsf(x) <= 3.0e38f)) x = 0.f;
+  for (float &x : H.col_scale)
+    if (!(fabsf(x) <= 3.0e38f)) x = 0.f;
+  return 0;
+}
+
+// =====================================================================================================================
+// device
+// =====================================================================================================================
+
+// ---- tcgen05 / TMEM plumbing (PTX ISA 8.7+, sm_100a) ----------------------------------------------------------------
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// tcgen05.commit: the mbarrier gets one arrival when every tcgen05.mma issued so far by this thread has completed
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem descriptor]; kind::f16 covers bf16 inputs with fp32 accumulate
+__device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
+      "[%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
+}
+
+// instruction descriptor of tcgen05.mma.kind::f16: D fp32, A and B bf16, both K-major, N = 48, M = 128
+constexpr uint32_t kBtIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kBtN >> 3) << 17) | ((uint32_t)(kBtRows >> 4) << 24);
+// shared-memory matrix descriptor of one 48 x 16 bf16 operand, K-major, no swizzle: core matrices (8 rows x 16 bytes) of
+// one k-half are contiguous (stride 128 bytes between 8-row groups = SBO), the second k-half follows 768 bytes later (LBO)
+__device__ __forceinline__ uint64_t bt_b_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)(768 >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) | (1ull << 46);
+}
+
+struct BtArgs {
+  const uint32_t *tile_chunk;
+  const uint64_t *bits;
+  const uint32_t *cta_tile_ptr;
+  const uint32_t *cta_item_ptr;
+  const uint2 *items;
+  const uint8_t *packed;    // chunks of kBtChunkBytes
+  const float *row_scale;
+  float *P;                 // [n_blk * 128][16]
+  int64_t n_rows;
+};
+
+// B' = col_scale[j] * B[j][:] split into bf16 hi | mid | lo (truncation, exact sum) in the operand layout of the MMA:
+// chunk c, k-step ks, element (n = piece*16 + col, k) at  c*6144 + ks*1536 + (k/8)*768 + (n/8)*128 + (n%8)*16 + (k%8)*2.
+// One thread = 8 consecutive rows of B x one column: three 16-byte stores.
+__global__ void __launch_bounds__(256) bt_pack_kernel(const float *__restrict__ B, const float *__restrict__ col_scale,
+                                                      uint8_t *__restrict__ packed, int64_t n_cols, int64_t n_groups) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t g = tid >> 4;
+  const int col = (int)(tid & 15);
+  if (g >= n_groups) return;
+  const int64_t j0 = g * 8;
+  uint32_t hi[4], mid[4], lo[4];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const int64_t j = j0 + i;
+    float x = 0.f;
+    if (j < n_cols) x = __ldg(col_scale + j) * __ldg(B + j * 16 + col);
+    const uint32_t xb = __float_as_uint(x);
+    const uint32_t hb = xb & 0xffff0000u;
+    const float r1 = x - __uint_as_float(hb);
+    const uint32_t mb = __float_as_uint(r1) & 0xffff0000u;
+    const float r2 = r1 - __uint_as_float(mb);
+    const uint32_t lb = __float_as_uint(r2) & 0xffff0000u;
+    if (i & 1) {
+      hi[i >> 1] |= hb;
+      mid[i >> 1] |= mb;
+      lo[i >> 1] |= lb;
+    } else {
+      hi[i >> 1] = hb >> 16;
+      mid[i >> 1] = mb >> 16;
+      lo[i >> 1] = lb >> 16;
+    }
+  }
+  const int64_t c = j0 >> 6;
+  const int kl = (int)(j0 & 63);
+  uint8_t *base = packed + c * kBtChunkBytes + (kl >> 4) * kBtKStepBytes + ((kl >> 3) & 1) * 768;
+  const int n0 = col;  // piece p: n = p*16 + col
+#pragma unroll
+  for (int p = 0; p < 3; p++) {
+    const int n = p * 16 + n0;
+    uint4 v;
+    const uint32_t *src = p == 0 ? hi : (p == 1 ? mid : lo);
+    v.x = src[0]; v.y = src[1]; v.z = src[2]; v.w = src[3];
+    *reinterpret_cast<uint4 *>(base + (n >> 3) * 128 + (n & 7) * 16) = v;
+  }
+}
+
+__device__ __forceinline__ uint64_t bt_ld_bits(const uint64_t *p) {
+  uint64_t v;
+  asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p));
+  return v;
+}
+
+// 32 bits -> 16 registers of two bf16 (0.0 or 1.0) each; bit q and bit q+16 of the word are the pair of register q
+__device__ __forceinline__ void bt_expand_word(uint32_t w, uint32_t *r) {
+  const uint32_t w8 = w >> 8;
+#pragma unroll
+  for (int q = 0; q < 8; q++) {
+    r[q] = (w & (0x00010001u << q)) * (0x3F80u >> q);
+    r[q + 8] = (w8 & (0x00010001u << q)) * (0x3F80u >> q);
+  }
+}
+
+__global__ void __maxnreg__(72) bt_mma_kernel(BtArgs a) {  // 448 threads x 72 registers leave half the register file to the remainder kernel
+  extern __shared__ __align__(128) uint8_t bt_smem[];
+  // layout: B stages | barriers | tmem base
+  uint8_t *smem_b = bt_smem;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(bt_smem + kBtBStages * kBtChunkBytes);
+  uint64_t *b_full = bars, *b_empty = bars + kBtBStages;
+  uint64_t *a_full = bars + 2 * kBtBStages, *a_empty = a_full + kBtAStages;
+  uint64_t *acc_full = a_empty + kBtAStages, *acc_empty = acc_full + 2;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = blockIdx.x;
+  const uint32_t tile0 = a.cta_tile_ptr[q];
+  const uint32_t T = a.cta_tile_ptr[q + 1] - tile0;
+  const uint32_t item0 = a.cta_item_ptr[q], item1 = a.cta_item_ptr[q + 1];
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kBtBStages; i++) {
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_empty[i], 1);
+    }
+    for (int i = 0; i < kBtAStages; i++) {
+      mbar_init(&a_full[i], 4);
+      mbar_init(&a_empty[i], 1);
+    }
+    for (int i = 0; i < 2; i++) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 13) {  // the MMA warp owns the TMEM allocation (all 512 columns: one CTA per SM)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t *>(tmem_slot);
+
+  if (warp < 8) {
+    // ---- expanders: warp = (group g = warp >> 2) x (lane quarter = warp & 3); group g takes positions t = g, g+2, ...
+    const int quarter = warp & 3, g = warp >> 2;
+    const uint64_t *bp = a.bits + (size_t)tile0 * kBtRows + quarter * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    uint32_t t = (uint32_t)g;
+    uint64_t w0 = t < T ? bt_ld_bits(bp + (size_t)t * kBtRows) : 0ull;
+    uint64_t w1 = t + 2 < T ? bt_ld_bits(bp + (size_t)(t + 2) * kBtRows) : 0ull;
+    uint64_t w2 = t + 4 < T ? bt_ld_bits(bp + (size_t)(t + 4) * kBtRows) : 0ull;
+    for (; t < T; t += 2) {
+      const uint64_t w3 = t + 6 < T ? bt_ld_bits(bp + (size_t)(t + 6) * kBtRows) : 0ull;
+      const uint32_t s = t % kBtAStages, use = t / kBtAStages;
+      uint32_t r[32];
+      bt_expand_word((uint32_t)w0, r);
+      bt_expand_word((uint32_t)(w0 >> 32), r + 16);
+      if (use > 0) mbar_wait(&a_empty[s], (use - 1) & 1);  // the MMAs that read this stage's previous content are done
+      tc_fence_after();
+      tc_st32(tmem + lane_base + s * 32, r);
+      tc_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&a_full[s]);
+      w0 = w1;
+      w1 = w2;
+      w2 = w3;
+    }
+  } else if (warp < 12) {
+    // ---- epilogue: thread = row (TMEM lane) of the block
+    const int quarter = warp & 3;
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    uint32_t prev_end = 0;
+    for (uint32_t it = item0; it < item1; it++) {
+      const uint2 item = a.items[it];
+      const uint32_t n_tiles = item.y - prev_end;
+      prev_end = item.y;
+      const uint32_t k = it - item0, set = k & 1, use = k >> 1;
+      const int64_t row = (int64_t)item.x * kBtRows + quarter * 32 + lane;
+      const float sc = row < a.n_rows ? __ldg(a.row_scale + row) : 0.f;
+      mbar_wait(&acc_full[set], use & 1);
+      tc_fence_after();
+      const uint32_t acc0 = tmem + lane_base + kBtAccCol0 + set * (kBtAcc * kBtN);
+      // one accumulator at a time (the next row block's MMAs run meanwhile on the other set; registers are what the
+      // co-resident remainder kernel needs): piece sums ((a0 + a1) + a2) + a3, then (lo + mid) + hi
+      float tot[16];
+#pragma unroll
+      for (int p = 2; p >= 0; p--) {
+        float s[16];
+        tc_ld16(acc0 + p * 16, s);
+        tc_wait_ld();
+        for (uint32_t c = 1; c < (uint32_t)kBtAcc && c < n_tiles; c++) {
+          float v[16];
+          tc_ld16(acc0 + c * kBtN + p * 16, v);
+          tc_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 16; i++) s[i] += v[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 16; i++) tot[i] = p == 2 ? s[i] : tot[i] + s[i];
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[set]);
+      float4 *dst = reinterpret_cast<float4 *>(a.P + row * 16);
+#pragma unroll
+      for (int i = 0; i < 4; i++)  // rows past n_rows exist in P (padded to whole blocks) and receive 0
+        dst[i] = make_float4(sc * tot[4 * i], sc * tot[4 * i + 1], sc * tot[4 * i + 2], sc * tot[4 * i + 3]);
+    }
+  } else if (warp == 12) {
+    // ---- producer of B': chunk ids are read 32 at a time, lane 0 issues the bulk copies
+    for (uint32_t base = 0; base < T; base += 32) {
+      const uint32_t mine = base + lane < T ? __ldg(a.tile_chunk + tile0 + base + lane) : 0u;
+      const uint32_t cnt = min(32u, T - base);
+      for (uint32_t k = 0; k < cnt; k++) {
+        const uint32_t c = __shfl_sync(0xffffffffu, mine, (int)k);
+        if (lane == 0) {
+          const uint32_t t = base + k, s = t % kBtBStages, use = t / kBtBStages;
+          if (use > 0) mbar_wait(&b_empty[s], (use - 1) & 1);
+          mbar_expect_tx(&b_full[s], kBtChunkBytes);
+          bulk_g2s(smem_b + s * kBtChunkBytes, a.packed + (size_t)c * kBtChunkBytes, kBtChunkBytes, &b_full[s]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (lane == 0) {
+    // ---- MMA issuer (one thread)
+    uint32_t t = 0;
+    uint2 item = item0 < item1 ? a.items[item0] : make_uint2(0, 0);
+    for (uint32_t it = item0; it < item1; it++) {
+      const uint2 next_item = it + 1 < item1 ? a.items[it + 1] : make_uint2(0, 0);
+      const uint32_t k = it - item0, set = k & 1, use = k >> 1;
+      if (use > 0) mbar_wait(&acc_empty[set], (use - 1) & 1);  // the epilogue has drained this accumulator set
+      tc_fence_after();
+      const uint32_t t_begin = t;
+      for (; t < item.y; t++) {
+        const uint32_t sa = t % kBtAStages, ua = t / kBtAStages, sb = t % kBtBStages, ub = t / kBtBStages;
+        mbar_wait(&a_full[sa], ua & 1);
+        mbar_wait(&b_full[sb], ub & 1);
+        tc_fence_after();
+        const uint32_t idx = t - t_begin;
+        const uint32_t d = tmem + kBtAccCol0 + set * (kBtAcc * kBtN) + (idx % kBtAcc) * kBtN;
+        const uint32_t b_addr = smem_u32(smem_b + sb * kBtChunkBytes);
+#pragma unroll
+        for (int ks = 0; ks < 4; ks++)
+          tc_mma_ts(d, tmem + sa * 32 + ks * 8, bt_b_desc(b_addr + ks * kBtKStepBytes), kBtIdesc,
+                    (ks > 0 || idx >= (uint32_t)kBtAcc) ? 1u : 0u);
+        tc_commit(&a_empty[sa]);
+        tc_commit(&b_empty[sb]);
+      }
+      tc_commit(&acc_full[set]);
+      item = next_item;
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 13) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
+}
+
+__global__ void __launch_bounds__(256) bt_add_kernel(const float4 *__restrict__ P, const float4 *__restrict__ R,
+                                                     float4 *__restrict__ C, int64_t n4) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 p = P[i], r = R[i];
+    C[i] = make_float4(p.x + r.x, p.y + r.y, p.z + r.z, p.w + r.w);
+  }
+}
+
+}  // namespace gcnb
+
+// =====================================================================================================================
+// C ABI
+// =====================================================================================================================
+struct gcnb_bittile_host {
+  BitTileHost H;
+};
+
+struct gcnb_bittile_plan {
+  int64_t n_rows = 0, n_cols = 0, nnz = 0, n_blk = 0, n_tiles = 0, tile_nnz = 0, rem_nnz = 0, n_chunks = 0;
+  int n_cta = 0;
+  uint32_t *d_tile_chunk = nullptr, *d_cta_tile_ptr = nullptr, *d_cta_item_ptr = nullptr;
+  uint2 *d_items = nullptr;
+  uint64_t *d_bits = nullptr;
+  uint32_t *d_r_indptr = nullptr, *d_r_indices = nullptr;
+  float *d_r_values = nullptr, *d_row_scale = nullptr, *d_col_scale = nullptr;
+  uint8_t *d_packed = nullptr;
+  float *d_P = nullptr, *d_R = nullptr;
+  gcnb_spmm_plan *rem = nullptr;
+  cudaStream_t aux = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+};
+
+namespace {
+constexpr size_t kBtSmemBytes = (size_t)kBtBStages * kBtChunkBytes + (2 * kBtBStages + 2 * kBtAStages + 4) * 8 + 16;
+
+template <class T>
+int bt_upload(T **dst, const T *src, size_t n, cudaStream_t stream) {
+  *dst = nullptr;
+  GCNB_CHECK(cudaMalloc((void **)dst, std::max<size_t>(n, 1) * sizeof(T)));
+  if (n) GCNB_CHECK(cudaMemcpyAsync(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice, stream));
+  return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int gcnb_bittile_host_build(const uint32_t *h_indptr, const uint32_t *h_indices, const float *h_values, int64_t n_rows,
+                            int64_t n_cols, const float *h_row_scale, const float *h_col_scale, int min_tile_nnz, int n_cta,
+                            int n_threads, gcnb_bittile_host **out) {
+  if (!out) return GCNB_E_BADARG;
+  auto *h = new gcnb_bittile_host();
+  const int rc = bittile_build_host(h_indptr, h_indices, h_values, n_rows, n_cols, h_row_scale, h_col_scale, min_tile_nnz,
+                                    n_cta, n_threads, h->H);
+  if (rc) {
+    delete h;
+    return rc;
+  }
+  *out = h;
+  return 0;
+}
+
+int gcnb_bittile_host_sizes(const gcnb_bittile_host *h, int64_t out[8]) {
+  if (!h || !out) return GCNB_E_BADARG;
+  const BitTileHost &H = h->H;
+  out[0] = H.n_rows; out[1] = H.n_cols; out[2] = H.nnz; out[3] = H.n_blk; out[4] = H.n_tiles; out[5] = H.tile_nnz;
+  out[6] = (int64_t)H.items.size(); out[7] = H.n_cta;
+  return 0;
+}
+
+// which: 0 tile_chunk, 1 bits (uint64), 2 cta_tile_ptr, 3 cta_item_ptr, 4 items (uint32 x2), 5 r_indptr, 6 r_indices,
+// 7 r_values, 8 row_scale, 9 col_scale.  Copies min(bytes, size) bytes.
+int gcnb_bittile_host_copy(const gcnb_bittile_host *h, int which, void *dst, int64_t bytes) {
+  if (!h || !dst || bytes < 0) return GCNB_E_BADARG;
+  const BitTileHost &H = h->H;
+  const void *src = nullptr;
+  size_t n = 0;
+  switch (which) {
+    case 0: src = H.tile_chunk.data(); n = H.tile_chunk.size() * 4; break;
+    case 1: src = H.bits.data(); n = H.bits.size() * 8; break;
+    case 2: src = H.cta_tile_ptr.data(); n = H.cta_tile_ptr.size() * 4; break;
+    case 3: src = H.cta_item_ptr.data(); n = H.cta_item_ptr.size() * 4; break;
+    case 4: src = H.items.data(); n = H.items.size() * sizeof(uint2); break;
+    case 5: src = H.r_indptr.data(); n = H.r_indptr.size() * 4; break;
+    case 6: src = H.r_indices.data(); n = H.r_indices.size() * 4; break;
+    case 7: src = H.r_values.data(); n = H.r_values.size() * 4; break;
+    case 8: src = H.row_scale.data(); n = H.row_scale.size() * 4; break;
+    case 9: src = H.col_scale.data(); n = H.col_scale.size() * 4; break;
+    default: return GCNB_E_BADARG;
+  }
+  if (n) memcpy(dst, src, std::min<size_t>(n, (size_t)bytes));
+  return 0;
+}
+
+int gcnb_bittile_host_destroy(gcnb_bittile_host *h) {
+  delete h;
+  return 0;
+}
+
+int gcnb_bittile_plan_destroy(gcnb_bittile_plan *p) {
+  if (!p) return 0;
+  if (p->rem) gcnb_spmm_plan_destroy(p->rem);
+  cudaFree(p->d_tile_chunk); cudaFree(p->d_cta_tile_ptr); cudaFree(p->d_cta_item_ptr); cudaFree(p->d_items);
+  cudaFree(p->d_bits); cudaFree(p->d_r_indptr); cudaFree(p->d_r_indices); cudaFree(p->d_r_values);
+  cudaFree(p->d_row_scale); cudaFree(p->d_col_scale); cudaFree(p->d_packed); cudaFree(p->d_P); cudaFree(p->d_R);
+  if (p->aux) cudaStreamDestroy(p->aux);
+  if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+  if (p->ev_join) cudaEventDestroy(p->ev_join);
+  delete p;
+  return 0;
+}
+
+int gcnb_bittile_plan_create(const uint32_t *h_indptr, const uint32_t *h_indices, const float *h_values, int64_t n_rows,
+                             int64_t n_cols, const float *h_row_scale, const float *h_col_scale, int min_tile_nnz,
+                             gcnb_stream_t stream_, gcnb_bittile_plan **out) {
+  if (!out) return GCNB_E_BADARG;
+  *out = nullptr;
+  const DeviceInfo &di = device_info();
+  if (!di.ok) return (int)cudaErrorNoDevice;
+  if (di.cc_major != 10) return GCNB_E_UNSUPPORTED;  // tcgen05 / TMEM
+  cudaStream_t stream = as_stream(stream_);
+  BitTileHost H;
+  int rc = bittile_build_host(h_indptr, h_indices, h_values, n_rows, n_cols, h_row_scale, h_col_scale, min_tile_nnz,
+                              di.sm_count, 0, H);
+  if (rc) return rc;
+  auto *p = new gcnb_bittile_plan();
+  auto fail = [&](int code) {
+    gcnb_bittile_plan_destroy(p);
+    return code;
+  };
+  p->n_rows = n_rows; p->n_cols = n_cols; p->nnz = H.nnz; p->n_blk = H.n_blk; p->n_tiles = H.n_tiles;
+  p->tile_nnz = H.tile_nnz; p->rem_nnz = (int64_t)H.r_indices.size(); p->n_cta = H.n_cta;
+  p->n_chunks = (n_cols + kBtChunk - 1) / kBtChunk;
+  if ((rc = bt_upload(&p->d_tile_chunk, H.tile_chunk.data(), H.tile_chunk.size(), stream))) return fail(rc);
+  if ((rc = bt_upload(&p->d_bits, H.bits.data(), H.bits.size(), stream))) return fail(rc);
+  if ((rc = bt_upload(&p->d_cta_tile_ptr, H.cta_tile_ptr.data(), H.cta_tile_ptr.size(), stream))) return fail(rc);
+  if ((rc = bt_upload(&p->d_cta_item_ptr, H.cta_item_ptr.data(), H.cta_item_ptr.size(), stream))) return fail(rc);
+  if ((rc = bt_upload(&p->d_items, H.items.data(), H.items.size(), stream))) return fail(rc);
+  if ((rc = bt_upload(&p->d_r_indptr, H.r_indptr.data(), H.r_indptr.size(), stream))) return fail(rc);
+  if ((rc = bt_upload(&p->d_r_indices, H.r_indices.data(), H.r_indices.size(), stream))) return fail(rc);
+  if ((rc = bt_upload(&p->d_r_values, H.r_values.data(), H.r_values.size(), stream))) return fail(rc);
+  if ((rc = bt_upload(&p->d_row_scale, H.row_scale.data(), H.row_scale.size(), stream))) return fail(rc);
+  if ((rc = bt_upload(&p->d_col_scale, H.col_scale.data(), H.col_scale.size(), stream))) return fail(rc);
+  const size_t packed_bytes = std::max<size_t>((size_t)p->n_chunks * kBtChunkBytes, 16);
+  const size_t p_bytes = std::max<size_t>((size_t)p->n_blk * kBtRows * 16 * sizeof(float), 16);
+  if ((rc = (int)cudaMalloc((void **)&p->d_packed, packed_bytes))) return fail(rc);
+  if ((rc = (int)cudaMalloc((void **)&p->d_P, p_bytes))) return fail(rc);
+  if ((rc = (int)cudaMalloc((void **)&p->d_R, std::max<size_t>((size_t)n_rows * 16 * sizeof(float), 16)))) return fail(rc);
+  if ((rc = (int)cudaMemsetAsync(p->d_P, 0, p_bytes, stream))) return fail(rc);  // blocks without tiles stay 0 for ever
+  if ((rc = (int)cudaStreamSynchronize(stream))) return fail(rc);                // host arrays go out of scope
+  if ((rc = gcnb_spmm_plan_create(p->d_r_indptr, p->d_r_indices, n_rows, n_cols, 0, stream_, &p->rem))) return fail(rc);
+  if ((rc = (int)cudaStreamCreateWithFlags(&p->aux, cudaStreamNonBlocking))) return fail(rc);
+  if ((rc = (int)cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming))) return fail(rc);
+  if ((rc = (int)cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming))) return fail(rc);
+  if ((rc = (int)cudaFuncSetAttribute(bt_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBtSmemBytes)))
+    return fail(rc);
+  *out = p;
+  return 0;
+}
+
+// out = {tiles, entries in tiles, remainder entries, row blocks, items (blocks with tiles), CTAs, bit-map bytes, packed B' bytes}
+int gcnb_bittile_plan_info(const gcnb_bittile_plan *p, int64_t out[8]) {
+  if (!p || !out) return GCNB_E_BADARG;
+  out[0] = p->n_tiles; out[1] = p->tile_nnz; out[2] = p->rem_nnz; out[3] = p->n_blk; out[4] = 0; out[5] = p->n_cta;
+  out[6] = p->n_tiles * (int64_t)kBtRows * 8; out[7] = p->n_chunks * (int64_t)kBtChunkBytes;
+  return 0;
+}
+
+// debugging aid: run the pack kernel alone and copy the operand image of B' back to the host
+int gcnb_bittile_debug_pack(gcnb_bittile_plan *p, const float *d_B, void *h_out, int64_t bytes, gcnb_stream_t stream_) {
+  if (!p || !d_B || !h_out || bytes < 0) return GCNB_E_BADARG;
+  cudaStream_t stream = as_stream(stream_);
+  const int64_t n_groups = p->n_chunks * (kBtChunk / 8);
+  if (n_groups == 0) return 0;
+  bt_pack_kernel<<<(unsigned)((n_groups * 16 + 255) / 256), 256, 0, stream>>>(d_B, p->d_col_scale, p->d_packed, p->n_cols,
+                                                                              n_groups);
+  GCNB_LAUNCH_CHECK();
+  GCNB_CHECK(cudaMemcpyAsync(h_out, p->d_packed, (size_t)std::min<int64_t>(bytes, p->n_chunks * (int64_t)kBtChunkBytes),
+                             cudaMemcpyDeviceToHost, stream));
+  GCNB_CHECK(cudaStreamSynchronize(stream));
+  return 0;
+}
+
+int gcnb_bittile_spmm16_f32(gcnb_bittile_plan *p, const float *d_B, float *d_C, gcnb_stream_t stream_) {
+  if (!p || !d_B || !d_C) return GCNB_E_BADARG;
+  if (p->n_rows == 0) return 0;
+  cudaStream_t stream = as_stream(stream_);
+  // remainder CSR on the second stream (reads B only)
+  GCNB_CHECK(cudaEventRecord(p->ev_fork, stream));
+  GCNB_CHECK(cudaStreamWaitEvent(p->aux, p->ev_fork, 0));
+  {
+    const int rc = gcnb::spmm_generic_launch(p->rem, p->d_r_values, nullptr, d_B, 16, p->d_R, 16, 16, p->aux);
+    if (rc) return rc;
+  }
+  GCNB_CHECK(cudaEventRecord(p->ev_join, p->aux));
+  if (p->n_tiles > 0) {
+    const int64_t n_groups = p->n_chunks * (kBtChunk / 8);
+    const int64_t threads = n_groups * 16;
+    bt_pack_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(d_B, p->d_col_scale, p->d_packed, p->n_cols,
+                                                                         n_groups);
+    GCNB_LAUNCH_CHECK();
+    BtArgs a;
+    a.tile_chunk = p->d_tile_chunk; a.bits = p->d_bits; a.cta_tile_ptr = p->d_cta_tile_ptr;
+    a.cta_item_ptr = p->d_cta_item_ptr; a.items = p->d_items; a.packed = p->d_packed; a.row_scale = p->d_row_scale;
+    a.P = p->d_P; a.n_rows = p->n_rows;
+    bt_mma_kernel<<<p->n_cta, kBtThreads, kBtSmemBytes, stream>>>(a);
+    GCNB_LAUNCH_CHECK();
+  }
+  GCNB_CHECK(cudaStreamWaitEvent(stream, p->ev_join, 0));
+  const int64_t n4 = p->n_rows * 4;
+  const int blocks = (int)std::min<int64_t>((n4 + 255) / 256, (int64_t)device_info().sm_count * 8);
+  bt_add_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const float4 *>(p->d_P), reinterpret_cast<const float4 *>(p->d_R),
+                                           reinterpret_cast<float4 *>(d_C), n4);
+  GCNB_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,248 @@
+"""Bit-tile GraphSum plan (parallel-gcn_b200/csrc/spmm_bittile.cu, host part) checked WITHOUT a GPU.
+
+A numpy emulation consumes the plan arrays the way the kernels do -- the expanders' bit -> bf16-pair formula, the pack
+kernel's byte layout read back through the shared-memory descriptor's addressing (K-major core matrices, LBO 768 /
+SBO 128), the four rotating accumulators per row block, the (lo + mid) + hi piece order, the remainder CSR -- and must
+reproduce the CSR product; every CSR entry must appear exactly once in (bit maps + remainder)."""
+import numpy as np
+import pytest
+
+from tests.util import assert_close
+
+ROWS, CHUNK, NACC = 128, 64, 4
+KSTEP_BYTES, CHUNK_BYTES = 1536, 6144
+
+
+@pytest.fixture(scope="module")
+def gcnb():
+    import importlib
+    import __graft_entry__ as ge
+    ge.load_package()
+    return importlib.import_module("parallel_gcn_b200.binding")
+
+
+def gcn_graph(rng, n, n_comm, deg_intra, deg_inter, dup=0, drop_diag=()):
+    """symmetric community graph in the reference's row layout (self first, parser.cpp:59-112) with GraphSum values
+    1/sqrtf(deg_i * deg_j) computed as parser.cpp:164-181 does; `dup` extra duplicate entries; rows in drop_diag lose
+    their self entry."""
+    bs = (n + n_comm - 1) // n_comm
+    src = np.repeat(np.arange(n), deg_intra)
+    dst = np.minimum((src // bs) * bs + rng.integers(0, bs, src.size), n - 1)
+    s2 = np.repeat(np.arange(n), deg_inter)
+    d2 = rng.integers(0, n, s2.size)
+    a = np.concatenate([src, s2, dst, d2])
+    b = np.concatenate([dst, d2, src, s2])
+    keep = a != b
+    pairs = np.unique(np.stack([a[keep], b[keep]], 1), axis=0)
+    rows = [[i] for i in range(n)]
+    for i, j in pairs:
+        rows[i].append(int(j))
+    for i in drop_diag:
+        rows[i] = rows[i][1:]
+    for _ in range(dup):
+        i = int(rng.integers(0, n))
+        if len(rows[i]) > 1:
+            rows[i].append(rows[i][int(rng.integers(0, len(rows[i])))])
+    indptr = np.zeros(n + 1, np.uint32)
+    indptr[1:] = np.cumsum([len(r) for r in rows])
+    indices = np.fromiter((j for r in rows for j in r), np.uint32)
+    deg = np.diff(indptr.astype(np.int64))
+    rr = np.repeat(np.arange(n), deg)
+    prod = (deg[rr] * deg[indices]).astype(np.uint32).astype(np.float32)
+    values = (1.0 / np.sqrt(prod).astype(np.float64)).astype(np.float32)
+    return indptr, indices, values
+
+
+def bf16_split(x):
+    """truncating split of fp32 into three bf16 pieces (as uint16 bit patterns) -- bt_pack_kernel"""
+    x = x.astype(np.float32)
+    xb = x.view(np.uint32)
+    hb = xb & np.uint32(0xFFFF0000)
+    r1 = x - hb.view(np.float32)
+    mb = r1.view(np.uint32) & np.uint32(0xFFFF0000)
+    r2 = r1 - mb.view(np.float32)
+    lb = r2.view(np.uint32) & np.uint32(0xFFFF0000)
+    assert np.array_equal(hb.view(np.float32).astype(np.float64) + mb.view(np.float32) + lb.view(np.float32),
+                          x.astype(np.float64)), "the three pieces must add up exactly"
+    return [(p >> np.uint32(16)).astype(np.uint16) for p in (hb, mb, lb)]
+
+
+def pack_b(B, col_scale):
+    """bt_pack_kernel: thread (group of 8 rows of B, column) writes three 16-byte vectors into the chunk image"""
+    n_cols = B.shape[0]
+    n_chunks = (n_cols + CHUNK - 1) // CHUNK
+    Bp = np.zeros((n_chunks * CHUNK, 16), np.float32)
+    Bp[:n_cols] = col_scale[:, None].astype(np.float32) * B.astype(np.float32)
+    pieces = bf16_split(Bp)
+    packed = np.zeros(n_chunks * CHUNK_BYTES // 2, np.uint16)
+    j = np.arange(n_chunks * CHUNK)
+    c, kl = j >> 6, j & 63
+    base = c * CHUNK_BYTES + (kl >> 4) * KSTEP_BYTES + ((kl >> 3) & 1) * 768 + (kl & 7) * 2
+    for p in range(3):
+        for col in range(16):
+            n = p * 16 + col
+            off = base + (n >> 3) * 128 + (n & 7) * 16
+            packed[off // 2] = pieces[p][:, col]
+    return packed, Bp
+
+
+def read_b_operand(packed, chunk, ks):
+    """what tcgen05.mma reads through bt_b_desc: element (n, k) of the 48 x 16 operand at
+    start + (k / 8) * LBO + (n / 8) * SBO + (n % 8) * 16 + (k % 8) * 2 with LBO = 768, SBO = 128 (K-major, no swizzle)"""
+    start = chunk * CHUNK_BYTES + ks * KSTEP_BYTES
+    n = np.arange(48)[:, None]
+    k = np.arange(16)[None, :]
+    off = start + (k // 8) * 768 + (n // 8) * 128 + (n % 8) * 16 + (k % 8) * 2
+    bits = packed[off // 2].astype(np.uint32) << np.uint32(16)
+    return bits.view(np.float32)  # [48, 16]
+
+
+def expand_words(words):
+    """bt_expand_word on the 128 rows of a tile: 64-bit word -> 32 registers (two bf16 each) -> A[128, 64] of 0.0 / 1.0"""
+    A = np.zeros((ROWS, CHUNK), np.float32)
+    for half in range(2):
+        w = ((words >> np.uint64(32 * half)) & np.uint64(0xFFFFFFFF)).astype(np.uint64)
+        w8 = w >> np.uint64(8)
+        for q in range(16):
+            src = w if q < 8 else w8
+            qq = q & 7
+            reg = ((src & np.uint64(0x00010001 << qq)) * np.uint64(0x3F80 >> qq)) & np.uint64(0xFFFFFFFF)
+            lo = ((reg & np.uint64(0xFFFF)) << np.uint64(16)).astype(np.uint32).view(np.float32)
+            hi = (reg & np.uint64(0xFFFF0000)).astype(np.uint32).view(np.float32)
+            col = half * 32 + 2 * q  # register q of the half = TMEM column (half*16 + q) = k elements 2q, 2q+1
+            A[:, col] = lo
+            A[:, col + 1] = hi
+    assert np.all((A == 0) | (A == 1))
+    return A
+
+
+def emulate(plan, B):
+    n_rows = plan["n_rows"]
+    packed, _ = pack_b(B, plan["col_scale"])
+    P = np.zeros((plan["n_blk"] * ROWS, 16), np.float64)
+    cells = []
+    block_seen = np.zeros(plan["n_blk"], np.int64)
+    tile_seen = np.zeros(plan["n_tiles"], np.int64)
+    for q in range(plan["n_cta"]):
+        t0, t1 = int(plan["cta_tile_ptr"][q]), int(plan["cta_tile_ptr"][q + 1])
+        pos = 0
+        for blk, end in plan["items"][plan["cta_item_ptr"][q]:plan["cta_item_ptr"][q + 1]]:
+            blk, end = int(blk), int(end)
+            assert end > pos, "an item owns at least one tile"
+            block_seen[blk] += 1
+            acc = np.zeros((NACC, ROWS, 48), np.float64)
+            chunks = plan["tile_chunk"][t0 + pos:t0 + end]
+            assert np.all(np.diff(chunks.astype(np.int64)) > 0), "chunks of a block ascend"
+            for idx in range(end - pos):
+                t = t0 + pos + idx
+                tile_seen[t] += 1
+                A = expand_words(plan["bits"][t])
+                for ks in range(4):
+                    Bop = read_b_operand(packed, int(chunks[idx]), ks)  # [48, 16]
+                    acc[idx % NACC] += A[:, ks * 16:(ks + 1) * 16].astype(np.float64) @ Bop.T.astype(np.float64)
+                r, c = np.nonzero(A)
+                cells.append(np.stack([blk * ROWS + r, int(chunks[idx]) * CHUNK + c], 1))
+            s = acc[0].copy()
+            for a in range(1, min(NACC, end - pos)):
+                s += acc[a]
+            tot = (s[:, 32:48] + s[:, 16:32]) + s[:, 0:16]
+            rows = np.arange(blk * ROWS, (blk + 1) * ROWS)
+            sc = np.where(rows < n_rows, plan["row_scale"][np.minimum(rows, n_rows - 1)], 0.0)
+            P[rows] = sc[:, None] * tot
+            pos = end
+        assert t0 + pos == t1
+    assert np.all(block_seen <= 1) and np.all(tile_seen == 1)
+    rp = plan["r_indptr"].astype(np.int64)
+    R = np.zeros((n_rows, 16), np.float64)
+    rrows = np.repeat(np.arange(n_rows), np.diff(rp))
+    np.add.at(R, rrows, plan["r_values"][:, None].astype(np.float64) * B[plan["r_indices"]])
+    cells = np.concatenate(cells) if cells else np.zeros((0, 2), np.int64)
+    return P[:n_rows] + R, cells, rrows
+
+
+def check_plan(gcnb, indptr, indices, values, B, explicit_scales=False, min_tile_nnz=0, n_cta=0, expect_tiles=True):
+    n = len(indptr) - 1
+    deg = np.diff(indptr.astype(np.int64))
+    rs = cs = None
+    if explicit_scales:
+        rs = cs = (1.0 / np.sqrt(deg.astype(np.float32))).astype(np.float32)
+    plan = gcnb.bittile_host_build(indptr, indices, values, n, rs, cs, min_tile_nnz=min_tile_nnz, n_cta=n_cta)
+    assert plan["nnz"] == indices.size and plan["tile_nnz"] + plan["rem_nnz"] == indices.size
+    out, cells, rrows = emulate(plan, B)
+    assert len(cells) == plan["tile_nnz"]
+    if expect_tiles:
+        assert plan["n_tiles"] > 0 and plan["tile_nnz"] > 0
+    # every CSR entry exactly once: multiset of (row, col) over bit maps + remainder == the CSR's
+    rows = np.repeat(np.arange(n), deg)
+    orig = np.sort(rows.astype(np.int64) * (1 << 32) + indices)
+    got = np.sort(np.concatenate([cells[:, 0] * (1 << 32) + cells[:, 1],
+                                  rrows.astype(np.int64) * (1 << 32) + plan["r_indices"]]))
+    assert np.array_equal(orig, got)
+    # remainder keeps the row's entry order and the original values
+    ref = np.zeros((n, 16), np.float64)
+    np.add.at(ref, rows, values[:, None].astype(np.float64) * B[indices])
+    assert_close(out, ref, rtol=2e-6, atol=1e-7 * np.abs(ref).max(), what="bit-tile emulation vs CSR product")
+    return plan
+
+
+def test_bit_position_formula_is_a_permutation(gcnb):
+    pos = [(c & 32) + ((c & 31) >> 1) + 16 * (c & 1) for c in range(64)]
+    assert sorted(pos) == list(range(64))
+    w = np.zeros(128, np.uint64)
+    for c in range(64):
+        w[c] |= np.uint64(1) << np.uint64(pos[c])  # row c has exactly column c set
+    A = expand_words(w)
+    assert np.array_equal(A[:64], np.eye(64, dtype=np.float32)) and not A[64:].any()
+
+
+def test_community_graph_matches_csr_product(gcnb):
+    rng = np.random.default_rng(7)
+    indptr, indices, values = gcn_graph(rng, 1500, 5, 24, 3)
+    B = rng.standard_normal((1500, 16)).astype(np.float32)
+    plan = check_plan(gcnb, indptr, indices, values, B, min_tile_nnz=96, n_cta=5)
+    assert plan["tile_nnz"] > 0.5 * indices.size
+    # explicit 1/sqrt(deg) scales select the same entries
+    plan2 = check_plan(gcnb, indptr, indices, values, B, explicit_scales=True, min_tile_nnz=96, n_cta=5)
+    assert plan2["tile_nnz"] == plan["tile_nnz"]
+
+
+def test_duplicates_missing_diagonals_and_ragged_sizes(gcnb):
+    rng = np.random.default_rng(11)
+    n = 777  # not a multiple of 128 or 64
+    indptr, indices, values = gcn_graph(rng, n, 3, 30, 2, dup=40, drop_diag=(5, 300, 776))
+    B = rng.standard_normal((n, 16)).astype(np.float32)
+    plan = check_plan(gcnb, indptr, indices, values, B, min_tile_nnz=64, n_cta=148)
+    # rows without a diagonal entry have no scale: none of their entries (nor entries pointing at them) is in a bit map
+    for i in (5, 300, 776):
+        assert plan["row_scale"][i] == 0 and plan["col_scale"][i] == 0
+    # values that do not factor stay in the remainder with their original value
+    values2 = values.copy()
+    values2[::7] *= 1.5
+    check_plan(gcnb, indptr, indices, values2, B, min_tile_nnz=64, n_cta=7)
+
+
+def test_sparse_graph_has_no_tiles_and_empty_graph(gcnb):
+    rng = np.random.default_rng(3)
+    n = 4000
+    deg = np.full(n, 3)
+    indptr = np.zeros(n + 1, np.uint32)
+    indptr[1:] = np.cumsum(deg)
+    indices = rng.integers(0, n, int(indptr[-1])).astype(np.uint32)
+    indices[indptr[:-1]] = np.arange(n)
+    values = rng.random(indices.size).astype(np.float32)
+    B = rng.standard_normal((n, 16)).astype(np.float32)
+    plan = check_plan(gcnb, indptr, indices, values, B, expect_tiles=False)
+    assert plan["n_tiles"] == 0 and plan["rem_nnz"] == indices.size
+    empty = gcnb.bittile_host_build(np.zeros(1, np.uint32), np.zeros(0, np.uint32), np.zeros(0, np.float32), 0)
+    assert empty["n_tiles"] == 0 and empty["n_rows"] == 0
+
+
+def test_schedule_is_balanced_and_deterministic(gcnb):
+    rng = np.random.default_rng(5)
+    indptr, indices, values = gcn_graph(rng, 3000, 6, 20, 2)
+    a = gcnb.bittile_host_build(indptr, indices, values, 3000, min_tile_nnz=64, n_cta=8, n_threads=1)
+    b = gcnb.bittile_host_build(indptr, indices, values, 3000, min_tile_nnz=64, n_cta=8, n_threads=7)
+    for k in ("tile_chunk", "bits", "cta_tile_ptr", "cta_item_ptr", "items", "r_indptr", "r_indices", "r_values"):
+        assert np.array_equal(a[k], b[k]), k
+    load = np.diff(a["cta_tile_ptr"].astype(np.int64))
+    assert load.max() <= load.mean() * 1.5 + 8
