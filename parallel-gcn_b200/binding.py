@@ -62,6 +62,7 @@ _sig("gcnb_bittile_plan_destroy", I32, [P])
 _sig("gcnb_bittile_plan_info", I32, [P, P])
 _sig("gcnb_bittile_spmm16_f32", I32, [P, P, P, P])
 _sig("gcnb_bittile_debug_pack", I32, [P, P, P, I64, P])
+_sig("gcnb_bittile_debug_parts", I32, [P, I32])
 _sig("gcnb_bittile_host_build", I32, [P, P, P, I64, I64, P, P, I32, I32, I32, P])
 _sig("gcnb_bittile_host_sizes", I32, [P, P])
 _sig("gcnb_bittile_host_copy", I32, [P, I32, P, I64])
@@ -305,6 +306,9 @@ class BitTilePlan:
 
     def spmm16(self, B, C_out):
         check(lib.gcnb_bittile_spmm16_f32(self.h, ptr(B), ptr(C_out), stream()))
+
+    def debug_parts(self, mask):
+        check(lib.gcnb_bittile_debug_parts(self.h, int(mask)))
 
     def debug_pack(self, B):
         import numpy as np

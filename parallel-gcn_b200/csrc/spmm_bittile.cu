@@ -616,6 +616,7 @@ struct gcnb_bittile_host {
 struct gcnb_bittile_plan {
   int64_t n_rows = 0, n_cols = 0, nnz = 0, n_blk = 0, n_tiles = 0, tile_nnz = 0, rem_nnz = 0, n_chunks = 0;
   int n_cta = 0;
+  int parts = 15;  // debugging: bit 0 pack, 1 MMA kernel, 2 remainder, 3 final add
   uint32_t *d_tile_chunk = nullptr, *d_cta_tile_ptr = nullptr, *d_cta_item_ptr = nullptr;
   uint2 *d_items = nullptr;
   uint64_t *d_bits = nullptr;
@@ -763,6 +764,13 @@ int gcnb_bittile_plan_info(const gcnb_bittile_plan *p, int64_t out[8]) {
   return 0;
 }
 
+// debugging aid: switch steps of gcnb_bittile_spmm16_f32 off (bit 0 pack, 1 MMA kernel, 2 remainder, 3 final add) to time them apart
+int gcnb_bittile_debug_parts(gcnb_bittile_plan *p, int parts) {
+  if (!p) return GCNB_E_BADARG;
+  p->parts = parts & 15;
+  return 0;
+}
+
 // debugging aid: run the pack kernel alone and copy the operand image of B' back to the host
 int gcnb_bittile_debug_pack(gcnb_bittile_plan *p, const float *d_B, void *h_out, int64_t bytes, gcnb_stream_t stream_) {
   if (!p || !d_B || !h_out || bytes < 0) return GCNB_E_BADARG;
@@ -782,20 +790,20 @@ int gcnb_bittile_spmm16_f32(gcnb_bittile_plan *p, const float *d_B, float *d_C, 
   if (!p || !d_B || !d_C) return GCNB_E_BADARG;
   if (p->n_rows == 0) return 0;
   cudaStream_t stream = as_stream(stream_);
-  // remainder CSR on the second stream (reads B only)
-  GCNB_CHECK(cudaEventRecord(p->ev_fork, stream));
-  GCNB_CHECK(cudaStreamWaitEvent(p->aux, p->ev_fork, 0));
-  {
-    const int rc = gcnb::spmm_generic_launch(p->rem, p->d_r_values, nullptr, d_B, 16, p->d_R, 16, 16, p->aux);
-    if (rc) return rc;
-  }
-  GCNB_CHECK(cudaEventRecord(p->ev_join, p->aux));
-  if (p->n_tiles > 0) {
+  const int parts = p->parts;  // 15 unless a probe switched steps off (gcnb_bittile_debug_parts)
+  const bool tiles = p->n_tiles > 0;
+  if (tiles && (parts & 1)) {
     const int64_t n_groups = p->n_chunks * (kBtChunk / 8);
     const int64_t threads = n_groups * 16;
     bt_pack_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(d_B, p->d_col_scale, p->d_packed, p->n_cols,
                                                                          n_groups);
     GCNB_LAUNCH_CHECK();
+  }
+  // The MMA kernel goes first (one CTA per SM, half the register file), then the remainder CSR on the second stream
+  // fills what is left of every SM: launched the other way round the remainder's persistent CTAs own all registers
+  // and the two kernels run one after the other.
+  GCNB_CHECK(cudaEventRecord(p->ev_fork, stream));
+  if (tiles && (parts & 2)) {
     BtArgs a;
     a.tile_chunk = p->d_tile_chunk; a.bits = p->d_bits; a.cta_tile_ptr = p->d_cta_tile_ptr;
     a.cta_item_ptr = p->d_cta_item_ptr; a.items = p->d_items; a.packed = p->d_packed; a.row_scale = p->d_row_scale;
@@ -803,11 +811,19 @@ int gcnb_bittile_spmm16_f32(gcnb_bittile_plan *p, const float *d_B, float *d_C, 
     bt_mma_kernel<<<p->n_cta, kBtThreads, kBtSmemBytes, stream>>>(a);
     GCNB_LAUNCH_CHECK();
   }
+  GCNB_CHECK(cudaStreamWaitEvent(p->aux, p->ev_fork, 0));
+  if (parts & 4) {
+    const int rc = gcnb::spmm_generic_launch(p->rem, p->d_r_values, nullptr, d_B, 16, p->d_R, 16, 16, p->aux);
+    if (rc) return rc;
+  }
+  GCNB_CHECK(cudaEventRecord(p->ev_join, p->aux));
   GCNB_CHECK(cudaStreamWaitEvent(stream, p->ev_join, 0));
-  const int64_t n4 = p->n_rows * 4;
-  const int blocks = (int)std::min<int64_t>((n4 + 255) / 256, (int64_t)device_info().sm_count * 8);
-  bt_add_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const float4 *>(p->d_P), reinterpret_cast<const float4 *>(p->d_R),
-                                           reinterpret_cast<float4 *>(d_C), n4);
+  if (parts & 8) {
+    const int64_t n4 = p->n_rows * 4;
+    const int blocks = (int)std::min<int64_t>((n4 + 255) / 256, (int64_t)device_info().sm_count * 8);
+    bt_add_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const float4 *>(p->d_P),
+                                             reinterpret_cast<const float4 *>(p->d_R), reinterpret_cast<float4 *>(d_C), n4);
+  }
   GCNB_LAUNCH_CHECK();
   return 0;
 }

@@ -116,6 +116,12 @@ def graph_case(scale):
     alg = 4 * (n + 1) + 8 * indices.size + 8 * n * 16
     emit(case="graph/%d" % scale, step="time", bittile_us=us_bt, generic_us=us_gen, algorithmic_bytes=alg,
          bittile_gbs=alg / us_bt / 1e3, generic_gbs=alg / us_gen / 1e3)
+    parts = {}
+    for name, mask in (("pack", 1), ("mma", 2), ("remainder", 4), ("add", 8), ("pack+mma", 3), ("mma+remainder", 6), ("all", 15)):
+        plan.debug_parts(mask)
+        parts[name] = timeit(lambda: plan.spmm16(B, out))
+    plan.debug_parts(15)
+    emit(case="graph/%d" % scale, step="parts_us", **parts)
     if args.staged:
         ref_plan.stage(d_values, 16, indptr, indices)
         us_st = timeit(lambda: ref_plan.spmm(d_values, B, ref, 16))
