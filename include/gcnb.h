@@ -128,6 +128,10 @@ GCNB_API int gcnb_bittile_plan_destroy(gcnb_bittile_plan *plan);
 /* out = {tiles, entries in tiles, remainder entries, row blocks, 0, CTAs, bit-map bytes, packed-B bytes} */
 GCNB_API int gcnb_bittile_plan_info(const gcnb_bittile_plan *plan, int64_t out[8]);
 GCNB_API int gcnb_bittile_spmm16_f32(gcnb_bittile_plan *plan, const float *d_B, float *d_C, gcnb_stream_t stream);
+/* Routes later gcnb_spmm_f32 / gcnb_spmm_ld_f32 calls on `plan` that use exactly this d_values pointer, no permutation,
+ * 16 contiguous columns (ldb == ldc == 16) through the bit-tile plan (built from the same CSR and the same values);
+ * every other call is unaffected.  The bit-tile plan is borrowed (destroy it after the spmm plan); bt = NULL detaches. */
+GCNB_API int gcnb_spmm_plan_attach_bittile(gcnb_spmm_plan *plan, gcnb_bittile_plan *bt, const float *d_values);
 /* debugging aid: bit mask of the steps gcnb_bittile_spmm16_f32 runs (1 pack, 2 MMA kernel, 4 remainder, 8 final add; default 15) */
 GCNB_API int gcnb_bittile_debug_parts(gcnb_bittile_plan *plan, int parts);
 /* debugging aid: runs the packing kernel alone and copies the bf16 operand image of B (6144 bytes per 64 rows) to h_out */

@@ -63,6 +63,7 @@ _sig("gcnb_bittile_plan_info", I32, [P, P])
 _sig("gcnb_bittile_spmm16_f32", I32, [P, P, P, P])
 _sig("gcnb_bittile_debug_pack", I32, [P, P, P, I64, P])
 _sig("gcnb_bittile_debug_parts", I32, [P, I32])
+_sig("gcnb_spmm_plan_attach_bittile", I32, [P, P, P])
 _sig("gcnb_bittile_host_build", I32, [P, P, P, I64, I64, P, P, I32, I32, I32, P])
 _sig("gcnb_bittile_host_sizes", I32, [P, P])
 _sig("gcnb_bittile_host_copy", I32, [P, I32, P, I64])
@@ -176,6 +177,11 @@ class SpmmPlan:
     def spmm(self, values, B, C_out, dim, perm=None):
         check(lib.gcnb_spmm_f32(self.h, ptr(values), ptr(perm), ptr(B), ptr(C_out), int(dim), stream()))
         return C_out
+
+    def attach_bittile(self, bt, values):
+        """route 16-column products with this value tensor through a BitTilePlan (None detaches)"""
+        self._bt, self._bt_values = bt, values  # keep both alive
+        check(lib.gcnb_spmm_plan_attach_bittile(self.h, bt.h if bt is not None else None, ptr(values)))
 
     def set_own_cols(self, col0, col1):
         """row-partitioned product: columns [col0, col1) are this rank's own slab of B (call before stage())"""

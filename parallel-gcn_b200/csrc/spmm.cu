@@ -488,6 +488,13 @@ int gcnb_spmm_plan_info(const gcnb_spmm_plan *p, int64_t out[8]) {
   return 0;
 }
 
+int gcnb_spmm_plan_attach_bittile(gcnb_spmm_plan *p, gcnb_bittile_plan *bt, const float *d_values) {
+  if (!p || (bt && !d_values)) return GCNB_E_BADARG;
+  p->bittile = bt;
+  p->bittile_values = bt ? d_values : nullptr;
+  return 0;
+}
+
 int gcnb_spmm_f32(gcnb_spmm_plan *p, const float *d_values, const uint32_t *d_perm, const float *d_B, float *d_C,
                   int dim, gcnb_stream_t stream_) {
   return gcnb_spmm_ld_f32(p, d_values, d_perm, d_B, dim, d_C, dim, dim, stream_);
@@ -500,6 +507,9 @@ int gcnb_spmm_ld_f32(gcnb_spmm_plan *p, const float *d_values, const uint32_t *d
   if (p->n_rows == 0) return 0;
   const int ldb = (int)ldb_, ldc = (int)ldc_;
   cudaStream_t stream = as_stream(stream_);
+  if (p->bittile && d_values == p->bittile_values && !d_perm && dim == 16 && ldb == 16 && ldc == 16 &&
+      (((uintptr_t)d_B | (uintptr_t)d_C) % 16 == 0))  // tensor-core bit tiles + remainder CSR, spmm_bittile.cu
+    return gcnb_bittile_spmm16_f32(p->bittile, d_B, d_C, stream_);
   if (p->staged) {  // window-staged fast path (static values, 16-column slabs), spmm_stage.cu
     int handled = 0;
     const int rc = gcnb_stage_try_spmm(p, d_values, d_perm, d_B, ldb, d_C, ldc, dim, stream, &handled);

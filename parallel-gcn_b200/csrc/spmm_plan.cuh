@@ -117,6 +117,9 @@ struct gcnb_spmm_plan {
   int batch = 1;                      // segments claimed per atomic ticket (short-row graphs: > 1)
   gcnb::StagedDev *staged = nullptr;  // optional window-staged fast path (gcnb_spmm_plan_stage)
   int64_t own_col0 = 0, own_col1 = 0;  // gcnb_spmm_plan_set_own_cols (before staging)
+  // optional bit-tile representation (spmm_bittile.cu), borrowed: used for 16-column contiguous products with this value array
+  struct gcnb_bittile_plan *bittile = nullptr;
+  const float *bittile_values = nullptr;
 };
 
 // spmm_stage.cu: runs the staged path if it applies to this call (same values pointer, same dim, no permutation) and

@@ -97,6 +97,7 @@ struct GCNLayer {
 struct GCNEngineState {
   cudaStream_t stream = nullptr;
   gcnb_spmm_plan *graph_plan = nullptr, *feat_plan = nullptr, *feat_csc_plan = nullptr;
+  gcnb_bittile_plan *graph_bittile = nullptr;  // GCNB_BITTILE=1: tensor-core bit tiles for GraphSum at width 16
   gcnb_csc *feat_csc = nullptr;
   const uint32_t *feat_perm = nullptr;
   int feat_dense = 0;
@@ -250,6 +251,7 @@ struct GCNEngineState {
   size_t graphsum_launches(natural dim) const {
     // staged: per 16-column slab the staged kernel, the remainder kernel and the merge kernel (+ the slab packing kernel
     // when the operand is wider than a slab); a remainder combine kernel, if any, is not counted
+    if (graph_bittile && dim == 16) return 4;  // pack, MMA kernel, remainder, add
     const int slabs = graph_staged ? gcnb_spmm_plan_stage_slabs(graph_plan, (int)dim) : 0;
     if (slabs > 0) return (size_t)slabs * (dim == 16 ? 3 : 4);
     return (size_t)graph_spmm_kernels;
@@ -270,6 +272,7 @@ struct GCNEngineState {
     if (feat_csc) gcnb_csc_destroy(feat_csc);
     if (feat_plan) gcnb_spmm_plan_destroy(feat_plan);
     if (graph_plan) gcnb_spmm_plan_destroy(graph_plan);
+    if (graph_bittile) gcnb_bittile_plan_destroy(graph_bittile);
     if (side && side != stream) cudaStreamDestroy(side);
     for (cudaEvent_t e : {ev_fork, ev_join, ev_bits, ev_epoch, ev_cfork, ev_gather})
       if (e) cudaEventDestroy(e);
@@ -433,6 +436,36 @@ void GCN::init(bool quiet, const natural *h_graph_indptr, const natural *h_graph
       int64_t sinfo[8];
       GCNB_CALL(gcnb_spmm_plan_stage_info(st->graph_plan, sinfo));
       st->graph_staged = sinfo[0] != 0;
+    }
+  }
+  {
+    // opt-in (round-1 status: kernel parity-checked on B200, engine path not yet): the dense blocks of the adjacency as
+    // bit maps on the tcgen05 tensor cores (csrc/spmm_bittile.cu); takes precedence over the staged path at width 16
+    const char *e = getenv("GCNB_BITTILE");
+    bool d16 = false;
+    for (const GCNLayer &ly : st->layers) d16 |= (ly.reorder ? ly.in_dim : ly.out_dim) == 16;
+    if (e && atoi(e) != 0 && !st->dist && d16 && N > 0) {
+      const size_t nnz = dev_data.dev_graph_index.indices_size;
+      std::vector<natural> hp, hi;
+      if (!h_graph_indptr || !h_graph_indices) {
+        hp.resize((size_t)N + 1);
+        hi.resize(nnz);
+        CHECK_CUDA_ERROR(cudaMemcpy(hp.data(), dev_data.dev_graph_index.dev_indptr.get(), hp.size() * sizeof(natural), cudaMemcpyDeviceToHost));
+        CHECK_CUDA_ERROR(cudaMemcpy(hi.data(), dev_data.dev_graph_index.dev_indices.get(), nnz * sizeof(natural), cudaMemcpyDeviceToHost));
+      }
+      std::vector<real> hv(nnz);
+      CHECK_CUDA_ERROR(cudaStreamSynchronize(st->stream));
+      CHECK_CUDA_ERROR(cudaMemcpy(hv.data(), dev_data.dev_graph_value.get(), nnz * sizeof(real), cudaMemcpyDeviceToHost));
+      GCNB_CALL(gcnb_bittile_plan_create(hp.empty() ? h_graph_indptr : hp.data(), hi.empty() ? h_graph_indices : hi.data(),
+                                         hv.data(), (int64_t)N, (int64_t)N, nullptr, nullptr, 0, st->stream, &st->graph_bittile));
+      int64_t binfo[8];
+      GCNB_CALL(gcnb_bittile_plan_info(st->graph_bittile, binfo));
+      if (binfo[0] > 0 && binfo[1] * 4 >= (int64_t)nnz) {  // worth it when at least a quarter of the entries sit in tiles
+        GCNB_CALL(gcnb_spmm_plan_attach_bittile(st->graph_plan, st->graph_bittile, dev_data.dev_graph_value.get()));
+      } else {
+        gcnb_bittile_plan_destroy(st->graph_bittile);
+        st->graph_bittile = nullptr;
+      }
     }
   }
   setup_lap("variables + staged GraphSum plan");

@@ -33,19 +33,22 @@ def gcn_graph(rng, n, n_comm, deg_intra, deg_inter, dup=0, drop_diag=()):
     a = np.concatenate([src, s2, dst, d2])
     b = np.concatenate([dst, d2, src, s2])
     keep = a != b
-    pairs = np.unique(np.stack([a[keep], b[keep]], 1), axis=0)
-    rows = [[i] for i in range(n)]
-    for i, j in pairs:
-        rows[i].append(int(j))
-    for i in drop_diag:
-        rows[i] = rows[i][1:]
-    for _ in range(dup):
-        i = int(rng.integers(0, n))
-        if len(rows[i]) > 1:
-            rows[i].append(rows[i][int(rng.integers(0, len(rows[i])))])
+    key = np.unique(a[keep].astype(np.int64) * n + b[keep])          # sorted (row, neighbour) pairs, no duplicates
+    key = np.concatenate([key, np.arange(n, dtype=np.int64) * n + np.arange(n)])
+    pi, pj = key // n, key % n
+    order = np.lexsort((np.where(pi == pj, -1, pj), pi))                # per row: self first, then ascending neighbours
+    pi, pj = pi[order], pj[order]
+    alive = np.ones(pi.size, bool)
+    alive[np.nonzero((pi == pj) & np.isin(pi, np.asarray(drop_diag, np.int64)))[0]] = False
+    pi, pj = pi[alive], pj[alive]
+    if dup:
+        pick = rng.integers(0, pi.size, dup)                             # duplicate entries, appended to their rows
+        pi, pj = np.concatenate([pi, pi[pick]]), np.concatenate([pj, pj[pick]])
+        order = np.argsort(pi, kind="stable")
+        pi, pj = pi[order], pj[order]
     indptr = np.zeros(n + 1, np.uint32)
-    indptr[1:] = np.cumsum([len(r) for r in rows])
-    indices = np.fromiter((j for r in rows for j in r), np.uint32)
+    indptr[1:] = np.cumsum(np.bincount(pi, minlength=n))
+    indices = pj.astype(np.uint32)
     deg = np.diff(indptr.astype(np.int64))
     rr = np.repeat(np.arange(n), deg)
     prod = (deg[rr] * deg[indices]).astype(np.uint32).astype(np.float32)
