@@ -112,7 +112,7 @@ GCNB_API int gcnb_stage_host_destroy(gcnb_stage_host *h);
 /* Bit-tile GraphSum (parallel-gcn_b200/csrc/spmm_bittile.cu): the dense blocks of a product whose values factor as
  * value[i,j] = row_scale[i] * col_scale[j] -- GraphSum's graph_value = 1/sqrt(deg_i deg_j), src/parser.cpp:164-181 --
  * run on the tcgen05 tensor cores.  Rows are cut into blocks of 128, columns into chunks of 64; a (block, chunk) tile
- * with >= min_tile_nnz (0 = 128) entries becomes a 128 x 64 bit map, B is pre-scaled and split into three exact bf16
+ * with >= min_tile_nnz (0 = 1.6 % of the cells) entries becomes a 128 x 64 bit map (chunk_cols = 128: 128 x 128), B is pre-scaled and split into three exact bf16
  * pieces per launch, the 0/1 x bf16 products are exact and accumulate in fp32 (TMEM); every other entry (sparse tiles,
  * duplicates, values that are not the product of the scales within 1e-6 relative) stays in a remainder CSR with its
  * original value and goes through the generic kernel on a second stream.  h_* are HOST arrays (the plan copies what it
@@ -123,9 +123,10 @@ GCNB_API int gcnb_stage_host_destroy(gcnb_stage_host *h);
 typedef struct gcnb_bittile_plan gcnb_bittile_plan;
 GCNB_API int gcnb_bittile_plan_create(const uint32_t *h_indptr, const uint32_t *h_indices, const float *h_values,
                                       int64_t n_rows, int64_t n_cols, const float *h_row_scale, const float *h_col_scale,
-                                      int min_tile_nnz, gcnb_stream_t stream, gcnb_bittile_plan **out);
+                                      int min_tile_nnz, int chunk_cols /*0 = 64; 64 or 128*/, gcnb_stream_t stream,
+                                      gcnb_bittile_plan **out);
 GCNB_API int gcnb_bittile_plan_destroy(gcnb_bittile_plan *plan);
-/* out = {tiles, entries in tiles, remainder entries, row blocks, 0, CTAs, bit-map bytes, packed-B bytes} */
+/* out = {tiles, entries in tiles, remainder entries, row blocks, columns per tile, CTAs, bit-map bytes, packed-B bytes} */
 GCNB_API int gcnb_bittile_plan_info(const gcnb_bittile_plan *plan, int64_t out[8]);
 GCNB_API int gcnb_bittile_spmm16_f32(gcnb_bittile_plan *plan, const float *d_B, float *d_C, gcnb_stream_t stream);
 /* Routes later gcnb_spmm_f32 / gcnb_spmm_ld_f32 calls on `plan` that use exactly this d_values pointer, no permutation,
@@ -138,15 +139,15 @@ GCNB_API int gcnb_bittile_debug_parts(gcnb_bittile_plan *plan, int parts);
 GCNB_API int gcnb_bittile_debug_pack(gcnb_bittile_plan *plan, const float *d_B, void *h_out, int64_t bytes,
                                      gcnb_stream_t stream);
 /* The builder on its own, host memory only, no CUDA call (tests/test_bittile_cpu.py consumes the arrays exactly as the
- * kernel does).  sizes: {n_rows, n_cols, nnz, row blocks, tiles, entries in tiles, items, CTAs}; copy: which = 0
- * tile_chunk, 1 bits (uint64 x 128 per tile), 2 cta_tile_ptr, 3 cta_item_ptr, 4 items (uint32 x 2), 5 r_indptr,
+ * kernel does).  sizes: {n_rows, n_cols, nnz, row blocks, tiles, entries in tiles, items, CTAs, columns per tile}; copy: which = 0
+ * tile_chunk, 1 bits (uint64 x 128 x columns/64 per tile), 2 cta_tile_ptr, 3 cta_item_ptr, 4 items (uint32 x 2), 5 r_indptr,
  * 6 r_indices, 7 r_values, 8 row_scale, 9 col_scale (layouts: BitTileHost in spmm_bittile.cu). */
 typedef struct gcnb_bittile_host gcnb_bittile_host;
 GCNB_API int gcnb_bittile_host_build(const uint32_t *h_indptr, const uint32_t *h_indices, const float *h_values,
                                      int64_t n_rows, int64_t n_cols, const float *h_row_scale, const float *h_col_scale,
-                                     int min_tile_nnz, int n_cta /*0 = 148*/, int n_threads /*0 = auto*/,
-                                     gcnb_bittile_host **out);
-GCNB_API int gcnb_bittile_host_sizes(const gcnb_bittile_host *h, int64_t out[8]);
+                                     int min_tile_nnz, int chunk_cols /*0 = 64*/, int n_cta /*0 = 148*/,
+                                     int n_threads /*0 = auto*/, gcnb_bittile_host **out);
+GCNB_API int gcnb_bittile_host_sizes(const gcnb_bittile_host *h, int64_t out[9]);
 GCNB_API int gcnb_bittile_host_copy(const gcnb_bittile_host *h, int which, void *dst, int64_t bytes);
 GCNB_API int gcnb_bittile_host_destroy(gcnb_bittile_host *h);
 

@@ -64,12 +64,14 @@ constexpr int kBtThreads = 14 * 32;
 // Host-side plan (pure CPU; unit-tested without a GPU through gcnb_bittile_host_*).
 //   CTA q processes tiles [cta_tile_ptr[q], cta_tile_ptr[q+1]) in order; they belong to its items
 //   [cta_item_ptr[q], cta_item_ptr[q+1]);  items[k] = (row block, end position of the block's tiles RELATIVE to the
-//   CTA's first tile).  tile_chunk[t] = column chunk of tile t; bits[t*128 + r] = the 64 cells of row r of tile t:
+//   CTA's first tile).  tile_chunk[t] = column chunk of tile t; bits[t*128 + r] = the 64 cells of row r of tile t
+//   (chunk = 128: bits[(t*128 + r)*2 + w], w = column / 64):
 //   low word = columns 0..31, high word = columns 32..63; inside a word column c sits at bit (c >> 1) + 16 * (c & 1),
 //   which lets register q of the expansion (columns 2q, 2q+1 as a bf16 pair) be  (word & (0x00010001 << q)) * (0x3F80 >> q).
 struct BitTileHost {
   int64_t n_rows = 0, n_cols = 0, nnz = 0, n_blk = 0, n_tiles = 0, tile_nnz = 0;
   int n_cta = 0, min_tile_nnz = 0;
+  int chunk = kBtChunk;  // columns per tile: 64 (one 64-bit word per row) or 128 (two adjacent words per row)
   std::vector<uint32_t> tile_chunk, cta_tile_ptr, cta_item_ptr;
   std::vector<uint2> items;
   HostArray<uint64_t> bits;
@@ -106,8 +108,10 @@ struct BlockOut {
 }  // namespace
 
 int bittile_build_host(const uint32_t *indptr, const uint32_t *indices, const float *values, int64_t n_rows, int64_t n_cols,
-                       const float *row_scale, const float *col_scale, int min_tile_nnz, int n_cta, int n_threads,
-                       BitTileHost &H) {
+                       const float *row_scale, const float *col_scale, int min_tile_nnz, int chunk_cols, int n_cta,
+                       int n_threads, BitTileHost &H) {
+  if (chunk_cols == 0) chunk_cols = kBtChunk;
+  if (chunk_cols != 64 && chunk_cols != 128) return GCNB_E_BADARG;
   if (!indptr || (!indices && indptr[n_rows] > 0) || (!values && indptr[n_rows] > 0) || n_rows < 0 || n_cols < 0 ||
       n_rows > 0xfffffff0ll || n_cols > 0xfffffff0ll)
     return GCNB_E_BADARG;
@@ -116,9 +120,12 @@ int bittile_build_host(const uint32_t *indptr, const uint32_t *indices, const fl
   H.n_cols = n_cols;
   H.nnz = indptr[n_rows];
   H.n_cta = n_cta > 0 ? n_cta : 148;
-  H.min_tile_nnz = min_tile_nnz > 0 ? min_tile_nnz : 128;
+  H.chunk = chunk_cols;
+  H.min_tile_nnz = min_tile_nnz > 0 ? min_tile_nnz : 2 * chunk_cols;  // 1.6 % of the cells
   H.n_blk = (n_rows + kBtRows - 1) / kBtRows;
-  const int64_t n_chunks = (n_cols + kBtChunk - 1) / kBtChunk;
+  const int64_t n_chunks = (n_cols + chunk_cols - 1) / chunk_cols;
+  const int shift = chunk_cols == 128 ? 7 : 6;
+  const size_t wpr = (size_t)chunk_cols / 64;  // bit-map words per row of a tile
   int T = n_threads > 0 ? n_threads : (int)std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency()));
   T = (int)std::max<int64_t>(1, std::min<int64_t>(T, H.n_blk));
 
@@ -162,7 +169,7 @@ int bittile_build_host(const uint32_t *indptr, const uint32_t *indices, const fl
       const int64_t r0 = b * kBtRows, r1 = std::min<int64_t>(n_rows, r0 + kBtRows);
       touched.clear();
       for (uint32_t e = indptr[r0]; e < indptr[r1]; e++) {
-        const uint32_t c = indices[e] >> 6;
+        const uint32_t c = indices[e] >> shift;
         if (cnt[c]++ == 0) touched.push_back(c);
       }
       std::sort(touched.begin(), touched.end());
@@ -172,7 +179,7 @@ int bittile_build_host(const uint32_t *indptr, const uint32_t *indices, const fl
           o.chunks.push_back(c);
         }
       }
-      o.bits.assign(o.chunks.size() * (size_t)kBtRows, 0ull);
+      o.bits.assign(o.chunks.size() * (size_t)kBtRows * wpr, 0ull);
       for (int64_t i = r0; i < r1; i++) {
         const int rl = (int)(i - r0);
         uint32_t rc = 0;
@@ -180,13 +187,14 @@ int bittile_build_host(const uint32_t *indptr, const uint32_t *indices, const fl
         for (uint32_t e = indptr[i]; e < indptr[i + 1]; e++) {
           const uint32_t j = indices[e];
           const float v = values[e];
-          const int32_t li = sel[j >> 6];
+          const int32_t li = sel[j >> shift];
           bool in_tile = false;
           if (li >= 0) {
             const float p = si * H.col_scale[j];
             if (fabsf(v - p) <= 1e-6f * fabsf(v)) {  // false for NaN scales
-              uint64_t &w = o.bits[(size_t)li * kBtRows + rl];
-              const uint64_t m = 1ull << bt_bit_of_col(j & 63u);
+              const uint32_t cc = j & (uint32_t)(chunk_cols - 1);
+              uint64_t &w = o.bits[((size_t)li * kBtRows + rl) * wpr + (cc >> 6)];
+              const uint64_t m = 1ull << bt_bit_of_col(cc & 63u);
               if (!(w & m)) {  // a duplicate entry cannot be a second bit: remainder
                 w |= m;
                 in_tile = true;
@@ -227,7 +235,7 @@ int bittile_build_host(const uint32_t *indptr, const uint32_t *indices, const fl
       Load l = pq.top();
       pq.pop();
       per_cta[(size_t)l.second].push_back(b);
-      l.first += blocks[b].chunks.size() + 6;
+      l.first += blocks[b].chunks.size() + (size_t)(chunk_cols == 128 ? 3 : 6);
       pq.push(l);
     }
   }
@@ -252,7 +260,7 @@ int bittile_build_host(const uint32_t *indptr, const uint32_t *indices, const fl
   H.cta_item_ptr[(size_t)H.n_cta] = (uint32_t)H.items.size();
   H.n_tiles = (int64_t)tiles;
   H.tile_chunk.assign((size_t)tiles, 0u);
-  H.bits.alloc((size_t)tiles * kBtRows);
+  H.bits.alloc((size_t)tiles * kBtRows * wpr);
 
   // remainder CSR offsets
   H.r_indptr.assign((size_t)n_rows + 1, 0u);
@@ -278,7 +286,7 @@ int bittile_build_host(const uint32_t *indptr, const uint32_t *indices, const fl
       BlockOut &o = blocks[(size_t)b];
       if (!o.chunks.empty()) {
         std::copy(o.chunks.begin(), o.chunks.end(), H.tile_chunk.begin() + (ptrdiff_t)tile_base[(size_t)b]);
-        memcpy(H.bits.data() + tile_base[(size_t)b] * kBtRows, o.bits.data(), o.bits.size() * sizeof(uint64_t));
+        memcpy(H.bits.data() + tile_base[(size_t)b] * kBtRows * wpr, o.bits.data(), o.bits.size() * sizeof(uint64_t));
       }
       if (!o.ridx.empty()) {
         const size_t at = H.r_indptr[(size_t)(b * kBtRows)];
@@ -596,6 +604,197 @@ __global__ void __maxnreg__(72) bt_mma_kernel(BtArgs a) {  // 448 threads x 72 r
   }
 }
 
+// ---- second generation of the MMA kernel ------------------------------------------------------------------------------
+// First B200 numbers (profiles/r1d_bittile_summary.txt): bt_mma_kernel spends ~650 clocks per 64-column tile against 96
+// of tensor time.  The one thread that issues the MMAs pays, per tile, two mbarrier waits (~90 clocks each even when
+// already complete) and two tcgen05.commit besides the four MMAs, and every tile is a full round trip through the
+// 4-deep A ring.  This version (a) unifies the rings: stage s = B' chunk in shared memory + A operand in TMEM, ONE
+// full[s] barrier (4 expander-warp arrivals + the producer's arrive.expect_tx + the copy's bytes) and ONE free[s]
+// barrier (one commit) per tile; (b) takes tiles of W * 64 columns (W = 2: 8 MMAs, 12 KB of B', 128 bits per row per
+// tile), halving the round trips per unit of work again.  Two accumulators per set (the measured error of 73-MMA chains
+// is 0.5 ulp: the TMEM accumulate does not drift), two sets so the epilogue overlaps the next row block.
+// TMEM: stages 8/W x 32W columns = 256, accumulators 2 x 2 x 48 = 192.
+template <int W>
+struct BtWide {
+  static constexpr int kStages = 8 / W;
+  static constexpr int kACols = 32 * W;
+  static constexpr int kKSteps = 4 * W;
+  static constexpr int kChunkBytes = kKSteps * kBtKStepBytes;
+  static constexpr int kAcc = 2;
+  static constexpr int kAccCol0 = kStages * kACols;  // 256
+  static constexpr size_t kSmemBytes = (size_t)kStages * kChunkBytes + (2 * kStages + 4) * 8 + 16;
+};
+
+template <int W>
+__global__ void __maxnreg__(96) bt_mma_wide_kernel(BtArgs a) {
+  using K = BtWide<W>;
+  extern __shared__ __align__(128) uint8_t bt_smem[];
+  uint8_t *smem_b = bt_smem;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(bt_smem + K::kStages * K::kChunkBytes);
+  uint64_t *full = bars, *free_ = bars + K::kStages;
+  uint64_t *acc_full = free_ + K::kStages, *acc_empty = acc_full + 2;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = blockIdx.x;
+  const uint32_t tile0 = a.cta_tile_ptr[q];
+  const uint32_t T = a.cta_tile_ptr[q + 1] - tile0;
+  const uint32_t item0 = a.cta_item_ptr[q], item1 = a.cta_item_ptr[q + 1];
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < K::kStages; i++) {
+      mbar_init(&full[i], 5);   // 4 expander warps + the producer's arrive.expect_tx
+      mbar_init(&free_[i], 1);  // one tcgen05.commit
+    }
+    for (int i = 0; i < 2; i++) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 13) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t *>(tmem_slot);
+
+  if (warp < 8) {
+    // ---- expanders: group g = warp >> 2 takes tiles t = g, g+2, ...; thread = row
+    const int quarter = warp & 3, g = warp >> 2;
+    const uint64_t *bp = a.bits + ((size_t)tile0 * kBtRows + quarter * 32 + lane) * W;
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    constexpr size_t kTileWords = (size_t)kBtRows * W;
+    uint64_t w0[W], w1[W], w2[W];
+    uint32_t t = (uint32_t)g;
+#pragma unroll
+    for (int i = 0; i < W; i++) {
+      w0[i] = t < T ? bt_ld_bits(bp + (size_t)t * kTileWords + i) : 0ull;
+      w1[i] = t + 2 < T ? bt_ld_bits(bp + (size_t)(t + 2) * kTileWords + i) : 0ull;
+      w2[i] = t + 4 < T ? bt_ld_bits(bp + (size_t)(t + 4) * kTileWords + i) : 0ull;
+    }
+    for (; t < T; t += 2) {
+      uint64_t w3[W];
+#pragma unroll
+      for (int i = 0; i < W; i++) w3[i] = t + 6 < T ? bt_ld_bits(bp + (size_t)(t + 6) * kTileWords + i) : 0ull;
+      const uint32_t s = t % K::kStages, use = t / K::kStages;
+      if (use > 0) mbar_wait(&free_[s], (use - 1) & 1);  // the MMAs that read this stage's previous content are done
+      tc_fence_after();
+#pragma unroll
+      for (int i = 0; i < W; i++) {
+        uint32_t r[32];
+        bt_expand_word((uint32_t)w0[i], r);
+        bt_expand_word((uint32_t)(w0[i] >> 32), r + 16);
+        tc_st32(tmem + lane_base + s * K::kACols + i * 32, r);
+      }
+      tc_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[s]);
+#pragma unroll
+      for (int i = 0; i < W; i++) {
+        w0[i] = w1[i];
+        w1[i] = w2[i];
+        w2[i] = w3[i];
+      }
+    }
+  } else if (warp < 12) {
+    // ---- epilogue: thread = row (TMEM lane) of the block
+    const int quarter = warp & 3;
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    uint32_t prev_end = 0;
+    for (uint32_t it = item0; it < item1; it++) {
+      const uint2 item = a.items[it];
+      const uint32_t n_tiles = item.y - prev_end;
+      prev_end = item.y;
+      const uint32_t k = it - item0, set = k & 1, use = k >> 1;
+      const int64_t row = (int64_t)item.x * kBtRows + quarter * 32 + lane;
+      const float sc = row < a.n_rows ? __ldg(a.row_scale + row) : 0.f;
+      mbar_wait(&acc_full[set], use & 1);
+      tc_fence_after();
+      const uint32_t acc0 = tmem + lane_base + K::kAccCol0 + set * (K::kAcc * kBtN);
+      float tot[16];
+#pragma unroll
+      for (int p = 2; p >= 0; p--) {  // lo, + mid, + hi
+        float s0[16];
+        tc_ld16(acc0 + p * 16, s0);
+        if (n_tiles > 1) {
+          float s1[16];
+          tc_ld16(acc0 + kBtN + p * 16, s1);
+          tc_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 16; i++) s0[i] += s1[i];
+        } else {
+          tc_wait_ld();
+        }
+#pragma unroll
+        for (int i = 0; i < 16; i++) tot[i] = p == 2 ? s0[i] : tot[i] + s0[i];
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[set]);
+      float4 *dst = reinterpret_cast<float4 *>(a.P + row * 16);
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+        dst[i] = make_float4(sc * tot[4 * i], sc * tot[4 * i + 1], sc * tot[4 * i + 2], sc * tot[4 * i + 3]);
+    }
+  } else if (warp == 12) {
+    // ---- producer of B'
+    for (uint32_t base = 0; base < T; base += 32) {
+      const uint32_t mine = base + lane < T ? __ldg(a.tile_chunk + tile0 + base + lane) : 0u;
+      const uint32_t cnt = min(32u, T - base);
+      for (uint32_t k = 0; k < cnt; k++) {
+        const uint32_t c = __shfl_sync(0xffffffffu, mine, (int)k);
+        if (lane == 0) {
+          const uint32_t t = base + k, s = t % K::kStages, use = t / K::kStages;
+          if (use > 0) mbar_wait(&free_[s], (use - 1) & 1);
+          mbar_expect_tx(&full[s], K::kChunkBytes);
+          bulk_g2s(smem_b + s * K::kChunkBytes, a.packed + (size_t)c * K::kChunkBytes, K::kChunkBytes, &full[s]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (lane == 0) {
+    // ---- MMA issuer: one wait, 4W MMAs, one commit per tile
+    uint32_t t = 0;
+    uint2 item = item0 < item1 ? a.items[item0] : make_uint2(0, 0);
+    for (uint32_t it = item0; it < item1; it++) {
+      const uint2 next_item = it + 1 < item1 ? a.items[it + 1] : make_uint2(0, 0);
+      const uint32_t k = it - item0, set = k & 1, use = k >> 1;
+      if (use > 0) mbar_wait(&acc_empty[set], (use - 1) & 1);
+      tc_fence_after();
+      const uint32_t t_begin = t;
+      for (; t < item.y; t++) {
+        const uint32_t s = t % K::kStages, u = t / K::kStages;
+        mbar_wait(&full[s], u & 1);
+        tc_fence_after();
+        const uint32_t idx = t - t_begin;
+        const uint32_t d = tmem + K::kAccCol0 + set * (K::kAcc * kBtN) + (idx % K::kAcc) * kBtN;
+        const uint32_t b_addr = smem_u32(smem_b + s * K::kChunkBytes);
+#pragma unroll
+        for (int ks = 0; ks < K::kKSteps; ks++)
+          tc_mma_ts(d, tmem + s * K::kACols + ks * 8, bt_b_desc(b_addr + ks * kBtKStepBytes), kBtIdesc,
+                    (ks > 0 || idx >= (uint32_t)K::kAcc) ? 1u : 0u);
+        tc_commit(&free_[s]);
+      }
+      tc_commit(&acc_full[set]);
+      item = next_item;
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 13) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
+}
+
+
 __global__ void __launch_bounds__(256) bt_add_kernel(const float4 *__restrict__ P, const float4 *__restrict__ R,
                                                      float4 *__restrict__ C, int64_t n4) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
@@ -616,6 +815,8 @@ struct gcnb_bittile_host {
 struct gcnb_bittile_plan {
   int64_t n_rows = 0, n_cols = 0, nnz = 0, n_blk = 0, n_tiles = 0, tile_nnz = 0, rem_nnz = 0, n_chunks = 0;
   int n_cta = 0;
+  int chunk = kBtChunk;  // columns per tile (64: bt_mma_kernel or, with unified = 1, bt_mma_wide_kernel<1>; 128: <2>)
+  int unified = 0;
   int parts = 15;  // debugging: bit 0 pack, 1 MMA kernel, 2 remainder, 3 final add
   uint32_t *d_tile_chunk = nullptr, *d_cta_tile_ptr = nullptr, *d_cta_item_ptr = nullptr;
   uint2 *d_items = nullptr;
@@ -644,12 +845,12 @@ int bt_upload(T **dst, const T *src, size_t n, cudaStream_t stream) {
 extern "C" {
 
 int gcnb_bittile_host_build(const uint32_t *h_indptr, const uint32_t *h_indices, const float *h_values, int64_t n_rows,
-                            int64_t n_cols, const float *h_row_scale, const float *h_col_scale, int min_tile_nnz, int n_cta,
-                            int n_threads, gcnb_bittile_host **out) {
+                            int64_t n_cols, const float *h_row_scale, const float *h_col_scale, int min_tile_nnz,
+                            int chunk_cols, int n_cta, int n_threads, gcnb_bittile_host **out) {
   if (!out) return GCNB_E_BADARG;
   auto *h = new gcnb_bittile_host();
   const int rc = bittile_build_host(h_indptr, h_indices, h_values, n_rows, n_cols, h_row_scale, h_col_scale, min_tile_nnz,
-                                    n_cta, n_threads, h->H);
+                                    chunk_cols, n_cta, n_threads, h->H);
   if (rc) {
     delete h;
     return rc;
@@ -658,11 +859,11 @@ int gcnb_bittile_host_build(const uint32_t *h_indptr, const uint32_t *h_indices,
   return 0;
 }
 
-int gcnb_bittile_host_sizes(const gcnb_bittile_host *h, int64_t out[8]) {
+int gcnb_bittile_host_sizes(const gcnb_bittile_host *h, int64_t out[9]) {
   if (!h || !out) return GCNB_E_BADARG;
   const BitTileHost &H = h->H;
   out[0] = H.n_rows; out[1] = H.n_cols; out[2] = H.nnz; out[3] = H.n_blk; out[4] = H.n_tiles; out[5] = H.tile_nnz;
-  out[6] = (int64_t)H.items.size(); out[7] = H.n_cta;
+  out[6] = (int64_t)H.items.size(); out[7] = H.n_cta; out[8] = H.chunk;
   return 0;
 }
 
@@ -710,7 +911,7 @@ int gcnb_bittile_plan_destroy(gcnb_bittile_plan *p) {
 
 int gcnb_bittile_plan_create(const uint32_t *h_indptr, const uint32_t *h_indices, const float *h_values, int64_t n_rows,
                              int64_t n_cols, const float *h_row_scale, const float *h_col_scale, int min_tile_nnz,
-                             gcnb_stream_t stream_, gcnb_bittile_plan **out) {
+                             int chunk_cols, gcnb_stream_t stream_, gcnb_bittile_plan **out) {
   if (!out) return GCNB_E_BADARG;
   *out = nullptr;
   const DeviceInfo &di = device_info();
@@ -718,8 +919,12 @@ int gcnb_bittile_plan_create(const uint32_t *h_indptr, const uint32_t *h_indices
   if (di.cc_major != 10) return GCNB_E_UNSUPPORTED;  // tcgen05 / TMEM
   cudaStream_t stream = as_stream(stream_);
   BitTileHost H;
+  int unified = 0;
+  if (const char *e = getenv("GCNB_BT_UNIFIED")) unified = atoi(e) != 0;  // tuning probe: 64-column tiles on the new kernel
+  if (chunk_cols == 0)
+    if (const char *e = getenv("GCNB_BT_CHUNK")) chunk_cols = atoi(e);    // tuning probe: 64 (default) or 128
   int rc = bittile_build_host(h_indptr, h_indices, h_values, n_rows, n_cols, h_row_scale, h_col_scale, min_tile_nnz,
-                              di.sm_count, 0, H);
+                              chunk_cols, di.sm_count, 0, H);
   if (rc) return rc;
   auto *p = new gcnb_bittile_plan();
   auto fail = [&](int code) {
@@ -728,7 +933,9 @@ int gcnb_bittile_plan_create(const uint32_t *h_indptr, const uint32_t *h_indices
   };
   p->n_rows = n_rows; p->n_cols = n_cols; p->nnz = H.nnz; p->n_blk = H.n_blk; p->n_tiles = H.n_tiles;
   p->tile_nnz = H.tile_nnz; p->rem_nnz = (int64_t)H.r_indices.size(); p->n_cta = H.n_cta;
-  p->n_chunks = (n_cols + kBtChunk - 1) / kBtChunk;
+  p->chunk = H.chunk;
+  p->unified = unified || H.chunk == 128;
+  p->n_chunks = (n_cols + 127) / 128 * 2;  // 64-row units of the packed B' image, padded to whole 128-column chunks
   if ((rc = bt_upload(&p->d_tile_chunk, H.tile_chunk.data(), H.tile_chunk.size(), stream))) return fail(rc);
   if ((rc = bt_upload(&p->d_bits, H.bits.data(), H.bits.size(), stream))) return fail(rc);
   if ((rc = bt_upload(&p->d_cta_tile_ptr, H.cta_tile_ptr.data(), H.cta_tile_ptr.size(), stream))) return fail(rc);
@@ -752,6 +959,12 @@ int gcnb_bittile_plan_create(const uint32_t *h_indptr, const uint32_t *h_indices
   if ((rc = (int)cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming))) return fail(rc);
   if ((rc = (int)cudaFuncSetAttribute(bt_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBtSmemBytes)))
     return fail(rc);
+  if ((rc = (int)cudaFuncSetAttribute(bt_mma_wide_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)BtWide<1>::kSmemBytes)))
+    return fail(rc);
+  if ((rc = (int)cudaFuncSetAttribute(bt_mma_wide_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)BtWide<2>::kSmemBytes)))
+    return fail(rc);
   *out = p;
   return 0;
 }
@@ -759,8 +972,8 @@ int gcnb_bittile_plan_create(const uint32_t *h_indptr, const uint32_t *h_indices
 // out = {tiles, entries in tiles, remainder entries, row blocks, items (blocks with tiles), CTAs, bit-map bytes, packed B' bytes}
 int gcnb_bittile_plan_info(const gcnb_bittile_plan *p, int64_t out[8]) {
   if (!p || !out) return GCNB_E_BADARG;
-  out[0] = p->n_tiles; out[1] = p->tile_nnz; out[2] = p->rem_nnz; out[3] = p->n_blk; out[4] = 0; out[5] = p->n_cta;
-  out[6] = p->n_tiles * (int64_t)kBtRows * 8; out[7] = p->n_chunks * (int64_t)kBtChunkBytes;
+  out[0] = p->n_tiles; out[1] = p->tile_nnz; out[2] = p->rem_nnz; out[3] = p->n_blk; out[4] = p->chunk; out[5] = p->n_cta;
+  out[6] = p->n_tiles * (int64_t)kBtRows * (p->chunk / 8); out[7] = p->n_chunks * (int64_t)kBtChunkBytes;
   return 0;
 }
 
@@ -808,7 +1021,9 @@ int gcnb_bittile_spmm16_f32(gcnb_bittile_plan *p, const float *d_B, float *d_C, 
     a.tile_chunk = p->d_tile_chunk; a.bits = p->d_bits; a.cta_tile_ptr = p->d_cta_tile_ptr;
     a.cta_item_ptr = p->d_cta_item_ptr; a.items = p->d_items; a.packed = p->d_packed; a.row_scale = p->d_row_scale;
     a.P = p->d_P; a.n_rows = p->n_rows;
-    bt_mma_kernel<<<p->n_cta, kBtThreads, kBtSmemBytes, stream>>>(a);
+    if (p->chunk == 128) bt_mma_wide_kernel<2><<<p->n_cta, kBtThreads, BtWide<2>::kSmemBytes, stream>>>(a);
+    else if (p->unified) bt_mma_wide_kernel<1><<<p->n_cta, kBtThreads, BtWide<1>::kSmemBytes, stream>>>(a);
+    else bt_mma_kernel<<<p->n_cta, kBtThreads, kBtSmemBytes, stream>>>(a);
     GCNB_LAUNCH_CHECK();
   }
   GCNB_CHECK(cudaStreamWaitEvent(p->aux, p->ev_fork, 0));

@@ -27,6 +27,8 @@ ap.add_argument("--scale", type=int, default=8)
 ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--min-tile-nnz", type=int, default=0)
 ap.add_argument("--staged", type=int, default=1, help="also time the window-staged path")
+ap.add_argument("--chunk", type=int, default=0, help="columns per tile: 64 (default) or 128; GCNB_BT_UNIFIED=1 selects the\n"
+                "second-generation kernel for 64")
 ap.add_argument("--out", default="gpurun_out/probe_bittile.jsonl")
 args = ap.parse_args()
 dev = torch.device("cuda:0")
@@ -53,7 +55,7 @@ def dense_case(name, n, density, seed, cols_used=None, dump=False):
     indices = cols.astype(np.uint32)
     values = (rs[rows] * cs[cols]).astype(np.float32)
     B = rng.standard_normal((n, 16)).astype(np.float32)
-    plan = gcnb.BitTilePlan(indptr, indices, values, n, rs, cs, min_tile_nnz=1)
+    plan = gcnb.BitTilePlan(indptr, indices, values, n, rs, cs, min_tile_nnz=1, chunk_cols=args.chunk)
     info = plan.info()
     Bd = torch.from_numpy(B).to(dev)
     packed = plan.debug_pack(Bd)
@@ -81,7 +83,7 @@ def graph_case(scale):
     indptr, indices = eng.synth_graph(n, m, n_blocks=max(2, 50 // scale))
     values = eng.synth_graph_values(indptr, indices, 0, np.diff(indptr).astype(np.uint32))  # parser.cpp:164-181 formula
     t1 = time.time()
-    plan = gcnb.BitTilePlan(indptr, indices, values, n, min_tile_nnz=args.min_tile_nnz)
+    plan = gcnb.BitTilePlan(indptr, indices, values, n, min_tile_nnz=args.min_tile_nnz, chunk_cols=args.chunk)
     t2 = time.time()
     info = plan.info()
     emit(case="graph/%d" % scale, step="plan", n=n, nnz=int(indices.size), gen_s=t1 - t0, plan_s=t2 - t1, info=info)

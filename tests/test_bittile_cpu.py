@@ -73,7 +73,7 @@ def bf16_split(x):
 def pack_b(B, col_scale):
     """bt_pack_kernel: thread (group of 8 rows of B, column) writes three 16-byte vectors into the chunk image"""
     n_cols = B.shape[0]
-    n_chunks = (n_cols + CHUNK - 1) // CHUNK
+    n_chunks = (n_cols + 127) // 128 * 2  # 64-row units, padded to whole 128-column chunks
     Bp = np.zeros((n_chunks * CHUNK, 16), np.float32)
     Bp[:n_cols] = col_scale[:, None].astype(np.float32) * B.astype(np.float32)
     pieces = bf16_split(Bp)
@@ -89,10 +89,11 @@ def pack_b(B, col_scale):
     return packed, Bp
 
 
-def read_b_operand(packed, chunk, ks):
+def read_b_operand(packed, chunk, ks, chunk_cols=CHUNK):
     """what tcgen05.mma reads through bt_b_desc: element (n, k) of the 48 x 16 operand at
-    start + (k / 8) * LBO + (n / 8) * SBO + (n % 8) * 16 + (k % 8) * 2 with LBO = 768, SBO = 128 (K-major, no swizzle)"""
-    start = chunk * CHUNK_BYTES + ks * KSTEP_BYTES
+    start + (k / 8) * LBO + (n / 8) * SBO + (n % 8) * 16 + (k % 8) * 2 with LBO = 768, SBO = 128 (K-major, no swizzle);
+    the image is chunk-size independent: k-step after k-step of 16 rows of B, a chunk is chunk_cols / 16 of them"""
+    start = chunk * (chunk_cols // 16) * KSTEP_BYTES + ks * KSTEP_BYTES
     n = np.arange(48)[:, None]
     k = np.arange(16)[None, :]
     off = start + (k // 8) * 768 + (n // 8) * 128 + (n % 8) * 16 + (k % 8) * 2
@@ -120,7 +121,8 @@ def expand_words(words):
 
 
 def emulate(plan, B):
-    n_rows = plan["n_rows"]
+    n_rows, CH = plan["n_rows"], plan["chunk"]
+    NACC = 4 if CH == 64 else 2  # bt_mma_kernel / bt_mma_wide_kernel<2>
     packed, _ = pack_b(B, plan["col_scale"])
     P = np.zeros((plan["n_blk"] * ROWS, 16), np.float64)
     cells = []
@@ -139,12 +141,12 @@ def emulate(plan, B):
             for idx in range(end - pos):
                 t = t0 + pos + idx
                 tile_seen[t] += 1
-                A = expand_words(plan["bits"][t])
-                for ks in range(4):
-                    Bop = read_b_operand(packed, int(chunks[idx]), ks)  # [48, 16]
+                A = np.concatenate([expand_words(plan["bits"][t][:, w]) for w in range(CH // 64)], 1)  # [128, CH]
+                for ks in range(CH // 16):
+                    Bop = read_b_operand(packed, int(chunks[idx]), ks, CH)  # [48, 16]
                     acc[idx % NACC] += A[:, ks * 16:(ks + 1) * 16].astype(np.float64) @ Bop.T.astype(np.float64)
                 r, c = np.nonzero(A)
-                cells.append(np.stack([blk * ROWS + r, int(chunks[idx]) * CHUNK + c], 1))
+                cells.append(np.stack([blk * ROWS + r, int(chunks[idx]) * CH + c], 1))
             s = acc[0].copy()
             for a in range(1, min(NACC, end - pos)):
                 s += acc[a]
@@ -163,13 +165,16 @@ def emulate(plan, B):
     return P[:n_rows] + R, cells, rrows
 
 
-def check_plan(gcnb, indptr, indices, values, B, explicit_scales=False, min_tile_nnz=0, n_cta=0, expect_tiles=True):
+def check_plan(gcnb, indptr, indices, values, B, explicit_scales=False, min_tile_nnz=0, n_cta=0, expect_tiles=True,
+               chunk_cols=0):
     n = len(indptr) - 1
     deg = np.diff(indptr.astype(np.int64))
     rs = cs = None
     if explicit_scales:
         rs = cs = (1.0 / np.sqrt(deg.astype(np.float32))).astype(np.float32)
-    plan = gcnb.bittile_host_build(indptr, indices, values, n, rs, cs, min_tile_nnz=min_tile_nnz, n_cta=n_cta)
+    plan = gcnb.bittile_host_build(indptr, indices, values, n, rs, cs, min_tile_nnz=min_tile_nnz, n_cta=n_cta,
+                                   chunk_cols=chunk_cols)
+    assert plan["chunk"] == (chunk_cols or 64)
     assert plan["nnz"] == indices.size and plan["tile_nnz"] + plan["rem_nnz"] == indices.size
     out, cells, rrows = emulate(plan, B)
     assert len(cells) == plan["tile_nnz"]
@@ -198,30 +203,33 @@ def test_bit_position_formula_is_a_permutation(gcnb):
     assert np.array_equal(A[:64], np.eye(64, dtype=np.float32)) and not A[64:].any()
 
 
-def test_community_graph_matches_csr_product(gcnb):
+@pytest.mark.parametrize("chunk_cols", [0, 128])
+def test_community_graph_matches_csr_product(gcnb, chunk_cols):
     rng = np.random.default_rng(7)
     indptr, indices, values = gcn_graph(rng, 1500, 5, 24, 3)
     B = rng.standard_normal((1500, 16)).astype(np.float32)
-    plan = check_plan(gcnb, indptr, indices, values, B, min_tile_nnz=96, n_cta=5)
+    thr = 96 * (2 if chunk_cols == 128 else 1)
+    plan = check_plan(gcnb, indptr, indices, values, B, min_tile_nnz=thr, n_cta=5, chunk_cols=chunk_cols)
     assert plan["tile_nnz"] > 0.5 * indices.size
     # explicit 1/sqrt(deg) scales select the same entries
-    plan2 = check_plan(gcnb, indptr, indices, values, B, explicit_scales=True, min_tile_nnz=96, n_cta=5)
+    plan2 = check_plan(gcnb, indptr, indices, values, B, explicit_scales=True, min_tile_nnz=thr, n_cta=5, chunk_cols=chunk_cols)
     assert plan2["tile_nnz"] == plan["tile_nnz"]
 
 
-def test_duplicates_missing_diagonals_and_ragged_sizes(gcnb):
+@pytest.mark.parametrize("chunk_cols", [64, 128])
+def test_duplicates_missing_diagonals_and_ragged_sizes(gcnb, chunk_cols):
     rng = np.random.default_rng(11)
     n = 777  # not a multiple of 128 or 64
     indptr, indices, values = gcn_graph(rng, n, 3, 30, 2, dup=40, drop_diag=(5, 300, 776))
     B = rng.standard_normal((n, 16)).astype(np.float32)
-    plan = check_plan(gcnb, indptr, indices, values, B, min_tile_nnz=64, n_cta=148)
+    plan = check_plan(gcnb, indptr, indices, values, B, min_tile_nnz=64, n_cta=148, chunk_cols=chunk_cols)
     # rows without a diagonal entry have no scale: none of their entries (nor entries pointing at them) is in a bit map
     for i in (5, 300, 776):
         assert plan["row_scale"][i] == 0 and plan["col_scale"][i] == 0
     # values that do not factor stay in the remainder with their original value
     values2 = values.copy()
     values2[::7] *= 1.5
-    check_plan(gcnb, indptr, indices, values2, B, min_tile_nnz=64, n_cta=7)
+    check_plan(gcnb, indptr, indices, values2, B, min_tile_nnz=64, n_cta=7, chunk_cols=chunk_cols)
 
 
 def test_sparse_graph_has_no_tiles_and_empty_graph(gcnb):
