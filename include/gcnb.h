@@ -123,10 +123,12 @@ GCNB_API int gcnb_stage_host_destroy(gcnb_stage_host *h);
 typedef struct gcnb_bittile_plan gcnb_bittile_plan;
 GCNB_API int gcnb_bittile_plan_create(const uint32_t *h_indptr, const uint32_t *h_indices, const float *h_values,
                                       int64_t n_rows, int64_t n_cols, const float *h_row_scale, const float *h_col_scale,
-                                      int min_tile_nnz, int chunk_cols /*0 = 64; 64 or 128*/, gcnb_stream_t stream,
+                                      int min_tile_nnz, int chunk_cols /*0 = 64; 64 or 128*/,
+                                      int row_blocks /*0 = 1; 2 = items of 256 rows (chunk 64 only)*/, gcnb_stream_t stream,
                                       gcnb_bittile_plan **out);
 GCNB_API int gcnb_bittile_plan_destroy(gcnb_bittile_plan *plan);
-/* out = {tiles, entries in tiles, remainder entries, row blocks, columns per tile, CTAs, bit-map bytes, packed-B bytes} */
+/* out = {tiles, entries in tiles, remainder entries, items' row blocks, columns per tile + 1000 * row_blocks, CTAs,
+ * bit-map bytes, packed-B bytes} */
 GCNB_API int gcnb_bittile_plan_info(const gcnb_bittile_plan *plan, int64_t out[8]);
 GCNB_API int gcnb_bittile_spmm16_f32(gcnb_bittile_plan *plan, const float *d_B, float *d_C, gcnb_stream_t stream);
 /* Routes later gcnb_spmm_f32 / gcnb_spmm_ld_f32 calls on `plan` that use exactly this d_values pointer, no permutation,
@@ -139,15 +141,16 @@ GCNB_API int gcnb_bittile_debug_parts(gcnb_bittile_plan *plan, int parts);
 GCNB_API int gcnb_bittile_debug_pack(gcnb_bittile_plan *plan, const float *d_B, void *h_out, int64_t bytes,
                                      gcnb_stream_t stream);
 /* The builder on its own, host memory only, no CUDA call (tests/test_bittile_cpu.py consumes the arrays exactly as the
- * kernel does).  sizes: {n_rows, n_cols, nnz, row blocks, tiles, entries in tiles, items, CTAs, columns per tile}; copy: which = 0
- * tile_chunk, 1 bits (uint64 x 128 x columns/64 per tile), 2 cta_tile_ptr, 3 cta_item_ptr, 4 items (uint32 x 2), 5 r_indptr,
+ * kernel does).  sizes: {n_rows, n_cols, nnz, blocks of 128 * row_blocks rows, tiles, entries in tiles, items, CTAs, columns per tile,
+ * row_blocks}; copy: which = 0
+ * tile_chunk, 1 bits (uint64 x row_blocks x 128 x columns/64 per tile), 2 cta_tile_ptr, 3 cta_item_ptr, 4 items (uint32 x 2), 5 r_indptr,
  * 6 r_indices, 7 r_values, 8 row_scale, 9 col_scale (layouts: BitTileHost in spmm_bittile.cu). */
 typedef struct gcnb_bittile_host gcnb_bittile_host;
 GCNB_API int gcnb_bittile_host_build(const uint32_t *h_indptr, const uint32_t *h_indices, const float *h_values,
                                      int64_t n_rows, int64_t n_cols, const float *h_row_scale, const float *h_col_scale,
-                                     int min_tile_nnz, int chunk_cols /*0 = 64*/, int n_cta /*0 = 148*/,
-                                     int n_threads /*0 = auto*/, gcnb_bittile_host **out);
-GCNB_API int gcnb_bittile_host_sizes(const gcnb_bittile_host *h, int64_t out[9]);
+                                     int min_tile_nnz, int chunk_cols /*0 = 64*/, int row_blocks /*0 = 1*/,
+                                     int n_cta /*0 = 148*/, int n_threads /*0 = auto*/, gcnb_bittile_host **out);
+GCNB_API int gcnb_bittile_host_sizes(const gcnb_bittile_host *h, int64_t out[10]);
 GCNB_API int gcnb_bittile_host_copy(const gcnb_bittile_host *h, int which, void *dst, int64_t bytes);
 GCNB_API int gcnb_bittile_host_destroy(gcnb_bittile_host *h);
 

@@ -57,14 +57,14 @@ _sig("gcnb_spmm_stage_own_f32", I32, [P, P, P, I32, P, P])
 _sig("gcnb_stage_host_sizes", I32, [P, P])
 _sig("gcnb_stage_host_copy", I32, [P, I32, P, I64])
 _sig("gcnb_stage_host_destroy", I32, [P])
-_sig("gcnb_bittile_plan_create", I32, [P, P, P, I64, I64, P, P, I32, I32, P, P])
+_sig("gcnb_bittile_plan_create", I32, [P, P, P, I64, I64, P, P, I32, I32, I32, P, P])
 _sig("gcnb_bittile_plan_destroy", I32, [P])
 _sig("gcnb_bittile_plan_info", I32, [P, P])
 _sig("gcnb_bittile_spmm16_f32", I32, [P, P, P, P])
 _sig("gcnb_bittile_debug_pack", I32, [P, P, P, I64, P])
 _sig("gcnb_bittile_debug_parts", I32, [P, I32])
 _sig("gcnb_spmm_plan_attach_bittile", I32, [P, P, P])
-_sig("gcnb_bittile_host_build", I32, [P, P, P, I64, I64, P, P, I32, I32, I32, I32, P])
+_sig("gcnb_bittile_host_build", I32, [P, P, P, I64, I64, P, P, I32, I32, I32, I32, I32, P])
 _sig("gcnb_bittile_host_sizes", I32, [P, P])
 _sig("gcnb_bittile_host_copy", I32, [P, I32, P, I64])
 _sig("gcnb_bittile_host_destroy", I32, [P])
@@ -253,7 +253,7 @@ def _np_ptr(a):
 
 
 def bittile_host_build(indptr, indices, values, n_cols, row_scale=None, col_scale=None, min_tile_nnz=0, n_cta=0, n_threads=0,
-                       chunk_cols=0):
+                       chunk_cols=0, row_blocks=0):
     """Host-only run of the bit-tile builder (no CUDA): plan arrays as numpy (BitTileHost, csrc/spmm_bittile.cu)."""
     import numpy as np
     indptr = np.ascontiguousarray(indptr, np.uint32)
@@ -263,11 +263,11 @@ def bittile_host_build(indptr, indices, values, n_cols, row_scale=None, col_scal
     cs = None if col_scale is None else np.ascontiguousarray(col_scale, np.float32)
     h = C.c_void_p()
     check(lib.gcnb_bittile_host_build(_np_ptr(indptr), _np_ptr(indices), _np_ptr(values), len(indptr) - 1, int(n_cols),
-                                      _np_ptr(rs), _np_ptr(cs), min_tile_nnz, chunk_cols, n_cta, n_threads, C.byref(h)))
+                                      _np_ptr(rs), _np_ptr(cs), min_tile_nnz, chunk_cols, row_blocks, n_cta, n_threads, C.byref(h)))
     try:
-        sz = (I64 * 9)()
+        sz = (I64 * 10)()
         check(lib.gcnb_bittile_host_sizes(h, sz))
-        keys = ("n_rows", "n_cols", "nnz", "n_blk", "n_tiles", "tile_nnz", "n_items", "n_cta", "chunk")
+        keys = ("n_rows", "n_cols", "nnz", "n_blk", "n_tiles", "tile_nnz", "n_items", "n_cta", "chunk", "rb")
         out = dict(zip(keys, [int(x) for x in sz]))
 
         def grab(which, n, dtype):
@@ -276,8 +276,8 @@ def bittile_host_build(indptr, indices, values, n_cols, row_scale=None, col_scal
                 check(lib.gcnb_bittile_host_copy(h, which, a.ctypes.data_as(C.c_void_p), a.nbytes))
             return a
         out["tile_chunk"] = grab(0, out["n_tiles"], np.uint32)
-        wpr = out["chunk"] // 64
-        out["bits"] = grab(1, out["n_tiles"] * 128 * wpr, np.uint64).reshape(-1, 128, wpr)
+        wpr, rb = out["chunk"] // 64, out["rb"]
+        out["bits"] = grab(1, out["n_tiles"] * rb * 128 * wpr, np.uint64).reshape(-1, rb, 128, wpr)
         out["cta_tile_ptr"] = grab(2, out["n_cta"] + 1, np.uint32)
         out["cta_item_ptr"] = grab(3, out["n_cta"] + 1, np.uint32)
         out["items"] = grab(4, out["n_items"] * 2, np.uint32).reshape(-1, 2)
@@ -295,7 +295,8 @@ def bittile_host_build(indptr, indices, values, n_cols, row_scale=None, col_scal
 class BitTilePlan:
     """gcnb_bittile_plan: tensor-core GraphSum on 128 x 64 bit-map tiles + remainder CSR (host numpy CSR in, device plan)."""
 
-    def __init__(self, indptr, indices, values, n_cols, row_scale=None, col_scale=None, min_tile_nnz=0, chunk_cols=0):
+    def __init__(self, indptr, indices, values, n_cols, row_scale=None, col_scale=None, min_tile_nnz=0, chunk_cols=0,
+                 row_blocks=0):
         import numpy as np
         indptr = np.ascontiguousarray(indptr, np.uint32)
         indices = np.ascontiguousarray(indices, np.uint32)
@@ -304,13 +305,15 @@ class BitTilePlan:
         cs = None if col_scale is None else np.ascontiguousarray(col_scale, np.float32)
         self.h = C.c_void_p()
         check(lib.gcnb_bittile_plan_create(_np_ptr(indptr), _np_ptr(indices), _np_ptr(values), len(indptr) - 1, int(n_cols),
-                                           _np_ptr(rs), _np_ptr(cs), min_tile_nnz, chunk_cols, stream(), C.byref(self.h)))
+                                           _np_ptr(rs), _np_ptr(cs), min_tile_nnz, chunk_cols, row_blocks, stream(), C.byref(self.h)))
 
     def info(self):
         out = (I64 * 8)()
         check(lib.gcnb_bittile_plan_info(self.h, out))
         keys = ("n_tiles", "tile_nnz", "rem_nnz", "n_blk", "chunk", "n_cta", "bitmap_bytes", "packed_bytes")
-        return dict(zip(keys, [int(x) for x in out]))
+        d = dict(zip(keys, [int(x) for x in out]))
+        d["rb"], d["chunk"] = d["chunk"] // 1000, d["chunk"] % 1000
+        return d
 
     def spmm16(self, B, C_out):
         check(lib.gcnb_bittile_spmm16_f32(self.h, ptr(B), ptr(C_out), stream()))

@@ -65,13 +65,15 @@ constexpr int kBtThreads = 14 * 32;
 //   CTA q processes tiles [cta_tile_ptr[q], cta_tile_ptr[q+1]) in order; they belong to its items
 //   [cta_item_ptr[q], cta_item_ptr[q+1]);  items[k] = (row block, end position of the block's tiles RELATIVE to the
 //   CTA's first tile).  tile_chunk[t] = column chunk of tile t; bits[t*128 + r] = the 64 cells of row r of tile t
-//   (chunk = 128: bits[(t*128 + r)*2 + w], w = column / 64):
+//   (in general bits[((t*rb + sub)*128 + r)*(chunk/64) + w]: sub = 128-row half of a 256-row item, w = column / 64;
+//   items[k].x counts blocks of 128*rb rows):
 //   low word = columns 0..31, high word = columns 32..63; inside a word column c sits at bit (c >> 1) + 16 * (c & 1),
 //   which lets register q of the expansion (columns 2q, 2q+1 as a bf16 pair) be  (word & (0x00010001 << q)) * (0x3F80 >> q).
 struct BitTileHost {
   int64_t n_rows = 0, n_cols = 0, nnz = 0, n_blk = 0, n_tiles = 0, tile_nnz = 0;
   int n_cta = 0, min_tile_nnz = 0;
   int chunk = kBtChunk;  // columns per tile: 64 (one 64-bit word per row) or 128 (two adjacent words per row)
+  int rb = 1;            // row blocks of 128 per item (2: super-tiles of 256 rows whose two MMAs share one B' stage)
   std::vector<uint32_t> tile_chunk, cta_tile_ptr, cta_item_ptr;
   std::vector<uint2> items;
   HostArray<uint64_t> bits;
@@ -101,17 +103,20 @@ struct BlockOut {
   std::vector<uint64_t> bits;
   std::vector<uint32_t> ridx;
   std::vector<float> rval;
-  uint32_t rcount[kBtRows];
+  uint32_t rcount[2 * kBtRows];
   int64_t tile_nnz = 0;
 };
 
 }  // namespace
 
 int bittile_build_host(const uint32_t *indptr, const uint32_t *indices, const float *values, int64_t n_rows, int64_t n_cols,
-                       const float *row_scale, const float *col_scale, int min_tile_nnz, int chunk_cols, int n_cta,
-                       int n_threads, BitTileHost &H) {
+                       const float *row_scale, const float *col_scale, int min_tile_nnz, int chunk_cols, int row_blocks,
+                       int n_cta, int n_threads, BitTileHost &H) {
   if (chunk_cols == 0) chunk_cols = kBtChunk;
+  if (row_blocks == 0) row_blocks = 1;
   if (chunk_cols != 64 && chunk_cols != 128) return GCNB_E_BADARG;
+  if (row_blocks != 1 && !(row_blocks == 2 && chunk_cols == 64)) return GCNB_E_BADARG;
+  const int64_t BH = (int64_t)kBtRows * row_blocks;  // rows per item
   if (!indptr || (!indices && indptr[n_rows] > 0) || (!values && indptr[n_rows] > 0) || n_rows < 0 || n_cols < 0 ||
       n_rows > 0xfffffff0ll || n_cols > 0xfffffff0ll)
     return GCNB_E_BADARG;
@@ -121,8 +126,9 @@ int bittile_build_host(const uint32_t *indptr, const uint32_t *indices, const fl
   H.nnz = indptr[n_rows];
   H.n_cta = n_cta > 0 ? n_cta : 148;
   H.chunk = chunk_cols;
-  H.min_tile_nnz = min_tile_nnz > 0 ? min_tile_nnz : 2 * chunk_cols;  // 1.6 % of the cells
-  H.n_blk = (n_rows + kBtRows - 1) / kBtRows;
+  H.rb = row_blocks;
+  H.min_tile_nnz = min_tile_nnz > 0 ? min_tile_nnz : 2 * chunk_cols * row_blocks;  // 1.6 % of the cells
+  H.n_blk = (n_rows + BH - 1) / BH;
   const int64_t n_chunks = (n_cols + chunk_cols - 1) / chunk_cols;
   const int shift = chunk_cols == 128 ? 7 : 6;
   const size_t wpr = (size_t)chunk_cols / 64;  // bit-map words per row of a tile
@@ -166,7 +172,7 @@ int bittile_build_host(const uint32_t *indptr, const uint32_t *indices, const fl
       const int64_t b = next.fetch_add(1);
       if (b >= H.n_blk) break;
       BlockOut &o = blocks[(size_t)b];
-      const int64_t r0 = b * kBtRows, r1 = std::min<int64_t>(n_rows, r0 + kBtRows);
+      const int64_t r0 = b * BH, r1 = std::min<int64_t>(n_rows, r0 + BH);
       touched.clear();
       for (uint32_t e = indptr[r0]; e < indptr[r1]; e++) {
         const uint32_t c = indices[e] >> shift;
@@ -179,7 +185,7 @@ int bittile_build_host(const uint32_t *indptr, const uint32_t *indices, const fl
           o.chunks.push_back(c);
         }
       }
-      o.bits.assign(o.chunks.size() * (size_t)kBtRows * wpr, 0ull);
+      o.bits.assign(o.chunks.size() * (size_t)BH * wpr, 0ull);
       for (int64_t i = r0; i < r1; i++) {
         const int rl = (int)(i - r0);
         uint32_t rc = 0;
@@ -193,7 +199,7 @@ int bittile_build_host(const uint32_t *indptr, const uint32_t *indices, const fl
             const float p = si * H.col_scale[j];
             if (fabsf(v - p) <= 1e-6f * fabsf(v)) {  // false for NaN scales
               const uint32_t cc = j & (uint32_t)(chunk_cols - 1);
-              uint64_t &w = o.bits[((size_t)li * kBtRows + rl) * wpr + (cc >> 6)];
+              uint64_t &w = o.bits[((size_t)li * BH + rl) * wpr + (cc >> 6)];  // rl = sub * 128 + row
               const uint64_t m = 1ull << bt_bit_of_col(cc & 63u);
               if (!(w & m)) {  // a duplicate entry cannot be a second bit: remainder
                 w |= m;
@@ -235,7 +241,7 @@ int bittile_build_host(const uint32_t *indptr, const uint32_t *indices, const fl
       Load l = pq.top();
       pq.pop();
       per_cta[(size_t)l.second].push_back(b);
-      l.first += blocks[b].chunks.size() + (size_t)(chunk_cols == 128 ? 3 : 6);
+      l.first += (blocks[b].chunks.size() + (size_t)(chunk_cols == 128 ? 3 : 6)) * (size_t)row_blocks;
       pq.push(l);
     }
   }
@@ -260,7 +266,7 @@ int bittile_build_host(const uint32_t *indptr, const uint32_t *indices, const fl
   H.cta_item_ptr[(size_t)H.n_cta] = (uint32_t)H.items.size();
   H.n_tiles = (int64_t)tiles;
   H.tile_chunk.assign((size_t)tiles, 0u);
-  H.bits.alloc((size_t)tiles * kBtRows * wpr);
+  H.bits.alloc((size_t)tiles * BH * wpr);
 
   // remainder CSR offsets
   H.r_indptr.assign((size_t)n_rows + 1, 0u);
@@ -268,7 +274,7 @@ int bittile_build_host(const uint32_t *indptr, const uint32_t *indices, const fl
   H.tile_nnz = 0;
   for (int64_t b = 0; b < H.n_blk; b++) {
     const BlockOut &o = blocks[(size_t)b];
-    const int64_t r0 = b * kBtRows, r1 = std::min<int64_t>(n_rows, r0 + kBtRows);
+    const int64_t r0 = b * BH, r1 = std::min<int64_t>(n_rows, r0 + BH);
     for (int64_t i = r0; i < r1; i++) {
       H.r_indptr[(size_t)i] = (uint32_t)racc;
       racc += o.rcount[i - r0];
@@ -286,10 +292,10 @@ int bittile_build_host(const uint32_t *indptr, const uint32_t *indices, const fl
       BlockOut &o = blocks[(size_t)b];
       if (!o.chunks.empty()) {
         std::copy(o.chunks.begin(), o.chunks.end(), H.tile_chunk.begin() + (ptrdiff_t)tile_base[(size_t)b]);
-        memcpy(H.bits.data() + tile_base[(size_t)b] * kBtRows * wpr, o.bits.data(), o.bits.size() * sizeof(uint64_t));
+        memcpy(H.bits.data() + tile_base[(size_t)b] * BH * wpr, o.bits.data(), o.bits.size() * sizeof(uint64_t));
       }
       if (!o.ridx.empty()) {
-        const size_t at = H.r_indptr[(size_t)(b * kBtRows)];
+        const size_t at = H.r_indptr[(size_t)(b * BH)];
         memcpy(H.r_indices.data() + at, o.ridx.data(), o.ridx.size() * 4);
         memcpy(H.r_values.data() + at, o.rval.data(), o.rval.size() * 4);
       }
@@ -613,21 +619,27 @@ __global__ void __maxnreg__(72) bt_mma_kernel(BtArgs a) {  // 448 threads x 72 r
 // barrier (one commit) per tile; (b) takes tiles of W * 64 columns (W = 2: 8 MMAs, 12 KB of B', 128 bits per row per
 // tile), halving the round trips per unit of work again.  Two accumulators per set (the measured error of 73-MMA chains
 // is 0.5 ulp: the TMEM accumulate does not drift), two sets so the epilogue overlaps the next row block.
-// TMEM: stages 8/W x 32W columns = 256, accumulators 2 x 2 x 48 = 192.
-template <int W>
+// TMEM: stages 8/W x 32W columns = 256, accumulators 2 sets x 2 x 48 = 192.
+template <int RB, int W>
 struct BtWide {
-  static constexpr int kStages = 8 / W;
-  static constexpr int kACols = 32 * W;
+  static_assert(RB == 1 || (RB == 2 && W == 1), "256-row items take 64-column tiles");
+  static constexpr int kStages = RB == 1 ? 8 / W : 5;
+  static constexpr int kACols = 32 * W * RB;           // TMEM columns of one stage's A operand(s)
   static constexpr int kKSteps = 4 * W;
   static constexpr int kChunkBytes = kKSteps * kBtKStepBytes;
-  static constexpr int kAcc = 2;
-  static constexpr int kAccCol0 = kStages * kACols;  // 256
+  static constexpr int kAcc = RB == 1 ? 2 : 1;         // accumulators per (set, 128-row half)
+  static constexpr int kAccCol0 = kStages * kACols;    // 256 / 320
+  static constexpr int kSetCols = RB * kAcc * kBtN;    // 96
+  static_assert(kAccCol0 + 2 * kSetCols <= 512, "TMEM columns");
   static constexpr size_t kSmemBytes = (size_t)kStages * kChunkBytes + (2 * kStages + 4) * 8 + 16;
 };
 
-template <int W>
+// RB = 2: an item is 256 rows, a tile 256 x 64 bits; the two 128-row halves are two MMAs (two TMEM accumulators, two A
+// operands in the stage) against the SAME B' stage, which halves the B' traffic through L2 and lets the plan select
+// tiles by the density of 256 x 64 cells.  One accumulator per half and set (chains of ~300 MMAs; measured: no drift).
+template <int RB, int W>
 __global__ void __maxnreg__(96) bt_mma_wide_kernel(BtArgs a) {
-  using K = BtWide<W>;
+  using K = BtWide<RB, W>;
   extern __shared__ __align__(128) uint8_t bt_smem[];
   uint8_t *smem_b = bt_smem;
   uint64_t *bars = reinterpret_cast<uint64_t *>(bt_smem + K::kStages * K::kChunkBytes);
@@ -663,46 +675,51 @@ __global__ void __maxnreg__(96) bt_mma_wide_kernel(BtArgs a) {
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t *>(tmem_slot);
 
   if (warp < 8) {
-    // ---- expanders: group g = warp >> 2 takes tiles t = g, g+2, ...; thread = row
+    // ---- expanders: group g = warp >> 2 takes tiles t = g, g+2, ...; thread = row of each 128-row half
+    constexpr int NW = RB * W;                                  // 64-bit words per thread per tile
+    constexpr size_t kHalfWords = (size_t)kBtRows * W;          // words between the two halves of a tile
+    constexpr size_t kTileWords = (size_t)RB * kHalfWords;
     const int quarter = warp & 3, g = warp >> 2;
-    const uint64_t *bp = a.bits + ((size_t)tile0 * kBtRows + quarter * 32 + lane) * W;
+    const uint64_t *bp = a.bits + (size_t)tile0 * kTileWords + (size_t)(quarter * 32 + lane) * W;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
-    constexpr size_t kTileWords = (size_t)kBtRows * W;
-    uint64_t w0[W], w1[W], w2[W];
+    auto word_at = [&](uint32_t t, int i) {  // i = half * W + w
+      return bt_ld_bits(bp + (size_t)t * kTileWords + (size_t)(i / W) * kHalfWords + (i % W));
+    };
+    uint64_t w0[NW], w1[NW], w2[NW];
     uint32_t t = (uint32_t)g;
 #pragma unroll
-    for (int i = 0; i < W; i++) {
-      w0[i] = t < T ? bt_ld_bits(bp + (size_t)t * kTileWords + i) : 0ull;
-      w1[i] = t + 2 < T ? bt_ld_bits(bp + (size_t)(t + 2) * kTileWords + i) : 0ull;
-      w2[i] = t + 4 < T ? bt_ld_bits(bp + (size_t)(t + 4) * kTileWords + i) : 0ull;
+    for (int i = 0; i < NW; i++) {
+      w0[i] = t < T ? word_at(t, i) : 0ull;
+      w1[i] = t + 2 < T ? word_at(t + 2, i) : 0ull;
+      w2[i] = t + 4 < T ? word_at(t + 4, i) : 0ull;
     }
     for (; t < T; t += 2) {
-      uint64_t w3[W];
+      uint64_t w3[NW];
 #pragma unroll
-      for (int i = 0; i < W; i++) w3[i] = t + 6 < T ? bt_ld_bits(bp + (size_t)(t + 6) * kTileWords + i) : 0ull;
+      for (int i = 0; i < NW; i++) w3[i] = t + 6 < T ? word_at(t + 6, i) : 0ull;
       const uint32_t s = t % K::kStages, use = t / K::kStages;
       if (use > 0) mbar_wait(&free_[s], (use - 1) & 1);  // the MMAs that read this stage's previous content are done
       tc_fence_after();
 #pragma unroll
-      for (int i = 0; i < W; i++) {
+      for (int i = 0; i < NW; i++) {
         uint32_t r[32];
         bt_expand_word((uint32_t)w0[i], r);
         bt_expand_word((uint32_t)(w0[i] >> 32), r + 16);
-        tc_st32(tmem + lane_base + s * K::kACols + i * 32, r);
+        tc_st32(tmem + lane_base + s * K::kACols + i * 32, r);  // half h occupies columns [h * 32 W, (h + 1) * 32 W)
       }
       tc_wait_st();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&full[s]);
 #pragma unroll
-      for (int i = 0; i < W; i++) {
+      for (int i = 0; i < NW; i++) {
         w0[i] = w1[i];
         w1[i] = w2[i];
         w2[i] = w3[i];
       }
     }
   } else if (warp < 12) {
-    // ---- epilogue: thread = row (TMEM lane) of the block
+    // ---- epilogue: thread = row (TMEM lane) of each 128-row half
     const int quarter = warp & 3;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     uint32_t prev_end = 0;
@@ -711,35 +728,38 @@ __global__ void __maxnreg__(96) bt_mma_wide_kernel(BtArgs a) {
       const uint32_t n_tiles = item.y - prev_end;
       prev_end = item.y;
       const uint32_t k = it - item0, set = k & 1, use = k >> 1;
-      const int64_t row = (int64_t)item.x * kBtRows + quarter * 32 + lane;
-      const float sc = row < a.n_rows ? __ldg(a.row_scale + row) : 0.f;
       mbar_wait(&acc_full[set], use & 1);
       tc_fence_after();
-      const uint32_t acc0 = tmem + lane_base + K::kAccCol0 + set * (K::kAcc * kBtN);
-      float tot[16];
 #pragma unroll
-      for (int p = 2; p >= 0; p--) {  // lo, + mid, + hi
-        float s0[16];
-        tc_ld16(acc0 + p * 16, s0);
-        if (n_tiles > 1) {
-          float s1[16];
-          tc_ld16(acc0 + kBtN + p * 16, s1);
-          tc_wait_ld();
+      for (int h = 0; h < RB; h++) {
+        const int64_t row = ((int64_t)item.x * RB + h) * kBtRows + quarter * 32 + lane;
+        const float sc = row < a.n_rows ? __ldg(a.row_scale + row) : 0.f;
+        const uint32_t acc0 = tmem + lane_base + K::kAccCol0 + set * K::kSetCols + h * (K::kAcc * kBtN);
+        float tot[16];
 #pragma unroll
-          for (int i = 0; i < 16; i++) s0[i] += s1[i];
-        } else {
-          tc_wait_ld();
+        for (int p = 2; p >= 0; p--) {  // lo, + mid, + hi
+          float s0[16];
+          tc_ld16(acc0 + p * 16, s0);
+          if (K::kAcc > 1 && n_tiles > 1) {
+            float s1[16];
+            tc_ld16(acc0 + kBtN + p * 16, s1);
+            tc_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 16; i++) s0[i] += s1[i];
+          } else {
+            tc_wait_ld();
+          }
+#pragma unroll
+          for (int i = 0; i < 16; i++) tot[i] = p == 2 ? s0[i] : tot[i] + s0[i];
         }
+        float4 *dst = reinterpret_cast<float4 *>(a.P + row * 16);
 #pragma unroll
-        for (int i = 0; i < 16; i++) tot[i] = p == 2 ? s0[i] : tot[i] + s0[i];
+        for (int i = 0; i < 4; i++)
+          dst[i] = make_float4(sc * tot[4 * i], sc * tot[4 * i + 1], sc * tot[4 * i + 2], sc * tot[4 * i + 3]);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[set]);
-      float4 *dst = reinterpret_cast<float4 *>(a.P + row * 16);
-#pragma unroll
-      for (int i = 0; i < 4; i++)
-        dst[i] = make_float4(sc * tot[4 * i], sc * tot[4 * i + 1], sc * tot[4 * i + 2], sc * tot[4 * i + 3]);
     }
   } else if (warp == 12) {
     // ---- producer of B'
@@ -758,7 +778,7 @@ __global__ void __maxnreg__(96) bt_mma_wide_kernel(BtArgs a) {
       }
     }
   } else if (lane == 0) {
-    // ---- MMA issuer: one wait, 4W MMAs, one commit per tile
+    // ---- MMA issuer: one wait, RB * 4W MMAs, one commit per tile
     uint32_t t = 0;
     uint2 item = item0 < item1 ? a.items[item0] : make_uint2(0, 0);
     for (uint32_t it = item0; it < item1; it++) {
@@ -772,12 +792,15 @@ __global__ void __maxnreg__(96) bt_mma_wide_kernel(BtArgs a) {
         mbar_wait(&full[s], u & 1);
         tc_fence_after();
         const uint32_t idx = t - t_begin;
-        const uint32_t d = tmem + K::kAccCol0 + set * (K::kAcc * kBtN) + (idx % K::kAcc) * kBtN;
         const uint32_t b_addr = smem_u32(smem_b + s * K::kChunkBytes);
 #pragma unroll
-        for (int ks = 0; ks < K::kKSteps; ks++)
-          tc_mma_ts(d, tmem + s * K::kACols + ks * 8, bt_b_desc(b_addr + ks * kBtKStepBytes), kBtIdesc,
-                    (ks > 0 || idx >= (uint32_t)K::kAcc) ? 1u : 0u);
+        for (int h = 0; h < RB; h++) {
+          const uint32_t d = tmem + K::kAccCol0 + set * K::kSetCols + (h * K::kAcc + idx % K::kAcc) * kBtN;
+#pragma unroll
+          for (int ks = 0; ks < K::kKSteps; ks++)
+            tc_mma_ts(d, tmem + s * K::kACols + h * (32 * W) + ks * 8, bt_b_desc(b_addr + ks * kBtKStepBytes), kBtIdesc,
+                      (ks > 0 || idx >= (uint32_t)K::kAcc) ? 1u : 0u);
+        }
         tc_commit(&free_[s]);
       }
       tc_commit(&acc_full[set]);
@@ -793,7 +816,6 @@ __global__ void __maxnreg__(96) bt_mma_wide_kernel(BtArgs a) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
   }
 }
-
 
 __global__ void __launch_bounds__(256) bt_add_kernel(const float4 *__restrict__ P, const float4 *__restrict__ R,
                                                      float4 *__restrict__ C, int64_t n4) {
@@ -815,7 +837,8 @@ struct gcnb_bittile_host {
 struct gcnb_bittile_plan {
   int64_t n_rows = 0, n_cols = 0, nnz = 0, n_blk = 0, n_tiles = 0, tile_nnz = 0, rem_nnz = 0, n_chunks = 0;
   int n_cta = 0;
-  int chunk = kBtChunk;  // columns per tile (64: bt_mma_kernel or, with unified = 1, bt_mma_wide_kernel<1>; 128: <2>)
+  int chunk = kBtChunk;  // columns per tile (64: bt_mma_kernel or, with unified = 1, bt_mma_wide_kernel<1, 1>; 128: <1, 2>)
+  int rb = 1;            // 128-row blocks per item (2: bt_mma_wide_kernel<2, 1>)
   int unified = 0;
   int parts = 15;  // debugging: bit 0 pack, 1 MMA kernel, 2 remainder, 3 final add
   uint32_t *d_tile_chunk = nullptr, *d_cta_tile_ptr = nullptr, *d_cta_item_ptr = nullptr;
@@ -846,11 +869,11 @@ extern "C" {
 
 int gcnb_bittile_host_build(const uint32_t *h_indptr, const uint32_t *h_indices, const float *h_values, int64_t n_rows,
                             int64_t n_cols, const float *h_row_scale, const float *h_col_scale, int min_tile_nnz,
-                            int chunk_cols, int n_cta, int n_threads, gcnb_bittile_host **out) {
+                            int chunk_cols, int row_blocks, int n_cta, int n_threads, gcnb_bittile_host **out) {
   if (!out) return GCNB_E_BADARG;
   auto *h = new gcnb_bittile_host();
   const int rc = bittile_build_host(h_indptr, h_indices, h_values, n_rows, n_cols, h_row_scale, h_col_scale, min_tile_nnz,
-                                    chunk_cols, n_cta, n_threads, h->H);
+                                    chunk_cols, row_blocks, n_cta, n_threads, h->H);
   if (rc) {
     delete h;
     return rc;
@@ -859,11 +882,11 @@ int gcnb_bittile_host_build(const uint32_t *h_indptr, const uint32_t *h_indices,
   return 0;
 }
 
-int gcnb_bittile_host_sizes(const gcnb_bittile_host *h, int64_t out[9]) {
+int gcnb_bittile_host_sizes(const gcnb_bittile_host *h, int64_t out[10]) {
   if (!h || !out) return GCNB_E_BADARG;
   const BitTileHost &H = h->H;
   out[0] = H.n_rows; out[1] = H.n_cols; out[2] = H.nnz; out[3] = H.n_blk; out[4] = H.n_tiles; out[5] = H.tile_nnz;
-  out[6] = (int64_t)H.items.size(); out[7] = H.n_cta; out[8] = H.chunk;
+  out[6] = (int64_t)H.items.size(); out[7] = H.n_cta; out[8] = H.chunk; out[9] = H.rb;
   return 0;
 }
 
@@ -911,7 +934,7 @@ int gcnb_bittile_plan_destroy(gcnb_bittile_plan *p) {
 
 int gcnb_bittile_plan_create(const uint32_t *h_indptr, const uint32_t *h_indices, const float *h_values, int64_t n_rows,
                              int64_t n_cols, const float *h_row_scale, const float *h_col_scale, int min_tile_nnz,
-                             int chunk_cols, gcnb_stream_t stream_, gcnb_bittile_plan **out) {
+                             int chunk_cols, int row_blocks, gcnb_stream_t stream_, gcnb_bittile_plan **out) {
   if (!out) return GCNB_E_BADARG;
   *out = nullptr;
   const DeviceInfo &di = device_info();
@@ -923,8 +946,10 @@ int gcnb_bittile_plan_create(const uint32_t *h_indptr, const uint32_t *h_indices
   if (const char *e = getenv("GCNB_BT_UNIFIED")) unified = atoi(e) != 0;  // tuning probe: 64-column tiles on the new kernel
   if (chunk_cols == 0)
     if (const char *e = getenv("GCNB_BT_CHUNK")) chunk_cols = atoi(e);    // tuning probe: 64 (default) or 128
+  if (row_blocks == 0)
+    if (const char *e = getenv("GCNB_BT_RB")) row_blocks = atoi(e);       // tuning probe: 1 (default) or 2
   int rc = bittile_build_host(h_indptr, h_indices, h_values, n_rows, n_cols, h_row_scale, h_col_scale, min_tile_nnz,
-                              chunk_cols, di.sm_count, 0, H);
+                              chunk_cols, row_blocks, di.sm_count, 0, H);
   if (rc) return rc;
   auto *p = new gcnb_bittile_plan();
   auto fail = [&](int code) {
@@ -934,7 +959,8 @@ int gcnb_bittile_plan_create(const uint32_t *h_indptr, const uint32_t *h_indices
   p->n_rows = n_rows; p->n_cols = n_cols; p->nnz = H.nnz; p->n_blk = H.n_blk; p->n_tiles = H.n_tiles;
   p->tile_nnz = H.tile_nnz; p->rem_nnz = (int64_t)H.r_indices.size(); p->n_cta = H.n_cta;
   p->chunk = H.chunk;
-  p->unified = unified || H.chunk == 128;
+  p->rb = H.rb;
+  p->unified = unified || H.chunk == 128 || H.rb == 2;
   p->n_chunks = (n_cols + 127) / 128 * 2;  // 64-row units of the packed B' image, padded to whole 128-column chunks
   if ((rc = bt_upload(&p->d_tile_chunk, H.tile_chunk.data(), H.tile_chunk.size(), stream))) return fail(rc);
   if ((rc = bt_upload(&p->d_bits, H.bits.data(), H.bits.size(), stream))) return fail(rc);
@@ -947,7 +973,7 @@ int gcnb_bittile_plan_create(const uint32_t *h_indptr, const uint32_t *h_indices
   if ((rc = bt_upload(&p->d_row_scale, H.row_scale.data(), H.row_scale.size(), stream))) return fail(rc);
   if ((rc = bt_upload(&p->d_col_scale, H.col_scale.data(), H.col_scale.size(), stream))) return fail(rc);
   const size_t packed_bytes = std::max<size_t>((size_t)p->n_chunks * kBtChunkBytes, 16);
-  const size_t p_bytes = std::max<size_t>((size_t)p->n_blk * kBtRows * 16 * sizeof(float), 16);
+  const size_t p_bytes = std::max<size_t>((size_t)p->n_blk * p->rb * kBtRows * 16 * sizeof(float), 16);
   if ((rc = (int)cudaMalloc((void **)&p->d_packed, packed_bytes))) return fail(rc);
   if ((rc = (int)cudaMalloc((void **)&p->d_P, p_bytes))) return fail(rc);
   if ((rc = (int)cudaMalloc((void **)&p->d_R, std::max<size_t>((size_t)n_rows * 16 * sizeof(float), 16)))) return fail(rc);
@@ -959,11 +985,14 @@ int gcnb_bittile_plan_create(const uint32_t *h_indptr, const uint32_t *h_indices
   if ((rc = (int)cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming))) return fail(rc);
   if ((rc = (int)cudaFuncSetAttribute(bt_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBtSmemBytes)))
     return fail(rc);
-  if ((rc = (int)cudaFuncSetAttribute(bt_mma_wide_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)BtWide<1>::kSmemBytes)))
+  if ((rc = (int)cudaFuncSetAttribute(bt_mma_wide_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)BtWide<1, 1>::kSmemBytes)))
     return fail(rc);
-  if ((rc = (int)cudaFuncSetAttribute(bt_mma_wide_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)BtWide<2>::kSmemBytes)))
+  if ((rc = (int)cudaFuncSetAttribute(bt_mma_wide_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)BtWide<1, 2>::kSmemBytes)))
+    return fail(rc);
+  if ((rc = (int)cudaFuncSetAttribute(bt_mma_wide_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)BtWide<2, 1>::kSmemBytes)))
     return fail(rc);
   *out = p;
   return 0;
@@ -972,8 +1001,9 @@ int gcnb_bittile_plan_create(const uint32_t *h_indptr, const uint32_t *h_indices
 // out = {tiles, entries in tiles, remainder entries, row blocks, items (blocks with tiles), CTAs, bit-map bytes, packed B' bytes}
 int gcnb_bittile_plan_info(const gcnb_bittile_plan *p, int64_t out[8]) {
   if (!p || !out) return GCNB_E_BADARG;
-  out[0] = p->n_tiles; out[1] = p->tile_nnz; out[2] = p->rem_nnz; out[3] = p->n_blk; out[4] = p->chunk; out[5] = p->n_cta;
-  out[6] = p->n_tiles * (int64_t)kBtRows * (p->chunk / 8); out[7] = p->n_chunks * (int64_t)kBtChunkBytes;
+  out[0] = p->n_tiles; out[1] = p->tile_nnz; out[2] = p->rem_nnz; out[3] = p->n_blk; out[4] = p->chunk + 1000 * p->rb;
+  out[5] = p->n_cta;
+  out[6] = p->n_tiles * (int64_t)kBtRows * p->rb * (p->chunk / 8); out[7] = p->n_chunks * (int64_t)kBtChunkBytes;
   return 0;
 }
 
@@ -1021,8 +1051,9 @@ int gcnb_bittile_spmm16_f32(gcnb_bittile_plan *p, const float *d_B, float *d_C, 
     a.tile_chunk = p->d_tile_chunk; a.bits = p->d_bits; a.cta_tile_ptr = p->d_cta_tile_ptr;
     a.cta_item_ptr = p->d_cta_item_ptr; a.items = p->d_items; a.packed = p->d_packed; a.row_scale = p->d_row_scale;
     a.P = p->d_P; a.n_rows = p->n_rows;
-    if (p->chunk == 128) bt_mma_wide_kernel<2><<<p->n_cta, kBtThreads, BtWide<2>::kSmemBytes, stream>>>(a);
-    else if (p->unified) bt_mma_wide_kernel<1><<<p->n_cta, kBtThreads, BtWide<1>::kSmemBytes, stream>>>(a);
+    if (p->rb == 2) bt_mma_wide_kernel<2, 1><<<p->n_cta, kBtThreads, BtWide<2, 1>::kSmemBytes, stream>>>(a);
+    else if (p->chunk == 128) bt_mma_wide_kernel<1, 2><<<p->n_cta, kBtThreads, BtWide<1, 2>::kSmemBytes, stream>>>(a);
+    else if (p->unified) bt_mma_wide_kernel<1, 1><<<p->n_cta, kBtThreads, BtWide<1, 1>::kSmemBytes, stream>>>(a);
     else bt_mma_kernel<<<p->n_cta, kBtThreads, kBtSmemBytes, stream>>>(a);
     GCNB_LAUNCH_CHECK();
   }

@@ -457,7 +457,7 @@ void GCN::init(bool quiet, const natural *h_graph_indptr, const natural *h_graph
       CHECK_CUDA_ERROR(cudaStreamSynchronize(st->stream));
       CHECK_CUDA_ERROR(cudaMemcpy(hv.data(), dev_data.dev_graph_value.get(), nnz * sizeof(real), cudaMemcpyDeviceToHost));
       GCNB_CALL(gcnb_bittile_plan_create(hp.empty() ? h_graph_indptr : hp.data(), hi.empty() ? h_graph_indices : hi.data(),
-                                         hv.data(), (int64_t)N, (int64_t)N, nullptr, nullptr, 0, 0, st->stream, &st->graph_bittile));
+                                         hv.data(), (int64_t)N, (int64_t)N, nullptr, nullptr, 0, 0, 0, st->stream, &st->graph_bittile));
       int64_t binfo[8];
       GCNB_CALL(gcnb_bittile_plan_info(st->graph_bittile, binfo));
       if (binfo[0] > 0 && binfo[1] * 4 >= (int64_t)nnz) {  // worth it when at least a quarter of the entries sit in tiles

@@ -5,6 +5,11 @@ flushes, so a hang in a later step loses nothing.  Run under `timeout`.
   python scripts/probe_bittile.py --stage small           # layout / pipeline diagnostics, seconds
   python scripts/probe_bittile.py --stage graph --scale 8 # 1/8 Reddit-shape community graph vs the generic kernel
   python scripts/probe_bittile.py --stage graph --scale 1 # the bench graph
+  ... --chunk 128 | --rb 2 | GCNB_BT_UNIFIED=1            # second-generation MMA kernel (128-column tiles / 256-row items /
+                                                          # 64-column tiles with unified stage barriers)
+Round-2 checklist: GCNB_TEST_BITTILE_WIDE=1 GCNB_TEST_BITTILE_ENGINE=1 pytest tests/test_zz_bittile_gpu.py -m gpu; this
+probe for the three shapes at --scale 1; then `ncu --set full --import-source on -k regex:bt_mma -c 1` on the best one
+(warp-state stalls per role: expanders = warps 0-7, epilogue 8-11, producer 12, MMA issuer 13).
 """
 import argparse
 import json
@@ -29,6 +34,7 @@ ap.add_argument("--min-tile-nnz", type=int, default=0)
 ap.add_argument("--staged", type=int, default=1, help="also time the window-staged path")
 ap.add_argument("--chunk", type=int, default=0, help="columns per tile: 64 (default) or 128; GCNB_BT_UNIFIED=1 selects the\n"
                 "second-generation kernel for 64")
+ap.add_argument("--rb", type=int, default=0, help="128-row blocks per item: 1 (default) or 2 (items of 256 rows share a B' stage)")
 ap.add_argument("--out", default="gpurun_out/probe_bittile.jsonl")
 args = ap.parse_args()
 dev = torch.device("cuda:0")
@@ -55,7 +61,7 @@ def dense_case(name, n, density, seed, cols_used=None, dump=False):
     indices = cols.astype(np.uint32)
     values = (rs[rows] * cs[cols]).astype(np.float32)
     B = rng.standard_normal((n, 16)).astype(np.float32)
-    plan = gcnb.BitTilePlan(indptr, indices, values, n, rs, cs, min_tile_nnz=1, chunk_cols=args.chunk)
+    plan = gcnb.BitTilePlan(indptr, indices, values, n, rs, cs, min_tile_nnz=1, chunk_cols=args.chunk, row_blocks=args.rb)
     info = plan.info()
     Bd = torch.from_numpy(B).to(dev)
     packed = plan.debug_pack(Bd)
@@ -83,7 +89,8 @@ def graph_case(scale):
     indptr, indices = eng.synth_graph(n, m, n_blocks=max(2, 50 // scale))
     values = eng.synth_graph_values(indptr, indices, 0, np.diff(indptr).astype(np.uint32))  # parser.cpp:164-181 formula
     t1 = time.time()
-    plan = gcnb.BitTilePlan(indptr, indices, values, n, min_tile_nnz=args.min_tile_nnz, chunk_cols=args.chunk)
+    plan = gcnb.BitTilePlan(indptr, indices, values, n, min_tile_nnz=args.min_tile_nnz, chunk_cols=args.chunk,
+                            row_blocks=args.rb)
     t2 = time.time()
     info = plan.info()
     emit(case="graph/%d" % scale, step="plan", n=n, nnz=int(indices.size), gen_s=t1 - t0, plan_s=t2 - t1, info=info)

@@ -121,10 +121,11 @@ def expand_words(words):
 
 
 def emulate(plan, B):
-    n_rows, CH = plan["n_rows"], plan["chunk"]
-    NACC = 4 if CH == 64 else 2  # bt_mma_kernel / bt_mma_wide_kernel<2>
+    n_rows, CH, RB = plan["n_rows"], plan["chunk"], plan["rb"]
+    BH = ROWS * RB
+    NACC = 1 if RB == 2 else (4 if CH == 64 else 2)  # bt_mma_kernel / bt_mma_wide_kernel<1, 2> / <2, 1>
     packed, _ = pack_b(B, plan["col_scale"])
-    P = np.zeros((plan["n_blk"] * ROWS, 16), np.float64)
+    P = np.zeros((plan["n_blk"] * BH, 16), np.float64)
     cells = []
     block_seen = np.zeros(plan["n_blk"], np.int64)
     tile_seen = np.zeros(plan["n_tiles"], np.int64)
@@ -135,25 +136,27 @@ def emulate(plan, B):
             blk, end = int(blk), int(end)
             assert end > pos, "an item owns at least one tile"
             block_seen[blk] += 1
-            acc = np.zeros((NACC, ROWS, 48), np.float64)
+            acc = np.zeros((RB, NACC, ROWS, 48), np.float64)
             chunks = plan["tile_chunk"][t0 + pos:t0 + end]
             assert np.all(np.diff(chunks.astype(np.int64)) > 0), "chunks of a block ascend"
             for idx in range(end - pos):
                 t = t0 + pos + idx
                 tile_seen[t] += 1
-                A = np.concatenate([expand_words(plan["bits"][t][:, w]) for w in range(CH // 64)], 1)  # [128, CH]
-                for ks in range(CH // 16):
-                    Bop = read_b_operand(packed, int(chunks[idx]), ks, CH)  # [48, 16]
-                    acc[idx % NACC] += A[:, ks * 16:(ks + 1) * 16].astype(np.float64) @ Bop.T.astype(np.float64)
-                r, c = np.nonzero(A)
-                cells.append(np.stack([blk * ROWS + r, int(chunks[idx]) * CH + c], 1))
-            s = acc[0].copy()
-            for a in range(1, min(NACC, end - pos)):
-                s += acc[a]
-            tot = (s[:, 32:48] + s[:, 16:32]) + s[:, 0:16]
-            rows = np.arange(blk * ROWS, (blk + 1) * ROWS)
-            sc = np.where(rows < n_rows, plan["row_scale"][np.minimum(rows, n_rows - 1)], 0.0)
-            P[rows] = sc[:, None] * tot
+                for h in range(RB):  # the two 128-row halves of a 256-row item share the B' stage
+                    A = np.concatenate([expand_words(plan["bits"][t][h][:, w]) for w in range(CH // 64)], 1)  # [128, CH]
+                    for ks in range(CH // 16):
+                        Bop = read_b_operand(packed, int(chunks[idx]), ks, CH)  # [48, 16]
+                        acc[h, idx % NACC] += A[:, ks * 16:(ks + 1) * 16].astype(np.float64) @ Bop.T.astype(np.float64)
+                    r, c = np.nonzero(A)
+                    cells.append(np.stack([blk * BH + h * ROWS + r, int(chunks[idx]) * CH + c], 1))
+            for h in range(RB):
+                s = acc[h, 0].copy()
+                for a in range(1, min(NACC, end - pos)):
+                    s += acc[h, a]
+                tot = (s[:, 32:48] + s[:, 16:32]) + s[:, 0:16]
+                rows = np.arange(blk * BH + h * ROWS, blk * BH + (h + 1) * ROWS)
+                sc = np.where(rows < n_rows, plan["row_scale"][np.minimum(rows, max(n_rows - 1, 0))], 0.0)
+                P[rows] = sc[:, None] * tot
             pos = end
         assert t0 + pos == t1
     assert np.all(block_seen <= 1) and np.all(tile_seen == 1)
@@ -162,19 +165,20 @@ def emulate(plan, B):
     rrows = np.repeat(np.arange(n_rows), np.diff(rp))
     np.add.at(R, rrows, plan["r_values"][:, None].astype(np.float64) * B[plan["r_indices"]])
     cells = np.concatenate(cells) if cells else np.zeros((0, 2), np.int64)
+    cells = cells[cells[:, 0] < max(n_rows, 1)] if len(cells) else cells
     return P[:n_rows] + R, cells, rrows
 
 
 def check_plan(gcnb, indptr, indices, values, B, explicit_scales=False, min_tile_nnz=0, n_cta=0, expect_tiles=True,
-               chunk_cols=0):
+               chunk_cols=0, row_blocks=0):
     n = len(indptr) - 1
     deg = np.diff(indptr.astype(np.int64))
     rs = cs = None
     if explicit_scales:
         rs = cs = (1.0 / np.sqrt(deg.astype(np.float32))).astype(np.float32)
     plan = gcnb.bittile_host_build(indptr, indices, values, n, rs, cs, min_tile_nnz=min_tile_nnz, n_cta=n_cta,
-                                   chunk_cols=chunk_cols)
-    assert plan["chunk"] == (chunk_cols or 64)
+                                   chunk_cols=chunk_cols, row_blocks=row_blocks)
+    assert plan["chunk"] == (chunk_cols or 64) and plan["rb"] == (row_blocks or 1)
     assert plan["nnz"] == indices.size and plan["tile_nnz"] + plan["rem_nnz"] == indices.size
     out, cells, rrows = emulate(plan, B)
     assert len(cells) == plan["tile_nnz"]
@@ -203,33 +207,37 @@ def test_bit_position_formula_is_a_permutation(gcnb):
     assert np.array_equal(A[:64], np.eye(64, dtype=np.float32)) and not A[64:].any()
 
 
-@pytest.mark.parametrize("chunk_cols", [0, 128])
-def test_community_graph_matches_csr_product(gcnb, chunk_cols):
+SHAPES = [(0, 0), (128, 1), (64, 2)]  # (columns per tile, 128-row blocks per item)
+
+
+@pytest.mark.parametrize("chunk_cols,row_blocks", SHAPES)
+def test_community_graph_matches_csr_product(gcnb, chunk_cols, row_blocks):
     rng = np.random.default_rng(7)
     indptr, indices, values = gcn_graph(rng, 1500, 5, 24, 3)
     B = rng.standard_normal((1500, 16)).astype(np.float32)
-    thr = 96 * (2 if chunk_cols == 128 else 1)
-    plan = check_plan(gcnb, indptr, indices, values, B, min_tile_nnz=thr, n_cta=5, chunk_cols=chunk_cols)
+    thr = 96 * (2 if chunk_cols == 128 or row_blocks == 2 else 1)
+    kw = dict(min_tile_nnz=thr, n_cta=5, chunk_cols=chunk_cols, row_blocks=row_blocks)
+    plan = check_plan(gcnb, indptr, indices, values, B, **kw)
     assert plan["tile_nnz"] > 0.5 * indices.size
     # explicit 1/sqrt(deg) scales select the same entries
-    plan2 = check_plan(gcnb, indptr, indices, values, B, explicit_scales=True, min_tile_nnz=thr, n_cta=5, chunk_cols=chunk_cols)
+    plan2 = check_plan(gcnb, indptr, indices, values, B, explicit_scales=True, **kw)
     assert plan2["tile_nnz"] == plan["tile_nnz"]
 
 
-@pytest.mark.parametrize("chunk_cols", [64, 128])
-def test_duplicates_missing_diagonals_and_ragged_sizes(gcnb, chunk_cols):
+@pytest.mark.parametrize("chunk_cols,row_blocks", SHAPES)
+def test_duplicates_missing_diagonals_and_ragged_sizes(gcnb, chunk_cols, row_blocks):
     rng = np.random.default_rng(11)
     n = 777  # not a multiple of 128 or 64
     indptr, indices, values = gcn_graph(rng, n, 3, 30, 2, dup=40, drop_diag=(5, 300, 776))
     B = rng.standard_normal((n, 16)).astype(np.float32)
-    plan = check_plan(gcnb, indptr, indices, values, B, min_tile_nnz=64, n_cta=148, chunk_cols=chunk_cols)
+    plan = check_plan(gcnb, indptr, indices, values, B, min_tile_nnz=64, n_cta=148, chunk_cols=chunk_cols, row_blocks=row_blocks)
     # rows without a diagonal entry have no scale: none of their entries (nor entries pointing at them) is in a bit map
     for i in (5, 300, 776):
         assert plan["row_scale"][i] == 0 and plan["col_scale"][i] == 0
     # values that do not factor stay in the remainder with their original value
     values2 = values.copy()
     values2[::7] *= 1.5
-    check_plan(gcnb, indptr, indices, values2, B, min_tile_nnz=64, n_cta=7, chunk_cols=chunk_cols)
+    check_plan(gcnb, indptr, indices, values2, B, min_tile_nnz=64, n_cta=7, chunk_cols=chunk_cols, row_blocks=row_blocks)
 
 
 def test_sparse_graph_has_no_tiles_and_empty_graph(gcnb):

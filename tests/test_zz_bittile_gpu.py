@@ -15,17 +15,19 @@ from tests.util import assert_close, to_dev, to_np
 pytestmark = pytest.mark.gpu
 f32 = np.float32
 # 64-column tiles on bt_mma_kernel ran on B200 in round 1; the second-generation kernel (bt_mma_wide_kernel: unified
-# stage barriers, 128-column tiles) has only been compiled and emulated on the CPU so far: opt-in
-CHUNKS = [0, 128] if os.environ.get("GCNB_TEST_BITTILE_WIDE") == "1" else [0]
+# stage barriers; 128-column tiles or 256-row items sharing a B' stage) has only been compiled and emulated on the CPU so
+# far: opt-in.  A shape is (columns per tile, 128-row blocks per item).
+SHAPES = [(0, 0), (128, 1), (64, 2)] if os.environ.get("GCNB_TEST_BITTILE_WIDE") == "1" else [(0, 0)]
 
 
-def _check(O, gcnb, dev, indptr, indices, values, rs=None, cs=None, min_tile_nnz=0, seed=0, chunk_cols=0):
+def _check(O, gcnb, dev, indptr, indices, values, rs=None, cs=None, min_tile_nnz=0, seed=0, shape=(0, 0)):
     import torch
     n = len(indptr) - 1
     x = np.random.default_rng(seed).standard_normal((n, 16)).astype(f32)
     want = np.empty((n, 16), f32)
     O.lib.orc_spmm(n, 16, O._p(indptr), O._p(indices), O._p(values), O._p(x), O._p(want))
-    plan = gcnb.BitTilePlan(indptr, indices, values, n, rs, cs, min_tile_nnz=min_tile_nnz, chunk_cols=chunk_cols)
+    plan = gcnb.BitTilePlan(indptr, indices, values, n, rs, cs, min_tile_nnz=min_tile_nnz, chunk_cols=shape[0],
+                            row_blocks=shape[1])
     info = plan.info()
     assert info["tile_nnz"] + info["rem_nnz"] == len(indices)
     d_x = to_dev(x, dev)
@@ -43,18 +45,18 @@ def _check(O, gcnb, dev, indptr, indices, values, rs=None, cs=None, min_tile_nnz
 
 @pytest.mark.parametrize("cfg", [dict(n=3000, comm=6, intra=40, inter=3, thr=64), dict(n=777, comm=2, intra=60, inter=2, thr=32),
                                  dict(n=20000, comm=5, intra=120, inter=10, thr=0)])
-@pytest.mark.parametrize("chunk_cols", CHUNKS)
-def test_community_graph_matches_oracle(O, gcnb, dev, cfg, chunk_cols):
+@pytest.mark.parametrize("shape", SHAPES)
+def test_community_graph_matches_oracle(O, gcnb, dev, cfg, shape):
     rng = np.random.default_rng(cfg["n"])
     indptr, indices, values = gcn_graph(rng, cfg["n"], cfg["comm"], cfg["intra"], cfg["inter"])
-    info = _check(O, gcnb, dev, indptr, indices, values, min_tile_nnz=cfg["thr"] * (2 if chunk_cols == 128 else 1), seed=1,
-                  chunk_cols=chunk_cols)
+    info = _check(O, gcnb, dev, indptr, indices, values, min_tile_nnz=cfg["thr"] * (1 if shape == (0, 0) else 2), seed=1,
+                  shape=shape)
     assert info["n_tiles"] > 0 and info["tile_nnz"] > 0.4 * len(indices)
 
 
-@pytest.mark.parametrize("chunk_cols", CHUNKS)
+@pytest.mark.parametrize("shape", SHAPES)
 @pytest.mark.parametrize("n,density", [(128, 0.3), (1000, 0.2), (1024, 0.05)])
-def test_dense_pattern_with_explicit_scales(O, gcnb, dev, n, density, chunk_cols):
+def test_dense_pattern_with_explicit_scales(O, gcnb, dev, n, density, shape):
     """every entry in a tile (explicit row / column scales, threshold 1): up to 16 tiles per row block => all four
     accumulators, accumulate flag, A / B stage re-use; n = 1000 leaves a ragged last block and chunk"""
     rng = np.random.default_rng(n)
@@ -65,7 +67,7 @@ def test_dense_pattern_with_explicit_scales(O, gcnb, dev, n, density, chunk_cols
     indptr = np.zeros(n + 1, np.uint32)
     indptr[1:] = np.cumsum(M.sum(1))
     values = (rs[rows] * cs[cols]).astype(f32)
-    info = _check(O, gcnb, dev, indptr, cols.astype(np.uint32), values, rs, cs, min_tile_nnz=1, seed=2, chunk_cols=chunk_cols)
+    info = _check(O, gcnb, dev, indptr, cols.astype(np.uint32), values, rs, cs, min_tile_nnz=1, seed=2, shape=shape)
     assert info["rem_nnz"] == 0
 
 
