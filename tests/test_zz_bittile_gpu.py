@@ -123,16 +123,20 @@ def test_engine_training_with_bit_tiles_matches_default_path(gcnb, dev):
     def run(flag):
         os.environ["GCNB_BITTILE"] = flag
         try:
-            ds = eng.synth_dataset(30000, 30000 * 40, 32, 6, n_blocks=8, seed=11)
+            # 8 communities of 2500 nodes, ~160 neighbours inside: 6 % dense blocks; small enough for CUDA-graph replay,
+            # so the captured epoch contains the bit-tile fork / join as well
+            ds = eng.synth_dataset(20000, 20000 * 100, 32, 6, n_blocks=8, seed=11)
             g = eng.GCN(ds, hidden_dims=(16,), dropouts=(0.5, 0.5))
             hist = [(g.train_epoch(), g.eval(2)) for _ in range(4)]
             w = [g.weight(l) for l in range(2)]
+            launches = g.launches_per_epoch()
             g.close()
-            return hist, w
+            return hist, w, launches
         finally:
             os.environ.pop("GCNB_BITTILE", None)
 
-    (h0, w0), (h1, w1) = run("0"), run("1")
+    (h0, w0, l0), (h1, w1, l1) = run("0"), run("1")
+    assert l1 != l0, "GCNB_BITTILE=1 did not change the GraphSum path (pack + MMA + remainder + add = 4 launches)"
     for ep, ((t0, v0), (t1, v1)) in enumerate(zip(h0, h1)):
         assert abs(t0[0] - t1[0]) <= 2e-5 * (1 + ep) * abs(t0[0]) and abs(v0[0] - v1[0]) <= 2e-5 * (1 + ep) * abs(v0[0])
     for a, b in zip(w0, w1):
