@@ -350,6 +350,18 @@ __device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&r)[32])
       "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
 }
+// one lane of the (converged) warp: the same lane every time for the same mask, so MMAs and their commits share a thread
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
@@ -777,8 +789,9 @@ __global__ void __maxnreg__(96) bt_mma_wide_kernel(BtArgs a) {
         __syncwarp();
       }
     }
-  } else if (lane == 0) {
-    // ---- MMA issuer: one wait, RB * 4W MMAs, one commit per tile
+  } else {
+    // ---- MMA issuer: one wait, RB * 4W MMAs, one commit per tile.  The whole warp walks the loop (warp-uniform control
+    // flow keeps addresses and descriptors in uniform registers); one elected lane issues.
     uint32_t t = 0;
     uint2 item = item0 < item1 ? a.items[item0] : make_uint2(0, 0);
     for (uint32_t it = item0; it < item1; it++) {
@@ -791,19 +804,24 @@ __global__ void __maxnreg__(96) bt_mma_wide_kernel(BtArgs a) {
         const uint32_t s = t % K::kStages, u = t / K::kStages;
         mbar_wait(&full[s], u & 1);
         tc_fence_after();
-        const uint32_t idx = t - t_begin;
-        const uint32_t b_addr = smem_u32(smem_b + s * K::kChunkBytes);
+        if (elect_one()) {
+          const uint32_t idx = t - t_begin;
+          const uint64_t bd = bt_b_desc(smem_u32(smem_b + s * K::kChunkBytes));
+          const uint32_t acc_flag = idx >= (uint32_t)K::kAcc ? 1u : 0u;
 #pragma unroll
-        for (int h = 0; h < RB; h++) {
-          const uint32_t d = tmem + K::kAccCol0 + set * K::kSetCols + (h * K::kAcc + idx % K::kAcc) * kBtN;
+          for (int h = 0; h < RB; h++) {
+            const uint32_t d = tmem + K::kAccCol0 + set * K::kSetCols + (h * K::kAcc + idx % K::kAcc) * kBtN;
+            const uint32_t a0 = tmem + s * K::kACols + h * (32 * W);
 #pragma unroll
-          for (int ks = 0; ks < K::kKSteps; ks++)
-            tc_mma_ts(d, tmem + s * K::kACols + h * (32 * W) + ks * 8, bt_b_desc(b_addr + ks * kBtKStepBytes), kBtIdesc,
-                      (ks > 0 || idx >= (uint32_t)K::kAcc) ? 1u : 0u);
+            for (int ks = 0; ks < K::kKSteps; ks++)  // the next k-step of B' is 1536 bytes = 96 descriptor units further
+              tc_mma_ts(d, a0 + ks * 8, bd + (uint64_t)(ks * (kBtKStepBytes >> 4)), kBtIdesc, ks > 0 ? 1u : acc_flag);
+          }
+          tc_commit(&free_[s]);
         }
-        tc_commit(&free_[s]);
+        __syncwarp();
       }
-      tc_commit(&acc_full[set]);
+      if (elect_one()) tc_commit(&acc_full[set]);
+      __syncwarp();
       item = next_item;
     }
   }
