@@ -12,7 +12,8 @@ import pytest
 from tests.test_bittile_cpu import gcn_graph
 from tests.util import assert_close, to_dev, to_np
 
-pytestmark = pytest.mark.gpu
+# a wedged mbarrier pipeline must end the run, not hang it: pytest-timeout's thread method exits the process
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300, method="thread")]
 f32 = np.float32
 # 64-column tiles on bt_mma_kernel ran on B200 in round 1; the second-generation kernel (bt_mma_wide_kernel: unified
 # stage barriers; 128-column tiles or 256-row items sharing a B' stage) has only been compiled and emulated on the CPU so
