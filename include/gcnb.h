@@ -77,6 +77,15 @@ GCNB_API int gcnb_spmm_plan_stage(gcnb_spmm_plan *plan, const uint32_t *h_indptr
 GCNB_API int gcnb_spmm_plan_stage_ex(gcnb_spmm_plan *plan, const uint32_t *h_indptr, const uint32_t *h_indices,
                                      const float *d_values, int dim, int window_rows, int min_seg, int seg_cap,
                                      int64_t min_window_nnz, gcnb_stream_t stream);
+/* Background staging: the same build and upload on a helper thread with its own stream (host copies of the index are read
+ * back from the device there), while the plan keeps serving products on the generic kernel.  _finish joins the helper
+ * and attaches the result; call it at a point of the caller's choosing (results before / after differ in summation
+ * order only), from the thread that uses the plan, while no product on this plan is being enqueued.  *job = NULL: nothing
+ * to do (other dim, empty matrix, already staged).  _done polls without blocking. */
+typedef struct gcnb_stage_job gcnb_stage_job;
+GCNB_API int gcnb_spmm_plan_stage_async_begin(gcnb_spmm_plan *plan, const float *d_values, int dim, gcnb_stage_job **job);
+GCNB_API int gcnb_spmm_plan_stage_async_done(const gcnb_stage_job *job);
+GCNB_API int gcnb_spmm_plan_stage_async_finish(gcnb_spmm_plan *plan, gcnb_stage_job *job);
 /* out = {staged?, window_rows, staged entries, remainder entries, segments, runs, chunks, partial slots} */
 GCNB_API int gcnb_spmm_plan_stage_info(const gcnb_spmm_plan *plan, int64_t out[8]);
 /* number of 16-column slabs a product of width `dim` runs as through the staged kernels (0: generic kernel).  Widths

@@ -100,6 +100,11 @@ GCNB_API int64_t gcnb_gcn_launches_total(const gcnb_gcn *g);
  * when graph + feature entries <= 8 Mi (GCNB_CUDA_GRAPH=0/1 overrides); never used by a partitioned model, with injected
  * masks, or while GraphSum launches are being timed.  Results are bit-identical to eager launches.
  * gcnb_gcn_uses_cuda_graph: 1 if the next passes may be replayed. */
+/* GCNB_ASYNC_STAGE=1 (large single-GPU models): gcnb_gcn_create returns as soon as the dataset is on the device and the
+ * first epochs run on the generic GraphSum kernel while the window-staged representation is built and uploaded by a helper
+ * thread; it is attached before training epoch GCNB_STAGE_SWITCH_EPOCH (default 128) -- a fixed point, so results do not
+ * depend on timing -- or by this call (which waits for the helper if it is still busy).  No-op otherwise. */
+GCNB_API int gcnb_gcn_finish_setup(gcnb_gcn *g);
 GCNB_API int gcnb_gcn_set_cuda_graph(gcnb_gcn *g, int on);
 GCNB_API int gcnb_gcn_uses_cuda_graph(const gcnb_gcn *g);
 /* measurement hook (bench.py): n_epochs x {train_epoch [+ eval(2)]} bracketed by CUDA events on the engine's stream.

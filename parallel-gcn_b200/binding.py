@@ -49,6 +49,9 @@ _sig("gcnb_spmm_ld_f32", I32, [P, P, P, P, I64, P, I64, I32, P])
 _sig("gcnb_spmm_plan_stage", I32, [P, P, P, P, I32, P])
 _sig("gcnb_spmm_plan_stage_ex", I32, [P, P, P, P, I32, I32, I32, I32, I64, P])
 _sig("gcnb_spmm_plan_stage_info", I32, [P, P])
+_sig("gcnb_spmm_plan_stage_async_begin", I32, [P, P, I32, P])
+_sig("gcnb_spmm_plan_stage_async_done", I32, [P])
+_sig("gcnb_spmm_plan_stage_async_finish", I32, [P, P])
 _sig("gcnb_spmm_plan_stage_slabs", I32, [P, I32])
 _sig("gcnb_stage_host_build", I32, [P, P, I64, I64, I32, I32, I32, I32, I64, I32, I32, P])
 _sig("gcnb_stage_host_build_own", I32, [P, P, I64, I64, I32, I32, I32, I32, I64, I32, I32, I64, I64, P])
@@ -166,6 +169,17 @@ class SpmmPlan:
         hi = h_indices.ctypes.data_as(C.c_void_p) if h_indices is not None else None
         check(lib.gcnb_spmm_plan_stage_ex(self.h, hp, hi, ptr(values), int(dim), window_rows, min_seg, seg_cap,
                                           min_window_nnz, stream()))
+        return self.stage_info()
+
+    def stage_async_begin(self, values, dim=16):
+        """background staging (helper thread + own stream); returns a job handle (None: nothing to do)"""
+        self._staged_values = values
+        job = C.c_void_p()
+        check(lib.gcnb_spmm_plan_stage_async_begin(self.h, ptr(values), int(dim), C.byref(job)))
+        return job if job.value else None
+
+    def stage_async_finish(self, job):
+        check(lib.gcnb_spmm_plan_stage_async_finish(self.h, job))
         return self.stage_info()
 
     def stage_info(self):

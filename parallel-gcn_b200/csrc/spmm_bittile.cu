@@ -34,6 +34,7 @@
 // Reference being replaced: graphsum_kernel, src/module.cu:172-186.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -135,6 +136,13 @@ int bittile_build_host(const uint32_t *indptr, const uint32_t *indices, const fl
   int T = n_threads > 0 ? n_threads : (int)std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency()));
   T = (int)std::max<int64_t>(1, std::min<int64_t>(T, H.n_blk));
 
+  const bool verbose = getenv("GCNB_SETUP_VERBOSE") != nullptr;
+  auto tp = std::chrono::steady_clock::now();
+  auto lap = [&](const char *what) {
+    const auto now = std::chrono::steady_clock::now();
+    if (verbose) fprintf(stderr, "[bittile build] %-28s %7.1f ms\n", what, std::chrono::duration<double, std::milli>(now - tp).count());
+    tp = now;
+  };
   // scales: given, or the square roots of the diagonal entries (GraphSum: value[i,i] = 1/deg_i, s_i = 1/sqrt(deg_i));
   // a row without a usable diagonal gets NaN, which fails every factorisation check => its entries stay in the remainder
   H.row_scale.assign((size_t)n_rows, 0.f);
@@ -162,6 +170,7 @@ int bittile_build_host(const uint32_t *indptr, const uint32_t *indices, const fl
     H.row_scale.resize((size_t)n_rows, nan);
   }
 
+  lap("scales");
   std::vector<BlockOut> blocks((size_t)H.n_blk);
   std::atomic<int64_t> next{0};
   const uint32_t thr = (uint32_t)H.min_tile_nnz;
@@ -224,6 +233,7 @@ int bittile_build_host(const uint32_t *indptr, const uint32_t *indices, const fl
     }
   });
 
+  lap("tiles + remainder per block");
   // CTA schedule: longest-processing-time greedy over the row blocks that own tiles (cost = tiles + a per-block
   // constant for the epilogue and the pipeline drain); deterministic
   std::vector<uint32_t> order;
@@ -284,6 +294,7 @@ int bittile_build_host(const uint32_t *indptr, const uint32_t *indices, const fl
   H.r_indptr[(size_t)n_rows] = (uint32_t)racc;
   H.r_indices.alloc((size_t)racc);
   H.r_values.alloc((size_t)racc);
+  lap("schedule + offsets");
   next = 0;
   bt_run_threads(T, [&](int) {
     for (;;) {
@@ -305,6 +316,7 @@ int bittile_build_host(const uint32_t *indptr, const uint32_t *indices, const fl
       std::vector<float>().swap(o.rval);
     }
   });
+  lap("flatten");
   // the kernels multiply by the scales unconditionally: rows / columns without a usable scale own no bit, give them 0
   for (float &x : H.row_scale)
     if (!(fabsf(x) <= 3.0e38f)) x = 0.f;

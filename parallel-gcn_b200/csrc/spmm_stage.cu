@@ -901,13 +901,14 @@ int gcnb_spmm_plan_stage(gcnb_spmm_plan *p, const uint32_t *h_indptr, const uint
   return gcnb_spmm_plan_stage_ex(p, h_indptr, h_indices, d_values, dim, 0, 0, 0, 0, stream_);
 }
 
-int gcnb_spmm_plan_stage_ex(gcnb_spmm_plan *p, const uint32_t *h_indptr, const uint32_t *h_indices,
-                            const float *d_values, int dim, int window_rows, int min_seg, int seg_cap,
-                            int64_t min_window_nnz, gcnb_stream_t stream_) {
-  if (!p || !d_values) return GCNB_E_BADARG;
+// Builds the staged representation of `p` WITHOUT attaching it (*out = nullptr when staging is not worthwhile): reads only
+// fields of the plan that never change after gcnb_spmm_plan_create / gcnb_spmm_plan_set_own_cols, so it may run on a
+// helper thread (own stream) while the plan is in use on the generic kernel.
+static int stage_make(const gcnb_spmm_plan *p, const uint32_t *h_indptr, const uint32_t *h_indices, const float *d_values,
+                      int dim, int window_rows, int min_seg, int seg_cap, int64_t min_window_nnz, gcnb_stream_t stream_,
+                      StagedDev **out) {
+  *out = nullptr;
   cudaStream_t stream = as_stream(stream_);
-  if (dim != 16 || p->n_rows == 0 || p->nnz == 0) return 0;  // only the dim-16 kernel exists; not an error
-  if (p->staged && p->staged->dim == dim) return gather_values(p->staged, d_values, stream);  // (new) values: re-gather
   std::vector<uint32_t> indptr_copy, indices_copy;
   if (!h_indptr) {
     indptr_copy.resize((size_t)p->n_rows + 1);
@@ -990,8 +991,68 @@ int gcnb_spmm_plan_stage_ex(gcnb_spmm_plan *p, const uint32_t *h_indptr, const u
     return fail(rc);
   if ((rc = gather_values(s, d_values, stream))) return fail(rc);
   if ((rc = (int)cudaStreamSynchronize(stream))) return fail(rc);
-  p->staged = s;
+  *out = s;
   return 0;
+}
+
+int gcnb_spmm_plan_stage_ex(gcnb_spmm_plan *p, const uint32_t *h_indptr, const uint32_t *h_indices,
+                            const float *d_values, int dim, int window_rows, int min_seg, int seg_cap,
+                            int64_t min_window_nnz, gcnb_stream_t stream_) {
+  if (!p || !d_values) return GCNB_E_BADARG;
+  if (dim != 16 || p->n_rows == 0 || p->nnz == 0) return 0;  // only the dim-16 kernel exists; not an error
+  if (p->staged && p->staged->dim == dim) return gather_values(p->staged, d_values, as_stream(stream_));  // re-gather
+  StagedDev *s = nullptr;
+  const int rc = stage_make(p, h_indptr, h_indices, d_values, dim, window_rows, min_seg, seg_cap, min_window_nnz, stream_, &s);
+  if (rc) return rc;
+  if (s) p->staged = s;
+  return 0;
+}
+
+// ---- background staging ----------------------------------------------------------------------------------------------
+// The build (0.2 s of host threads at Reddit scale) and the upload of the packed arrays (0.7 GB) run on a helper thread
+// with its own stream while the caller already trains on the generic kernel; _finish joins and attaches.  WHEN the
+// caller finishes is the caller's decision (the engine does it at a fixed epoch), so results do not depend on timing.
+struct gcnb_stage_job {
+  std::thread th;
+  int rc = 0;
+  int device = 0;
+  StagedDev *s = nullptr;
+  std::atomic<int> done{0};
+};
+
+int gcnb_spmm_plan_stage_async_begin(gcnb_spmm_plan *p, const float *d_values, int dim, gcnb_stage_job **out) {
+  if (!p || !d_values || !out) return GCNB_E_BADARG;
+  *out = nullptr;
+  if (dim != 16 || p->n_rows == 0 || p->nnz == 0 || p->staged) return 0;  // nothing to do: no job
+  auto *job = new gcnb_stage_job();
+  GCNB_CHECK(cudaGetDevice(&job->device));
+  const gcnb_spmm_plan *cp = p;
+  job->th = std::thread([job, cp, d_values, dim] {
+    cudaStream_t st = nullptr;
+    int rc = (int)cudaSetDevice(job->device);
+    if (!rc) rc = (int)cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+    // host copies of the index are read back from the device here (the caller's host arrays may be gone by now)
+    if (!rc) rc = stage_make(cp, nullptr, nullptr, d_values, dim, 0, 0, 0, 0, (gcnb_stream_t)st, &job->s);
+    if (st) cudaStreamDestroy(st);
+    job->rc = rc;
+    job->done.store(1, std::memory_order_release);
+  });
+  *out = job;
+  return 0;
+}
+
+int gcnb_spmm_plan_stage_async_done(const gcnb_stage_job *job) { return !job || job->done.load(std::memory_order_acquire); }
+
+int gcnb_spmm_plan_stage_async_finish(gcnb_spmm_plan *p, gcnb_stage_job *job) {
+  if (!job) return 0;
+  if (job->th.joinable()) job->th.join();
+  const int rc = job->rc;
+  if (!rc && job->s) {
+    if (p && !p->staged) p->staged = job->s;
+    else stage_destroy(job->s);
+  }
+  delete job;
+  return rc;
 }
 
 int gcnb_spmm_plan_set_own_cols(gcnb_spmm_plan *p, int64_t col0, int64_t col1) {

@@ -59,6 +59,7 @@ _sig("gcnb_gcn_set_mask", I32, [P, I32, P])
 _sig("gcnb_gcn_launches_per_epoch", I64, [P])
 _sig("gcnb_gcn_graph_staged", I32, [P])
 _sig("gcnb_gcn_set_cuda_graph", I32, [P, I32])
+_sig("gcnb_gcn_finish_setup", I32, [P])
 _sig("gcnb_gcn_uses_cuda_graph", I32, [P])
 _sig("gcnb_gcn_launches_total", I64, [P])
 _sig("gcnb_gcn_timed_epochs", I32, [P, I32, I32, I32, P])
@@ -369,6 +370,13 @@ class GCN:
 
     def launches_per_epoch(self):
         return int(lib.gcnb_gcn_launches_per_epoch(self.h))
+
+    def graph_staged(self):
+        return bool(lib.gcnb_gcn_graph_staged(self.h))
+
+    def finish_setup(self):
+        """attach the background-staged GraphSum representation now (GCNB_ASYNC_STAGE=1); no-op otherwise"""
+        check(lib.gcnb_gcn_finish_setup(self.h))
 
     def set_cuda_graph(self, on):
         check(lib.gcnb_gcn_set_cuda_graph(self.h, int(on)))

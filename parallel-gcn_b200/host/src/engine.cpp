@@ -382,6 +382,11 @@ int gcnb_gcn_set_cuda_graph(gcnb_gcn *g, int on) {
   g->gcn->set_use_cuda_graph(on != 0);
   return 0;
 }
+int gcnb_gcn_finish_setup(gcnb_gcn *g) {
+  if (!g) return GCNB_E_BADARG;
+  g->gcn->finish_setup();
+  return 0;
+}
 int gcnb_gcn_uses_cuda_graph(const gcnb_gcn *g) { return g ? (int)g->gcn->uses_cuda_graph() : -1; }
 int gcnb_gcn_graph_staged(const gcnb_gcn *g) { return g ? (int)g->gcn->graph_staged() : -1; }
 int64_t gcnb_gcn_launches_total(const gcnb_gcn *g) { return g ? (int64_t)g->gcn->launches_total() : -1; }

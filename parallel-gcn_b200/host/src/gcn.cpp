@@ -205,6 +205,20 @@ struct GCNEngineState {
   natural epochs_run = 0;
   int graph_spmm_kernels = 1, feat_spmm_kernels = 1, feat_csc_kernels = 1;  // 1 + combine kernel when rows are split
   bool graph_staged = false;  // window-staged GraphSum (csrc/spmm_stage.cu) for widths 16 and >= 64
+  // GCNB_ASYNC_STAGE=1: that representation is built and uploaded on a helper thread while the first epochs run on the
+  // generic kernel; it is attached before training epoch `stage_switch_epoch` (or by finish_setup()), never at a
+  // timing-dependent moment
+  gcnb_stage_job *stage_job = nullptr;
+  size_t train_calls = 0, stage_switch_epoch = 128;
+  void finish_stage() {
+    if (!stage_job) return;
+    CHECK_CUDA_ERROR(cudaStreamSynchronize(stream));
+    GCNB_CALL(gcnb_spmm_plan_stage_async_finish(graph_plan, stage_job));
+    stage_job = nullptr;
+    int64_t sinfo[8];
+    GCNB_CALL(gcnb_spmm_plan_stage_info(graph_plan, sinfo));
+    graph_staged = sinfo[0] != 0;
+  }
   // optional per-launch timing of the GraphSum SpMM (bench.py roofline): event pairs on the engine stream
   bool time_graphsum = false;
   std::vector<cudaEvent_t> gs_events;
@@ -266,6 +280,7 @@ struct GCNEngineState {
     gs_used = 0;
   }
   ~GCNEngineState() {
+    if (stage_job) gcnb_spmm_plan_stage_async_finish(graph_plan, stage_job);
     drop_graphs();
     for (auto e : gs_events) cudaEventDestroy(e);
     if (feat_csc_plan) gcnb_spmm_plan_destroy(feat_csc_plan);
@@ -430,7 +445,13 @@ void GCN::init(bool quiet, const natural *h_graph_indptr, const natural *h_graph
       wanted |= d == 16 || d >= 64;
     }
     if (wanted && st->dist) GCNB_CALL(gcnb_spmm_plan_set_own_cols(st->graph_plan, (int64_t)st->row0, (int64_t)(st->row0 + N)));
-    if (wanted) {
+    const char *async_env = getenv("GCNB_ASYNC_STAGE");
+    const size_t big = dev_data.dev_graph_index.indices_size + dev_data.dev_feature_index.indices_size;
+    if (wanted && !st->dist && async_env && atoi(async_env) != 0 && big > (size_t(8) << 20)) {
+      // large graphs (no CUDA-graph replay): start training right away, stage in the background
+      if (const char *e = getenv("GCNB_STAGE_SWITCH_EPOCH")) st->stage_switch_epoch = (size_t)std::max(0, atoi(e));
+      GCNB_CALL(gcnb_spmm_plan_stage_async_begin(st->graph_plan, dev_data.dev_graph_value.get(), 16, &st->stage_job));
+    } else if (wanted) {
       GCNB_CALL(gcnb_spmm_plan_stage(st->graph_plan, h_graph_indptr, h_graph_indices, dev_data.dev_graph_value.get(),
                                      16, st->stream));
       int64_t sinfo[8];
@@ -646,7 +667,7 @@ void GCN::forward_pass(bool training, natural split, cudaStream_t s) {
     Variable::rng_consume(input_elems);  // the reference draws even when p == 0
     st->x_train_vals = xvals;
   }
-  if (!training && st->dense_fast && st->allow_reorder && !st->ax_tried) {
+  if (!training && st->dense_fast && st->allow_reorder && !st->ax_tried && !st->stage_job) {  // after the staging switch
     st->ax_tried = true;
     if (st->dist) {
       if (st->ax_planned) {  // collective: every rank takes this branch (ax_planned depends on global sizes only)
@@ -862,7 +883,11 @@ void GCN::train_body(cudaStream_t s) {
   st->launches++;
 }
 
+void GCN::finish_setup() { st->finish_stage(); }
+
 std::pair<real, real> GCN::train_epoch() {
+  if (st->stage_job && st->train_calls >= st->stage_switch_epoch) st->finish_stage();
+  st->train_calls++;
   const size_t before = st->launches;
   cudaStream_t s = st->stream;
   if (st->graphs_usable() && st->train_exec) {

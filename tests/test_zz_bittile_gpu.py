@@ -142,3 +142,68 @@ def test_engine_training_with_bit_tiles_matches_default_path(gcnb, dev):
         assert abs(t0[0] - t1[0]) <= 2e-5 * (1 + ep) * abs(t0[0]) and abs(v0[0] - v1[0]) <= 2e-5 * (1 + ep) * abs(v0[0])
     for a, b in zip(w0, w1):
         assert_close(b, a, rtol=1e-4, atol=1e-6, what="weights after 4 epochs")
+
+
+# ---- background staging of the window-staged GraphSum (spmm_stage.cu, gcnb_spmm_plan_stage_async_*): opt-in until it has
+# ---- been run on a GPU (GCNB_TEST_ASYNC_STAGE=1)
+@pytest.mark.skipif(os.environ.get("GCNB_TEST_ASYNC_STAGE") != "1", reason="opt-in: background staging not yet run on a GPU")
+def test_background_staging_attaches_the_same_plan(gcnb, dev):
+    import torch
+    from tests.test_stage_cpu import community_csr
+    rng = np.random.default_rng(21)
+    n = 20000
+    indptr, indices = community_csr(rng, n, 5, 100, 0.8, ((77, 2500),))
+    values = rng.standard_normal(len(indices)).astype(f32)
+    d_ip, d_ix, d_v = (to_dev(a, dev) for a in (indptr, indices, values))
+    x = torch.randn(n, 16, device=dev)
+    sync_plan = gcnb.SpmmPlan(d_ip, d_ix, n)
+    generic = torch.empty(n, 16, device=dev)
+    sync_plan.spmm(d_v, x, generic, 16)
+    assert sync_plan.stage(d_v, 16)["staged"] == 1
+    staged = torch.empty(n, 16, device=dev)
+    sync_plan.spmm(d_v, x, staged, 16)
+    plan = gcnb.SpmmPlan(d_ip, d_ix, n)
+    job = plan.stage_async_begin(d_v, 16)
+    assert job is not None
+    out = torch.empty(n, 16, device=dev)
+    for _ in range(5):  # the plan serves products on the generic kernel while the helper builds
+        plan.spmm(d_v, x, out, 16)
+        assert torch.equal(out, generic)
+    torch.cuda.synchronize()
+    assert plan.stage_async_finish(job)["staged"] == 1
+    plan.spmm(d_v, x, out, 16)
+    assert torch.equal(out, staged), "the background build must produce the plan the synchronous call produces"
+    plan.close()
+    sync_plan.close()
+
+
+@pytest.mark.skipif(os.environ.get("GCNB_TEST_ASYNC_STAGE") != "1", reason="opt-in: background staging not yet run on a GPU")
+def test_engine_background_staging_switches_at_a_fixed_epoch(gcnb, dev):
+    import importlib
+    eng = importlib.import_module("parallel_gcn_b200.engine")
+    # > 8 Mi entries so that CUDA-graph replay is off and background staging applies
+    ds = eng.synth_dataset(60000, 60000 * 80, 16, 6, n_blocks=12, seed=3)
+
+    def run(env):
+        os.environ.update(env)
+        try:
+            g = eng.GCN(ds, hidden_dims=(16,), dropouts=(0.5, 0.5))
+            staged0 = g.graph_staged()
+            hist = [(g.train_epoch(), g.eval(2)) for _ in range(5)]
+            staged1 = g.graph_staged()
+            w = [g.weight(l) for l in range(2)]
+            g.close()
+            return hist, w, staged0, staged1
+        finally:
+            for k in env:
+                os.environ.pop(k, None)
+
+    h0, w0, a0, a1 = run({})
+    h1, w1, b0, b1 = run({"GCNB_ASYNC_STAGE": "1", "GCNB_STAGE_SWITCH_EPOCH": "2"})
+    h2, w2, _, _ = run({"GCNB_ASYNC_STAGE": "1", "GCNB_STAGE_SWITCH_EPOCH": "2"})
+    assert a0 and a1 and not b0 and b1
+    assert h1 == h2 and all(np.array_equal(x, y) for x, y in zip(w1, w2)), "fixed switch epoch => reproducible bits"
+    for ep, ((t0, v0), (t1, v1)) in enumerate(zip(h0, h1)):
+        assert abs(t0[0] - t1[0]) <= 2e-5 * (1 + ep) * abs(t0[0]) and abs(v0[0] - v1[0]) <= 2e-5 * (1 + ep) * abs(v0[0])
+    for a, b in zip(w0, w1):
+        assert_close(b, a, rtol=1e-4, atol=1e-6, what="weights after 5 epochs")
