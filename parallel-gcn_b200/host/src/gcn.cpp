@@ -210,9 +210,22 @@ struct GCNEngineState {
   // timing-dependent moment
   gcnb_stage_job *stage_job = nullptr;
   size_t train_calls = 0, stage_switch_epoch = 128;
+  std::thread bt_thread;                    // background build of the bit-tile plan (GCNB_BITTILE=1 in background mode)
+  gcnb_bittile_plan *bt_pending = nullptr;
+  int bt_rc = 0;
+  const real *graph_values_dev = nullptr;
   void finish_stage() {
     if (!stage_job) return;
     CHECK_CUDA_ERROR(cudaStreamSynchronize(stream));
+    if (bt_thread.joinable()) {
+      bt_thread.join();
+      GCNB_CALL(bt_rc);
+      if (bt_pending) {
+        graph_bittile = bt_pending;
+        bt_pending = nullptr;
+        GCNB_CALL(gcnb_spmm_plan_attach_bittile(graph_plan, graph_bittile, graph_values_dev));
+      }
+    }
     GCNB_CALL(gcnb_spmm_plan_stage_async_finish(graph_plan, stage_job));
     stage_job = nullptr;
     int64_t sinfo[8];
@@ -280,6 +293,8 @@ struct GCNEngineState {
     gs_used = 0;
   }
   ~GCNEngineState() {
+    if (bt_thread.joinable()) bt_thread.join();
+    if (bt_pending) gcnb_bittile_plan_destroy(bt_pending);
     if (stage_job) gcnb_spmm_plan_stage_async_finish(graph_plan, stage_job);
     drop_graphs();
     for (auto e : gs_events) cudaEventDestroy(e);
@@ -451,6 +466,7 @@ void GCN::init(bool quiet, const natural *h_graph_indptr, const natural *h_graph
       // large graphs (no CUDA-graph replay): start training right away, stage in the background
       if (const char *e = getenv("GCNB_STAGE_SWITCH_EPOCH")) st->stage_switch_epoch = (size_t)std::max(0, atoi(e));
       GCNB_CALL(gcnb_spmm_plan_stage_async_begin(st->graph_plan, dev_data.dev_graph_value.get(), 16, &st->stage_job));
+      st->graph_values_dev = dev_data.dev_graph_value.get();
     } else if (wanted) {
       GCNB_CALL(gcnb_spmm_plan_stage(st->graph_plan, h_graph_indptr, h_graph_indices, dev_data.dev_graph_value.get(),
                                      16, st->stream));
@@ -461,31 +477,52 @@ void GCN::init(bool quiet, const natural *h_graph_indptr, const natural *h_graph
   }
   {
     // opt-in (round-1 status: kernel parity-checked on B200, engine path not yet): the dense blocks of the adjacency as
-    // bit maps on the tcgen05 tensor cores (csrc/spmm_bittile.cu); takes precedence over the staged path at width 16
+    // bit maps on the tcgen05 tensor cores (csrc/spmm_bittile.cu); takes precedence over the staged path at width 16.
+    // With GCNB_ASYNC_STAGE=1 (large graphs) the plan is built on a helper thread and attached at the staging switch.
     const char *e = getenv("GCNB_BITTILE");
     bool d16 = false;
     for (const GCNLayer &ly : st->layers) d16 |= (ly.reorder ? ly.in_dim : ly.out_dim) == 16;
     if (e && atoi(e) != 0 && !st->dist && d16 && N > 0) {
       const size_t nnz = dev_data.dev_graph_index.indices_size;
-      std::vector<natural> hp, hi;
-      if (!h_graph_indptr || !h_graph_indices) {
-        hp.resize((size_t)N + 1);
-        hi.resize(nnz);
-        CHECK_CUDA_ERROR(cudaMemcpy(hp.data(), dev_data.dev_graph_index.dev_indptr.get(), hp.size() * sizeof(natural), cudaMemcpyDeviceToHost));
-        CHECK_CUDA_ERROR(cudaMemcpy(hi.data(), dev_data.dev_graph_index.dev_indices.get(), nnz * sizeof(natural), cudaMemcpyDeviceToHost));
-      }
-      std::vector<real> hv(nnz);
-      CHECK_CUDA_ERROR(cudaStreamSynchronize(st->stream));
-      CHECK_CUDA_ERROR(cudaMemcpy(hv.data(), dev_data.dev_graph_value.get(), nnz * sizeof(real), cudaMemcpyDeviceToHost));
-      GCNB_CALL(gcnb_bittile_plan_create(hp.empty() ? h_graph_indptr : hp.data(), hi.empty() ? h_graph_indices : hi.data(),
-                                         hv.data(), (int64_t)N, (int64_t)N, nullptr, nullptr, 0, 0, 0, st->stream, &st->graph_bittile));
-      int64_t binfo[8];
-      GCNB_CALL(gcnb_bittile_plan_info(st->graph_bittile, binfo));
-      if (binfo[0] > 0 && binfo[1] * 4 >= (int64_t)nnz) {  // worth it when at least a quarter of the entries sit in tiles
-        GCNB_CALL(gcnb_spmm_plan_attach_bittile(st->graph_plan, st->graph_bittile, dev_data.dev_graph_value.get()));
+      const natural *d_ip = dev_data.dev_graph_index.dev_indptr.get(), *d_ix = dev_data.dev_graph_index.dev_indices.get();
+      const real *d_gv = dev_data.dev_graph_value.get();
+      CHECK_CUDA_ERROR(cudaStreamSynchronize(st->stream));  // graph_value may have been computed on this stream
+      // everything is read back from the device: the helper must not depend on the caller's host arrays
+      auto make = [N, nnz, d_ip, d_ix, d_gv](cudaStream_t stream, gcnb_bittile_plan **out) -> int {
+        *out = nullptr;
+        std::vector<natural> hp((size_t)N + 1), hi(nnz);
+        std::vector<real> hv(nnz);
+        int rc = (int)cudaMemcpyAsync(hp.data(), d_ip, hp.size() * sizeof(natural), cudaMemcpyDeviceToHost, stream);
+        if (!rc) rc = (int)cudaMemcpyAsync(hi.data(), d_ix, nnz * sizeof(natural), cudaMemcpyDeviceToHost, stream);
+        if (!rc) rc = (int)cudaMemcpyAsync(hv.data(), d_gv, nnz * sizeof(real), cudaMemcpyDeviceToHost, stream);
+        if (!rc) rc = (int)cudaStreamSynchronize(stream);
+        if (rc) return rc;
+        gcnb_bittile_plan *bt = nullptr;
+        rc = gcnb_bittile_plan_create(hp.data(), hi.data(), hv.data(), (int64_t)N, (int64_t)N, nullptr, nullptr, 0, 0, 0,
+                                      (gcnb_stream_t)stream, &bt);
+        if (rc) return rc;
+        int64_t binfo[8];
+        gcnb_bittile_plan_info(bt, binfo);
+        if (binfo[0] > 0 && binfo[1] * 4 >= (int64_t)nnz) *out = bt;  // worth it when a quarter of the entries sit in tiles
+        else gcnb_bittile_plan_destroy(bt);
+        return 0;
+      };
+      if (st->stage_job) {  // background mode is on
+        int device = 0;
+        CHECK_CUDA_ERROR(cudaGetDevice(&device));
+        GCNEngineState *state = st.get();
+        st->bt_thread = std::thread([state, make, device] {
+          cudaStream_t hs = nullptr;
+          int rc = (int)cudaSetDevice(device);
+          if (!rc) rc = (int)cudaStreamCreateWithFlags(&hs, cudaStreamNonBlocking);
+          if (!rc) rc = make(hs, &state->bt_pending);
+          if (hs) cudaStreamDestroy(hs);
+          state->bt_rc = rc;
+        });
       } else {
-        gcnb_bittile_plan_destroy(st->graph_bittile);
-        st->graph_bittile = nullptr;
+        GCNB_CALL(make(st->stream, &st->graph_bittile));
+        if (st->graph_bittile)
+          GCNB_CALL(gcnb_spmm_plan_attach_bittile(st->graph_plan, st->graph_bittile, dev_data.dev_graph_value.get()));
       }
     }
   }
