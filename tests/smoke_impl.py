@@ -41,3 +41,17 @@ def run():
     print("smoke ok: graphsum parity, epoch loss %.6f (oracle %.6f), val acc %.4f, %d launches/epoch" %
           (le, lo, ve[1], g.launches_per_epoch()))
     g.close()
+    # 3) GraphSum on a community graph through the tcgen05 bit-tile path (csrc/spmm_bittile.cu)
+    from tests.test_bittile_cpu import gcn_graph
+    ip, ix, gv = gcn_graph(np.random.default_rng(1), 1500, 3, 40, 3)
+    xb = np.random.default_rng(2).standard_normal((1500, 16)).astype(np.float32)
+    want_b = np.empty((1500, 16), np.float32)
+    O.lib.orc_graphsum(1500, 16, O._p(ip), O._p(ix), O._p(gv), O._p(xb), O._p(want_b))
+    bt = gcnb.BitTilePlan(ip, ix, gv, 1500, min_tile_nnz=64)
+    out_b = torch.empty((1500, 16), device=dev)
+    bt.spmm16(to_dev(xb, dev), out_b)
+    torch.cuda.synchronize()
+    assert bt.info()["n_tiles"] > 0
+    assert_close(to_np(out_b), want_b, what="smoke bit-tile graphsum")
+    bt.close()
+    print("smoke ok: bit-tile GraphSum (tcgen05) parity on a community graph")
