@@ -569,6 +569,7 @@ int gcnb::spmm_generic_launch(gcnb_spmm_plan *p, const float *d_values, const ui
       blocks_per_sm = it->second;
     }
   }
+  if (p->max_cta_per_sm > 0) blocks_per_sm = std::min(blocks_per_sm, p->max_cta_per_sm);
   const int64_t warps_needed = p->n_seg;
   int64_t grid = (int64_t)p->n_queues * blocks_per_sm;
   const int64_t min_grid = (warps_needed + (kThreads / 32) - 1) / (kThreads / 32);

@@ -1010,6 +1010,10 @@ int gcnb_bittile_plan_create(const uint32_t *h_indptr, const uint32_t *h_indices
   if ((rc = (int)cudaMemsetAsync(p->d_P, 0, p_bytes, stream))) return fail(rc);  // blocks without tiles stay 0 for ever
   if ((rc = (int)cudaStreamSynchronize(stream))) return fail(rc);                // host arrays go out of scope
   if ((rc = gcnb_spmm_plan_create(p->d_r_indptr, p->d_r_indices, n_rows, n_cols, 0, stream_, &p->rem))) return fail(rc);
+  // tuning probe: cap the remainder kernel's CTAs per SM so that, whichever kernel the block scheduler sees first, the MMA
+  // kernel's CTA (448 threads x 68 registers) still fits on every SM (first measurements: launched at the same instant the
+  // two kernels took 772 us instead of 502)
+  if (const char *e = getenv("GCNB_BT_REM_CTAS")) p->rem->max_cta_per_sm = std::max(0, atoi(e));
   if ((rc = (int)cudaStreamCreateWithFlags(&p->aux, cudaStreamNonBlocking))) return fail(rc);
   if ((rc = (int)cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming))) return fail(rc);
   if ((rc = (int)cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming))) return fail(rc);

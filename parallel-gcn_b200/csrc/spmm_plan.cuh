@@ -115,6 +115,7 @@ struct gcnb_spmm_plan {
   int64_t scratch_dim = 0;
   int64_t max_deg = 0;
   int batch = 1;                      // segments claimed per atomic ticket (short-row graphs: > 1)
+  int max_cta_per_sm = 0;             // > 0 caps the persistent grid (a co-resident kernel needs the rest of the SM)
   gcnb::StagedDev *staged = nullptr;  // optional window-staged fast path (gcnb_spmm_plan_stage)
   int64_t own_col0 = 0, own_col1 = 0;  // gcnb_spmm_plan_set_own_cols (before staging)
   // optional bit-tile representation (spmm_bittile.cu), borrowed: used for 16-column contiguous products with this value array
