@@ -95,6 +95,8 @@ GCNB_API int gcnb_gcn_set_mask(gcnb_gcn *g, int site, const uint8_t *host_mask);
 GCNB_API int64_t gcnb_gcn_launches_per_epoch(const gcnb_gcn *g);
 /* 1 if GraphSum at feature width 16 uses the window-staged kernels (graph with column locality), else 0 */
 GCNB_API int gcnb_gcn_graph_staged(const gcnb_gcn *g);
+/* 1 if GraphSum at width 16 runs the tcgen05 bit-tile path (GCNB_BITTILE=1, parallel-gcn_b200/csrc/spmm_bittile.cu) */
+GCNB_API int gcnb_gcn_graph_bittile(const gcnb_gcn *g);
 GCNB_API int64_t gcnb_gcn_launches_total(const gcnb_gcn *g);
 /* CUDA-graph replay of the training epoch and of the evaluation passes (small datasets are launch-bound).  Default: on
  * when graph + feature entries <= 8 Mi (GCNB_CUDA_GRAPH=0/1 overrides); never used by a partitioned model, with injected

@@ -58,6 +58,7 @@ _sig("gcnb_gcn_get_logits", I32, [P, P])
 _sig("gcnb_gcn_set_mask", I32, [P, I32, P])
 _sig("gcnb_gcn_launches_per_epoch", I64, [P])
 _sig("gcnb_gcn_graph_staged", I32, [P])
+_sig("gcnb_gcn_graph_bittile", I32, [P])
 _sig("gcnb_gcn_set_cuda_graph", I32, [P, I32])
 _sig("gcnb_gcn_finish_setup", I32, [P])
 _sig("gcnb_gcn_uses_cuda_graph", I32, [P])
@@ -373,6 +374,9 @@ class GCN:
 
     def graph_staged(self):
         return bool(lib.gcnb_gcn_graph_staged(self.h))
+
+    def graph_bittile(self):
+        return bool(lib.gcnb_gcn_graph_bittile(self.h))
 
     def finish_setup(self):
         """attach the background-staged GraphSum representation now (GCNB_ASYNC_STAGE=1); no-op otherwise"""

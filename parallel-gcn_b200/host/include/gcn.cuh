@@ -158,6 +158,7 @@ class GCN {
   // GCNB_ASYNC_STAGE=1 builds the staged GraphSum representation in the background and attaches it before a fixed training
   // epoch (GCNB_STAGE_SWITCH_EPOCH, default 128); finish_setup() attaches it now (waits for the helper if need be)
   void finish_setup();
+  bool graph_bittile() const;  // GraphSum at width 16 runs the tcgen05 bit-tile path (GCNB_BITTILE=1)
   bool graph_staged() const;  // GraphSum at widths 16 / >= 64 runs the window-staged kernels (csrc/spmm_stage.cu)
   size_t launches_total() const;
   void set_time_graphsum(bool on);                        // event pair around every GraphSum launch

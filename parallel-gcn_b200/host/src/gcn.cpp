@@ -588,6 +588,7 @@ void GCN::set_reorder(bool on) {
 }
 size_t GCN::launches_per_epoch() const { return st->launches_last_epoch; }
 bool GCN::graph_staged() const { return st->graph_staged; }
+bool GCN::graph_bittile() const { return st->graph_bittile != nullptr; }
 size_t GCN::launches_total() const { return st->launches; }
 void GCN::set_time_graphsum(bool on) {
   st->drop_graphs();
