@@ -34,6 +34,10 @@ step 300 r2_bench_default.log python bench.py --no-cpu-baseline
 step 300 r2_bench_async.log env GCNB_ASYNC_STAGE=1 python bench.py --no-cpu-baseline
 step 300 r2_bench_bittile.log env GCNB_BITTILE=1 python bench.py --no-cpu-baseline
 step 300 r2_bench_bittile_rb2.log env GCNB_BITTILE=1 GCNB_BT_RB=2 python bench.py --no-cpu-baseline
+# 5b. same-box A/B against the reference's OWN CUDA code (oracle/_ref/ref_gpu_bench, built by `make -C oracle`)
+step 300 r2_ref_gpu_cora.log python scripts/bench_ref_gpu.py --dataset cora --epochs 100 --reps 5
+step 300 r2_ref_gpu_citeseer.log python scripts/bench_ref_gpu.py --dataset citeseer --epochs 100 --reps 5
+step 900 r2_ref_gpu_reddit.log python scripts/bench_ref_gpu.py --dataset reddit_shape --epochs 20 --reps 1 --timeout 600
 # 6. one full-set ncu capture of the MMA kernel of the best shape (edit the env / flags), after the runs above exited 0:
 #   ncu --set full --clock-control none --import-source on -k regex:bt_mma -c 1 -o gpurun_out/r2_bt_mma \
 #       python scripts/probe_bittile.py --stage graph --scale 1 --iters 1 --staged 0 --rb 2
