@@ -265,3 +265,143 @@ def test_schedule_is_balanced_and_deterministic(gcnb):
         assert np.array_equal(a[k], b[k]), k
     load = np.diff(a["cta_tile_ptr"].astype(np.int64))
     assert load.max() <= load.mean() * 1.5 + 8
+
+
+# ---- mbarrier protocol of the MMA kernels, simulated -----------------------------------------------------------------
+# A discrete-event model of one CTA of bt_mma_kernel / bt_mma_wide_kernel: the warp roles are state machines that follow
+# the kernels' stage / use / parity arithmetic line by line, the barriers have the hardware's semantics (pending count,
+# transaction bytes, phase parity -- a wait sees only the PARITY of the phase, so an overrun by two phases blocks for
+# ever), tcgen05.commit arrivals and bulk-copy completions are delayed events that fire in issue order.  A random
+# scheduler interleaves everything; the run must finish (no deadlock) and every MMA must find in its stage exactly the
+# tile / chunk it is meant to consume.
+class _Bar:
+    def __init__(self, count):
+        self.count, self.pending, self.tx, self.done = count, count, 0, 0
+
+    def _check(self):
+        if self.pending == 0 and self.tx == 0:
+            self.done += 1
+            self.pending = self.count
+
+    def arrive(self, tx=0):
+        assert self.pending > 0, "more arrivals than the barrier expects in this phase"
+        self.tx += tx
+        self.pending -= 1
+        self._check()
+
+    def complete_tx(self, n):
+        self.tx -= n
+        self._check()
+
+    def passed(self, parity):  # mbarrier.try_wait.parity
+        return (self.done & 1) != parity
+
+
+def _simulate_cta(items, unified, stages_a, stages_b, n_acc, rng):
+    """items: list of tile counts per row block.  Returns the number of scheduler steps."""
+    T = sum(items)
+    ends = np.cumsum(items)
+    if unified:
+        full = [_Bar(5) for _ in range(stages_a)]
+        free = [_Bar(1) for _ in range(stages_a)]
+        a_full = b_full = full
+        a_empty = b_empty = free
+        stages_b = stages_a
+    else:
+        a_full, a_empty = [_Bar(4) for _ in range(stages_a)], [_Bar(1) for _ in range(stages_a)]
+        b_full, b_empty = [_Bar(1) for _ in range(stages_b)], [_Bar(1) for _ in range(stages_b)]
+    acc_full, acc_empty = [_Bar(1), _Bar(1)], [_Bar(4), _Bar(4)]
+    A = [[None] * 4 for _ in range(stages_a)]   # tile held by (stage, lane quarter)
+    B = [None] * stages_b
+    acc_owner = [None, None]                    # item whose sums sit in the accumulator set
+    events = []                                 # delayed arrivals, fired in order per queue
+    copies = []
+
+    def expander(g, quarter):
+        for t in range(g, T, 2):
+            s, use = t % stages_a, t // stages_a
+            if use > 0:
+                while not a_empty[s].passed((use - 1) & 1):
+                    yield
+            A[s][quarter] = t
+            a_full[s].arrive()
+            yield
+
+    def producer():
+        for t in range(T):
+            s, use = t % stages_b, t // stages_b
+            if use > 0:
+                while not b_empty[s].passed((use - 1) & 1):
+                    yield
+            b_full[s].arrive(tx=6144)
+            copies.append((s, t))
+            yield
+
+    def mma():
+        t = 0
+        for k, n_tiles in enumerate(items):
+            st, use = k & 1, k >> 1
+            if use > 0:
+                while not acc_empty[st].passed((use - 1) & 1):
+                    yield
+            acc_owner[st] = k
+            for idx in range(n_tiles):
+                sa, ua, sb, ub = t % stages_a, t // stages_a, t % stages_b, t // stages_b
+                while not a_full[sa].passed(ua & 1):
+                    yield
+                while not b_full[sb].passed(ub & 1):
+                    yield
+                assert A[sa] == [t] * 4, ("A stage holds", A[sa], "MMA wants", t)
+                assert B[sb] == t, ("B stage holds", B[sb], "MMA wants", t)
+                assert acc_owner[st] == k
+                if unified:
+                    events.append(free[sa])
+                else:
+                    events.append(a_empty[sa])
+                    events.append(b_empty[sb])
+                t += 1
+                yield
+            events.append(acc_full[st])
+            yield
+
+    def epilogue():
+        for k in range(len(items)):
+            st, use = k & 1, k >> 1
+            while not acc_full[st].passed(use & 1):
+                yield
+            assert acc_owner[st] == k, "the accumulator set was overwritten before the epilogue read it"
+            acc_empty[st].arrive()
+            yield
+
+    agents = [expander(g, q) for g in range(2) for q in range(4)] + [producer(), mma()] + [epilogue() for _ in range(4)]
+    alive = list(range(len(agents)))
+    steps = idle = 0
+    while alive or events or copies:
+        steps += 1
+        assert steps < 400 * (T + len(items) + 10), "no progress: the protocol deadlocks"
+        r = rng.random()
+        if events and r < 0.15:
+            events.pop(0).arrive()           # commits complete in issue order
+            continue
+        if copies and r < 0.3:
+            s, t = copies.pop(int(rng.integers(0, len(copies))))  # bulk copies may land out of order
+            B[s] = t
+            b_full[s].complete_tx(6144)
+            continue
+        if not alive:
+            continue
+        i = alive[int(rng.integers(0, len(alive)))]
+        try:
+            next(agents[i])
+        except StopIteration:
+            alive.remove(i)
+    return steps
+
+
+@pytest.mark.parametrize("name,unified,stages_a,stages_b,n_acc", [
+    ("bt_mma_kernel", False, 4, 8, 4), ("wide<1,1>", True, 8, 8, 2), ("wide<1,2>", True, 4, 4, 2), ("wide<2,1>", True, 5, 5, 1)])
+def test_barrier_protocol_simulation(name, unified, stages_a, stages_b, n_acc):
+    rng = np.random.default_rng(len(name))
+    for items in ([1], [3], [4, 1, 1], [9, 2, 7, 1, 12], [37, 5, 1, 1, 2, 40], list(rng.integers(1, 30, 12))):
+        for _ in range(3):
+            _simulate_cta([int(x) for x in items], unified, stages_a, stages_b, n_acc, rng)
