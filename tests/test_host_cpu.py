@@ -270,7 +270,8 @@ def test_synth_graph_properties(eng):
 
 
 def test_reference_main_compiles_against_product_headers(tmp_path):
-    """drop-in at source level: the reference's own src/main.cpp and test/performance_gpu.cpp compile UNCHANGED against
+    """drop-in at source level: the reference's own src/main.cpp and its three GPU drivers (test/performance_gpu.cpp,
+    tuning_cuda.cpp, tuning_accuracy.cpp, with the flags of the reference Makefile's targets) compile UNCHANGED against
     parallel-gcn_b200/host/include and link against libgcn_b200.so (needs /root/reference; compile+link only)."""
     ref = "/root/reference"
     if not os.path.isdir(ref):
@@ -278,7 +279,10 @@ def test_reference_main_compiles_against_product_headers(tmp_path):
     inc = os.path.join(ROOT, "parallel-gcn_b200", "host", "include")
     os.symlink(inc, tmp_path / "include")
     for sub, fn, flags in (("src", "main.cpp", []), ("src", "main.cpp", ["-DPART2", "-DNO_FEATURE"]),
-                           ("test", "performance_gpu.cpp", ["-DNO_OUTPUT", "-DTUNE_CUDA", "-DPERFORMANCE"])):
+                           ("test", "performance_gpu.cpp", ["-DNO_OUTPUT", "-DTUNE_CUDA", "-DPERFORMANCE"]),
+                           ("test", "tuning_cuda.cpp", ["-DDEBUG_CUDA", "-DNO_OUTPUT", "-DTUNE_CUDA"]),
+                           ("test", "tuning_accuracy.cpp", ["-DDEBUG_CUDA", "-DNO_OUTPUT", "-DTUNE_ACCURACY", "-DPART2"]),
+                           ("test", "tuning_accuracy.cpp", ["-DDEBUG_CUDA", "-DNO_OUTPUT", "-DTUNE_ACCURACY", "-DNO_FEATURE", "-DPART2"])):
         (tmp_path / sub).mkdir(exist_ok=True)
         dst = tmp_path / sub / fn
         if not dst.exists():
