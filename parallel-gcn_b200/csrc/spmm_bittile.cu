@@ -28,6 +28,10 @@
 //                      with rounded fp32 adds (the tensor core's accumulate truncates).
 //   generic kernel     remainder CSR on a second stream, concurrently (it lives on the LSU pipe, the MMA path does not)
 //   bt_add_kernel      C = P + R
+// Two generations of the MMA kernel live here: bt_mma_kernel (64-column tiles, separate A / B rings; the one measured on
+// B200 in round 1: correct, 302 us alone on the bench graph) and bt_mma_wide_kernel<RB, W> (unified stage barriers, a
+// warp-converged issuer, 128-column tiles or 256-row items that share a B' stage; compiled, emulated and protocol-
+// simulated on the CPU, selected by chunk_cols / row_blocks / GCNB_BT_* -- see the comment above it).
 // Summation order is fixed by the plan => bit-reproducible run to run.  Relative to the CSR product the result differs
 // by the rounding of s_i * s_j against 1/sqrtf(deg_i * deg_j) and by the summation order (~1e-6 relative; parity bar 1e-5).
 //
