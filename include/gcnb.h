@@ -144,6 +144,10 @@ GCNB_API int gcnb_bittile_spmm16_f32(gcnb_bittile_plan *plan, const float *d_B, 
  * 16 contiguous columns (ldb == ldc == 16) through the bit-tile plan (built from the same CSR and the same values);
  * every other call is unaffected.  The bit-tile plan is borrowed (destroy it after the spmm plan); bt = NULL detaches. */
 GCNB_API int gcnb_spmm_plan_attach_bittile(gcnb_spmm_plan *plan, gcnb_bittile_plan *bt, const float *d_values);
+/* the same product on column slabs of wider row-major matrices (row strides ldb / ldc floats, 16 <= dim <= ldb, ldc): runs
+ * 16 columns at a time (pack + MMA kernel + remainder + add per slab), the last slab shifted left to end at dim */
+GCNB_API int gcnb_bittile_spmm_ld_f32(gcnb_bittile_plan *plan, const float *d_B, int64_t ldb, float *d_C, int64_t ldc, int dim,
+                                      gcnb_stream_t stream);
 /* debugging aid: bit mask of the steps gcnb_bittile_spmm16_f32 runs (1 pack, 2 MMA kernel, 4 remainder, 8 final add; default 15) */
 GCNB_API int gcnb_bittile_debug_parts(gcnb_bittile_plan *plan, int parts);
 /* debugging aid: runs the packing kernel alone and copies the bf16 operand image of B (6144 bytes per 64 rows) to h_out */

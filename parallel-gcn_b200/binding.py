@@ -64,6 +64,7 @@ _sig("gcnb_bittile_plan_create", I32, [P, P, P, I64, I64, P, P, I32, I32, I32, P
 _sig("gcnb_bittile_plan_destroy", I32, [P])
 _sig("gcnb_bittile_plan_info", I32, [P, P])
 _sig("gcnb_bittile_spmm16_f32", I32, [P, P, P, P])
+_sig("gcnb_bittile_spmm_ld_f32", I32, [P, P, I64, P, I64, I32, P])
 _sig("gcnb_bittile_debug_pack", I32, [P, P, P, I64, P])
 _sig("gcnb_bittile_debug_parts", I32, [P, I32])
 _sig("gcnb_spmm_plan_attach_bittile", I32, [P, P, P])
@@ -331,6 +332,11 @@ class BitTilePlan:
 
     def spmm16(self, B, C_out):
         check(lib.gcnb_bittile_spmm16_f32(self.h, ptr(B), ptr(C_out), stream()))
+
+    def spmm_ld(self, B, ldb, C_out, ldc, dim, b_off=0, c_off=0):
+        """product on the column slab [off, off + dim) of wider row-major matrices, 16 columns at a time"""
+        check(lib.gcnb_bittile_spmm_ld_f32(self.h, C.c_void_p(B.data_ptr() + 4 * int(b_off)), int(ldb),
+                                           C.c_void_p(C_out.data_ptr() + 4 * int(c_off)), int(ldc), int(dim), stream()))
 
     def debug_parts(self, mask):
         check(lib.gcnb_bittile_debug_parts(self.h, int(mask)))

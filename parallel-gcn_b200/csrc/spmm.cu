@@ -507,9 +507,11 @@ int gcnb_spmm_ld_f32(gcnb_spmm_plan *p, const float *d_values, const uint32_t *d
   if (p->n_rows == 0) return 0;
   const int ldb = (int)ldb_, ldc = (int)ldc_;
   cudaStream_t stream = as_stream(stream_);
-  if (p->bittile && d_values == p->bittile_values && !d_perm && dim == 16 && ldb == 16 && ldc == 16 &&
-      (((uintptr_t)d_B | (uintptr_t)d_C) % 16 == 0))  // tensor-core bit tiles + remainder CSR, spmm_bittile.cu
-    return gcnb_bittile_spmm16_f32(p->bittile, d_B, d_C, stream_);
+  if (p->bittile && d_values == p->bittile_values && !d_perm) {  // tensor-core bit tiles + remainder CSR, spmm_bittile.cu
+    if (dim == 16 && ldb == 16 && ldc == 16 && (((uintptr_t)d_B | (uintptr_t)d_C) % 16 == 0))
+      return gcnb_bittile_spmm16_f32(p->bittile, d_B, d_C, stream_);
+    if (dim >= 64) return gcnb_bittile_spmm_ld_f32(p->bittile, d_B, ldb, d_C, ldc, dim, stream_);  // 16-column slabs
+  }
   if (p->staged) {  // window-staged fast path (static values, 16-column slabs), spmm_stage.cu
     int handled = 0;
     const int rc = gcnb_stage_try_spmm(p, d_values, d_perm, d_B, ldb, d_C, ldc, dim, stream, &handled);

@@ -459,6 +459,57 @@ __global__ void __launch_bounds__(256) bt_pack_kernel(const float *__restrict__ 
   }
 }
 
+// The same packing for a 16-column slab of a wider row-major matrix (row stride ldb floats)
+__global__ void __launch_bounds__(256) bt_pack_ld_kernel(const float *__restrict__ B, int64_t ldb,
+                                                         const float *__restrict__ col_scale, uint8_t *__restrict__ packed,
+                                                         int64_t n_cols, int64_t n_groups) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t g = tid >> 4;
+  const int col = (int)(tid & 15);
+  if (g >= n_groups) return;
+  const int64_t j0 = g * 8;
+  uint32_t hi[4], mid[4], lo[4];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const int64_t j = j0 + i;
+    float x = 0.f;
+    if (j < n_cols) x = __ldg(col_scale + j) * __ldg(B + j * ldb + col);
+    const uint32_t xb = __float_as_uint(x);
+    const uint32_t hb = xb & 0xffff0000u;
+    const float r1 = x - __uint_as_float(hb);
+    const uint32_t mb = __float_as_uint(r1) & 0xffff0000u;
+    const float r2 = r1 - __uint_as_float(mb);
+    const uint32_t lb = __float_as_uint(r2) & 0xffff0000u;
+    if (i & 1) {
+      hi[i >> 1] |= hb;
+      mid[i >> 1] |= mb;
+      lo[i >> 1] |= lb;
+    } else {
+      hi[i >> 1] = hb >> 16;
+      mid[i >> 1] = mb >> 16;
+      lo[i >> 1] = lb >> 16;
+    }
+  }
+  const int64_t c = j0 >> 6;
+  const int kl = (int)(j0 & 63);
+  uint8_t *base = packed + c * kBtChunkBytes + (kl >> 4) * kBtKStepBytes + ((kl >> 3) & 1) * 768;
+#pragma unroll
+  for (int p = 0; p < 3; p++) {
+    const int n = p * 16 + col;
+    uint4 v;
+    const uint32_t *src = p == 0 ? hi : (p == 1 ? mid : lo);
+    v.x = src[0]; v.y = src[1]; v.z = src[2]; v.w = src[3];
+    *reinterpret_cast<uint4 *>(base + (n >> 3) * 128 + (n & 7) * 16) = v;
+  }
+}
+
+// C[:, 0..16) (row stride ldc) = P + R
+__global__ void __launch_bounds__(256) bt_add_ld_kernel(const float *__restrict__ P, const float *__restrict__ R,
+                                                        float *__restrict__ C, int64_t ldc, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    C[(i >> 4) * ldc + (i & 15)] = P[i] + R[i];
+}
+
 __device__ __forceinline__ uint64_t bt_ld_bits(const uint64_t *p) {
   uint64_t v;
   asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p));
@@ -1067,17 +1118,20 @@ int gcnb_bittile_debug_pack(gcnb_bittile_plan *p, const float *d_B, void *h_out,
   return 0;
 }
 
-int gcnb_bittile_spmm16_f32(gcnb_bittile_plan *p, const float *d_B, float *d_C, gcnb_stream_t stream_) {
-  if (!p || !d_B || !d_C) return GCNB_E_BADARG;
-  if (p->n_rows == 0) return 0;
-  cudaStream_t stream = as_stream(stream_);
+// one 16-column slab: B row stride ldb, C row stride ldc (16 / 16: the contiguous kernels measured in round 1)
+static int bt_slab16(gcnb_bittile_plan *p, const float *d_B, int64_t ldb, float *d_C, int64_t ldc, cudaStream_t stream) {
   const int parts = p->parts;  // 15 unless a probe switched steps off (gcnb_bittile_debug_parts)
   const bool tiles = p->n_tiles > 0;
+  const bool contiguous = ldb == 16 && ldc == 16 && (((uintptr_t)d_B | (uintptr_t)d_C) % 16 == 0);
   if (tiles && (parts & 1)) {
     const int64_t n_groups = p->n_chunks * (kBtChunk / 8);
     const int64_t threads = n_groups * 16;
-    bt_pack_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(d_B, p->d_col_scale, p->d_packed, p->n_cols,
-                                                                         n_groups);
+    if (ldb == 16)
+      bt_pack_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(d_B, p->d_col_scale, p->d_packed, p->n_cols,
+                                                                           n_groups);
+    else
+      bt_pack_ld_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(d_B, ldb, p->d_col_scale, p->d_packed,
+                                                                              p->n_cols, n_groups);
     GCNB_LAUNCH_CHECK();
   }
   // The MMA kernel goes first (one CTA per SM, half the register file), then the remainder CSR on the second stream
@@ -1097,18 +1151,44 @@ int gcnb_bittile_spmm16_f32(gcnb_bittile_plan *p, const float *d_B, float *d_C, 
   }
   GCNB_CHECK(cudaStreamWaitEvent(p->aux, p->ev_fork, 0));
   if (parts & 4) {
-    const int rc = gcnb::spmm_generic_launch(p->rem, p->d_r_values, nullptr, d_B, 16, p->d_R, 16, 16, p->aux);
+    const int rc = gcnb::spmm_generic_launch(p->rem, p->d_r_values, nullptr, d_B, (int)ldb, p->d_R, 16, 16, p->aux);
     if (rc) return rc;
   }
   GCNB_CHECK(cudaEventRecord(p->ev_join, p->aux));
   GCNB_CHECK(cudaStreamWaitEvent(stream, p->ev_join, 0));
   if (parts & 8) {
-    const int64_t n4 = p->n_rows * 4;
-    const int blocks = (int)std::min<int64_t>((n4 + 255) / 256, (int64_t)device_info().sm_count * 8);
-    bt_add_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const float4 *>(p->d_P),
-                                             reinterpret_cast<const float4 *>(p->d_R), reinterpret_cast<float4 *>(d_C), n4);
+    if (contiguous) {
+      const int64_t n4 = p->n_rows * 4;
+      const int blocks = (int)std::min<int64_t>((n4 + 255) / 256, (int64_t)device_info().sm_count * 8);
+      bt_add_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const float4 *>(p->d_P),
+                                               reinterpret_cast<const float4 *>(p->d_R), reinterpret_cast<float4 *>(d_C), n4);
+    } else {
+      const int64_t n = p->n_rows * 16;
+      const int blocks = (int)std::min<int64_t>((n + 255) / 256, (int64_t)device_info().sm_count * 16);
+      bt_add_ld_kernel<<<blocks, 256, 0, stream>>>(p->d_P, p->d_R, d_C, ldc, n);
+    }
   }
   GCNB_LAUNCH_CHECK();
+  return 0;
+}
+
+int gcnb_bittile_spmm16_f32(gcnb_bittile_plan *p, const float *d_B, float *d_C, gcnb_stream_t stream_) {
+  if (!p || !d_B || !d_C) return GCNB_E_BADARG;
+  if (p->n_rows == 0) return 0;
+  return bt_slab16(p, d_B, 16, d_C, 16, as_stream(stream_));
+}
+
+// C[:, 0..dim) = A * B[:, 0..dim) on column slabs of wider row-major matrices (row strides ldb / ldc floats, dim >= 16):
+// 16 columns at a time, the last slab shifted left so that it ends at dim (its overlap is computed twice, identically)
+int gcnb_bittile_spmm_ld_f32(gcnb_bittile_plan *p, const float *d_B, int64_t ldb, float *d_C, int64_t ldc, int dim,
+                             gcnb_stream_t stream_) {
+  if (!p || !d_B || !d_C || dim < 16 || ldb < dim || ldc < dim || ldb > (1 << 28) || ldc > (1 << 28)) return GCNB_E_BADARG;
+  if (p->n_rows == 0) return 0;
+  for (int c0 = 0; c0 < dim; c0 += 16) {
+    const int c = std::min(c0, dim - 16);
+    const int rc = bt_slab16(p, d_B + c, ldb, d_C + c, ldc, as_stream(stream_));
+    if (rc) return rc;
+  }
   return 0;
 }
 

@@ -144,6 +144,27 @@ def test_engine_training_with_bit_tiles_matches_default_path(gcnb, dev):
         assert_close(b, a, rtol=1e-4, atol=1e-6, what="weights after 4 epochs")
 
 
+@pytest.mark.skipif(os.environ.get("GCNB_TEST_BITTILE_WIDE") != "1", reason="opt-in: strided slabs not yet run on a GPU")
+def test_wide_operands_run_as_16_column_slabs(O, gcnb, dev):
+    import torch
+    rng = np.random.default_rng(9)
+    n, dim, ld = 3000, 70, 96  # 70 = 4 slabs + a shifted last one; operands are column slabs of wider matrices
+    indptr, indices, values = gcn_graph(rng, n, 6, 40, 3)
+    x = rng.standard_normal((n, ld)).astype(f32)
+    want = np.empty((n, dim), f32)
+    xs = np.ascontiguousarray(x[:, 8:8 + dim])
+    O.lib.orc_spmm(n, dim, O._p(indptr), O._p(indices), O._p(values), O._p(xs), O._p(want))
+    bt = gcnb.BitTilePlan(indptr, indices, values, n, min_tile_nnz=64)
+    d_x = to_dev(x, dev)
+    out = torch.full((n, ld), float("nan"), device=dev)
+    bt.spmm_ld(d_x, ld, out, ld, dim, b_off=8, c_off=4)
+    torch.cuda.synchronize()
+    got = to_np(out)
+    assert_close(got[:, 4:4 + dim], want, what="bit-tile slabs")
+    assert np.isnan(got[:, :4]).all() and np.isnan(got[:, 4 + dim:]).all(), "columns outside the slab were written"
+    bt.close()
+
+
 # ---- background staging of the window-staged GraphSum (spmm_stage.cu, gcnb_spmm_plan_stage_async_*): opt-in until it has
 # ---- been run on a GPU (GCNB_TEST_ASYNC_STAGE=1)
 @pytest.mark.skipif(os.environ.get("GCNB_TEST_ASYNC_STAGE") != "1", reason="opt-in: background staging not yet run on a GPU")
