@@ -717,7 +717,7 @@ struct BtWide {
 // operands in the stage) against the SAME B' stage, which halves the B' traffic through L2 and lets the plan select
 // tiles by the density of 256 x 64 cells.  One accumulator per half and set (chains of ~300 MMAs; measured: no drift).
 template <int RB, int W>
-__global__ void __maxnreg__(96) bt_mma_wide_kernel(BtArgs a) {
+__global__ void __maxnreg__(72) bt_mma_wide_kernel(BtArgs a) {  // no spills at 72; leaves half the register file to the remainder kernel
   using K = BtWide<RB, W>;
   extern __shared__ __align__(128) uint8_t bt_smem[];
   uint8_t *smem_b = bt_smem;
