@@ -181,6 +181,8 @@ int bittile_build_host(const uint32_t *indptr, const uint32_t *indices, const fl
   bt_run_threads(T, [&](int) {
     std::vector<uint32_t> cnt((size_t)n_chunks, 0u), touched;
     std::vector<int32_t> sel((size_t)n_chunks, -1);
+    std::vector<uint32_t> sr_idx;  // remainder of the current block: thread-local scratch, copied out at its exact size
+    std::vector<float> sr_val;     // (growing one vector per block by push_back made 16 threads fight over the allocator)
     for (;;) {
       const int64_t b = next.fetch_add(1);
       if (b >= H.n_blk) break;
@@ -199,6 +201,12 @@ int bittile_build_host(const uint32_t *indptr, const uint32_t *indices, const fl
         }
       }
       o.bits.assign(o.chunks.size() * (size_t)BH * wpr, 0ull);
+      const size_t block_entries = indptr[r1] - indptr[r0];
+      if (sr_idx.size() < block_entries) {
+        sr_idx.resize(block_entries);
+        sr_val.resize(block_entries);
+      }
+      size_t n_rem = 0;
       for (int64_t i = r0; i < r1; i++) {
         const int rl = (int)(i - r0);
         uint32_t rc = 0;
@@ -223,13 +231,16 @@ int bittile_build_host(const uint32_t *indptr, const uint32_t *indices, const fl
           if (in_tile) {
             o.tile_nnz++;
           } else {
-            o.ridx.push_back(j);
-            o.rval.push_back(v);
+            sr_idx[n_rem] = j;
+            sr_val[n_rem] = v;
+            n_rem++;
             rc++;
           }
         }
         o.rcount[rl] = rc;
       }
+      o.ridx.assign(sr_idx.begin(), sr_idx.begin() + (ptrdiff_t)n_rem);
+      o.rval.assign(sr_val.begin(), sr_val.begin() + (ptrdiff_t)n_rem);
       for (uint32_t c : touched) {
         cnt[c] = 0;
         sel[c] = -1;
