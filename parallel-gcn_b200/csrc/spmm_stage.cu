@@ -1024,8 +1024,10 @@ int gcnb_spmm_plan_stage_async_begin(gcnb_spmm_plan *p, const float *d_values, i
   if (!p || !d_values || !out) return GCNB_E_BADARG;
   *out = nullptr;
   if (dim != 16 || p->n_rows == 0 || p->nnz == 0 || p->staged) return 0;  // nothing to do: no job
+  int device = 0;
+  GCNB_CHECK(cudaGetDevice(&device));
   auto *job = new gcnb_stage_job();
-  GCNB_CHECK(cudaGetDevice(&job->device));
+  job->device = device;
   const gcnb_spmm_plan *cp = p;
   job->th = std::thread([job, cp, d_values, dim] {
     cudaStream_t st = nullptr;
