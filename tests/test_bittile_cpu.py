@@ -405,3 +405,28 @@ def test_barrier_protocol_simulation(name, unified, stages_a, stages_b, n_acc):
     for items in ([1], [3], [4, 1, 1], [9, 2, 7, 1, 12], [37, 5, 1, 1, 2, 40], list(rng.integers(1, 30, 12))):
         for _ in range(3):
             _simulate_cta([int(x) for x in items], unified, stages_a, stages_b, n_acc, rng)
+
+
+@pytest.mark.parametrize("chunk_cols,row_blocks", SHAPES)
+def test_row_block_of_a_partitioned_graph(gcnb, chunk_cols, row_blocks):
+    """a rank's row block of a row-partitioned GraphSum: rectangular (rows [r0, r1) x all columns), explicit global scales"""
+    rng = np.random.default_rng(13)
+    n, r0, r1 = 1500, 517, 1203
+    indptr, indices, values = gcn_graph(rng, n, 5, 24, 3)
+    s = (1.0 / np.sqrt(np.diff(indptr.astype(np.int64)).astype(np.float32))).astype(np.float32)
+    ip = (indptr[r0:r1 + 1] - indptr[r0]).astype(np.uint32)
+    ix, v = indices[indptr[r0]:indptr[r1]], values[indptr[r0]:indptr[r1]]
+    B = rng.standard_normal((n, 16)).astype(np.float32)
+    plan = gcnb.bittile_host_build(ip, ix, v, n, s[r0:r1], s, min_tile_nnz=48 * (2 if (chunk_cols == 128 or row_blocks == 2) else 1),
+                                   n_cta=4, chunk_cols=chunk_cols, row_blocks=row_blocks)
+    assert plan["n_rows"] == r1 - r0 and plan["n_cols"] == n and plan["n_tiles"] > 0
+    out, cells, rrows = emulate(plan, B)
+    rows = np.repeat(np.arange(r1 - r0), np.diff(ip.astype(np.int64)))
+    ref = np.zeros((r1 - r0, 16), np.float64)
+    np.add.at(ref, rows, v[:, None].astype(np.float64) * B[ix])
+    assert_close(out, ref, rtol=2e-6, atol=1e-7 * np.abs(ref).max(), what="row block")
+    got = np.sort(np.concatenate([cells[:, 0] * (1 << 32) + cells[:, 1], rrows.astype(np.int64) * (1 << 32) + plan["r_indices"]]))
+    assert np.array_equal(got, np.sort(rows.astype(np.int64) * (1 << 32) + ix))
+    # without explicit scales a rectangular block has no diagonal to derive them from: everything stays in the remainder
+    none = gcnb.bittile_host_build(ip, ix, v, n, chunk_cols=chunk_cols, row_blocks=row_blocks)
+    assert none["tile_nnz"] == 0 and none["rem_nnz"] == len(ix)
