@@ -252,7 +252,7 @@ struct GCNEngineState {
         }
       CHECK_CUDA_ERROR(cudaEventRecord(gs_events[gs_used], stream));
     }
-    if (dist && overlap_gather && graph_staged && dim == 16) {
+    if (dist && overlap_gather && graph_staged && dim == 16 && !graph_bittile) {
       // the exchange runs on its own stream while the staged windows that lie inside this rank's own slab are already
       // being processed from `in`; everything that needs a peer's rows waits for ev_gather
       CHECK_CUDA_ERROR(cudaEventRecord(ev_cfork, stream));
@@ -482,6 +482,52 @@ void GCN::init(bool quiet, const natural *h_graph_indptr, const natural *h_graph
     const char *e = getenv("GCNB_BITTILE");
     bool d16 = false;
     for (const GCNLayer &ly : st->layers) d16 |= (ly.reorder ? ly.in_dim : ly.out_dim) == 16;
+    if (e && atoi(e) != 0 && st->dist && d16 && N > 0) {
+      // Row-partitioned model: this rank's row block x all global columns.  The scales are the square roots of the
+      // diagonal values (the diagonal of local row i is global column row0 + i); every rank's block of scales is
+      // all-gathered so that all ranks use the same column scales.  Whether the path is used is agreed collectively
+      // (the exchange in graphsum() differs between the two paths).  Synchronous: every step below is collective.
+      const size_t nnz = dev_data.dev_graph_index.indices_size;
+      std::vector<natural> hp((size_t)N + 1), hi(nnz);
+      std::vector<real> hv(nnz);
+      CHECK_CUDA_ERROR(cudaStreamSynchronize(st->stream));
+      CHECK_CUDA_ERROR(cudaMemcpy(hp.data(), dev_data.dev_graph_index.dev_indptr.get(), hp.size() * sizeof(natural), cudaMemcpyDeviceToHost));
+      CHECK_CUDA_ERROR(cudaMemcpy(hi.data(), dev_data.dev_graph_index.dev_indices.get(), nnz * sizeof(natural), cudaMemcpyDeviceToHost));
+      CHECK_CUDA_ERROR(cudaMemcpy(hv.data(), dev_data.dev_graph_value.get(), nnz * sizeof(real), cudaMemcpyDeviceToHost));
+      const size_t world = (size_t)gcnb_comm_world(st->comm);
+      std::vector<real> s_loc(st->block, 0.f), s_all(world * st->block, 0.f);
+      for (size_t i = 0; i < N; i++)
+        for (natural k = hp[i]; k < hp[i + 1]; k++)
+          if (hi[k] == (natural)(st->row0 + i)) {
+            if (hv[k] > 0.f) s_loc[i] = sqrtf(hv[k]);
+            break;
+          }
+      dev_shared_ptr<real> d_loc(st->block), d_all(world * st->block);
+      CHECK_CUDA_ERROR(cudaMemcpy(d_loc.get(), s_loc.data(), st->block * sizeof(real), cudaMemcpyHostToDevice));
+      GCNB_CALL(gcnb_comm_all_gather_f32(st->comm, d_loc.get(), d_all.get(), (int64_t)st->block, st->stream));
+      CHECK_CUDA_ERROR(cudaStreamSynchronize(st->stream));
+      CHECK_CUDA_ERROR(cudaMemcpy(s_all.data(), d_all.get(), s_all.size() * sizeof(real), cudaMemcpyDeviceToHost));
+      for (real &x : s_all)
+        if (!(x > 0.f)) x = std::nanf("");  // no usable diagonal: entries of that row / column stay in the remainder
+      std::vector<real> s_rows(s_all.begin() + (ptrdiff_t)st->row0, s_all.begin() + (ptrdiff_t)(st->row0 + N));
+      gcnb_bittile_plan *bt = nullptr;
+      GCNB_CALL(gcnb_bittile_plan_create(hp.data(), hi.data(), hv.data(), (int64_t)N, (int64_t)st->n_global, s_rows.data(),
+                                         s_all.data(), 0, 0, 0, st->stream, &bt));
+      int64_t binfo[8];
+      GCNB_CALL(gcnb_bittile_plan_info(bt, binfo));
+      natural ok_flag = (binfo[0] > 0 && binfo[1] * 4 >= (int64_t)nnz) ? 1u : 0u;
+      dev_shared_ptr<natural> d_flag(1);
+      CHECK_CUDA_ERROR(cudaMemcpy(d_flag.get(), &ok_flag, sizeof(natural), cudaMemcpyHostToDevice));
+      GCNB_CALL(gcnb_comm_all_reduce_sum(st->comm, d_flag.get(), 1, 1, st->stream));
+      CHECK_CUDA_ERROR(cudaStreamSynchronize(st->stream));
+      CHECK_CUDA_ERROR(cudaMemcpy(&ok_flag, d_flag.get(), sizeof(natural), cudaMemcpyDeviceToHost));
+      if (ok_flag == (natural)world) {  // every rank has dense blocks worth the path
+        st->graph_bittile = bt;
+        GCNB_CALL(gcnb_spmm_plan_attach_bittile(st->graph_plan, bt, dev_data.dev_graph_value.get()));
+      } else {
+        gcnb_bittile_plan_destroy(bt);
+      }
+    }
     if (e && atoi(e) != 0 && !st->dist && d16 && N > 0) {
       const size_t nnz = dev_data.dev_graph_index.indices_size;
       const natural *d_ip = dev_data.dev_graph_index.dev_indptr.get(), *d_ix = dev_data.dev_graph_index.dev_indices.get();

@@ -38,6 +38,11 @@ step 300 r2_bench_bittile_rb2.log env GCNB_BITTILE=1 GCNB_BT_RB=2 python bench.p
 step 300 r2_ref_gpu_cora.log python scripts/bench_ref_gpu.py --dataset cora --epochs 100 --reps 5
 step 300 r2_ref_gpu_citeseer.log python scripts/bench_ref_gpu.py --dataset citeseer --epochs 100 --reps 5
 step 900 r2_ref_gpu_reddit.log python scripts/bench_ref_gpu.py --dataset reddit_shape --epochs 20 --reps 1 --timeout 600
+# 5c. (needs `gpurun --gpus 2`) bit tiles in the row-partitioned engine: parity of 2 ranks against the oracle / single rank
+#   GCNB_BITTILE=1 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+#       scripts/dist_check_native.py
+#   GCNB_BITTILE=1 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 \
+#       bench.py --gpus 2 --no-cpu-baseline
 # 6. one full-set ncu capture of the MMA kernel of the best shape (edit the env / flags), after the runs above exited 0:
 #   ncu --set full --clock-control none --import-source on -k regex:bt_mma -c 1 -o gpurun_out/r2_bt_mma \
 #       python scripts/probe_bittile.py --stage graph --scale 1 --iters 1 --staged 0 --rb 2
