@@ -278,6 +278,20 @@ GCNB_API int gcnb_dense_feat_tn_f32(const float *d_X, const uint32_t *d_bits, fl
                                     float *d_dW, int64_t n, int f, int p, void *d_ws, int64_t ws_bytes,
                                     gcnb_stream_t stream);
 
+/* Exact-split tcgen05 GEMM for a WIDE first layer (hidden 600, parameters/parameters_reddit.txt): out[n x p] = X[n x f] * W
+ * with X and W each carried as three bf16 pieces and the six piece products of weight >= 2^-24 accumulated in fp32 in TMEM
+ * (parallel-gcn_b200/csrc/dense_tc.cu).  X is packed once per dataset into the operand image the MMA reads
+ * (gcnb_dense_tc_x_bytes / gcnb_dense_tc_pack_x); W is packed per call into d_ws (gcnb_dense_tc_w_bytes).  No dropout on X
+ * (the wide configuration has none; evaluation never has).  Status: written in round 1, not yet run on a GPU; nothing in
+ * the engine calls it yet. */
+GCNB_API int gcnb_dense_tc_supported(int f, int p);
+GCNB_API int64_t gcnb_dense_tc_x_bytes(int64_t n, int f);
+GCNB_API int64_t gcnb_dense_tc_w_bytes(int f, int p);
+GCNB_API int gcnb_dense_tc_pack_x(const float *d_X, void *d_img, int64_t n, int f, gcnb_stream_t stream);
+GCNB_API int gcnb_dense_tc_fwd_f32(const void *d_x_img, const float *d_W, float *d_out, int64_t n, int f, int p, void *d_ws,
+                                   int64_t ws_bytes, gcnb_stream_t stream);
+GCNB_API int gcnb_dense_tc_debug_pack_w(const float *d_W, void *d_ws, int f, int p, gcnb_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------------
  * CrossEntropyLoss::forward (src/module.cu:484-541) + GCN::get_accuracy (src/gcn.cu:264-289) in one pass.
  * In-place logits -= rowmax for rows with truth >= 0 (API-visible side effect kept); if training:

@@ -85,6 +85,11 @@ _sig("gcnb_dropout_maskbits", I32, [P, I64, I32, F32, P, P])
 _sig("gcnb_dense_feat_fwd_f32", I32, [P, P, F32, P, P, I64, I32, I32, P])
 _sig("gcnb_dense_feat_tn_workspace", I64, [I64, I32, I32])
 _sig("gcnb_dense_feat_tn_f32", I32, [P, P, F32, P, P, I64, I32, I32, P, I64, P])
+_sig("gcnb_dense_tc_supported", I32, [I32, I32])
+_sig("gcnb_dense_tc_x_bytes", I64, [I64, I32])
+_sig("gcnb_dense_tc_w_bytes", I64, [I32, I32])
+_sig("gcnb_dense_tc_pack_x", I32, [P, P, I64, I32, P])
+_sig("gcnb_dense_tc_fwd_f32", I32, [P, P, P, I64, I32, I32, P, I64, P])
 _sig("gcnb_glorot_f32", I32, [P, I64, U32, U32, P, P])
 _sig("gcnb_dropout_fwd_f32", I32, [P, P, P, I64, F32, P, P])
 _sig("gcnb_dropout_fwd_oop_f32", I32, [P, P, P, P, I64, F32, P, P])
@@ -434,6 +439,23 @@ def dense_feat_tn(X, bits, p_drop, dH, dW, n, f, p, ws=None):
         ws = torch.empty((need + 3) // 4, dtype=torch.float32, device=X.device)
     check(lib.gcnb_dense_feat_tn_f32(ptr(X), ptr(bits), p_drop, ptr(dH), ptr(dW), n, f, p, ptr(ws),
                                      ws.numel() * ws.element_size(), stream()))
+
+
+def dense_tc_pack_x(X, n, f):
+    """packed bf16 x 3 operand image of X for gcnb_dense_tc_fwd_f32 (once per dataset)"""
+    import torch
+    img = torch.empty(lib.gcnb_dense_tc_x_bytes(n, f), dtype=torch.uint8, device=X.device)
+    check(lib.gcnb_dense_tc_pack_x(ptr(X), ptr(img), n, f, stream()))
+    return img
+
+
+def dense_tc_fwd(x_img, W, out, n, f, p, ws=None):
+    import torch
+    need = lib.gcnb_dense_tc_w_bytes(f, p)
+    if ws is None:
+        ws = torch.empty(need, dtype=torch.uint8, device=W.device)
+    check(lib.gcnb_dense_tc_fwd_f32(ptr(x_img), ptr(W), ptr(out), n, f, p, ptr(ws), ws.numel(), stream()))
+    return out
 
 
 def glorot(w, rows, cols, rng):

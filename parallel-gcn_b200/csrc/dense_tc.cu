@@ -1,0 +1,370 @@
+// dense_tc.cu -- exact-split tcgen05 GEMM for the wide first layer:  out[n x p] = X[n x f] * W[f x p]  (hidden 600 of
+// parameters/parameters_reddit.txt; SparseMatmul::forward on an all-columns feature matrix, src/module.cu:108-132).
+//
+// STATUS (end of round 1): compiled, packing layouts emulated on the CPU (tests/test_dense_tc_cpu.py), NOT yet run on a
+// GPU; nothing calls it by default (opt-in GPU test GCNB_TEST_DENSE_TC=1).  It re-uses exactly the tcgen05 pieces the
+// bit-tile GraphSum validated on B200 (spmm_bittile.cu): no-swizzle K-major shared-memory descriptors fed by
+// cp.async.bulk of pre-packed operand images, fp32 accumulators in TMEM, tcgen05.commit / mbarrier stage recycling.
+//
+// Why: at hidden 600 the product is compute bound (168 GFLOP per call) and the fp32 SIMT kernel runs at ~18 TFLOP/s =
+// 15 ms.  Exactness on bf16 tensor cores: x and w are split into three bf16 pieces each (8 + 8 + 8
+// significand bits, exact), a product of two pieces is exact in fp32, and of the nine piece products the six with
+// (piece_x + piece_w) <= 2 are kept -- hi*hi, hi*mid, mid*hi, hi*lo, lo*hi, mid*mid -- the dropped ones are below
+// 2^-24 of the product.  Six bf16 MMAs per k-step instead of one: ~1 PFLOP-equivalent, ~0.5 ms at the B200's bf16 rate.
+//
+// X is a constant of the training run: it is packed ONCE (gcnb_dense_tc_pack_x) into the operand image the MMA reads
+// from shared memory -- per (block of 128 rows, k-step of 16 features, piece) a 4 KB K-major tile -- so the kernel has no
+// operand transformation at all: one thread streams A and B tiles with bulk copies, one thread issues MMAs, four warps
+// drain the accumulators.  W (f x p) is packed per call (gcnb_dense_tc_pack_w, 2 MB).  The p columns are cut into parts
+// of <= 256 columns (600 -> 3 x 208) so that two accumulator sets fit in TMEM (the epilogue of one item overlaps the
+// MMAs of the next); the parts of a row block are consecutive items of one CTA, so X's tiles are re-read from L2.
+// Dropout on X is not supported here (the wide configuration has input dropout 0; evaluation never has one).
+#include <algorithm>
+#include <cstdint>
+
+#include "bulk.cuh"
+#include "common.cuh"
+
+using namespace gcnb;
+
+namespace gcnb {
+
+constexpr int kTcRows = 128;
+constexpr int kTcATile = kTcRows * 16 * 2;  // 4096 bytes: 128 x 16 bf16
+constexpr int kTcStages = 4;
+constexpr int kTcThreads = 6 * 32;          // warps 0-3 epilogue, 4 producer, 5 MMA issuer
+
+__device__ __forceinline__ void tcg_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcg_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcg_mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tcg_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ bool tcg_elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+// D[tmem] (+)= A[smem descriptor] * B[smem descriptor]
+__device__ __forceinline__ void tcg_mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tcg_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
+      "[%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tcg_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, no swizzle: element (row, k) of an operand of R rows x 16 at (k / 8) * lbo + (row / 8) * 128 + (row % 8) * 16 +
+// (k % 8) * 2; lbo = R * 16 bytes (the core matrices of one k-half are contiguous), stride between 8-row groups 128
+__device__ __forceinline__ uint64_t tcg_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) | (1ull << 46);
+}
+
+__device__ __forceinline__ void tcg_split3(float x, uint32_t &hi, uint32_t &mid, uint32_t &lo) {  // bf16 bit patterns
+  const uint32_t hb = __float_as_uint(x) & 0xffff0000u;
+  const float r1 = x - __uint_as_float(hb);
+  const uint32_t mb = __float_as_uint(r1) & 0xffff0000u;
+  const float r2 = r1 - __uint_as_float(mb);
+  hi = hb >> 16;
+  mid = mb >> 16;
+  lo = (__float_as_uint(r2) & 0xffff0000u) >> 16;
+}
+
+// A image: tile (row block b, k-step ks, piece pc) at ((b * KS + ks) * 3 + pc) * 4096; thread = (row, k-half): 8 features
+__global__ void __launch_bounds__(256) tc_pack_x_kernel(const float *__restrict__ X, uint8_t *__restrict__ img, int64_t n, int f,
+                                                        int KS, int64_t n_blk) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // over n_blk * 128 rows x KS k-steps x 2 halves
+  const int64_t total = n_blk * kTcRows * (int64_t)KS * 2;
+  if (tid >= total) return;
+  const int half = (int)(tid & 1);
+  const int64_t t2 = tid >> 1;
+  const int r = (int)(t2 % kTcRows);
+  const int64_t t3 = t2 / kTcRows;
+  const int ks = (int)(t3 % KS);
+  const int64_t b = t3 / KS;
+  const int64_t row = b * kTcRows + r;
+  uint32_t h[4] = {0, 0, 0, 0}, m[4] = {0, 0, 0, 0}, l[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const int k = ks * 16 + half * 8 + i;
+    const float x = (row < n && k < f) ? __ldg(X + row * f + k) : 0.f;
+    uint32_t a, c, d;
+    tcg_split3(x, a, c, d);
+    const int sh = (i & 1) * 16;
+    h[i >> 1] |= a << sh;
+    m[i >> 1] |= c << sh;
+    l[i >> 1] |= d << sh;
+  }
+  uint8_t *tile = img + ((b * KS + ks) * 3) * (int64_t)kTcATile + half * 2048 + (r >> 3) * 128 + (r & 7) * 16;
+  *reinterpret_cast<uint4 *>(tile) = make_uint4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<uint4 *>(tile + kTcATile) = make_uint4(m[0], m[1], m[2], m[3]);
+  *reinterpret_cast<uint4 *>(tile + 2 * kTcATile) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// B image: tile (part q, k-step ks, piece pc) at ((q * KS + ks) * 3 + pc) * pcols * 32; operand row = output column
+__global__ void __launch_bounds__(256) tc_pack_w_kernel(const float *__restrict__ W, uint8_t *__restrict__ img, int f, int p, int KS,
+                                                        int n_parts, int pcols) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // over parts x KS x pcols columns x 2 halves
+  const int64_t total = (int64_t)n_parts * KS * pcols * 2;
+  if (tid >= total) return;
+  const int half = (int)(tid & 1);
+  const int64_t t2 = tid >> 1;
+  const int c = (int)(t2 % pcols);
+  const int64_t t3 = t2 / pcols;
+  const int ks = (int)(t3 % KS);
+  const int q = (int)(t3 / KS);
+  const int col = q * pcols + c;
+  uint32_t h[4] = {0, 0, 0, 0}, m[4] = {0, 0, 0, 0}, l[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const int k = ks * 16 + half * 8 + i;
+    const float x = (col < p && k < f) ? __ldg(W + (int64_t)k * p + col) : 0.f;
+    uint32_t a, b2, d;
+    tcg_split3(x, a, b2, d);
+    const int sh = (i & 1) * 16;
+    h[i >> 1] |= a << sh;
+    m[i >> 1] |= b2 << sh;
+    l[i >> 1] |= d << sh;
+  }
+  const int64_t piece_bytes = (int64_t)pcols * 32;
+  uint8_t *tile = img + (((int64_t)q * KS + ks) * 3) * piece_bytes + (int64_t)half * (pcols * 16) + (c >> 3) * 128 + (c & 7) * 16;
+  *reinterpret_cast<uint4 *>(tile) = make_uint4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<uint4 *>(tile + piece_bytes) = make_uint4(m[0], m[1], m[2], m[3]);
+  *reinterpret_cast<uint4 *>(tile + 2 * piece_bytes) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+struct TcArgs {
+  const uint8_t *a_img, *b_img;
+  float *out;
+  int64_t n, n_blk;
+  int p, KS, n_parts, pcols;
+};
+
+// persistent: CTA c takes row blocks c, c + grid, ...; the n_parts column parts of a block are consecutive items
+__global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(TcArgs a) {
+  extern __shared__ __align__(128) uint8_t tc_smem[];
+  const uint32_t b_stage_bytes = 3u * (uint32_t)a.pcols * 32u;
+  const uint32_t stage_bytes = 3u * kTcATile + b_stage_bytes;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(tc_smem + (size_t)kTcStages * stage_bytes);
+  uint64_t *full = bars, *free_ = bars + kTcStages, *acc_full = free_ + kTcStages, *acc_empty = acc_full + 2;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kTcStages; i++) {
+      mbar_init(&full[i], 1);
+      mbar_init(&free_[i], 1);
+    }
+    for (int i = 0; i < 2; i++) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 5) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcg_fence_before();
+  __syncthreads();
+  tcg_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t *>(tmem_slot);
+  // items of this CTA: (block, part) for block = blockIdx.x, blockIdx.x + gridDim.x, ...; item index k counts them
+  const int64_t my_blocks = a.n_blk > (int64_t)blockIdx.x ? (a.n_blk - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int64_t n_items = my_blocks * a.n_parts;
+
+  if (warp < 4) {
+    // ---- epilogue: thread = row
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    for (int64_t k = 0; k < n_items; k++) {
+      const int64_t blk = blockIdx.x + (k / a.n_parts) * gridDim.x;
+      const int q = (int)(k % a.n_parts);
+      const uint32_t set = (uint32_t)(k & 1), use = (uint32_t)(k >> 1);
+      const int64_t row = blk * kTcRows + warp * 32 + lane;
+      mbar_wait(&acc_full[set], use & 1);
+      tcg_fence_after();
+      const uint32_t acc0 = tmem + lane_base + set * 256;
+      for (int c0 = 0; c0 < a.pcols; c0 += 16) {
+        float v[16];
+        tcg_ld16(acc0 + c0, v);
+        tcg_wait_ld();
+        const int col0 = q * a.pcols + c0;
+        if (row < a.n) {
+          float *dst = a.out + row * a.p + col0;
+#pragma unroll
+          for (int i = 0; i < 16; i++)
+            if (col0 + i < a.p) dst[i] = v[i];
+        }
+      }
+      tcg_fence_before();
+      __syncwarp();
+      if (lane == 0) tcg_mbar_arrive(&acc_empty[set]);
+    }
+  } else if (warp == 4) {
+    // ---- producer: one A stage (3 x 4 KB) + one B stage (3 x pcols x 32 bytes) per k-step
+    if (lane == 0) {
+      uint64_t t = 0;
+      for (int64_t k = 0; k < n_items; k++) {
+        const int64_t blk = blockIdx.x + (k / a.n_parts) * gridDim.x;
+        const int q = (int)(k % a.n_parts);
+        for (int ks = 0; ks < a.KS; ks++, t++) {
+          const uint32_t s = (uint32_t)(t % kTcStages), use = (uint32_t)(t / kTcStages);
+          if (use > 0) mbar_wait(&free_[s], (use - 1) & 1);
+          uint8_t *stage = tc_smem + (size_t)s * stage_bytes;
+          mbar_expect_tx(&full[s], stage_bytes);
+          bulk_g2s(stage, a.a_img + ((blk * a.KS + ks) * 3) * (int64_t)kTcATile, 3 * kTcATile, &full[s]);
+          bulk_g2s(stage + 3 * kTcATile, a.b_img + (((int64_t)q * a.KS + ks) * 3) * (int64_t)(a.pcols * 32), b_stage_bytes,
+                   &full[s]);
+        }
+      }
+    }
+  } else {
+    // ---- MMA issuer (warp converged, one elected lane issues): six piece products per k-step
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.pcols >> 3) << 17) | ((uint32_t)(kTcRows >> 4) << 24);
+    uint64_t t = 0;
+    for (int64_t k = 0; k < n_items; k++) {
+      const uint32_t set = (uint32_t)(k & 1), use = (uint32_t)(k >> 1);
+      if (use > 0) mbar_wait(&acc_empty[set], (use - 1) & 1);
+      tcg_fence_after();
+      const uint32_t d = tmem + set * 256;
+      for (int ks = 0; ks < a.KS; ks++, t++) {
+        const uint32_t s = (uint32_t)(t % kTcStages), u = (uint32_t)(t / kTcStages);
+        mbar_wait(&full[s], u & 1);
+        tcg_fence_after();
+        if (tcg_elect_one()) {
+          const uint32_t sa = smem_u32(tc_smem + (size_t)s * stage_bytes);
+          const uint32_t sb = sa + 3 * kTcATile;
+          const uint32_t pb = (uint32_t)a.pcols * 32u;
+          const uint64_t a0 = tcg_desc(sa, 2048), a1 = tcg_desc(sa + kTcATile, 2048), a2 = tcg_desc(sa + 2 * kTcATile, 2048);
+          const uint64_t b0 = tcg_desc(sb, (uint32_t)a.pcols * 16u), b1 = tcg_desc(sb + pb, (uint32_t)a.pcols * 16u),
+                         b2 = tcg_desc(sb + 2 * pb, (uint32_t)a.pcols * 16u);
+          // smallest terms first inside the k-step: lo*hi, hi*lo, mid*mid, mid*hi, hi*mid, hi*hi
+          tcg_mma_ss(d, a2, b0, idesc, ks > 0 ? 1u : 0u);
+          tcg_mma_ss(d, a0, b2, idesc, 1u);
+          tcg_mma_ss(d, a1, b1, idesc, 1u);
+          tcg_mma_ss(d, a1, b0, idesc, 1u);
+          tcg_mma_ss(d, a0, b1, idesc, 1u);
+          tcg_mma_ss(d, a0, b0, idesc, 1u);
+          tcg_commit(&free_[s]);
+        }
+        __syncwarp();
+      }
+      if (tcg_elect_one()) tcg_commit(&acc_full[set]);
+      __syncwarp();
+    }
+  }
+  __syncwarp();
+  tcg_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
+}
+
+static void tc_shape(int f, int p, int *KS, int *n_parts, int *pcols) {
+  *KS = (f + 15) / 16;
+  const int p_pad = (p + 15) / 16 * 16;
+  *n_parts = (p_pad + 255) / 256;
+  *pcols = ((p_pad + *n_parts - 1) / *n_parts + 15) / 16 * 16;  // <= 256: two accumulator sets of 256 TMEM columns
+}
+
+}  // namespace gcnb
+
+extern "C" {
+
+int gcnb_dense_tc_supported(int f, int p) { return f >= 1 && p >= 16 && p <= 4096; }
+
+// bytes of the packed X image (n rows, f features) and of the per-call workspace for W (f x p)
+int64_t gcnb_dense_tc_x_bytes(int64_t n, int f) {
+  const int64_t n_blk = (n + kTcRows - 1) / kTcRows;
+  return n_blk * ((f + 15) / 16) * 3 * (int64_t)kTcATile;
+}
+int64_t gcnb_dense_tc_w_bytes(int f, int p) {
+  int KS, n_parts, pcols;
+  tc_shape(f, p, &KS, &n_parts, &pcols);
+  return (int64_t)n_parts * KS * 3 * pcols * 32;
+}
+
+int gcnb_dense_tc_pack_x(const float *d_X, void *d_img, int64_t n, int f, gcnb_stream_t stream_) {
+  if (!d_X || !d_img || n < 0 || f < 1) return GCNB_E_BADARG;
+  if (n == 0) return 0;
+  const int64_t n_blk = (n + kTcRows - 1) / kTcRows;
+  const int KS = (f + 15) / 16;
+  const int64_t total = n_blk * kTcRows * (int64_t)KS * 2;
+  tc_pack_x_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream_)>>>(d_X, (uint8_t *)d_img, n, f, KS, n_blk);
+  GCNB_LAUNCH_CHECK();
+  return 0;
+}
+
+// out[n x p] = X * W with X given as its packed image (gcnb_dense_tc_pack_x); d_ws: gcnb_dense_tc_w_bytes(f, p) bytes
+int gcnb_dense_tc_fwd_f32(const void *d_x_img, const float *d_W, float *d_out, int64_t n, int f, int p, void *d_ws,
+                          int64_t ws_bytes, gcnb_stream_t stream_) {
+  if (!d_x_img || !d_W || !d_out || !d_ws || n < 0 || !gcnb_dense_tc_supported(f, p)) return GCNB_E_BADARG;
+  if (ws_bytes < gcnb_dense_tc_w_bytes(f, p)) return GCNB_E_BADARG;
+  if (n == 0) return 0;
+  const DeviceInfo &di = device_info();
+  if (!di.ok) return (int)cudaErrorNoDevice;
+  if (di.cc_major != 10) return GCNB_E_UNSUPPORTED;
+  cudaStream_t stream = as_stream(stream_);
+  TcArgs a;
+  tc_shape(f, p, &a.KS, &a.n_parts, &a.pcols);
+  a.a_img = (const uint8_t *)d_x_img;
+  a.b_img = (const uint8_t *)d_ws;
+  a.out = d_out;
+  a.n = n;
+  a.n_blk = (n + kTcRows - 1) / kTcRows;
+  a.p = p;
+  const int64_t wt = (int64_t)a.n_parts * a.KS * a.pcols * 2;
+  tc_pack_w_kernel<<<(unsigned)((wt + 255) / 256), 256, 0, stream>>>(d_W, (uint8_t *)d_ws, f, p, a.KS, a.n_parts, a.pcols);
+  GCNB_LAUNCH_CHECK();
+  const size_t smem = (size_t)kTcStages * (3 * kTcATile + 3 * (size_t)a.pcols * 32) + (2 * kTcStages + 4) * 8 + 16;
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    GCNB_CHECK(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  const int grid = (int)std::min<int64_t>(a.n_blk, std::max(1, di.sm_count));
+  tc_gemm_kernel<<<grid, kTcThreads, smem, stream>>>(a);
+  GCNB_LAUNCH_CHECK();
+  return 0;
+}
+
+// debugging aid: copies of the packed images for the CPU-side layout check
+int gcnb_dense_tc_debug_pack_w(const float *d_W, void *d_ws, int f, int p, gcnb_stream_t stream_) {
+  if (!d_W || !d_ws || !gcnb_dense_tc_supported(f, p)) return GCNB_E_BADARG;
+  int KS, n_parts, pcols;
+  tc_shape(f, p, &KS, &n_parts, &pcols);
+  const int64_t wt = (int64_t)n_parts * KS * pcols * 2;
+  tc_pack_w_kernel<<<(unsigned)((wt + 255) / 256), 256, 0, as_stream(stream_)>>>(d_W, (uint8_t *)d_ws, f, p, KS, n_parts, pcols);
+  GCNB_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

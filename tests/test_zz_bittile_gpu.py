@@ -228,3 +228,23 @@ def test_engine_background_staging_switches_at_a_fixed_epoch(gcnb, dev):
         assert abs(t0[0] - t1[0]) <= 2e-5 * (1 + ep) * abs(t0[0]) and abs(v0[0] - v1[0]) <= 2e-5 * (1 + ep) * abs(v0[0])
     for a, b in zip(w0, w1):
         assert_close(b, a, rtol=1e-4, atol=1e-6, what="weights after 5 epochs")
+
+
+# ---- exact-split tcgen05 GEMM for the wide first layer (csrc/dense_tc.cu): opt-in until it has been run on a GPU
+@pytest.mark.skipif(os.environ.get("GCNB_TEST_DENSE_TC") != "1", reason="opt-in: dense_tc.cu not yet run on a GPU")
+@pytest.mark.parametrize("n,f,p", [(128, 16, 16), (300, 50, 16), (1000, 602, 600), (4096 + 77, 602, 41)])
+def test_exact_split_gemm_matches_float64(gcnb, dev, n, f, p):
+    import torch
+    rng = np.random.default_rng(n + f + p)
+    X = rng.standard_normal((n, f)).astype(f32)
+    W = ((rng.random((f, p)) - 0.5) * 2 * np.sqrt(6.0 / (f + p))).astype(f32)
+    want = X.astype(np.float64) @ W.astype(np.float64)
+    d_X, d_W = to_dev(X, dev), to_dev(W, dev)
+    img = gcnb.dense_tc_pack_x(d_X, n, f)
+    out = torch.full((n, p), float("nan"), device=dev)
+    gcnb.dense_tc_fwd(img, d_W, out, n, f, p)
+    torch.cuda.synchronize()
+    assert_close(to_np(out), want, what="exact-split GEMM %dx%dx%d" % (n, f, p))
+    out2 = torch.empty_like(out)
+    gcnb.dense_tc_fwd(img, d_W, out2, n, f, p)
+    assert torch.equal(out, out2)
