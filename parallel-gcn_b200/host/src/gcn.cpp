@@ -106,6 +106,8 @@ struct GCNEngineState {
   // dense feature matrix: dropout applied on the fly from a bit mask (csrc/dense_feat.cu), X never copied
   bool dense_fast = false;
   dev_shared_ptr<natural> x_bits, x_bits_next;
+  // GCNB_DENSE_TC=1, wide first layer on a dense feature matrix: X packed once as bf16 x 3 operand images (csrc/dense_tc.cu)
+  dev_shared_ptr<natural> x_img, x_img_ws;
   // the keep bits of the NEXT training epoch are generated on the side stream while this epoch runs (the Philox
   // stream is a pure function of the consumption history, so the descriptor is known as soon as this epoch's
   // forward has been enqueued); used only if the descriptor still matches when the next epoch starts
@@ -580,6 +582,13 @@ void GCN::init(bool quiet, const natural *h_graph_indptr, const natural *h_graph
     st->dense_tn_ws_bytes = gcnb_dense_feat_tn_workspace(N, (int)F, (int)dims[1]);
     st->dense_tn_ws = dev_shared_ptr<real>((st->dense_tn_ws_bytes + 3) / 4);
   }
+  if (const char *e = getenv("GCNB_DENSE_TC")) {
+    if (atoi(e) != 0 && st->feat_dense && !st->dense_fast && gcnb_dense_tc_supported((int)F, (int)dims[1])) {
+      st->x_img = dev_shared_ptr<natural>((size_t)(gcnb_dense_tc_x_bytes((int64_t)N, (int)F) + 3) / 4);
+      st->x_img_ws = dev_shared_ptr<natural>((size_t)(gcnb_dense_tc_w_bytes((int)F, (int)dims[1]) + 3) / 4);
+      GCNB_CALL(gcnb_dense_tc_pack_x(dev_data.dev_feature_value.get(), st->x_img.get(), (int64_t)N, (int)F, st->stream));
+    }
+  }
   st->tn_ws_bytes = tn_need;
   st->tn_ws = dev_shared_ptr<real>((tn_need + 3) / 4);
   st->ce_ws = dev_shared_ptr<natural>((gcnb_ce_workspace(N) + 3) / 4);
@@ -791,6 +800,12 @@ void GCN::forward_pass(bool training, natural split, cudaStream_t s) {
         GCNB_CALL(gcnb_dense_feat_fwd_f32(xvals, xbits, xp, weights[0]->dev_data.get(), l0.pre->dev_data.get(), N, (int)F,
                                           (int)l0.out_dim, s));
       st->launches += 1;
+    } else if (st->feat_dense && st->x_img.get() && xvals == dev_data.dev_feature_value.get()) {
+      // opt-in (GCNB_DENSE_TC=1): pristine features (no input dropout, or evaluation) through the exact-split tcgen05 GEMM
+      if (live)
+        GCNB_CALL(gcnb_dense_tc_fwd_f32(st->x_img.get(), weights[0]->dev_data.get(), l0.pre->dev_data.get(), N, (int)F,
+                                        (int)l0.out_dim, st->x_img_ws.get(), (int64_t)st->x_img_ws.get_n_elements() * 4, s));
+      st->launches += 2;
     } else if (st->feat_dense) {
       if (live) GCNB_CALL(gcnb_matmul_nn_f32(xvals, weights[0]->dev_data.get(), l0.pre->dev_data.get(), N, F, l0.out_dim, s));
       st->launches += 1;
