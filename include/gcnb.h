@@ -290,6 +290,14 @@ GCNB_API int64_t gcnb_dense_tc_w_bytes(int f, int p);
 GCNB_API int gcnb_dense_tc_pack_x(const float *d_X, void *d_img, int64_t n, int f, gcnb_stream_t stream);
 GCNB_API int gcnb_dense_tc_fwd_f32(const void *d_x_img, const float *d_W, float *d_out, int64_t n, int f, int p, void *d_ws,
                                    int64_t ws_bytes, gcnb_stream_t stream);
+/* weight gradient dW[f x p] = X^T * dH (SparseMatmul::backward on a dense X, src/module.cu:136-163; atomicAdd there): X^T is
+ * packed once (gcnb_dense_tc_xt_bytes / gcnb_dense_tc_pack_xt), dH per call; K (the nodes) is cut into slices whose partial
+ * tiles are added in ascending order.  d_ws: gcnb_dense_tc_tn_workspace(n, f, p) bytes. */
+GCNB_API int64_t gcnb_dense_tc_xt_bytes(int64_t n, int f);
+GCNB_API int gcnb_dense_tc_pack_xt(const float *d_X, void *d_img, int64_t n, int f, gcnb_stream_t stream);
+GCNB_API int64_t gcnb_dense_tc_tn_workspace(int64_t n, int f, int p);
+GCNB_API int gcnb_dense_tc_tn_f32(const void *d_xt_img, const float *d_dH, float *d_dW, int64_t n, int f, int p, void *d_ws,
+                                  int64_t ws_bytes, gcnb_stream_t stream);
 GCNB_API int gcnb_dense_tc_debug_pack_w(const float *d_W, void *d_ws, int f, int p, gcnb_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------

@@ -90,6 +90,10 @@ _sig("gcnb_dense_tc_x_bytes", I64, [I64, I32])
 _sig("gcnb_dense_tc_w_bytes", I64, [I32, I32])
 _sig("gcnb_dense_tc_pack_x", I32, [P, P, I64, I32, P])
 _sig("gcnb_dense_tc_fwd_f32", I32, [P, P, P, I64, I32, I32, P, I64, P])
+_sig("gcnb_dense_tc_xt_bytes", I64, [I64, I32])
+_sig("gcnb_dense_tc_pack_xt", I32, [P, P, I64, I32, P])
+_sig("gcnb_dense_tc_tn_workspace", I64, [I64, I32, I32])
+_sig("gcnb_dense_tc_tn_f32", I32, [P, P, P, I64, I32, I32, P, I64, P])
 _sig("gcnb_glorot_f32", I32, [P, I64, U32, U32, P, P])
 _sig("gcnb_dropout_fwd_f32", I32, [P, P, P, I64, F32, P, P])
 _sig("gcnb_dropout_fwd_oop_f32", I32, [P, P, P, P, I64, F32, P, P])
@@ -456,6 +460,21 @@ def dense_tc_fwd(x_img, W, out, n, f, p, ws=None):
         ws = torch.empty(need, dtype=torch.uint8, device=W.device)
     check(lib.gcnb_dense_tc_fwd_f32(ptr(x_img), ptr(W), ptr(out), n, f, p, ptr(ws), ws.numel(), stream()))
     return out
+
+
+def dense_tc_pack_xt(X, n, f):
+    import torch
+    img = torch.empty(lib.gcnb_dense_tc_xt_bytes(n, f), dtype=torch.uint8, device=X.device)
+    check(lib.gcnb_dense_tc_pack_xt(ptr(X), ptr(img), n, f, stream()))
+    return img
+
+
+def dense_tc_tn(xt_img, dH, dW, n, f, p, ws=None):
+    import torch
+    if ws is None:
+        ws = torch.empty(lib.gcnb_dense_tc_tn_workspace(n, f, p), dtype=torch.uint8, device=dH.device)
+    check(lib.gcnb_dense_tc_tn_f32(ptr(xt_img), ptr(dH), ptr(dW), n, f, p, ptr(ws), ws.numel(), stream()))
+    return dW
 
 
 def glorot(w, rows, cols, rng):

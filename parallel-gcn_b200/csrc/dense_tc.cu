@@ -160,10 +160,43 @@ __global__ void __launch_bounds__(256) tc_pack_w_kernel(const float *__restrict_
 
 struct TcArgs {
   const uint8_t *a_img, *b_img;
-  float *out;
-  int64_t n, n_blk;
-  int p, KS, n_parts, pcols;
+  float *out;        // k_slices == 1: out[n x p];  k_slices > 1: partial tiles [slice][block][part][128][pcols]
+  int64_t n, n_blk;  // rows of the A operand (output rows) and their blocks of 128
+  int p, KS, n_parts, pcols, k_slices;
 };
+
+// item j of a CTA -> (row block, column part, k range).  One k slice: the parts of a row block are consecutive items of one
+// CTA (the A tiles are re-read from L2).  Split K (the transposed product: few output tiles, long K): flat round robin.
+struct TcItem {
+  int64_t blk;
+  int q, ks0, ks1, slice;
+};
+__device__ __forceinline__ int64_t tc_item_count(const TcArgs &a) {
+  if (a.k_slices == 1) {
+    const int64_t my_blocks = a.n_blk > (int64_t)blockIdx.x ? (a.n_blk - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    return my_blocks * a.n_parts;
+  }
+  const int64_t total = a.n_blk * a.n_parts * a.k_slices;
+  return total > (int64_t)blockIdx.x ? (total - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+}
+__device__ __forceinline__ TcItem tc_item(const TcArgs &a, int64_t j) {
+  TcItem it;
+  if (a.k_slices == 1) {
+    it.blk = blockIdx.x + (j / a.n_parts) * gridDim.x;
+    it.q = (int)(j % a.n_parts);
+    it.slice = 0;
+    it.ks0 = 0;
+    it.ks1 = a.KS;
+  } else {
+    const int64_t id = blockIdx.x + j * gridDim.x;
+    it.q = (int)(id % a.n_parts);
+    it.blk = (id / a.n_parts) % a.n_blk;
+    it.slice = (int)(id / (a.n_parts * a.n_blk));
+    it.ks0 = (int)((int64_t)a.KS * it.slice / a.k_slices);
+    it.ks1 = (int)((int64_t)a.KS * (it.slice + 1) / a.k_slices);
+  }
+  return it;
+}
 
 // persistent: CTA c takes row blocks c, c + grid, ...; the n_parts column parts of a block are consecutive items
 __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(TcArgs a) {
@@ -195,27 +228,34 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(TcArgs a) {
   __syncthreads();
   tcg_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t *>(tmem_slot);
-  // items of this CTA: (block, part) for block = blockIdx.x, blockIdx.x + gridDim.x, ...; item index k counts them
-  const int64_t my_blocks = a.n_blk > (int64_t)blockIdx.x ? (a.n_blk - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  const int64_t n_items = my_blocks * a.n_parts;
+  const int64_t n_items = tc_item_count(a);
 
   if (warp < 4) {
     // ---- epilogue: thread = row
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
     for (int64_t k = 0; k < n_items; k++) {
-      const int64_t blk = blockIdx.x + (k / a.n_parts) * gridDim.x;
-      const int q = (int)(k % a.n_parts);
+      const TcItem it = tc_item(a, k);
+      const int64_t blk = it.blk;
+      const int q = it.q;
       const uint32_t set = (uint32_t)(k & 1), use = (uint32_t)(k >> 1);
-      const int64_t row = blk * kTcRows + warp * 32 + lane;
+      const int r_in_blk = warp * 32 + lane;
+      const int64_t row = blk * kTcRows + r_in_blk;
       mbar_wait(&acc_full[set], use & 1);
       tcg_fence_after();
       const uint32_t acc0 = tmem + lane_base + set * 256;
+      float *tile = a.k_slices > 1
+                        ? a.out + ((((int64_t)it.slice * a.n_blk + blk) * a.n_parts + q) * kTcRows + r_in_blk) * (int64_t)a.pcols
+                        : nullptr;
       for (int c0 = 0; c0 < a.pcols; c0 += 16) {
         float v[16];
         tcg_ld16(acc0 + c0, v);
         tcg_wait_ld();
-        const int col0 = q * a.pcols + c0;
-        if (row < a.n) {
+        if (tile) {  // partial tile of this k slice: every element is written (padding rows / columns hold exact zeros)
+#pragma unroll
+          for (int i = 0; i < 4; i++)
+            reinterpret_cast<float4 *>(tile + c0)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        } else if (row < a.n) {
+          const int col0 = q * a.pcols + c0;
           float *dst = a.out + row * a.p + col0;
 #pragma unroll
           for (int i = 0; i < 16; i++)
@@ -231,9 +271,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(TcArgs a) {
     if (lane == 0) {
       uint64_t t = 0;
       for (int64_t k = 0; k < n_items; k++) {
-        const int64_t blk = blockIdx.x + (k / a.n_parts) * gridDim.x;
-        const int q = (int)(k % a.n_parts);
-        for (int ks = 0; ks < a.KS; ks++, t++) {
+        const TcItem it = tc_item(a, k);
+        const int64_t blk = it.blk;
+        const int q = it.q;
+        for (int ks = it.ks0; ks < it.ks1; ks++, t++) {
           const uint32_t s = (uint32_t)(t % kTcStages), use = (uint32_t)(t / kTcStages);
           if (use > 0) mbar_wait(&free_[s], (use - 1) & 1);
           uint8_t *stage = tc_smem + (size_t)s * stage_bytes;
@@ -253,7 +294,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(TcArgs a) {
       if (use > 0) mbar_wait(&acc_empty[set], (use - 1) & 1);
       tcg_fence_after();
       const uint32_t d = tmem + set * 256;
-      for (int ks = 0; ks < a.KS; ks++, t++) {
+      const TcItem it = tc_item(a, k);
+      for (int ks = it.ks0; ks < it.ks1; ks++, t++) {
         const uint32_t s = (uint32_t)(t % kTcStages), u = (uint32_t)(t / kTcStages);
         mbar_wait(&full[s], u & 1);
         tcg_fence_after();
@@ -265,7 +307,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(TcArgs a) {
           const uint64_t b0 = tcg_desc(sb, (uint32_t)a.pcols * 16u), b1 = tcg_desc(sb + pb, (uint32_t)a.pcols * 16u),
                          b2 = tcg_desc(sb + 2 * pb, (uint32_t)a.pcols * 16u);
           // smallest terms first inside the k-step: lo*hi, hi*lo, mid*mid, mid*hi, hi*mid, hi*hi
-          tcg_mma_ss(d, a2, b0, idesc, ks > 0 ? 1u : 0u);
+          tcg_mma_ss(d, a2, b0, idesc, ks > it.ks0 ? 1u : 0u);
           tcg_mma_ss(d, a0, b2, idesc, 1u);
           tcg_mma_ss(d, a1, b1, idesc, 1u);
           tcg_mma_ss(d, a1, b0, idesc, 1u);
@@ -286,6 +328,60 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(TcArgs a) {
     __syncwarp();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
   }
+}
+
+// A image of X^T for the weight gradient dW[f x p] = X^T * dH: operand row = feature, k = node.  Same tile format as
+// tc_pack_x_kernel; thread = (feature, k-half) of one (feature block, k-step)
+__global__ void __launch_bounds__(256) tc_pack_xt_kernel(const float *__restrict__ X, uint8_t *__restrict__ img, int64_t n, int f,
+                                                         int KS, int64_t f_blk) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = f_blk * kTcRows * (int64_t)KS * 2;
+  if (tid >= total) return;
+  const int r = (int)(tid % kTcRows);          // adjacent threads = adjacent features: coalesced reads of X's rows
+  const int64_t t2 = tid / kTcRows;
+  const int half = (int)(t2 & 1);
+  const int64_t t3 = t2 >> 1;
+  const int ks = (int)(t3 % KS);
+  const int64_t b = t3 / KS;
+  const int64_t feat = b * kTcRows + r;
+  uint32_t h[4] = {0, 0, 0, 0}, m[4] = {0, 0, 0, 0}, l[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const int64_t node = (int64_t)ks * 16 + half * 8 + i;
+    const float x = (feat < f && node < n) ? __ldg(X + node * f + feat) : 0.f;
+    uint32_t a, c, d;
+    tcg_split3(x, a, c, d);
+    const int sh = (i & 1) * 16;
+    h[i >> 1] |= a << sh;
+    m[i >> 1] |= c << sh;
+    l[i >> 1] |= d << sh;
+  }
+  uint8_t *tile = img + ((b * KS + ks) * 3) * (int64_t)kTcATile + half * 2048 + (r >> 3) * 128 + (r & 7) * 16;
+  *reinterpret_cast<uint4 *>(tile) = make_uint4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<uint4 *>(tile + kTcATile) = make_uint4(m[0], m[1], m[2], m[3]);
+  *reinterpret_cast<uint4 *>(tile + 2 * kTcATile) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// out[rows x p] = sum over the k slices, ascending, of the partial tiles
+__global__ void __launch_bounds__(256) tc_reduce_kernel(const float *__restrict__ partial, float *__restrict__ out, int64_t rows,
+                                                        int p, int64_t n_blk, int n_parts, int pcols, int k_slices) {
+  const int64_t total = rows * p;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / p;
+    const int col = (int)(i % p);
+    const int64_t blk = row / kTcRows;
+    const int r = (int)(row % kTcRows), q = col / pcols, c = col % pcols;
+    float s = 0.f;
+    for (int sl = 0; sl < k_slices; sl++)
+      s += partial[((((int64_t)sl * n_blk + blk) * n_parts + q) * kTcRows + r) * (int64_t)pcols + c];
+    out[i] = s;
+  }
+}
+
+// 4 stages x (12 KB of A + at most 24 KB of B) + barriers: allow it once
+static cudaError_t tc_allow_smem() {
+  static cudaError_t rc = cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+  return rc;
 }
 
 static void tc_shape(int f, int p, int *KS, int *n_parts, int *pcols) {
@@ -341,18 +437,86 @@ int gcnb_dense_tc_fwd_f32(const void *d_x_img, const float *d_W, float *d_out, i
   a.n = n;
   a.n_blk = (n + kTcRows - 1) / kTcRows;
   a.p = p;
+  a.k_slices = 1;
   const int64_t wt = (int64_t)a.n_parts * a.KS * a.pcols * 2;
   tc_pack_w_kernel<<<(unsigned)((wt + 255) / 256), 256, 0, stream>>>(d_W, (uint8_t *)d_ws, f, p, a.KS, a.n_parts, a.pcols);
   GCNB_LAUNCH_CHECK();
   const size_t smem = (size_t)kTcStages * (3 * kTcATile + 3 * (size_t)a.pcols * 32) + (2 * kTcStages + 4) * 8 + 16;
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    GCNB_CHECK(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
-  }
+  GCNB_CHECK(tc_allow_smem());
   const int grid = (int)std::min<int64_t>(a.n_blk, std::max(1, di.sm_count));
   tc_gemm_kernel<<<grid, kTcThreads, smem, stream>>>(a);
   GCNB_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---- weight gradient  dW[f x p] = X^T[f x n] * dH[n x p]  (SparseMatmul::backward on a dense X, src/module.cu:136-163) --------
+// X^T is packed once (operand rows = features, K = nodes); dH is packed per call; K is cut into slices so that all SMs have
+// work (5 feature blocks x 3 column parts only), the slices' partial tiles are added in ascending order.
+static int tc_tn_slices(int64_t n, int f, int p, int sms) {
+  int KS, n_parts, pcols;
+  tc_shape((int)std::min<int64_t>(n, 1 << 30), p, &KS, &n_parts, &pcols);
+  const int64_t tiles = ((f + kTcRows - 1) / kTcRows) * (int64_t)n_parts;
+  const int64_t ks = (n + 15) / 16;
+  return (int)std::max<int64_t>(1, std::min<int64_t>(ks, (2 * (int64_t)sms) / std::max<int64_t>(1, tiles)));
+}
+int64_t gcnb_dense_tc_xt_bytes(int64_t n, int f) {
+  return ((f + kTcRows - 1) / kTcRows) * ((n + 15) / 16) * 3 * (int64_t)kTcATile;
+}
+int gcnb_dense_tc_pack_xt(const float *d_X, void *d_img, int64_t n, int f, gcnb_stream_t stream_) {
+  if (!d_X || !d_img || n < 0 || f < 1 || n > (1ll << 30)) return GCNB_E_BADARG;
+  if (n == 0) return 0;
+  const int64_t f_blk = (f + kTcRows - 1) / kTcRows;
+  const int KS = (int)((n + 15) / 16);
+  const int64_t total = f_blk * kTcRows * (int64_t)KS * 2;
+  tc_pack_xt_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream_)>>>(d_X, (uint8_t *)d_img, n, f, KS, f_blk);
+  GCNB_LAUNCH_CHECK();
+  return 0;
+}
+// workspace: packed dH image + partial tiles (148 SMs assumed for sizing when no device is present)
+int64_t gcnb_dense_tc_tn_workspace(int64_t n, int f, int p) {
+  if (n < 1 || n > (1ll << 30) || !gcnb_dense_tc_supported(f, p)) return 0;
+  int KS, n_parts, pcols;
+  tc_shape((int)n, p, &KS, &n_parts, &pcols);
+  const DeviceInfo &di = device_info();
+  const int slices = tc_tn_slices(n, f, p, di.ok ? std::max(1, di.sm_count) : 148);
+  const int64_t img = (int64_t)n_parts * KS * 3 * pcols * 32;
+  const int64_t partial = (int64_t)slices * ((f + kTcRows - 1) / kTcRows) * n_parts * kTcRows * pcols * 4;
+  return img + partial + 256;
+}
+int gcnb_dense_tc_tn_f32(const void *d_xt_img, const float *d_dH, float *d_dW, int64_t n, int f, int p, void *d_ws,
+                         int64_t ws_bytes, gcnb_stream_t stream_) {
+  if (!d_xt_img || !d_dH || !d_dW || !d_ws || n < 1 || n > (1ll << 30) || !gcnb_dense_tc_supported(f, p)) return GCNB_E_BADARG;
+  if (ws_bytes < gcnb_dense_tc_tn_workspace(n, f, p)) return GCNB_E_BADARG;
+  const DeviceInfo &di = device_info();
+  if (!di.ok) return (int)cudaErrorNoDevice;
+  if (di.cc_major != 10) return GCNB_E_UNSUPPORTED;
+  cudaStream_t stream = as_stream(stream_);
+  TcArgs a;
+  tc_shape((int)n, p, &a.KS, &a.n_parts, &a.pcols);  // K = nodes
+  a.k_slices = tc_tn_slices(n, f, p, std::max(1, di.sm_count));
+  a.n = f;
+  a.n_blk = (f + kTcRows - 1) / kTcRows;
+  a.p = p;
+  const int64_t img_bytes = ((int64_t)a.n_parts * a.KS * 3 * a.pcols * 32 + 255) / 256 * 256;
+  a.a_img = (const uint8_t *)d_xt_img;
+  a.b_img = (const uint8_t *)d_ws;
+  float *partial = reinterpret_cast<float *>((uint8_t *)d_ws + img_bytes);
+  a.out = a.k_slices > 1 ? partial : d_dW;
+  const int64_t wt = (int64_t)a.n_parts * a.KS * a.pcols * 2;
+  tc_pack_w_kernel<<<(unsigned)((wt + 255) / 256), 256, 0, stream>>>(d_dH, (uint8_t *)d_ws, (int)n, p, a.KS, a.n_parts, a.pcols);
+  GCNB_LAUNCH_CHECK();
+  const size_t smem = (size_t)kTcStages * (3 * kTcATile + 3 * (size_t)a.pcols * 32) + (2 * kTcStages + 4) * 8 + 16;
+  GCNB_CHECK(tc_allow_smem());
+  const int64_t items = a.n_blk * a.n_parts * a.k_slices;
+  const int grid = (int)std::min<int64_t>(items, std::max(1, di.sm_count));
+  tc_gemm_kernel<<<grid, kTcThreads, smem, stream>>>(a);
+  GCNB_LAUNCH_CHECK();
+  if (a.k_slices > 1) {
+    const int64_t total = (int64_t)f * p;
+    tc_reduce_kernel<<<(unsigned)std::min<int64_t>((total + 255) / 256, (int64_t)di.sm_count * 8), 256, 0, stream>>>(
+        partial, d_dW, f, p, a.n_blk, a.n_parts, a.pcols, a.k_slices);
+    GCNB_LAUNCH_CHECK();
+  }
   return 0;
 }
 

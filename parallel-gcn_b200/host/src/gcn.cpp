@@ -107,7 +107,7 @@ struct GCNEngineState {
   bool dense_fast = false;
   dev_shared_ptr<natural> x_bits, x_bits_next;
   // GCNB_DENSE_TC=1, wide first layer on a dense feature matrix: X packed once as bf16 x 3 operand images (csrc/dense_tc.cu)
-  dev_shared_ptr<natural> x_img, x_img_ws;
+  dev_shared_ptr<natural> x_img, x_img_ws, xt_img, xt_ws;
   // the keep bits of the NEXT training epoch are generated on the side stream while this epoch runs (the Philox
   // stream is a pure function of the consumption history, so the descriptor is known as soon as this epoch's
   // forward has been enqueued); used only if the descriptor still matches when the next epoch starts
@@ -587,6 +587,11 @@ void GCN::init(bool quiet, const natural *h_graph_indptr, const natural *h_graph
       st->x_img = dev_shared_ptr<natural>((size_t)(gcnb_dense_tc_x_bytes((int64_t)N, (int)F) + 3) / 4);
       st->x_img_ws = dev_shared_ptr<natural>((size_t)(gcnb_dense_tc_w_bytes((int)F, (int)dims[1]) + 3) / 4);
       GCNB_CALL(gcnb_dense_tc_pack_x(dev_data.dev_feature_value.get(), st->x_img.get(), (int64_t)N, (int)F, st->stream));
+      if (params->dropouts.front() == 0.f) {  // the weight gradient reads the features the training forward used
+        st->xt_img = dev_shared_ptr<natural>((size_t)(gcnb_dense_tc_xt_bytes((int64_t)N, (int)F) + 3) / 4);
+        st->xt_ws = dev_shared_ptr<natural>((size_t)(gcnb_dense_tc_tn_workspace((int64_t)N, (int)F, (int)dims[1]) + 3) / 4);
+        GCNB_CALL(gcnb_dense_tc_pack_xt(dev_data.dev_feature_value.get(), st->xt_img.get(), (int64_t)N, (int)F, st->stream));
+      }
     }
   }
   st->tn_ws_bytes = tn_need;
@@ -917,6 +922,11 @@ void GCN::backward_pass(cudaStream_t s) {
                                      weights[0]->dev_grad.get(), N, (int)F, (int)l0.out_dim, st->dense_tn_ws.get(),
                                      st->dense_tn_ws_bytes, s));
     st->launches += 2;
+  } else if (st->feat_dense && st->xt_img.get() && st->x_train_vals == dev_data.dev_feature_value.get()) {
+    // opt-in (GCNB_DENSE_TC=1): pristine features => X^T dH through the exact-split tcgen05 GEMM (pack, GEMM, slice reduce)
+    GCNB_CALL(gcnb_dense_tc_tn_f32(st->xt_img.get(), l0.pre->dev_grad.get(), weights[0]->dev_grad.get(), (int64_t)N, (int)F,
+                                   (int)l0.out_dim, st->xt_ws.get(), (int64_t)st->xt_ws.get_n_elements() * 4, s));
+    st->launches += 3;
   } else if (st->feat_dense) {
     GCNB_CALL(gcnb_matmul_tn_f32(st->x_train_vals, l0.pre->dev_grad.get(), weights[0]->dev_grad.get(), N, F, l0.out_dim,
                                  st->tn_ws.get(), st->tn_ws_bytes, s));

@@ -248,3 +248,22 @@ def test_exact_split_gemm_matches_float64(gcnb, dev, n, f, p):
     out2 = torch.empty_like(out)
     gcnb.dense_tc_fwd(img, d_W, out2, n, f, p)
     assert torch.equal(out, out2)
+
+
+@pytest.mark.skipif(os.environ.get("GCNB_TEST_DENSE_TC") != "1", reason="opt-in: dense_tc.cu not yet run on a GPU")
+@pytest.mark.parametrize("n,f,p", [(200, 16, 16), (5000, 50, 41), (30000, 602, 600)])
+def test_exact_split_weight_gradient_matches_float64(gcnb, dev, n, f, p):
+    import torch
+    rng = np.random.default_rng(n + f + p)
+    X = rng.standard_normal((n, f)).astype(f32)
+    dH = (rng.standard_normal((n, p)) * 1e-3).astype(f32)
+    want = X.astype(np.float64).T @ dH.astype(np.float64)
+    d_X, d_dH = to_dev(X, dev), to_dev(dH, dev)
+    img = gcnb.dense_tc_pack_xt(d_X, n, f)
+    dW = torch.full((f, p), float("nan"), device=dev)
+    gcnb.dense_tc_tn(img, d_dH, dW, n, f, p)
+    torch.cuda.synchronize()
+    assert_close(to_np(dW), want, what="exact-split X^T dH %dx%dx%d" % (n, f, p))
+    dW2 = torch.empty_like(dW)
+    gcnb.dense_tc_tn(img, d_dH, dW2, n, f, p)
+    assert torch.equal(dW, dW2)
