@@ -45,3 +45,107 @@ def test_shape_helpers(monkeypatch):
     assert gcnb.lib.gcnb_dense_tc_x_bytes(232965, 602) == n_blk * ks * 3 * 4096
     assert gcnb.lib.gcnb_dense_tc_w_bytes(602, 600) == 3 * ks * 3 * 208 * 32  # 600 columns -> 3 parts of 208
     assert gcnb.lib.gcnb_dense_tc_w_bytes(50, 16) == 1 * 4 * 3 * 16 * 32
+
+
+# ---- operand images: the pack kernels' write offsets against the descriptors' read addressing (dense_tc.cu restated) ------
+def _bf16_bits(x):
+    return (x.astype(np.float32).view(np.uint32) >> np.uint32(16)).astype(np.uint16)
+
+
+def _from_bits(b):
+    return (b.astype(np.uint32) << np.uint32(16)).view(np.float32).astype(np.float64)
+
+
+def _shape(f, p):
+    KS = (f + 15) // 16
+    p_pad = (p + 15) // 16 * 16
+    n_parts = (p_pad + 255) // 256
+    pcols = ((p_pad + n_parts - 1) // n_parts + 15) // 16 * 16
+    return KS, n_parts, pcols
+
+
+def _pack_rows(M, n_rows_pad, KS):
+    """tc_pack_x_kernel / tc_pack_xt_kernel: M[row][k] (row = operand row) -> tiles ((b * KS + ks) * 3 + piece) of 4096 bytes,
+    element at half * 2048 + (r / 8) * 128 + (r % 8) * 16 + (k % 8) * 2"""
+    rows, K = M.shape
+    n_blk = n_rows_pad // 128
+    img = np.zeros(n_blk * KS * 3 * 2048, np.uint16)
+    Mp = np.zeros((n_rows_pad, KS * 16), np.float32)
+    Mp[:rows, :K] = M
+    pieces = [_bf16_bits(p) for p in split3(Mp)]
+    r = np.arange(n_rows_pad)[:, None]
+    k = np.arange(KS * 16)[None, :]
+    b, rr, ks, kk = r // 128, r % 128, k // 16, k % 16
+    for pc in range(3):
+        off = ((b * KS + ks) * 3 + pc) * 4096 + (kk // 8) * 2048 + (rr // 8) * 128 + (rr % 8) * 16 + (kk % 8) * 2
+        img[off // 2] = pieces[pc]
+    return img
+
+
+def _pack_w(W, f, p):
+    """tc_pack_w_kernel: tile ((q * KS + ks) * 3 + piece) of pcols * 32 bytes, element (column c, k) at
+    (k / 8) * pcols * 16 + (c / 8) * 128 + (c % 8) * 16 + (k % 8) * 2"""
+    KS, n_parts, pcols = _shape(f, p)
+    Wp = np.zeros((KS * 16, n_parts * pcols), np.float32)
+    Wp[:f, :p] = W
+    pieces = [_bf16_bits(x) for x in split3(Wp)]
+    img = np.zeros(n_parts * KS * 3 * pcols * 16, np.uint16)
+    k = np.arange(KS * 16)[:, None]
+    col = np.arange(n_parts * pcols)[None, :]
+    q, c, ks, kk = col // pcols, col % pcols, k // 16, k % 16
+    for pc in range(3):
+        off = ((q * KS + ks) * 3 + pc) * (pcols * 32) + (kk // 8) * (pcols * 16) + (c // 8) * 128 + (c % 8) * 16 + (kk % 8) * 2
+        img[off // 2] = pieces[pc]
+    return img
+
+
+def _read_operand(img, base_bytes, rows, lbo):
+    """what tcgen05.mma reads through tcg_desc(base, lbo): element (row, k) at base + (k / 8) * lbo + (row / 8) * 128 +
+    (row % 8) * 16 + (k % 8) * 2"""
+    r = np.arange(rows)[:, None]
+    k = np.arange(16)[None, :]
+    off = base_bytes + (k // 8) * lbo + (r // 8) * 128 + (r % 8) * 16 + (k % 8) * 2
+    return _from_bits(img[off // 2])
+
+
+def _gemm_emulated(a_img, b_img, n_rows_pad, KS, n_parts, pcols, k_slices=1):
+    """tc_gemm_kernel: per (row block, part, k slice) the six piece products per k-step, slices added in ascending order"""
+    n_blk = n_rows_pad // 128
+    out = np.zeros((n_rows_pad, n_parts * pcols))
+    for blk in range(n_blk):
+        for q in range(n_parts):
+            for sl in range(k_slices):
+                acc = np.zeros((128, pcols))
+                for ks in range(KS * sl // k_slices, KS * (sl + 1) // k_slices):
+                    A = [_read_operand(a_img, ((blk * KS + ks) * 3 + pc) * 4096, 128, 2048) for pc in range(3)]
+                    B = [_read_operand(b_img, ((q * KS + ks) * 3 + pc) * pcols * 32, pcols, pcols * 16) for pc in range(3)]
+                    for i, j in ((2, 0), (0, 2), (1, 1), (1, 0), (0, 1), (0, 0)):
+                        acc += A[i] @ B[j].T
+                out[blk * 128:(blk + 1) * 128, q * pcols:(q + 1) * pcols] += acc
+    return out
+
+
+def test_forward_operand_images_and_descriptor_addressing():
+    rng = np.random.default_rng(1)
+    for n, f, p in ((200, 50, 41), (130, 602, 600)):
+        X = rng.standard_normal((n, f)).astype(np.float32)
+        W = rng.standard_normal((f, p)).astype(np.float32)
+        KS, n_parts, pcols = _shape(f, p)
+        n_pad = (n + 127) // 128 * 128
+        got = _gemm_emulated(_pack_rows(X, n_pad, KS), _pack_w(W, f, p), n_pad, KS, n_parts, pcols)[:n, :p]
+        assert_close(got, X.astype(np.float64) @ W.astype(np.float64), what="forward image %dx%dx%d" % (n, f, p))
+
+
+def test_weight_gradient_images_and_split_k():
+    rng = np.random.default_rng(2)
+    n, f, p = 1000, 150, 41  # operand rows = features (2 blocks of 128), K = nodes (63 k-steps), 5 k slices
+    X = rng.standard_normal((n, f)).astype(np.float32)
+    dH = rng.standard_normal((n, p)).astype(np.float32)
+    KS, n_parts, pcols = _shape(n, p)
+    f_pad = (f + 127) // 128 * 128
+    a_img = _pack_rows(np.ascontiguousarray(X.T), f_pad, KS)  # tc_pack_xt_kernel: operand row = feature, k = node
+    b_img = _pack_w(dH, n, p)                                 # tc_pack_w_kernel with K = n
+    want = X.astype(np.float64).T @ dH.astype(np.float64)
+    for k_slices in (1, 5, 63):
+        got = _gemm_emulated(a_img, b_img, f_pad, KS, n_parts, pcols, k_slices)[:f, :p]
+        assert_close(got, want, what="X^T dH, %d k slices" % k_slices)
