@@ -31,6 +31,7 @@ step 120 r2_bt_g1_rb2_cap2.log env GCNB_BT_REM_CTAS=2 python scripts/probe_bitti
 step 300 r2_engine_optin.log env GCNB_TEST_BITTILE_ENGINE=1 GCNB_TEST_ASYNC_STAGE=1 python -m pytest tests/test_zz_bittile_gpu.py -m gpu -x -q -k "engine or background"
 # 4b. exact-split tcgen05 GEMM for the wide first layer (csrc/dense_tc.cu)
 step 300 r2_dense_tc.log env GCNB_TEST_DENSE_TC=1 python -m pytest tests/test_zz_bittile_gpu.py -m gpu -x -q -k exact_split
+step 300 r2_dense_tc_probe.log python scripts/probe_dense_tc.py --out gpurun_out/r2_probe_dense_tc.jsonl
 step 600 r2_configs_default.log python scripts/bench_configs.py
 step 600 r2_configs_dense_tc.log env GCNB_DENSE_TC=1 python scripts/bench_configs.py
 # 5. bench lines: default, background staging, bit tiles (+ the best shape from step 3 through GCNB_BT_CHUNK / GCNB_BT_RB)
