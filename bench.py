@@ -261,6 +261,8 @@ def run_ours(args, rank, world, local_rank):
                        "evaluation_layer0": "(A_hat X) W0 with A_hat X computed once at the first evaluation (its 38 GraphSum "
                                             "slabs are part of e2e and of the warm-up, not of the timed steps): 5 GraphSum "
                                             "calls per step instead of 6; GCNB_PROPAGATE=0 restores A_hat (X W0)",
+                       "graphsum_path": "bit tiles (tcgen05)" if g.graph_bittile() else ("window-staged" if staged else "generic"),
+                       "switches": {k: os.environ[k] for k in sorted(os.environ) if k.startswith("GCNB_")},
                        "final_train_loss": last[0][0], "final_val_acc": last[1][1], "published_other_hw": PUBLISHED},
             "clocks": clk, "e2e": e2e, "gpu_launches": r["launches"], "roofline": roofline}
     g.close()
