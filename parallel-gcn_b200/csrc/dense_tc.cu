@@ -24,6 +24,7 @@
 
 #include "bulk.cuh"
 #include "common.cuh"
+#include "tcgen05.cuh"
 
 using namespace gcnb;
 
@@ -33,57 +34,6 @@ constexpr int kTcRows = 128;
 constexpr int kTcATile = kTcRows * 16 * 2;  // 4096 bytes: 128 x 16 bf16
 constexpr int kTcStages = 4;
 constexpr int kTcThreads = 6 * 32;          // warps 0-3 epilogue, 4 producer, 5 MMA issuer
-
-__device__ __forceinline__ void tcg_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcg_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcg_mbar_arrive(uint64_t *bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tcg_commit(uint64_t *bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ bool tcg_elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "elect.sync _|p, 0xffffffff;\n"
-      "selp.u32 %0, 1, 0, p;\n"
-      "}\n"
-      : "=r"(pred));
-  return pred != 0;
-}
-// D[tmem] (+)= A[smem descriptor] * B[smem descriptor]
-__device__ __forceinline__ void tcg_mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void tcg_ld16(uint32_t taddr, float (&v)[16]) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
-      "[%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-#pragma unroll
-  for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ void tcg_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major, no swizzle: element (row, k) of an operand of R rows x 16 at (k / 8) * lbo + (row / 8) * 128 + (row % 8) * 16 +
-// (k % 8) * 2; lbo = R * 16 bytes (the core matrices of one k-half are contiguous), stride between 8-row groups 128
-__device__ __forceinline__ uint64_t tcg_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
-  return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) | (1ull << 46);
-}
 
 __device__ __forceinline__ void tcg_split3(float x, uint32_t &hi, uint32_t &mid, uint32_t &lo) {  // bf16 bit patterns
   const uint32_t hb = __float_as_uint(x) & 0xffff0000u;
@@ -224,9 +174,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(TcArgs a) {
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  tcg_fence_before();
+  tc_fence_before();
   __syncthreads();
-  tcg_fence_after();
+  tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t *>(tmem_slot);
   const int64_t n_items = tc_item_count(a);
 
@@ -241,15 +191,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(TcArgs a) {
       const int r_in_blk = warp * 32 + lane;
       const int64_t row = blk * kTcRows + r_in_blk;
       mbar_wait(&acc_full[set], use & 1);
-      tcg_fence_after();
+      tc_fence_after();
       const uint32_t acc0 = tmem + lane_base + set * 256;
       float *tile = a.k_slices > 1
                         ? a.out + ((((int64_t)it.slice * a.n_blk + blk) * a.n_parts + q) * kTcRows + r_in_blk) * (int64_t)a.pcols
                         : nullptr;
       for (int c0 = 0; c0 < a.pcols; c0 += 16) {
         float v[16];
-        tcg_ld16(acc0 + c0, v);
-        tcg_wait_ld();
+        tc_ld16(acc0 + c0, v);
+        tc_wait_ld();
         if (tile) {  // partial tile of this k slice: every element is written (padding rows / columns hold exact zeros)
 #pragma unroll
           for (int i = 0; i < 4; i++)
@@ -262,9 +212,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(TcArgs a) {
             if (col0 + i < a.p) dst[i] = v[i];
         }
       }
-      tcg_fence_before();
+      tc_fence_before();
       __syncwarp();
-      if (lane == 0) tcg_mbar_arrive(&acc_empty[set]);
+      if (lane == 0) mbar_arrive(&acc_empty[set]);
     }
   } else if (warp == 4) {
     // ---- producer: one A stage (3 x 4 KB) + one B stage (3 x pcols x 32 bytes) per k-step
@@ -292,37 +242,37 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(TcArgs a) {
     for (int64_t k = 0; k < n_items; k++) {
       const uint32_t set = (uint32_t)(k & 1), use = (uint32_t)(k >> 1);
       if (use > 0) mbar_wait(&acc_empty[set], (use - 1) & 1);
-      tcg_fence_after();
+      tc_fence_after();
       const uint32_t d = tmem + set * 256;
       const TcItem it = tc_item(a, k);
       for (int ks = it.ks0; ks < it.ks1; ks++, t++) {
         const uint32_t s = (uint32_t)(t % kTcStages), u = (uint32_t)(t / kTcStages);
         mbar_wait(&full[s], u & 1);
-        tcg_fence_after();
-        if (tcg_elect_one()) {
+        tc_fence_after();
+        if (elect_one()) {
           const uint32_t sa = smem_u32(tc_smem + (size_t)s * stage_bytes);
           const uint32_t sb = sa + 3 * kTcATile;
           const uint32_t pb = (uint32_t)a.pcols * 32u;
-          const uint64_t a0 = tcg_desc(sa, 2048), a1 = tcg_desc(sa + kTcATile, 2048), a2 = tcg_desc(sa + 2 * kTcATile, 2048);
-          const uint64_t b0 = tcg_desc(sb, (uint32_t)a.pcols * 16u), b1 = tcg_desc(sb + pb, (uint32_t)a.pcols * 16u),
-                         b2 = tcg_desc(sb + 2 * pb, (uint32_t)a.pcols * 16u);
+          const uint64_t a0 = tc_smem_desc(sa, 2048), a1 = tc_smem_desc(sa + kTcATile, 2048), a2 = tc_smem_desc(sa + 2 * kTcATile, 2048);
+          const uint64_t b0 = tc_smem_desc(sb, (uint32_t)a.pcols * 16u), b1 = tc_smem_desc(sb + pb, (uint32_t)a.pcols * 16u),
+                         b2 = tc_smem_desc(sb + 2 * pb, (uint32_t)a.pcols * 16u);
           // smallest terms first inside the k-step: lo*hi, hi*lo, mid*mid, mid*hi, hi*mid, hi*hi
-          tcg_mma_ss(d, a2, b0, idesc, ks > it.ks0 ? 1u : 0u);
-          tcg_mma_ss(d, a0, b2, idesc, 1u);
-          tcg_mma_ss(d, a1, b1, idesc, 1u);
-          tcg_mma_ss(d, a1, b0, idesc, 1u);
-          tcg_mma_ss(d, a0, b1, idesc, 1u);
-          tcg_mma_ss(d, a0, b0, idesc, 1u);
-          tcg_commit(&free_[s]);
+          tc_mma_ss(d, a2, b0, idesc, ks > it.ks0 ? 1u : 0u);
+          tc_mma_ss(d, a0, b2, idesc, 1u);
+          tc_mma_ss(d, a1, b1, idesc, 1u);
+          tc_mma_ss(d, a1, b0, idesc, 1u);
+          tc_mma_ss(d, a0, b1, idesc, 1u);
+          tc_mma_ss(d, a0, b0, idesc, 1u);
+          tc_commit(&free_[s]);
         }
         __syncwarp();
       }
-      if (tcg_elect_one()) tcg_commit(&acc_full[set]);
+      if (elect_one()) tc_commit(&acc_full[set]);
       __syncwarp();
     }
   }
   __syncwarp();
-  tcg_fence_before();
+  tc_fence_before();
   __syncthreads();
   if (warp == 5) {
     __syncwarp();
