@@ -34,6 +34,7 @@ step 300 r2_dense_tc.log env GCNB_TEST_DENSE_TC=1 python -m pytest tests/test_zz
 step 300 r2_dense_tc_probe.log python scripts/probe_dense_tc.py --out gpurun_out/r2_probe_dense_tc.jsonl
 step 600 r2_configs_default.log python scripts/bench_configs.py
 step 600 r2_configs_dense_tc.log env GCNB_DENSE_TC=1 python scripts/bench_configs.py
+step 600 r2_configs_dense_tc_bittile.log env GCNB_DENSE_TC=1 GCNB_BITTILE=1 python scripts/bench_configs.py
 # 5. bench lines: default, background staging, bit tiles (+ the best shape from step 3 through GCNB_BT_CHUNK / GCNB_BT_RB)
 step 300 r2_bench_default.log python bench.py --no-cpu-baseline
 step 300 r2_bench_async.log env GCNB_ASYNC_STAGE=1 python bench.py --no-cpu-baseline
