@@ -149,3 +149,81 @@ def test_weight_gradient_images_and_split_k():
     for k_slices in (1, 5, 63):
         got = _gemm_emulated(a_img, b_img, f_pad, KS, n_parts, pcols, k_slices)[:f, :p]
         assert_close(got, want, what="X^T dH, %d k slices" % k_slices)
+
+
+# ---- mbarrier protocol of tc_gemm_kernel, simulated (same model as tests/test_bittile_cpu.py: parity-only waits, delayed
+# ---- commits in issue order, bulk copies landing out of order, random interleaving of the roles)
+def test_gemm_barrier_protocol_simulation():
+    from tests.test_bittile_cpu import _Bar
+    rng = np.random.default_rng(4)
+    stages = 4
+    for items in ([1], [3, 1], [38, 38, 38], [5, 9, 2, 7, 1, 1, 12], list(rng.integers(1, 20, 9))):
+        for _ in range(3):
+            full, free = [_Bar(1) for _ in range(stages)], [_Bar(1) for _ in range(stages)]
+            acc_full, acc_empty = [_Bar(1), _Bar(1)], [_Bar(4), _Bar(4)]
+            stage, acc_owner, events, copies = [None] * stages, [None, None], [], []
+            T = int(sum(items))
+
+            def producer():
+                for t in range(T):
+                    s, use = t % stages, t // stages
+                    if use > 0:
+                        while not free[s].passed((use - 1) & 1):
+                            yield
+                    full[s].arrive(tx=2)          # arrive.expect_tx, then two bulk copies (A tiles, B tiles)
+                    copies.append((s, t, "a"))
+                    copies.append((s, t, "b"))
+                    yield
+
+            def mma():
+                t = 0
+                for k, n in enumerate(items):
+                    st, use = k & 1, k >> 1
+                    if use > 0:
+                        while not acc_empty[st].passed((use - 1) & 1):
+                            yield
+                    acc_owner[st] = k
+                    for _ in range(int(n)):
+                        s, u = t % stages, t // stages
+                        while not full[s].passed(u & 1):
+                            yield
+                        assert stage[s] == {"a": t, "b": t}, (stage[s], t)
+                        events.append(free[s])
+                        t += 1
+                        yield
+                    events.append(acc_full[st])
+                    yield
+
+            def epilogue():
+                for k in range(len(items)):
+                    st, use = k & 1, k >> 1
+                    while not acc_full[st].passed(use & 1):
+                        yield
+                    assert acc_owner[st] == k
+                    acc_empty[st].arrive()
+                    yield
+
+            agents = [producer(), mma()] + [epilogue() for _ in range(4)]
+            alive = list(range(len(agents)))
+            steps = 0
+            while alive or events or copies:
+                steps += 1
+                assert steps < 2000 * (T + 10), "deadlock"
+                r = rng.random()
+                if events and r < 0.15:
+                    events.pop(0).arrive()
+                    continue
+                if copies and r < 0.35:
+                    s, t, which = copies.pop(int(rng.integers(0, len(copies))))
+                    if stage[s] is None or stage[s].get(which) is not None and stage[s].get("a") == stage[s].get("b") and stage[s]["a"] != t:
+                        stage[s] = {}
+                    stage[s] = dict(stage[s] or {}, **{which: t})
+                    full[s].complete_tx(1)
+                    continue
+                if not alive:
+                    continue
+                i = alive[int(rng.integers(0, len(alive)))]
+                try:
+                    next(agents[i])
+                except StopIteration:
+                    alive.remove(i)
