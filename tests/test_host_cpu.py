@@ -111,6 +111,71 @@ def test_parser_edge_cases(O, eng, tmp_path):
     assert (nf.f_value == 1.0).all()
 
 
+# ---- randomised parser parity: product parser == oracle parser == the reference's OWN parser on ragged files ----
+def fmt_float(rng, x):
+    k = rng.integers(0, 7)
+    if k == 0: return "%g" % x
+    if k == 1: return "%.6f" % x
+    if k == 2: return "%e" % x
+    if k == 3: return ("+%g" % abs(x))
+    if k == 4: return "%d" % int(round(x))
+    if k == 5: return ("%.3f" % x).lstrip("0") if 0 < x < 1 else "%g" % x   # ".5"
+    return "%d." % int(round(x))                                               # "3."
+
+def make(rng, d, name, n):
+    sep = lambda: " " * int(rng.integers(1, 3))
+    eol = lambda: "\r\n" if rng.random() < 0.1 else "\n"
+    g, s, v = [], [], []
+    for i in range(n):
+        deg = int(rng.integers(0, 6))
+        nb = [str(int(rng.integers(0, n))) for _ in range(deg)]
+        if rng.random() < 0.2 and nb: nb.append(nb[0])          # duplicate neighbour
+        if rng.random() < 0.2: nb.append(str(i))               # explicit self entry
+        g.append(sep().join(nb) + (" " if rng.random() < 0.2 else "") + eol())
+        if rng.random() < 0.1:
+            v.append(eol())                                     # blank svmlight line: label -1
+        else:
+            k = int(rng.integers(0, 5))
+            idx = sorted(set(int(x) for x in rng.integers(0, 12, k)))
+            feats = ["%d:%s" % (j, fmt_float(rng, float(rng.normal()) * 10 ** int(rng.integers(-3, 3)))) for j in idx]
+            v.append(sep().join([str(int(rng.integers(0, 4)))] + feats) + eol())
+        s.append(str(int(rng.integers(1, 4))) + eol())
+    if rng.random() < 0.3:                                      # unterminated last line
+        g[-1] = g[-1].rstrip("\r\n"); v[-1] = v[-1].rstrip("\r\n"); s[-1] = s[-1].rstrip("\r\n")
+    open(os.path.join(d, name + ".graph"), "w", newline="").write("".join(g))
+    open(os.path.join(d, name + ".svmlight"), "w", newline="").write("".join(v))
+    open(os.path.join(d, name + ".split"), "w", newline="").write("".join(s))
+
+
+
+def test_parser_matches_reference_on_random_ragged_files(O, eng, tmp_path):
+    """60 seeded random datasets with the quirks real files have: empty neighbour lists, duplicate neighbours, explicit self
+    entries, blank svmlight lines (label -1), CRLF line ends, trailing blanks, unterminated last lines, numbers written as
+    1e-3 / +2.5 / .5 / 3. / integers.  Every array must equal the reference parser's bit for bit (and the oracle's)."""
+    for seed in range(60):
+        rng = np.random.default_rng(seed)
+        root = tmp_path / ("s%d" % seed)
+        d = root / "data"
+        d.mkdir(parents=True)
+        make(rng, str(d), "t", int(rng.integers(1, 12)))
+        mine = eng.parse_dataset(str(root), "t")
+        orc = O.parse_dataset(str(d / "t"))
+        assert (mine is None) == (orc is None), seed
+        if mine is None:
+            continue
+        for k in ("g_indptr", "g_indices", "f_indptr", "f_indices", "label", "split"):
+            assert (getattr(mine, k) == getattr(orc, k)).all(), (seed, k)
+        assert (mine.f_value.view(u32) == orc.f_value.view(u32)).all(), seed
+        assert (mine.input_dim, mine.output_dim) == (orc.input_dim, orc.output_dim), seed
+        if O.ref is not None:
+            _, rds = O.ref_parse_dataset(str(root), "t")
+            assert rds is not None, seed
+            for k in ("g_indptr", "g_indices", "f_indptr", "f_indices", "label", "split"):
+                a, b = getattr(mine, k), getattr(rds, k)
+                assert a.shape == b.shape and (a.view(i32) == b).all(), (seed, k)
+            assert (mine.f_value.view(u32) == rds.f_value.view(u32)).all(), seed
+
+
 def test_oracle_pinned_to_reference_cpu(O, datasets):
     """the C restatement reproduces the reference's own CPU implementation bit for bit: 3 epochs of losses, accuracies
     and both weight matrices (needs oracle/_ref, i.e. /root/reference at build time)."""
