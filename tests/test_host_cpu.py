@@ -128,9 +128,9 @@ def make(rng, d, name, n):
     g, s, v = [], [], []
     for i in range(n):
         deg = int(rng.integers(0, 6))
-        nb = [str(int(rng.integers(0, n))) for _ in range(deg)]
+        nb = [str(int(rng.integers(0, max(1, n - 1)))) for _ in range(deg)]  # valid even if the last line is dropped
         if rng.random() < 0.2 and nb: nb.append(nb[0])          # duplicate neighbour
-        if rng.random() < 0.2: nb.append(str(i))               # explicit self entry
+        if rng.random() < 0.2 and i < n - 1: nb.append(str(i))  # explicit self entry
         g.append(sep().join(nb) + (" " if rng.random() < 0.2 else "") + eol())
         if rng.random() < 0.1:
             v.append(eol())                                     # blank svmlight line: label -1
@@ -200,6 +200,48 @@ def test_oracle_pinned_to_reference_cpu(O, datasets):
             assert (w.view(u32) == og.W[l].view(u32)).all()
         O.ref.ref_gcn_free(g)
         O.ref.ref_dataset_free(h)
+
+
+def test_oracle_pinned_to_reference_cpu_on_random_ragged_datasets(O, tmp_path):
+    """beyond cora / citeseer: 30 seeded random datasets (directed graphs with duplicate and self entries, isolated nodes,
+    unlabelled nodes, rows without features, feature magnitudes over five decades) trained for 3 epochs by the reference's
+    own CPU code and by the restatement -- every loss, accuracy and weight bit must agree."""
+    if O.ref is None:
+        pytest.skip("oracle/_ref not built (no /root/reference on this box)")
+    trained = 0
+    for seed in range(30):
+        rng = np.random.default_rng(1000 + seed)
+        root = tmp_path / ("r%d" % seed)
+        d = root / "data"
+        d.mkdir(parents=True)
+        make(rng, str(d), "t", int(rng.integers(6, 40)))
+        ds = O.parse_dataset(str(d / "t"))
+        res = O.ref_parse_dataset(str(root), "t")
+        if ds is None or res is None or res[1] is None:
+            continue
+        h = res[0]
+        if not all(((ds.split == k) & (ds.label >= 0)).sum() > 0 for k in (1, 2)):
+            O.ref.ref_dataset_free(h)
+            continue
+        trained += 1
+        O.ref.ref_srand(1)
+        g = O.ref.ref_gcn_create(h, 16, 0.5, 0.01, 5e-4, 100, 0)
+        O.lib.orc_libc_srand(1)
+        og = O.OracleGCN(ds, flavour="ref_cpu")
+        out = np.zeros(2, f32)
+        for ep in range(3):
+            O.ref.ref_gcn_train_epoch(g, O._p(out)); rt = tuple(out)
+            O.ref.ref_gcn_eval(g, 2, O._p(out)); rv = tuple(out)
+            ot, ov = og.train_epoch(), og.eval(2)
+            a, b = np.array([ot[0], ot[1], ov[0], ov[1]], f32), np.array([rt[0], rt[1], rv[0], rv[1]], f32)
+            assert (a.view(u32) == b.view(u32)).all(), (seed, ep, a, b)
+        for idx, l in ((2, 0), (5, 1)):
+            w = np.empty(og.W[l].size, f32)
+            O.ref.ref_gcn_variable_get(g, idx, 0, O._p(w))
+            assert (w.view(u32) == og.W[l].view(u32)).all(), (seed, l)
+        O.ref.ref_gcn_free(g)
+        O.ref.ref_dataset_free(h)
+    assert trained >= 20
 
 
 def test_oracle_against_golden_training_curves(O, datasets):
