@@ -29,6 +29,7 @@ step 120 r2_bt_g1_rb2.log python scripts/probe_bittile.py --stage graph --scale 
 step 120 r2_bt_g1_rb2_cap2.log env GCNB_BT_REM_CTAS=2 python scripts/probe_bittile.py --stage graph --scale 1 --iters 10 --staged 0 --rb 2 --out gpurun_out/r2_probe.jsonl
 # 4. engine paths: bit tiles in the engine, background staging
 step 300 r2_engine_optin.log env GCNB_TEST_BITTILE_ENGINE=1 GCNB_TEST_ASYNC_STAGE=1 python -m pytest tests/test_zz_bittile_gpu.py -m gpu -x -q -k "engine or background"
+step 300 r2_ragged_engine.log env GCNB_TEST_RAGGED_ENGINE=1 python -m pytest tests/test_zz_bittile_gpu.py -m gpu -x -q -k ragged
 # 4b. exact-split tcgen05 GEMM for the wide first layer (csrc/dense_tc.cu)
 step 300 r2_dense_tc.log env GCNB_TEST_DENSE_TC=1 python -m pytest tests/test_zz_bittile_gpu.py -m gpu -x -q -k exact_split
 step 300 r2_dense_tc_probe.log python scripts/probe_dense_tc.py --out gpurun_out/r2_probe_dense_tc.jsonl

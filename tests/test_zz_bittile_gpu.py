@@ -267,3 +267,47 @@ def test_exact_split_weight_gradient_matches_float64(gcnb, dev, n, f, p):
     dW2 = torch.empty_like(dW)
     gcnb.dense_tc_tn(img, d_dH, dW2, n, f, p)
     assert torch.equal(dW, dW2)
+
+
+# ---- engine parity on random ragged SYMMETRIC datasets (duplicate edges, explicit self entries, isolated and unlabelled
+# ---- nodes, rows without features): opt-in (GCNB_TEST_RAGGED_ENGINE=1) until it has been run once on a GPU
+@pytest.mark.skipif(os.environ.get("GCNB_TEST_RAGGED_ENGINE") != "1", reason="opt-in: new inputs for the engine, not yet run")
+def test_engine_matches_oracle_on_random_ragged_symmetric_datasets(O, gcnb, dev, tmp_path):
+    import importlib
+    eng = importlib.import_module("parallel_gcn_b200.engine")
+    from tests.test_engine_gpu import _run_pair
+    for seed in range(12):
+        rng = np.random.default_rng(500 + seed)
+        n = int(rng.integers(8, 200))
+        rows = [[] for _ in range(n)]
+        for _ in range(int(rng.integers(0, 4 * n))):
+            i, j = int(rng.integers(0, n)), int(rng.integers(0, n))
+            m = 2 if rng.random() < 0.1 else 1            # duplicate edges, both directions
+            for _ in range(m):
+                rows[i].append(j)
+                if i != j:
+                    rows[j].append(i)                      # i == j: an explicit self entry (listed once)
+        root = tmp_path / ("g%d" % seed)
+        d = root / "data"
+        d.mkdir(parents=True)
+        (d / "t.graph").write_text("".join(" ".join(map(str, r)) + "\n" for r in rows))
+        lines = []
+        for i in range(n):
+            if rng.random() < 0.1:
+                lines.append("\n")                         # unlabelled node without features
+                continue
+            idx = sorted(set(int(x) for x in rng.integers(0, 20, int(rng.integers(0, 6)))))
+            lines.append(" ".join([str(int(rng.integers(0, 5)))] + ["%d:%g" % (k, rng.normal()) for k in idx]) + "\n")
+        (d / "t.svmlight").write_text("".join(lines))
+        (d / "t.split").write_text("".join("%d\n" % int(rng.integers(1, 4)) for _ in range(n)))
+        ds_e = eng.parse_dataset(str(root), "t")
+        ds_o = O.parse_dataset(str(d / "t"))
+        if ds_e is None or not all(((ds_o.split == k) & (ds_o.label >= 0)).sum() > 0 for k in (1, 2, 3)):
+            continue
+        og, g, hist = _run_pair(O, eng, ds_o, ds_e, 3)
+        for ep, (to, te, vo, ve) in enumerate(hist):
+            assert abs(te[0] - to[0]) <= 2e-5 * (1 + ep) * abs(to[0]) and abs(ve[0] - vo[0]) <= 2e-5 * (1 + ep) * abs(vo[0]), (seed, ep)
+            assert abs(te[1] - to[1]) < 1e-6 and abs(ve[1] - vo[1]) < 1e-6, (seed, ep)
+        for l in range(2):
+            assert_close(g.weight(l), og.W[l], rtol=1e-4, atol=1e-6, what="weights, dataset %d" % seed)
+        g.close()
