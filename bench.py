@@ -100,10 +100,19 @@ class ClockSampler:
                 "samples": len(self.sm)}
 
 
-def make_dataset(eng, scale=1, pinned=True):
+def synth_module():
+    """the workload generator alone (parallel-gcn_b200/synth.py -> libgcn_synth.so: host C++, nothing of the product's
+    compute), so the CPU legs never map libgcn_b200.so"""
+    import __graft_entry__ as ge
+    ge.load_package()
+    return importlib.import_module("parallel_gcn_b200.synth")
+
+
+def make_dataset(gen, scale=1, pinned=True, shuffle_ids=False):
+    """gen: any module exposing synth_dataset (engine.py or synth.py)"""
     w = workload_config(scale)
     t0 = time.time()
-    ds = eng.synth_dataset(w["n"], w["m"], w["f"], w["c"], n_blocks=w["blocks"], intra=w["intra"], sigma=w["sigma"],
+    ds = gen.synth_dataset(w["n"], w["m"], w["f"], w["c"], n_blocks=w["blocks"], intra=w["intra"], sigma=w["sigma"],
                            max_deg=w["max_deg"], seed=w["seed"], pinned=pinned)
     return ds, w, time.time() - t0
 
@@ -114,60 +123,92 @@ def graphsum_alg_bytes(n, nnz, d):
 
 
 # ------------------------------------------------------------------------------------------------------------------
-def cpu_reference_step_ms(steps, warmup, scale):
-    """The reference's own CPU implementation (oracle/_ref = hpdga-spring23 compiled in place) on a 1/scale Reddit-shape
-    sample; falls back to the oracle port when _ref did not travel.  Returns (ms per full-size step, kind, sample, cores)."""
-    import __graft_entry__ as ge
-    ge.load_package()
-    eng = importlib.import_module("parallel_gcn_b200.engine")  # generator only (host code)
+def cpu_reference_step_ms(steps, warmup, scale=1, budget_s=None):
+    """The reference's own CPU implementation (oracle/_ref = hpdga-spring23 compiled in place, sequential as the
+    reference is) on the bench graph itself (scale 1: the same generator call as the GPU arm, same seed => the same
+    dataset); falls back to the oracle port when _ref did not travel.  One step = train_epoch + eval(2), exactly the GPU
+    arm's step.  budget_s bounds the wall clock: when the projected total exceeds it the remaining steps are dropped
+    and the returned count says how many were timed.
+    Returns (ms per step, kind, sample text, cores, timed steps, warm-up steps run)."""
+    gen = synth_module()
     from oracle import oracle as O
-    ds, w, _ = make_dataset(eng, scale, pinned=False)
-    sample = ("1/%d-scale Reddit-shape graph from the same generator (%d nodes, %d CSR entries, %d dense features, %d "
-              "classes), one train epoch + validation forward per step, time x%d (linear in nnz and N*F; small-graph "
-              "cache residency makes this favour the CPU)" % (scale, ds.num_nodes, len(ds.g_indices), w["f"], w["c"], scale))
+    ds, w, gen_s = make_dataset(gen, scale, pinned=False)
+    sample = ("%s Reddit-shape bench graph (%d nodes, %d CSR entries, %d dense features, %d classes; same generator and "
+              "seed as the GPU arm), one train epoch + validation forward per step" %
+              ("the full-size" if scale == 1 else "1/%d-scale" % scale, ds.num_nodes, len(ds.g_indices), w["f"], w["c"]))
     ods = O.Dataset(g_indptr=ds.g_indptr, g_indices=ds.g_indices, f_indptr=ds.f_indptr, f_indices=ds.f_indices,
                     f_value=ds.f_value, label=ds.label, split=ds.split, input_dim=w["f"], output_dim=w["c"])
-    times = []
+    times, t_start, warm_run = [], time.perf_counter(), 0
     if O.ref is not None:
         kind = "reference"
         h = O.ref_dataset_from(ods)
+        del ds
         O.ref.ref_srand(1)
         g = O.ref.ref_gcn_create(h, MODEL["hidden"][0], MODEL["dropouts"][0], MODEL["lr"], MODEL["weight_decay"], 100, 0)
         out = np.zeros(2, np.float32)
-        for i in range(warmup + steps):
-            t0 = time.perf_counter()
+
+        def step():
             O.ref.ref_gcn_train_epoch(g, O._p(out))
             O.ref.ref_gcn_eval(g, 2, O._p(out))
-            if i >= warmup:
-                times.append(time.perf_counter() - t0)
-        O.ref.ref_gcn_free(g)
-        O.ref.ref_dataset_free(h)
+
+        def done():
+            O.ref.ref_gcn_free(g)
+            O.ref.ref_dataset_free(h)
     else:
         kind = "port"
         og = O.OracleGCN(ods, hidden_dims=MODEL["hidden"], dropouts=MODEL["dropouts"], flavour="ref_cpu", libc_seed=1)
-        for i in range(warmup + steps):
-            t0 = time.perf_counter()
+
+        def step():
             og.train_epoch()
             og.eval(2)
-            if i >= warmup:
-                times.append(time.perf_counter() - t0)
-    return float(np.mean(times)) * 1e3 * scale, kind, sample, 1
+
+        def done():
+            pass
+    n_warm, n_timed, i = warmup, steps, 0
+    while i < n_warm + n_timed:
+        t0 = time.perf_counter()
+        step()
+        dt = time.perf_counter() - t0
+        if i >= n_warm:
+            times.append(dt)
+        else:
+            warm_run += 1
+        i += 1
+        if budget_s is not None and i == 1:
+            # plan the rest against the budget: warm-up steps go first (one is kept when any was asked for, so that
+            # first-touch page faults stay outside the timing), then timed steps (at least one)
+            room = int(max(0.0, budget_s - (time.perf_counter() - t_start)) / dt)
+            done_w, done_t = warm_run, len(times)
+            n_timed = max(1, min(steps, done_t + room))
+            n_warm = done_w + max(0, min(warmup - done_w, room - (n_timed - done_t)))
+    done()
+    return float(np.mean(times)) * 1e3, kind, sample, 1, len(times), warm_run
 
 
 def run_reference(args, rank, world):
+    """--impl reference: the reference's own sequential CPU implementation on the SAME full-size workload, the steps
+    the caller asked for (rank 0 only; the other ranks of a torchrun launch exit at once)."""
     if rank != 0:
         return
-    scale = 16
-    ms, kind, sample, cores = cpu_reference_step_ms(args.steps, args.warmup, scale)
-    w = workload_config(1)
-    line = {"impl": "reference", "metric": METRIC, "value": ms, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
+    budget = float(os.environ.get("GCNB_REF_BUDGET_S", "1500"))
+    # a CPU epoch costs the same whether it is called warm-up or not; when the budget cannot hold W + K full-size steps
+    # the warm-up is the first thing to go (one step is kept so that first-touch page faults stay outside the timing)
+    ms, kind, sample, cores, timed, warm = cpu_reference_step_ms(args.steps, args.warmup, args.scale, budget_s=budget)
+    w = workload_config(args.scale)
+    line = {"impl": "reference", "metric": METRIC, "value": ms, "unit": UNIT, "n_gpus": args.gpus, "steps": timed,
+            "warmup": warm, "ms_per_step": ms, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "same_config": args.scale == 1, "extrapolated": False,
+            "reference_kind": "cpu (hpdga-spring23, sequential)", "steps_requested": args.steps,
+            "warmup_requested": args.warmup,
             "config": {"workload": "reddit_shape_synthetic n=%d nnz=%d f=%d c=%d; 2-layer GCN hidden 16 dropout 0.5/0.5 Adam; "
                                    "step = train_epoch + eval(2)" % (w["n"], 2 * w["m"] + w["n"], w["f"], w["c"]),
-                       "host_cpu": cpu_name(), "host_cores_total": os.cpu_count()},
+                       "scale": args.scale, "host_cpu": cpu_name(), "host_cores_total": os.cpu_count(),
+                       "budget_s": budget},
             "cpu_baseline": {"value": ms, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": ms, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if timed < args.steps:
+        line["note"] = ("%d of the %d requested steps timed: the wall-clock budget of %.0f s (GCNB_REF_BUDGET_S) was "
+                        "reached; every CPU step does identical work" % (timed, args.steps, budget))
     print(json.dumps(line), flush=True)
 
 
@@ -268,8 +309,8 @@ def run_ours(args, rank, world, local_rank):
             "clocks": clk, "e2e": e2e, "gpu_launches": r["launches"], "roofline": roofline}
     g.close()
     if not args.no_cpu_baseline:
-        ms, kind, sample, cores = cpu_reference_step_ms(2, 0, 16)
-        line["cpu_baseline"] = {"value": ms, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
+        ms, kind, sample, cores, timed, _ = cpu_reference_step_ms(1, 0, 1)
+        line["cpu_baseline"] = {"value": ms, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample + " (1 step)",
                                 "host_cpu": cpu_name(), "host_cores_total": os.cpu_count()}
     print(json.dumps(line), flush=True)
 

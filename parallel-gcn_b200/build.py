@@ -9,6 +9,8 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "libgcn_b200.so")
+SYNTH_LIB = os.path.join(HERE, "libgcn_synth.so")  # the synthetic-workload generator alone (host C++, no CUDA): synth.py
+SYNTH_SRC = os.path.join(HERE, "host", "src", "synth.cpp")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ARCH + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread"]
 # kernels + C ABI: only the GCNB_API symbols are exported
@@ -35,7 +37,16 @@ def stale():
     return any(os.path.getmtime(f) > t for f in sources() + headers() + [os.path.abspath(__file__)])
 
 
+def build_synth(force=False):
+    deps = [SYNTH_SRC, os.path.join(os.path.dirname(HERE), "include", "gcnb_engine.h")]
+    if force or not os.path.exists(SYNTH_LIB) or any(os.path.getmtime(d) > os.path.getmtime(SYNTH_LIB) for d in deps):
+        subprocess.check_call([os.environ.get("CXX", "g++"), "-O3", "-std=c++17", "-fPIC", "-shared", "-pthread",
+                               "-fvisibility=hidden", "-o", SYNTH_LIB, SYNTH_SRC])
+    return SYNTH_LIB
+
+
 def build(force=False, verbose=False):
+    build_synth(force)
     if not force and not stale():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
