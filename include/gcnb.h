@@ -136,8 +136,8 @@ GCNB_API int gcnb_bittile_plan_create(const uint32_t *h_indptr, const uint32_t *
                                       int row_blocks /*0 = 1; 2 = items of 256 rows (chunk 64 only)*/, gcnb_stream_t stream,
                                       gcnb_bittile_plan **out);
 GCNB_API int gcnb_bittile_plan_destroy(gcnb_bittile_plan *plan);
-/* out = {tiles, entries in tiles, remainder entries, items' row blocks, columns per tile + 1000 * row_blocks, CTAs,
- * bit-map bytes, packed-B bytes} */
+/* out = {tiles, entries in tiles, remainder entries, items' row blocks, columns per tile + 1000 * row_blocks
+ * (+ 100000 when the remainder runs on the pattern-only ELL kernel below), CTAs, bit-map bytes, packed-B bytes} */
 GCNB_API int gcnb_bittile_plan_info(const gcnb_bittile_plan *plan, int64_t out[8]);
 GCNB_API int gcnb_bittile_spmm16_f32(gcnb_bittile_plan *plan, const float *d_B, float *d_C, gcnb_stream_t stream);
 /* Routes later gcnb_spmm_f32 / gcnb_spmm_ld_f32 calls on `plan` that use exactly this d_values pointer, no permutation,
@@ -155,7 +155,7 @@ GCNB_API int gcnb_bittile_debug_pack(gcnb_bittile_plan *plan, const float *d_B, 
                                      gcnb_stream_t stream);
 /* The builder on its own, host memory only, no CUDA call (tests/test_bittile_cpu.py consumes the arrays exactly as the
  * kernel does).  sizes: {n_rows, n_cols, nnz, blocks of 128 * row_blocks rows, tiles, entries in tiles, items, CTAs, columns per tile,
- * row_blocks}; copy: which = 0
+ * row_blocks, remainder entries that do not factor, remainder entries}; copy: which = 0
  * tile_chunk, 1 bits (uint64 x row_blocks x 128 x columns/64 per tile), 2 cta_tile_ptr, 3 cta_item_ptr, 4 items (uint32 x 2), 5 r_indptr,
  * 6 r_indices, 7 r_values, 8 row_scale, 9 col_scale (layouts: BitTileHost in spmm_bittile.cu). */
 typedef struct gcnb_bittile_host gcnb_bittile_host;
@@ -163,9 +163,30 @@ GCNB_API int gcnb_bittile_host_build(const uint32_t *h_indptr, const uint32_t *h
                                      int64_t n_rows, int64_t n_cols, const float *h_row_scale, const float *h_col_scale,
                                      int min_tile_nnz, int chunk_cols /*0 = 64*/, int row_blocks /*0 = 1*/,
                                      int n_cta /*0 = 148*/, int n_threads /*0 = auto*/, gcnb_bittile_host **out);
-GCNB_API int gcnb_bittile_host_sizes(const gcnb_bittile_host *h, int64_t out[10]);
+GCNB_API int gcnb_bittile_host_sizes(const gcnb_bittile_host *h, int64_t out[12]);
 GCNB_API int gcnb_bittile_host_copy(const gcnb_bittile_host *h, int which, void *dst, int64_t bytes);
 GCNB_API int gcnb_bittile_host_destroy(gcnb_bittile_host *h);
+
+/* Pattern-only row gather at width 16 (csrc/spmm_ell.cu): R[i][:] = row_scale[i] * sum over the CSR entries (i, j) of
+ * B2[j][:].  The remainder kernel of a bit-tile plan whose entries all factor (value = row_scale * col_scale): the pack
+ * kernel writes B2 = diag(col_scale) * B once per launch, so entries carry no value.  Replaces the part of
+ * graphsum_kernel (src/module.cu:172-186) the tensor-core tiles do not cover.  d_B2 holds n_cols + 1 rows of 16
+ * floats, the LAST ONE ALL ZERO (padding entries point at it).  Deterministic (fixed summation order).
+ * gcnb_ell_host_*: the host builder alone, for CPU tests that consume the arrays as the kernel does;
+ *   sizes: {rows, cols, entries, bundles, index words, split rows, partial slots, wide-bundle minimum length}
+ *   copy which: 0 idx (uint32), 1 off (bundles + 1), 2 steps, 3 rows (bundles x 8), 4 split_row, 5 split_ptr */
+typedef struct gcnb_ell_host gcnb_ell_host;
+typedef struct gcnb_ell_plan gcnb_ell_plan;
+GCNB_API int gcnb_ell_host_build(const uint32_t *h_indptr, const uint32_t *h_indices, int64_t n_rows, int64_t n_cols,
+                                 int n_threads, gcnb_ell_host **out);
+GCNB_API int gcnb_ell_host_sizes(const gcnb_ell_host *h, int64_t out[8]);
+GCNB_API int gcnb_ell_host_copy(const gcnb_ell_host *h, int which, void *dst, int64_t bytes);
+GCNB_API int gcnb_ell_host_destroy(gcnb_ell_host *h);
+GCNB_API int gcnb_ell_plan_create(const uint32_t *h_indptr, const uint32_t *h_indices, int64_t n_rows, int64_t n_cols,
+                                  gcnb_stream_t stream, gcnb_ell_plan **out);
+GCNB_API int gcnb_ell_plan_destroy(gcnb_ell_plan *plan);
+GCNB_API int gcnb_ell_gather16_f32(gcnb_ell_plan *plan, const float *d_B2, const float *d_row_scale, float *d_R,
+                                   gcnb_stream_t stream);
 
 /* C[n_rows x dim] = A_csr * B[n_cols x dim],  A_csr values = d_values[e] (or d_values[d_perm[e]] if d_perm).
  *   GraphSum::forward/backward + graphsum_kernel            src/module.cu:172-210  (values = graph_value)

@@ -72,6 +72,13 @@ _sig("gcnb_bittile_host_build", I32, [P, P, P, I64, I64, P, P, I32, I32, I32, I3
 _sig("gcnb_bittile_host_sizes", I32, [P, P])
 _sig("gcnb_bittile_host_copy", I32, [P, I32, P, I64])
 _sig("gcnb_bittile_host_destroy", I32, [P])
+_sig("gcnb_ell_host_build", I32, [P, P, I64, I64, I32, P])
+_sig("gcnb_ell_host_sizes", I32, [P, P])
+_sig("gcnb_ell_host_copy", I32, [P, I32, P, I64])
+_sig("gcnb_ell_host_destroy", I32, [P])
+_sig("gcnb_ell_plan_create", I32, [P, P, I64, I64, P, P])
+_sig("gcnb_ell_plan_destroy", I32, [P])
+_sig("gcnb_ell_gather16_f32", I32, [P, P, P, P, P])
 _sig("gcnb_csc_create", I32, [P, P, I64, I64, P, P])
 _sig("gcnb_csc_destroy", I32, [P])
 _sig("gcnb_csc_arrays", I32, [P, P, P, P, P])
@@ -289,9 +296,10 @@ def bittile_host_build(indptr, indices, values, n_cols, row_scale=None, col_scal
     check(lib.gcnb_bittile_host_build(_np_ptr(indptr), _np_ptr(indices), _np_ptr(values), len(indptr) - 1, int(n_cols),
                                       _np_ptr(rs), _np_ptr(cs), min_tile_nnz, chunk_cols, row_blocks, n_cta, n_threads, C.byref(h)))
     try:
-        sz = (I64 * 10)()
+        sz = (I64 * 12)()
         check(lib.gcnb_bittile_host_sizes(h, sz))
-        keys = ("n_rows", "n_cols", "nnz", "n_blk", "n_tiles", "tile_nnz", "n_items", "n_cta", "chunk", "rb")
+        keys = ("n_rows", "n_cols", "nnz", "n_blk", "n_tiles", "tile_nnz", "n_items", "n_cta", "chunk", "rb", "n_unfactored",
+                "rem_nnz")
         out = dict(zip(keys, [int(x) for x in sz]))
 
         def grab(which, n, dtype):
@@ -316,6 +324,60 @@ def bittile_host_build(indptr, indices, values, n_cols, row_scale=None, col_scal
         lib.gcnb_bittile_host_destroy(h)
 
 
+def ell_host_build(indptr, indices, n_cols, n_threads=0):
+    """Host-only run of the pattern-only ELL builder (EllHost, csrc/spmm_ell.cu): plan arrays as numpy."""
+    import numpy as np
+    indptr = np.ascontiguousarray(indptr, np.uint32)
+    indices = np.ascontiguousarray(indices, np.uint32)
+    h = P()
+    check(lib.gcnb_ell_host_build(_np_ptr(indptr), _np_ptr(indices), len(indptr) - 1, int(n_cols), n_threads, C.byref(h)))
+    try:
+        sz = (I64 * 8)()
+        check(lib.gcnb_ell_host_sizes(h, sz))
+        keys = ("n_rows", "n_cols", "nnz", "n_bundles", "idx_words", "n_split", "n_slots", "wide_min")
+        out = dict(zip(keys, [int(x) for x in sz]))
+
+        def grab(which, count):
+            a = np.zeros(count, np.uint32)
+            if count:
+                check(lib.gcnb_ell_host_copy(h, which, a.ctypes.data_as(C.c_void_p), a.nbytes))
+            return a
+        out["idx"] = grab(0, out["idx_words"])
+        out["off"] = grab(1, out["n_bundles"] + 1)
+        out["steps"] = grab(2, out["n_bundles"])
+        out["rows"] = grab(3, out["n_bundles"] * 8)
+        out["split_row"] = grab(4, out["n_split"])
+        out["split_ptr"] = grab(5, out["n_split"] + 1)
+        return out
+    finally:
+        lib.gcnb_ell_host_destroy(h)
+
+
+class EllPlan:
+    """gcnb_ell_plan: R = diag(row_scale) * pattern * B2 at width 16 (host numpy CSR pattern in, device plan)."""
+
+    def __init__(self, indptr, indices, n_cols):
+        import numpy as np
+        indptr = np.ascontiguousarray(indptr, np.uint32)
+        indices = np.ascontiguousarray(indices, np.uint32)
+        self.n_rows, self.n_cols = len(indptr) - 1, int(n_cols)
+        h = P()
+        check(lib.gcnb_ell_plan_create(_np_ptr(indptr), _np_ptr(indices), self.n_rows, self.n_cols, stream(), C.byref(h)))
+        self.h = h
+
+    def gather16(self, B2, row_scale, R_out):
+        """B2: (n_cols + 1) x 16 device tensor whose last row is zero"""
+        check(lib.gcnb_ell_gather16_f32(self.h, ptr(B2), ptr(row_scale), ptr(R_out), stream()))
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib.gcnb_ell_plan_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+
 class BitTilePlan:
     """gcnb_bittile_plan: tensor-core GraphSum on 128 x 64 bit-map tiles + remainder CSR (host numpy CSR in, device plan)."""
 
@@ -336,7 +398,7 @@ class BitTilePlan:
         check(lib.gcnb_bittile_plan_info(self.h, out))
         keys = ("n_tiles", "tile_nnz", "rem_nnz", "n_blk", "chunk", "n_cta", "bitmap_bytes", "packed_bytes")
         d = dict(zip(keys, [int(x) for x in out]))
-        d["rb"], d["chunk"] = d["chunk"] // 1000, d["chunk"] % 1000
+        d["ell"], d["rb"], d["chunk"] = d["chunk"] // 100000, (d["chunk"] // 1000) % 100, d["chunk"] % 1000
         return d
 
     def spmm16(self, B, C_out):

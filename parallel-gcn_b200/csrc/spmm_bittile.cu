@@ -87,6 +87,7 @@ struct BitTileHost {
   HostArray<uint32_t> r_indices;
   HostArray<float> r_values;
   std::vector<float> row_scale, col_scale;
+  int64_t n_unfactored = 0;  // remainder entries whose value is NOT row_scale * col_scale (0: the pattern-only ELL kernel applies)
 };
 
 namespace {
@@ -110,7 +111,7 @@ struct BlockOut {
   std::vector<uint32_t> ridx;
   std::vector<float> rval;
   uint32_t rcount[2 * kBtRows];
-  int64_t tile_nnz = 0;
+  int64_t tile_nnz = 0, unfactored = 0;
 };
 
 }  // namespace
@@ -217,9 +218,11 @@ int bittile_build_host(const uint32_t *indptr, const uint32_t *indices, const fl
           const float v = values[e];
           const int32_t li = sel[j >> shift];
           bool in_tile = false;
+          const float p = si * H.col_scale[j];
+          const bool factors = fabsf(v - p) <= 1e-6f * fabsf(v);  // false for NaN scales
+          if (!factors) o.unfactored++;
           if (li >= 0) {
-            const float p = si * H.col_scale[j];
-            if (fabsf(v - p) <= 1e-6f * fabsf(v)) {  // false for NaN scales
+            if (factors) {
               const uint32_t cc = j & (uint32_t)(chunk_cols - 1);
               uint64_t &w = o.bits[((size_t)li * BH + rl) * wpr + (cc >> 6)];  // rl = sub * 128 + row
               const uint64_t m = 1ull << bt_bit_of_col(cc & 63u);
@@ -298,6 +301,7 @@ int bittile_build_host(const uint32_t *indptr, const uint32_t *indices, const fl
   H.r_indptr.assign((size_t)n_rows + 1, 0u);
   uint64_t racc = 0;
   H.tile_nnz = 0;
+  H.n_unfactored = 0;
   for (int64_t b = 0; b < H.n_blk; b++) {
     const BlockOut &o = blocks[(size_t)b];
     const int64_t r0 = b * BH, r1 = std::min<int64_t>(n_rows, r0 + BH);
@@ -306,6 +310,7 @@ int bittile_build_host(const uint32_t *indptr, const uint32_t *indices, const fl
       racc += o.rcount[i - r0];
     }
     H.tile_nnz += o.tile_nnz;
+    H.n_unfactored += o.unfactored;
   }
   H.r_indptr[(size_t)n_rows] = (uint32_t)racc;
   H.r_indices.alloc((size_t)racc);
@@ -369,7 +374,8 @@ struct BtArgs {
 // chunk c, k-step ks, element (n = piece*16 + col, k) at  c*6144 + ks*1536 + (k/8)*768 + (n/8)*128 + (n%8)*16 + (k%8)*2.
 // One thread = 8 consecutive rows of B x one column: three 16-byte stores.
 __global__ void __launch_bounds__(256) bt_pack_kernel(const float *__restrict__ B, const float *__restrict__ col_scale,
-                                                      uint8_t *__restrict__ packed, int64_t n_cols, int64_t n_groups) {
+                                                      uint8_t *__restrict__ packed, float *__restrict__ B2, int64_t n_cols,
+                                                      int64_t n_groups) {
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t g = tid >> 4;
   const int col = (int)(tid & 15);
@@ -380,7 +386,10 @@ __global__ void __launch_bounds__(256) bt_pack_kernel(const float *__restrict__ 
   for (int i = 0; i < 8; i++) {
     const int64_t j = j0 + i;
     float x = 0.f;
-    if (j < n_cols) x = __ldg(col_scale + j) * __ldg(B + j * 16 + col);
+    if (j < n_cols) {
+      x = __ldg(col_scale + j) * __ldg(B + j * 16 + col);
+      if (B2) B2[j * 16 + col] = x;  // fp32 copy of B' for the pattern-only remainder kernel (spmm_ell.cu)
+    }
     const uint32_t xb = __float_as_uint(x);
     const uint32_t hb = xb & 0xffff0000u;
     const float r1 = x - __uint_as_float(hb);
@@ -414,7 +423,7 @@ __global__ void __launch_bounds__(256) bt_pack_kernel(const float *__restrict__ 
 // The same packing for a 16-column slab of a wider row-major matrix (row stride ldb floats)
 __global__ void __launch_bounds__(256) bt_pack_ld_kernel(const float *__restrict__ B, int64_t ldb,
                                                          const float *__restrict__ col_scale, uint8_t *__restrict__ packed,
-                                                         int64_t n_cols, int64_t n_groups) {
+                                                         float *__restrict__ B2, int64_t n_cols, int64_t n_groups) {
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t g = tid >> 4;
   const int col = (int)(tid & 15);
@@ -425,7 +434,10 @@ __global__ void __launch_bounds__(256) bt_pack_ld_kernel(const float *__restrict
   for (int i = 0; i < 8; i++) {
     const int64_t j = j0 + i;
     float x = 0.f;
-    if (j < n_cols) x = __ldg(col_scale + j) * __ldg(B + j * ldb + col);
+    if (j < n_cols) {
+      x = __ldg(col_scale + j) * __ldg(B + j * ldb + col);
+      if (B2) B2[j * 16 + col] = x;
+    }
     const uint32_t xb = __float_as_uint(x);
     const uint32_t hb = xb & 0xffff0000u;
     const float r1 = x - __uint_as_float(hb);
@@ -885,7 +897,10 @@ struct gcnb_bittile_plan {
   float *d_r_values = nullptr, *d_row_scale = nullptr, *d_col_scale = nullptr;
   uint8_t *d_packed = nullptr;
   float *d_P = nullptr, *d_R = nullptr;
-  gcnb_spmm_plan *rem = nullptr;
+  gcnb_spmm_plan *rem = nullptr;  // valued remainder CSR on the generic kernel (entries that do not factor exist, or GCNB_BT_ELL=0)
+  gcnb::EllDev *ell = nullptr;    // pattern-only remainder (spmm_ell.cu): every remainder entry factors
+  float *d_B2 = nullptr;          // [n_cols + 1][16]: diag(col_scale) * B of the current launch, last row zero
+  int rem_ctas = 0;               // CTAs per SM of the remainder kernel (0 = its default)
   cudaStream_t aux = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
@@ -919,11 +934,12 @@ int gcnb_bittile_host_build(const uint32_t *h_indptr, const uint32_t *h_indices,
   return 0;
 }
 
-int gcnb_bittile_host_sizes(const gcnb_bittile_host *h, int64_t out[10]) {
+int gcnb_bittile_host_sizes(const gcnb_bittile_host *h, int64_t out[12]) {
   if (!h || !out) return GCNB_E_BADARG;
   const BitTileHost &H = h->H;
   out[0] = H.n_rows; out[1] = H.n_cols; out[2] = H.nnz; out[3] = H.n_blk; out[4] = H.n_tiles; out[5] = H.tile_nnz;
   out[6] = (int64_t)H.items.size(); out[7] = H.n_cta; out[8] = H.chunk; out[9] = H.rb;
+  out[10] = H.n_unfactored; out[11] = (int64_t)H.r_indices.size();
   return 0;
 }
 
@@ -959,6 +975,8 @@ int gcnb_bittile_host_destroy(gcnb_bittile_host *h) {
 int gcnb_bittile_plan_destroy(gcnb_bittile_plan *p) {
   if (!p) return 0;
   if (p->rem) gcnb_spmm_plan_destroy(p->rem);
+  gcnb::ell_destroy(p->ell);
+  cudaFree(p->d_B2);
   cudaFree(p->d_tile_chunk); cudaFree(p->d_cta_tile_ptr); cudaFree(p->d_cta_item_ptr); cudaFree(p->d_items);
   cudaFree(p->d_bits); cudaFree(p->d_r_indptr); cudaFree(p->d_r_indices); cudaFree(p->d_r_values);
   cudaFree(p->d_row_scale); cudaFree(p->d_col_scale); cudaFree(p->d_packed); cudaFree(p->d_P); cudaFree(p->d_R);
@@ -1004,9 +1022,20 @@ int gcnb_bittile_plan_create(const uint32_t *h_indptr, const uint32_t *h_indices
   if ((rc = bt_upload(&p->d_cta_tile_ptr, H.cta_tile_ptr.data(), H.cta_tile_ptr.size(), stream))) return fail(rc);
   if ((rc = bt_upload(&p->d_cta_item_ptr, H.cta_item_ptr.data(), H.cta_item_ptr.size(), stream))) return fail(rc);
   if ((rc = bt_upload(&p->d_items, H.items.data(), H.items.size(), stream))) return fail(rc);
-  if ((rc = bt_upload(&p->d_r_indptr, H.r_indptr.data(), H.r_indptr.size(), stream))) return fail(rc);
-  if ((rc = bt_upload(&p->d_r_indices, H.r_indices.data(), H.r_indices.size(), stream))) return fail(rc);
-  if ((rc = bt_upload(&p->d_r_values, H.r_values.data(), H.r_values.size(), stream))) return fail(rc);
+  bool use_ell = H.n_unfactored == 0 && H.n_tiles > 0;
+  if (const char *e = getenv("GCNB_BT_ELL")) use_ell = use_ell && atoi(e) != 0;  // tuning probe: 0 keeps the valued generic kernel
+  if (use_ell) {
+    gcnb::EllHost E;
+    if ((rc = gcnb::ell_build_host(H.r_indptr.data(), H.r_indices.data(), n_rows, n_cols, 0, E))) return fail(rc);
+    if ((rc = gcnb::ell_upload_plan(E, stream, &p->ell))) return fail(rc);
+    const size_t b2_bytes = ((size_t)n_cols + 1) * 16 * sizeof(float);
+    if ((rc = (int)cudaMalloc((void **)&p->d_B2, b2_bytes))) return fail(rc);
+    if ((rc = (int)cudaMemsetAsync(p->d_B2, 0, b2_bytes, stream))) return fail(rc);  // the padding row stays zero
+  } else {
+    if ((rc = bt_upload(&p->d_r_indptr, H.r_indptr.data(), H.r_indptr.size(), stream))) return fail(rc);
+    if ((rc = bt_upload(&p->d_r_indices, H.r_indices.data(), H.r_indices.size(), stream))) return fail(rc);
+    if ((rc = bt_upload(&p->d_r_values, H.r_values.data(), H.r_values.size(), stream))) return fail(rc);
+  }
   if ((rc = bt_upload(&p->d_row_scale, H.row_scale.data(), H.row_scale.size(), stream))) return fail(rc);
   if ((rc = bt_upload(&p->d_col_scale, H.col_scale.data(), H.col_scale.size(), stream))) return fail(rc);
   const size_t packed_bytes = std::max<size_t>((size_t)p->n_chunks * kBtChunkBytes, 16);
@@ -1016,11 +1045,14 @@ int gcnb_bittile_plan_create(const uint32_t *h_indptr, const uint32_t *h_indices
   if ((rc = (int)cudaMalloc((void **)&p->d_R, std::max<size_t>((size_t)n_rows * 16 * sizeof(float), 16)))) return fail(rc);
   if ((rc = (int)cudaMemsetAsync(p->d_P, 0, p_bytes, stream))) return fail(rc);  // blocks without tiles stay 0 for ever
   if ((rc = (int)cudaStreamSynchronize(stream))) return fail(rc);                // host arrays go out of scope
-  if ((rc = gcnb_spmm_plan_create(p->d_r_indptr, p->d_r_indices, n_rows, n_cols, 0, stream_, &p->rem))) return fail(rc);
+  if (!p->ell && (rc = gcnb_spmm_plan_create(p->d_r_indptr, p->d_r_indices, n_rows, n_cols, 0, stream_, &p->rem))) return fail(rc);
   // tuning probe: cap the remainder kernel's CTAs per SM so that, whichever kernel the block scheduler sees first, the MMA
   // kernel's CTA (448 threads x 68 registers) still fits on every SM (first measurements: launched at the same instant the
   // two kernels took 772 us instead of 502)
-  if (const char *e = getenv("GCNB_BT_REM_CTAS")) p->rem->max_cta_per_sm = std::max(0, atoi(e));
+  if (const char *e = getenv("GCNB_BT_REM_CTAS")) {
+    p->rem_ctas = std::max(0, atoi(e));
+    if (p->rem) p->rem->max_cta_per_sm = p->rem_ctas;
+  }
   if ((rc = (int)cudaStreamCreateWithFlags(&p->aux, cudaStreamNonBlocking))) return fail(rc);
   if ((rc = (int)cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming))) return fail(rc);
   if ((rc = (int)cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming))) return fail(rc);
@@ -1042,7 +1074,7 @@ int gcnb_bittile_plan_create(const uint32_t *h_indptr, const uint32_t *h_indices
 // out = {tiles, entries in tiles, remainder entries, row blocks, items (blocks with tiles), CTAs, bit-map bytes, packed B' bytes}
 int gcnb_bittile_plan_info(const gcnb_bittile_plan *p, int64_t out[8]) {
   if (!p || !out) return GCNB_E_BADARG;
-  out[0] = p->n_tiles; out[1] = p->tile_nnz; out[2] = p->rem_nnz; out[3] = p->n_blk; out[4] = p->chunk + 1000 * p->rb;
+  out[0] = p->n_tiles; out[1] = p->tile_nnz; out[2] = p->rem_nnz; out[3] = p->n_blk; out[4] = p->chunk + 1000 * p->rb + (p->ell ? 100000 : 0);
   out[5] = p->n_cta;
   out[6] = p->n_tiles * (int64_t)kBtRows * p->rb * (p->chunk / 8); out[7] = p->n_chunks * (int64_t)kBtChunkBytes;
   return 0;
@@ -1061,8 +1093,8 @@ int gcnb_bittile_debug_pack(gcnb_bittile_plan *p, const float *d_B, void *h_out,
   cudaStream_t stream = as_stream(stream_);
   const int64_t n_groups = p->n_chunks * (kBtChunk / 8);
   if (n_groups == 0) return 0;
-  bt_pack_kernel<<<(unsigned)((n_groups * 16 + 255) / 256), 256, 0, stream>>>(d_B, p->d_col_scale, p->d_packed, p->n_cols,
-                                                                              n_groups);
+  bt_pack_kernel<<<(unsigned)((n_groups * 16 + 255) / 256), 256, 0, stream>>>(d_B, p->d_col_scale, p->d_packed, nullptr,
+                                                                              p->n_cols, n_groups);
   GCNB_LAUNCH_CHECK();
   GCNB_CHECK(cudaMemcpyAsync(h_out, p->d_packed, (size_t)std::min<int64_t>(bytes, p->n_chunks * (int64_t)kBtChunkBytes),
                              cudaMemcpyDeviceToHost, stream));
@@ -1079,11 +1111,11 @@ static int bt_slab16(gcnb_bittile_plan *p, const float *d_B, int64_t ldb, float 
     const int64_t n_groups = p->n_chunks * (kBtChunk / 8);
     const int64_t threads = n_groups * 16;
     if (ldb == 16)
-      bt_pack_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(d_B, p->d_col_scale, p->d_packed, p->n_cols,
-                                                                           n_groups);
+      bt_pack_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(d_B, p->d_col_scale, p->d_packed, p->d_B2,
+                                                                           p->n_cols, n_groups);
     else
       bt_pack_ld_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(d_B, ldb, p->d_col_scale, p->d_packed,
-                                                                              p->n_cols, n_groups);
+                                                                              p->d_B2, p->n_cols, n_groups);
     GCNB_LAUNCH_CHECK();
   }
   // The MMA kernel goes first (one CTA per SM, half the register file), then the remainder CSR on the second stream
@@ -1103,7 +1135,8 @@ static int bt_slab16(gcnb_bittile_plan *p, const float *d_B, int64_t ldb, float 
   }
   GCNB_CHECK(cudaStreamWaitEvent(p->aux, p->ev_fork, 0));
   if (parts & 4) {
-    const int rc = gcnb::spmm_generic_launch(p->rem, p->d_r_values, nullptr, d_B, (int)ldb, p->d_R, 16, 16, p->aux);
+    const int rc = p->ell ? gcnb::ell_launch(p->ell, p->d_B2, p->d_row_scale, p->d_R, p->rem_ctas, p->aux)
+                          : gcnb::spmm_generic_launch(p->rem, p->d_r_values, nullptr, d_B, (int)ldb, p->d_R, 16, 16, p->aux);
     if (rc) return rc;
   }
   GCNB_CHECK(cudaEventRecord(p->ev_join, p->aux));

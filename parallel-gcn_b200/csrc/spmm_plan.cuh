@@ -94,6 +94,30 @@ struct StagedHost {
 int stage_build_host(const uint32_t *indptr, const uint32_t *indices, int64_t n_rows, int64_t n_cols,
                      const StageParams &params, StagedHost &out);
 
+// ---- pattern-only row gather at width 16 (spmm_ell.cu): the remainder of a bit-tile plan whose entries all factor --------
+constexpr int kEllWideMin = 256;   // rows with more entries are shared by the 8 lane groups of a warp (wide bundle)
+constexpr int kEllWideMax = 8192;  // longer rows are cut into parts with partial slots
+// bundles in ticket order; off[b] = first uint4-row of bundle b (a uint4-row = 8 groups x 4 indices = 128 bytes);
+// steps[b] = uint4-rows of the bundle | 0x80000000 for a wide bundle; rows[b*8 + g] = row owned by lane group g
+// (0xffffffff: unused) or, wide, rows[b*8] = the row and rows[b*8 + 1] = its partial slot (0xffffffff: writes R directly);
+// split_row[k] = k-th row assembled from the slots [split_ptr[k], split_ptr[k+1])
+struct EllHost {
+  int64_t n_rows = 0, n_cols = 0, nnz = 0, n_bundles = 0, n_slots = 0;
+  HostArray<uint32_t> idx;
+  std::vector<uint32_t> off, steps, rows, split_row, split_ptr;
+};
+struct EllDev {
+  int64_t n_rows = 0, n_cols = 0, nnz = 0, n_bundles = 0, n_split = 0, n_slots = 0;
+  uint32_t *d_idx = nullptr, *d_off = nullptr, *d_steps = nullptr, *d_rows = nullptr, *d_split_row = nullptr,
+           *d_split_ptr = nullptr, *d_counter = nullptr;
+  float *d_slots = nullptr;
+};
+int ell_build_host(const uint32_t *indptr, const uint32_t *indices, int64_t n_rows, int64_t n_cols, int n_threads, EllHost &out);
+int ell_upload_plan(const EllHost &H, cudaStream_t stream, EllDev **out);
+void ell_destroy(EllDev *e);
+// R[n_rows x 16] = diag(row_scale) * pattern * B2 (B2: n_cols + 1 rows, the last one zero); ctas_per_sm 0 = default
+int ell_launch(EllDev *e, const float *d_B2, const float *d_row_scale, float *d_R, int ctas_per_sm, cudaStream_t stream);
+
 struct StagedDev;  // device mirror, spmm_stage.cu
 void stage_destroy(StagedDev *s);
 
