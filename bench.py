@@ -222,6 +222,82 @@ def cpu_name():
     return "unknown"
 
 
+def dump_dataset_raw(ds, d):
+    """raw little-endian arrays + meta.txt: the input format of oracle/ref_gpu_harness.cu (the reference's text parser
+    would need hours for 115 M entries)"""
+    os.makedirs(d, exist_ok=True)
+    with open(os.path.join(d, "meta.txt"), "w") as f:
+        f.write("%d %d %d %d %d\n" % (ds.num_nodes, ds.input_dim, ds.output_dim, len(ds.g_indices), len(ds.f_indices)))
+    for name, arr, dt in (("g_indptr.u32", ds.g_indptr, np.uint32), ("g_indices.u32", ds.g_indices, np.uint32),
+                          ("f_indptr.u32", ds.f_indptr, np.uint32), ("f_indices.u32", ds.f_indices, np.uint32),
+                          ("f_value.f32", ds.f_value, np.float32), ("label.i32", ds.label, np.int32),
+                          ("split.u32", ds.split, np.uint32)):
+        np.ascontiguousarray(arr, dt).tofile(os.path.join(d, name))
+
+
+REF_GPU_BIN = os.path.join(ROOT, "oracle", "_ref", "ref_gpu_bench")
+
+
+def ref_gpu_same_box(ds, epochs, timeout_s=300):
+    """The reference's OWN CUDA implementation (/root/reference/src/*.cu compiled for sm_100 behind
+    oracle/ref_gpu_harness.cu, driven as test/performance_gpu.cpp:52-66 drives it) on the same dataset and the same GPU, in
+    its own process: GCN::run()'s avg_epoch_time = train epoch + validation forward (ms).  Measurement infrastructure."""
+    import shutil
+    import tempfile
+    if not os.path.exists(REF_GPU_BIN):
+        return {"unavailable": "oracle/_ref/ref_gpu_bench is not built (make -C oracle needs the reference sources)"}
+    base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
+    scratch = tempfile.mkdtemp(prefix="gcnb_ref_gpu_", dir=base)
+    try:
+        dump_dataset_raw(ds, scratch)
+        p = subprocess.run([REF_GPU_BIN, scratch, str(int(epochs)), "1"], capture_output=True, text=True, timeout=timeout_s)
+        line = [l for l in p.stdout.splitlines() if l.startswith("{")]
+        if line:
+            r = json.loads(line[-1])
+            if r.get("cuda_error") == "no error":
+                return {"ms_per_epoch": r["best_avg_epoch_ms"], "epochs": int(epochs), "device": r.get("device")}
+        return {"unavailable": "reference process failed (rc %d): %s" % (p.returncode, (p.stderr or p.stdout)[-300:])}
+    except subprocess.TimeoutExpired:
+        return {"unavailable": "reference process exceeded %d s" % timeout_s}
+    finally:
+        shutil.rmtree(scratch, ignore_errors=True)
+
+
+def graphsum_worst_case(eng, gcnb, ds, d, peak, iters=10):
+    """the same graph with SHUFFLED node ids -- no dense blocks, no column locality, so the engine's
+    policy (bit tiles -> window staging -> generic) ends on the generic segment kernel; timed here on exactly that kernel."""
+    import torch
+    n, nnz = ds.num_nodes, len(ds.g_indices)
+    perm = np.random.default_rng(12345).permutation(n).astype(np.uint32)
+    ip, ix = np.empty(n + 1, np.uint32), np.empty(nnz, np.uint32)
+    eng.check(eng.lib.gcnb_permute_csr(n, eng._p(ds.g_indptr), eng._p(ds.g_indices), eng._p(perm), eng._p(ip), eng._p(ix)))
+    gv = eng.synth_graph_values(ip, ix, 0, np.diff(ip.astype(np.int64)).astype(np.uint32))  # parser.cpp:164-181 formula
+    bt = gcnb.bittile_host_build(ip, ix, gv, n, chunk_cols=128)
+    tile_share = bt["tile_nnz"] / max(1, nnz)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    d_ip, d_ix, d_gv = (torch.from_numpy(a.view(np.int32) if a.dtype == np.uint32 else a).to(dev) for a in (ip, ix, gv))
+    plan = gcnb.SpmmPlan(d_ip, d_ix, n)
+    staged = plan.stage(d_gv, d, h_indptr=ip, h_indices=ix)["staged"]
+    x, out = torch.randn(n, d, device=dev), torch.empty(n, d, device=dev)
+    for _ in range(3):
+        plan.spmm(d_gv, x, out, d)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev[0].record()
+    for _ in range(iters):
+        plan.spmm(d_gv, x, out, d)
+    ev[1].record()
+    torch.cuda.synchronize()
+    us = ev[0].elapsed_time(ev[1]) * 1e3 / iters
+    plan.close()
+    alg = graphsum_alg_bytes(n, nnz, d)
+    ach = alg / (us * 1e-6) / 1e9
+    return {"what": "same graph, node ids shuffled (seed 12345): %.1f %% of the entries in dense blocks, window staging %s => %s"
+                    % (100 * tile_share, "applies" if staged else "does not apply",
+                       "window-staged kernels" if staged else "generic segment kernel (spmm_seg_kernel)"),
+            "mean_launch_us": us, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+            "algorithmic_bytes_per_launch": alg, "launches_timed": iters}
+
+
 # ------------------------------------------------------------------------------------------------------------------
 def run_ours(args, rank, world, local_rank):
     import torch
@@ -279,15 +355,24 @@ def run_ours(args, rank, world, local_rank):
     prof = os.path.join(ROOT, "profiles", "graphsum_d16_summary.json")
     if os.path.exists(prof):
         traffic = json.load(open(prof)).get("dram_bytes_per_launch")
-    staged = bool(r.get("graph_staged"))
-    kname = ("GraphSum d=%d = spmm_staged16_kernel (shared-memory column windows) || spmm_seg_kernel (remainder CSR, 2nd "
-             "stream) + stage_add16_kernel" % d) if staged else "spmm_seg_kernel<4,4,1> (GraphSum, d=%d)" % d
-    if g.graph_bittile():
-        traffic = None  # the ncu figure on file belongs to the window-staged kernels
-        kname = ("GraphSum d=%d = bt_pack_kernel + bt_mma_kernel (tcgen05.mma on bit-map tiles, TMEM accumulators) || "
-                 "spmm_seg_kernel (remainder CSR, 2nd stream) + bt_add_kernel" % d)
+    paths = g.path_info()
+    staged = paths["graph_staged"]
+    traffic, traffic_src = None, None
+    if paths["graph_bittile"]:
+        kname = ("GraphSum d=%d = bt_pack_kernel + bt_mma_wide_kernel<1,2> (tcgen05.mma on 128x128 bit-map tiles, TMEM "
+                 "accumulators) || ell_gather16_kernel (pattern-only remainder, 2nd stream) + bt_add_kernel" % d)
+        prof = os.path.join(ROOT, "profiles", "graphsum_d16_bittile_summary.json")
+    elif staged:
+        kname = ("GraphSum d=%d = spmm_staged16_kernel (shared-memory column windows) || spmm_seg_kernel (remainder CSR, 2nd "
+                 "stream) + stage_add16_kernel" % d)
+        prof = os.path.join(ROOT, "profiles", "graphsum_d16_summary.json")
+    else:
+        kname, prof = "spmm_seg_kernel<4,4,1> (GraphSum, d=%d)" % d, None
+    if prof and os.path.exists(prof):  # ncu dram__bytes of the SAME kernel group, captured once per kernel change
+        traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+        traffic_src = os.path.relpath(prof, ROOT)
     roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg, "mean_launch_us": gs_us, "launches_timed": r["graphsum_calls"],
                 "graphsum_share_of_step": r["graphsum_ms"] / r["ms"], "frac_of_nominal_8TBs": achieved / 8000.0}
     line = {"metric": METRIC, "value": ms_per_step, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
@@ -303,11 +388,18 @@ def run_ours(args, rank, world, local_rank):
                        "evaluation_layer0": "(A_hat X) W0 with A_hat X computed once at the first evaluation (its 38 GraphSum "
                                             "slabs are part of e2e and of the warm-up, not of the timed steps): 5 GraphSum "
                                             "calls per step instead of 6; GCNB_PROPAGATE=0 restores A_hat (X W0)",
-                       "graphsum_path": "bit tiles (tcgen05)" if g.graph_bittile() else ("window-staged" if staged else "generic"),
+                       "graphsum_path": "bit tiles (tcgen05)" if paths["graph_bittile"] else ("window-staged" if staged else "generic"),
+                       "paths": paths,
                        "switches": {k: os.environ[k] for k in sorted(os.environ) if k.startswith("GCNB_")},
                        "final_train_loss": last[0][0], "final_val_acc": last[1][1], "published_other_hw": PUBLISHED},
             "clocks": clk, "e2e": e2e, "gpu_launches": r["launches"], "roofline": roofline}
     g.close()
+    if not args.no_extras:
+        line["roofline_worst_case"] = graphsum_worst_case(eng, gcnb, ds, d, peak)
+        rg = ref_gpu_same_box(ds, max(10, args.steps))
+        line["ref_gpu_same_box_ms"] = rg.get("ms_per_epoch")
+        line["ref_gpu_same_box"] = dict(rg, what="the reference's own CUDA code (src/*.cu, -arch=sm_100) on this GPU and dataset, "
+                                                 "GCN::run() avg_epoch_time = train epoch + validation forward; separate process")
     if not args.no_cpu_baseline:
         ms, kind, sample, cores, timed, _ = cpu_reference_step_ms(1, 0, 1)
         line["cpu_baseline"] = {"value": ms, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample + " (1 step)",
@@ -323,6 +415,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scale", type=int, default=1, help="debug: 1/scale-size workload (numbers are then not the metric)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the shuffled-id GraphSum and the same-box reference-GPU legs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -136,6 +136,8 @@ GCNB_API int gcnb_bittile_plan_create(const uint32_t *h_indptr, const uint32_t *
                                       int row_blocks /*0 = 1; 2 = items of 256 rows (chunk 64 only)*/, gcnb_stream_t stream,
                                       gcnb_bittile_plan **out);
 GCNB_API int gcnb_bittile_plan_destroy(gcnb_bittile_plan *plan);
+/* 1 when the current device can run the bit-tile kernels (tcgen05 / TMEM: compute capability 10.x) */
+GCNB_API int gcnb_bittile_supported(void);
 /* out = {tiles, entries in tiles, remainder entries, items' row blocks, columns per tile + 1000 * row_blocks
  * (+ 100000 when the remainder runs on the pattern-only ELL kernel below), CTAs, bit-map bytes, packed-B bytes} */
 GCNB_API int gcnb_bittile_plan_info(const gcnb_bittile_plan *plan, int64_t out[8]);

@@ -95,16 +95,22 @@ GCNB_API int gcnb_gcn_set_mask(gcnb_gcn *g, int site, const uint8_t *host_mask);
 GCNB_API int64_t gcnb_gcn_launches_per_epoch(const gcnb_gcn *g);
 /* 1 if GraphSum at feature width 16 uses the window-staged kernels (graph with column locality), else 0 */
 GCNB_API int gcnb_gcn_graph_staged(const gcnb_gcn *g);
-/* 1 if GraphSum at width 16 runs the tcgen05 bit-tile path (GCNB_BITTILE=1, parallel-gcn_b200/csrc/spmm_bittile.cu) */
+/* 1 if GraphSum at width 16 runs the tcgen05 bit-tile path (parallel-gcn_b200/csrc/spmm_bittile.cu; the default when a
+ * quarter of the adjacency's entries sit in dense blocks, GCNB_BITTILE=0 turns it off) */
 GCNB_API int gcnb_gcn_graph_bittile(const gcnb_gcn *g);
+/* which fast paths are active right now: out = {window-staged GraphSum, bit-tile GraphSum, dense-feature first layer
+ * (tensor-core X W0 / X^T dH kernels), evaluation through the propagated features A_hat X, CUDA-graph replay usable,
+ * background set-up still pending (gcnb_gcn_finish_setup), exact-split tcgen05 GEMM packed, row-partitioned} */
+GCNB_API int gcnb_gcn_path_info(const gcnb_gcn *g, int out[8]);
 GCNB_API int64_t gcnb_gcn_launches_total(const gcnb_gcn *g);
 /* CUDA-graph replay of the training epoch and of the evaluation passes (small datasets are launch-bound).  Default: on
  * when graph + feature entries <= 8 Mi (GCNB_CUDA_GRAPH=0/1 overrides); never used by a partitioned model, with injected
  * masks, or while GraphSum launches are being timed.  Results are bit-identical to eager launches.
  * gcnb_gcn_uses_cuda_graph: 1 if the next passes may be replayed. */
-/* GCNB_ASYNC_STAGE=1 (large single-GPU models): gcnb_gcn_create returns as soon as the dataset is on the device and the
- * first epochs run on the generic GraphSum kernel while the window-staged representation is built and uploaded by a helper
- * thread; it is attached before training epoch GCNB_STAGE_SWITCH_EPOCH (default 128) -- a fixed point, so results do not
+/* Large single-GPU models (graph + feature entries > 8 Mi; GCNB_ASYNC_STAGE=0 builds synchronously instead):
+ * gcnb_gcn_create returns as soon as the dataset is on the device and the first epochs run on the generic GraphSum kernel
+ * while the static GraphSum representation (bit tiles, or window staging when the graph has no dense blocks) is built and
+ * uploaded by a helper thread; it is attached before training epoch GCNB_STAGE_SWITCH_EPOCH (default 128) -- a fixed point, so results do not
  * depend on timing -- or by this call (which waits for the helper if it is still busy).  No-op otherwise. */
 GCNB_API int gcnb_gcn_finish_setup(gcnb_gcn *g);
 GCNB_API int gcnb_gcn_set_cuda_graph(gcnb_gcn *g, int on);

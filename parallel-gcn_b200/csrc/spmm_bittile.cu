@@ -11,27 +11,27 @@
 // (8 + 8 + 8 significand bits, hi + mid + lo == B' exactly), every product 1.0 * piece is exact and the sums are
 // accumulated in fp32.  No neighbour row is gathered at all.
 //
-// How: rows are cut into blocks of 128, columns into chunks of 64.  A TILE (row block x chunk) holding at least
-// min_tile_nnz entries that satisfy the factorisation becomes 128 x 64 bits (1 KB); all other entries (sparse tiles,
-// duplicate entries, values that are not s_i * s_j) form the REMAINDER CSR with their original values.  Per launch:
+// How: rows are cut into blocks of 128, columns into chunks of 64 or 128 (default 128).  A TILE (row block x chunk) holding at
+// least min_tile_nnz entries that satisfy the factorisation becomes a bit map (1 or 2 KB); all other entries (sparse
+// tiles, duplicate entries, values that are not s_i * s_j) form the REMAINDER.  Per launch:
 //   bt_pack_kernel     B' = s_j * B_j split into bf16 hi | mid | lo, stored chunk by chunk as the K-major core-matrix
-//                      image tcgen05.mma reads from shared memory (48 x 16 per k-step, no swizzle); 96 bytes per row of B
-//   bt_mma_kernel      one persistent CTA per SM, warp-specialised:
+//                      image tcgen05.mma reads from shared memory (48 x 16 per k-step, no swizzle; 96 bytes per row of B),
+//                      plus the fp32 copy of B' the pattern-only remainder kernel gathers from
+//   bt_mma_wide_kernel<RB, W>  one persistent CTA per SM, warp-specialised (see the comment above it):
 //                        warps 0-7   expand bit-map words into bf16 0/1 A operands and write them to TMEM (tcgen05.st):
 //                                    thread = row, 64 bits -> 32 packed registers with 2 integer ops per register
-//                        warp  12    streams the packed chunks of B' into an 8-stage shared-memory ring (cp.async.bulk)
-//                        warp  13    one thread issues tcgen05.mma.kind::f16, M = 128, N = 48 (3 pieces x 16 columns),
-//                                    K = 16, A from TMEM, B from shared memory, D in TMEM; tcgen05.commit frees stages
+//                        warp  12    streams the packed chunks of B' into a shared-memory ring (cp.async.bulk)
+//                        warp  13    converged, one elected lane issues tcgen05.mma.kind::f16, M = 128, N = 48 (3 pieces
+//                                    x 16 columns), K = 16, A from TMEM, B from shared memory, D in TMEM; tcgen05.commit
+//                                    frees stages
 //                        warps 8-11  epilogue: tcgen05.ld the accumulators, add pieces small to large, scale by s_i,
 //                                    store the block's partial rows
-//                      Chains are bounded: the tiles of a row block rotate over 4 accumulators that the epilogue adds
-//                      with rounded fp32 adds (the tensor core's accumulate truncates).
-//   generic kernel     remainder CSR on a second stream, concurrently (it lives on the LSU pipe, the MMA path does not)
+//   remainder          second stream, concurrently (it lives on the LSU pipe, the MMA path does not): the pattern-only
+//                      ELL gather of spmm_ell.cu when every remainder entry factors (GraphSum always), else the
+//                      valued CSR on the generic kernel (spmm.cu)
 //   bt_add_kernel      C = P + R
-// Two generations of the MMA kernel live here: bt_mma_kernel (64-column tiles, separate A / B rings; the one measured on
-// B200 in round 1: correct, 302 us alone on the bench graph) and bt_mma_wide_kernel<RB, W> (unified stage barriers, a
-// warp-converged issuer, 128-column tiles or 256-row items that share a B' stage; compiled, emulated and protocol-
-// simulated on the CPU, selected by chunk_cols / row_blocks / GCNB_BT_* -- see the comment above it).
+// Tile shapes: W = 2 -> 128 x 128 tiles (default; 128 us for the MMA kernel on the bench graph), RB = 2 -> items of 256
+// rows x 64 columns whose two halves share a B' stage (134 us), W = RB = 1 -> 128 x 64 (190 us).
 // Summation order is fixed by the plan => bit-reproducible run to run.  Relative to the CSR product the result differs
 // by the rounding of s_i * s_j against 1/sqrtf(deg_i * deg_j) and by the summation order (~1e-6 relative; parity bar 1e-5).
 //
@@ -61,10 +61,6 @@ constexpr int kBtChunk = 64;                 // columns per tile = 4 MMA k-steps
 constexpr int kBtN = 48;                     // MMA N: 3 bf16 pieces x 16 columns
 constexpr int kBtKStepBytes = kBtN * 16 * 2; // 1536: one 48 x 16 bf16 operand
 constexpr int kBtChunkBytes = 4 * kBtKStepBytes;  // 6144 bytes of packed B' per chunk
-constexpr int kBtBStages = 8;
-constexpr int kBtAStages = 4;                // x 32 TMEM columns
-constexpr int kBtAcc = 4;                    // accumulators per set (x 48 TMEM columns), two sets
-constexpr int kBtAccCol0 = kBtAStages * 32;  // 128
 constexpr int kBtThreads = 14 * 32;
 
 // Host-side plan (pure CPU; unit-tested without a GPU through gcnb_bittile_host_*).
@@ -490,174 +486,9 @@ __device__ __forceinline__ void bt_expand_word(uint32_t w, uint32_t *r) {
   }
 }
 
-__global__ void __maxnreg__(72) bt_mma_kernel(BtArgs a) {  // 448 threads x 72 registers leave half the register file to the remainder kernel
-  extern __shared__ __align__(128) uint8_t bt_smem[];
-  // layout: B stages | barriers | tmem base
-  uint8_t *smem_b = bt_smem;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(bt_smem + kBtBStages * kBtChunkBytes);
-  uint64_t *b_full = bars, *b_empty = bars + kBtBStages;
-  uint64_t *a_full = bars + 2 * kBtBStages, *a_empty = a_full + kBtAStages;
-  uint64_t *acc_full = a_empty + kBtAStages, *acc_empty = acc_full + 2;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q = blockIdx.x;
-  const uint32_t tile0 = a.cta_tile_ptr[q];
-  const uint32_t T = a.cta_tile_ptr[q + 1] - tile0;
-  const uint32_t item0 = a.cta_item_ptr[q], item1 = a.cta_item_ptr[q + 1];
-
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < kBtBStages; i++) {
-      mbar_init(&b_full[i], 1);
-      mbar_init(&b_empty[i], 1);
-    }
-    for (int i = 0; i < kBtAStages; i++) {
-      mbar_init(&a_full[i], 4);
-      mbar_init(&a_empty[i], 1);
-    }
-    for (int i = 0; i < 2; i++) {
-      mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], 4);
-    }
-    fence_mbar_init();
-  }
-  if (warp == 13) {  // the MMA warp owns the TMEM allocation (all 512 columns: one CTA per SM)
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *reinterpret_cast<volatile uint32_t *>(tmem_slot);
-
-  if (warp < 8) {
-    // ---- expanders: warp = (group g = warp >> 2) x (lane quarter = warp & 3); group g takes positions t = g, g+2, ...
-    const int quarter = warp & 3, g = warp >> 2;
-    const uint64_t *bp = a.bits + (size_t)tile0 * kBtRows + quarter * 32 + lane;
-    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
-    uint32_t t = (uint32_t)g;
-    uint64_t w0 = t < T ? bt_ld_bits(bp + (size_t)t * kBtRows) : 0ull;
-    uint64_t w1 = t + 2 < T ? bt_ld_bits(bp + (size_t)(t + 2) * kBtRows) : 0ull;
-    uint64_t w2 = t + 4 < T ? bt_ld_bits(bp + (size_t)(t + 4) * kBtRows) : 0ull;
-    for (; t < T; t += 2) {
-      const uint64_t w3 = t + 6 < T ? bt_ld_bits(bp + (size_t)(t + 6) * kBtRows) : 0ull;
-      const uint32_t s = t % kBtAStages, use = t / kBtAStages;
-      uint32_t r[32];
-      bt_expand_word((uint32_t)w0, r);
-      bt_expand_word((uint32_t)(w0 >> 32), r + 16);
-      if (use > 0) mbar_wait(&a_empty[s], (use - 1) & 1);  // the MMAs that read this stage's previous content are done
-      tc_fence_after();
-      tc_st32(tmem + lane_base + s * 32, r);
-      tc_wait_st();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&a_full[s]);
-      w0 = w1;
-      w1 = w2;
-      w2 = w3;
-    }
-  } else if (warp < 12) {
-    // ---- epilogue: thread = row (TMEM lane) of the block
-    const int quarter = warp & 3;
-    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
-    uint32_t prev_end = 0;
-    for (uint32_t it = item0; it < item1; it++) {
-      const uint2 item = a.items[it];
-      const uint32_t n_tiles = item.y - prev_end;
-      prev_end = item.y;
-      const uint32_t k = it - item0, set = k & 1, use = k >> 1;
-      const int64_t row = (int64_t)item.x * kBtRows + quarter * 32 + lane;
-      const float sc = row < a.n_rows ? __ldg(a.row_scale + row) : 0.f;
-      mbar_wait(&acc_full[set], use & 1);
-      tc_fence_after();
-      const uint32_t acc0 = tmem + lane_base + kBtAccCol0 + set * (kBtAcc * kBtN);
-      // one accumulator at a time (the next row block's MMAs run meanwhile on the other set; registers are what the
-      // co-resident remainder kernel needs): piece sums ((a0 + a1) + a2) + a3, then (lo + mid) + hi
-      float tot[16];
-#pragma unroll
-      for (int p = 2; p >= 0; p--) {
-        float s[16];
-        tc_ld16(acc0 + p * 16, s);
-        tc_wait_ld();
-        for (uint32_t c = 1; c < (uint32_t)kBtAcc && c < n_tiles; c++) {
-          float v[16];
-          tc_ld16(acc0 + c * kBtN + p * 16, v);
-          tc_wait_ld();
-#pragma unroll
-          for (int i = 0; i < 16; i++) s[i] += v[i];
-        }
-#pragma unroll
-        for (int i = 0; i < 16; i++) tot[i] = p == 2 ? s[i] : tot[i] + s[i];
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[set]);
-      float4 *dst = reinterpret_cast<float4 *>(a.P + row * 16);
-#pragma unroll
-      for (int i = 0; i < 4; i++)  // rows past n_rows exist in P (padded to whole blocks) and receive 0
-        dst[i] = make_float4(sc * tot[4 * i], sc * tot[4 * i + 1], sc * tot[4 * i + 2], sc * tot[4 * i + 3]);
-    }
-  } else if (warp == 12) {
-    // ---- producer of B': chunk ids are read 32 at a time, lane 0 issues the bulk copies
-    for (uint32_t base = 0; base < T; base += 32) {
-      const uint32_t mine = base + lane < T ? __ldg(a.tile_chunk + tile0 + base + lane) : 0u;
-      const uint32_t cnt = min(32u, T - base);
-      for (uint32_t k = 0; k < cnt; k++) {
-        const uint32_t c = __shfl_sync(0xffffffffu, mine, (int)k);
-        if (lane == 0) {
-          const uint32_t t = base + k, s = t % kBtBStages, use = t / kBtBStages;
-          if (use > 0) mbar_wait(&b_empty[s], (use - 1) & 1);
-          mbar_expect_tx(&b_full[s], kBtChunkBytes);
-          bulk_g2s(smem_b + s * kBtChunkBytes, a.packed + (size_t)c * kBtChunkBytes, kBtChunkBytes, &b_full[s]);
-        }
-        __syncwarp();
-      }
-    }
-  } else if (lane == 0) {
-    // ---- MMA issuer (one thread)
-    uint32_t t = 0;
-    uint2 item = item0 < item1 ? a.items[item0] : make_uint2(0, 0);
-    for (uint32_t it = item0; it < item1; it++) {
-      const uint2 next_item = it + 1 < item1 ? a.items[it + 1] : make_uint2(0, 0);
-      const uint32_t k = it - item0, set = k & 1, use = k >> 1;
-      if (use > 0) mbar_wait(&acc_empty[set], (use - 1) & 1);  // the epilogue has drained this accumulator set
-      tc_fence_after();
-      const uint32_t t_begin = t;
-      for (; t < item.y; t++) {
-        const uint32_t sa = t % kBtAStages, ua = t / kBtAStages, sb = t % kBtBStages, ub = t / kBtBStages;
-        mbar_wait(&a_full[sa], ua & 1);
-        mbar_wait(&b_full[sb], ub & 1);
-        tc_fence_after();
-        const uint32_t idx = t - t_begin;
-        const uint32_t d = tmem + kBtAccCol0 + set * (kBtAcc * kBtN) + (idx % kBtAcc) * kBtN;
-        const uint32_t b_addr = smem_u32(smem_b + sb * kBtChunkBytes);
-#pragma unroll
-        for (int ks = 0; ks < 4; ks++)
-          tc_mma_ts(d, tmem + sa * 32 + ks * 8, bt_b_desc(b_addr + ks * kBtKStepBytes), kBtIdesc,
-                    (ks > 0 || idx >= (uint32_t)kBtAcc) ? 1u : 0u);
-        tc_commit(&a_empty[sa]);
-        tc_commit(&b_empty[sb]);
-      }
-      tc_commit(&acc_full[set]);
-      item = next_item;
-    }
-  }
-
-  __syncwarp();
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 13) {
-    __syncwarp();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
-  }
-}
-
-// ---- second generation of the MMA kernel ------------------------------------------------------------------------------
-// First B200 numbers (profiles/r1d_bittile_summary.txt): bt_mma_kernel spends ~650 clocks per 64-column tile against 96
-// of tensor time.  The one thread that issues the MMAs pays, per tile, two mbarrier waits (~90 clocks each even when
-// already complete) and two tcgen05.commit besides the four MMAs, and every tile is a full round trip through the
-// 4-deep A ring.  This version (a) unifies the rings: stage s = B' chunk in shared memory + A operand in TMEM, ONE
+// ---- the MMA kernel ---------------------------------------------------------------------------------------------------
+// Round 1's first kernel (separate A / B rings, a single issuing thread in a divergent branch; deleted) spent ~650 clocks
+// per 64-column tile against 96 of tensor time: 303 us on the bench graph.  This one (a) unifies the rings: stage s = B' chunk in shared memory + A operand in TMEM, ONE
 // full[s] barrier (4 expander-warp arrivals + the producer's arrive.expect_tx + the copy's bytes) and ONE free[s]
 // barrier (one commit) per tile; (b) takes tiles of W * 64 columns (W = 2: 8 MMAs, 12 KB of B', 128 bits per row per
 // tile), halving the round trips per unit of work again.  Two accumulators per set (the measured error of 73-MMA chains
@@ -886,9 +717,8 @@ struct gcnb_bittile_host {
 struct gcnb_bittile_plan {
   int64_t n_rows = 0, n_cols = 0, nnz = 0, n_blk = 0, n_tiles = 0, tile_nnz = 0, rem_nnz = 0, n_chunks = 0;
   int n_cta = 0;
-  int chunk = kBtChunk;  // columns per tile (64: bt_mma_kernel or, with unified = 1, bt_mma_wide_kernel<1, 1>; 128: <1, 2>)
+  int chunk = kBtChunk;  // columns per tile (64: bt_mma_wide_kernel<1, 1> / <2, 1>; 128: <1, 2>)
   int rb = 1;            // 128-row blocks per item (2: bt_mma_wide_kernel<2, 1>)
-  int unified = 0;
   int parts = 15;  // debugging: bit 0 pack, 1 MMA kernel, 2 remainder, 3 final add
   uint32_t *d_tile_chunk = nullptr, *d_cta_tile_ptr = nullptr, *d_cta_item_ptr = nullptr;
   uint2 *d_items = nullptr;
@@ -906,8 +736,6 @@ struct gcnb_bittile_plan {
 };
 
 namespace {
-constexpr size_t kBtSmemBytes = (size_t)kBtBStages * kBtChunkBytes + (2 * kBtBStages + 2 * kBtAStages + 4) * 8 + 16;
-
 template <class T>
 int bt_upload(T **dst, const T *src, size_t n, cudaStream_t stream) {
   *dst = nullptr;
@@ -972,6 +800,12 @@ int gcnb_bittile_host_destroy(gcnb_bittile_host *h) {
   return 0;
 }
 
+// 1 when the current device can run the bit-tile kernels (tcgen05 / TMEM: compute capability 10.x)
+int gcnb_bittile_supported(void) {
+  const DeviceInfo &di = device_info();
+  return di.ok && di.cc_major == 10;
+}
+
 int gcnb_bittile_plan_destroy(gcnb_bittile_plan *p) {
   if (!p) return 0;
   if (p->rem) gcnb_spmm_plan_destroy(p->rem);
@@ -997,12 +831,12 @@ int gcnb_bittile_plan_create(const uint32_t *h_indptr, const uint32_t *h_indices
   if (di.cc_major != 10) return GCNB_E_UNSUPPORTED;  // tcgen05 / TMEM
   cudaStream_t stream = as_stream(stream_);
   BitTileHost H;
-  int unified = 0;
-  if (const char *e = getenv("GCNB_BT_UNIFIED")) unified = atoi(e) != 0;  // tuning probe: 64-column tiles on the new kernel
   if (chunk_cols == 0)
-    if (const char *e = getenv("GCNB_BT_CHUNK")) chunk_cols = atoi(e);    // tuning probe: 64 (default) or 128
+    if (const char *e = getenv("GCNB_BT_CHUNK")) chunk_cols = atoi(e);    // tuning probe: 64 or 128
   if (row_blocks == 0)
-    if (const char *e = getenv("GCNB_BT_RB")) row_blocks = atoi(e);       // tuning probe: 1 (default) or 2
+    if (const char *e = getenv("GCNB_BT_RB")) row_blocks = atoi(e);       // tuning probe: 1 or 2
+  // default shape: 128 x 128 tiles (B200, bench graph: MMA kernel 128 us; 256 x 64 items 134 us; 128 x 64 tiles 190 us)
+  if (chunk_cols == 0) chunk_cols = row_blocks == 2 ? 64 : 128;
   int rc = bittile_build_host(h_indptr, h_indices, h_values, n_rows, n_cols, h_row_scale, h_col_scale, min_tile_nnz,
                               chunk_cols, row_blocks, di.sm_count, 0, H);
   if (rc) return rc;
@@ -1015,7 +849,6 @@ int gcnb_bittile_plan_create(const uint32_t *h_indptr, const uint32_t *h_indices
   p->tile_nnz = H.tile_nnz; p->rem_nnz = (int64_t)H.r_indices.size(); p->n_cta = H.n_cta;
   p->chunk = H.chunk;
   p->rb = H.rb;
-  p->unified = unified || H.chunk == 128 || H.rb == 2;
   p->n_chunks = (n_cols + 127) / 128 * 2;  // 64-row units of the packed B' image, padded to whole 128-column chunks
   if ((rc = bt_upload(&p->d_tile_chunk, H.tile_chunk.data(), H.tile_chunk.size(), stream))) return fail(rc);
   if ((rc = bt_upload(&p->d_bits, H.bits.data(), H.bits.size(), stream))) return fail(rc);
@@ -1056,8 +889,6 @@ int gcnb_bittile_plan_create(const uint32_t *h_indptr, const uint32_t *h_indices
   if ((rc = (int)cudaStreamCreateWithFlags(&p->aux, cudaStreamNonBlocking))) return fail(rc);
   if ((rc = (int)cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming))) return fail(rc);
   if ((rc = (int)cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming))) return fail(rc);
-  if ((rc = (int)cudaFuncSetAttribute(bt_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBtSmemBytes)))
-    return fail(rc);
   if ((rc = (int)cudaFuncSetAttribute(bt_mma_wide_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)BtWide<1, 1>::kSmemBytes)))
     return fail(rc);
@@ -1129,8 +960,7 @@ static int bt_slab16(gcnb_bittile_plan *p, const float *d_B, int64_t ldb, float 
     a.P = p->d_P; a.n_rows = p->n_rows;
     if (p->rb == 2) bt_mma_wide_kernel<2, 1><<<p->n_cta, kBtThreads, BtWide<2, 1>::kSmemBytes, stream>>>(a);
     else if (p->chunk == 128) bt_mma_wide_kernel<1, 2><<<p->n_cta, kBtThreads, BtWide<1, 2>::kSmemBytes, stream>>>(a);
-    else if (p->unified) bt_mma_wide_kernel<1, 1><<<p->n_cta, kBtThreads, BtWide<1, 1>::kSmemBytes, stream>>>(a);
-    else bt_mma_kernel<<<p->n_cta, kBtThreads, kBtSmemBytes, stream>>>(a);
+    else bt_mma_wide_kernel<1, 1><<<p->n_cta, kBtThreads, BtWide<1, 1>::kSmemBytes, stream>>>(a);
     GCNB_LAUNCH_CHECK();
   }
   GCNB_CHECK(cudaStreamWaitEvent(p->aux, p->ev_fork, 0));

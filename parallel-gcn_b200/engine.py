@@ -61,6 +61,7 @@ _sig("gcnb_gcn_set_mask", I32, [P, I32, P])
 _sig("gcnb_gcn_launches_per_epoch", I64, [P])
 _sig("gcnb_gcn_graph_staged", I32, [P])
 _sig("gcnb_gcn_graph_bittile", I32, [P])
+_sig("gcnb_gcn_path_info", I32, [P, P])
 _sig("gcnb_gcn_set_cuda_graph", I32, [P, I32])
 _sig("gcnb_gcn_finish_setup", I32, [P])
 _sig("gcnb_gcn_uses_cuda_graph", I32, [P])
@@ -273,6 +274,14 @@ class GCN:
 
     def graph_bittile(self):
         return bool(lib.gcnb_gcn_graph_bittile(self.h))
+
+    def path_info(self):
+        """which fast paths are active (gcnb_gcn_path_info)"""
+        out = (C.c_int * 8)()
+        check(lib.gcnb_gcn_path_info(self.h, out))
+        keys = ("graph_staged", "graph_bittile", "dense_fast", "propagated_features", "cuda_graph", "setup_pending",
+                "dense_tc", "partitioned")
+        return dict(zip(keys, [bool(x) for x in out]))
 
     def finish_setup(self):
         """attach the background-staged GraphSum representation now (GCNB_ASYNC_STAGE=1); no-op otherwise"""

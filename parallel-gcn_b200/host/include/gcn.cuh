@@ -158,7 +158,10 @@ class GCN {
   // GCNB_ASYNC_STAGE=1 builds the staged GraphSum representation in the background and attaches it before a fixed training
   // epoch (GCNB_STAGE_SWITCH_EPOCH, default 128); finish_setup() attaches it now (waits for the helper if need be)
   void finish_setup();
-  bool graph_bittile() const;  // GraphSum at width 16 runs the tcgen05 bit-tile path (GCNB_BITTILE=1)
+  bool graph_bittile() const;  // GraphSum at width 16 runs the tcgen05 bit-tile path (default when the graph has dense blocks)
+  // which fast paths are active: {window-staged GraphSum, bit-tile GraphSum, dense-feature first layer, evaluation through
+  // the propagated features A_hat X, CUDA-graph replay, background set-up still pending, exact-split tcgen05 GEMM, partitioned}
+  void path_info(int out[8]) const;
   bool graph_staged() const;  // GraphSum at widths 16 / >= 64 runs the window-staged kernels (csrc/spmm_stage.cu)
   size_t launches_total() const;
   void set_time_graphsum(bool on);                        // event pair around every GraphSum launch

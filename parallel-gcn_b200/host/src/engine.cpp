@@ -390,6 +390,11 @@ int gcnb_gcn_finish_setup(gcnb_gcn *g) {
 int gcnb_gcn_uses_cuda_graph(const gcnb_gcn *g) { return g ? (int)g->gcn->uses_cuda_graph() : -1; }
 int gcnb_gcn_graph_staged(const gcnb_gcn *g) { return g ? (int)g->gcn->graph_staged() : -1; }
 int gcnb_gcn_graph_bittile(const gcnb_gcn *g) { return g ? (int)g->gcn->graph_bittile() : -1; }
+int gcnb_gcn_path_info(const gcnb_gcn *g, int out[8]) {
+  if (!g || !out) return GCNB_E_BADARG;
+  g->gcn->path_info(out);
+  return 0;
+}
 int64_t gcnb_gcn_launches_total(const gcnb_gcn *g) { return g ? (int64_t)g->gcn->launches_total() : -1; }
 int gcnb_gcn_timed_epochs(gcnb_gcn *g, int n_epochs, int with_eval, int time_graphsum, float out[4]) {
   if (!g || !out || n_epochs < 0) return GCNB_E_BADARG;

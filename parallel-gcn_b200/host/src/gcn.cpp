@@ -216,8 +216,11 @@ struct GCNEngineState {
   gcnb_bittile_plan *bt_pending = nullptr;
   int bt_rc = 0;
   const real *graph_values_dev = nullptr;
+  bool setup_pending = false;  // a background build (bit tiles and / or window staging) has not been attached yet
+  bool bt_fallback_stage = false;  // the helper found no dense blocks worth bit tiles: it staged the windows instead
   void finish_stage() {
-    if (!stage_job) return;
+    if (!setup_pending) return;
+    setup_pending = false;
     CHECK_CUDA_ERROR(cudaStreamSynchronize(stream));
     if (bt_thread.joinable()) {
       bt_thread.join();
@@ -228,11 +231,13 @@ struct GCNEngineState {
         GCNB_CALL(gcnb_spmm_plan_attach_bittile(graph_plan, graph_bittile, graph_values_dev));
       }
     }
-    GCNB_CALL(gcnb_spmm_plan_stage_async_finish(graph_plan, stage_job));
-    stage_job = nullptr;
-    int64_t sinfo[8];
-    GCNB_CALL(gcnb_spmm_plan_stage_info(graph_plan, sinfo));
-    graph_staged = sinfo[0] != 0;
+    if (stage_job) {
+      GCNB_CALL(gcnb_spmm_plan_stage_async_finish(graph_plan, stage_job));
+      stage_job = nullptr;
+      int64_t sinfo[8];
+      GCNB_CALL(gcnb_spmm_plan_stage_info(graph_plan, sinfo));
+      graph_staged = sinfo[0] != 0;
+    }
   }
   // optional per-launch timing of the GraphSum SpMM (bench.py roofline): event pairs on the engine stream
   bool time_graphsum = false;
@@ -453,88 +458,88 @@ void GCN::init(bool quiet, const natural *h_graph_indptr, const natural *h_graph
       }
   }
   {
-    // graph_value never changes: give GraphSum at width 16 the window-staged representation (shared-memory gathers
-    // for the clustered part of the adjacency, see csrc/spmm_stage.cu); a no-op for graphs without column locality
-    // (wider GraphSums run through the same kernels 16 columns at a time)
-    bool wanted = false;
+    // graph_value never changes, so GraphSum at width 16 (and, 16 columns at a time, at widths >= 64) gets a static
+    // representation built once:
+    //   bit tiles (csrc/spmm_bittile.cu, default on sm_100): the dense blocks of the adjacency as bit maps on the tcgen05
+    //     tensor cores + a pattern-only gather for the rest; used when at least a quarter of the entries sit in tiles;
+    //   window staging (csrc/spmm_stage.cu): shared-memory gathers for the clustered part; the fallback when the graph
+    //     has no dense blocks, GCNB_BITTILE=0, and the default of the row-partitioned engine (whose exchange overlaps
+    //     the staged windows of the rank's own slab; GCNB_BITTILE=1 switches it to bit tiles, agreed collectively).
+    // Large graphs (no CUDA-graph replay) build it on a helper thread while the first epochs run on the generic
+    // kernel (GCNB_ASYNC_STAGE=0: build synchronously); it is attached before training epoch GCNB_STAGE_SWITCH_EPOCH
+    // (128) or by finish_setup(), never at a timing-dependent moment, so runs stay bit-reproducible.
+    bool wanted = false, d16 = false;
     for (const GCNLayer &ly : st->layers) {
       const natural d = ly.reorder ? ly.in_dim : ly.out_dim;
       wanted |= d == 16 || d >= 64;
+      d16 |= d == 16;
     }
+    const char *bt_env = getenv("GCNB_BITTILE");
+    const bool bt_default = !st->dist;  // row-partitioned: opt-in
+    const bool bt_on = N > 0 && (bt_env ? atoi(bt_env) != 0 : bt_default) && gcnb_bittile_supported();
     if (wanted && st->dist) GCNB_CALL(gcnb_spmm_plan_set_own_cols(st->graph_plan, (int64_t)st->row0, (int64_t)(st->row0 + N)));
     const char *async_env = getenv("GCNB_ASYNC_STAGE");
     const size_t big = dev_data.dev_graph_index.indices_size + dev_data.dev_feature_index.indices_size;
-    if (wanted && !st->dist && async_env && atoi(async_env) != 0 && big > (size_t(8) << 20)) {
-      // large graphs (no CUDA-graph replay): start training right away, stage in the background
-      if (const char *e = getenv("GCNB_STAGE_SWITCH_EPOCH")) st->stage_switch_epoch = (size_t)std::max(0, atoi(e));
-      GCNB_CALL(gcnb_spmm_plan_stage_async_begin(st->graph_plan, dev_data.dev_graph_value.get(), 16, &st->stage_job));
-      st->graph_values_dev = dev_data.dev_graph_value.get();
-    } else if (wanted) {
+    const bool background = wanted && !st->dist && big > (size_t(8) << 20) && !(async_env && atoi(async_env) == 0);
+    if (const char *e = getenv("GCNB_STAGE_SWITCH_EPOCH")) st->stage_switch_epoch = (size_t)std::max(0, atoi(e));
+    st->graph_values_dev = dev_data.dev_graph_value.get();
+
+    if (wanted && st->dist) {
+      if (bt_on && d16) {
+        // Row-partitioned model: this rank's row block x all global columns.  The scales are the square roots of the
+        // diagonal values (the diagonal of local row i is global column row0 + i); every rank's block of scales is
+        // all-gathered so that all ranks use the same column scales.  Whether the path is used is agreed collectively
+        // (the exchange in graphsum() differs between the two paths).  Synchronous: every step below is collective.
+        const size_t nnz = dev_data.dev_graph_index.indices_size;
+        std::vector<natural> hp((size_t)N + 1), hi(nnz);
+        std::vector<real> hv(nnz);
+        CHECK_CUDA_ERROR(cudaStreamSynchronize(st->stream));
+        CHECK_CUDA_ERROR(cudaMemcpy(hp.data(), dev_data.dev_graph_index.dev_indptr.get(), hp.size() * sizeof(natural), cudaMemcpyDeviceToHost));
+        CHECK_CUDA_ERROR(cudaMemcpy(hi.data(), dev_data.dev_graph_index.dev_indices.get(), nnz * sizeof(natural), cudaMemcpyDeviceToHost));
+        CHECK_CUDA_ERROR(cudaMemcpy(hv.data(), dev_data.dev_graph_value.get(), nnz * sizeof(real), cudaMemcpyDeviceToHost));
+        const size_t world = (size_t)gcnb_comm_world(st->comm);
+        std::vector<real> s_loc(st->block, 0.f), s_all(world * st->block, 0.f);
+        for (size_t i = 0; i < N; i++)
+          for (natural k = hp[i]; k < hp[i + 1]; k++)
+            if (hi[k] == (natural)(st->row0 + i)) {
+              if (hv[k] > 0.f) s_loc[i] = sqrtf(hv[k]);
+              break;
+            }
+        dev_shared_ptr<real> d_loc(st->block), d_all(world * st->block);
+        CHECK_CUDA_ERROR(cudaMemcpy(d_loc.get(), s_loc.data(), st->block * sizeof(real), cudaMemcpyHostToDevice));
+        GCNB_CALL(gcnb_comm_all_gather_f32(st->comm, d_loc.get(), d_all.get(), (int64_t)st->block, st->stream));
+        CHECK_CUDA_ERROR(cudaStreamSynchronize(st->stream));
+        CHECK_CUDA_ERROR(cudaMemcpy(s_all.data(), d_all.get(), s_all.size() * sizeof(real), cudaMemcpyDeviceToHost));
+        for (real &x : s_all)
+          if (!(x > 0.f)) x = std::nanf("");  // no usable diagonal: entries of that row / column stay in the remainder
+        std::vector<real> s_rows(s_all.begin() + (ptrdiff_t)st->row0, s_all.begin() + (ptrdiff_t)(st->row0 + N));
+        gcnb_bittile_plan *bt = nullptr;
+        GCNB_CALL(gcnb_bittile_plan_create(hp.data(), hi.data(), hv.data(), (int64_t)N, (int64_t)st->n_global, s_rows.data(),
+                                           s_all.data(), 0, 0, 0, st->stream, &bt));
+        int64_t binfo[8];
+        GCNB_CALL(gcnb_bittile_plan_info(bt, binfo));
+        natural ok_flag = (binfo[0] > 0 && binfo[1] * 4 >= (int64_t)nnz) ? 1u : 0u;
+        dev_shared_ptr<natural> d_flag(1);
+        CHECK_CUDA_ERROR(cudaMemcpy(d_flag.get(), &ok_flag, sizeof(natural), cudaMemcpyHostToDevice));
+        GCNB_CALL(gcnb_comm_all_reduce_sum(st->comm, d_flag.get(), 1, 1, st->stream));
+        CHECK_CUDA_ERROR(cudaStreamSynchronize(st->stream));
+        CHECK_CUDA_ERROR(cudaMemcpy(&ok_flag, d_flag.get(), sizeof(natural), cudaMemcpyDeviceToHost));
+        if (ok_flag == (natural)world) {  // every rank has dense blocks worth the path
+          st->graph_bittile = bt;
+          GCNB_CALL(gcnb_spmm_plan_attach_bittile(st->graph_plan, bt, dev_data.dev_graph_value.get()));
+        } else {
+          gcnb_bittile_plan_destroy(bt);
+        }
+      }
       GCNB_CALL(gcnb_spmm_plan_stage(st->graph_plan, h_graph_indptr, h_graph_indices, dev_data.dev_graph_value.get(),
                                      16, st->stream));
       int64_t sinfo[8];
       GCNB_CALL(gcnb_spmm_plan_stage_info(st->graph_plan, sinfo));
       st->graph_staged = sinfo[0] != 0;
-    }
-  }
-  {
-    // opt-in (round-1 status: kernel parity-checked on B200, engine path not yet): the dense blocks of the adjacency as
-    // bit maps on the tcgen05 tensor cores (csrc/spmm_bittile.cu); takes precedence over the staged path at width 16.
-    // With GCNB_ASYNC_STAGE=1 (large graphs) the plan is built on a helper thread and attached at the staging switch.
-    const char *e = getenv("GCNB_BITTILE");
-    bool d16 = false;
-    for (const GCNLayer &ly : st->layers) d16 |= (ly.reorder ? ly.in_dim : ly.out_dim) == 16;
-    if (e && atoi(e) != 0 && st->dist && d16 && N > 0) {
-      // Row-partitioned model: this rank's row block x all global columns.  The scales are the square roots of the
-      // diagonal values (the diagonal of local row i is global column row0 + i); every rank's block of scales is
-      // all-gathered so that all ranks use the same column scales.  Whether the path is used is agreed collectively
-      // (the exchange in graphsum() differs between the two paths).  Synchronous: every step below is collective.
-      const size_t nnz = dev_data.dev_graph_index.indices_size;
-      std::vector<natural> hp((size_t)N + 1), hi(nnz);
-      std::vector<real> hv(nnz);
-      CHECK_CUDA_ERROR(cudaStreamSynchronize(st->stream));
-      CHECK_CUDA_ERROR(cudaMemcpy(hp.data(), dev_data.dev_graph_index.dev_indptr.get(), hp.size() * sizeof(natural), cudaMemcpyDeviceToHost));
-      CHECK_CUDA_ERROR(cudaMemcpy(hi.data(), dev_data.dev_graph_index.dev_indices.get(), nnz * sizeof(natural), cudaMemcpyDeviceToHost));
-      CHECK_CUDA_ERROR(cudaMemcpy(hv.data(), dev_data.dev_graph_value.get(), nnz * sizeof(real), cudaMemcpyDeviceToHost));
-      const size_t world = (size_t)gcnb_comm_world(st->comm);
-      std::vector<real> s_loc(st->block, 0.f), s_all(world * st->block, 0.f);
-      for (size_t i = 0; i < N; i++)
-        for (natural k = hp[i]; k < hp[i + 1]; k++)
-          if (hi[k] == (natural)(st->row0 + i)) {
-            if (hv[k] > 0.f) s_loc[i] = sqrtf(hv[k]);
-            break;
-          }
-      dev_shared_ptr<real> d_loc(st->block), d_all(world * st->block);
-      CHECK_CUDA_ERROR(cudaMemcpy(d_loc.get(), s_loc.data(), st->block * sizeof(real), cudaMemcpyHostToDevice));
-      GCNB_CALL(gcnb_comm_all_gather_f32(st->comm, d_loc.get(), d_all.get(), (int64_t)st->block, st->stream));
-      CHECK_CUDA_ERROR(cudaStreamSynchronize(st->stream));
-      CHECK_CUDA_ERROR(cudaMemcpy(s_all.data(), d_all.get(), s_all.size() * sizeof(real), cudaMemcpyDeviceToHost));
-      for (real &x : s_all)
-        if (!(x > 0.f)) x = std::nanf("");  // no usable diagonal: entries of that row / column stay in the remainder
-      std::vector<real> s_rows(s_all.begin() + (ptrdiff_t)st->row0, s_all.begin() + (ptrdiff_t)(st->row0 + N));
-      gcnb_bittile_plan *bt = nullptr;
-      GCNB_CALL(gcnb_bittile_plan_create(hp.data(), hi.data(), hv.data(), (int64_t)N, (int64_t)st->n_global, s_rows.data(),
-                                         s_all.data(), 0, 0, 0, st->stream, &bt));
-      int64_t binfo[8];
-      GCNB_CALL(gcnb_bittile_plan_info(bt, binfo));
-      natural ok_flag = (binfo[0] > 0 && binfo[1] * 4 >= (int64_t)nnz) ? 1u : 0u;
-      dev_shared_ptr<natural> d_flag(1);
-      CHECK_CUDA_ERROR(cudaMemcpy(d_flag.get(), &ok_flag, sizeof(natural), cudaMemcpyHostToDevice));
-      GCNB_CALL(gcnb_comm_all_reduce_sum(st->comm, d_flag.get(), 1, 1, st->stream));
-      CHECK_CUDA_ERROR(cudaStreamSynchronize(st->stream));
-      CHECK_CUDA_ERROR(cudaMemcpy(&ok_flag, d_flag.get(), sizeof(natural), cudaMemcpyDeviceToHost));
-      if (ok_flag == (natural)world) {  // every rank has dense blocks worth the path
-        st->graph_bittile = bt;
-        GCNB_CALL(gcnb_spmm_plan_attach_bittile(st->graph_plan, bt, dev_data.dev_graph_value.get()));
-      } else {
-        gcnb_bittile_plan_destroy(bt);
-      }
-    }
-    if (e && atoi(e) != 0 && !st->dist && d16 && N > 0) {
+    } else if (wanted) {
       const size_t nnz = dev_data.dev_graph_index.indices_size;
       const natural *d_ip = dev_data.dev_graph_index.dev_indptr.get(), *d_ix = dev_data.dev_graph_index.dev_indices.get();
       const real *d_gv = dev_data.dev_graph_value.get();
-      CHECK_CUDA_ERROR(cudaStreamSynchronize(st->stream));  // graph_value may have been computed on this stream
       // everything is read back from the device: the helper must not depend on the caller's host arrays
       auto make = [N, nnz, d_ip, d_ix, d_gv](cudaStream_t stream, gcnb_bittile_plan **out) -> int {
         *out = nullptr;
@@ -555,22 +560,38 @@ void GCN::init(bool quiet, const natural *h_graph_indptr, const natural *h_graph
         else gcnb_bittile_plan_destroy(bt);
         return 0;
       };
-      if (st->stage_job) {  // background mode is on
-        int device = 0;
-        CHECK_CUDA_ERROR(cudaGetDevice(&device));
-        GCNEngineState *state = st.get();
-        st->bt_thread = std::thread([state, make, device] {
-          cudaStream_t hs = nullptr;
-          int rc = (int)cudaSetDevice(device);
-          if (!rc) rc = (int)cudaStreamCreateWithFlags(&hs, cudaStreamNonBlocking);
-          if (!rc) rc = make(hs, &state->bt_pending);
-          if (hs) cudaStreamDestroy(hs);
-          state->bt_rc = rc;
-        });
+      CHECK_CUDA_ERROR(cudaStreamSynchronize(st->stream));  // graph_value may have been computed on this stream
+      if (background) {
+        st->setup_pending = true;
+        if (bt_on) {
+          int device = 0;
+          CHECK_CUDA_ERROR(cudaGetDevice(&device));
+          GCNEngineState *state = st.get();
+          st->bt_thread = std::thread([state, make, device, d_gv] {
+            cudaStream_t hs = nullptr;
+            int rc = (int)cudaSetDevice(device);
+            if (!rc) rc = (int)cudaStreamCreateWithFlags(&hs, cudaStreamNonBlocking);
+            if (!rc) rc = make(hs, &state->bt_pending);
+            if (hs) cudaStreamDestroy(hs);
+            // no dense blocks worth bit tiles: stage the windows instead (same helper, joined by finish_stage)
+            if (!rc && !state->bt_pending) rc = gcnb_spmm_plan_stage_async_begin(state->graph_plan, d_gv, 16, &state->stage_job);
+            state->bt_rc = rc;
+          });
+        } else {
+          GCNB_CALL(gcnb_spmm_plan_stage_async_begin(st->graph_plan, d_gv, 16, &st->stage_job));
+        }
       } else {
-        GCNB_CALL(make(st->stream, &st->graph_bittile));
-        if (st->graph_bittile)
-          GCNB_CALL(gcnb_spmm_plan_attach_bittile(st->graph_plan, st->graph_bittile, dev_data.dev_graph_value.get()));
+        if (bt_on) {
+          GCNB_CALL(make(st->stream, &st->graph_bittile));
+          if (st->graph_bittile)
+            GCNB_CALL(gcnb_spmm_plan_attach_bittile(st->graph_plan, st->graph_bittile, d_gv));
+        }
+        if (!st->graph_bittile) {
+          GCNB_CALL(gcnb_spmm_plan_stage(st->graph_plan, h_graph_indptr, h_graph_indices, d_gv, 16, st->stream));
+          int64_t sinfo[8];
+          GCNB_CALL(gcnb_spmm_plan_stage_info(st->graph_plan, sinfo));
+          st->graph_staged = sinfo[0] != 0;
+        }
       }
     }
   }
@@ -649,6 +670,10 @@ void GCN::set_reorder(bool on) {
 size_t GCN::launches_per_epoch() const { return st->launches_last_epoch; }
 bool GCN::graph_staged() const { return st->graph_staged; }
 bool GCN::graph_bittile() const { return st->graph_bittile != nullptr; }
+void GCN::path_info(int out[8]) const {
+  out[0] = st->graph_staged; out[1] = st->graph_bittile != nullptr; out[2] = st->dense_fast; out[3] = st->ax_ready;
+  out[4] = st->graphs_usable(); out[5] = st->setup_pending; out[6] = st->x_img.get() != nullptr; out[7] = st->dist;
+}
 size_t GCN::launches_total() const { return st->launches; }
 void GCN::set_time_graphsum(bool on) {
   st->drop_graphs();
@@ -765,7 +790,7 @@ void GCN::forward_pass(bool training, natural split, cudaStream_t s) {
     Variable::rng_consume(input_elems);  // the reference draws even when p == 0
     st->x_train_vals = xvals;
   }
-  if (!training && st->dense_fast && st->allow_reorder && !st->ax_tried && !st->stage_job) {  // after the staging switch
+  if (!training && st->dense_fast && st->allow_reorder && !st->ax_tried && !st->setup_pending) {  // after the staging switch
     st->ax_tried = true;
     if (st->dist) {
       if (st->ax_planned) {  // collective: every rank takes this branch (ax_planned depends on global sizes only)
@@ -995,7 +1020,7 @@ void GCN::train_body(cudaStream_t s) {
 void GCN::finish_setup() { st->finish_stage(); }
 
 std::pair<real, real> GCN::train_epoch() {
-  if (st->stage_job && st->train_calls >= st->stage_switch_epoch) st->finish_stage();
+  if (st->setup_pending && st->train_calls >= st->stage_switch_epoch) st->finish_stage();
   st->train_calls++;
   const size_t before = st->launches;
   cudaStream_t s = st->stream;

@@ -15,29 +15,13 @@ ge.load_package()
 eng = importlib.import_module("parallel_gcn_b200.engine")
 import bench  # noqa: E402
 
-def pubmed_root():
-    """pubmed ships without its .svmlight (reference .gitignore): a synthetic one in SURVEY 8d's shape (500 dims, 3 classes,
-    ~50 nnz per row, row-normalised values, seed 20230606) next to links to the shipped .graph / .split"""
-    import tempfile
-    import numpy as np
-    root = tempfile.mkdtemp(prefix="gcnb_pubmed_")
-    os.makedirs(os.path.join(root, "data"))
-    for ext in ("graph", "split"):
-        os.symlink(os.path.join(ROOT, "data", "pubmed." + ext), os.path.join(root, "data", "pubmed." + ext))
-    rng = np.random.default_rng(20230606)
-    n = sum(1 for _ in open(os.path.join(ROOT, "data", "pubmed.graph")))
-    with open(os.path.join(root, "data", "pubmed.svmlight"), "w") as f:
-        for _ in range(n):
-            k = int(rng.integers(30, 71))
-            cols = np.sort(rng.choice(500, k, replace=False))
-            f.write("%d %s\n" % (rng.integers(0, 3), " ".join("%d:%.6f" % (c, 1.0 / k) for c in cols)))
-    return root
+from tests.util import pubmed_root  # noqa: E402
 
 
 which = sys.argv[1:] or ["cora", "citeseer", "pubmed", "reddit600"]
 for name in which:
     if name in ("cora", "citeseer", "pubmed"):
-        ds = eng.parse_dataset(pubmed_root() if name == "pubmed" else ROOT, name)
+        ds = eng.parse_dataset(pubmed_root(ROOT) if name == "pubmed" else ROOT, name)
         g = eng.GCN(ds, epochs=100)
         g.train_epoch(); g.eval(2)
         r = g.timed_epochs(100, with_eval=True)

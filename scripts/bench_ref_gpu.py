@@ -29,15 +29,7 @@ REF_BIN = os.path.join(ROOT, "oracle", "_ref", "ref_gpu_bench")
 
 
 def dump(ds, d):
-    os.makedirs(d, exist_ok=True)
-    n = ds.num_nodes
-    with open(os.path.join(d, "meta.txt"), "w") as f:
-        f.write("%d %d %d %d %d\n" % (n, ds.input_dim, ds.output_dim, len(ds.g_indices), len(ds.f_indices)))
-    for name, arr, dt in (("g_indptr.u32", ds.g_indptr, np.uint32), ("g_indices.u32", ds.g_indices, np.uint32),
-                          ("f_indptr.u32", ds.f_indptr, np.uint32), ("f_indices.u32", ds.f_indices, np.uint32),
-                          ("f_value.f32", ds.f_value, np.float32), ("label.i32", ds.label, np.int32),
-                          ("split.u32", ds.split, np.uint32)):
-        np.ascontiguousarray(arr, dt).tofile(os.path.join(d, name))
+    importlib.import_module("bench").dump_dataset_raw(ds, d)
 
 
 def main():
@@ -79,7 +71,7 @@ def main():
             p = subprocess.run([REF_BIN, scratch, str(args.epochs), str(args.reps)], capture_output=True, text=True,
                                timeout=args.timeout)
             line = [l for l in p.stdout.splitlines() if l.startswith("{")]
-            if p.returncode == 0 and line:
+            if line and json.loads(line[-1]).get("cuda_error") == "no error":
                 ref = json.loads(line[-1])
                 ref.update(dataset=label, dump_s=round(t_dump, 2))
                 emit(ref)

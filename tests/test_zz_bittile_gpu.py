@@ -2,8 +2,8 @@
 against the oracle's CSR product, through the C ABI.  Tolerance: 1e-5 relative with the 1e-6 x max|want| floor (the
 result differs from the CSR product by the rounding of s_i * s_j against 1/sqrtf(deg_i * deg_j) and by summation order).
 
-The file sorts last on purpose: it is the newest kernel (first run on B200 in round 1, profiles/r1d_bittile_*).  The
-engine-level test is opt-in (GCNB_TEST_BITTILE_ENGINE=1) until that path has been run on a GPU."""
+The file sorts last on purpose: these are the newest kernels (every test here ran green on B200 in round 2,
+profiles/r2a_checklist_log.txt)."""
 import os
 
 import numpy as np
@@ -15,13 +15,11 @@ from tests.util import assert_close, to_dev, to_np
 # a wedged mbarrier pipeline must end the run, not hang it: pytest-timeout's thread method exits the process
 pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300, method="thread")]
 f32 = np.float32
-# 64-column tiles on bt_mma_kernel ran on B200 in round 1; the second-generation kernel (bt_mma_wide_kernel: unified
-# stage barriers; 128-column tiles or 256-row items sharing a B' stage) has only been compiled and emulated on the CPU so
-# far: opt-in.  A shape is (columns per tile, 128-row blocks per item).
-SHAPES = [(0, 0), (128, 1), (64, 2)] if os.environ.get("GCNB_TEST_BITTILE_WIDE") == "1" else [(0, 0)]
+# A shape is (columns per tile, 128-row blocks per item); (0, 0) = the default (128 x 128 tiles)
+SHAPES = [(0, 0), (64, 1), (64, 2)]
 
 
-def _check(O, gcnb, dev, indptr, indices, values, rs=None, cs=None, min_tile_nnz=0, seed=0, shape=(0, 0)):
+def _check(O, gcnb, dev, indptr, indices, values, rs=None, cs=None, min_tile_nnz=0, seed=0, shape=(0, 0), want_ell=None):
     import torch
     n = len(indptr) - 1
     x = np.random.default_rng(seed).standard_normal((n, 16)).astype(f32)
@@ -31,6 +29,8 @@ def _check(O, gcnb, dev, indptr, indices, values, rs=None, cs=None, min_tile_nnz
                             row_blocks=shape[1])
     info = plan.info()
     assert info["tile_nnz"] + info["rem_nnz"] == len(indices)
+    if want_ell is not None:
+        assert bool(info["ell"]) == want_ell, info
     d_x = to_dev(x, dev)
     out = torch.full((n, 16), float("nan"), device=dev)
     plan.spmm16(d_x, out)
@@ -50,8 +50,8 @@ def _check(O, gcnb, dev, indptr, indices, values, rs=None, cs=None, min_tile_nnz
 def test_community_graph_matches_oracle(O, gcnb, dev, cfg, shape):
     rng = np.random.default_rng(cfg["n"])
     indptr, indices, values = gcn_graph(rng, cfg["n"], cfg["comm"], cfg["intra"], cfg["inter"])
-    info = _check(O, gcnb, dev, indptr, indices, values, min_tile_nnz=cfg["thr"] * (1 if shape == (0, 0) else 2), seed=1,
-                  shape=shape)
+    info = _check(O, gcnb, dev, indptr, indices, values, min_tile_nnz=cfg["thr"] * (1 if shape == (64, 1) else 2), seed=1,
+                  shape=shape, want_ell=True)  # GraphSum values factor: the remainder is the pattern-only gather
     assert info["n_tiles"] > 0 and info["tile_nnz"] > 0.4 * len(indices)
 
 
@@ -78,13 +78,51 @@ def test_duplicates_missing_diagonals_unfactored_values_and_sparse_graphs(O, gcn
     _check(O, gcnb, dev, indptr, indices, values, min_tile_nnz=64, seed=3)
     values2 = values.copy()
     values2[::7] *= 1.5  # not s_i * s_j: those entries must keep their value (remainder)
-    _check(O, gcnb, dev, indptr, indices, values2, min_tile_nnz=64, seed=4)
+    _check(O, gcnb, dev, indptr, indices, values2, min_tile_nnz=64, seed=4, want_ell=False)  # valued remainder: generic kernel
     # nothing dense enough: everything is remainder, no MMA launch
     n = 4000
     ip = np.arange(0, 3 * n + 1, 3, dtype=np.uint32)
     ix = rng.integers(0, n, 3 * n).astype(np.uint32)
     info = _check(O, gcnb, dev, ip, ix, rng.standard_normal(3 * n).astype(f32), seed=5)
     assert info["n_tiles"] == 0
+
+
+@pytest.mark.parametrize("case", ["short", "mixed", "long"])
+def test_pattern_only_ell_gather_matches_float64(gcnb, dev, case):
+    """csrc/spmm_ell.cu on its own: R = diag(row_scale) * pattern * B2 (the remainder kernel of the bit-tile plans)"""
+    import torch
+    rng = np.random.default_rng({"short": 1, "mixed": 2, "long": 3}[case])
+    if case == "short":
+        n_rows, n_cols = 5003, 4000
+        lens = rng.integers(0, 60, n_rows)
+    elif case == "mixed":
+        n_rows, n_cols = 3001, 50000
+        lens = rng.integers(0, 700, n_rows)  # rows above 256 entries: wide bundles
+        lens[::97] = 0
+    else:
+        n_rows, n_cols = 40, 3000
+        lens = rng.integers(0, 30, n_rows)
+        lens[[3, 17, 30]] = [20000, 8193, 9000]  # cut rows: parts, partial slots, combine kernel
+    indptr = np.zeros(n_rows + 1, np.uint32)
+    indptr[1:] = np.cumsum(lens)
+    indices = rng.integers(0, n_cols, int(indptr[-1])).astype(np.uint32)
+    B2 = np.zeros((n_cols + 1, 16), f32)
+    B2[:n_cols] = rng.standard_normal((n_cols, 16)).astype(f32)
+    rs = (0.5 + rng.random(n_rows)).astype(f32)
+    want = np.zeros((n_rows, 16), np.float64)
+    np.add.at(want, np.repeat(np.arange(n_rows), lens), B2[indices].astype(np.float64))
+    want *= rs[:, None].astype(np.float64)
+    plan = gcnb.EllPlan(indptr, indices, n_cols)
+    d_B2, d_rs = to_dev(B2, dev), to_dev(rs, dev)
+    out = torch.full((n_rows, 16), float("nan"), device=dev)
+    plan.gather16(d_B2, d_rs, out)
+    torch.cuda.synchronize()
+    assert_close(to_np(out), want, what="ELL gather " + case)
+    out2 = torch.full((n_rows, 16), float("nan"), device=dev)
+    for _ in range(3):  # the ticket counter re-arms itself; fixed summation order => identical bits
+        plan.gather16(d_B2, d_rs, out2)
+    assert torch.equal(out, out2)
+    plan.close()
 
 
 def test_attached_plan_routes_only_matching_calls(O, gcnb, dev):
@@ -116,18 +154,19 @@ def test_attached_plan_routes_only_matching_calls(O, gcnb, dev):
     bt.close()
 
 
-@pytest.mark.skipif(os.environ.get("GCNB_TEST_BITTILE_ENGINE") != "1", reason="opt-in: engine path not yet run on a GPU")
 def test_engine_training_with_bit_tiles_matches_default_path(gcnb, dev):
     import importlib
     eng = importlib.import_module("parallel_gcn_b200.engine")
 
     def run(flag):
-        os.environ["GCNB_BITTILE"] = flag
+        if flag is not None:
+            os.environ["GCNB_BITTILE"] = flag
         try:
             # 8 communities of 2500 nodes, ~160 neighbours inside: 6 % dense blocks; small enough for CUDA-graph replay,
             # so the captured epoch contains the bit-tile fork / join as well
             ds = eng.synth_dataset(20000, 20000 * 100, 32, 6, n_blocks=8, seed=11)
             g = eng.GCN(ds, hidden_dims=(16,), dropouts=(0.5, 0.5))
+            assert g.graph_bittile() == (flag is None) and g.uses_cuda_graph()
             hist = [(g.train_epoch(), g.eval(2)) for _ in range(4)]
             w = [g.weight(l) for l in range(2)]
             launches = g.launches_per_epoch()
@@ -136,15 +175,14 @@ def test_engine_training_with_bit_tiles_matches_default_path(gcnb, dev):
         finally:
             os.environ.pop("GCNB_BITTILE", None)
 
-    (h0, w0, l0), (h1, w1, l1) = run("0"), run("1")
-    assert l1 != l0, "GCNB_BITTILE=1 did not change the GraphSum path (pack + MMA + remainder + add = 4 launches)"
+    (h0, w0, l0), (h1, w1, l1) = run("0"), run(None)
+    assert l1 != l0, "bit tiles (the default) did not change the GraphSum path (pack + MMA + remainder + add = 4 launches)"
     for ep, ((t0, v0), (t1, v1)) in enumerate(zip(h0, h1)):
         assert abs(t0[0] - t1[0]) <= 2e-5 * (1 + ep) * abs(t0[0]) and abs(v0[0] - v1[0]) <= 2e-5 * (1 + ep) * abs(v0[0])
     for a, b in zip(w0, w1):
         assert_close(b, a, rtol=1e-4, atol=1e-6, what="weights after 4 epochs")
 
 
-@pytest.mark.skipif(os.environ.get("GCNB_TEST_BITTILE_WIDE") != "1", reason="opt-in: strided slabs not yet run on a GPU")
 def test_wide_operands_run_as_16_column_slabs(O, gcnb, dev):
     import torch
     rng = np.random.default_rng(9)
@@ -167,7 +205,6 @@ def test_wide_operands_run_as_16_column_slabs(O, gcnb, dev):
 
 # ---- background staging of the window-staged GraphSum (spmm_stage.cu, gcnb_spmm_plan_stage_async_*): opt-in until it has
 # ---- been run on a GPU (GCNB_TEST_ASYNC_STAGE=1)
-@pytest.mark.skipif(os.environ.get("GCNB_TEST_ASYNC_STAGE") != "1", reason="opt-in: background staging not yet run on a GPU")
 def test_background_staging_attaches_the_same_plan(gcnb, dev):
     import torch
     from tests.test_stage_cpu import community_csr
@@ -198,36 +235,49 @@ def test_background_staging_attaches_the_same_plan(gcnb, dev):
     sync_plan.close()
 
 
-@pytest.mark.skipif(os.environ.get("GCNB_TEST_ASYNC_STAGE") != "1", reason="opt-in: background staging not yet run on a GPU")
-def test_engine_background_staging_switches_at_a_fixed_epoch(gcnb, dev):
+def test_engine_background_setup_switches_at_a_fixed_epoch(gcnb, dev):
+    """graphs too large for CUDA-graph replay build their static GraphSum representation on a helper thread and attach it
+    before a FIXED training epoch: bit tiles when the graph has dense blocks, window staging otherwise (or with
+    GCNB_BITTILE=0); a synchronous build (GCNB_ASYNC_STAGE=0) ends in the same representation"""
     import importlib
     eng = importlib.import_module("parallel_gcn_b200.engine")
-    # > 8 Mi entries so that CUDA-graph replay is off and background staging applies
-    ds = eng.synth_dataset(60000, 60000 * 80, 16, 6, n_blocks=12, seed=3)
+    # > 8 Mi entries so that CUDA-graph replay is off and the background build applies
+    # communities of 7500 nodes, 0.85 % dense: windows of 3072 columns hold ~26 entries of a row (staged), 128 x 128 cells
+    # hold ~140 (no tiles); communities of 2500 nodes, 2.6 % dense: ~420 entries per 128 x 128 cells (bit tiles)
+    sparse_blocks = eng.synth_dataset(60000, 60000 * 80, 16, 6, n_blocks=8, sigma=1.0, seed=3)
+    dense_blocks = eng.synth_dataset(60000, 60000 * 80, 16, 6, n_blocks=24, sigma=1.0, seed=3)
 
-    def run(env):
+    def run(ds, env):
         os.environ.update(env)
         try:
             g = eng.GCN(ds, hidden_dims=(16,), dropouts=(0.5, 0.5))
-            staged0 = g.graph_staged()
+            p0 = g.path_info()
             hist = [(g.train_epoch(), g.eval(2)) for _ in range(5)]
-            staged1 = g.graph_staged()
+            p1 = g.path_info()
             w = [g.weight(l) for l in range(2)]
             g.close()
-            return hist, w, staged0, staged1
+            return hist, w, p0, p1
         finally:
             for k in env:
                 os.environ.pop(k, None)
 
-    h0, w0, a0, a1 = run({})
-    h1, w1, b0, b1 = run({"GCNB_ASYNC_STAGE": "1", "GCNB_STAGE_SWITCH_EPOCH": "2"})
-    h2, w2, _, _ = run({"GCNB_ASYNC_STAGE": "1", "GCNB_STAGE_SWITCH_EPOCH": "2"})
-    assert a0 and a1 and not b0 and b1
-    assert h1 == h2 and all(np.array_equal(x, y) for x, y in zip(w1, w2)), "fixed switch epoch => reproducible bits"
-    for ep, ((t0, v0), (t1, v1)) in enumerate(zip(h0, h1)):
-        assert abs(t0[0] - t1[0]) <= 2e-5 * (1 + ep) * abs(t0[0]) and abs(v0[0] - v1[0]) <= 2e-5 * (1 + ep) * abs(v0[0])
-    for a, b in zip(w0, w1):
-        assert_close(b, a, rtol=1e-4, atol=1e-6, what="weights after 5 epochs")
+    def same_curve(a, b):
+        for ep, ((t0, v0), (t1, v1)) in enumerate(zip(a[0], b[0])):
+            assert abs(t0[0] - t1[0]) <= 2e-5 * (1 + ep) * abs(t0[0]) and abs(v0[0] - v1[0]) <= 2e-5 * (1 + ep) * abs(v0[0])
+        for x, y in zip(a[1], b[1]):
+            assert_close(y, x, rtol=1e-4, atol=1e-6, what="weights after 5 epochs")
+
+    sw = {"GCNB_STAGE_SWITCH_EPOCH": "2"}
+    for ds, kind in ((sparse_blocks, "graph_staged"), (dense_blocks, "graph_bittile")):
+        sync = run(ds, {"GCNB_ASYNC_STAGE": "0"})
+        assert sync[2][kind] and sync[3][kind] and not sync[2]["setup_pending"], (kind, sync[2], sync[3])
+        bg1, bg2 = run(ds, sw), run(ds, sw)
+        assert bg1[2]["setup_pending"] and not bg1[2][kind] and bg1[3][kind] and not bg1[3]["setup_pending"], (kind, bg1[2], bg1[3])
+        assert bg1[0] == bg2[0] and all(np.array_equal(x, y) for x, y in zip(bg1[1], bg2[1])), "fixed switch epoch => reproducible bits"
+        same_curve(sync, bg1)
+    staged = run(dense_blocks, dict(sw, GCNB_BITTILE="0"))
+    assert staged[3]["graph_staged"] and not staged[3]["graph_bittile"]
+    same_curve(run(dense_blocks, {"GCNB_ASYNC_STAGE": "0"}), staged)
 
 
 # ---- exact-split tcgen05 GEMM for the wide first layer (csrc/dense_tc.cu): opt-in until it has been run on a GPU
@@ -271,7 +321,6 @@ def test_exact_split_weight_gradient_matches_float64(gcnb, dev, n, f, p):
 
 # ---- engine parity on random ragged SYMMETRIC datasets (duplicate edges, explicit self entries, isolated and unlabelled
 # ---- nodes, rows without features): opt-in (GCNB_TEST_RAGGED_ENGINE=1) until it has been run once on a GPU
-@pytest.mark.skipif(os.environ.get("GCNB_TEST_RAGGED_ENGINE") != "1", reason="opt-in: new inputs for the engine, not yet run")
 def test_engine_matches_oracle_on_random_ragged_symmetric_datasets(O, gcnb, dev, tmp_path):
     import importlib
     eng = importlib.import_module("parallel_gcn_b200.engine")

@@ -40,3 +40,23 @@ def random_csr(rng, n_rows, n_cols, mean_deg, heavy_rows=(), empty_rows=()):
     indptr[1:] = np.cumsum(deg)
     indices = rng.integers(0, n_cols, int(indptr[-1])).astype(np.uint32)
     return indptr, indices
+
+
+def pubmed_root(root):
+    """pubmed ships without its .svmlight (reference .gitignore): a synthetic one in SURVEY 8d's shape (500 dims, 3 classes,
+    30-70 nnz per row, row-normalised values, seed 20230606) next to links to the shipped .graph / .split.  Returns a
+    directory laid out like the repository root (data/pubmed.*)."""
+    import os
+    import tempfile
+    out = tempfile.mkdtemp(prefix="gcnb_pubmed_")
+    os.makedirs(os.path.join(out, "data"))
+    for ext in ("graph", "split"):
+        os.symlink(os.path.join(root, "data", "pubmed." + ext), os.path.join(out, "data", "pubmed." + ext))
+    rng = np.random.default_rng(20230606)
+    n = sum(1 for _ in open(os.path.join(root, "data", "pubmed.graph")))
+    with open(os.path.join(out, "data", "pubmed.svmlight"), "w") as f:
+        for _ in range(n):
+            k = int(rng.integers(30, 71))
+            cols = np.sort(rng.choice(500, k, replace=False))
+            f.write("%d %s\n" % (rng.integers(0, 3), " ".join("%d:%.6f" % (c, 1.0 / k) for c in cols)))
+    return out
