@@ -238,7 +238,7 @@ GCNB_API int gcnb_matmul_tn_f32(const float *d_A, const float *d_dC, float *d_dB
  * covered state g (src/variable.cu:5-11,44-61; src/module.cu:16-63).  The caller describes "earlier ops" by
  * up to GCNB_MAX_RNG_HIST (n_groups, count) pairs: t(g) = sum(count_i for n_groups_i > g).
  * ------------------------------------------------------------------------------------------------- */
-#define GCNB_MAX_RNG_HIST 16
+#define GCNB_MAX_RNG_HIST 48 /* an L-layer model has up to 2L distinct RNG consumer sizes: models up to 24 layers */
 typedef struct {
   uint32_t seed;
   uint32_t group_offset; /* row-partitioned ranks: a local slab whose element 0 is GLOBAL element e0 passes        */
@@ -341,7 +341,7 @@ GCNB_API int gcnb_softmax_ce_f32(float *d_logits, float *d_grad, const int32_t *
  * Adam::step (src/optim.cu:42-95) for up to GCNB_MAX_TENSORS weights in ONE launch, and
  * GCN::get_l2_penalty (src/gcn.cu:230-260) as a fixed-order sum of squares.
  * ------------------------------------------------------------------------------------------------- */
-#define GCNB_MAX_TENSORS 16
+#define GCNB_MAX_TENSORS 48
 typedef struct {
   int n_tensors;
   float *w[GCNB_MAX_TENSORS];

@@ -120,6 +120,13 @@ GCNB_API int gcnb_gcn_uses_cuda_graph(const gcnb_gcn *g);
  * out[2] = number of GraphSum launches, out[3] = CUDA kernels launched in the region */
 GCNB_API int gcnb_gcn_timed_epochs(gcnb_gcn *g, int n_epochs, int with_eval, int time_graphsum, float out[4]);
 
+/* Host-only view of the stateless-Philox bookkeeping behind Variable (src/variable.cu:13-26 keeps a state array; here the
+ * consumption history IS the state): reset = Variable::initialize_random(), consume = "an RNG op over n_elements ran"
+ * (64-bit: GLOBAL element counts of row-partitioned models), descriptor = what the next RNG kernel receives.  No CUDA. */
+GCNB_API int gcnb_rng_history_reset(void);
+GCNB_API int gcnb_rng_history_consume(uint64_t n_elements);
+GCNB_API int gcnb_rng_history_descriptor(gcnb_rng_t *out);
+
 /* ---- synthetic workloads (BASELINE.json configs 3-5; deterministic in seed, independent of thread count) ----
  * Symmetric simple graph with `n_blocks` contiguous planted communities: undirected edges are drawn with endpoint
  * probability proportional to a lognormal(sigma) weight (expected-degree model, weights clipped so that no expected

@@ -18,8 +18,8 @@ if not os.path.exists(LIB_PATH):
 lib = C.CDLL(LIB_PATH)
 P, I64, I32, U32, F32 = C.c_void_p, C.c_int64, C.c_int, C.c_uint32, C.c_float
 
-MAX_RNG_HIST = 16
-MAX_TENSORS = 16
+MAX_RNG_HIST = 48  # GCNB_MAX_RNG_HIST / GCNB_MAX_TENSORS of include/gcnb.h
+MAX_TENSORS = 48
 
 
 class RngT(C.Structure):

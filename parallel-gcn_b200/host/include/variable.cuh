@@ -36,6 +36,6 @@ class Variable {
 
   // RNG bookkeeping shared with Dropout
   static gcnb_rng_t rng_descriptor();            // history so far, seed = CudaParams::SEED
-  static void rng_consume(natural n_elements);   // an RNG op over n_elements just ran
+  static void rng_consume(size_t n_elements);    // an RNG op over n_elements just ran (64-bit: global counts of partitioned models)
 };
 #endif

@@ -387,6 +387,21 @@ int gcnb_gcn_finish_setup(gcnb_gcn *g) {
   g->gcn->finish_setup();
   return 0;
 }
+
+// host-only access to the Philox consumption bookkeeping (Variable::rng_history), for tests: no CUDA call
+int gcnb_rng_history_reset(void) {
+  Variable::initialize_random();
+  return 0;
+}
+int gcnb_rng_history_consume(uint64_t n_elements) {
+  Variable::rng_consume((size_t)n_elements);
+  return 0;
+}
+int gcnb_rng_history_descriptor(gcnb_rng_t *out) {
+  if (!out) return GCNB_E_BADARG;
+  *out = Variable::rng_descriptor();
+  return 0;
+}
 int gcnb_gcn_uses_cuda_graph(const gcnb_gcn *g) { return g ? (int)g->gcn->uses_cuda_graph() : -1; }
 int gcnb_gcn_graph_staged(const gcnb_gcn *g) { return g ? (int)g->gcn->graph_staged() : -1; }
 int gcnb_gcn_graph_bittile(const gcnb_gcn *g) { return g ? (int)g->gcn->graph_bittile() : -1; }

@@ -541,7 +541,9 @@ void GCN::init(bool quiet, const natural *h_graph_indptr, const natural *h_graph
       const natural *d_ip = dev_data.dev_graph_index.dev_indptr.get(), *d_ix = dev_data.dev_graph_index.dev_indices.get();
       const real *d_gv = dev_data.dev_graph_value.get();
       // everything is read back from the device: the helper must not depend on the caller's host arrays
-      auto make = [N, nnz, d_ip, d_ix, d_gv](cudaStream_t stream, gcnb_bittile_plan **out) -> int {
+      int64_t min_cover = 25;  // per cent of the entries that must sit in tiles (GCNB_BT_MIN_COVERAGE: tuning / test probe)
+      if (const char *e = getenv("GCNB_BT_MIN_COVERAGE")) min_cover = std::max(0, atoi(e));
+      auto make = [N, nnz, d_ip, d_ix, d_gv, min_cover](cudaStream_t stream, gcnb_bittile_plan **out) -> int {
         *out = nullptr;
         std::vector<natural> hp((size_t)N + 1), hi(nnz);
         std::vector<real> hv(nnz);
@@ -556,7 +558,7 @@ void GCN::init(bool quiet, const natural *h_graph_indptr, const natural *h_graph
         if (rc) return rc;
         int64_t binfo[8];
         gcnb_bittile_plan_info(bt, binfo);
-        if (binfo[0] > 0 && binfo[1] * 4 >= (int64_t)nnz) *out = bt;  // worth it when a quarter of the entries sit in tiles
+        if (binfo[0] > 0 && binfo[1] * 100 >= (int64_t)nnz * min_cover) *out = bt;  // worth it when a quarter of the entries sit in tiles
         else gcnb_bittile_plan_destroy(bt);
         return 0;
       };

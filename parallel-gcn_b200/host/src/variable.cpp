@@ -34,7 +34,16 @@ gcnb_rng_t Variable::rng_descriptor() {
   return r;
 }
 
-void Variable::rng_consume(natural n_elements) { rng_history[CEIL(n_elements, 4)] += 1; }
+void Variable::rng_consume(size_t n_elements) {
+  // GLOBAL element counts of a row-partitioned model exceed 32 bits long before a rank's share does: count the Philox
+  // groups in 64 bits; the descriptor's group index is 32-bit (up to 16 Gi elements per consumer), beyond that fail loudly
+  const uint64_t groups = ((uint64_t)n_elements + 3) / 4;
+  if (groups > 0xffffffffull) {
+    std::cerr << "Variable::rng_consume: " << n_elements << " elements exceed the 2^34-element range of the Philox descriptor" << std::endl;
+    exit(EXIT_FAILURE);
+  }
+  rng_history[(natural)groups] += 1;
+}
 
 void Variable::glorot() const {
   if (!rng_initialized) {

@@ -425,3 +425,31 @@ def test_binary_container_roundtrip_is_bit_identical(tmp_path):
     (tmp_path / "junk.gcnb").write_bytes(b"x" * 4096)
     assert eng.load_dataset(tmp_path / "junk.gcnb") is None
     assert eng.load_dataset(tmp_path / "missing.gcnb") is None
+
+
+def test_rng_history_counts_global_elements_in_64_bits():
+    """a row-partitioned model consumes GLOBAL element counts (8 M nodes x 602 features > 2^32); the Philox
+    group count must not wrap, and distinct consumer sizes up to the table's capacity must fit (deep models)."""
+    import ctypes as C
+    import importlib
+    import __graft_entry__ as ge
+    ge.load_package()
+    b = importlib.import_module("parallel_gcn_b200.binding")
+    lib = b.lib
+    lib.gcnb_rng_history_consume.argtypes = [C.c_uint64]
+    lib.gcnb_rng_history_descriptor.argtypes = [C.c_void_p]
+    assert lib.gcnb_rng_history_reset() == 0
+    big = 8_000_000 * 602            # 4.8e9 elements > 2^32
+    for n in (big, big, (1 << 32) + 5, 7):
+        assert lib.gcnb_rng_history_consume(n) == 0
+    r = b.RngT()
+    assert lib.gcnb_rng_history_descriptor(C.byref(r)) == 0
+    got = {int(r.hist_groups[i]): int(r.hist_count[i]) for i in range(r.n_hist)}
+    assert got == {(big + 3) // 4: 2, ((1 << 32) + 5 + 3) // 4: 1, 2: 1}
+    assert (big + 3) // 4 > (big % (1 << 32) + 3) // 4, "the old 32-bit count would have recorded a truncated prefix"
+    # 40 distinct consumer sizes (a 20-layer model) fit the descriptor
+    lib.gcnb_rng_history_reset()
+    for k in range(40):
+        lib.gcnb_rng_history_consume(1000 + 4 * k)
+    assert lib.gcnb_rng_history_descriptor(C.byref(r)) == 0 and r.n_hist == 40 and b.MAX_RNG_HIST >= 40
+    lib.gcnb_rng_history_reset()

@@ -242,10 +242,10 @@ def test_engine_background_setup_switches_at_a_fixed_epoch(gcnb, dev):
     import importlib
     eng = importlib.import_module("parallel_gcn_b200.engine")
     # > 8 Mi entries so that CUDA-graph replay is off and the background build applies
-    # communities of 7500 nodes, 0.85 % dense: windows of 3072 columns hold ~26 entries of a row (staged), 128 x 128 cells
-    # hold ~140 (no tiles); communities of 2500 nodes, 2.6 % dense: ~420 entries per 128 x 128 cells (bit tiles)
-    sparse_blocks = eng.synth_dataset(60000, 60000 * 80, 16, 6, n_blocks=8, sigma=1.0, seed=3)
-    dense_blocks = eng.synth_dataset(60000, 60000 * 80, 16, 6, n_blocks=24, sigma=1.0, seed=3)
+    # communities of 2500 nodes, 2.6 % dense: ~420 entries per 128 x 128 cells (bit tiles) and ~80 entries of a row per
+    # window of 3072 columns (window staging, when bit tiles are refused: GCNB_BT_MIN_COVERAGE=101 makes the builder find
+    # "no dense blocks worth it", the fallback inside the same helper thread)
+    ds = eng.synth_dataset(60000, 60000 * 80, 16, 6, n_blocks=24, sigma=1.0, seed=3)
 
     def run(ds, env):
         os.environ.update(env)
@@ -268,16 +268,19 @@ def test_engine_background_setup_switches_at_a_fixed_epoch(gcnb, dev):
             assert_close(y, x, rtol=1e-4, atol=1e-6, what="weights after 5 epochs")
 
     sw = {"GCNB_STAGE_SWITCH_EPOCH": "2"}
-    for ds, kind in ((sparse_blocks, "graph_staged"), (dense_blocks, "graph_bittile")):
-        sync = run(ds, {"GCNB_ASYNC_STAGE": "0"})
-        assert sync[2][kind] and sync[3][kind] and not sync[2]["setup_pending"], (kind, sync[2], sync[3])
-        bg1, bg2 = run(ds, sw), run(ds, sw)
-        assert bg1[2]["setup_pending"] and not bg1[2][kind] and bg1[3][kind] and not bg1[3]["setup_pending"], (kind, bg1[2], bg1[3])
+    curves = []
+    for extra, kind in (({}, "graph_bittile"), ({"GCNB_BT_MIN_COVERAGE": "101"}, "graph_staged"), ({"GCNB_BITTILE": "0"}, "graph_staged")):
+        other = "graph_staged" if kind == "graph_bittile" else "graph_bittile"
+        sync = run(ds, dict(extra, GCNB_ASYNC_STAGE="0"))
+        assert sync[2][kind] and sync[3][kind] and not sync[2][other] and not sync[2]["setup_pending"], (extra, sync[2], sync[3])
+        bg1, bg2 = run(ds, dict(extra, **sw)), run(ds, dict(extra, **sw))
+        assert bg1[2]["setup_pending"] and not bg1[2][kind] and bg1[3][kind] and not bg1[3][other] and not bg1[3]["setup_pending"], \
+            (extra, bg1[2], bg1[3])
         assert bg1[0] == bg2[0] and all(np.array_equal(x, y) for x, y in zip(bg1[1], bg2[1])), "fixed switch epoch => reproducible bits"
         same_curve(sync, bg1)
-    staged = run(dense_blocks, dict(sw, GCNB_BITTILE="0"))
-    assert staged[3]["graph_staged"] and not staged[3]["graph_bittile"]
-    same_curve(run(dense_blocks, {"GCNB_ASYNC_STAGE": "0"}), staged)
+        curves.append(sync)
+    same_curve(curves[0], curves[1])
+    same_curve(curves[1], curves[2])
 
 
 # ---- exact-split tcgen05 GEMM for the wide first layer (csrc/dense_tc.cu): opt-in until it has been run on a GPU
