@@ -142,6 +142,8 @@ GCNB_API int gcnb_bittile_supported(void);
  * (+ 100000 when the remainder runs on the pattern-only ELL kernel below), CTAs, bit-map bytes, packed-B bytes} */
 GCNB_API int gcnb_bittile_plan_info(const gcnb_bittile_plan *plan, int64_t out[8]);
 GCNB_API int gcnb_bittile_spmm16_f32(gcnb_bittile_plan *plan, const float *d_B, float *d_C, gcnb_stream_t stream);
+/* kernels launched per 16-column product (pack, MMA kernel, remainder [+ combine], [+ final add]) */
+GCNB_API int gcnb_bittile_plan_launches(const gcnb_bittile_plan *plan);
 /* Routes later gcnb_spmm_f32 / gcnb_spmm_ld_f32 calls on `plan` that use exactly this d_values pointer, no permutation,
  * 16 contiguous columns (ldb == ldc == 16) through the bit-tile plan (built from the same CSR and the same values);
  * every other call is unaffected.  The bit-tile plan is borrowed (destroy it after the spmm plan); bt = NULL detaches. */

@@ -362,7 +362,9 @@ struct BtArgs {
   const uint2 *items;
   const uint8_t *packed;    // chunks of kBtChunkBytes
   const float *row_scale;
-  float *P;                 // [n_blk * 128][16]
+  float *P;                 // [n_blk * 128][16]: the tiles' partial rows (C == nullptr)
+  float *C;                 // or: the product itself, zeroed by the pack kernel; partial rows are ADDED (row stride ldc)
+  int64_t ldc;
   int64_t n_rows;
 };
 
@@ -371,12 +373,15 @@ struct BtArgs {
 // One thread = 8 consecutive rows of B x one column: three 16-byte stores.
 __global__ void __launch_bounds__(256) bt_pack_kernel(const float *__restrict__ B, const float *__restrict__ col_scale,
                                                       uint8_t *__restrict__ packed, float *__restrict__ B2, int64_t n_cols,
-                                                      int64_t n_groups) {
+                                                      int64_t n_groups, float *__restrict__ Cz, int64_t ldc, int64_t n_rows) {
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t g = tid >> 4;
   const int col = (int)(tid & 15);
   if (g >= n_groups) return;
   const int64_t j0 = g * 8;
+  if (Cz)  // merge by reduction (bt_slab16): the product starts from zero
+    for (int i = 0; i < 8; i++)
+      if (j0 + i < n_rows) Cz[(j0 + i) * ldc + col] = 0.f;
   uint32_t hi[4], mid[4], lo[4];
 #pragma unroll
   for (int i = 0; i < 8; i++) {
@@ -419,12 +424,16 @@ __global__ void __launch_bounds__(256) bt_pack_kernel(const float *__restrict__ 
 // The same packing for a 16-column slab of a wider row-major matrix (row stride ldb floats)
 __global__ void __launch_bounds__(256) bt_pack_ld_kernel(const float *__restrict__ B, int64_t ldb,
                                                          const float *__restrict__ col_scale, uint8_t *__restrict__ packed,
-                                                         float *__restrict__ B2, int64_t n_cols, int64_t n_groups) {
+                                                         float *__restrict__ B2, int64_t n_cols, int64_t n_groups,
+                                                         float *__restrict__ Cz, int64_t ldc, int64_t n_rows) {
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t g = tid >> 4;
   const int col = (int)(tid & 15);
   if (g >= n_groups) return;
   const int64_t j0 = g * 8;
+  if (Cz)
+    for (int i = 0; i < 8; i++)
+      if (j0 + i < n_rows) Cz[(j0 + i) * ldc + col] = 0.f;
   uint32_t hi[4], mid[4], lo[4];
 #pragma unroll
   for (int i = 0; i < 8; i++) {
@@ -626,10 +635,21 @@ __global__ void __maxnreg__(72) bt_mma_wide_kernel(BtArgs a) {  // no spills at 
 #pragma unroll
           for (int i = 0; i < 16; i++) tot[i] = p == 2 ? s0[i] : tot[i] + s0[i];
         }
-        float4 *dst = reinterpret_cast<float4 *>(a.P + row * 16);
+        if (a.C) {  // merge by reduction: whichever of this kernel and the remainder kernel finishes a row first, 0 + p + r
+          if (row < a.n_rows) {
+            float *dst = a.C + row * a.ldc;
 #pragma unroll
-        for (int i = 0; i < 4; i++)
-          dst[i] = make_float4(sc * tot[4 * i], sc * tot[4 * i + 1], sc * tot[4 * i + 2], sc * tot[4 * i + 3]);
+            for (int i = 0; i < 4; i++)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * i), "f"(sc * tot[4 * i]),
+                           "f"(sc * tot[4 * i + 1]), "f"(sc * tot[4 * i + 2]), "f"(sc * tot[4 * i + 3])
+                           : "memory");
+          }
+        } else {
+          float4 *dst = reinterpret_cast<float4 *>(a.P + row * 16);
+#pragma unroll
+          for (int i = 0; i < 4; i++)
+            dst[i] = make_float4(sc * tot[4 * i], sc * tot[4 * i + 1], sc * tot[4 * i + 2], sc * tot[4 * i + 3]);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -731,6 +751,7 @@ struct gcnb_bittile_plan {
   gcnb::EllDev *ell = nullptr;    // pattern-only remainder (spmm_ell.cu): every remainder entry factors
   float *d_B2 = nullptr;          // [n_cols + 1][16]: diag(col_scale) * B of the current launch, last row zero
   int rem_ctas = 0;               // CTAs per SM of the remainder kernel (0 = its default)
+  int merge_by_reduction = 1;     // GCNB_BT_MERGE=0 (tuning probe): partial buffers + bt_add_kernel even with the ELL remainder
   cudaStream_t aux = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
@@ -882,6 +903,7 @@ int gcnb_bittile_plan_create(const uint32_t *h_indptr, const uint32_t *h_indices
   // tuning probe: cap the remainder kernel's CTAs per SM so that, whichever kernel the block scheduler sees first, the MMA
   // kernel's CTA (448 threads x 68 registers) still fits on every SM (first measurements: launched at the same instant the
   // two kernels took 772 us instead of 502)
+  if (const char *e = getenv("GCNB_BT_MERGE")) p->merge_by_reduction = atoi(e) != 0;
   if (const char *e = getenv("GCNB_BT_REM_CTAS")) {
     p->rem_ctas = std::max(0, atoi(e));
     if (p->rem) p->rem->max_cta_per_sm = p->rem_ctas;
@@ -911,6 +933,17 @@ int gcnb_bittile_plan_info(const gcnb_bittile_plan *p, int64_t out[8]) {
   return 0;
 }
 
+// kernels launched per 16-column product on aligned operands: pack, MMA kernel, remainder (+ its combine kernel when rows are
+// cut), and the final add unless the two halves are merged by reduction
+int gcnb_bittile_plan_launches(const gcnb_bittile_plan *p) {
+  if (!p) return 0;
+  const bool merge = p->n_tiles > 0 && p->ell && p->merge_by_reduction;
+  int n = (p->n_tiles > 0 ? 2 : 0) + 1 + (merge ? 0 : 1);
+  if (p->ell && p->ell->n_split > 0) n++;
+  if (p->rem && p->rem->n_split_rows > 0) n++;
+  return n;
+}
+
 // debugging aid: switch steps of gcnb_bittile_spmm16_f32 off (bit 0 pack, 1 MMA kernel, 2 remainder, 3 final add) to time them apart
 int gcnb_bittile_debug_parts(gcnb_bittile_plan *p, int parts) {
   if (!p) return GCNB_E_BADARG;
@@ -925,7 +958,7 @@ int gcnb_bittile_debug_pack(gcnb_bittile_plan *p, const float *d_B, void *h_out,
   const int64_t n_groups = p->n_chunks * (kBtChunk / 8);
   if (n_groups == 0) return 0;
   bt_pack_kernel<<<(unsigned)((n_groups * 16 + 255) / 256), 256, 0, stream>>>(d_B, p->d_col_scale, p->d_packed, nullptr,
-                                                                              p->n_cols, n_groups);
+                                                                              p->n_cols, n_groups, nullptr, 0, 0);
   GCNB_LAUNCH_CHECK();
   GCNB_CHECK(cudaMemcpyAsync(h_out, p->d_packed, (size_t)std::min<int64_t>(bytes, p->n_chunks * (int64_t)kBtChunkBytes),
                              cudaMemcpyDeviceToHost, stream));
@@ -938,18 +971,26 @@ static int bt_slab16(gcnb_bittile_plan *p, const float *d_B, int64_t ldb, float 
   const int parts = p->parts;  // 15 unless a probe switched steps off (gcnb_bittile_debug_parts)
   const bool tiles = p->n_tiles > 0;
   const bool contiguous = ldb == 16 && ldc == 16 && (((uintptr_t)d_B | (uintptr_t)d_C) % 16 == 0);
+  const int64_t n_groups = p->n_chunks * (kBtChunk / 8);
+  // Merge by reduction (the default whenever the remainder is the pattern-only ELL kernel): the pack kernel zeroes C, then
+  // the MMA kernel's epilogue and the remainder kernel each ADD their half of a row (REDG.ADD.F32x4).  0 + a + b == 0 + b + a
+  // in floating point, so the result does not depend on which finishes first; no partial buffers, no final add kernel.
+  // Otherwise (valued remainder, unaligned slabs, C overlapping B, probes): partial buffers P and R + bt_add_kernel.
+  const bool overlap = d_C < d_B + (p->n_cols - 1) * ldb + 16 && d_B < d_C + (p->n_rows - 1) * ldc + 16;
+  const bool merge = tiles && p->ell && parts == 15 && p->merge_by_reduction && (uintptr_t)d_C % 16 == 0 && ldc % 4 == 0 &&
+                     p->n_rows <= n_groups * 8 && !overlap;
   if (tiles && (parts & 1)) {
-    const int64_t n_groups = p->n_chunks * (kBtChunk / 8);
     const int64_t threads = n_groups * 16;
+    float *cz = merge ? d_C : nullptr;
     if (ldb == 16)
       bt_pack_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(d_B, p->d_col_scale, p->d_packed, p->d_B2,
-                                                                           p->n_cols, n_groups);
+                                                                           p->n_cols, n_groups, cz, ldc, p->n_rows);
     else
       bt_pack_ld_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(d_B, ldb, p->d_col_scale, p->d_packed,
-                                                                              p->d_B2, p->n_cols, n_groups);
+                                                                              p->d_B2, p->n_cols, n_groups, cz, ldc, p->n_rows);
     GCNB_LAUNCH_CHECK();
   }
-  // The MMA kernel goes first (one CTA per SM, half the register file), then the remainder CSR on the second stream
+  // The MMA kernel goes first (one CTA per SM, half the register file), then the remainder on the second stream
   // fills what is left of every SM: launched the other way round the remainder's persistent CTAs own all registers
   // and the two kernels run one after the other.
   GCNB_CHECK(cudaEventRecord(p->ev_fork, stream));
@@ -957,7 +998,7 @@ static int bt_slab16(gcnb_bittile_plan *p, const float *d_B, int64_t ldb, float 
     BtArgs a;
     a.tile_chunk = p->d_tile_chunk; a.bits = p->d_bits; a.cta_tile_ptr = p->d_cta_tile_ptr;
     a.cta_item_ptr = p->d_cta_item_ptr; a.items = p->d_items; a.packed = p->d_packed; a.row_scale = p->d_row_scale;
-    a.P = p->d_P; a.n_rows = p->n_rows;
+    a.P = p->d_P; a.C = merge ? d_C : nullptr; a.ldc = ldc; a.n_rows = p->n_rows;
     if (p->rb == 2) bt_mma_wide_kernel<2, 1><<<p->n_cta, kBtThreads, BtWide<2, 1>::kSmemBytes, stream>>>(a);
     else if (p->chunk == 128) bt_mma_wide_kernel<1, 2><<<p->n_cta, kBtThreads, BtWide<1, 2>::kSmemBytes, stream>>>(a);
     else bt_mma_wide_kernel<1, 1><<<p->n_cta, kBtThreads, BtWide<1, 1>::kSmemBytes, stream>>>(a);
@@ -965,13 +1006,14 @@ static int bt_slab16(gcnb_bittile_plan *p, const float *d_B, int64_t ldb, float 
   }
   GCNB_CHECK(cudaStreamWaitEvent(p->aux, p->ev_fork, 0));
   if (parts & 4) {
-    const int rc = p->ell ? gcnb::ell_launch(p->ell, p->d_B2, p->d_row_scale, p->d_R, p->rem_ctas, p->aux)
+    const int rc = p->ell ? gcnb::ell_launch(p->ell, p->d_B2, p->d_row_scale, merge ? d_C : p->d_R, merge ? ldc : 16, merge ? 1 : 0,
+                                             p->rem_ctas, p->aux)
                           : gcnb::spmm_generic_launch(p->rem, p->d_r_values, nullptr, d_B, (int)ldb, p->d_R, 16, 16, p->aux);
     if (rc) return rc;
   }
   GCNB_CHECK(cudaEventRecord(p->ev_join, p->aux));
   GCNB_CHECK(cudaStreamWaitEvent(stream, p->ev_join, 0));
-  if (parts & 8) {
+  if ((parts & 8) && !merge) {
     if (contiguous) {
       const int64_t n4 = p->n_rows * 4;
       const int blocks = (int)std::min<int64_t>((n4 + 255) / 256, (int64_t)device_info().sm_count * 8);

@@ -147,6 +147,16 @@ __device__ __forceinline__ void ell_add(float4 &a, const float4 &x) {
   a.x += x.x; a.y += x.y; a.z += x.z; a.w += x.w;
 }
 
+// out[0..4) = v, or out += v with one vector reduction (REDG.ADD.F32x4): the bit-tile plan lets the MMA kernel's epilogue and
+// this kernel add their halves of a row into a zeroed C in whichever order they finish -- 0 + a + b == 0 + b + a in
+// floating point, so the result does not depend on the order
+__device__ __forceinline__ void ell_out(float *dst, const float4 v, const bool accumulate) {
+  if (accumulate)
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+  else
+    *reinterpret_cast<float4 *>(dst) = v;
+}
+
 struct EllHeader {
   uint32_t off, steps, row, slot;
 };
@@ -165,7 +175,8 @@ __device__ __forceinline__ EllHeader ell_header(const uint32_t *__restrict__ off
 __global__ void __launch_bounds__(256, 4)
 ell_gather16_kernel(const uint4 *__restrict__ idx4, const uint32_t *__restrict__ off, const uint32_t *__restrict__ steps,
                     const uint32_t *__restrict__ rows, const float *__restrict__ B2, const float *__restrict__ row_scale,
-                    float *__restrict__ R, float *__restrict__ slots, uint32_t *__restrict__ counter, uint32_t n_bundles) {
+                    float *__restrict__ R, int64_t ldr, int accumulate, float *__restrict__ slots,
+                    uint32_t *__restrict__ counter, uint32_t n_bundles) {
   const int lane = threadIdx.x & 31, g = lane >> 2, l = lane & 3;
   const float *B2l = B2 + l * 4;
   uint32_t t = 0, tn = 0;
@@ -221,14 +232,14 @@ ell_gather16_kernel(const uint4 *__restrict__ idx4, const uint32_t *__restrict__
       if (g == 0) {
         if (h.slot == kEllNone) {
           const float sc = __ldg(row_scale + h.row);
-          *reinterpret_cast<float4 *>(R + (size_t)h.row * 16 + l * 4) = make_float4(acc.x * sc, acc.y * sc, acc.z * sc, acc.w * sc);
+          ell_out(R + (size_t)h.row * ldr + l * 4, make_float4(acc.x * sc, acc.y * sc, acc.z * sc, acc.w * sc), accumulate != 0);
         } else {
           *reinterpret_cast<float4 *>(slots + (size_t)h.slot * 16 + l * 4) = acc;
         }
       }
     } else if (h.row != kEllNone) {
       const float sc = __ldg(row_scale + h.row);
-      *reinterpret_cast<float4 *>(R + (size_t)h.row * 16 + l * 4) = make_float4(acc.x * sc, acc.y * sc, acc.z * sc, acc.w * sc);
+      ell_out(R + (size_t)h.row * ldr + l * 4, make_float4(acc.x * sc, acc.y * sc, acc.z * sc, acc.w * sc), accumulate != 0);
     }
     t = tn;
     h = hn;
@@ -248,7 +259,7 @@ ell_gather16_kernel(const uint4 *__restrict__ idx4, const uint32_t *__restrict__
 // rows cut into parts: R[row] = row_scale[row] * (slot[s0] + slot[s0 + 1] + ...), ascending; 4 lanes per row
 __global__ void __launch_bounds__(256) ell_combine_kernel(const uint32_t *__restrict__ split_row, const uint32_t *__restrict__ split_ptr,
                                                           const float *__restrict__ slots, const float *__restrict__ row_scale,
-                                                          float *__restrict__ R, int64_t n_split) {
+                                                          float *__restrict__ R, int64_t ldr, int accumulate, int64_t n_split) {
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t k = tid >> 2;
   const int l = (int)(tid & 3);
@@ -257,7 +268,7 @@ __global__ void __launch_bounds__(256) ell_combine_kernel(const uint32_t *__rest
   for (uint32_t s = split_ptr[k]; s < split_ptr[k + 1]; s++) ell_add(acc, *reinterpret_cast<const float4 *>(slots + (size_t)s * 16 + l * 4));
   const uint32_t row = split_row[k];
   const float sc = row_scale[row];
-  *reinterpret_cast<float4 *>(R + (size_t)row * 16 + l * 4) = make_float4(acc.x * sc, acc.y * sc, acc.z * sc, acc.w * sc);
+  ell_out(R + (size_t)row * ldr + l * 4, make_float4(acc.x * sc, acc.y * sc, acc.z * sc, acc.w * sc), accumulate != 0);
 }
 
 template <class T>
@@ -301,18 +312,20 @@ int ell_upload_plan(const EllHost &H, cudaStream_t stream, EllDev **out) {
   return 0;
 }
 
-int ell_launch(EllDev *e, const float *d_B2, const float *d_row_scale, float *d_R, int ctas_per_sm, cudaStream_t stream) {
+int ell_launch(EllDev *e, const float *d_B2, const float *d_row_scale, float *d_R, int64_t ldr, int accumulate, int ctas_per_sm,
+               cudaStream_t stream) {
   if (e->n_bundles == 0) return 0;
   const DeviceInfo &di = device_info();
   const int per_sm = ctas_per_sm > 0 ? ctas_per_sm : 2;
   const int64_t want = (e->n_bundles + 7) / 8;  // 8 warps per CTA
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)std::max(1, di.sm_count) * per_sm));
   ell_gather16_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const uint4 *>(e->d_idx), e->d_off, e->d_steps, e->d_rows,
-                                                d_B2, d_row_scale, d_R, e->d_slots, e->d_counter, (uint32_t)e->n_bundles);
+                                                d_B2, d_row_scale, d_R, ldr, accumulate, e->d_slots, e->d_counter,
+                                                (uint32_t)e->n_bundles);
   GCNB_LAUNCH_CHECK();
   if (e->n_split > 0) {
     ell_combine_kernel<<<(unsigned)((e->n_split * 4 + 255) / 256), 256, 0, stream>>>(e->d_split_row, e->d_split_ptr, e->d_slots,
-                                                                                     d_row_scale, d_R, e->n_split);
+                                                                                     d_row_scale, d_R, ldr, accumulate, e->n_split);
     GCNB_LAUNCH_CHECK();
   }
   return 0;
@@ -406,7 +419,7 @@ int gcnb_ell_plan_destroy(gcnb_ell_plan *p) {
 // R[n_rows x 16] = diag(row_scale) * pattern * B2; d_B2 holds n_cols + 1 rows of 16 floats, the LAST ONE ALL ZERO
 int gcnb_ell_gather16_f32(gcnb_ell_plan *p, const float *d_B2, const float *d_row_scale, float *d_R, gcnb_stream_t stream) {
   if (!p || !p->dev || !d_B2 || !d_row_scale || !d_R) return GCNB_E_BADARG;
-  return ell_launch(p->dev, d_B2, d_row_scale, d_R, 0, as_stream(stream));
+  return ell_launch(p->dev, d_B2, d_row_scale, d_R, 16, 0, 0, as_stream(stream));
 }
 
 }  // extern "C"

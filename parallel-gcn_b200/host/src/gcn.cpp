@@ -285,7 +285,7 @@ struct GCNEngineState {
   size_t graphsum_launches(natural dim) const {
     // staged: per 16-column slab the staged kernel, the remainder kernel and the merge kernel (+ the slab packing kernel
     // when the operand is wider than a slab); a remainder combine kernel, if any, is not counted
-    if (graph_bittile && dim == 16) return 4;  // pack, MMA kernel, remainder, add
+    if (graph_bittile && dim == 16) return (size_t)gcnb_bittile_plan_launches(graph_bittile);  // pack, MMA kernel, remainder
     const int slabs = graph_staged ? gcnb_spmm_plan_stage_slabs(graph_plan, (int)dim) : 0;
     if (slabs > 0) return (size_t)slabs * (dim == 16 ? 3 : 4);
     return (size_t)graph_spmm_kernels;

@@ -175,8 +175,7 @@ def test_engine_training_with_bit_tiles_matches_default_path(gcnb, dev):
         finally:
             os.environ.pop("GCNB_BITTILE", None)
 
-    (h0, w0, l0), (h1, w1, l1) = run("0"), run(None)
-    assert l1 != l0, "bit tiles (the default) did not change the GraphSum path (pack + MMA + remainder + add = 4 launches)"
+    (h0, w0, l0), (h1, w1, l1) = run("0"), run(None)  # the path itself is asserted inside run()
     for ep, ((t0, v0), (t1, v1)) in enumerate(zip(h0, h1)):
         assert abs(t0[0] - t1[0]) <= 2e-5 * (1 + ep) * abs(t0[0]) and abs(v0[0] - v1[0]) <= 2e-5 * (1 + ep) * abs(v0[0])
     for a, b in zip(w0, w1):
