@@ -359,8 +359,8 @@ def run_ours(args, rank, world, local_rank):
     staged = paths["graph_staged"]
     traffic, traffic_src = None, None
     if paths["graph_bittile"]:
-        kname = ("GraphSum d=%d = bt_pack_kernel + bt_mma_wide_kernel<1,2> (tcgen05.mma on 128x128 bit-map tiles, TMEM "
-                 "accumulators) || ell_gather16_kernel (pattern-only remainder, 2nd stream) + bt_add_kernel" % d)
+        kname = ("GraphSum d=%d = bt_pack_kernel + bt_mma_wide_kernel (tcgen05.mma on bit-map tiles, TMEM accumulators) || "
+                 "ell_gather16_kernel (pattern-only remainder, 2nd stream), the two halves merged by vector reductions into C" % d)
         prof = os.path.join(ROOT, "profiles", "graphsum_d16_bittile_summary.json")
     elif staged:
         kname = ("GraphSum d=%d = spmm_staged16_kernel (shared-memory column windows) || spmm_seg_kernel (remainder CSR, 2nd "
@@ -400,6 +400,10 @@ def run_ours(args, rank, world, local_rank):
         line["ref_gpu_same_box_ms"] = rg.get("ms_per_epoch")
         line["ref_gpu_same_box"] = dict(rg, what="the reference's own CUDA code (src/*.cu, -arch=sm_100) on this GPU and dataset, "
                                                  "GCN::run() avg_epoch_time = train epoch + validation forward; separate process")
+    if not args.no_scaleout:
+        del ds
+        dist_mod = importlib.import_module("parallel_gcn_b200.dist")
+        line["scaleout"] = dist_mod.scaleout_record(0, 1, local_rank, None, steps=max(3, min(args.steps, 5)), warmup=2)
     if not args.no_cpu_baseline:
         ms, kind, sample, cores, timed, _ = cpu_reference_step_ms(1, 0, 1)
         line["cpu_baseline"] = {"value": ms, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample + " (1 step)",
@@ -415,6 +419,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scale", type=int, default=1, help="debug: 1/scale-size workload (numbers are then not the metric)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-scaleout", action="store_true", help="skip the secondary 1.01e9-entry scale-out record (BASELINE configs[4])")
     ap.add_argument("--no-extras", action="store_true", help="skip the shuffled-id GraphSum and the same-box reference-GPU legs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -36,6 +36,10 @@ typedef void *gcnb_stream_t; /* cudaStream_t */
 GCNB_API const char *gcnb_error_string(int code);
 
 GCNB_API int gcnb_version(void);
+/* host threads the plan builders (window staging, bit tiles, ELL) may use; 0 = default = min(16, hardware threads) or
+ * GCNB_HOST_THREADS.  The row-partitioned engine sets hardware threads / ranks: the ranks of a job share one host. */
+GCNB_API int gcnb_set_host_threads(int n);
+GCNB_API int gcnb_host_threads(void);
 /* device sanity: fails unless the current device is compute capability 10.x; fills SM count. */
 GCNB_API int gcnb_device_check(int *sm_count);
 
@@ -142,6 +146,12 @@ GCNB_API int gcnb_bittile_supported(void);
  * (+ 100000 when the remainder runs on the pattern-only ELL kernel below), CTAs, bit-map bytes, packed-B bytes} */
 GCNB_API int gcnb_bittile_plan_info(const gcnb_bittile_plan *plan, int64_t out[8]);
 GCNB_API int gcnb_bittile_spmm16_f32(gcnb_bittile_plan *plan, const float *d_B, float *d_C, gcnb_stream_t stream);
+/* A plan built from a RENUMBERED square matrix (rows and columns permuted alike -- gcnb_reorder_communities +
+ * gcnb_permute_csr of include/gcnb_engine.h): plan index k is row h_old_of_new[k] of the caller's B and C.  The pack
+ * kernel gathers B through it and both halves of the product add their rows to C through it: the caller's operands keep
+ * their numbering.  Needs a plan whose remainder is the ELL kernel (every entry factors).  h_values of
+ * gcnb_bittile_plan_create may be NULL when both scale arrays are given: the matrix is then the PATTERN scaled by them. */
+GCNB_API int gcnb_bittile_plan_set_permutation(gcnb_bittile_plan *plan, const uint32_t *h_old_of_new, gcnb_stream_t stream);
 /* kernels launched per 16-column product (pack, MMA kernel, remainder [+ combine], [+ final add]) */
 GCNB_API int gcnb_bittile_plan_launches(const gcnb_bittile_plan *plan);
 /* Routes later gcnb_spmm_f32 / gcnb_spmm_ld_f32 calls on `plan` that use exactly this d_values pointer, no permutation,

@@ -30,6 +30,10 @@ struct DeviceInfo {
 };
 const DeviceInfo &device_info();
 
+// host threads a plan builder may use (window staging, bit tiles, ELL): min(16, hardware threads) unless
+// gcnb_set_host_threads / GCNB_HOST_THREADS say otherwise -- N ranks on one host share its cores
+int host_threads();
+
 // Kernels whose arguments change from epoch to epoch (the Philox descriptor of the dropout kernels, Adam's step size) are
 // registered with the index of that argument, so that a captured epoch (CUDA graph) can be replayed with the node's
 // arguments patched in place (gcnb_graph_patch_node, spmm.cu) instead of being captured again.

@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <mutex>
 #include <unordered_map>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -34,6 +35,14 @@ const DeviceInfo &device_info() {
     return d;
   }();
   return info;
+}
+
+static int g_host_threads = 0;
+int host_threads() {
+  if (g_host_threads > 0) return g_host_threads;
+  if (const char *e = getenv("GCNB_HOST_THREADS"))
+    if (atoi(e) > 0) return atoi(e);
+  return (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
 }
 
 struct Patchable {
@@ -712,6 +721,11 @@ const char *gcnb_error_string(int code) {
   return cudaGetErrorString((cudaError_t)code);
 }
 int gcnb_version(void) { return 100; }
+int gcnb_set_host_threads(int n) {
+  gcnb::g_host_threads = n > 0 ? n : 0;
+  return 0;
+}
+int gcnb_host_threads(void) { return gcnb::host_threads(); }
 int gcnb_device_check(int *sm_count) {
   int n = 0;
   GCNB_CHECK(cudaGetDeviceCount(&n));

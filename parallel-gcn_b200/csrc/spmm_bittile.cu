@@ -120,10 +120,11 @@ int bittile_build_host(const uint32_t *indptr, const uint32_t *indices, const fl
   if (chunk_cols != 64 && chunk_cols != 128) return GCNB_E_BADARG;
   if (row_blocks != 1 && !(row_blocks == 2 && chunk_cols == 64)) return GCNB_E_BADARG;
   const int64_t BH = (int64_t)kBtRows * row_blocks;  // rows per item
-  if (!indptr || (!indices && indptr[n_rows] > 0) || (!values && indptr[n_rows] > 0) || n_rows < 0 || n_cols < 0 ||
-      n_rows > 0xfffffff0ll || n_cols > 0xfffffff0ll)
+  if (!indptr || (!indices && indptr[n_rows] > 0) || n_rows < 0 || n_cols < 0 || n_rows > 0xfffffff0ll || n_cols > 0xfffffff0ll)
     return GCNB_E_BADARG;
   if ((row_scale == nullptr) != (col_scale == nullptr)) return GCNB_E_BADARG;
+  // values == NULL (explicit scales only): a PATTERN -- every entry (i, j) has the value row_scale[i] * col_scale[j]
+  if (!values && indptr[n_rows] > 0 && !row_scale) return GCNB_E_BADARG;
   H.n_rows = n_rows;
   H.n_cols = n_cols;
   H.nnz = indptr[n_rows];
@@ -135,7 +136,7 @@ int bittile_build_host(const uint32_t *indptr, const uint32_t *indices, const fl
   const int64_t n_chunks = (n_cols + chunk_cols - 1) / chunk_cols;
   const int shift = chunk_cols == 128 ? 7 : 6;
   const size_t wpr = (size_t)chunk_cols / 64;  // bit-map words per row of a tile
-  int T = n_threads > 0 ? n_threads : (int)std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency()));
+  int T = n_threads > 0 ? n_threads : host_threads();
   T = (int)std::max<int64_t>(1, std::min<int64_t>(T, H.n_blk));
 
   const bool verbose = getenv("GCNB_SETUP_VERBOSE") != nullptr;
@@ -211,10 +212,10 @@ int bittile_build_host(const uint32_t *indptr, const uint32_t *indices, const fl
         const float si = H.row_scale[(size_t)i];
         for (uint32_t e = indptr[i]; e < indptr[i + 1]; e++) {
           const uint32_t j = indices[e];
-          const float v = values[e];
+          const float p = si * H.col_scale[j];
+          const float v = values ? values[e] : p;
           const int32_t li = sel[j >> shift];
           bool in_tile = false;
-          const float p = si * H.col_scale[j];
           const bool factors = fabsf(v - p) <= 1e-6f * fabsf(v);  // false for NaN scales
           if (!factors) o.unfactored++;
           if (li >= 0) {
@@ -366,6 +367,7 @@ struct BtArgs {
   float *C;                 // or: the product itself, zeroed by the pack kernel; partial rows are ADDED (row stride ldc)
   int64_t ldc;
   int64_t n_rows;
+  const uint32_t *perm;     // optional: plan row / column k is row perm[k] of the caller's B and C (renumbered plans)
 };
 
 // B' = col_scale[j] * B[j][:] split into bf16 hi | mid | lo (truncation, exact sum) in the operand layout of the MMA:
@@ -373,7 +375,8 @@ struct BtArgs {
 // One thread = 8 consecutive rows of B x one column: three 16-byte stores.
 __global__ void __launch_bounds__(256) bt_pack_kernel(const float *__restrict__ B, const float *__restrict__ col_scale,
                                                       uint8_t *__restrict__ packed, float *__restrict__ B2, int64_t n_cols,
-                                                      int64_t n_groups, float *__restrict__ Cz, int64_t ldc, int64_t n_rows) {
+                                                      int64_t n_groups, float *__restrict__ Cz, int64_t ldc, int64_t n_rows,
+                                                      const uint32_t *__restrict__ perm) {
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t g = tid >> 4;
   const int col = (int)(tid & 15);
@@ -388,7 +391,8 @@ __global__ void __launch_bounds__(256) bt_pack_kernel(const float *__restrict__ 
     const int64_t j = j0 + i;
     float x = 0.f;
     if (j < n_cols) {
-      x = __ldg(col_scale + j) * __ldg(B + j * 16 + col);
+      const int64_t jb = perm ? (int64_t)__ldg(perm + j) : j;  // renumbered plan: its column j is the caller's row perm[j]
+      x = __ldg(col_scale + j) * __ldg(B + jb * 16 + col);
       if (B2) B2[j * 16 + col] = x;  // fp32 copy of B' for the pattern-only remainder kernel (spmm_ell.cu)
     }
     const uint32_t xb = __float_as_uint(x);
@@ -425,7 +429,8 @@ __global__ void __launch_bounds__(256) bt_pack_kernel(const float *__restrict__ 
 __global__ void __launch_bounds__(256) bt_pack_ld_kernel(const float *__restrict__ B, int64_t ldb,
                                                          const float *__restrict__ col_scale, uint8_t *__restrict__ packed,
                                                          float *__restrict__ B2, int64_t n_cols, int64_t n_groups,
-                                                         float *__restrict__ Cz, int64_t ldc, int64_t n_rows) {
+                                                         float *__restrict__ Cz, int64_t ldc, int64_t n_rows,
+                                                         const uint32_t *__restrict__ perm) {
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t g = tid >> 4;
   const int col = (int)(tid & 15);
@@ -440,7 +445,8 @@ __global__ void __launch_bounds__(256) bt_pack_ld_kernel(const float *__restrict
     const int64_t j = j0 + i;
     float x = 0.f;
     if (j < n_cols) {
-      x = __ldg(col_scale + j) * __ldg(B + j * ldb + col);
+      const int64_t jb = perm ? (int64_t)__ldg(perm + j) : j;
+      x = __ldg(col_scale + j) * __ldg(B + jb * ldb + col);
       if (B2) B2[j * 16 + col] = x;
     }
     const uint32_t xb = __float_as_uint(x);
@@ -521,7 +527,7 @@ struct BtWide {
 // operands in the stage) against the SAME B' stage, which halves the B' traffic through L2 and lets the plan select
 // tiles by the density of 256 x 64 cells.  One accumulator per half and set (chains of ~300 MMAs; measured: no drift).
 template <int RB, int W>
-__global__ void __maxnreg__(72) bt_mma_wide_kernel(BtArgs a) {  // no spills at 72; leaves half the register file to the remainder kernel
+__global__ void __maxnreg__(64) bt_mma_wide_kernel(BtArgs a) {  // 448 x 64 registers: two 256-thread x 64-register remainder CTAs stay co-resident (at 72 they do not: +60 us)
   using K = BtWide<RB, W>;
   extern __shared__ __align__(128) uint8_t bt_smem[];
   uint8_t *smem_b = bt_smem;
@@ -637,7 +643,7 @@ __global__ void __maxnreg__(72) bt_mma_wide_kernel(BtArgs a) {  // no spills at 
         }
         if (a.C) {  // merge by reduction: whichever of this kernel and the remainder kernel finishes a row first, 0 + p + r
           if (row < a.n_rows) {
-            float *dst = a.C + row * a.ldc;
+            float *dst = a.C + (a.perm ? (int64_t)__ldg(a.perm + row) : row) * a.ldc;
 #pragma unroll
             for (int i = 0; i < 4; i++)
               asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * i), "f"(sc * tot[4 * i]),
@@ -751,6 +757,7 @@ struct gcnb_bittile_plan {
   gcnb::EllDev *ell = nullptr;    // pattern-only remainder (spmm_ell.cu): every remainder entry factors
   float *d_B2 = nullptr;          // [n_cols + 1][16]: diag(col_scale) * B of the current launch, last row zero
   int rem_ctas = 0;               // CTAs per SM of the remainder kernel (0 = its default)
+  uint32_t *d_perm = nullptr;     // gcnb_bittile_plan_set_permutation: plan index k = caller's row perm[k] (needs the merge path)
   int merge_by_reduction = 1;     // GCNB_BT_MERGE=0 (tuning probe): partial buffers + bt_add_kernel even with the ELL remainder
   cudaStream_t aux = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -832,6 +839,7 @@ int gcnb_bittile_plan_destroy(gcnb_bittile_plan *p) {
   if (p->rem) gcnb_spmm_plan_destroy(p->rem);
   gcnb::ell_destroy(p->ell);
   cudaFree(p->d_B2);
+  cudaFree(p->d_perm);
   cudaFree(p->d_tile_chunk); cudaFree(p->d_cta_tile_ptr); cudaFree(p->d_cta_item_ptr); cudaFree(p->d_items);
   cudaFree(p->d_bits); cudaFree(p->d_r_indptr); cudaFree(p->d_r_indices); cudaFree(p->d_r_values);
   cudaFree(p->d_row_scale); cudaFree(p->d_col_scale); cudaFree(p->d_packed); cudaFree(p->d_P); cudaFree(p->d_R);
@@ -933,6 +941,24 @@ int gcnb_bittile_plan_info(const gcnb_bittile_plan *p, int64_t out[8]) {
   return 0;
 }
 
+// A plan built from a RENUMBERED matrix (rows and columns permuted alike, e.g. community by community): plan index k is row
+// h_old_of_new[k] of the caller's operands.  The pack kernel gathers B through it and both halves of the product add their
+// rows to C through it, so the caller never sees the renumbering.  Square plans whose remainder is the ELL kernel only.
+int gcnb_bittile_plan_set_permutation(gcnb_bittile_plan *p, const uint32_t *h_old_of_new, gcnb_stream_t stream_) {
+  if (!p || !h_old_of_new) return GCNB_E_BADARG;
+  if (p->n_rows != p->n_cols || !p->ell || p->n_tiles == 0 || !p->merge_by_reduction) return GCNB_E_UNSUPPORTED;
+  std::vector<uint8_t> seen((size_t)p->n_rows, 0);
+  for (int64_t k = 0; k < p->n_rows; k++) {
+    if (h_old_of_new[k] >= (uint64_t)p->n_rows || seen[h_old_of_new[k]]) return GCNB_E_BADARG;
+    seen[h_old_of_new[k]] = 1;
+  }
+  cudaStream_t stream = as_stream(stream_);
+  if (!p->d_perm) GCNB_CHECK(cudaMalloc((void **)&p->d_perm, std::max<size_t>((size_t)p->n_rows, 1) * 4));
+  GCNB_CHECK(cudaMemcpyAsync(p->d_perm, h_old_of_new, (size_t)p->n_rows * 4, cudaMemcpyHostToDevice, stream));
+  GCNB_CHECK(cudaStreamSynchronize(stream));
+  return 0;
+}
+
 // kernels launched per 16-column product on aligned operands: pack, MMA kernel, remainder (+ its combine kernel when rows are
 // cut), and the final add unless the two halves are merged by reduction
 int gcnb_bittile_plan_launches(const gcnb_bittile_plan *p) {
@@ -958,7 +984,7 @@ int gcnb_bittile_debug_pack(gcnb_bittile_plan *p, const float *d_B, void *h_out,
   const int64_t n_groups = p->n_chunks * (kBtChunk / 8);
   if (n_groups == 0) return 0;
   bt_pack_kernel<<<(unsigned)((n_groups * 16 + 255) / 256), 256, 0, stream>>>(d_B, p->d_col_scale, p->d_packed, nullptr,
-                                                                              p->n_cols, n_groups, nullptr, 0, 0);
+                                                                              p->n_cols, n_groups, nullptr, 0, 0, nullptr);
   GCNB_LAUNCH_CHECK();
   GCNB_CHECK(cudaMemcpyAsync(h_out, p->d_packed, (size_t)std::min<int64_t>(bytes, p->n_chunks * (int64_t)kBtChunkBytes),
                              cudaMemcpyDeviceToHost, stream));
@@ -979,15 +1005,17 @@ static int bt_slab16(gcnb_bittile_plan *p, const float *d_B, int64_t ldb, float 
   const bool overlap = d_C < d_B + (p->n_cols - 1) * ldb + 16 && d_B < d_C + (p->n_rows - 1) * ldc + 16;
   const bool merge = tiles && p->ell && parts == 15 && p->merge_by_reduction && (uintptr_t)d_C % 16 == 0 && ldc % 4 == 0 &&
                      p->n_rows <= n_groups * 8 && !overlap;
+  if (p->d_perm && !merge) return GCNB_E_UNSUPPORTED;  // a renumbered plan writes its rows through the reduction path only
   if (tiles && (parts & 1)) {
     const int64_t threads = n_groups * 16;
     float *cz = merge ? d_C : nullptr;
     if (ldb == 16)
       bt_pack_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(d_B, p->d_col_scale, p->d_packed, p->d_B2,
-                                                                           p->n_cols, n_groups, cz, ldc, p->n_rows);
+                                                                           p->n_cols, n_groups, cz, ldc, p->n_rows, p->d_perm);
     else
       bt_pack_ld_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(d_B, ldb, p->d_col_scale, p->d_packed,
-                                                                              p->d_B2, p->n_cols, n_groups, cz, ldc, p->n_rows);
+                                                                              p->d_B2, p->n_cols, n_groups, cz, ldc, p->n_rows,
+                                                                              p->d_perm);
     GCNB_LAUNCH_CHECK();
   }
   // The MMA kernel goes first (one CTA per SM, half the register file), then the remainder on the second stream
@@ -998,7 +1026,7 @@ static int bt_slab16(gcnb_bittile_plan *p, const float *d_B, int64_t ldb, float 
     BtArgs a;
     a.tile_chunk = p->d_tile_chunk; a.bits = p->d_bits; a.cta_tile_ptr = p->d_cta_tile_ptr;
     a.cta_item_ptr = p->d_cta_item_ptr; a.items = p->d_items; a.packed = p->d_packed; a.row_scale = p->d_row_scale;
-    a.P = p->d_P; a.C = merge ? d_C : nullptr; a.ldc = ldc; a.n_rows = p->n_rows;
+    a.P = p->d_P; a.C = merge ? d_C : nullptr; a.ldc = ldc; a.n_rows = p->n_rows; a.perm = p->d_perm;
     if (p->rb == 2) bt_mma_wide_kernel<2, 1><<<p->n_cta, kBtThreads, BtWide<2, 1>::kSmemBytes, stream>>>(a);
     else if (p->chunk == 128) bt_mma_wide_kernel<1, 2><<<p->n_cta, kBtThreads, BtWide<1, 2>::kSmemBytes, stream>>>(a);
     else bt_mma_wide_kernel<1, 1><<<p->n_cta, kBtThreads, BtWide<1, 1>::kSmemBytes, stream>>>(a);
@@ -1007,7 +1035,7 @@ static int bt_slab16(gcnb_bittile_plan *p, const float *d_B, int64_t ldb, float 
   GCNB_CHECK(cudaStreamWaitEvent(p->aux, p->ev_fork, 0));
   if (parts & 4) {
     const int rc = p->ell ? gcnb::ell_launch(p->ell, p->d_B2, p->d_row_scale, merge ? d_C : p->d_R, merge ? ldc : 16, merge ? 1 : 0,
-                                             p->rem_ctas, p->aux)
+                                             merge ? p->d_perm : nullptr, p->rem_ctas, p->aux)
                           : gcnb::spmm_generic_launch(p->rem, p->d_r_values, nullptr, d_B, (int)ldb, p->d_R, 16, 16, p->aux);
     if (rc) return rc;
   }

@@ -101,7 +101,7 @@ int ell_build_host(const uint32_t *indptr, const uint32_t *indices, int64_t n_ro
   H.n_bundles = (int64_t)n_b;
   H.idx.alloc((size_t)acc * 32);
   // ---- fill: idx[((off + k / 4) * 8 + g) * 4 + k % 4] = column of entry k of group g, n_cols (the zero row) as padding
-  int T = n_threads > 0 ? n_threads : (int)std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency()));
+  int T = n_threads > 0 ? n_threads : host_threads();
   T = (int)std::max<size_t>(1, std::min<size_t>((size_t)T, n_b / 64 + 1));
   const uint32_t pad = (uint32_t)n_cols;
   uint32_t *out = H.idx.data();
@@ -175,8 +175,8 @@ __device__ __forceinline__ EllHeader ell_header(const uint32_t *__restrict__ off
 __global__ void __launch_bounds__(256, 4)
 ell_gather16_kernel(const uint4 *__restrict__ idx4, const uint32_t *__restrict__ off, const uint32_t *__restrict__ steps,
                     const uint32_t *__restrict__ rows, const float *__restrict__ B2, const float *__restrict__ row_scale,
-                    float *__restrict__ R, int64_t ldr, int accumulate, float *__restrict__ slots,
-                    uint32_t *__restrict__ counter, uint32_t n_bundles) {
+                    float *__restrict__ R, int64_t ldr, int accumulate, const uint32_t *__restrict__ row_map,
+                    float *__restrict__ slots, uint32_t *__restrict__ counter, uint32_t n_bundles) {
   const int lane = threadIdx.x & 31, g = lane >> 2, l = lane & 3;
   const float *B2l = B2 + l * 4;
   uint32_t t = 0, tn = 0;
@@ -232,14 +232,16 @@ ell_gather16_kernel(const uint4 *__restrict__ idx4, const uint32_t *__restrict__
       if (g == 0) {
         if (h.slot == kEllNone) {
           const float sc = __ldg(row_scale + h.row);
-          ell_out(R + (size_t)h.row * ldr + l * 4, make_float4(acc.x * sc, acc.y * sc, acc.z * sc, acc.w * sc), accumulate != 0);
+          const size_t ro = row_map ? __ldg(row_map + h.row) : h.row;  // renumbered plan: its row k is the caller's row_map[k]
+          ell_out(R + ro * ldr + l * 4, make_float4(acc.x * sc, acc.y * sc, acc.z * sc, acc.w * sc), accumulate != 0);
         } else {
           *reinterpret_cast<float4 *>(slots + (size_t)h.slot * 16 + l * 4) = acc;
         }
       }
     } else if (h.row != kEllNone) {
       const float sc = __ldg(row_scale + h.row);
-      ell_out(R + (size_t)h.row * ldr + l * 4, make_float4(acc.x * sc, acc.y * sc, acc.z * sc, acc.w * sc), accumulate != 0);
+      const size_t ro = row_map ? __ldg(row_map + h.row) : h.row;
+      ell_out(R + ro * ldr + l * 4, make_float4(acc.x * sc, acc.y * sc, acc.z * sc, acc.w * sc), accumulate != 0);
     }
     t = tn;
     h = hn;
@@ -259,7 +261,8 @@ ell_gather16_kernel(const uint4 *__restrict__ idx4, const uint32_t *__restrict__
 // rows cut into parts: R[row] = row_scale[row] * (slot[s0] + slot[s0 + 1] + ...), ascending; 4 lanes per row
 __global__ void __launch_bounds__(256) ell_combine_kernel(const uint32_t *__restrict__ split_row, const uint32_t *__restrict__ split_ptr,
                                                           const float *__restrict__ slots, const float *__restrict__ row_scale,
-                                                          float *__restrict__ R, int64_t ldr, int accumulate, int64_t n_split) {
+                                                          float *__restrict__ R, int64_t ldr, int accumulate,
+                                                          const uint32_t *__restrict__ row_map, int64_t n_split) {
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t k = tid >> 2;
   const int l = (int)(tid & 3);
@@ -268,7 +271,8 @@ __global__ void __launch_bounds__(256) ell_combine_kernel(const uint32_t *__rest
   for (uint32_t s = split_ptr[k]; s < split_ptr[k + 1]; s++) ell_add(acc, *reinterpret_cast<const float4 *>(slots + (size_t)s * 16 + l * 4));
   const uint32_t row = split_row[k];
   const float sc = row_scale[row];
-  ell_out(R + (size_t)row * ldr + l * 4, make_float4(acc.x * sc, acc.y * sc, acc.z * sc, acc.w * sc), accumulate != 0);
+  const size_t ro = row_map ? row_map[row] : row;
+  ell_out(R + ro * ldr + l * 4, make_float4(acc.x * sc, acc.y * sc, acc.z * sc, acc.w * sc), accumulate != 0);
 }
 
 template <class T>
@@ -312,20 +316,21 @@ int ell_upload_plan(const EllHost &H, cudaStream_t stream, EllDev **out) {
   return 0;
 }
 
-int ell_launch(EllDev *e, const float *d_B2, const float *d_row_scale, float *d_R, int64_t ldr, int accumulate, int ctas_per_sm,
-               cudaStream_t stream) {
+int ell_launch(EllDev *e, const float *d_B2, const float *d_row_scale, float *d_R, int64_t ldr, int accumulate,
+               const uint32_t *d_row_map, int ctas_per_sm, cudaStream_t stream) {
   if (e->n_bundles == 0) return 0;
   const DeviceInfo &di = device_info();
   const int per_sm = ctas_per_sm > 0 ? ctas_per_sm : 2;
   const int64_t want = (e->n_bundles + 7) / 8;  // 8 warps per CTA
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)std::max(1, di.sm_count) * per_sm));
   ell_gather16_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const uint4 *>(e->d_idx), e->d_off, e->d_steps, e->d_rows,
-                                                d_B2, d_row_scale, d_R, ldr, accumulate, e->d_slots, e->d_counter,
+                                                d_B2, d_row_scale, d_R, ldr, accumulate, d_row_map, e->d_slots, e->d_counter,
                                                 (uint32_t)e->n_bundles);
   GCNB_LAUNCH_CHECK();
   if (e->n_split > 0) {
     ell_combine_kernel<<<(unsigned)((e->n_split * 4 + 255) / 256), 256, 0, stream>>>(e->d_split_row, e->d_split_ptr, e->d_slots,
-                                                                                     d_row_scale, d_R, ldr, accumulate, e->n_split);
+                                                                                     d_row_scale, d_R, ldr, accumulate, d_row_map,
+                                                                                     e->n_split);
     GCNB_LAUNCH_CHECK();
   }
   return 0;
@@ -419,7 +424,7 @@ int gcnb_ell_plan_destroy(gcnb_ell_plan *p) {
 // R[n_rows x 16] = diag(row_scale) * pattern * B2; d_B2 holds n_cols + 1 rows of 16 floats, the LAST ONE ALL ZERO
 int gcnb_ell_gather16_f32(gcnb_ell_plan *p, const float *d_B2, const float *d_row_scale, float *d_R, gcnb_stream_t stream) {
   if (!p || !p->dev || !d_B2 || !d_row_scale || !d_R) return GCNB_E_BADARG;
-  return ell_launch(p->dev, d_B2, d_row_scale, d_R, 16, 0, 0, as_stream(stream));
+  return ell_launch(p->dev, d_B2, d_row_scale, d_R, 16, 0, nullptr, 0, as_stream(stream));
 }
 
 }  // extern "C"

@@ -116,9 +116,10 @@ int ell_build_host(const uint32_t *indptr, const uint32_t *indices, int64_t n_ro
 int ell_upload_plan(const EllHost &H, cudaStream_t stream, EllDev **out);
 void ell_destroy(EllDev *e);
 // R[n_rows x 16] (row stride ldr floats, 16-byte aligned rows) = or += diag(row_scale) * pattern * B2 (B2: n_cols + 1 rows,
-// the last one zero); accumulate: vector reductions into R instead of stores; ctas_per_sm 0 = default
-int ell_launch(EllDev *e, const float *d_B2, const float *d_row_scale, float *d_R, int64_t ldr, int accumulate, int ctas_per_sm,
-               cudaStream_t stream);
+// the last one zero); accumulate: vector reductions into R instead of stores; d_row_map (optional): plan row k is written
+// to row d_row_map[k] of R; ctas_per_sm 0 = default
+int ell_launch(EllDev *e, const float *d_B2, const float *d_row_scale, float *d_R, int64_t ldr, int accumulate,
+               const uint32_t *d_row_map, int ctas_per_sm, cudaStream_t stream);
 
 struct StagedDev;  // device mirror, spmm_stage.cu
 void stage_destroy(StagedDev *s);

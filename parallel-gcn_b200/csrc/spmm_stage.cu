@@ -79,7 +79,7 @@ int stage_build_host(const uint32_t *indptr, const uint32_t *indices, int64_t n_
   const uint32_t min_seg = (uint32_t)std::max(1, P.min_seg);
   const uint32_t seg_cap = (uint32_t)std::min(65535, std::max(4, P.seg_cap));
   const int64_t min_window_nnz = P.min_window_nnz > 0 ? P.min_window_nnz : (int64_t)8 * wc;
-  int T = P.n_threads > 0 ? P.n_threads : (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+  int T = P.n_threads > 0 ? P.n_threads : host_threads();
   if (nnz < (1 << 16)) T = 1;
   const WinDiv win_of((uint32_t)wc);
 

@@ -15,6 +15,8 @@ CPU gloo tests only, a numpy backend the tests build on top of the oracle.  This
 """
 import math
 
+import os
+
 import numpy as np
 
 
@@ -391,6 +393,93 @@ def make_comm(eng, dist, rank, world, dev):
     return eng.Comm(rank, world, bytes(ident.cpu().numpy().tobytes()))
 
 
+def scaleout_record(rank, world, local_rank, dist, n=4000000, block=4000, intra=230.0, inter=58.0, reflect=2048, sigma=1.0,
+                    features=128, classes=47, hidden=16, steps=5, warmup=2, seed=20240229):
+    """Scale-out workload (BASELINE.json configs[4]; north_star: >= 5x 1-GPU throughput on 8 GPUs for a >= 1B-edge synthetic
+    graph): a symmetric community graph with 1.01e9 CSR entries generated ROW-LOCALLY (every rank builds only its row block,
+    gcnb_synth_sym_rows), dense features, 2-layer GCN hidden 16, through the native (row-partitioned) engine.  Returns the
+    record on rank 0 (None elsewhere): ms per train_epoch + eval(2), CUDA events on the engine stream, max over ranks.
+    `dist`: an initialised torch.distributed (world > 1) or None."""
+    import time
+    import torch
+    from . import engine as eng
+    dev = torch.device("cuda", local_rank)
+    B = block_rows(n, world)
+    r0, r1 = min(n, rank * B), min(n, (rank + 1) * B)
+    rows = r1 - r0
+    t0 = time.perf_counter()
+    g_indptr, g_indices = eng.synth_sym_rows(n, r0, rows, block, intra, inter, reflect, sigma, seed)
+    t_graph = time.perf_counter() - t0
+    deg_local = np.diff(g_indptr.astype(np.int64)).astype(np.uint32)
+    if world > 1:
+        pad = torch.zeros(B, dtype=torch.int32, device=dev)
+        pad[:rows] = torch.from_numpy(deg_local.view(np.int32)).to(dev)
+        allpad = torch.empty(world * B, dtype=torch.int32, device=dev)
+        dist.all_gather_into_tensor(allpad, pad)
+        deg_global = allpad[:n].cpu().numpy().view(np.uint32)
+        nnz_t = torch.tensor([len(g_indices)], dtype=torch.int64, device=dev)
+        dist.all_reduce(nnz_t)
+        nnz_global = int(nnz_t.item())
+    else:
+        deg_global, nnz_global = deg_local, len(g_indices)
+    gv = eng.synth_graph_values(g_indptr, g_indices, r0, deg_global)
+    f_indptr, f_indices, f_value = eng.synth_dense_features_uniform(rows, features, seed, r0 * features)
+    label_all, split_all = eng.synth_labels(n, classes, seed=seed)
+    t_gen = time.perf_counter() - t0
+    part = dict(n_global=n, block=B, r0=r0, r1=r1, n_local=rows, g_indptr=g_indptr, g_indices=g_indices, graph_value=gv,
+                f_indptr=f_indptr, f_indices=f_indices, f_value=f_value, f_elem_offset=r0 * features,
+                label=np.ascontiguousarray(label_all[r0:r1]), split=np.ascontiguousarray(split_all[r0:r1]),
+                f_nnz_global=n * features, input_dim=features, output_dim=classes)
+    model = dict(hidden_dims=(hidden,), dropouts=(0.5, 0.5), lr=0.01, weight_decay=5e-4, seed=seed)
+    comm = None
+    t0 = time.perf_counter()
+    if world > 1:
+        comm = make_comm(eng, dist, rank, world, dev)
+        g = eng.GCN(eng.PartDataset(part), comm=comm, **model)
+    else:
+        g = eng.GCN(eng.PartDataset(part), **model)
+    g.finish_setup()
+    torch.cuda.synchronize()
+    t_create = time.perf_counter() - t0
+    last = None
+    for _ in range(warmup):
+        last = (g.train_epoch(), g.eval(2))
+    clocks = None
+    if rank == 0:
+        try:
+            import bench as _bench
+            clocks = _bench.ClockSampler(local_rank).start()
+        except Exception:
+            clocks = None
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    r = g.timed_epochs(steps, with_eval=True, time_graphsum=True)
+    torch.cuda.synchronize()
+    clk = clocks.stop() if clocks is not None else None
+    ms = torch.tensor([r["ms"], r["graphsum_ms"] / max(1, r["graphsum_calls"]), t_create * 1e3, t_gen * 1e3, t_graph * 1e3],
+                      dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    line = None
+    if rank == 0:
+        free_b, total_b = torch.cuda.mem_get_info()
+        line = {"workload": "scaleout_sym_community n=%d nnz=%d (community %d, intra %.0f, inter %.0f, sigma %.1f) f=%d c=%d; "
+                            "2-layer GCN hidden %d; step = train_epoch + eval(2)" %
+                            (n, nnz_global, block, intra, inter, sigma, features, classes, hidden),
+                "n_gpus": world, "ms_per_epoch": float(ms[0]) / steps, "unit": "ms/epoch", "scaling": "strong",
+                "graphsum_mean_ms": float(ms[1]), "graphsum_calls_per_step": r["graphsum_calls"] / steps,
+                "launches_per_step": r["launches"] / steps, "paths": g.path_info(), "setup_ms": float(ms[2]),
+                "gen_ms": float(ms[3]), "graph_gen_ms": float(ms[4]), "deg_max": int(deg_global.max()),
+                "deg_mean": float(nnz_global / n), "train": last[0] if last else None, "val": last[1] if last else None,
+                "gpu_mem_used_gb_rank0": (total_b - free_b) / 2**30, "steps": steps, "warmup": warmup, "clocks": clk,
+                "host_cores": os.cpu_count()}
+    g.close()
+    if comm is not None:
+        comm.close()
+    return line
+
+
 def bench_main(args, rank, world, local_rank, bench):
     """bench.py --gpus N (N > 1): strong scaling of the Reddit-shape epoch.  One rank per GPU; the native engine
     (host/src/gcn.cpp) runs the row block and issues the NCCL collectives itself; torch.distributed only bootstraps
@@ -424,6 +513,7 @@ def bench_main(args, rank, world, local_rank, bench):
         last = (tl, vl)
     torch.cuda.synchronize(); dist.barrier()
     wall = time.perf_counter() - tw0
+    g.finish_setup()
     for _ in range(args.warmup):
         g.train_epoch(); g.eval(2)
     clocks = bench.ClockSampler(local_rank).start()
@@ -438,6 +528,11 @@ def bench_main(args, rank, world, local_rank, bench):
         step_ms = float(ms[0]) / args.steps
         h2d = sum(v.nbytes for v in part.values() if isinstance(v, np.ndarray))
         d = bench.MODEL["hidden"][0]
+        paths = g.path_info()
+        gather_mode = {0: "single rank", 1: "NCCL all-gather", 2: "peer-memory push over NVLink (CUDA IPC stores + "
+                       "release/acquire flags)"}[int(eng.lib.gcnb_comm_gather_mode(comm.h))]
+        gs_path = "bit tiles (tcgen05) + pattern-only ELL remainder" if paths["graph_bittile"] else (
+            "window-staged (own-slab windows overlap the exchange) || generic remainder" if paths["graph_staged"] else "generic")
         gs_us = float(ms[3]) * 1e3
         alg = bench.graphsum_alg_bytes(n, nnz_global, d)
         peak, peak_src = bench.peaks()
@@ -447,9 +542,11 @@ def bench_main(args, rank, world, local_rank, bench):
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": "reddit_shape_synthetic n=%d nnz=%d f=%d c=%d; 2-layer GCN hidden %d; step = train_epoch + "
                                        "eval(2)" % (n, nnz_global, w["f"], w["c"], d),
-                           "parallelism": "row-partitioned x%d (native engine): NCCL all-gather of the [N x 16] GraphSum input "
-                                          "per GraphSum, grouped all-reduce of the weight gradients per epoch and of the "
-                                          "loss/count scalars per pass" % world,
+                           "parallelism": "row-partitioned x%d (native engine): per GraphSum one exchange of the [N x 16] input "
+                                          "slabs (%s), grouped NCCL all-reduce of the weight gradients per epoch and of the "
+                                          "loss/count scalars per pass" % (world, gather_mode),
+                           "gather_mode": gather_mode, "paths": paths,
+                           "switches": {k: os.environ[k] for k in sorted(os.environ) if k.startswith("GCNB_")},
                            "l2_policy": "inputs larger than L2", "dataset_gen_s": round(gen_s, 1), "scale": args.scale,
                            "final_train_loss": last[0][0], "final_val_acc": last[1][1]},
                 "clocks": clk,
@@ -459,14 +556,19 @@ def bench_main(args, rank, world, local_rank, bench):
                         "note": "per rank: upload of its row block + plans, then K steps with per-pass host read of the metrics; "
                                 "max over ranks, wall clock / K"},
                 "gpu_launches": r["launches"],
-                "roofline": {"bound": "hbm", "kernel": "GraphSum d=%d on a row block (all-gather + staged/generic SpMM)" % d,
+                "roofline": {"bound": "hbm", "kernel": "GraphSum d=%d on a row block: slab exchange + %s" % (d, gs_path),
                              "achieved": achieved, "peak": peak * world, "unit": "GB/s", "frac": achieved / (peak * world),
                              "traffic": None, "peak_source": peak_src + " x %d GPUs" % world,
                              "algorithmic_bytes_per_launch": alg, "mean_launch_us": gs_us,
                              "graph_staged": r.get("graph_staged")}}
-        print(json.dumps(line), flush=True)
     g.close()
     comm.close()
+    if not getattr(args, "no_scaleout", False):
+        rec = scaleout_record(rank, world, local_rank, dist, steps=max(3, min(args.steps, 5)), warmup=2)
+        if rank == 0:
+            line["scaleout"] = rec
+    if rank == 0:
+        print(json.dumps(line), flush=True)
     dist.destroy_process_group()
 
 

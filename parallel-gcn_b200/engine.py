@@ -48,6 +48,7 @@ _sig("gcnb_gcn_create_partitioned", I32, [P, P, P, P])
 _sig("gcnb_comm_unique_id", I32, [P])
 _sig("gcnb_comm_create", I32, [I32, I32, P, P])
 _sig("gcnb_comm_destroy", I32, [P])
+_sig("gcnb_comm_gather_mode", I32, [P])
 _sig("gcnb_gcn_destroy", I32, [P])
 _sig("gcnb_gcn_train_epoch", I32, [P, P])
 _sig("gcnb_gcn_eval", I32, [P, I32, P])

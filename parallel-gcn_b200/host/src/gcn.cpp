@@ -363,6 +363,10 @@ void GCN::init(bool quiet, const natural *h_graph_indptr, const natural *h_graph
     st->block = part->block;
     st->f_elem_off = part->feat_elem_offset;
     st->f_nnz_global = part->feat_nnz_global;
+    // the ranks of a job share one host: split its cores between their plan builders (r1: every rank started 16 builder
+    // threads, set-up time grew 4x from 1 to 8 ranks)
+    if (!getenv("GCNB_HOST_THREADS") && world > 1)
+      gcnb_set_host_threads((int)std::max<size_t>(2, std::thread::hardware_concurrency() / world));
   }
   CHECK_CUDA_ERROR(cudaStreamCreateWithFlags(&st->stream, cudaStreamNonBlocking));
   if (const char *e = getenv("GCNB_SIDE_STREAM")) st->use_side = atoi(e);  // tuning probe: 0 = single stream
