@@ -58,6 +58,10 @@ GCNB_API int gcnb_spmm_plan_create(const uint32_t *d_indptr, const uint32_t *d_i
                                    int64_t n_cols, int seg_nnz /*0 = default*/, gcnb_stream_t stream,
                                    gcnb_spmm_plan **out);
 GCNB_API int gcnb_spmm_plan_destroy(gcnb_spmm_plan *plan);
+/* d_out[i] = value of the first entry (i, i + col0) of CSR row i, 0 when the row has none: the diagonal of a row block of
+ * the normalised adjacency (src/parser.cpp:164-181: 1 / deg_i), whose square roots are the scales of a bit-tile plan */
+GCNB_API int gcnb_csr_diagonal_f32(const uint32_t *d_indptr, const uint32_t *d_indices, const float *d_values,
+                                   int64_t n_rows, int64_t col0, float *d_out, gcnb_stream_t stream);
 /* number of segments / split rows / queues (introspection for tests & DESIGN numbers) */
 GCNB_API int gcnb_spmm_plan_info(const gcnb_spmm_plan *plan, int64_t out[8]);
 
@@ -151,6 +155,7 @@ GCNB_API int gcnb_bittile_spmm16_f32(gcnb_bittile_plan *plan, const float *d_B, 
  * kernel gathers B through it and both halves of the product add their rows to C through it: the caller's operands keep
  * their numbering.  Needs a plan whose remainder is the ELL kernel (every entry factors).  h_values of
  * gcnb_bittile_plan_create may be NULL when both scale arrays are given: the matrix is then the PATTERN scaled by them. */
+GCNB_API int64_t gcnb_bittile_plan_unfactored(const gcnb_bittile_plan *plan); /* entries with value != row_scale * col_scale */
 GCNB_API int gcnb_bittile_plan_set_permutation(gcnb_bittile_plan *plan, const uint32_t *h_old_of_new, gcnb_stream_t stream);
 /* kernels launched per 16-column product (pack, MMA kernel, remainder [+ combine], [+ final add]) */
 GCNB_API int gcnb_bittile_plan_launches(const gcnb_bittile_plan *plan);

@@ -100,7 +100,8 @@ GCNB_API int gcnb_gcn_graph_staged(const gcnb_gcn *g);
 GCNB_API int gcnb_gcn_graph_bittile(const gcnb_gcn *g);
 /* which fast paths are active right now: out = {window-staged GraphSum, bit-tile GraphSum, dense-feature first layer
  * (tensor-core X W0 / X^T dH kernels), evaluation through the propagated features A_hat X, CUDA-graph replay usable,
- * background set-up still pending (gcnb_gcn_finish_setup), exact-split tcgen05 GEMM packed, row-partitioned} */
+ * background set-up still pending (gcnb_gcn_finish_setup), exact-split tcgen05 GEMM packed, 1 = row-partitioned /
+ * 2 = the bit tiles were built from the graph renumbered community by community (transparent: GCNB_RENUMBER=0 disables)} */
 GCNB_API int gcnb_gcn_path_info(const gcnb_gcn *g, int out[8]);
 GCNB_API int64_t gcnb_gcn_launches_total(const gcnb_gcn *g);
 /* CUDA-graph replay of the training epoch and of the evaluation passes (small datasets are launch-bound).  Default: on

@@ -336,6 +336,21 @@ spmm_seg_kernel(const uint4 *__restrict__ segs, const uint32_t *__restrict__ que
   }
 }
 
+// out[i] = value of the first entry (i, i + col0) of row i, 0 if the row has none (the scales of a bit-tile plan are the
+// square roots of the diagonal of the normalised adjacency)
+__global__ void csr_diagonal_kernel(const uint32_t *__restrict__ indptr, const uint32_t *__restrict__ indices,
+                                    const float *__restrict__ values, int64_t n_rows, int64_t col0, float *__restrict__ out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_rows; i += (int64_t)gridDim.x * blockDim.x) {
+    float d = 0.f;
+    for (uint32_t e = indptr[i]; e < indptr[i + 1]; e++)
+      if ((int64_t)indices[e] == i + col0) {
+        d = values[e];
+        break;
+      }
+    out[i] = d;
+  }
+}
+
 // rows cut into several segments: out[row] = partial[s0] + partial[s0+1] + ... in ascending order
 __global__ void spmm_combine_kernel(const uint32_t *__restrict__ split_row, const uint32_t *__restrict__ split_slot,
                                     const float *__restrict__ scratch, float *__restrict__ C, int64_t n_split,
@@ -474,6 +489,16 @@ int gcnb_spmm_plan_create(const uint32_t *d_indptr, const uint32_t *d_indices, i
     return rc;
   }
   *out = p;
+  return 0;
+}
+
+int gcnb_csr_diagonal_f32(const uint32_t *d_indptr, const uint32_t *d_indices, const float *d_values, int64_t n_rows,
+                          int64_t col0, float *d_out, gcnb_stream_t stream) {
+  if (!d_indptr || !d_out || n_rows < 0 || (n_rows > 0 && (!d_indices || !d_values))) return GCNB_E_BADARG;
+  if (n_rows == 0) return 0;
+  const int blocks = (int)std::min<int64_t>((n_rows + 255) / 256, (int64_t)std::max(1, device_info().sm_count) * 8);
+  csr_diagonal_kernel<<<blocks, 256, 0, as_stream(stream)>>>(d_indptr, d_indices, d_values, n_rows, col0, d_out);
+  GCNB_LAUNCH_CHECK();
   return 0;
 }
 

@@ -757,6 +757,7 @@ struct gcnb_bittile_plan {
   gcnb::EllDev *ell = nullptr;    // pattern-only remainder (spmm_ell.cu): every remainder entry factors
   float *d_B2 = nullptr;          // [n_cols + 1][16]: diag(col_scale) * B of the current launch, last row zero
   int rem_ctas = 0;               // CTAs per SM of the remainder kernel (0 = its default)
+  int64_t n_unfactored = 0;       // entries whose value is not row_scale * col_scale (0: the matrix is a scaled pattern)
   uint32_t *d_perm = nullptr;     // gcnb_bittile_plan_set_permutation: plan index k = caller's row perm[k] (needs the merge path)
   int merge_by_reduction = 1;     // GCNB_BT_MERGE=0 (tuning probe): partial buffers + bt_add_kernel even with the ELL remainder
   cudaStream_t aux = nullptr;
@@ -876,6 +877,7 @@ int gcnb_bittile_plan_create(const uint32_t *h_indptr, const uint32_t *h_indices
   };
   p->n_rows = n_rows; p->n_cols = n_cols; p->nnz = H.nnz; p->n_blk = H.n_blk; p->n_tiles = H.n_tiles;
   p->tile_nnz = H.tile_nnz; p->rem_nnz = (int64_t)H.r_indices.size(); p->n_cta = H.n_cta;
+  p->n_unfactored = H.n_unfactored;
   p->chunk = H.chunk;
   p->rb = H.rb;
   p->n_chunks = (n_cols + 127) / 128 * 2;  // 64-row units of the packed B' image, padded to whole 128-column chunks
@@ -940,6 +942,9 @@ int gcnb_bittile_plan_info(const gcnb_bittile_plan *p, int64_t out[8]) {
   out[6] = p->n_tiles * (int64_t)kBtRows * p->rb * (p->chunk / 8); out[7] = p->n_chunks * (int64_t)kBtChunkBytes;
   return 0;
 }
+
+// entries of the matrix whose value is not row_scale * col_scale (0: a renumbered, pattern-only plan may replace this one)
+int64_t gcnb_bittile_plan_unfactored(const gcnb_bittile_plan *p) { return p ? p->n_unfactored : -1; }
 
 // A plan built from a RENUMBERED matrix (rows and columns permuted alike, e.g. community by community): plan index k is row
 // h_old_of_new[k] of the caller's operands.  The pack kernel gathers B through it and both halves of the product add their

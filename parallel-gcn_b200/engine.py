@@ -281,8 +281,10 @@ class GCN:
         out = (C.c_int * 8)()
         check(lib.gcnb_gcn_path_info(self.h, out))
         keys = ("graph_staged", "graph_bittile", "dense_fast", "propagated_features", "cuda_graph", "setup_pending",
-                "dense_tc", "partitioned")
-        return dict(zip(keys, [bool(x) for x in out]))
+                "dense_tc")
+        d = dict(zip(keys, [bool(x) for x in out]))
+        d["partitioned"], d["graph_renumbered"] = out[7] == 1, out[7] == 2
+        return d
 
     def finish_setup(self):
         """attach the background-staged GraphSum representation now (GCNB_ASYNC_STAGE=1); no-op otherwise"""

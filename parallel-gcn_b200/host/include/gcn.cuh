@@ -160,7 +160,8 @@ class GCN {
   void finish_setup();
   bool graph_bittile() const;  // GraphSum at width 16 runs the tcgen05 bit-tile path (default when the graph has dense blocks)
   // which fast paths are active: {window-staged GraphSum, bit-tile GraphSum, dense-feature first layer, evaluation through
-  // the propagated features A_hat X, CUDA-graph replay, background set-up still pending, exact-split tcgen05 GEMM, partitioned}
+  // the propagated features A_hat X, CUDA-graph replay, background set-up still pending, exact-split tcgen05 GEMM,
+  // 1 = partitioned / 2 = graph renumbered for the bit tiles}
   void path_info(int out[8]) const;
   bool graph_staged() const;  // GraphSum at widths 16 / >= 64 runs the window-staged kernels (csrc/spmm_stage.cu)
   size_t launches_total() const;

@@ -11,6 +11,7 @@
 #include <thread>
 #include <tuple>
 #include "../../../include/gcnb.h"
+#include "../../../include/gcnb_engine.h"
 
 GCNSmartObjects::GCNSmartObjects(const natural n_layers)
     : forward_training_stream(High), forward_evaluation_stream(High) {
@@ -61,7 +62,7 @@ static GCNDataView view_of(const GCNData &d) {
 DevGCNData::DevGCNData(const GCNData &gcn_data) : DevGCNData(view_of(gcn_data)) {}
 
 DevGCNData::DevGCNData(const GCNDataView &v)
-    : dev_graph_index(v.graph_indptr, v.num_nodes + 1, v.graph_indices, v.graph_nnz),
+    : dev_graph_index((setup_lap(nullptr), v.graph_indptr), v.num_nodes + 1, v.graph_indices, v.graph_nnz),
       dev_feature_index(v.feat_indptr, v.num_nodes + 1, v.feat_indices, v.feat_nnz) {
   setup_lap("upload graph + feature index");
   label_size = static_cast<natural>(v.num_nodes);
@@ -216,8 +217,11 @@ struct GCNEngineState {
   gcnb_bittile_plan *bt_pending = nullptr;
   int bt_rc = 0;
   const real *graph_values_dev = nullptr;
+  bool graph_renumbered = false;  // the bit-tile plan was built from the graph renumbered community by community
+  int64_t graph_communities = 0;
   bool setup_pending = false;  // a background build (bit tiles and / or window staging) has not been attached yet
   bool bt_fallback_stage = false;  // the helper found no dense blocks worth bit tiles: it staged the windows instead
+  bool bt_collective = false;  // row-partitioned: the ranks agree on the bit-tile path in finish_stage()
   void finish_stage() {
     if (!setup_pending) return;
     setup_pending = false;
@@ -225,11 +229,48 @@ struct GCNEngineState {
     if (bt_thread.joinable()) {
       bt_thread.join();
       GCNB_CALL(bt_rc);
-      if (bt_pending) {
+    }
+    if (dist) {
+      // every rank is here before the same training epoch (or in its finish_setup() call): collective from now on
+      bool use_bt = false;
+      if (bt_collective) {
+        natural ok_flag = bt_pending ? 1u : 0u;
+        dev_shared_ptr<natural> d_flag(1);
+        CHECK_CUDA_ERROR(cudaMemcpy(d_flag.get(), &ok_flag, sizeof(natural), cudaMemcpyHostToDevice));
+        GCNB_CALL(gcnb_comm_all_reduce_sum(comm, d_flag.get(), 1, 1, stream));
+        CHECK_CUDA_ERROR(cudaStreamSynchronize(stream));
+        CHECK_CUDA_ERROR(cudaMemcpy(&ok_flag, d_flag.get(), sizeof(natural), cudaMemcpyDeviceToHost));
+        use_bt = ok_flag == (natural)gcnb_comm_world(comm);  // every rank has dense blocks worth the path
+      }
+      if (use_bt) {
         graph_bittile = bt_pending;
         bt_pending = nullptr;
         GCNB_CALL(gcnb_spmm_plan_attach_bittile(graph_plan, graph_bittile, graph_values_dev));
+        if (stage_job) {  // built as a precaution by a rank that ... cannot happen when all ranks are ok; drop it
+          GCNB_CALL(gcnb_spmm_plan_stage_async_finish(nullptr, stage_job));
+          stage_job = nullptr;
+        }
+      } else {
+        if (bt_pending) {
+          gcnb_bittile_plan_destroy(bt_pending);
+          bt_pending = nullptr;
+        }
+        if (stage_job) {
+          GCNB_CALL(gcnb_spmm_plan_stage_async_finish(graph_plan, stage_job));
+          stage_job = nullptr;
+        } else {
+          GCNB_CALL(gcnb_spmm_plan_stage(graph_plan, nullptr, nullptr, graph_values_dev, 16, stream));
+        }
+        int64_t sinfo[8];
+        GCNB_CALL(gcnb_spmm_plan_stage_info(graph_plan, sinfo));
+        graph_staged = sinfo[0] != 0;
       }
+      return;
+    }
+    if (bt_pending) {
+      graph_bittile = bt_pending;
+      bt_pending = nullptr;
+      GCNB_CALL(gcnb_spmm_plan_attach_bittile(graph_plan, graph_bittile, graph_values_dev));
     }
     if (stage_job) {
       GCNB_CALL(gcnb_spmm_plan_stage_async_finish(graph_plan, stage_job));
@@ -467,8 +508,8 @@ void GCN::init(bool quiet, const natural *h_graph_indptr, const natural *h_graph
     //   bit tiles (csrc/spmm_bittile.cu, default on sm_100): the dense blocks of the adjacency as bit maps on the tcgen05
     //     tensor cores + a pattern-only gather for the rest; used when at least a quarter of the entries sit in tiles;
     //   window staging (csrc/spmm_stage.cu): shared-memory gathers for the clustered part; the fallback when the graph
-    //     has no dense blocks, GCNB_BITTILE=0, and the default of the row-partitioned engine (whose exchange overlaps
-    //     the staged windows of the rank's own slab; GCNB_BITTILE=1 switches it to bit tiles, agreed collectively).
+    //     has no dense blocks or with GCNB_BITTILE=0 (row-partitioned: its exchange overlaps the staged windows of the
+    //     rank's own slab).  Row-partitioned models take bit tiles only when EVERY rank finds them worth it.
     // Large graphs (no CUDA-graph replay) build it on a helper thread while the first epochs run on the generic
     // kernel (GCNB_ASYNC_STAGE=0: build synchronously); it is attached before training epoch GCNB_STAGE_SWITCH_EPOCH
     // (128) or by finish_setup(), never at a timing-dependent moment, so runs stay bit-reproducible.
@@ -479,7 +520,7 @@ void GCN::init(bool quiet, const natural *h_graph_indptr, const natural *h_graph
       d16 |= d == 16;
     }
     const char *bt_env = getenv("GCNB_BITTILE");
-    const bool bt_default = !st->dist;  // row-partitioned: opt-in
+    const bool bt_default = true;  // also row-partitioned (N = 2: step 2.18 -> 1.45 ms); the ranks agree collectively
     const bool bt_on = N > 0 && (bt_env ? atoi(bt_env) != 0 : bt_default) && gcnb_bittile_supported();
     if (wanted && st->dist) GCNB_CALL(gcnb_spmm_plan_set_own_cols(st->graph_plan, (int64_t)st->row0, (int64_t)(st->row0 + N)));
     const char *async_env = getenv("GCNB_ASYNC_STAGE");
@@ -489,57 +530,81 @@ void GCN::init(bool quiet, const natural *h_graph_indptr, const natural *h_graph
     st->graph_values_dev = dev_data.dev_graph_value.get();
 
     if (wanted && st->dist) {
-      if (bt_on && d16) {
-        // Row-partitioned model: this rank's row block x all global columns.  The scales are the square roots of the
-        // diagonal values (the diagonal of local row i is global column row0 + i); every rank's block of scales is
-        // all-gathered so that all ranks use the same column scales.  Whether the path is used is agreed collectively
-        // (the exchange in graphsum() differs between the two paths).  Synchronous: every step below is collective.
-        const size_t nnz = dev_data.dev_graph_index.indices_size;
-        std::vector<natural> hp((size_t)N + 1), hi(nnz);
-        std::vector<real> hv(nnz);
+      // Row-partitioned model: this rank's row block x all global columns.  Decisions that change the exchange pattern
+      // (which representation, when it is attached) are taken COLLECTIVELY and at fixed points: the scales and the size
+      // criterion here, the agreement on bit tiles in finish_stage() (every rank calls it before the same training epoch).
+      const size_t nnz = dev_data.dev_graph_index.indices_size;
+      const size_t world = (size_t)gcnb_comm_world(st->comm);
+      const natural *d_ip = dev_data.dev_graph_index.dev_indptr.get(), *d_ix = dev_data.dev_graph_index.dev_indices.get();
+      const real *d_gv = dev_data.dev_graph_value.get();
+      // global entry count: the background criterion must not differ between ranks
+      double cnt = (double)nnz;
+      {
+        dev_shared_ptr<real> d_cnt(1);
+        real c32 = (real)nnz;  // fp32 sum of counts: only compared with a threshold
+        CHECK_CUDA_ERROR(cudaMemcpy(d_cnt.get(), &c32, sizeof(real), cudaMemcpyHostToDevice));
+        GCNB_CALL(gcnb_comm_all_reduce_sum(st->comm, d_cnt.get(), 1, 0, st->stream));
         CHECK_CUDA_ERROR(cudaStreamSynchronize(st->stream));
-        CHECK_CUDA_ERROR(cudaMemcpy(hp.data(), dev_data.dev_graph_index.dev_indptr.get(), hp.size() * sizeof(natural), cudaMemcpyDeviceToHost));
-        CHECK_CUDA_ERROR(cudaMemcpy(hi.data(), dev_data.dev_graph_index.dev_indices.get(), nnz * sizeof(natural), cudaMemcpyDeviceToHost));
-        CHECK_CUDA_ERROR(cudaMemcpy(hv.data(), dev_data.dev_graph_value.get(), nnz * sizeof(real), cudaMemcpyDeviceToHost));
-        const size_t world = (size_t)gcnb_comm_world(st->comm);
-        std::vector<real> s_loc(st->block, 0.f), s_all(world * st->block, 0.f);
-        for (size_t i = 0; i < N; i++)
-          for (natural k = hp[i]; k < hp[i + 1]; k++)
-            if (hi[k] == (natural)(st->row0 + i)) {
-              if (hv[k] > 0.f) s_loc[i] = sqrtf(hv[k]);
-              break;
-            }
+        CHECK_CUDA_ERROR(cudaMemcpy(&c32, d_cnt.get(), sizeof(real), cudaMemcpyDeviceToHost));
+        cnt = c32;
+      }
+      const bool dist_background = (cnt + (double)st->f_nnz_global) > (double)(size_t(8) << 20) && !(async_env && atoi(async_env) == 0);
+      std::vector<real> s_all;
+      if (bt_on && d16) {
+        // scales = square roots of the diagonal values (the diagonal of local row i is global column row0 + i); every
+        // rank's block is all-gathered so that all ranks use the same column scales
         dev_shared_ptr<real> d_loc(st->block), d_all(world * st->block);
-        CHECK_CUDA_ERROR(cudaMemcpy(d_loc.get(), s_loc.data(), st->block * sizeof(real), cudaMemcpyHostToDevice));
+        CHECK_CUDA_ERROR(cudaMemsetAsync(d_loc.get(), 0, st->block * sizeof(real), st->stream));
+        GCNB_CALL(gcnb_csr_diagonal_f32(d_ip, d_ix, d_gv, (int64_t)N, (int64_t)st->row0, d_loc.get(), st->stream));
         GCNB_CALL(gcnb_comm_all_gather_f32(st->comm, d_loc.get(), d_all.get(), (int64_t)st->block, st->stream));
         CHECK_CUDA_ERROR(cudaStreamSynchronize(st->stream));
+        s_all.resize(world * st->block);
         CHECK_CUDA_ERROR(cudaMemcpy(s_all.data(), d_all.get(), s_all.size() * sizeof(real), cudaMemcpyDeviceToHost));
-        for (real &x : s_all)
-          if (!(x > 0.f)) x = std::nanf("");  // no usable diagonal: entries of that row / column stay in the remainder
-        std::vector<real> s_rows(s_all.begin() + (ptrdiff_t)st->row0, s_all.begin() + (ptrdiff_t)(st->row0 + N));
-        gcnb_bittile_plan *bt = nullptr;
-        GCNB_CALL(gcnb_bittile_plan_create(hp.data(), hi.data(), hv.data(), (int64_t)N, (int64_t)st->n_global, s_rows.data(),
-                                           s_all.data(), 0, 0, 0, st->stream, &bt));
-        int64_t binfo[8];
-        GCNB_CALL(gcnb_bittile_plan_info(bt, binfo));
-        natural ok_flag = (binfo[0] > 0 && binfo[1] * 4 >= (int64_t)nnz) ? 1u : 0u;
-        dev_shared_ptr<natural> d_flag(1);
-        CHECK_CUDA_ERROR(cudaMemcpy(d_flag.get(), &ok_flag, sizeof(natural), cudaMemcpyHostToDevice));
-        GCNB_CALL(gcnb_comm_all_reduce_sum(st->comm, d_flag.get(), 1, 1, st->stream));
-        CHECK_CUDA_ERROR(cudaStreamSynchronize(st->stream));
-        CHECK_CUDA_ERROR(cudaMemcpy(&ok_flag, d_flag.get(), sizeof(natural), cudaMemcpyDeviceToHost));
-        if (ok_flag == (natural)world) {  // every rank has dense blocks worth the path
-          st->graph_bittile = bt;
-          GCNB_CALL(gcnb_spmm_plan_attach_bittile(st->graph_plan, bt, dev_data.dev_graph_value.get()));
-        } else {
-          gcnb_bittile_plan_destroy(bt);
-        }
+        for (real &x : s_all) x = x > 0.f ? sqrtf(x) : std::nanf("");  // no usable diagonal: that row / column stays in the remainder
       }
-      GCNB_CALL(gcnb_spmm_plan_stage(st->graph_plan, h_graph_indptr, h_graph_indices, dev_data.dev_graph_value.get(),
-                                     16, st->stream));
-      int64_t sinfo[8];
-      GCNB_CALL(gcnb_spmm_plan_stage_info(st->graph_plan, sinfo));
-      st->graph_staged = sinfo[0] != 0;
+      const size_t row0 = st->row0, n_global = st->n_global;
+      auto make_dist = [N, nnz, d_ip, d_ix, d_gv, row0, n_global, s_all](cudaStream_t stream, gcnb_bittile_plan **out) -> int {
+        *out = nullptr;
+        std::vector<natural> hp((size_t)N + 1), hi(nnz);
+        std::vector<real> hv(nnz);
+        int rc = (int)cudaMemcpyAsync(hp.data(), d_ip, hp.size() * sizeof(natural), cudaMemcpyDeviceToHost, stream);
+        if (!rc) rc = (int)cudaMemcpyAsync(hi.data(), d_ix, nnz * sizeof(natural), cudaMemcpyDeviceToHost, stream);
+        if (!rc) rc = (int)cudaMemcpyAsync(hv.data(), d_gv, nnz * sizeof(real), cudaMemcpyDeviceToHost, stream);
+        if (!rc) rc = (int)cudaStreamSynchronize(stream);
+        if (rc) return rc;
+        gcnb_bittile_plan *bt = nullptr;
+        rc = gcnb_bittile_plan_create(hp.data(), hi.data(), hv.data(), (int64_t)N, (int64_t)n_global, s_all.data() + row0,
+                                      s_all.data(), 0, 0, 0, (gcnb_stream_t)stream, &bt);
+        if (rc) return rc;
+        int64_t binfo[8];
+        gcnb_bittile_plan_info(bt, binfo);
+        if (binfo[0] > 0 && binfo[1] * 4 >= (int64_t)nnz) *out = bt;
+        else gcnb_bittile_plan_destroy(bt);
+        return 0;
+      };
+      st->bt_collective = bt_on && d16;
+      if (dist_background) {
+        st->setup_pending = true;
+        int device = 0;
+        CHECK_CUDA_ERROR(cudaGetDevice(&device));
+        GCNEngineState *state = st.get();
+        const bool try_bt = st->bt_collective;
+        CHECK_CUDA_ERROR(cudaStreamSynchronize(st->stream));
+        st->bt_thread = std::thread([state, make_dist, device, d_gv, try_bt] {
+          cudaStream_t hs = nullptr;
+          int rc = (int)cudaSetDevice(device);
+          if (!rc) rc = (int)cudaStreamCreateWithFlags(&hs, cudaStreamNonBlocking);
+          if (!rc && try_bt) rc = make_dist(hs, &state->bt_pending);
+          if (hs) cudaStreamDestroy(hs);
+          // no dense blocks worth bit tiles on this rank: the ranks will agree on window staging; build it now
+          if (!rc && !state->bt_pending) rc = gcnb_spmm_plan_stage_async_begin(state->graph_plan, d_gv, 16, &state->stage_job);
+          state->bt_rc = rc;
+        });
+      } else {
+        if (st->bt_collective) GCNB_CALL(make_dist(st->stream, &st->bt_pending));
+        st->setup_pending = true;
+        st->finish_stage();  // synchronous: agree and attach right away
+      }
     } else if (wanted) {
       const size_t nnz = dev_data.dev_graph_index.indices_size;
       const natural *d_ip = dev_data.dev_graph_index.dev_indptr.get(), *d_ix = dev_data.dev_graph_index.dev_indices.get();
@@ -547,7 +612,10 @@ void GCN::init(bool quiet, const natural *h_graph_indptr, const natural *h_graph
       // everything is read back from the device: the helper must not depend on the caller's host arrays
       int64_t min_cover = 25;  // per cent of the entries that must sit in tiles (GCNB_BT_MIN_COVERAGE: tuning / test probe)
       if (const char *e = getenv("GCNB_BT_MIN_COVERAGE")) min_cover = std::max(0, atoi(e));
-      auto make = [N, nnz, d_ip, d_ix, d_gv, min_cover](cudaStream_t stream, gcnb_bittile_plan **out) -> int {
+      int renumber = 1;  // GCNB_RENUMBER=0: never renumber the graph for the bit tiles
+      if (const char *e = getenv("GCNB_RENUMBER")) renumber = atoi(e);
+      GCNEngineState *stp = st.get();
+      auto make = [N, nnz, d_ip, d_ix, d_gv, min_cover, renumber, stp](cudaStream_t stream, gcnb_bittile_plan **out) -> int {
         *out = nullptr;
         std::vector<natural> hp((size_t)N + 1), hi(nnz);
         std::vector<real> hv(nnz);
@@ -562,7 +630,62 @@ void GCN::init(bool quiet, const natural *h_graph_indptr, const natural *h_graph
         if (rc) return rc;
         int64_t binfo[8];
         gcnb_bittile_plan_info(bt, binfo);
-        if (binfo[0] > 0 && binfo[1] * 100 >= (int64_t)nnz * min_cover) *out = bt;  // worth it when a quarter of the entries sit in tiles
+        int64_t cover = nnz ? binfo[1] * 100 / (int64_t)nnz : 0;
+        // Locality renumbering, transparent: when the given node order leaves less than half of the entries
+        // in dense blocks, look for communities (label propagation, host/src/reorder.cpp), renumber the GRAPH community by
+        // community and build the tiles from that; the permutation lives inside the GraphSum plan (the pack kernel
+        // gathers through it, both halves of the product add their rows through it), so features, labels, masks, the
+        // Philox streams and every output keep the caller's numbering.  Needs a matrix that is a scaled pattern.
+        if (renumber && cover < 50 && gcnb_bittile_plan_unfactored(bt) == 0 && N > 1) {
+          std::vector<real> s((size_t)N, 0.f);
+          bool diag_ok = true;
+          for (size_t i = 0; i < N && diag_ok; i++) {
+            diag_ok = false;
+            for (natural k = hp[i]; k < hp[i + 1]; k++)
+              if (hi[k] == (natural)i) {
+                diag_ok = hv[k] > 0.f;
+                s[i] = sqrtf(hv[k]);
+                break;
+              }
+          }
+          if (diag_ok) {
+            std::vector<natural> new_of_old(N), hp2((size_t)N + 1), hi2(nnz);
+            int64_t n_comm = 0;
+            rc = gcnb_reorder_communities((int64_t)N, hp.data(), hi.data(), 0, 1, new_of_old.data(), &n_comm);
+            if (!rc) rc = gcnb_permute_csr((int64_t)N, hp.data(), hi.data(), new_of_old.data(), hp2.data(), hi2.data());
+            if (rc) {
+              gcnb_bittile_plan_destroy(bt);
+              return rc;
+            }
+            std::vector<real> s2((size_t)N);
+            std::vector<natural> old_of_new(N);
+            for (size_t i = 0; i < N; i++) {
+              s2[new_of_old[i]] = s[i];
+              old_of_new[new_of_old[i]] = (natural)i;
+            }
+            gcnb_bittile_plan *bt2 = nullptr;
+            rc = gcnb_bittile_plan_create(hp2.data(), hi2.data(), nullptr, (int64_t)N, (int64_t)N, s2.data(), s2.data(), 0, 0, 0,
+                                          (gcnb_stream_t)stream, &bt2);
+            if (rc) {
+              gcnb_bittile_plan_destroy(bt);
+              return rc;
+            }
+            int64_t binfo2[8];
+            gcnb_bittile_plan_info(bt2, binfo2);
+            const int64_t cover2 = nnz ? binfo2[1] * 100 / (int64_t)nnz : 0;
+            if (cover2 >= cover + 10 && cover2 >= min_cover &&
+                gcnb_bittile_plan_set_permutation(bt2, old_of_new.data(), (gcnb_stream_t)stream) == 0) {
+              gcnb_bittile_plan_destroy(bt);
+              bt = bt2;
+              cover = cover2;
+              stp->graph_renumbered = true;
+              stp->graph_communities = n_comm;
+            } else {
+              gcnb_bittile_plan_destroy(bt2);
+            }
+          }
+        }
+        if (binfo[0] >= 0 && cover >= min_cover && cover > 0) *out = bt;  // worth it when a quarter of the entries sit in tiles
         else gcnb_bittile_plan_destroy(bt);
         return 0;
       };
@@ -678,7 +801,8 @@ bool GCN::graph_staged() const { return st->graph_staged; }
 bool GCN::graph_bittile() const { return st->graph_bittile != nullptr; }
 void GCN::path_info(int out[8]) const {
   out[0] = st->graph_staged; out[1] = st->graph_bittile != nullptr; out[2] = st->dense_fast; out[3] = st->ax_ready;
-  out[4] = st->graphs_usable(); out[5] = st->setup_pending; out[6] = st->x_img.get() != nullptr; out[7] = st->dist;
+  out[4] = st->graphs_usable(); out[5] = st->setup_pending; out[6] = st->x_img.get() != nullptr;
+  out[7] = st->dist ? 1 : (st->graph_renumbered ? 2 : 0);
 }
 size_t GCN::launches_total() const { return st->launches; }
 void GCN::set_time_graphsum(bool on) {

@@ -87,6 +87,30 @@ def test_bench_path_on_a_sixteenth_of_the_reddit_shape_graph(O, eng, path):
             os.environ.pop(k, None)
 
 
+@pytest.mark.parametrize("n,deg", [(20000, 100), (60000, 80)])  # CUDA-graph mode (synchronous build) / background build
+def test_shuffled_node_ids_are_renumbered_transparently(O, eng, n, deg):
+    """a community graph whose node ids carry no locality.  The engine finds the communities, builds its
+    bit tiles from the renumbered graph and keeps the renumbering INSIDE the GraphSum plan: features, labels, Philox
+    streams, logits stay in the caller's numbering, so the run must follow the oracle's on the very same (shuffled)
+    dataset -- same masks, same per-row predictions."""
+    base = eng.synth_dataset(n, n * deg, 32, 6, n_blocks=n // 2500, sigma=1.0, seed=11)
+    shuffle = np.random.default_rng(5).permutation(n).astype(np.uint32)
+    ds = eng.permute_dataset(base, shuffle)
+    for env, want in (({}, True), ({"GCNB_RENUMBER": "0"}, False)):
+        os.environ.update(env)
+        try:
+            og = O.OracleGCN(_ods(O, ds, 32, 6), flavour="ref_gpu")
+            g = eng.GCN(ds)
+            g.finish_setup()
+            info = g.path_info()
+            assert info["graph_renumbered"] == want and info["graph_bittile"] == want, (env, info)
+            _compare_epochs(og, g, 3, 6, "shuffled ids, renumbered=%s" % want)
+            g.close()
+        finally:
+            for k in env:
+                os.environ.pop(k, None)
+
+
 def test_pubmed_graph_with_synthetic_svmlight_features(O, eng):
     root = pubmed_root(ROOT)
     ds_e = eng.parse_dataset(root, "pubmed")
