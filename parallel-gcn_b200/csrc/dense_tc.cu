@@ -1,10 +1,12 @@
 // dense_tc.cu -- exact-split tcgen05 GEMM for the wide first layer:  out[n x p] = X[n x f] * W[f x p]  (hidden 600 of
 // parameters/parameters_reddit.txt; SparseMatmul::forward on an all-columns feature matrix, src/module.cu:108-132).
 //
-// STATUS (end of round 1): compiled, packing layouts emulated on the CPU (tests/test_dense_tc_cpu.py), NOT yet run on a
-// GPU; nothing calls it by default (opt-in GPU test GCNB_TEST_DENSE_TC=1).  It re-uses exactly the tcgen05 pieces the
-// bit-tile GraphSum validated on B200 (spmm_bittile.cu): no-swizzle K-major shared-memory descriptors fed by
-// cp.async.bulk of pre-packed operand images, fp32 accumulators in TMEM, tcgen05.commit / mbarrier stage recycling.
+// It re-uses exactly the tcgen05 pieces of the bit-tile GraphSum (spmm_bittile.cu): no-swizzle K-major shared-memory
+// descriptors fed by cp.async.bulk of pre-packed operand images, fp32 accumulators in TMEM, tcgen05.commit / mbarrier stage
+// recycling.  First B200 run (round 2): 1.0 ms against 8.0 ms on the SIMT kernel at 232965 x 602 x 600, but 1e-5 off: the
+// tensor core's fp32 accumulate TRUNCATES, and a chain of 228 MMAs into one accumulator drifts by ~228 * 2^-25 of its
+// magnitude.  (The bit-tile product does not drift: its addends are 8-bit-significand pieces whose partial sums stay
+// exactly representable.)  Hence the accumulator CLASSES below.
 //
 // Why: at hidden 600 the product is compute bound (168 GFLOP per call) and the fp32 SIMT kernel runs at ~18 TFLOP/s =
 // 15 ms.  Exactness on bf16 tensor cores: x and w are split into three bf16 pieces each (8 + 8 + 8
@@ -16,8 +18,12 @@
 // from shared memory -- per (block of 128 rows, k-step of 16 features, piece) a 4 KB K-major tile -- so the kernel has no
 // operand transformation at all: one thread streams A and B tiles with bulk copies, one thread issues MMAs, four warps
 // drain the accumulators.  W (f x p) is packed per call (gcnb_dense_tc_pack_w, 2 MB).  The p columns are cut into parts
-// of <= 256 columns (600 -> 3 x 208) so that two accumulator sets fit in TMEM (the epilogue of one item overlaps the
-// MMAs of the next); the parts of a row block are consecutive items of one CTA, so X's tiles are re-read from L2.
+// of <= 160 columns (600 -> 4 x 160); a part owns THREE accumulators of that width in TMEM, one per magnitude class of
+// the piece products -- hi*hi | hi*mid + mid*hi | hi*lo + lo*hi + mid*mid -- so that the only chain whose truncation
+// matters (hi*hi) is one MMA per k-step long (38 at f = 602: <= 38 * 2^-24 of the sum), and the epilogue adds the
+// classes small to large with rounded fp32 adds.  The weight gradient cuts K (the nodes) into slices of <= 32 k-steps for
+// the same reason; their partial tiles are added in ascending order.  The parts of a row block are consecutive items of
+// one CTA, so X's tiles are re-read from L2.
 // Dropout on X is not supported here (the wide configuration has input dropout 0; evaluation never has one).
 #include <algorithm>
 #include <cstdint>
@@ -163,7 +169,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(TcArgs a) {
       mbar_init(&full[i], 1);
       mbar_init(&free_[i], 1);
     }
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < 2; i++) {  // one accumulator set (three classes x pcols columns); slot 1 is unused
       mbar_init(&acc_full[i], 1);
       mbar_init(&acc_empty[i], 4);
     }
@@ -187,19 +193,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(TcArgs a) {
       const TcItem it = tc_item(a, k);
       const int64_t blk = it.blk;
       const int q = it.q;
-      const uint32_t set = (uint32_t)(k & 1), use = (uint32_t)(k >> 1);
+      const uint32_t set = 0u, use = (uint32_t)k;
       const int r_in_blk = warp * 32 + lane;
       const int64_t row = blk * kTcRows + r_in_blk;
       mbar_wait(&acc_full[set], use & 1);
       tc_fence_after();
-      const uint32_t acc0 = tmem + lane_base + set * 256;
+      const uint32_t acc0 = tmem + lane_base;
       float *tile = a.k_slices > 1
                         ? a.out + ((((int64_t)it.slice * a.n_blk + blk) * a.n_parts + q) * kTcRows + r_in_blk) * (int64_t)a.pcols
                         : nullptr;
       for (int c0 = 0; c0 < a.pcols; c0 += 16) {
-        float v[16];
-        tc_ld16(acc0 + c0, v);
+        float v[16], v1[16], v2[16];
+        tc_ld16(acc0 + 2 * a.pcols + c0, v2);  // hi*lo + lo*hi + mid*mid
+        tc_ld16(acc0 + a.pcols + c0, v1);      // hi*mid + mid*hi
+        tc_ld16(acc0 + c0, v);                 // hi*hi
         tc_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 16; i++) v[i] = (v2[i] + v1[i]) + v[i];  // small to large, rounded adds
         if (tile) {  // partial tile of this k slice: every element is written (padding rows / columns hold exact zeros)
 #pragma unroll
           for (int i = 0; i < 4; i++)
@@ -240,10 +250,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(TcArgs a) {
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.pcols >> 3) << 17) | ((uint32_t)(kTcRows >> 4) << 24);
     uint64_t t = 0;
     for (int64_t k = 0; k < n_items; k++) {
-      const uint32_t set = (uint32_t)(k & 1), use = (uint32_t)(k >> 1);
+      const uint32_t set = 0u, use = (uint32_t)k;
       if (use > 0) mbar_wait(&acc_empty[set], (use - 1) & 1);
       tc_fence_after();
-      const uint32_t d = tmem + set * 256;
+      const uint32_t d0 = tmem, d1 = tmem + (uint32_t)a.pcols, d2 = tmem + 2u * (uint32_t)a.pcols;  // accumulator classes
       const TcItem it = tc_item(a, k);
       for (int ks = it.ks0; ks < it.ks1; ks++, t++) {
         const uint32_t s = (uint32_t)(t % kTcStages), u = (uint32_t)(t / kTcStages);
@@ -256,13 +266,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(TcArgs a) {
           const uint64_t a0 = tc_smem_desc(sa, 2048), a1 = tc_smem_desc(sa + kTcATile, 2048), a2 = tc_smem_desc(sa + 2 * kTcATile, 2048);
           const uint64_t b0 = tc_smem_desc(sb, (uint32_t)a.pcols * 16u), b1 = tc_smem_desc(sb + pb, (uint32_t)a.pcols * 16u),
                          b2 = tc_smem_desc(sb + 2 * pb, (uint32_t)a.pcols * 16u);
-          // smallest terms first inside the k-step: lo*hi, hi*lo, mid*mid, mid*hi, hi*mid, hi*hi
-          tc_mma_ss(d, a2, b0, idesc, ks > it.ks0 ? 1u : 0u);
-          tc_mma_ss(d, a0, b2, idesc, 1u);
-          tc_mma_ss(d, a1, b1, idesc, 1u);
-          tc_mma_ss(d, a1, b0, idesc, 1u);
-          tc_mma_ss(d, a0, b1, idesc, 1u);
-          tc_mma_ss(d, a0, b0, idesc, 1u);
+          const uint32_t first = ks > it.ks0 ? 1u : 0u;
+          tc_mma_ss(d2, a2, b0, idesc, first);  // lo*hi   \
+          tc_mma_ss(d2, a0, b2, idesc, 1u);     // hi*lo    > class 2: below 2^-16 of the product
+          tc_mma_ss(d2, a1, b1, idesc, 1u);     // mid*mid /
+          tc_mma_ss(d1, a1, b0, idesc, first);  // mid*hi  \ class 1: below 2^-8
+          tc_mma_ss(d1, a0, b1, idesc, 1u);     // hi*mid  /
+          tc_mma_ss(d0, a0, b0, idesc, first);  // hi*hi: class 0, one MMA per k-step => the shortest chain
           tc_commit(&free_[s]);
         }
         __syncwarp();
@@ -337,8 +347,8 @@ static cudaError_t tc_allow_smem() {
 static void tc_shape(int f, int p, int *KS, int *n_parts, int *pcols) {
   *KS = (f + 15) / 16;
   const int p_pad = (p + 15) / 16 * 16;
-  *n_parts = (p_pad + 255) / 256;
-  *pcols = ((p_pad + *n_parts - 1) / *n_parts + 15) / 16 * 16;  // <= 256: two accumulator sets of 256 TMEM columns
+  *n_parts = (p_pad + 159) / 160;
+  *pcols = ((p_pad + *n_parts - 1) / *n_parts + 15) / 16 * 16;  // <= 160: three accumulator classes in 512 TMEM columns
 }
 
 }  // namespace gcnb
@@ -403,11 +413,9 @@ int gcnb_dense_tc_fwd_f32(const void *d_x_img, const float *d_W, float *d_out, i
 // X^T is packed once (operand rows = features, K = nodes); dH is packed per call; K is cut into slices so that all SMs have
 // work (5 feature blocks x 3 column parts only), the slices' partial tiles are added in ascending order.
 static int tc_tn_slices(int64_t n, int f, int p, int sms) {
-  int KS, n_parts, pcols;
-  tc_shape((int)std::min<int64_t>(n, 1 << 30), p, &KS, &n_parts, &pcols);
-  const int64_t tiles = ((f + kTcRows - 1) / kTcRows) * (int64_t)n_parts;
+  (void)f; (void)p; (void)sms;
   const int64_t ks = (n + 15) / 16;
-  return (int)std::max<int64_t>(1, std::min<int64_t>(ks, (2 * (int64_t)sms) / std::max<int64_t>(1, tiles)));
+  return (int)std::max<int64_t>(1, (ks + 31) / 32);  // <= 32 k-steps per accumulator chain (see the header)
 }
 int64_t gcnb_dense_tc_xt_bytes(int64_t n, int f) {
   return ((f + kTcRows - 1) / kTcRows) * ((n + 15) / 16) * 3 * (int64_t)kTcATile;

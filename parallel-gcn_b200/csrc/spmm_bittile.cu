@@ -479,10 +479,14 @@ __global__ void __launch_bounds__(256) bt_pack_ld_kernel(const float *__restrict
 }
 
 // C[:, 0..16) (row stride ldc) = P + R
+// (plan row k is row perm[k] of C for a renumbered plan)
 __global__ void __launch_bounds__(256) bt_add_ld_kernel(const float *__restrict__ P, const float *__restrict__ R,
-                                                        float *__restrict__ C, int64_t ldc, int64_t n) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    C[(i >> 4) * ldc + (i & 15)] = P[i] + R[i];
+                                                        float *__restrict__ C, int64_t ldc, int64_t n,
+                                                        const uint32_t *__restrict__ perm) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = perm ? (int64_t)__ldg(perm + (i >> 4)) : (i >> 4);
+    C[row * ldc + (i & 15)] = P[i] + R[i];
+  }
 }
 
 __device__ __forceinline__ uint64_t bt_ld_bits(const uint64_t *p) {
@@ -865,7 +869,12 @@ int gcnb_bittile_plan_create(const uint32_t *h_indptr, const uint32_t *h_indices
     if (const char *e = getenv("GCNB_BT_CHUNK")) chunk_cols = atoi(e);    // tuning probe: 64 or 128
   if (row_blocks == 0)
     if (const char *e = getenv("GCNB_BT_RB")) row_blocks = atoi(e);       // tuning probe: 1 or 2
-  // default shape: 128 x 128 tiles (B200, bench graph: MMA kernel 128 us; 256 x 64 items 134 us; 128 x 64 tiles 190 us)
+  // default shape: items of 256 rows x 64 columns whose two halves share a B' stage (B200, bench graph, GraphSum in the
+  // bench step: 235 us; 128 x 128 tiles 242 us; alone the MMA kernels take 131 / 126 us, 128 x 64 tiles 190 us)
+  if (chunk_cols == 0 && row_blocks == 0) {
+    chunk_cols = 64;
+    row_blocks = 2;
+  }
   if (chunk_cols == 0) chunk_cols = row_blocks == 2 ? 64 : 128;
   int rc = bittile_build_host(h_indptr, h_indices, h_values, n_rows, n_cols, h_row_scale, h_col_scale, min_tile_nnz,
                               chunk_cols, row_blocks, di.sm_count, 0, H);
@@ -1010,7 +1019,6 @@ static int bt_slab16(gcnb_bittile_plan *p, const float *d_B, int64_t ldb, float 
   const bool overlap = d_C < d_B + (p->n_cols - 1) * ldb + 16 && d_B < d_C + (p->n_rows - 1) * ldc + 16;
   const bool merge = tiles && p->ell && parts == 15 && p->merge_by_reduction && (uintptr_t)d_C % 16 == 0 && ldc % 4 == 0 &&
                      p->n_rows <= n_groups * 8 && !overlap;
-  if (p->d_perm && !merge) return GCNB_E_UNSUPPORTED;  // a renumbered plan writes its rows through the reduction path only
   if (tiles && (parts & 1)) {
     const int64_t threads = n_groups * 16;
     float *cz = merge ? d_C : nullptr;
@@ -1047,7 +1055,7 @@ static int bt_slab16(gcnb_bittile_plan *p, const float *d_B, int64_t ldb, float 
   GCNB_CHECK(cudaEventRecord(p->ev_join, p->aux));
   GCNB_CHECK(cudaStreamWaitEvent(stream, p->ev_join, 0));
   if ((parts & 8) && !merge) {
-    if (contiguous) {
+    if (contiguous && !p->d_perm) {
       const int64_t n4 = p->n_rows * 4;
       const int blocks = (int)std::min<int64_t>((n4 + 255) / 256, (int64_t)device_info().sm_count * 8);
       bt_add_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const float4 *>(p->d_P),
@@ -1055,7 +1063,7 @@ static int bt_slab16(gcnb_bittile_plan *p, const float *d_B, int64_t ldb, float 
     } else {
       const int64_t n = p->n_rows * 16;
       const int blocks = (int)std::min<int64_t>((n + 255) / 256, (int64_t)device_info().sm_count * 16);
-      bt_add_ld_kernel<<<blocks, 256, 0, stream>>>(p->d_P, p->d_R, d_C, ldc, n);
+      bt_add_ld_kernel<<<blocks, 256, 0, stream>>>(p->d_P, p->d_R, d_C, ldc, n, p->d_perm);
     }
   }
   GCNB_LAUNCH_CHECK();

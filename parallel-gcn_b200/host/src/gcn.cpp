@@ -523,6 +523,9 @@ void GCN::init(bool quiet, const natural *h_graph_indptr, const natural *h_graph
     const bool bt_default = true;  // also row-partitioned (N = 2: step 2.18 -> 1.45 ms); the ranks agree collectively
     const bool bt_on = N > 0 && (bt_env ? atoi(bt_env) != 0 : bt_default) && gcnb_bittile_supported();
     if (wanted && st->dist) GCNB_CALL(gcnb_spmm_plan_set_own_cols(st->graph_plan, (int64_t)st->row0, (int64_t)(st->row0 + N)));
+    // graphs below ~1 M entries are launch-bound (a whole GraphSum is a few microseconds on the generic kernel): no tiles
+    size_t bt_min_nnz = size_t(1) << 20;
+    if (const char *e = getenv("GCNB_BT_MIN_NNZ")) bt_min_nnz = (size_t)std::max(0ll, atoll(e));
     const char *async_env = getenv("GCNB_ASYNC_STAGE");
     const size_t big = dev_data.dev_graph_index.indices_size + dev_data.dev_feature_index.indices_size;
     const bool background = wanted && !st->dist && big > (size_t(8) << 20) && !(async_env && atoi(async_env) == 0);
@@ -563,8 +566,9 @@ void GCN::init(bool quiet, const natural *h_graph_indptr, const natural *h_graph
         for (real &x : s_all) x = x > 0.f ? sqrtf(x) : std::nanf("");  // no usable diagonal: that row / column stays in the remainder
       }
       const size_t row0 = st->row0, n_global = st->n_global;
-      auto make_dist = [N, nnz, d_ip, d_ix, d_gv, row0, n_global, s_all](cudaStream_t stream, gcnb_bittile_plan **out) -> int {
+      auto make_dist = [N, nnz, d_ip, d_ix, d_gv, row0, n_global, s_all, bt_min_nnz](cudaStream_t stream, gcnb_bittile_plan **out) -> int {
         *out = nullptr;
+        if (nnz < bt_min_nnz) return 0;
         std::vector<natural> hp((size_t)N + 1), hi(nnz);
         std::vector<real> hv(nnz);
         int rc = (int)cudaMemcpyAsync(hp.data(), d_ip, hp.size() * sizeof(natural), cudaMemcpyDeviceToHost, stream);
@@ -615,8 +619,9 @@ void GCN::init(bool quiet, const natural *h_graph_indptr, const natural *h_graph
       int renumber = 1;  // GCNB_RENUMBER=0: never renumber the graph for the bit tiles
       if (const char *e = getenv("GCNB_RENUMBER")) renumber = atoi(e);
       GCNEngineState *stp = st.get();
-      auto make = [N, nnz, d_ip, d_ix, d_gv, min_cover, renumber, stp](cudaStream_t stream, gcnb_bittile_plan **out) -> int {
+      auto make = [N, nnz, d_ip, d_ix, d_gv, min_cover, renumber, stp, bt_min_nnz](cudaStream_t stream, gcnb_bittile_plan **out) -> int {
         *out = nullptr;
+        if (nnz < bt_min_nnz) return 0;  // launch-bound regime: one generic kernel beats pack + MMA + remainder
         std::vector<natural> hp((size_t)N + 1), hi(nnz);
         std::vector<real> hv(nnz);
         int rc = (int)cudaMemcpyAsync(hp.data(), d_ip, hp.size() * sizeof(natural), cudaMemcpyDeviceToHost, stream);

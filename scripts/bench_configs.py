@@ -37,6 +37,7 @@ for name in which:
     else:
         ds, w, gen_s = bench.make_dataset(eng, 1, pinned=True)
         g = eng.GCN(ds, hidden_dims=(600,), dropouts=(0.0, 0.1), lr=0.01, weight_decay=5e-5, seed=w["seed"])
+        g.finish_setup()  # attach the background-built GraphSum representation before timing
         for _ in range(2):
             g.train_epoch(); g.eval(2)
         r = g.timed_epochs(5, with_eval=True, time_graphsum=True)

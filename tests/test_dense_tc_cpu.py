@@ -43,7 +43,7 @@ def test_shape_helpers(monkeypatch):
     assert gcnb.lib.gcnb_dense_tc_supported(602, 600) == 1 and gcnb.lib.gcnb_dense_tc_supported(602, 8) == 0
     n_blk, ks = (232965 + 127) // 128, (602 + 15) // 16
     assert gcnb.lib.gcnb_dense_tc_x_bytes(232965, 602) == n_blk * ks * 3 * 4096
-    assert gcnb.lib.gcnb_dense_tc_w_bytes(602, 600) == 3 * ks * 3 * 208 * 32  # 600 columns -> 3 parts of 208
+    assert gcnb.lib.gcnb_dense_tc_w_bytes(602, 600) == 4 * ks * 3 * 160 * 32  # 600 columns -> 4 parts of 160 (3 accumulator classes)
     assert gcnb.lib.gcnb_dense_tc_w_bytes(50, 16) == 1 * 4 * 3 * 16 * 32
 
 
@@ -59,7 +59,7 @@ def _from_bits(b):
 def _shape(f, p):
     KS = (f + 15) // 16
     p_pad = (p + 15) // 16 * 16
-    n_parts = (p_pad + 255) // 256
+    n_parts = (p_pad + 159) // 160
     pcols = ((p_pad + n_parts - 1) // n_parts + 15) // 16 * 16
     return KS, n_parts, pcols
 

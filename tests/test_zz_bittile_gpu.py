@@ -15,8 +15,8 @@ from tests.util import assert_close, to_dev, to_np
 # a wedged mbarrier pipeline must end the run, not hang it: pytest-timeout's thread method exits the process
 pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300, method="thread")]
 f32 = np.float32
-# A shape is (columns per tile, 128-row blocks per item); (0, 0) = the default (128 x 128 tiles)
-SHAPES = [(0, 0), (64, 1), (64, 2)]
+# A shape is (columns per tile, 128-row blocks per item); (0, 0) = the default (items of 256 rows x 64 columns)
+SHAPES = [(0, 0), (64, 1), (128, 1)]
 
 
 def _check(O, gcnb, dev, indptr, indices, values, rs=None, cs=None, min_tile_nnz=0, seed=0, shape=(0, 0), want_ell=None):
