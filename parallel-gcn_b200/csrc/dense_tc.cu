@@ -267,12 +267,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(TcArgs a) {
           const uint64_t b0 = tc_smem_desc(sb, (uint32_t)a.pcols * 16u), b1 = tc_smem_desc(sb + pb, (uint32_t)a.pcols * 16u),
                          b2 = tc_smem_desc(sb + 2 * pb, (uint32_t)a.pcols * 16u);
           const uint32_t first = ks > it.ks0 ? 1u : 0u;
-          tc_mma_ss(d2, a2, b0, idesc, first);  // lo*hi   \
-          tc_mma_ss(d2, a0, b2, idesc, 1u);     // hi*lo    > class 2: below 2^-16 of the product
-          tc_mma_ss(d2, a1, b1, idesc, 1u);     // mid*mid /
-          tc_mma_ss(d1, a1, b0, idesc, first);  // mid*hi  \ class 1: below 2^-8
-          tc_mma_ss(d1, a0, b1, idesc, 1u);     // hi*mid  /
-          tc_mma_ss(d0, a0, b0, idesc, first);  // hi*hi: class 0, one MMA per k-step => the shortest chain
+          tc_mma_ss(d2, a2, b0, idesc, first);  // lo*hi    class 2 (with the next two): below 2^-16 of the product
+          tc_mma_ss(d2, a0, b2, idesc, 1u);     // hi*lo
+          tc_mma_ss(d2, a1, b1, idesc, 1u);     // mid*mid
+          tc_mma_ss(d1, a1, b0, idesc, first);  // mid*hi   class 1 (with the next one): below 2^-8
+          tc_mma_ss(d1, a0, b1, idesc, 1u);     // hi*mid
+          tc_mma_ss(d0, a0, b0, idesc, first);  // hi*hi    class 0: one MMA per k-step => the shortest chain
           tc_commit(&free_[s]);
         }
         __syncwarp();

@@ -111,7 +111,8 @@ class GCN {
   void backward_pass(cudaStream_t stream);
   std::pair<real, real> finalize(cudaStream_t stream, int slot) const;
   std::pair<real, real> read_result(int slot) const;
-  void train_and_eval(natural split, std::pair<real, real> &train, std::pair<real, real> &val);
+  // returns false when sync == false and the passes were only enqueued (graph replays): results via read_result after a sync
+  bool train_and_eval(natural split, std::pair<real, real> &train, std::pair<real, real> &val, bool sync = true);
   void print_variable_info() const;
   void init(bool quiet, const natural *h_graph_indptr = nullptr, const natural *h_graph_indices = nullptr,
             const GCNPartition *part = nullptr);

@@ -137,7 +137,7 @@ def test_wide_hidden_layer_model_of_parameters_reddit(O, eng):
     g = eng.GCN(ds, lr=0.01, **kw)
     g.finish_setup()
     info = g.path_info()
-    assert info["graph_bittile"] or info["graph_staged"], info
+    assert (info["graph_bittile"] or info["graph_staged"]) and info["dense_tc"], info  # tcgen05: wide GraphSum slabs + exact-split GEMM
     _compare_epochs(og, g, 2, 41, "hidden 600")
     g.close()
 

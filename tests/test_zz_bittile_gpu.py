@@ -282,8 +282,7 @@ def test_engine_background_setup_switches_at_a_fixed_epoch(gcnb, dev):
     same_curve(curves[1], curves[2])
 
 
-# ---- exact-split tcgen05 GEMM for the wide first layer (csrc/dense_tc.cu): opt-in until it has been run on a GPU
-@pytest.mark.skipif(os.environ.get("GCNB_TEST_DENSE_TC") != "1", reason="opt-in: dense_tc.cu not yet run on a GPU")
+# ---- exact-split tcgen05 GEMM for the wide first layer (csrc/dense_tc.cu)
 @pytest.mark.parametrize("n,f,p", [(128, 16, 16), (300, 50, 16), (1000, 602, 600), (4096 + 77, 602, 41)])
 def test_exact_split_gemm_matches_float64(gcnb, dev, n, f, p):
     import torch
@@ -302,7 +301,6 @@ def test_exact_split_gemm_matches_float64(gcnb, dev, n, f, p):
     assert torch.equal(out, out2)
 
 
-@pytest.mark.skipif(os.environ.get("GCNB_TEST_DENSE_TC") != "1", reason="opt-in: dense_tc.cu not yet run on a GPU")
 @pytest.mark.parametrize("n,f,p", [(200, 16, 16), (5000, 50, 41), (30000, 602, 600)])
 def test_exact_split_weight_gradient_matches_float64(gcnb, dev, n, f, p):
     import torch
