@@ -523,6 +523,13 @@ void GCN::init(bool quiet, const natural *h_graph_indptr, const natural *h_graph
     const bool bt_default = true;  // also row-partitioned (N = 2: step 2.18 -> 1.45 ms); the ranks agree collectively
     const bool bt_on = N > 0 && (bt_env ? atoi(bt_env) != 0 : bt_default) && gcnb_bittile_supported();
     if (wanted && st->dist) GCNB_CALL(gcnb_spmm_plan_set_own_cols(st->graph_plan, (int64_t)st->row0, (int64_t)(st->row0 + N)));
+    // tile shape (0 = the plan's default or GCNB_BT_CHUNK / GCNB_BT_RB): models with a wide GraphSum (>= 64 columns, run as
+    // strided 16-column slabs) do better on 128 x 128 tiles (hidden 600: 7.0 vs 8.3 ms per call), width 16 alone on the
+    // default 256 x 64 items (233 vs 242 us)
+    bool wide_graphsum = false;
+    for (const GCNLayer &ly : st->layers) wide_graphsum |= (ly.reorder ? ly.in_dim : ly.out_dim) >= 64;
+    const bool shape_env = getenv("GCNB_BT_CHUNK") || getenv("GCNB_BT_RB");
+    const int bt_chunk = (!shape_env && wide_graphsum) ? 128 : 0, bt_rb = (!shape_env && wide_graphsum) ? 1 : 0;
     // graphs below ~1 M entries are launch-bound (a whole GraphSum is a few microseconds on the generic kernel): no tiles
     size_t bt_min_nnz = size_t(1) << 20;
     if (const char *e = getenv("GCNB_BT_MIN_NNZ")) bt_min_nnz = (size_t)std::max(0ll, atoll(e));
@@ -566,7 +573,7 @@ void GCN::init(bool quiet, const natural *h_graph_indptr, const natural *h_graph
         for (real &x : s_all) x = x > 0.f ? sqrtf(x) : std::nanf("");  // no usable diagonal: that row / column stays in the remainder
       }
       const size_t row0 = st->row0, n_global = st->n_global;
-      auto make_dist = [N, nnz, d_ip, d_ix, d_gv, row0, n_global, s_all, bt_min_nnz](cudaStream_t stream, gcnb_bittile_plan **out) -> int {
+      auto make_dist = [N, nnz, d_ip, d_ix, d_gv, row0, n_global, s_all, bt_min_nnz, bt_chunk, bt_rb](cudaStream_t stream, gcnb_bittile_plan **out) -> int {
         *out = nullptr;
         if (nnz < bt_min_nnz) return 0;
         std::vector<natural> hp((size_t)N + 1), hi(nnz);
@@ -578,7 +585,7 @@ void GCN::init(bool quiet, const natural *h_graph_indptr, const natural *h_graph
         if (rc) return rc;
         gcnb_bittile_plan *bt = nullptr;
         rc = gcnb_bittile_plan_create(hp.data(), hi.data(), hv.data(), (int64_t)N, (int64_t)n_global, s_all.data() + row0,
-                                      s_all.data(), 0, 0, 0, (gcnb_stream_t)stream, &bt);
+                                      s_all.data(), 0, bt_chunk, bt_rb, (gcnb_stream_t)stream, &bt);
         if (rc) return rc;
         int64_t binfo[8];
         gcnb_bittile_plan_info(bt, binfo);
@@ -619,7 +626,7 @@ void GCN::init(bool quiet, const natural *h_graph_indptr, const natural *h_graph
       int renumber = 1;  // GCNB_RENUMBER=0: never renumber the graph for the bit tiles
       if (const char *e = getenv("GCNB_RENUMBER")) renumber = atoi(e);
       GCNEngineState *stp = st.get();
-      auto make = [N, nnz, d_ip, d_ix, d_gv, min_cover, renumber, stp, bt_min_nnz](cudaStream_t stream, gcnb_bittile_plan **out) -> int {
+      auto make = [N, nnz, d_ip, d_ix, d_gv, min_cover, renumber, stp, bt_min_nnz, bt_chunk, bt_rb](cudaStream_t stream, gcnb_bittile_plan **out) -> int {
         *out = nullptr;
         if (nnz < bt_min_nnz) return 0;  // launch-bound regime: one generic kernel beats pack + MMA + remainder
         std::vector<natural> hp((size_t)N + 1), hi(nnz);
@@ -630,7 +637,7 @@ void GCN::init(bool quiet, const natural *h_graph_indptr, const natural *h_graph
         if (!rc) rc = (int)cudaStreamSynchronize(stream);
         if (rc) return rc;
         gcnb_bittile_plan *bt = nullptr;
-        rc = gcnb_bittile_plan_create(hp.data(), hi.data(), hv.data(), (int64_t)N, (int64_t)N, nullptr, nullptr, 0, 0, 0,
+        rc = gcnb_bittile_plan_create(hp.data(), hi.data(), hv.data(), (int64_t)N, (int64_t)N, nullptr, nullptr, 0, bt_chunk, bt_rb,
                                       (gcnb_stream_t)stream, &bt);
         if (rc) return rc;
         int64_t binfo[8];
@@ -669,8 +676,8 @@ void GCN::init(bool quiet, const natural *h_graph_indptr, const natural *h_graph
               old_of_new[new_of_old[i]] = (natural)i;
             }
             gcnb_bittile_plan *bt2 = nullptr;
-            rc = gcnb_bittile_plan_create(hp2.data(), hi2.data(), nullptr, (int64_t)N, (int64_t)N, s2.data(), s2.data(), 0, 0, 0,
-                                          (gcnb_stream_t)stream, &bt2);
+            rc = gcnb_bittile_plan_create(hp2.data(), hi2.data(), nullptr, (int64_t)N, (int64_t)N, s2.data(), s2.data(), 0, bt_chunk,
+                                          bt_rb, (gcnb_stream_t)stream, &bt2);
             if (rc) {
               gcnb_bittile_plan_destroy(bt);
               return rc;

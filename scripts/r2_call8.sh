@@ -1,0 +1,18 @@
+#!/usr/bin/env bash
+set -u
+mkdir -p gpurun_out
+step() {
+  local t=$1 log=$2
+  shift 2
+  echo "== $* (limit ${t}s) -> gpurun_out/$log"
+  local t0=$(date +%s)
+  timeout -k 5 "$t" "$@" > "gpurun_out/$log" 2>&1
+  echo "   rc=$? ($(( $(date +%s) - t0 ))s)"
+  tail -5 "gpurun_out/$log" | cut -c1-1500
+}
+step 1500 r2h_gpu_tests.log python -m pytest tests -m gpu -q --durations=8
+step 200 r2h_dense_tc_probe.log python scripts/probe_dense_tc.py --out gpurun_out/r2h_probe_dense_tc.jsonl
+step 400 r2h_configs.log python scripts/bench_configs.py
+step 200 r2h_ref_gpu_cora.log python scripts/bench_ref_gpu.py --dataset cora --epochs 100 --reps 5
+step 200 r2h_ref_gpu_citeseer.log python scripts/bench_ref_gpu.py --dataset citeseer --epochs 100 --reps 5
+echo "== done"
