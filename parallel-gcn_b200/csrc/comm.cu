@@ -169,10 +169,24 @@ int gcnb_comm_create(int rank, int world, const void *id_bytes, gcnb_comm **out)
     }
     ncclUniqueId id;
     memcpy(&id, id_bytes, sizeof(id));
-    const int rc = nccl_rc(a.CommInitRank(&c->comm, world, id, rank));
+    int rc = nccl_rc(a.CommInitRank(&c->comm, world, id, rank));
     if (rc) {
       delete c;
       return rc;
+    }
+    // NCCL sets its channels up lazily at the first collective (hundreds of milliseconds): pay for it here, where the
+    // communicator is created, not inside the first model's constructor
+    uint32_t *d_one = nullptr;
+    if (cudaMalloc((void **)&d_one, 4) == cudaSuccess) {
+      cudaMemset(d_one, 0, 4);
+      rc = nccl_rc(a.AllReduce(d_one, d_one, 1, ncclUint32, ncclSum, c->comm, nullptr));
+      cudaStreamSynchronize(nullptr);
+      cudaFree(d_one);
+      if (rc) {
+        nccl().CommDestroy(c->comm);
+        delete c;
+        return rc;
+      }
     }
   }
   *out = c;

@@ -306,21 +306,28 @@ spmm_seg_kernel(const uint4 *__restrict__ segs, const uint32_t *__restrict__ que
   const int q0 = (int)(smid % (uint32_t)n_queues);
   // 1) this SM's own queue (contiguous rows => L1 reuse of gathered neighbour rows)
   drain_queue<VEC, LPR, KT, EXACT>(A, queue_begin, counters, q0, lane, batch);
-  // 2) steal: probe 32 queues at a time, drain the ones that still hold segments
-  for (int base = 1; base < n_queues; base += 32) {
-    const int off = base + lane;
-    bool has = false;
-    int q = 0;
-    if (off < n_queues) {
-      q = (q0 + off) % n_queues;
-      const uint32_t taken = *((volatile uint32_t *)(counters + q));
-      has = taken < __ldg(queue_begin + q + 1) - __ldg(queue_begin + q);
+  // 2) steal: look at ALL other queues at once -- every lane probes up to 8 of them with independent loads (one L2 latency
+  // instead of one per 32 queues: on cora-sized graphs the serial probe loop was most of the kernel) -- then drain the ones
+  // that still hold segments
+  for (int base = 1; base < n_queues; base += 256) {
+    uint32_t mine = 0;  // bit k: queue (q0 + base + 32 k + lane) % n_queues still holds segments
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int off = base + k * 32 + lane;
+      if (off < n_queues) {
+        const int q = (q0 + off) % n_queues;
+        const uint32_t taken = *((volatile uint32_t *)(counters + q));
+        if (taken < __ldg(queue_begin + q + 1) - __ldg(queue_begin + q)) mine |= 1u << k;
+      }
     }
-    uint32_t mask = __ballot_sync(0xffffffffu, has);
-    while (mask) {
-      const int src = __ffs(mask) - 1;
-      mask &= mask - 1;
-      drain_queue<VEC, LPR, KT, EXACT>(A, queue_begin, counters, __shfl_sync(0xffffffffu, q, src), lane, batch);
+#pragma unroll 1
+    for (int k = 0; k < 8 && base + k * 32 < n_queues; k++) {
+      uint32_t mask = __ballot_sync(0xffffffffu, (mine >> k) & 1u);
+      while (mask) {
+        const int src = __ffs(mask) - 1;
+        mask &= mask - 1;
+        drain_queue<VEC, LPR, KT, EXACT>(A, queue_begin, counters, (q0 + base + k * 32 + src) % n_queues, lane, batch);
+      }
     }
   }
   // the last CTA to finish leaves the tickets zeroed for the next launch (no memset per launch: on small graphs a
