@@ -77,6 +77,7 @@ constexpr int kThreads = 256;
 #endif
 constexpr int kBlocksNarrow = GCNB_BLOCKS_NARROW;  // resident CTAs per SM asked of ptxas for the one-tile kernels
 constexpr uint32_t kNoSlot = 0xffffffffu;
+constexpr int64_t kStaticMaxSegs = 32768;  // up to this many segments: one warp per segment, no queues (see spmm_seg_kernel)
 
 template <int VEC>
 struct Vec;
@@ -301,6 +302,19 @@ spmm_seg_kernel(const uint4 *__restrict__ segs, const uint32_t *__restrict__ que
                 float *__restrict__ C, float *__restrict__ scratch, int dim, int ldb, int ldc, int batch) {
   const SegArgs<VEC, LPR, KT, EXACT> A{segs, indices, values, perm, B, C, scratch, dim, ldb, ldc};
   const int lane = threadIdx.x & 31;
+  if (batch == 0) {
+    // small matrices (cora: 13 k entries): warp w runs segment w -- no tickets, no stealing, no counter reset.  The queue
+    // machinery below costs ~15 us per launch whatever the size, nine SpMM launches per epoch.  Same run_segment, same bits.
+    const uint32_t w = (uint32_t)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+    if (w < (uint32_t)n_queues) {  // n_queues carries the segment count in this mode
+      const uint4 sg = __ldg(segs + w);
+      uint32_t idx_n;
+      float val_n;
+      load_chunk(A, sg.y + lane, sg.z, idx_n, val_n);
+      run_segment<VEC, LPR, KT, EXACT>(A, sg, lane, idx_n, val_n, false, make_uint4(0, 0, 0, 0));
+    }
+    return;
+  }
   uint32_t smid;
   asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
   const int q0 = (int)(smid % (uint32_t)n_queues);
@@ -611,6 +625,21 @@ int gcnb::spmm_generic_launch(gcnb_spmm_plan *p, const float *d_values, const ui
     } else {
       blocks_per_sm = it->second;
     }
+  }
+  if (p->n_seg <= kStaticMaxSegs && p->max_cta_per_sm == 0) {
+    // launch-bound regime: one warp per segment, statically
+    const int64_t grid = std::max<int64_t>(1, (p->n_seg + (kThreads / 32) - 1) / (kThreads / 32));
+    fn<<<(unsigned)grid, kThreads, 0, stream>>>(p->d_segs, p->d_queue_begin, p->d_counters, (int)p->n_seg, p->d_indices, d_values,
+                                                d_perm, d_B, d_C, p->d_scratch, dim, ldb, ldc, /*batch = static*/ 0);
+    GCNB_LAUNCH_CHECK();
+    if (p->n_split_rows > 0) {
+      const int64_t total = p->n_split_rows * dim;
+      const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)p->n_queues * 8);
+      spmm_combine_kernel<<<blocks, 256, 0, stream>>>(p->d_split_row, p->d_split_slot, p->d_scratch, d_C, p->n_split_rows, dim,
+                                                      ldc);
+      GCNB_LAUNCH_CHECK();
+    }
+    return 0;
   }
   if (p->max_cta_per_sm > 0) blocks_per_sm = std::min(blocks_per_sm, p->max_cta_per_sm);
   const int64_t warps_needed = p->n_seg;
