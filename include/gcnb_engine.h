@@ -120,6 +120,10 @@ GCNB_API int gcnb_gcn_uses_cuda_graph(const gcnb_gcn *g);
  * out[0] = total ms, out[1] = summed ms of the GraphSum SpMM launches (event pair per launch, if time_graphsum),
  * out[2] = number of GraphSum launches, out[3] = CUDA kernels launched in the region */
 GCNB_API int gcnb_gcn_timed_epochs(gcnb_gcn *g, int n_epochs, int with_eval, int time_graphsum, float out[4]);
+/* row-partitioned models, after a gcnb_gcn_timed_epochs call with time_graphsum: the part of the summed GraphSum time
+ * (out[1]) that passed between the start of a call and the moment every peer's slab had landed -- the slab exchange, and
+ * with window staging the own-slab windows that overlap it */
+GCNB_API double gcnb_gcn_graphsum_exchange_ms(const gcnb_gcn *g);
 
 /* Host-only view of the stateless-Philox bookkeeping behind Variable (src/variable.cu:13-26 keeps a state array; here the
  * consumption history IS the state): reset = Variable::initialize_random(), consume = "an RNG op over n_elements ran"

@@ -176,10 +176,22 @@ int gcnb_comm_create(int rank, int world, const void *id_bytes, gcnb_comm **out)
     }
     // NCCL sets its channels up lazily at the first collective (hundreds of milliseconds): pay for it here, where the
     // communicator is created, not inside the first model's constructor
+    // ... and peer access to the other GPUs of the node (the slab exchange maps every peer's buffers with CUDA IPC;
+    // enabling access lazily inside cudaIpcOpenMemHandle costs tens of milliseconds per peer: 0.3 s at 8 ranks)
+    {
+      int cur = 0, count = 0;
+      if (cudaGetDevice(&cur) == cudaSuccess && cudaGetDeviceCount(&count) == cudaSuccess)
+        for (int d = 0; d < count; d++) {
+          int can = 0;
+          if (d != cur && cudaDeviceCanAccessPeer(&can, cur, d) == cudaSuccess && can) cudaDeviceEnablePeerAccess(d, 0);
+        }
+      cudaGetLastError();  // already enabled / not supported: not an error here
+    }
     uint32_t *d_one = nullptr;
-    if (cudaMalloc((void **)&d_one, 4) == cudaSuccess) {
-      cudaMemset(d_one, 0, 4);
+    if (cudaMalloc((void **)&d_one, 4 * (size_t)world) == cudaSuccess) {
+      cudaMemset(d_one, 0, 4 * (size_t)world);
       rc = nccl_rc(a.AllReduce(d_one, d_one, 1, ncclUint32, ncclSum, c->comm, nullptr));
+      if (!rc) rc = nccl_rc(a.AllGather(d_one + rank, d_one, 1, ncclUint32, c->comm, nullptr));
       cudaStreamSynchronize(nullptr);
       cudaFree(d_one);
       if (rc) {

@@ -668,15 +668,14 @@ struct gcnb_csc {
   int64_t n_rows = 0, n_cols = 0, nnz = 0;
 };
 
-int gcnb_csc_create(const uint32_t *d_indptr, const uint32_t *d_indices, int64_t n_rows, int64_t n_cols,
-                    gcnb_stream_t stream_, gcnb_csc **out) {
-  if (!d_indptr || !out) return GCNB_E_BADARG;
-  cudaStream_t stream = as_stream(stream_);
+static int csc_build(gcnb_csc *c, const uint32_t *d_indptr, const uint32_t *d_indices, int64_t n_rows, int64_t n_cols,
+                     cudaStream_t stream) {
   std::vector<uint32_t> indptr((size_t)n_rows + 1);
   GCNB_CHECK(cudaMemcpyAsync(indptr.data(), d_indptr, indptr.size() * 4, cudaMemcpyDeviceToHost, stream));
   GCNB_CHECK(cudaStreamSynchronize(stream));
   const int64_t nnz = n_rows ? indptr[n_rows] : 0;
-  auto *c = new gcnb_csc();
+  for (int64_t r = 0; r < n_rows; r++)
+    if (indptr[r + 1] < indptr[r]) return GCNB_E_BADARG;  // not a CSR offset array
   c->n_rows = n_rows;
   c->n_cols = n_cols;
   c->nnz = nnz;
@@ -686,12 +685,15 @@ int gcnb_csc_create(const uint32_t *d_indptr, const uint32_t *d_indices, int64_t
   if (dense && nnz) {
     unsigned int *d_flag = nullptr, h_flag = 0;
     GCNB_CHECK(cudaMalloc((void **)&d_flag, 4));
-    GCNB_CHECK(cudaMemsetAsync(d_flag, 0, 4, stream));
-    const int blocks = (int)std::min<int64_t>((nnz + 255) / 256, (int64_t)std::max(1, device_info().sm_count) * 16);
-    dense_check_kernel<<<blocks, 256, 0, stream>>>(d_indices, nnz, (uint32_t)n_cols, d_flag);
-    GCNB_CHECK(cudaMemcpyAsync(&h_flag, d_flag, 4, cudaMemcpyDeviceToHost, stream));
-    GCNB_CHECK(cudaStreamSynchronize(stream));
+    int rc = (int)cudaMemsetAsync(d_flag, 0, 4, stream);
+    if (!rc) {
+      const int blocks = (int)std::min<int64_t>((nnz + 255) / 256, (int64_t)std::max(1, device_info().sm_count) * 16);
+      dense_check_kernel<<<blocks, 256, 0, stream>>>(d_indices, nnz, (uint32_t)n_cols, d_flag);
+      rc = (int)cudaMemcpyAsync(&h_flag, d_flag, 4, cudaMemcpyDeviceToHost, stream);
+    }
+    if (!rc) rc = (int)cudaStreamSynchronize(stream);
     cudaFree(d_flag);
+    if (rc) return rc;
     dense = (h_flag == 0);
   }
   c->is_dense = dense ? 1 : 0;
@@ -701,6 +703,10 @@ int gcnb_csc_create(const uint32_t *d_indptr, const uint32_t *d_indices, int64_t
       GCNB_CHECK(cudaMemcpyAsync(indices.data(), d_indices, (size_t)nnz * 4, cudaMemcpyDeviceToHost, stream));
       GCNB_CHECK(cudaStreamSynchronize(stream));
     }
+    // a column index beyond n_cols (a negative svmlight index cast to uint32, a wrong input_dim) would overrun the
+    // counting sort below: an error, not a heap overflow
+    for (int64_t e = 0; e < nnz; e++)
+      if (indices[e] >= (uint64_t)n_cols) return GCNB_E_BADARG;
     // stable counting sort by column: entries of a column stay in ascending row order => fixed summation order
     std::vector<uint32_t> colptr((size_t)n_cols + 1, 0), rowidx((size_t)nnz), perm((size_t)nnz);
     for (int64_t e = 0; e < nnz; e++) colptr[indices[e] + 1]++;
@@ -721,6 +727,19 @@ int gcnb_csc_create(const uint32_t *d_indptr, const uint32_t *d_indices, int64_t
       GCNB_CHECK(cudaMemcpyAsync(c->d_perm, perm.data(), perm.size() * 4, cudaMemcpyHostToDevice, stream));
     }
     GCNB_CHECK(cudaStreamSynchronize(stream));
+  }
+  return 0;
+}
+
+int gcnb_csc_create(const uint32_t *d_indptr, const uint32_t *d_indices, int64_t n_rows, int64_t n_cols,
+                    gcnb_stream_t stream_, gcnb_csc **out) {
+  if (!d_indptr || !out || n_rows < 0 || n_cols < 0) return GCNB_E_BADARG;
+  *out = nullptr;
+  auto *c = new gcnb_csc();
+  const int rc = csc_build(c, d_indptr, d_indices, n_rows, n_cols, as_stream(stream_));
+  if (rc) {  // nothing leaks on an error path
+    gcnb_csc_destroy(c);
+    return rc;
   }
   *out = c;
   return 0;

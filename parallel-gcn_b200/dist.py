@@ -537,8 +537,8 @@ def bench_main(args, rank, world, local_rank, bench):
     r = g.timed_epochs(args.steps, with_eval=True, time_graphsum=True)  # CUDA events on the engine stream
     torch.cuda.synchronize(); dist.barrier()
     clk = clocks.stop()
-    ms = torch.tensor([r["ms"], wall * 1e3, t_create * 1e3, r["graphsum_ms"] / max(1, r["graphsum_calls"])],
-                      dtype=torch.float64, device=dev)
+    ms = torch.tensor([r["ms"], wall * 1e3, t_create * 1e3, r["graphsum_ms"] / max(1, r["graphsum_calls"]),
+                       r["graphsum_exchange_ms"] / max(1, r["graphsum_calls"])], dtype=torch.float64, device=dev)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     if rank == 0:
         step_ms = float(ms[0]) / args.steps
@@ -576,6 +576,9 @@ def bench_main(args, rank, world, local_rank, bench):
                              "achieved": achieved, "peak": peak * world, "unit": "GB/s", "frac": achieved / (peak * world),
                              "traffic": None, "peak_source": peak_src + " x %d GPUs" % world,
                              "algorithmic_bytes_per_launch": alg, "mean_launch_us": gs_us,
+                             "exchange_us": float(ms[4]) * 1e3, "product_us": gs_us - float(ms[4]) * 1e3,
+                             "phases": "exchange_us = start of the call until every peer's slab has landed (max over ranks; with "
+                                       "window staging the own-slab windows run inside it), product_us = the rest",
                              "graph_staged": r.get("graph_staged")}}
     g.close()
     comm.close()

@@ -68,6 +68,7 @@ _sig("gcnb_gcn_finish_setup", I32, [P])
 _sig("gcnb_gcn_uses_cuda_graph", I32, [P])
 _sig("gcnb_gcn_launches_total", I64, [P])
 _sig("gcnb_gcn_timed_epochs", I32, [P, I32, I32, I32, P])
+_sig("gcnb_gcn_graphsum_exchange_ms", C.c_double, [P])
 _sig("gcnb_host_free", None, [P])
 _sig("gcnb_reorder_communities", I32, [I64, P, P, I32, C.c_uint64, P, P])
 _sig("gcnb_permute_csr", I32, [I64, P, P, P, P, P])
@@ -265,7 +266,8 @@ class GCN:
         out = (F32 * 4)()
         check(lib.gcnb_gcn_timed_epochs(self.h, int(n_epochs), int(with_eval), int(time_graphsum), out))
         return dict(ms=float(out[0]), graphsum_ms=float(out[1]), graphsum_calls=int(out[2]), launches=int(out[3]),
-                    graph_staged=int(lib.gcnb_gcn_graph_staged(self.h)))
+                    graph_staged=int(lib.gcnb_gcn_graph_staged(self.h)),
+                    graphsum_exchange_ms=float(lib.gcnb_gcn_graphsum_exchange_ms(self.h)))
 
     def launches_per_epoch(self):
         return int(lib.gcnb_gcn_launches_per_epoch(self.h))

@@ -22,6 +22,7 @@ struct gcnb_gcn {
   std::unique_ptr<GCN> gcn;
   std::vector<std::vector<unsigned char>> unused;
   std::vector<const unsigned char *> masks;
+  double last_exchange_ms = 0;  // of the last gcnb_gcn_timed_epochs call with GraphSum timing
 };
 
 extern "C" {
@@ -422,8 +423,10 @@ int gcnb_gcn_timed_epochs(gcnb_gcn *g, int n_epochs, int with_eval, int time_gra
   out[1] = (float)ms;
   out[2] = (float)calls;
   out[3] = (float)(g->gcn->launches_total() - l0);
+  g->last_exchange_ms = g->gcn->graphsum_exchange_ms();
   g->gcn->set_time_graphsum(false);
   return 0;
 }
+double gcnb_gcn_graphsum_exchange_ms(const gcnb_gcn *g) { return g ? g->last_exchange_ms : 0.0; }
 
 }  // extern "C"

@@ -284,7 +284,7 @@ struct GCNEngineState {
   bool time_graphsum = false;
   std::vector<cudaEvent_t> gs_events;
   size_t gs_used = 0;
-  double gs_ms_total = 0;
+  double gs_ms_total = 0, gs_exchange_ms_total = 0;  // exchange: start of the call -> the peers' slabs have landed (partitioned)
   size_t gs_calls = 0;
   void graphsum(const real *gv, const real *in, real *out, natural dim) {
     if (!live()) {  // replay: the captured graph holds these launches
@@ -292,8 +292,8 @@ struct GCNEngineState {
       return;
     }
     if (time_graphsum) {
-      if (gs_used + 2 > gs_events.size())
-        for (int i = 0; i < 2; i++) {
+      if (gs_used + 3 > gs_events.size())
+        for (int i = 0; i < 3; i++) {
           cudaEvent_t e;
           CHECK_CUDA_ERROR(cudaEventCreate(&e));
           gs_events.push_back(e);
@@ -316,10 +316,11 @@ struct GCNEngineState {
       // the slab [block x dim] of every rank, concatenated in rank order, IS the global [N x dim] matrix
       GCNB_CALL(gcnb_comm_gather_slabs_f32(comm, in, (int64_t)block * dim, &in, stream));
     }
+    if (time_graphsum) CHECK_CUDA_ERROR(cudaEventRecord(gs_events[gs_used + 1], stream));  // exchange done (own windows too, if overlapped)
     GCNB_CALL(gcnb_spmm_f32(graph_plan, gv, nullptr, in, out, dim, stream));
     if (time_graphsum) {
-      CHECK_CUDA_ERROR(cudaEventRecord(gs_events[gs_used + 1], stream));
-      gs_used += 2;
+      CHECK_CUDA_ERROR(cudaEventRecord(gs_events[gs_used + 2], stream));
+      gs_used += 3;
     }
     launches += graphsum_launches(dim);
   }
@@ -332,10 +333,12 @@ struct GCNEngineState {
     return (size_t)graph_spmm_kernels;
   }
   void collect_graphsum_times() {  // after a stream sync
-    for (size_t i = 0; i + 1 < gs_used; i += 2) {
-      float ms = 0;
-      CHECK_CUDA_ERROR(cudaEventElapsedTime(&ms, gs_events[i], gs_events[i + 1]));
+    for (size_t i = 0; i + 2 < gs_used; i += 3) {
+      float ms = 0, ex = 0;
+      CHECK_CUDA_ERROR(cudaEventElapsedTime(&ms, gs_events[i], gs_events[i + 2]));
+      CHECK_CUDA_ERROR(cudaEventElapsedTime(&ex, gs_events[i], gs_events[i + 1]));
       gs_ms_total += ms;
+      gs_exchange_ms_total += ex;
       gs_calls++;
     }
     gs_used = 0;
@@ -593,7 +596,12 @@ void GCN::init(bool quiet, const natural *h_graph_indptr, const natural *h_graph
         else gcnb_bittile_plan_destroy(bt);
         return 0;
       };
-      st->bt_collective = bt_on && d16;
+      // bit tiles gather from the whole exchanged matrix (pack pass + random row gathers over all n_global rows) and do not
+      // overlap the exchange; the window-staged kernels start on the rank's own slab while the peers' slabs travel.  8 B200:
+      // Reddit-shape (15 MB matrix) 1.16 ms with bit tiles / 1.22 staged; the 1.01 G-entry graph (256 MB matrix) 6.50 / 5.61.
+      // So: bit tiles while the exchanged matrix stays L2-resident (GCNB_BITTILE=1 forces them).
+      const bool bt_small_matrix = (double)st->n_global * 16 * sizeof(real) <= 96e6;
+      st->bt_collective = bt_on && d16 && (bt_small_matrix || (bt_env && atoi(bt_env) != 0));
       if (dist_background) {
         st->setup_pending = true;
         int device = 0;
@@ -827,8 +835,10 @@ void GCN::set_time_graphsum(bool on) {
   st->drop_graphs();
   st->time_graphsum = on;
   st->gs_ms_total = 0;
+  st->gs_exchange_ms_total = 0;
   st->gs_calls = 0;
 }
+double GCN::graphsum_exchange_ms() const { return st->gs_exchange_ms_total; }
 void GCN::graphsum_timing(double *ms_total, size_t *calls) const {
   *ms_total = st->gs_ms_total;
   *calls = st->gs_calls;
