@@ -181,6 +181,22 @@ int gcnb_dataset_load(const char *path, gcnb_dataset **out) {
   take(d->data.split, 6);
   take(d->data.graph_value, 7);
   munmap(map, (size_t)sb.st_size);
+  // a short or crafted file must be an error here, not an out-of-bounds read on the device later: label / split per node,
+  // monotone offsets that end at the entry counts, indices inside their dimensions
+  const size_t n = d->params.num_nodes;
+  auto csr_ok = [](const std::vector<natural> &ip, const std::vector<natural> &ix, size_t dim) {
+    if (ip.empty() || ip.front() != 0 || ip.back() != ix.size()) return false;
+    for (size_t i = 0; i + 1 < ip.size(); i++)
+      if (ip[i + 1] < ip[i]) return false;
+    for (natural c : ix)
+      if (c >= dim) return false;
+    return true;
+  };
+  if (d->data.label.size() != n || d->data.split.size() != n || !csr_ok(d->data.graph.indptr, d->data.graph.indices, n) ||
+      !csr_ok(d->data.feature_index.indptr, d->data.feature_index.indices, d->params.input_dim))
+    return GCNB_E_BADARG;
+  for (integer l : d->data.label)
+    if (l >= (integer)d->params.output_dim) return GCNB_E_BADARG;
   *out = d.release();
   return 0;
 }

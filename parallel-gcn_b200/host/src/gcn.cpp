@@ -964,10 +964,13 @@ void GCN::forward_pass(bool training, natural split, cudaStream_t s) {
       }
     } else {
       const char *e = getenv("GCNB_PROPAGATE");  // tuning probe: 0 keeps the module chain's A_hat (X W0) in evaluation
+      // decided from the problem size and the device's TOTAL memory, not from what other tenants happen to hold: the two
+      // associations round differently, and a near-tie in early stopping must not depend on the neighbours.
+      // The model itself needs ~3 copies of the feature matrix; the propagated copy is the fourth.
       size_t free_b = 0, total_b = 0;
       CHECK_CUDA_ERROR(cudaMemGetInfo(&free_b, &total_b));
       const size_t bytes = (size_t)N * F * sizeof(real);
-      if (!(e && atoi(e) == 0) && free_b > bytes + (size_t(4) << 30)) {
+      if (!(e && atoi(e) == 0) && 6 * bytes + (size_t(8) << 30) < total_b) {
         st->ax = dev_shared_ptr<real>((size_t)N * F);
         GCNB_CALL(gcnb_spmm_ld_f32(st->graph_plan, dev_data.dev_graph_value.get(), nullptr, xvals, F, st->ax.get(), F, (int)F, s));
         st->ax_ready = true;
