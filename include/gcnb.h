@@ -355,6 +355,24 @@ GCNB_API int gcnb_softmax_ce_f32(float *d_logits, float *d_grad, const int32_t *
                                  gcnb_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------
+ * Output head in one kernel (csrc/head.cu): the last layer's Matmul::forward (src/module.cu:274-328) on the narrow
+ * GraphSum result y [n x in_dim], CrossEntropyLoss::forward (:484-541) + get_accuracy (src/gcn.cu:264-289) and, when
+ * training, Matmul::backward (src/module.cu:332-391): d_dy = dz W^T and the partial sums of dW = y^T dz.  Same element
+ * arithmetic as gcnb_matmul_nn_f32 / gcnb_softmax_ce_f32 / gcnb_matmul_nt_f32 (bit-identical logits, loss, dy);
+ * d_logits receives the CE-shifted logits; d_grad (dz, [n x classes]) may be NULL: it then never reaches memory.
+ * d_result as for gcnb_softmax_ce_f32.  gcnb_head_reduce_dw_f32 adds the partial sums in a fixed order (any stream that
+ * is ordered after the head kernel).  in_dim 8 / 16 / 32, classes <= 64 (gcnb_head_supported); d_y / d_dy 16-byte aligned.
+ * d_ws: gcnb_head_workspace() bytes, zero-filled ONCE by the caller before the first launch.
+ * ------------------------------------------------------------------------------------------------- */
+GCNB_API int gcnb_head_supported(int in_dim, int num_classes);
+GCNB_API int64_t gcnb_head_workspace(int64_t n, int in_dim, int num_classes);
+GCNB_API int gcnb_head_f32(const float *d_y, const float *d_w, const int32_t *d_truth, int64_t n, int in_dim, int num_classes,
+                           uint32_t num_samples, int training, float *d_logits, float *d_grad, float *d_dy, float *d_result,
+                           void *d_ws, int64_t ws_bytes, gcnb_stream_t stream);
+GCNB_API int gcnb_head_reduce_dw_f32(const void *d_ws, float *d_dw, int64_t n, int in_dim, int num_classes,
+                                     gcnb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------
  * Adam::step (src/optim.cu:42-95) for up to GCNB_MAX_TENSORS weights in ONE launch, and
  * GCN::get_l2_penalty (src/gcn.cu:230-260) as a fixed-order sum of squares.
  * ------------------------------------------------------------------------------------------------- */

@@ -113,6 +113,10 @@ _sig("gcnb_set_truth", I32, [P, P, P, I64, U32, P])
 _sig("gcnb_graph_values_f32", I32, [P, P, I64, P, P])
 _sig("gcnb_ce_workspace", I64, [I64])
 _sig("gcnb_softmax_ce_f32", I32, [P, P, P, I64, I32, U32, I32, P, P, P])
+_sig("gcnb_head_supported", I32, [I32, I32])
+_sig("gcnb_head_workspace", I64, [I64, I32, I32])
+_sig("gcnb_head_f32", I32, [P, P, P, I64, I32, I32, U32, I32, P, P, P, P, P, I64, P])
+_sig("gcnb_head_reduce_dw_f32", I32, [P, P, I64, I32, I32, P])
 _sig("gcnb_adam_step_f32", I32, [P, F32, F32, F32, F32, F32, P])
 _sig("gcnb_sumsq_workspace", I64, [I64])
 _sig("gcnb_sumsq_f32", I32, [P, I64, P, P, P])
@@ -582,6 +586,14 @@ def zeroed_workspace(nbytes, device):
 def softmax_ce(logits, grad, truth, n, num_classes, num_samples, training, result, ws):
     check(lib.gcnb_softmax_ce_f32(ptr(logits), ptr(grad), ptr(truth), n, num_classes, num_samples, int(training),
                                   ptr(result), ptr(ws), stream()))
+
+
+def head(y, w, truth, n, in_dim, num_classes, num_samples, training, logits, grad, dy, dw, result, ws):
+    """Output head in one kernel (csrc/head.cu): logits = y W, softmax cross-entropy + counts, dy = dz W^T, dW = y^T dz."""
+    check(lib.gcnb_head_f32(ptr(y), ptr(w), ptr(truth), n, in_dim, num_classes, num_samples, int(training), ptr(logits),
+                            ptr(grad), ptr(dy), ptr(result), ptr(ws), ws.numel() * 4, stream()))
+    if training:
+        check(lib.gcnb_head_reduce_dw_f32(ptr(ws), ptr(dw), n, in_dim, num_classes, stream()))
 
 
 def adam_step(tensors, weight_decay, beta1, beta2, eps, step_size):

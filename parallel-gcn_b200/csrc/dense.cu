@@ -185,65 +185,9 @@ __global__ void __launch_bounds__(256) slab_reduce_kernel(const float *__restric
   }
 }
 
-// Both dimensions small (K <= 64, N <= 64: the 16 -> 41 layer, 53 MB of traffic for 0.3 GFLOP): the register-tiled kernel
-// above runs it at a quarter of the HBM roofline (33 us; its 128 x 64 tiles are 64 % / 25 % full and its stores are 16-byte
-// pieces).  Here a CTA walks tiles of 64 rows: the 64 x K block of A' is one contiguous, coalesced read, B' sits in shared
-// memory, thread (row, q) computes the columns q, q + 4, ... with the same ascending-k fmaf chain as sgemm_kernel (same
-// bits), and the 64 x N block of C leaves as one contiguous, coalesced write.
-template <int MODE>
-__global__ void __launch_bounds__(256) rows_narrow_kernel(const float *__restrict__ A, const float *__restrict__ B,
-                                                           float *__restrict__ C, int64_t M, int N, int K) {
-  constexpr int TR = 64;
-  __shared__ float As[TR * 65];  // [row][k], stride K + 1; reused as the output block [row][j], stride N
-  __shared__ float Bs[64 * 64];  // [k][j], stride N
-  const int tid = threadIdx.x, r = tid >> 2, q = tid & 3;
-  for (int e = tid; e < K * N; e += 256) {
-    const int k = e / N, j = e % N;
-    Bs[e] = MODE == MODE_NT ? __ldg(B + (size_t)j * K + k) : __ldg(B + e);
-  }
-  const int64_t n_tiles = (M + TR - 1) / TR;
-  const int ks = K + 1;
-  for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-    const int64_t r0 = t * TR;
-    const int rows = (int)min((int64_t)TR, M - r0);
-    __syncthreads();  // Bs ready / the previous tile's output block has been written out
-    const float *src = A + (size_t)r0 * K;
-    for (int e = tid; e < rows * K; e += 256) As[(e / K) * ks + (e % K)] = __ldg(src + e);
-    __syncthreads();
-    float acc[16];
-#pragma unroll
-    for (int c = 0; c < 16; c++) acc[c] = 0.f;
-    if (r < rows) {
-      for (int k = 0; k < K; k++) {
-        const float a = As[r * ks + k];
-        const float *b = Bs + k * N + q;
-#pragma unroll
-        for (int c = 0; c < 16; c++)
-          if (q + 4 * c < N) acc[c] = fmaf(a, b[4 * c], acc[c]);
-      }
-    }
-    __syncthreads();  // everybody has read As
-    if (r < rows) {
-#pragma unroll
-      for (int c = 0; c < 16; c++)
-        if (q + 4 * c < N) As[r * N + q + 4 * c] = acc[c];
-    }
-    __syncthreads();
-    float *dst = C + (size_t)r0 * N;
-    for (int e = tid; e < rows * N; e += 256) dst[e] = As[e];
-  }
-}
-
 template <int MODE>
 int launch_rows(const float *A, const float *B, float *C, int64_t M, int N, int64_t K, cudaStream_t stream) {
   // M = number of node rows (huge), N small
-  if (K <= 64 && N <= 64 && M >= 4096 && MODE != MODE_TN) {
-    const int64_t tiles = (M + 63) / 64;
-    const int grid = (int)std::min<int64_t>(tiles, (int64_t)std::max(1, device_info().sm_count) * 6);
-    rows_narrow_kernel<MODE><<<grid, 256, 0, stream>>>(A, B, C, M, N, (int)K);
-    GCNB_LAUNCH_CHECK();
-    return 0;
-  }
   if (N <= 16) {
     constexpr int BM = 128, BN = 16, BK = 16, TM = 8, TN = 1;
     dim3 grid((unsigned)((M + BM - 1) / BM), (N + BN - 1) / BN);

@@ -137,6 +137,20 @@ struct GCNEngineState {
   // (A_hat X) W0 with P = A_hat X computed once (first evaluation), instead of A_hat (X W0) -- one GraphSum less per pass
   dev_shared_ptr<real> ax;
   bool ax_tried = false, ax_ready = false, ax_planned = false;
+  // ... and when the input dropout is 0 the TRAINING passes read pristine features too: layer 0 is P W0 in both directions
+  // (dW0 = P^T dz0), no GraphSum at the hidden width at all (hidden 600 of parameters_reddit.txt: three 13 ms calls per step)
+  bool img_is_ax = false;    // the exact-split operand images (x_img / xt_img) were packed from P instead of X
+  bool x_train_ax = false;   // the last training forward went through P
+  // output head (csrc/head.cu): last layer in the (A_hat a) W association with narrow dims -- product, softmax
+  // cross-entropy, counts, dy and the partial sums of dW in one kernel
+  bool head_enabled = true;
+  dev_shared_ptr<natural> head_ws;
+  int64_t head_ws_bytes = 0;
+  bool head_on() const {
+    if (!head_enabled || layers.size() < 2) return false;
+    const GCNLayer &ly = layers.back();
+    return ly.reorder && gcnb_head_supported((int)ly.in_dim, (int)ly.out_dim) != 0;
+  }
   dev_shared_ptr<real> tn_ws;
   int64_t tn_ws_bytes = 0;
   dev_shared_ptr<natural> ce_ws, sumsq_ws;
@@ -773,6 +787,12 @@ void GCN::init(bool quiet, const natural *h_graph_indptr, const natural *h_graph
   st->tn_ws_bytes = tn_need;
   st->tn_ws = dev_shared_ptr<real>((tn_need + 3) / 4);
   st->ce_ws = dev_shared_ptr<natural>((gcnb_ce_workspace(N) + 3) / 4);
+  if (const char *e = getenv("GCNB_HEAD")) st->head_enabled = atoi(e) != 0;  // tuning probe: 0 = separate product / loss kernels
+  if (L >= 2 && gcnb_head_supported((int)st->layers.back().in_dim, (int)st->layers.back().out_dim)) {
+    st->head_ws_bytes = gcnb_head_workspace(N, (int)st->layers.back().in_dim, (int)st->layers.back().out_dim);
+    st->head_ws = dev_shared_ptr<natural>((st->head_ws_bytes + 3) / 4);
+    CHECK_CUDA_ERROR(cudaMemset(st->head_ws.get(), 0, st->head_ws.get_n_elements() * 4));
+  }
   st->sumsq_ws = dev_shared_ptr<natural>((gcnb_sumsq_workspace(weights[0]->size) + 3) / 4);
   CHECK_CUDA_ERROR(cudaMemset(st->ce_ws.get(), 0, st->ce_ws.get_n_elements() * 4));
   CHECK_CUDA_ERROR(cudaMemset(st->sumsq_ws.get(), 0, st->sumsq_ws.get_n_elements() * 4));
@@ -948,7 +968,10 @@ void GCN::forward_pass(bool training, natural split, cudaStream_t s) {
     Variable::rng_consume(input_elems);  // the reference draws even when p == 0
     st->x_train_vals = xvals;
   }
-  if (!training && st->dense_fast && st->allow_reorder && !st->ax_tried && !st->setup_pending) {  // after the staging switch
+  // passes that read pristine features: evaluation, and training when the input dropout is 0 (and no mask is injected)
+  const bool pristine = !training || (params->dropouts.front() == 0.f && !st->ext_masks[0].get());
+  const bool ax_candidate = st->dense_fast || (!st->dist && st->feat_dense && st->x_img.get());
+  if (pristine && ax_candidate && st->allow_reorder && !st->ax_tried && !st->setup_pending) {  // after the staging switch
     st->ax_tried = true;
     if (st->dist) {
       if (st->ax_planned) {  // collective: every rank takes this branch (ax_planned depends on global sizes only)
@@ -972,18 +995,33 @@ void GCN::forward_pass(bool training, natural split, cudaStream_t s) {
       const size_t bytes = (size_t)N * F * sizeof(real);
       if (!(e && atoi(e) == 0) && 6 * bytes + (size_t(8) << 30) < total_b) {
         st->ax = dev_shared_ptr<real>((size_t)N * F);
-        GCNB_CALL(gcnb_spmm_ld_f32(st->graph_plan, dev_data.dev_graph_value.get(), nullptr, xvals, F, st->ax.get(), F, (int)F, s));
+        GCNB_CALL(gcnb_spmm_ld_f32(st->graph_plan, dev_data.dev_graph_value.get(), nullptr, dev_data.dev_feature_value.get(), F,
+                                   st->ax.get(), F, (int)F, s));
+        if (!st->dense_fast) {  // wide first layer: the operand images now hold P (X itself is only needed with a dropped input)
+          GCNB_CALL(gcnb_dense_tc_pack_x(st->ax.get(), st->x_img.get(), (int64_t)N, (int)F, s));
+          if (st->xt_img.get()) GCNB_CALL(gcnb_dense_tc_pack_xt(st->ax.get(), st->xt_img.get(), (int64_t)N, (int)F, s));
+          st->img_is_ax = true;
+        }
         st->ax_ready = true;
       }
     }
   }
   const bool live = st->live();  // false in a graph replay: the captured graph holds every launch below
-  if (!training && st->ax_ready && st->allow_reorder) {
+  const bool use_ax = pristine && st->ax_ready && st->allow_reorder;
+  if (training) st->x_train_ax = use_ax;
+  if (use_ax) {
     GCNLayer &l0 = st->layers[0];
-    if (live)
-      GCNB_CALL(gcnb_dense_feat_fwd_f32(st->ax.get(), nullptr, 0.f, weights[0]->dev_data.get(), l0.z->dev_data.get(), N,
-                                        (int)F, (int)l0.out_dim, s));
-    st->launches += 1;
+    if (st->dense_fast) {
+      if (live)
+        GCNB_CALL(gcnb_dense_feat_fwd_f32(st->ax.get(), nullptr, 0.f, weights[0]->dev_data.get(), l0.z->dev_data.get(), N,
+                                          (int)F, (int)l0.out_dim, s));
+      st->launches += 1;
+    } else {
+      if (live)
+        GCNB_CALL(gcnb_dense_tc_fwd_f32(st->x_img.get(), weights[0]->dev_data.get(), l0.z->dev_data.get(), N, (int)F,
+                                        (int)l0.out_dim, st->x_img_ws.get(), (int64_t)st->x_img_ws.get_n_elements() * 4, s));
+      st->launches += 2;
+    }
   } else {
     GCNLayer &l0 = st->layers[0];
     if (st->dense_fast) {
@@ -991,7 +1029,7 @@ void GCN::forward_pass(bool training, natural split, cudaStream_t s) {
         GCNB_CALL(gcnb_dense_feat_fwd_f32(xvals, xbits, xp, weights[0]->dev_data.get(), l0.pre->dev_data.get(), N, (int)F,
                                           (int)l0.out_dim, s));
       st->launches += 1;
-    } else if (st->feat_dense && st->x_img.get() && xvals == dev_data.dev_feature_value.get()) {
+    } else if (st->feat_dense && st->x_img.get() && !st->img_is_ax && xvals == dev_data.dev_feature_value.get()) {
       // pristine features (no input dropout, or evaluation) through the exact-split tcgen05 GEMM
       if (live)
         GCNB_CALL(gcnb_dense_tc_fwd_f32(st->x_img.get(), weights[0]->dev_data.get(), l0.pre->dev_data.get(), N, (int)F,
@@ -1008,13 +1046,14 @@ void GCN::forward_pass(bool training, natural split, cudaStream_t s) {
     }
     st->graphsum(dev_data.dev_graph_value.get(), l0.pre->dev_data.get(), l0.z->dev_data.get(), l0.out_dim);
   }
+  const bool head = st->head_on();
   for (natural l = 0; l < L; l++) {
     GCNLayer &ly = st->layers[l];
     if (l > 0) {
       const real *a = st->layers[l - 1].z->dev_data.get();
       if (ly.reorder) {
         st->graphsum(dev_data.dev_graph_value.get(), a, ly.pre->dev_data.get(), ly.in_dim);
-        if (live)
+        if (live && !(head && l + 1 == L))  // (the head kernel below multiplies by W itself)
           GCNB_CALL(gcnb_matmul_nn_f32(ly.pre->dev_data.get(), weights[l]->dev_data.get(), ly.z->dev_data.get(), N,
                                        ly.in_dim, ly.out_dim, s));
       } else {
@@ -1022,7 +1061,7 @@ void GCN::forward_pass(bool training, natural split, cudaStream_t s) {
           GCNB_CALL(gcnb_matmul_nn_f32(a, weights[l]->dev_data.get(), ly.pre->dev_data.get(), N, ly.in_dim, ly.out_dim, s));
         st->graphsum(dev_data.dev_graph_value.get(), ly.pre->dev_data.get(), ly.z->dev_data.get(), ly.out_dim);
       }
-      st->launches += 1;
+      if (!(head && l + 1 == L)) st->launches += 1;
     }
     if (l + 1 < L) {
       const real p = params->dropouts[l + 1];
@@ -1038,9 +1077,27 @@ void GCN::forward_pass(bool training, natural split, cudaStream_t s) {
     }
   }
   // ---- loss + accuracy (one kernel) and the L2 term of the decayed weights
-  if (live)
+  if (head) {
+    // logits = y W, loss, counts and -- training -- dy and the partial sums of dW, one kernel; the fixed-order sum of the
+    // partials only feeds Adam: side stream, joined by the backward pass
+    GCNLayer &ly = st->layers.back();
+    if (live) {
+      GCNB_CALL(gcnb_head_f32(ly.pre->dev_data.get(), weights[L - 1]->dev_data.get(), dev_truth.get(), N, (int)ly.in_dim,
+                              (int)ly.out_dim, st->cur_num_samples, training, output->dev_data.get(), nullptr,
+                              ly.pre->dev_grad.get(), st->dev_result.get(), st->head_ws.get(), st->head_ws_bytes, s));
+      if (training) {
+        CHECK_CUDA_ERROR(cudaEventRecord(st->ev_fork, s));
+        CHECK_CUDA_ERROR(cudaStreamWaitEvent(st->side, st->ev_fork, 0));
+        GCNB_CALL(gcnb_head_reduce_dw_f32(st->head_ws.get(), weights[L - 1]->dev_grad.get(), N, (int)ly.in_dim, (int)ly.out_dim,
+                                          st->side));
+        st->side_pending = true;
+      }
+    }
+    if (training) st->launches++;
+  } else if (live) {
     GCNB_CALL(gcnb_softmax_ce_f32(output->dev_data.get(), output->dev_grad.get(), dev_truth.get(), N, params->output_dim,
                                   st->cur_num_samples, training, st->dev_result.get(), st->ce_ws.get(), s));
+  }
   if (st->dist) {  // loss sum (float) and wrong / labelled counts (uint32 bit patterns) over all row blocks
     GCNB_CALL(gcnb_comm_group_start(st->comm));
     GCNB_CALL(gcnb_comm_all_reduce_sum(st->comm, st->dev_result.get(), 1, 0, s));
@@ -1070,7 +1127,11 @@ void GCN::backward_pass(cudaStream_t s) {
     GCNLayer &prev = st->layers[l - 1];
     // the weight gradient only feeds Adam: it runs on the side stream (the reference uses a second backward stream
     // for the same product, src/module.cu:456-472) while the main stream carries on with dA and the next GraphSum
-    if (ly.reorder) {
+    const bool by_head = l + 1 == L && st->head_on();
+    if (by_head) {
+      // dy and dW were produced by the head kernel of the forward pass (csrc/head.cu): da = A_hat dy is all that is left
+      st->graphsum(gv, ly.pre->dev_grad.get(), prev.z->dev_grad.get(), ly.in_dim);
+    } else if (ly.reorder) {
       // z = y W, y = A_hat a  =>  dW = y^T g ; dy = g W^T ; da = A_hat dy   (A_hat symmetric)
       CHECK_CUDA_ERROR(cudaEventRecord(st->ev_fork, s));
       CHECK_CUDA_ERROR(cudaStreamWaitEvent(st->side, st->ev_fork, 0));
@@ -1091,11 +1152,17 @@ void GCN::backward_pass(cudaStream_t s) {
     st->side_pending = true;
     GCNB_CALL(gcnb_relu_dropout_bwd_f32(prev.z->dev_grad.get(), prev.mask.get(), (size_t)N * prev.out_dim,
                                         params->dropouts[l], s));
-    st->launches += 2 + 1 + 1;  // split-K weight gradient (2 kernels), dA product, mask kernel
+    st->launches += by_head ? 1 : 2 + 1 + 1;  // split-K weight gradient (2 kernels), dA product, mask kernel
     g = prev.z->dev_grad.get();
   }
   GCNLayer &l0 = st->layers[0];
-  st->graphsum(gv, g, l0.pre->dev_grad.get(), l0.out_dim);
+  // layer 0 through the propagated features P = A_hat X (input dropout 0): z0 = P W0, so dW0 = P^T dz0 -- no GraphSum
+  const real *g0 = g;
+  if (!st->x_train_ax) {
+    st->graphsum(gv, g, l0.pre->dev_grad.get(), l0.out_dim);
+    g0 = l0.pre->dev_grad.get();
+  }
+  const real *x_tn = st->x_train_ax ? st->ax.get() : st->x_train_vals;
   auto join_side = [&]() {
     if (!st->side_pending) return;
     CHECK_CUDA_ERROR(cudaEventRecord(st->ev_join, st->side));
@@ -1104,21 +1171,22 @@ void GCN::backward_pass(cudaStream_t s) {
   };
   if (!st->dense_fast && st->feat_dense) join_side();  // that branch re-uses the split-K workspace
   if (st->dense_fast) {
-    GCNB_CALL(gcnb_dense_feat_tn_f32(st->x_train_vals, st->x_train_bits, st->x_train_p, l0.pre->dev_grad.get(),
+    GCNB_CALL(gcnb_dense_feat_tn_f32(x_tn, st->x_train_ax ? nullptr : st->x_train_bits, st->x_train_ax ? 0.f : st->x_train_p, g0,
                                      weights[0]->dev_grad.get(), N, (int)F, (int)l0.out_dim, st->dense_tn_ws.get(),
                                      st->dense_tn_ws_bytes, s));
     st->launches += 2;
-  } else if (st->feat_dense && st->xt_img.get() && st->x_train_vals == dev_data.dev_feature_value.get()) {
-    // pristine features => X^T dH through the exact-split tcgen05 GEMM (pack, GEMM, slice reduce)
-    GCNB_CALL(gcnb_dense_tc_tn_f32(st->xt_img.get(), l0.pre->dev_grad.get(), weights[0]->dev_grad.get(), (int64_t)N, (int)F,
+  } else if (st->feat_dense && st->xt_img.get() &&
+             (st->x_train_ax ? st->img_is_ax : (!st->img_is_ax && st->x_train_vals == dev_data.dev_feature_value.get()))) {
+    // pristine features => X^T dH (or P^T dz0) through the exact-split tcgen05 GEMM (pack, GEMM, slice reduce)
+    GCNB_CALL(gcnb_dense_tc_tn_f32(st->xt_img.get(), g0, weights[0]->dev_grad.get(), (int64_t)N, (int)F,
                                    (int)l0.out_dim, st->xt_ws.get(), (int64_t)st->xt_ws.get_n_elements() * 4, s));
     st->launches += 3;
   } else if (st->feat_dense) {
-    GCNB_CALL(gcnb_matmul_tn_f32(st->x_train_vals, l0.pre->dev_grad.get(), weights[0]->dev_grad.get(), N, F, l0.out_dim,
+    GCNB_CALL(gcnb_matmul_tn_f32(x_tn, g0, weights[0]->dev_grad.get(), N, F, l0.out_dim,
                                  st->tn_ws.get(), st->tn_ws_bytes, s));
     st->launches += 2;
   } else {
-    GCNB_CALL(gcnb_spmm_f32(st->feat_csc_plan, st->x_train_vals, st->feat_perm, l0.pre->dev_grad.get(),
+    GCNB_CALL(gcnb_spmm_f32(st->feat_csc_plan, st->x_train_vals, st->feat_perm, g0,
                             weights[0]->dev_grad.get(), l0.out_dim, s));
     st->launches += st->feat_csc_kernels;
   }

@@ -420,6 +420,69 @@ def test_softmax_ce(O, gcnb, dev, n, C, training):
         assert_close(to_np(d_g), gw, rtol=1e-5, atol=1e-9, what="ce grad")
 
 
+@pytest.mark.parametrize("n,K,C,training,with_grad", [(5000, 16, 41, 1, 0), (5000, 16, 41, 0, 0), (20011, 16, 41, 1, 1), (2708, 16, 64, 1, 0),
+                                                     (1000, 8, 9, 1, 1), (333, 32, 40, 1, 0), (31, 16, 17, 1, 1), (1, 16, 41, 1, 0),
+                                                     (4096, 16, 20, 0, 0), (70000, 16, 41, 1, 0)])
+def test_output_head_in_one_kernel(O, gcnb, dev, n, K, C, training, with_grad):
+    """csrc/head.cu against the oracle's module chain: Matmul forward, cross-entropy + counts, Matmul backward."""
+    import torch
+    rng = np.random.default_rng(n * 7 + K + C)
+    y = rng.standard_normal((n, K)).astype(f32)
+    w = (rng.standard_normal((K, C)) * 0.7).astype(f32)
+    truth = rng.integers(0, C, n).astype(i32)
+    truth[rng.random(n) < 0.35] = -1
+    ns = int((truth >= 0).sum()) + 3
+    z = np.empty((n, C), f32)
+    O.lib.orc_matmul(n, K, C, O._p(y), O._p(w), O._p(z))
+    gw = np.zeros((n, C), f32)
+    cnt = np.zeros(1, np.int64)
+    loss_want = O.lib.orc_cross_entropy(n, C, O._p(z), O._p(truth), O._p(gw) if training else None, ns, training, O._p(cnt))
+    wrong_want = O.lib.orc_wrong_count(n, C, O._p(z), O._p(truth), None)
+    dy_want, dw_want = np.empty((n, K), f32), np.empty((K, C), f32)
+    if training:
+        O.lib.orc_matmul_bwd(n, K, C, O._p(y), O._p(w), O._p(gw), O._p(dy_want), O._p(dw_want))
+    assert gcnb.lib.gcnb_head_supported(K, C) == 1
+    d_y, d_w, d_t = to_dev(y, dev), to_dev(w, dev), to_dev(truth, dev)
+    d_z = torch.full((n, C), float("nan"), device=dev)
+    d_g = torch.full((n, C), float("nan"), device=dev) if with_grad else None
+    d_dy = torch.full((n, K), float("nan"), device=dev)
+    d_dw = torch.full((K, C), float("nan"), device=dev)
+    res = torch.zeros(4, device=dev)
+    ws = gcnb.zeroed_workspace(gcnb.lib.gcnb_head_workspace(n, K, C), dev)
+    outs = []
+    for _ in range(2):  # second launch: self-resetting ticket, bit-repeatable sums
+        gcnb.head(d_y, d_w, d_t, n, K, C, ns, training, d_z, d_g, d_dy, d_dw, res, ws)
+        torch.cuda.synchronize()
+        outs.append((to_np(res).copy(), to_np(d_dw).copy()))
+    r = outs[0][0]
+    assert (outs[0][0].view(u32) == outs[1][0].view(u32)).all()
+    assert_close(r[0], loss_want, rtol=1e-5, what="loss sum")
+    assert int(r.view(u32)[1]) == wrong_want and int(r.view(u32)[2]) == int(cnt[0])
+    assert_close(to_np(d_z), z, rtol=1e-5, atol=1e-5, what="shifted logits")
+    assert (to_np(d_z).argmax(1) == z.argmax(1)).mean() > 0.999
+    if training:
+        assert (outs[0][1].view(u32) == outs[1][1].view(u32)).all(), "weight gradient must be deterministic"
+        assert_close(to_np(d_dy), dy_want, what="head dy")
+        assert_close(to_np(d_dw), dw_want, rtol=2e-5, atol=2e-6 * np.abs(dw_want).max(), what="head dW")
+        if with_grad:
+            assert_close(to_np(d_g), gw, what="head dz")
+    # the unfused kernels compute the same elements with the same arithmetic
+    z2 = torch.empty((n, C), device=dev)
+    gcnb.matmul_nn(d_y, d_w, z2, n, K, C)
+    g2 = torch.empty((n, C), device=dev)
+    res2 = torch.zeros(4, device=dev)
+    ws2 = gcnb.zeroed_workspace(gcnb.lib.gcnb_ce_workspace(n), dev)
+    gcnb.softmax_ce(z2, g2, d_t, n, C, ns, training, res2, ws2)
+    assert torch.equal(z2, d_z), "fused and unfused logits differ"
+    if training:
+        dy2 = torch.empty((n, K), device=dev)
+        gcnb.matmul_nt(g2, d_w, dy2, n, K, C)
+        lab = torch.from_numpy(truth >= 0).to(dev)
+        assert torch.equal(dy2[lab], d_dy[lab]), "fused and unfused dy differ"
+        if with_grad:
+            assert torch.equal(g2, d_g)
+
+
 def test_adam_and_sumsq(O, gcnb, dev):
     import torch
     rng = np.random.default_rng(5)
