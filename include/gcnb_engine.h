@@ -125,6 +125,31 @@ GCNB_API int gcnb_gcn_timed_epochs(gcnb_gcn *g, int n_epochs, int with_eval, int
  * with window staging the own-slab windows that overlap it */
 GCNB_API double gcnb_gcn_graphsum_exchange_ms(const gcnb_gcn *g);
 
+/* ---- tuning sweep as a throughput workload (test/tuning_accuracy.cpp:56-196, test/tuning_cuda.cpp of the reference) ----
+ * The reference tunes by constructing one model after the other (20 seeds x every parameter combination, 1000 epochs with
+ * early stopping each): every constructor uploads the dataset again and a cora-sized epoch leaves most of the GPU idle.
+ * gcnb_sweep_run uploads the dataset ONCE and runs the trials on `workers` host threads, each model on its own streams with
+ * its own Philox context and (small datasets) its own CUDA-graph replays, so the epochs of several models overlap on the
+ * device.  A trial is exactly `CudaParams::SEED = seed; GCN gcn{params, adam_params, data}; gcn.run();` in the quiet build:
+ * results do not depend on `workers` or on which trials run side by side (bit-identical to running them one by one).
+ * workers <= 0: min(8, hardware threads).  wall_s: wall-clock seconds of the whole sweep (upload included). */
+typedef struct {
+  int32_t n_layers;          /* 1..8 */
+  uint32_t hidden_dims[7];   /* n_layers - 1 entries used */
+  float dropouts[8];         /* n_layers entries used */
+  uint32_t epochs, early_stopping;
+  float learning_rate, weight_decay; /* beta1 0.9, beta2 0.999, eps 1e-8 as the reference's AdamParams defaults */
+  uint32_t seed;
+} gcnb_sweep_trial;
+typedef struct {
+  float last_val_accuracy, last_val_loss, last_train_loss;
+  float avg_epoch_ms;  /* the reference's TMR_TRAIN average: wall time of the trial / (epochs run + 1) */
+  float total_s;
+  uint32_t epochs_run;
+} gcnb_sweep_result;
+GCNB_API int gcnb_sweep_run(const gcnb_dataset *d, const gcnb_sweep_trial *trials, int64_t n_trials, int workers,
+                            gcnb_sweep_result *results, double *wall_s);
+
 /* Host-only view of the stateless-Philox bookkeeping behind Variable (src/variable.cu:13-26 keeps a state array; here the
  * consumption history IS the state): reset = Variable::initialize_random(), consume = "an RNG op over n_elements ran"
  * (64-bit: GLOBAL element counts of row-partitioned models), descriptor = what the next RNG kernel receives.  No CUDA. */

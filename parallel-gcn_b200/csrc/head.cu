@@ -16,6 +16,7 @@
 // The arithmetic of every element is the one of sgemm_kernel (ascending-k fmaf chains, dense.cu) and of
 // softmax_ce_rows_kernel (loss.cu), so the fused and the unfused paths agree bit for bit in logits, loss and dy.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -34,8 +35,8 @@ __host__ __device__ inline int head_warp_floats(int in, int C) {
   return tile > fin ? tile : fin;
 }
 
-template <int IN>
-__global__ void __launch_bounds__(kT, 2)
+template <int IN, int CTAS>
+__global__ void __launch_bounds__(kT, CTAS)
 head_kernel(const float *__restrict__ Y, const float *__restrict__ W, const int32_t *__restrict__ truth, int64_t n, int C,
             uint32_t num_samples, int training, int aligned16, uint32_t div_magic, float *__restrict__ logits,
             float *__restrict__ grad, float *__restrict__ dY, float *__restrict__ dw_part, float *__restrict__ result,
@@ -69,46 +70,68 @@ head_kernel(const float *__restrict__ Y, const float *__restrict__ W, const int3
   float loss = 0.f;
   uint32_t wrong = 0, labelled = 0;
 
-  float4 yn[IN4];  // next tile's row of this lane, in flight while the current tile is processed
-  int tn = -1;
-  auto fetch = [&](int64_t tile) {
-    const int64_t row = tile * 32 + lane;
-    if (row < n) {
-      const float4 *src = reinterpret_cast<const float4 *>(Y + (size_t)row * IN);
-#pragma unroll
-      for (int c = 0; c < IN4; c++) yn[c] = __ldg(src + c);
-      tn = __ldg(truth + row);
-    } else {
-#pragma unroll
-      for (int c = 0; c < IN4; c++) yn[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-      tn = -1;
-    }
-  };
-  if (gw < ntiles) fetch(gw);
-
   for (int64_t tile = gw; tile < ntiles; tile += nw) {
-    float y[IN];
-#pragma unroll
-    for (int c = 0; c < IN4; c++) {
-      y[4 * c] = yn[c].x;
-      y[4 * c + 1] = yn[c].y;
-      y[4 * c + 2] = yn[c].z;
-      y[4 * c + 3] = yn[c].w;
-    }
-    const int t = tn;
     const int64_t r0 = tile * 32;
     const int rows = (int)min((int64_t)32, n - r0);
     const int total = rows * C;
-    if (training) {
-      float4 *dst = reinterpret_cast<float4 *>(yt + lane * IN);
+    float y[IN];
+    int t = -1;
+    {
+      float4 yn[IN4];
+      if (lane < rows) {
+        const float4 *src = reinterpret_cast<const float4 *>(Y + (size_t)(r0 + lane) * IN);
 #pragma unroll
-      for (int c = 0; c < IN4; c++) dst[c] = yn[c];
+        for (int c = 0; c < IN4; c++) yn[c] = __ldg(src + c);
+        t = __ldg(truth + r0 + lane);
+      } else {
+#pragma unroll
+        for (int c = 0; c < IN4; c++) yn[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      if (training) {
+        float4 *dst = reinterpret_cast<float4 *>(yt + lane * IN);
+#pragma unroll
+        for (int c = 0; c < IN4; c++) dst[c] = yn[c];
+      }
+#pragma unroll
+      for (int c = 0; c < IN4; c++) {
+        y[4 * c] = yn[c].x;
+        y[4 * c + 1] = yn[c].y;
+        y[4 * c + 2] = yn[c].z;
+        y[4 * c + 3] = yn[c].w;
+      }
     }
-    if (tile + nw < ntiles) fetch(tile + nw);
 
-    // ---- z = y W: four columns at a time, ascending-k fmaf chains (the chains of sgemm_kernel)
+    // ---- z = y W: ascending-k fmaf chains (the chains of sgemm_kernel)
     float *zr = zt + lane * CP;
-    for (int j4 = 0; j4 < CW; j4 += 4) {
+    float mx = -INFINITY;  // row maximum, gathered on the way
+    int j4 = 0;
+    for (; j4 + 8 <= CW; j4 += 8) {  // eight columns at a time: eight independent chains
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < IN; k++) {
+        const float4 w = *reinterpret_cast<const float4 *>(Ws + k * CW + j4);
+        const float4 v = *reinterpret_cast<const float4 *>(Ws + k * CW + j4 + 4);
+        a.x = fmaf(y[k], w.x, a.x);
+        a.y = fmaf(y[k], w.y, a.y);
+        a.z = fmaf(y[k], w.z, a.z);
+        a.w = fmaf(y[k], w.w, a.w);
+        b.x = fmaf(y[k], v.x, b.x);
+        b.y = fmaf(y[k], v.y, b.y);
+        b.z = fmaf(y[k], v.z, b.z);
+        b.w = fmaf(y[k], v.w, b.w);
+      }
+      zr[j4] = a.x;
+      zr[j4 + 1] = a.y;
+      zr[j4 + 2] = a.z;
+      zr[j4 + 3] = a.w;
+      mx = fmaxf(fmaxf(fmaxf(mx, a.x), fmaxf(a.y, a.z)), a.w);
+      zr[j4 + 4] = b.x;
+      mx = fmaxf(mx, b.x);
+      if (j4 + 5 < C) zr[j4 + 5] = b.y, mx = fmaxf(mx, b.y);
+      if (j4 + 6 < C) zr[j4 + 6] = b.z, mx = fmaxf(mx, b.z);
+      if (j4 + 7 < C) zr[j4 + 7] = b.w, mx = fmaxf(mx, b.w);
+    }
+    if (j4 < CW) {
       float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int k = 0; k < IN; k++) {
@@ -119,15 +142,15 @@ head_kernel(const float *__restrict__ Y, const float *__restrict__ W, const int3
         a.w = fmaf(y[k], w.w, a.w);
       }
       zr[j4] = a.x;
-      if (j4 + 1 < C) zr[j4 + 1] = a.y;
-      if (j4 + 2 < C) zr[j4 + 2] = a.z;
-      if (j4 + 3 < C) zr[j4 + 3] = a.w;
+      mx = fmaxf(mx, a.x);
+      if (j4 + 1 < C) zr[j4 + 1] = a.y, mx = fmaxf(mx, a.y);
+      if (j4 + 2 < C) zr[j4 + 2] = a.z, mx = fmaxf(mx, a.z);
+      if (j4 + 3 < C) zr[j4 + 3] = a.w, mx = fmaxf(mx, a.w);
     }
     // ---- shift by the row maximum (labelled rows; written back: API-visible side effect of the reference)
     float xt = 0.f;
     if (t >= 0) {
-      float mx = -INFINITY;
-      for (int j = 0; j < C; j++) mx = fmaxf(mx, zr[j]);
+#pragma unroll 4
       for (int j = 0; j < C; j++) zr[j] -= mx;
       xt = zr[t];
     }
@@ -151,8 +174,9 @@ head_kernel(const float *__restrict__ Y, const float *__restrict__ W, const int3
     }
     __syncwarp();
     // ---- exponentials, loss, counts, gradient: in place (the arithmetic of softmax_ce_rows_kernel)
+    float sum = 0.f;
     if (t >= 0) {
-      float sum = 0.f;
+#pragma unroll 4
       for (int j = 0; j < C; j++) {
         const float e = expf(zr[j]);
         zr[j] = e;
@@ -161,22 +185,21 @@ head_kernel(const float *__restrict__ Y, const float *__restrict__ W, const int3
       loss += logf(sum) - xt;
       labelled++;
       if (xt < 0.f) wrong++;  // src/gcn.cu:273-276
-      if (training) {
-        const float inv = 1.0f / sum;
-        for (int j = 0; j < C; j++) zr[j] = (zr[j] * inv) * inv_ns;
-        zr[t] = (float)((double)zr[t] - 1.0 / (double)num_samples);  // double literal in the reference (src/module.cu:517)
-      }
     }
     if (training) {
       const unsigned lab = __ballot_sync(0xffffffffu, t >= 0);
-      // ---- dy = dz W^T (ascending-j fmaf chains); rows without a label have a zero gradient
+      // ---- dz in place and dy = dz W^T (ascending-j fmaf chains) in the same walk; rows without a label: zero gradient
       if (lane < rows) {
         float d[IN];
 #pragma unroll
         for (int k = 0; k < IN; k++) d[k] = 0.f;
         if (t >= 0) {
+          const float inv = 1.0f / sum;
+#pragma unroll 2
           for (int j = 0; j < C; j++) {
-            const float g = zr[j];
+            float g = (zr[j] * inv) * inv_ns;
+            if (j == t) g = (float)((double)g - 1.0 / (double)num_samples);  // double literal in the reference (src/module.cu:517)
+            zr[j] = g;
             const float4 *w4 = reinterpret_cast<const float4 *>(Wt + j * IN);
 #pragma unroll
             for (int c = 0; c < IN4; c++) {
@@ -324,10 +347,19 @@ __global__ void __launch_bounds__(256) head_reduce_kernel(const float *__restric
   }
 }
 
+// CTAs per SM: the kernel is bound by shared memory -> register bandwidth (every broadcast LDS.128 of W delivers 512 bytes
+// for four FMAs per lane), not by latency: a third CTA per SM (85 registers, a few spills) measured 83 us against 73 with two
+int head_ctas_per_sm() {
+  static const int v = [] {
+    const char *e = getenv("GCNB_HEAD_CTAS");  // tuning probe
+    return e && atoi(e) == 3 ? 3 : 2;
+  }();
+  return v;
+}
 int head_blocks(int64_t n) {
   const int sm = std::max(1, device_info().sm_count);
   const int64_t want = ((n + 31) / 32 + kWarps - 1) / kWarps;
-  return (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(want, (int64_t)sm * 2), kMaxBlocks));
+  return (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(want, (int64_t)sm * head_ctas_per_sm()), kMaxBlocks));
 }
 
 size_t head_smem_bytes(int in, int C) {
@@ -335,18 +367,18 @@ size_t head_smem_bytes(int in, int C) {
   return ((size_t)2 * in * CW + (size_t)kWarps * head_warp_floats(in, C)) * sizeof(float);
 }
 
-template <int IN>
+template <int IN, int CTAS>
 int launch_head(const float *Y, const float *W, const int32_t *truth, int64_t n, int C, uint32_t num_samples, int training,
                 float *logits, float *grad, float *dY, float *dw_part, float *result, float *part_loss, uint32_t *part_cnt,
                 unsigned int *ticket, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    GCNB_CHECK(cudaFuncSetAttribute(head_kernel<IN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)head_smem_bytes(IN, kMaxC)));
+    GCNB_CHECK(cudaFuncSetAttribute(head_kernel<IN, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)head_smem_bytes(IN, kMaxC)));
     attr_set = true;
   }
   const int aligned16 = (((uintptr_t)logits | (uintptr_t)grad) % 16) == 0;
   const uint32_t magic = (1u << 17) / (uint32_t)C + 1u;  // i / C == (i * magic) >> 17 for i < 2048, C <= 64
-  head_kernel<IN><<<head_blocks(n), kT, head_smem_bytes(IN, C), st>>>(Y, W, truth, n, C, num_samples, training, aligned16, magic,
+  head_kernel<IN, CTAS><<<head_blocks(n), kT, head_smem_bytes(IN, C), st>>>(Y, W, truth, n, C, num_samples, training, aligned16, magic,
                                                                       logits, grad, dY, dw_part, result, part_loss, part_cnt, ticket);
   GCNB_LAUNCH_CHECK();
   return 0;
@@ -377,9 +409,12 @@ int gcnb_head_f32(const float *d_y, const float *d_w, const int32_t *d_truth, in
   uint32_t *part_cnt = (uint32_t *)d_ws + 4 + kMaxBlocks;
   float *dw_part = (float *)d_ws + 4 + 3 * kMaxBlocks;
   cudaStream_t st = as_stream(s);
-#define HEAD(IN_) \
-  return launch_head<IN_>(d_y, d_w, d_truth, n, num_classes, num_samples, training, d_logits, d_grad, d_dy, dw_part, d_result, \
-                          part_loss, part_cnt, ticket, st)
+#define HEAD(IN_)                                                                                                              \
+  return head_ctas_per_sm() == 3                                                                                               \
+             ? launch_head<IN_, 3>(d_y, d_w, d_truth, n, num_classes, num_samples, training, d_logits, d_grad, d_dy, dw_part,  \
+                                   d_result, part_loss, part_cnt, ticket, st)                                                  \
+             : launch_head<IN_, 2>(d_y, d_w, d_truth, n, num_classes, num_samples, training, d_logits, d_grad, d_dy, dw_part,  \
+                                   d_result, part_loss, part_cnt, ticket, st)
   if (in_dim == 8) HEAD(8);
   if (in_dim == 16) HEAD(16);
   HEAD(32);

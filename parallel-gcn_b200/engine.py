@@ -70,6 +70,7 @@ _sig("gcnb_gcn_launches_total", I64, [P])
 _sig("gcnb_gcn_timed_epochs", I32, [P, I32, I32, I32, P])
 _sig("gcnb_gcn_graphsum_exchange_ms", C.c_double, [P])
 _sig("gcnb_host_free", None, [P])
+_sig("gcnb_sweep_run", I32, [P, P, I64, I32, P, P])
 _sig("gcnb_reorder_communities", I32, [I64, P, P, I32, C.c_uint64, P, P])
 _sig("gcnb_permute_csr", I32, [I64, P, P, P, P, P])
 _sig("gcnb_permute_rows", I32, [I64, I64, P, P, P])
@@ -78,6 +79,51 @@ _sig("gcnb_unpermute_rows", I32, [I64, I64, P, P, P])
 
 def _p(a):
     return None if a is None else a.ctypes.data_as(P)
+
+
+class SweepTrial(C.Structure):
+    _fields_ = [("n_layers", I32), ("hidden_dims", U32 * 7), ("dropouts", F32 * 8), ("epochs", U32), ("early_stopping", U32),
+                ("learning_rate", F32), ("weight_decay", F32), ("seed", U32)]
+
+
+class SweepResult(C.Structure):
+    _fields_ = [("last_val_accuracy", F32), ("last_val_loss", F32), ("last_train_loss", F32), ("avg_epoch_ms", F32),
+                ("total_s", F32), ("epochs_run", U32)]
+
+
+def sweep_run(source, trials, workers=0):
+    """The reference's tuning sweep (test/tuning_accuracy.cpp) as a throughput workload: gcnb_sweep_run.
+
+    source: (root, name) of a shipped dataset or the path of a binary container; trials: list of dicts with keys
+    hidden_dims, dropouts, epochs, early_stopping, learning_rate, weight_decay, seed.  Returns (list of result dicts in
+    trial order, wall seconds).  Results do not depend on `workers`."""
+    h = P()
+    if isinstance(source, (tuple, list)):
+        rc = lib.gcnb_dataset_parse(str(source[0]).encode(), source[1].encode(), 0, C.byref(h))
+    else:
+        rc = lib.gcnb_dataset_load(str(source).encode(), C.byref(h))
+    if rc != 0:
+        raise GcnbError("sweep_run: cannot read the dataset %r (code %d)" % (source, rc))
+    try:
+        arr = (SweepTrial * len(trials))()
+        for t, src in zip(arr, trials):
+            hd, dr = list(src.get("hidden_dims", [16])), list(src.get("dropouts", [0.5, 0.5]))
+            t.n_layers = len(hd) + 1
+            assert len(dr) == t.n_layers and t.n_layers <= 8
+            for i, v in enumerate(hd):
+                t.hidden_dims[i] = int(v)
+            for i, v in enumerate(dr):
+                t.dropouts[i] = float(v)
+            t.epochs, t.early_stopping = int(src.get("epochs", 100)), int(src.get("early_stopping", 0))
+            t.learning_rate, t.weight_decay = float(src.get("learning_rate", 0.01)), float(src.get("weight_decay", 5e-4))
+            t.seed = int(src.get("seed", 19990304))
+        res = (SweepResult * len(trials))()
+        wall = C.c_double(0)
+        check(lib.gcnb_sweep_run(h, arr, len(trials), int(workers), res, C.byref(wall)))
+        out = [{f: getattr(r, f) for f, _ in SweepResult._fields_} for r in res]
+        return out, wall.value
+    finally:
+        lib.gcnb_dataset_free(h)
 
 
 def parse_dataset(root, name, no_feature=False, save_to=None):

@@ -114,8 +114,9 @@ class GCN {
   // returns false when sync == false and the passes were only enqueued (graph replays): results via read_result after a sync
   bool train_and_eval(natural split, std::pair<real, real> &train, std::pair<real, real> &val, bool sync = true);
   void print_variable_info() const;
+  void run_concurrent();
   void init(bool quiet, const natural *h_graph_indptr = nullptr, const natural *h_graph_indices = nullptr,
-            const GCNPartition *part = nullptr);
+            const GCNPartition *part = nullptr, const natural *seed = nullptr);
 
  public:
   real avg_epoch_time;
@@ -137,8 +138,13 @@ class GCN {
   // row-partitioned rank: params_->num_nodes = LOCAL rows, train/val/test_dim = GLOBAL counts, view = the row block
   GCN(GCNParams const *params_, AdamParams const *adam_params_, const GCNDataView &view, const GCNPartition &part,
       bool quiet);
+  // several models over ONE device-resident dataset (the tuning sweeps of test/tuning_accuracy.cpp construct 20 models per
+  // parameter combination and upload the dataset 20 times): the buffers of `shared` are referenced, not copied; the seed
+  // is the model's own (CudaParams::SEED is process-wide, concurrent constructors would race on it)
+  GCN(GCNParams const *params_, AdamParams const *adam_params_, const DevGCNData &shared, natural seed, bool quiet);
   ~GCN();
   void run();
+  void set_concurrent(bool on);  // several models run at once from several host threads: run() keeps its timers private
 
   // ---- extensions (not in the reference's public surface; used by the C ABI engine, tests and bench) ----
   std::pair<real, real> train_epoch();                       // reference: private, src/gcn.cu:307-343
@@ -171,5 +177,6 @@ class GCN {
   double graphsum_exchange_ms() const;  // partitioned: summed time from the start of a GraphSum call until the peers' slabs have landed
   float timed_epochs(natural n_epochs, bool with_eval);   // ms between CUDA events on the engine stream
   natural epochs_run() const;
+  real last_val_loss = 0, last_train_loss = 0;  // of the last epoch run() completed
 };
 #endif

@@ -8,7 +8,10 @@
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
+#include <atomic>
+#include <chrono>
 #include <cstdio>
+#include <thread>
 #include <type_traits>
 
 struct gcnb_dataset {
@@ -323,6 +326,59 @@ int gcnb_gcn_create_from_dataset(const gcnb_gcn_config *cfg, const gcnb_dataset 
   gd.label = d->data.label.data();
   gd.split = d->data.split.data();
   return gcnb_gcn_create(&c, &gd, out);
+}
+
+int gcnb_sweep_run(const gcnb_dataset *d, const gcnb_sweep_trial *trials, int64_t n_trials, int workers,
+                   gcnb_sweep_result *results, double *wall_s) {
+  if (!d || (n_trials > 0 && (!trials || !results)) || n_trials < 0) return GCNB_E_BADARG;
+  for (int64_t i = 0; i < n_trials; i++)
+    if (trials[i].n_layers < 1 || trials[i].n_layers > 8) return GCNB_E_BADARG;
+  int sm = 0;
+  const int dc = gcnb_device_check(&sm);
+  if (dc) return dc;  // no GPU => error, never a CPU path
+  const auto t0 = std::chrono::steady_clock::now();
+  int device = 0;
+  CHECK_CUDA_ERROR(cudaGetDevice(&device));
+  const DevGCNData shared(d->data);  // one upload for every trial
+  if (workers <= 0) workers = (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+  workers = (int)std::min<int64_t>(workers, std::max<int64_t>(1, n_trials));
+  std::atomic<int64_t> next{0};
+  auto work = [&]() {
+    CHECK_CUDA_ERROR(cudaSetDevice(device));
+    for (;;) {
+      const int64_t i = next.fetch_add(1);
+      if (i >= n_trials) return;
+      const gcnb_sweep_trial &t = trials[i];
+      GCNParams params = d->params;  // num_nodes, dims and split counts parsed from the data
+      params.n_layers = (natural)t.n_layers;
+      params.hidden_dims.assign(t.hidden_dims, t.hidden_dims + (t.n_layers - 1));
+      params.dropouts.assign(t.dropouts, t.dropouts + t.n_layers);
+      params.epochs = t.epochs;
+      params.early_stopping = t.early_stopping;
+      AdamParams adam;
+      adam.learning_rate = t.learning_rate;
+      adam.weight_decay = t.weight_decay;
+      GCN gcn(&params, &adam, shared, t.seed, true);
+      gcn.run();
+      gcnb_sweep_result &r = results[i];
+      r.last_val_accuracy = gcn.last_val_accuracy;
+      r.last_val_loss = gcn.last_val_loss;
+      r.last_train_loss = gcn.last_train_loss;
+      r.avg_epoch_ms = gcn.avg_epoch_time;
+      r.total_s = gcn.total_time;
+      r.epochs_run = gcn.epochs_run();
+    }
+  };
+  if (workers == 1) {
+    work();
+  } else {
+    std::vector<std::thread> pool;
+    for (int w = 0; w < workers; w++) pool.emplace_back(work);
+    for (auto &th : pool) th.join();
+  }
+  CHECK_CUDA_ERROR(cudaDeviceSynchronize());
+  if (wall_s) *wall_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  return 0;
 }
 
 int gcnb_gcn_destroy(gcnb_gcn *g) {

@@ -96,6 +96,8 @@ struct GCNLayer {
 };
 
 struct GCNEngineState {
+  GCNRngContext rng;        // this model's Philox consumption history and seed (bound to the calling thread by RngScope)
+  bool concurrent = false;  // other models may be running on other host threads: no process-wide timers
   cudaStream_t stream = nullptr;
   gcnb_spmm_plan *graph_plan = nullptr, *feat_plan = nullptr, *feat_csc_plan = nullptr;
   gcnb_bittile_plan *graph_bittile = nullptr;  // GCNB_BITTILE=1: tensor-core bit tiles for GraphSum at width 16
@@ -376,6 +378,20 @@ struct GCNEngineState {
   }
 };
 
+// binds a model's RNG context to the calling thread for the duration of one of its public calls
+struct RngScope {
+  GCNRngContext *prev;
+  explicit RngScope(GCNRngContext *ctx) : prev(Variable::rng_bind(ctx)) {}
+  ~RngScope() { Variable::rng_bind(prev); }
+  RngScope(const RngScope &) = delete;
+  RngScope &operator=(const RngScope &) = delete;
+};
+
+GCN::GCN(GCNParams const *params_, AdamParams const *adam_params_, const DevGCNData &shared, natural seed, bool quiet)
+    : smart_objects(params_->n_layers), data(nullptr), dev_data{shared}, params(params_), adam_params(adam_params_) {
+  init(quiet, nullptr, nullptr, nullptr, &seed);
+}
+
 GCN::GCN(GCNParams const *params_, AdamParams const *adam_params_, GCNData const *data_, bool quiet)
     : smart_objects(params_->n_layers), data(data_), dev_data{DevGCNData(*data_)}, params(params_),
       adam_params(adam_params_) {
@@ -395,17 +411,21 @@ GCN::GCN(GCNParams const *params_, AdamParams const *adam_params_, const GCNData
   init(quiet, view.graph_indptr, view.graph_indices, &part);
 }
 
-void GCN::init(bool quiet, const natural *h_graph_indptr, const natural *h_graph_indices, const GCNPartition *part) {
+void GCN::init(bool quiet, const natural *h_graph_indptr, const natural *h_graph_indices, const GCNPartition *part,
+               const natural *seed) {
   int sm = 0;
   GCNB_CALL(gcnb_device_check(&sm));  // no CPU fallback: a missing/unsupported GPU is fatal here
   setup_lap(nullptr);
+  st = std::make_shared<GCNEngineState>();
+  st->rng.seed = seed ? *seed : CudaParams::SEED;  // the reference seeds its streams in the constructor (src/gcn.cu:146-149)
+  st->concurrent = seed != nullptr;
+  RngScope rng_scope(&st->rng);
   L = params->n_layers;
   if (L < 1 || params->hidden_dims.size() != L - 1 || params->dropouts.size() != L) {
     std::cerr << "GCN: n_layers / hidden_dims / dropouts are inconsistent" << std::endl;
     exit(1);
   }
   avg_epoch_time = total_time = last_val_accuracy = 0;
-  st = std::make_shared<GCNEngineState>();
   st->quiet = quiet;
   if (part) {
     const size_t world = (size_t)gcnb_comm_world(part->comm);
@@ -791,20 +811,27 @@ void GCN::init(bool quiet, const natural *h_graph_indptr, const natural *h_graph
   if (L >= 2 && gcnb_head_supported((int)st->layers.back().in_dim, (int)st->layers.back().out_dim)) {
     st->head_ws_bytes = gcnb_head_workspace(N, (int)st->layers.back().in_dim, (int)st->layers.back().out_dim);
     st->head_ws = dev_shared_ptr<natural>((st->head_ws_bytes + 3) / 4);
-    CHECK_CUDA_ERROR(cudaMemset(st->head_ws.get(), 0, st->head_ws.get_n_elements() * 4));
+    CHECK_CUDA_ERROR(cudaMemsetAsync(st->head_ws.get(), 0, st->head_ws.get_n_elements() * 4, st->stream));
   }
   st->sumsq_ws = dev_shared_ptr<natural>((gcnb_sumsq_workspace(weights[0]->size) + 3) / 4);
-  CHECK_CUDA_ERROR(cudaMemset(st->ce_ws.get(), 0, st->ce_ws.get_n_elements() * 4));
-  CHECK_CUDA_ERROR(cudaMemset(st->sumsq_ws.get(), 0, st->sumsq_ws.get_n_elements() * 4));
+  CHECK_CUDA_ERROR(cudaMemsetAsync(st->ce_ws.get(), 0, st->ce_ws.get_n_elements() * 4, st->stream));
+  CHECK_CUDA_ERROR(cudaMemsetAsync(st->sumsq_ws.get(), 0, st->sumsq_ws.get_n_elements() * 4, st->stream));
   st->dev_result = dev_shared_ptr<real>(8);
-  CHECK_CUDA_ERROR(cudaMemset(st->dev_result.get(), 0, 8 * sizeof(real)));
+  CHECK_CUDA_ERROR(cudaMemsetAsync(st->dev_result.get(), 0, 8 * sizeof(real), st->stream));
   st->host_result = pinned_host_ptr<real>(16);
   st->ext_masks.resize(L);
 
   if (!st->quiet) print_variable_info();
   Variable::initialize_random();
-  for (const auto &weight : weights) weight->glorot();
-  CHECK_CUDA_ERROR(cudaDeviceSynchronize());  // glorot ran on the default stream (as in the reference)
+  if (st->concurrent) {
+    // other models may be capturing CUDA graphs on other threads: a device-wide synchronisation is invalid then (and would
+    // invalidate THEIR capture), so this model's set-up stays on its own stream
+    for (const auto &weight : weights) weight->glorot(st->stream);
+    CHECK_CUDA_ERROR(cudaStreamSynchronize(st->stream));
+  } else {
+    for (const auto &weight : weights) weight->glorot();
+    CHECK_CUDA_ERROR(cudaDeviceSynchronize());  // glorot ran on the default stream (as in the reference)
+  }
   optimizer = Adam(weights, decays, adam_params, smart_objects.backward_streams, smart_objects.start_matmul_forward,
                    smart_objects.forward_training_stream);
   setup_lap("workspaces, glorot, Adam state");
@@ -821,6 +848,7 @@ GCN::~GCN() {
 }
 
 void GCN::set_quiet(bool q) { st->quiet = q; }
+void GCN::set_concurrent(bool on) { st->concurrent = on; }
 void GCN::set_use_cuda_graph(bool on) {
   if (!on) st->drop_graphs();
   st->graph_enabled = on;
@@ -864,6 +892,7 @@ void GCN::graphsum_timing(double *ms_total, size_t *calls) const {
   *calls = st->gs_calls;
 }
 float GCN::timed_epochs(natural n_epochs, bool with_eval) {
+  RngScope rng_scope(&st->rng);
   // K epochs bracketed by CUDA events on the engine's own stream (bench.py: device time, not wall clock)
   cudaEvent_t e0, e1;
   CHECK_CUDA_ERROR(cudaEventCreate(&e0));
@@ -1249,6 +1278,7 @@ void GCN::train_body(cudaStream_t s) {
 void GCN::finish_setup() { st->finish_stage(); }
 
 std::pair<real, real> GCN::train_epoch() {
+  RngScope rng_scope(&st->rng);
   if (st->setup_pending && st->train_calls >= st->stage_switch_epoch) st->finish_stage();
   st->train_calls++;
   const size_t before = st->launches;
@@ -1286,6 +1316,7 @@ std::pair<real, real> GCN::train_epoch() {
 // graph affects future launches only; the result blocks are overwritten by every epoch, the caller reads the last one
 // after its own synchronisation (read_result).  Returns whether it synchronised.
 bool GCN::train_and_eval(natural split, std::pair<real, real> &train, std::pair<real, real> &val, bool sync) {
+  RngScope rng_scope(&st->rng);
   const natural k = split < 4 ? split : 0;
   if (!(st->graphs_usable() && st->train_exec && k != 0 && st->eval_exec[k])) {
     train = train_epoch();
@@ -1310,6 +1341,7 @@ bool GCN::train_and_eval(natural split, std::pair<real, real> &train, std::pair<
 }
 
 std::pair<real, real> GCN::eval(const natural current_split) {
+  RngScope rng_scope(&st->rng);
   cudaStream_t s = st->stream;
   const natural k = current_split < 4 ? current_split : 0;
   if (st->graphs_usable() && st->eval_exec[k]) {
@@ -1332,9 +1364,56 @@ std::pair<real, real> GCN::eval(const natural current_split) {
   return finalize(s, 1);
 }
 
+// run() for a model that trains next to others on other host threads (gcnb_sweep_run): same loop, same early stopping,
+// quiet, wall-clock kept in locals instead of the process-wide timers of include/timer.h
+void GCN::run_concurrent() {
+  using clk = std::chrono::steady_clock;
+  const auto t_total = clk::now();
+  natural epoch = 1;
+  std::vector<real> loss_history;
+  loss_history.reserve(params->epochs);
+  real train_loss{0.f}, train_acc{0.f}, val_loss{0.f}, val_acc{0.f};
+  const bool pipelined = params->early_stopping == 0;
+  bool pending = false;
+  for (; epoch <= params->epochs; epoch++) {
+    std::pair<real, real> tr, va;
+    if (train_and_eval(2, tr, va, !pipelined)) {
+      std::tie(train_loss, train_acc) = tr;
+      std::tie(val_loss, val_acc) = va;
+      pending = false;
+    } else {
+      pending = true;
+    }
+    if (pipelined) continue;
+    loss_history.push_back(val_loss);
+    if (epoch >= params->early_stopping) {
+      real recent_loss = 0.0;
+      for (natural i = epoch - params->early_stopping; i < epoch; i++) recent_loss += loss_history[i];
+      if (val_loss > recent_loss / static_cast<real>(params->early_stopping)) break;
+    }
+  }
+  CHECK_CUDA_ERROR(cudaStreamSynchronize(st->stream));
+  if (pending) {
+    std::tie(train_loss, train_acc) = read_result(0);
+    std::tie(val_loss, val_acc) = read_result(1);
+  }
+  const double total_s = std::chrono::duration<double>(clk::now() - t_total).count();
+  st->epochs_run = std::min(epoch, params->epochs);
+  avg_epoch_time = (real)(total_s * 1000 / epoch);  // the reference divides by `epoch`
+  total_time = (real)total_s;
+  last_val_accuracy = val_acc;
+  last_val_loss = val_loss;
+  last_train_loss = train_loss;
+}
+
 void GCN::run() {
+  RngScope rng_scope(&st->rng);
   const bool out = !st->quiet;
   if (out) std::cout << "TRAINING AND EVALUATION OF GCN:" << std::endl;
+  if (st->concurrent) {
+    run_concurrent();
+    return;
+  }
   timer_start(TMR_TOTAL);
   natural epoch = 1;
   std::vector<real> loss_history;
@@ -1388,6 +1467,8 @@ void GCN::run() {
   avg_epoch_time = TIMER_AVERAGE_NO_OUTPUT(TMR_TRAIN, epoch);
   total_time = timer_total(TMR_TOTAL);
   last_val_accuracy = val_acc;
+  last_val_loss = val_loss;
+  last_train_loss = train_loss;
   if (out) {
     real test_loss, test_acc;
     timer_start(TMR_TEST);

@@ -2,26 +2,35 @@
 #include "../include/variable.cuh"
 #include <algorithm>
 
+static thread_local GCNRngContext *t_rng_ctx = nullptr;
+
+GCNRngContext *Variable::rng_bind(GCNRngContext *ctx) {
+  GCNRngContext *prev = t_rng_ctx;
+  t_rng_ctx = ctx;
+  return prev;
+}
+
 Variable::Variable(const natural size_, const bool requires_grad, const bool rand, const natural rows_,
                    const natural cols_)
     : size(size_), rows(rows_), cols(cols_) {
   dev_data = dev_shared_ptr<real>(size);
   dev_grad = requires_grad ? dev_shared_ptr<real>(size) : dev_shared_ptr<real>();
-  if (rand) sizes.push_back(size);
+  if (rand && !t_rng_ctx) sizes.push_back(size);  // (bookkeeping of the reference's state array; models with their own context skip it)
 }
 
 void Variable::initialize_random() {
   // reference: allocates ceil(max(sizes)/4) Philox states and curand_init()s them (src/variable.cu:13-26).
   // Stateless equivalent: every stream restarts at draw 0.
-  rng_history.clear();
+  if (t_rng_ctx) t_rng_ctx->history.clear();
+  else rng_history.clear();
   rng_initialized = true;
 }
 
 gcnb_rng_t Variable::rng_descriptor() {
   gcnb_rng_t r{};
-  r.seed = CudaParams::SEED;
+  r.seed = t_rng_ctx ? t_rng_ctx->seed : CudaParams::SEED;
   r.n_hist = 0;
-  for (const auto &kv : rng_history) {
+  for (const auto &kv : (t_rng_ctx ? t_rng_ctx->history : rng_history)) {
     if (kv.second == 0) continue;
     if (r.n_hist == GCNB_MAX_RNG_HIST) {
       std::cerr << "Variable: more than " << GCNB_MAX_RNG_HIST << " distinct RNG consumer sizes" << std::endl;
@@ -42,10 +51,10 @@ void Variable::rng_consume(size_t n_elements) {
     std::cerr << "Variable::rng_consume: " << n_elements << " elements exceed the 2^34-element range of the Philox descriptor" << std::endl;
     exit(EXIT_FAILURE);
   }
-  rng_history[(natural)groups] += 1;
+  (t_rng_ctx ? t_rng_ctx->history : rng_history)[(natural)groups] += 1;
 }
 
-void Variable::glorot() const {
+void Variable::glorot(cudaStream_t stream) const {
   if (!rng_initialized) {
     std::cerr << "Variable::glorot: Variable must be initialized with rand = true" << std::endl;
     exit(EXIT_FAILURE);
@@ -55,7 +64,7 @@ void Variable::glorot() const {
     exit(EXIT_FAILURE);
   }
   const gcnb_rng_t rng = rng_descriptor();
-  GCNB_CALL(gcnb_glorot_f32(dev_data.get(), size, rows, cols, &rng, nullptr));  // default stream, as the reference
+  GCNB_CALL(gcnb_glorot_f32(dev_data.get(), size, rows, cols, &rng, stream));  // default stream unless told otherwise, as the reference
   rng_consume(size);
 }
 

@@ -281,3 +281,32 @@ def test_cuda_graph_replay_is_bit_identical_to_eager(eng, datasets, name):
     for a, b in zip(eager[1], graph[1]):
         assert np.array_equal(a, b)
     assert eager[2] == graph[2]
+
+
+def test_tuning_sweep_is_independent_of_concurrency(eng):
+    """gcnb_sweep_run (the reference's test/tuning_accuracy.cpp loop as a throughput workload): trials running side by side
+    on several host threads and streams give bit for bit the results of running them one after the other, and those of the
+    plain `CudaParams::SEED = seed; GCN gcn{...}; gcn.run()` a caller of the reference would write."""
+    trials = []
+    seeds = [1804289383, 846930886, 1681692777, 1714636915]
+    for hidden in ((8,), (16,), (32, 32)):
+        for d1, d2 in ((0.0, 0.2), (0.6, 0.4)):
+            for seed in seeds[:2]:
+                trials.append(dict(hidden_dims=hidden, dropouts=(d1,) + (d2,) * len(hidden), epochs=40, early_stopping=10,
+                                   learning_rate=0.01, weight_decay=5e-4, seed=seed))
+    trials.append(dict(hidden_dims=(16,), dropouts=(0.5, 0.5), epochs=25, early_stopping=0, seed=seeds[2]))  # pipelined replays
+    one, _ = eng.sweep_run((ROOT, "cora"), trials, workers=1)
+    many, _ = eng.sweep_run((ROOT, "cora"), trials, workers=6)
+    keys = ("last_val_accuracy", "last_val_loss", "last_train_loss", "epochs_run")
+    for t, a, b in zip(trials, one, many):
+        assert all(a[k] == b[k] for k in keys), (t, a, b)
+        assert 1 <= a["epochs_run"] <= t["epochs"] and 0.0 <= a["last_val_accuracy"] <= 1.0 and np.isfinite(a["last_val_loss"])
+    assert len({r["last_val_accuracy"] for r in one}) > 3  # different seeds / models really are different runs
+    ds = eng.parse_dataset(ROOT, "cora")
+    for i in (0, 5, len(trials) - 1):
+        t = trials[i]
+        g = eng.GCN(ds, hidden_dims=t["hidden_dims"], dropouts=t["dropouts"], epochs=t["epochs"], early_stopping=t["early_stopping"],
+                    lr=t.get("learning_rate", 0.01), weight_decay=t.get("weight_decay", 5e-4), seed=t["seed"], quiet=True)
+        res = g.run()
+        g.close()
+        assert res["epochs"] == one[i]["epochs_run"] and res["last_val_acc"] == one[i]["last_val_accuracy"], (t, res, one[i])

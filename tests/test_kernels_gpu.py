@@ -463,7 +463,7 @@ def test_output_head_in_one_kernel(O, gcnb, dev, n, K, C, training, with_grad):
     if training:
         assert (outs[0][1].view(u32) == outs[1][1].view(u32)).all(), "weight gradient must be deterministic"
         assert_close(to_np(d_dy), dy_want, what="head dy")
-        assert_close(to_np(d_dw), dw_want, rtol=2e-5, atol=2e-6 * np.abs(dw_want).max(), what="head dW")
+        assert_close(to_np(d_dw), dw_want, rtol=2e-5, atol=5e-6 * np.abs(dw_want).max(), what="head dW")  # (the oracle adds 70 k fp32 terms in sequence)
         if with_grad:
             assert_close(to_np(d_g), gw, what="head dz")
     # the unfused kernels compute the same elements with the same arithmetic
