@@ -433,6 +433,20 @@ GCNB_API int gcnb_comm_gather_slabs_f32(gcnb_comm *c, const float *d_slab, int64
 GCNB_API int gcnb_comm_gather_slabs_ex_f32(gcnb_comm *c, const float *d_slab, int64_t count_per_rank,
                                            const float **d_full_out, int overlapped, gcnb_stream_t stream);
 GCNB_API int gcnb_comm_gather_mode(const gcnb_comm *c);
+/* Halo exchange: after this call the slab gathers whose slab is [block x dim] ship to every peer only
+ * the rows of this rank's block that the peer's row block references (same buffers, flags and slot layout: column ids
+ * need no translation, nothing downstream changes; unreferenced rows of a peer's slot are never written nor read).
+ * d_indices / nnz: the column ids of this rank's CSR block in the slot layout (column c = row c % block of rank
+ * c / block); rows_local <= block.  Collective (one all-gather of n_global / 8 bytes per rank).  The lists are used when
+ * they hold at most max_fraction of what the full push sends (GCNB_HALO=0 / 1 forces it), peer-memory mode only.
+ * info: {active, rows sent per exchange, rows of the full push, rows this rank references in other ranks' blocks}.
+ * gcnb_halo_lists_from_masks: the host logic behind it (masks = [world][words] bits over the column space; rows_out is
+ * malloc'ed, off_out has world + 1 entries) -- exported for CPU tests. */
+GCNB_API int gcnb_comm_halo_setup(gcnb_comm *c, const uint32_t *d_indices, int64_t nnz, int64_t rows_local, int64_t block,
+                                  double max_fraction, int64_t info[4], gcnb_stream_t stream);
+GCNB_API int gcnb_comm_halo_active(const gcnb_comm *c);
+GCNB_API int gcnb_halo_lists_from_masks(const uint32_t *masks, int world, int rank, int64_t words, int64_t block,
+                                        int64_t rows_local, uint32_t **rows_out, int64_t *off_out);
 GCNB_API int gcnb_comm_group_start(gcnb_comm *c);
 GCNB_API int gcnb_comm_group_end(gcnb_comm *c);
 

@@ -124,6 +124,9 @@ GCNB_API int gcnb_gcn_timed_epochs(gcnb_gcn *g, int n_epochs, int with_eval, int
  * (out[1]) that passed between the start of a call and the moment every peer's slab had landed -- the slab exchange, and
  * with window staging the own-slab windows that overlap it */
 GCNB_API double gcnb_gcn_graphsum_exchange_ms(const gcnb_gcn *g);
+/* row-partitioned models: {halo exchange active (gcnb_comm_halo_setup), rows this rank ships per exchange, rows a full
+ * slab push would ship, rows of other ranks' blocks this rank references} */
+GCNB_API int gcnb_gcn_halo_info(const gcnb_gcn *g, int64_t out[4]);
 
 /* ---- tuning sweep as a throughput workload (test/tuning_accuracy.cpp:56-196, test/tuning_cuda.cpp of the reference) ----
  * The reference tunes by constructing one model after the other (20 seeds x every parameter combination, 1000 epochs with
@@ -184,6 +187,12 @@ GCNB_API int gcnb_synth_labels(int64_t n, int classes, double frac_train, double
 GCNB_API int gcnb_synth_sym_rows(int64_t n, int64_t row0, int64_t rows, int64_t block_size, double mean_intra,
                                  double mean_inter, int n_reflect, double sigma, uint64_t seed, uint32_t **indptr_out,
                                  uint32_t **indices_out, int64_t *nnz_out);
+/* same with LOCAL inter-community edges (inter_window > 0; 0 = the reflections above): across communities node i's candidates
+ * are i +- d_k for n_reflect / 2 fixed shifts d_k in [block_size, inter_window], so a row block references only rows within
+ * inter_window of its borders -- the structure the halo exchange (gcnb_comm_halo_setup) is for */
+GCNB_API int gcnb_synth_sym_rows_local(int64_t n, int64_t row0, int64_t rows, int64_t block_size, double mean_intra,
+                                       double mean_inter, int n_reflect, int64_t inter_window, double sigma, uint64_t seed,
+                                       uint32_t **indptr_out, uint32_t **indices_out, int64_t *nnz_out);
 /* graph_value of a row block from the GLOBAL degree array (Parser::calculateGraphValues arithmetic, src/parser.cpp:164-181) */
 GCNB_API int gcnb_synth_graph_values(const uint32_t *indptr, const uint32_t *indices, int64_t rows, int64_t row0,
                                      const uint32_t *deg_global, float *out);
@@ -199,6 +208,14 @@ GCNB_API int gcnb_synth_dense_features_uniform(int64_t n, int f, uint64_t seed, 
  * gcnb_unpermute_rows maps per-node outputs (logits) back to the original numbering. */
 GCNB_API int gcnb_reorder_communities(int64_t n, const uint32_t *indptr, const uint32_t *indices, int max_sweeps,
                                       uint64_t seed, uint32_t *new_of_old, int64_t *n_communities);
+/* Balanced, community-aligned row partition for `world` ranks: equal CSR-entry counts per rank, rank
+ * boundaries on community borders where one lies within `tolerance` (fraction of a rank's share; 0 = 0.1) of the balanced
+ * cut.  new_of_old[i] in [0, world * block): rank r owns the ids [r * block, r * block + rows_out[r]), block = a multiple of
+ * 4 (the engine's slab size); the remaining ids are padding.  stats: {communities, cut entries, cut entries of the plain
+ * equal-row-block partition of the given numbering, largest entry count of a rank}. */
+GCNB_API int gcnb_partition_communities(int64_t n, const uint32_t *indptr, const uint32_t *indices, int world, int max_sweeps,
+                                        uint64_t seed, double tolerance, uint32_t *new_of_old, int64_t *block_out,
+                                        int64_t *rows_out, int64_t stats[4]);
 GCNB_API int gcnb_permute_csr(int64_t n, const uint32_t *indptr, const uint32_t *indices, const uint32_t *new_of_old,
                               uint32_t *out_indptr, uint32_t *out_indices);
 GCNB_API int gcnb_permute_rows(int64_t n, int64_t row_bytes, const uint32_t *new_of_old, const void *in, void *out);

@@ -74,6 +74,10 @@ struct P2PPeers {
   int world, rank;
 };
 
+struct HaloOffsets {
+  int64_t off[kMaxWorld + 1];  // rows for peer p: d_halo_rows[off[p] .. off[p + 1])
+};
+
 struct gcnb_comm {
   ncclComm_t comm = nullptr;
   int rank = 0, world = 1;
@@ -87,6 +91,11 @@ struct gcnb_comm {
   void *opened[3 * kMaxWorld] = {nullptr};
   int n_opened = 0;
   uint32_t epoch = 0;
+  // halo exchange (gcnb_comm_halo_setup): the rows of this rank's slab that each peer's row block references
+  bool halo = false;
+  int64_t halo_block = 0, halo_rows_local = 0, halo_send_total = 0, halo_need_total = 0;
+  uint32_t *d_halo_rows = nullptr;  // [halo_send_total] local row ids, grouped by destination rank
+  HaloOffsets halo_off{};
 };
 
 namespace {
@@ -112,6 +121,50 @@ p2p_push_kernel(const float4 *__restrict__ slab, int64_t n4, P2PPeers peers, int
       asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(epoch) : "memory");
     }
     if (threadIdx.x == 0) *ticket = 0;
+  }
+}
+
+// Halo exchange: the same buffers, flags and slot layout as p2p_push_kernel (row i of rank r lives at row r * block + i of
+// every rank's buffer, so column ids need no translation and nothing downstream changes) -- but a peer receives only the
+// rows its row block references; the rest of its copy of this rank's slot is never written and never read.  The rank's
+// own slot gets the whole slab (local copy).  One thread per float4 of a row; consecutive list entries are mostly
+// consecutive rows, so the NVLink stores coalesce.
+__global__ void __launch_bounds__(256)
+p2p_push_rows_kernel(const float4 *__restrict__ slab, int64_t n4_self, int d4, const uint32_t *__restrict__ rows, HaloOffsets off,
+                     P2PPeers peers, int buf, int64_t slot_off4, uint32_t epoch, unsigned int *__restrict__ ticket) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x, t0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  float4 *self = reinterpret_cast<float4 *>(peers.gather[buf][peers.rank]) + slot_off4;
+  for (int64_t i = t0; i < n4_self; i += stride) self[i] = __ldg(slab + i);
+  const int64_t total = off.off[peers.world] * d4;
+  int p = 0;
+  for (int64_t t = t0; t < total; t += stride) {
+    const int64_t e = t / d4;
+    const int c = (int)(t - e * d4);
+    while (e >= off.off[p + 1]) p++;  // entries are grouped by destination; t only grows
+    const int64_t k = (int64_t)__ldg(rows + e) * d4 + c;
+    reinterpret_cast<float4 *>(peers.gather[buf][p])[slot_off4 + k] = __ldg(slab + k);
+  }
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool last;
+  if (threadIdx.x == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (last) {
+    __threadfence_system();
+    if (threadIdx.x < peers.world) {
+      uint32_t *f = peers.flags[threadIdx.x] + peers.rank;
+      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(epoch) : "memory");
+    }
+    if (threadIdx.x == 0) *ticket = 0;
+  }
+}
+
+// bit c of the mask <- 1 for every column id c of the rank's CSR block
+__global__ void halo_mask_kernel(const uint32_t *__restrict__ indices, int64_t nnz, uint32_t *__restrict__ mask) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nnz; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t c = __ldg(indices + i);
+    const uint32_t bit = 1u << (c & 31);
+    if (!(mask[c >> 5] & bit)) atomicOr(mask + (c >> 5), bit);
   }
 }
 
@@ -213,6 +266,7 @@ int gcnb_comm_destroy(gcnb_comm *c) {
   cudaFree(c->gather_local[1]);
   cudaFree(c->flags_local);
   cudaFree(c->d_ticket);
+  cudaFree(c->d_halo_rows);
   if (c->comm) nccl().CommDestroy(c->comm);
   delete c;
   return 0;
@@ -239,6 +293,9 @@ int gcnb_comm_gather_setup(gcnb_comm *c, int64_t gather_floats) {
     c->d_ticket = nullptr;
     c->p2p = false;
     c->epoch = 0;
+    cudaFree(c->d_halo_rows);
+    c->d_halo_rows = nullptr;
+    c->halo = false;
   }
   c->gather_floats = gather_floats;
   for (int b = 0; b < 2; b++) {
@@ -335,6 +392,17 @@ int gcnb_comm_gather_slabs_ex_f32(gcnb_comm *c, const float *d_slab, int64_t cou
     const char *e = getenv("GCNB_P2P_DMA");  // tuning probe: 0 never, 1 always, unset = overlapped exchanges >= 4 MB
     return e ? atoi(e) : -1;
   }();
+  if (c->halo && c->halo_block > 0 && count_per_rank % c->halo_block == 0 && (count_per_rank / c->halo_block) % 4 == 0) {
+    const int d4 = (int)(count_per_rank / c->halo_block / 4);
+    const int64_t n4_self = c->halo_rows_local * d4, work = std::max(n4_self, c->halo_send_total * d4);
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((work + 255) / 256, (int64_t)std::max(1, gcnb::device_info().sm_count) * 2));
+    p2p_push_rows_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float4 *>(d_slab), n4_self, d4, c->d_halo_rows, c->halo_off,
+                                                 c->peers, buf, (int64_t)c->rank * (count_per_rank / 4), epoch, c->d_ticket);
+    GCNB_LAUNCH_CHECK();
+    p2p_wait_kernel<<<1, 32, 0, st>>>(c->flags_local, c->world, epoch);
+    GCNB_LAUNCH_CHECK();
+    return 0;
+  }
   const bool dma = dma_env == 1 || (dma_env < 0 && overlapped && count_per_rank * 4 >= (4 << 20));
   if (dma) {
     for (int k = 0; k < c->world; k++) {
@@ -357,6 +425,111 @@ int gcnb_comm_gather_slabs_ex_f32(gcnb_comm *c, const float *d_slab, int64_t cou
   GCNB_LAUNCH_CHECK();
   return 0;
 }
+
+// Which rows of rank `rank`'s block does each peer reference?  masks = [world][words] bit masks over the slot-layout column
+// space (bit c of masks[p]: rank p's row block holds column c).  Pure host logic (tests/test_halo_cpu.py).
+int gcnb_halo_lists_from_masks(const uint32_t *masks, int world, int rank, int64_t words, int64_t block, int64_t rows_local,
+                               uint32_t **rows_out, int64_t *off_out /* [world + 1] */) {
+  if (!masks || world < 1 || world > kMaxWorld || rank < 0 || rank >= world || block <= 0 || rows_local < 0 ||
+      rows_local > block || words * 32 < (int64_t)world * block || !rows_out || !off_out)
+    return GCNB_E_BADARG;
+  std::vector<uint32_t> rows;
+  const int64_t base = (int64_t)rank * block;
+  for (int p = 0; p < world; p++) {
+    off_out[p] = (int64_t)rows.size();
+    if (p == rank) continue;
+    const uint32_t *m = masks + (size_t)p * words;
+    for (int64_t i = 0; i < rows_local; i++) {
+      const int64_t c = base + i;
+      if (m[c >> 5] >> (c & 31) & 1u) rows.push_back((uint32_t)i);
+    }
+  }
+  off_out[world] = (int64_t)rows.size();
+  uint32_t *out = (uint32_t *)malloc(std::max<size_t>(4, rows.size() * 4));
+  if (!out) return GCNB_E_UNSUPPORTED;
+  if (!rows.empty()) memcpy(out, rows.data(), rows.size() * 4);
+  *rows_out = out;
+  return 0;
+}
+
+// Halo exchange for the slab gather (graphs whose [N x d] matrix is too large to ship whole).  From the
+// column ids of this rank's CSR block (slot layout: column c = row c % block of rank c / block) every rank marks the
+// columns it references, the marks are all-gathered (n_global / 8 bytes per rank), and each rank keeps, per peer, the list
+// of its OWN rows that peer references.  From then on gcnb_comm_gather_slabs*_f32 calls whose slab is [block x dim] push
+// only those rows.  Sender-side decision: the lists are used when they hold at most max_fraction of what the full push
+// sends (GCNB_HALO=0 / 1 forces it off / on); a receiver gets every row it references either way.  Peer-memory mode only
+// (the NCCL all-gather fallback ships whole slabs).  info: {active, rows sent per exchange, rows of the full push
+// ((world - 1) x rows_local), rows this rank references in other ranks' blocks}.
+int gcnb_comm_halo_setup(gcnb_comm *c, const uint32_t *d_indices, int64_t nnz, int64_t rows_local, int64_t block,
+                         double max_fraction, int64_t info[4], gcnb_stream_t s) {
+  if (!c || (nnz > 0 && !d_indices) || nnz < 0 || block <= 0 || rows_local < 0 || rows_local > block) return GCNB_E_BADARG;
+  if (info) info[0] = info[1] = info[2] = info[3] = 0;
+  cudaFree(c->d_halo_rows);
+  c->d_halo_rows = nullptr;
+  c->halo = false;
+  if (c->world == 1 || c->world > kMaxWorld) return 0;
+  cudaStream_t st = as_stream(s);
+  const int64_t words = ((int64_t)c->world * block + 31) / 32;
+  uint32_t *d_masks = nullptr;
+  GCNB_CHECK(cudaMalloc((void **)&d_masks, (size_t)words * 4 * c->world));
+  uint32_t *mine = d_masks + (size_t)c->rank * words;
+  GCNB_CHECK(cudaMemsetAsync(mine, 0, (size_t)words * 4, st));
+  if (nnz > 0) {
+    halo_mask_kernel<<<(int)std::min<int64_t>((nnz + 255) / 256, 4096), 256, 0, st>>>(d_indices, nnz, mine);
+    if (cudaPeekAtLastError() != cudaSuccess) {
+      cudaFree(d_masks);
+      return (int)cudaGetLastError();
+    }
+  }
+  int rc = nccl_rc(nccl().AllGather(mine, d_masks, (size_t)words, ncclUint32, c->comm, st));
+  std::vector<uint32_t> masks((size_t)words * c->world);
+  if (!rc) rc = (int)cudaMemcpyAsync(masks.data(), d_masks, masks.size() * 4, cudaMemcpyDeviceToHost, st);
+  if (!rc) rc = (int)cudaStreamSynchronize(st);
+  cudaFree(d_masks);
+  if (rc) return rc;
+  uint32_t *rows = nullptr;
+  HaloOffsets off{};
+  rc = gcnb_halo_lists_from_masks(masks.data(), c->world, c->rank, words, block, rows_local, &rows, off.off);
+  if (rc) return rc;
+  int64_t need = 0;  // rows of OTHER ranks' blocks that this rank references
+  {
+    const uint32_t *m = masks.data() + (size_t)c->rank * words;
+    const int64_t lo = (int64_t)c->rank * block, hi = lo + block;
+    for (int64_t w = 0; w < words; w++) {
+      uint32_t v = m[w];
+      while (v) {
+        const int64_t col = w * 32 + __builtin_ctz(v);
+        v &= v - 1;
+        if (col < lo || col >= hi) need++;
+      }
+    }
+  }
+  const int64_t total = off.off[c->world], full = (int64_t)(c->world - 1) * rows_local;
+  const char *env = getenv("GCNB_HALO");
+  const bool want = env ? atoi(env) != 0 : (double)total <= max_fraction * (double)full;
+  if (info) {
+    info[1] = total;
+    info[2] = full;
+    info[3] = need;
+  }
+  if (want && c->p2p) {
+    rc = (int)cudaMalloc((void **)&c->d_halo_rows, std::max<size_t>(4, (size_t)total * 4));
+    if (!rc && total > 0) rc = (int)cudaMemcpy(c->d_halo_rows, rows, (size_t)total * 4, cudaMemcpyHostToDevice);
+    if (!rc) {
+      c->halo = true;
+      c->halo_block = block;
+      c->halo_rows_local = rows_local;
+      c->halo_send_total = total;
+      c->halo_need_total = need;
+      c->halo_off = off;
+      if (info) info[0] = 1;
+    }
+  }
+  free(rows);
+  return rc;
+}
+
+int gcnb_comm_halo_active(const gcnb_comm *c) { return c && c->halo ? 1 : 0; }
 
 int gcnb_comm_rank(const gcnb_comm *c) { return c ? c->rank : 0; }
 int gcnb_comm_world(const gcnb_comm *c) { return c ? c->world : 1; }

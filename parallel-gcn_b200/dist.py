@@ -394,7 +394,7 @@ def make_comm(eng, dist, rank, world, dev):
 
 
 def scaleout_record(rank, world, local_rank, dist, n=4000000, block=4000, intra=230.0, inter=58.0, reflect=2048, sigma=1.0,
-                    features=128, classes=47, hidden=16, steps=5, warmup=2, seed=20240229):
+                    features=128, classes=47, hidden=16, steps=5, warmup=2, seed=20240229, inter_window=0):
     """Scale-out workload (BASELINE.json configs[4]; north_star: >= 5x 1-GPU throughput on 8 GPUs for a >= 1B-edge synthetic
     graph): a symmetric community graph with 1.01e9 CSR entries generated ROW-LOCALLY (every rank builds only its row block,
     gcnb_synth_sym_rows), dense features, 2-layer GCN hidden 16, through the native (row-partitioned) engine.  Returns the
@@ -408,7 +408,7 @@ def scaleout_record(rank, world, local_rank, dist, n=4000000, block=4000, intra=
     r0, r1 = min(n, rank * B), min(n, (rank + 1) * B)
     rows = r1 - r0
     t0 = time.perf_counter()
-    g_indptr, g_indices = eng.synth_sym_rows(n, r0, rows, block, intra, inter, reflect, sigma, seed)
+    g_indptr, g_indices = eng.synth_sym_rows(n, r0, rows, block, intra, inter, reflect, sigma, seed, inter_window=inter_window)
     t_graph = time.perf_counter() - t0
     deg_local = np.diff(g_indptr.astype(np.int64)).astype(np.uint32)
     if world > 1:
@@ -457,10 +457,14 @@ def scaleout_record(rank, world, local_rank, dist, n=4000000, block=4000, intra=
     r = g.timed_epochs(steps, with_eval=True, time_graphsum=True)
     torch.cuda.synchronize()
     clk = clocks.stop() if clocks is not None else None
-    ms = torch.tensor([r["ms"], r["graphsum_ms"] / max(1, r["graphsum_calls"]), t_create * 1e3, t_gen * 1e3, t_graph * 1e3],
-                      dtype=torch.float64, device=dev)
+    ms = torch.tensor([r["ms"], r["graphsum_ms"] / max(1, r["graphsum_calls"]), t_create * 1e3, t_gen * 1e3, t_graph * 1e3,
+                       r.get("graphsum_exchange_ms", 0.0) / max(1, r["graphsum_calls"])], dtype=torch.float64, device=dev)
+    halo = g.halo_info() if world > 1 else None
+    halo_sum = torch.tensor([halo["active"], halo["rows_sent"], halo["rows_full_push"], halo["rows_needed"]] if halo else [0, 0, 0, 0],
+                            dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(halo_sum)
     line = None
     if rank == 0:
         free_b, total_b = torch.cuda.mem_get_info()
@@ -473,7 +477,11 @@ def scaleout_record(rank, world, local_rank, dist, n=4000000, block=4000, intra=
                 "gen_ms": float(ms[3]), "graph_gen_ms": float(ms[4]), "deg_max": int(deg_global.max()),
                 "deg_mean": float(nnz_global / n), "train": last[0] if last else None, "val": last[1] if last else None,
                 "gpu_mem_used_gb_rank0": (total_b - free_b) / 2**30, "steps": steps, "warmup": warmup, "clocks": clk,
-                "host_cores": os.cpu_count()}
+                "host_cores": os.cpu_count(), "inter_window": inter_window, "graphsum_exchange_mean_ms": float(ms[5]),
+                "halo": None if world == 1 else {
+                    "ranks_active": int(halo_sum[0]), "rows_sent_per_exchange_all_ranks": int(halo_sum[1]),
+                    "rows_of_full_slab_push_all_ranks": int(halo_sum[2]), "rows_needed_all_ranks": int(halo_sum[3]),
+                    "fraction_of_full_push": float(halo_sum[1] / max(1.0, float(halo_sum[2])))}}
     g.close()
     if comm is not None:
         comm.close()

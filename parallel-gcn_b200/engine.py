@@ -72,6 +72,8 @@ _sig("gcnb_gcn_graphsum_exchange_ms", C.c_double, [P])
 _sig("gcnb_host_free", None, [P])
 _sig("gcnb_sweep_run", I32, [P, P, I64, I32, P, P])
 _sig("gcnb_reorder_communities", I32, [I64, P, P, I32, C.c_uint64, P, P])
+_sig("gcnb_partition_communities", I32, [I64, P, P, I32, I32, C.c_uint64, C.c_double, P, P, P, P])
+_sig("gcnb_gcn_halo_info", I32, [P, P])
 _sig("gcnb_permute_csr", I32, [I64, P, P, P, P, P])
 _sig("gcnb_permute_rows", I32, [I64, I64, P, P, P])
 _sig("gcnb_unpermute_rows", I32, [I64, I64, P, P, P])
@@ -168,6 +170,61 @@ def reorder_communities(indptr, indices, max_sweeps=0, seed=1):
     return new_of_old, int(nc.value)
 
 
+def partition_communities(indptr, indices, world, max_sweeps=0, seed=1, tolerance=0.0):
+    """balanced, community-aligned row partition (gcnb_partition_communities): returns (new_of_old into the padded id space
+    [0, world * block), block, rows per rank, stats dict)"""
+    n = len(indptr) - 1
+    new_of_old, block, rows, stats = np.empty(n, np.uint32), I64(0), (I64 * world)(), (I64 * 4)()
+    check(lib.gcnb_partition_communities(n, _p(indptr), _p(indices), int(world), int(max_sweeps), int(seed), float(tolerance),
+                                         _p(new_of_old), C.byref(block), rows, stats))
+    return new_of_old, int(block.value), [int(r) for r in rows], dict(
+        communities=int(stats[0]), cut_entries=int(stats[1]), cut_entries_equal_row_blocks=int(stats[2]),
+        max_rank_entries=int(stats[3]), total_entries=int(indptr[-1]))
+
+
+def pad_dataset(ds, n_pad):
+    """the dataset with isolated dummy nodes appended up to n_pad nodes: a self entry in the graph, no label, no split, a
+    zero feature row (fixed-width datasets keep their width so that the all-columns detection still holds)"""
+    n = ds.num_nodes
+    extra = n_pad - n
+    assert extra >= 0
+    if extra == 0:
+        return ds
+    g_indptr = np.concatenate([ds.g_indptr, ds.g_indptr[-1] + np.arange(1, extra + 1, dtype=np.uint32)]).astype(np.uint32)
+    g_indices = np.concatenate([ds.g_indices, np.arange(n, n_pad, dtype=np.uint32)])
+    flen = np.diff(ds.f_indptr.astype(np.int64))
+    if len(flen) and (flen == flen[0]).all() and flen[0] > 0:
+        w = int(flen[0])
+        f_indptr = (np.arange(n_pad + 1, dtype=np.int64) * w).astype(np.uint32)
+        f_indices = np.concatenate([ds.f_indices, np.tile(ds.f_indices[:w], extra)])
+        f_value = np.concatenate([ds.f_value, np.zeros(extra * w, np.float32)])
+    else:
+        f_indptr = np.concatenate([ds.f_indptr, np.full(extra, ds.f_indptr[-1], np.uint32)])
+        f_indices, f_value = ds.f_indices, ds.f_value
+    out = HostDataset(g_indptr=g_indptr, g_indices=g_indices, f_indptr=f_indptr, f_indices=f_indices, f_value=f_value,
+                      label=np.concatenate([ds.label, np.full(extra, -1, np.int32)]),
+                      split=np.concatenate([ds.split, np.zeros(extra, np.uint32)]), input_dim=ds.input_dim,
+                      output_dim=ds.output_dim)
+    if getattr(ds, "split_counts", None) is not None:
+        out.split_counts = ds.split_counts
+    return out
+
+
+def balanced_partition(ds, world, max_sweeps=0, seed=1, tolerance=0.0):
+    """Dataset laid out for `world` ranks by gcnb_partition_communities: rank r's nodes occupy the ids
+    [r * block, r * block + rows[r]) of the returned dataset (world * block nodes; the ids in between are isolated dummy nodes
+    without label or split), so dist.partition_dataset(out, r, world) hands every rank the same number of CSR entries and
+    whole communities.  Returns (dataset, new_of_old, info); per-node outputs go back with permute_rows(..., inverse=True)
+    on the first num_nodes entries of new_of_old."""
+    new_of_old, block, rows, stats = partition_communities(ds.g_indptr, ds.g_indices, world, max_sweeps, seed, tolerance)
+    n_pad = world * block
+    used = np.zeros(n_pad, bool)
+    used[new_of_old] = True
+    full = np.concatenate([new_of_old, np.flatnonzero(~used).astype(np.uint32)])
+    out = permute_dataset(pad_dataset(ds, n_pad), full)
+    return out, new_of_old, dict(stats, block=block, rows=rows, world=world)
+
+
 def permute_rows(a, new_of_old, inverse=False):
     """rows of `a` moved to their new positions (inverse: back to the original numbering)"""
     a = np.ascontiguousarray(a)
@@ -224,6 +281,10 @@ class Comm:
         check(lib.gcnb_comm_create(self.rank, self.world, buf, C.byref(h)))
         self.h = h
 
+    def gather_mode(self):
+        """0 single rank, 1 NCCL all-gather, 2 peer-memory push (valid once a model has set the exchange up)"""
+        return int(lib.gcnb_comm_gather_mode(self.h))
+
     def close(self):
         if getattr(self, "h", None) and lib is not None:
             lib.gcnb_comm_destroy(self.h)
@@ -278,6 +339,12 @@ class GCN:
 
     def eval(self, split):
         return self._pair(lib.gcnb_gcn_eval, int(split))
+
+    def halo_info(self):
+        """row-partitioned models: dict(active, rows_sent, rows_full_push, rows_needed) of the halo exchange"""
+        out = (I64 * 4)()
+        check(lib.gcnb_gcn_halo_info(self.h, out))
+        return dict(active=int(out[0]), rows_sent=int(out[1]), rows_full_push=int(out[2]), rows_needed=int(out[3]))
 
     def run(self):
         out = (F32 * 4)()

@@ -174,6 +174,7 @@ class GCN {
   size_t launches_total() const;
   void set_time_graphsum(bool on);                        // event pair around every GraphSum launch
   void graphsum_timing(double *ms_total, size_t *calls) const;
+  void halo_info(int64_t out[4]) const;  // partitioned: {halo exchange active, rows sent per exchange, rows of a full push, rows needed}
   double graphsum_exchange_ms() const;  // partitioned: summed time from the start of a GraphSum call until the peers' slabs have landed
   float timed_epochs(natural n_epochs, bool with_eval);   // ms between CUDA events on the engine stream
   natural epochs_run() const;

@@ -381,6 +381,12 @@ int gcnb_sweep_run(const gcnb_dataset *d, const gcnb_sweep_trial *trials, int64_
   return 0;
 }
 
+int gcnb_gcn_halo_info(const gcnb_gcn *g, int64_t out[4]) {
+  if (!g || !out) return GCNB_E_BADARG;
+  g->gcn->halo_info(out);
+  return 0;
+}
+
 int gcnb_gcn_destroy(gcnb_gcn *g) {
   delete g;
   return 0;

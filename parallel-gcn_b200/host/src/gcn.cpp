@@ -96,6 +96,7 @@ struct GCNLayer {
 };
 
 struct GCNEngineState {
+  int64_t halo_info[4] = {0, 0, 0, 0};  // partitioned: {halo exchange active, rows sent, rows of a full push, rows needed}
   GCNRngContext rng;        // this model's Philox consumption history and seed (bound to the calling thread by RngScope)
   bool concurrent = false;  // other models may be running on other host threads: no process-wide timers
   cudaStream_t stream = nullptr;
@@ -533,6 +534,11 @@ void GCN::init(bool quiet, const natural *h_graph_indptr, const natural *h_graph
       if (st->ax_planned) dmax = std::max(dmax, F);
     }
     GCNB_CALL(gcnb_comm_gather_setup(st->comm, (int64_t)gcnb_comm_world(st->comm) * st->block * dmax));
+    // halo exchange: ship to a peer only the rows its block references, when that is at most half of the slab
+    // (graphs with locality / community-aligned partitions; a graph whose every remote row is referenced keeps the push)
+    GCNB_CALL(gcnb_comm_halo_setup(st->comm, dev_data.dev_graph_index.dev_indices.get(),
+                                   (int64_t)dev_data.dev_graph_index.indices_size, (int64_t)N, (int64_t)st->block, 0.5,
+                                   st->halo_info, st->stream));
     for (GCNLayer &ly : st->layers)  // padding rows are shipped by the all-gather: keep them defined
       for (const shared_ptr<Variable> &v : {ly.pre, ly.z}) {
         if (v->dev_data.get()) CHECK_CUDA_ERROR(cudaMemset(v->dev_data.get(), 0, (size_t)v->size * sizeof(real)));
@@ -887,6 +893,9 @@ void GCN::set_time_graphsum(bool on) {
   st->gs_calls = 0;
 }
 double GCN::graphsum_exchange_ms() const { return st->gs_exchange_ms_total; }
+void GCN::halo_info(int64_t out[4]) const {
+  for (int i = 0; i < 4; i++) out[i] = st->halo_info[i];
+}
 void GCN::graphsum_timing(double *ms_total, size_t *calls) const {
   *ms_total = st->gs_ms_total;
   *calls = st->gs_calls;

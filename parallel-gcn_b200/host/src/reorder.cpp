@@ -11,6 +11,7 @@
 // the graph through its random long-range edges.
 #include <algorithm>
 #include <atomic>
+#include <cmath>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
@@ -50,15 +51,12 @@ void parallel_rows(int64_t n, const uint32_t *indptr, F fn) {  // contiguous row
   for (auto &x : th) x.join();
 }
 
-}  // namespace
-
-extern "C" {
-
-int gcnb_reorder_communities(int64_t n, const uint32_t *indptr, const uint32_t *indices, int max_sweeps, uint64_t seed,
-                             uint32_t *new_of_old, int64_t *n_communities) {
-  if (n < 0 || n > 0xffffffffll || !indptr || (!indices && n && indptr[n]) || !new_of_old) return GCNB_E_BADARG;
+// label[i] = community of node i (a node id of that community)
+void propagate_labels(int64_t n, const uint32_t *indptr, const uint32_t *indices, int max_sweeps, uint64_t seed,
+                      std::vector<uint32_t> &label) {
   if (max_sweeps <= 0) max_sweeps = 8;
-  std::vector<uint32_t> label((size_t)n), next((size_t)n);
+  std::vector<uint32_t> next((size_t)n);
+  label.resize((size_t)n);
   std::iota(label.begin(), label.end(), 0u);
   for (int sweep = 0; sweep < max_sweeps; sweep++) {
     std::atomic<int64_t> changed_total(0);
@@ -97,7 +95,28 @@ int gcnb_reorder_communities(int64_t n, const uint32_t *indptr, const uint32_t *
     label.swap(next);
     if (changed_total.load() * 200 < n) break;  // < 0.5 % of the nodes moved
   }
-  // communities in order of their smallest member, members in their original order (stable => deterministic)
+}
+
+// nodes community by community: communities in order of their smallest member, members in their original order
+// (stable => deterministic); order[k] = old id of the k-th node
+void community_order(int64_t n, const std::vector<uint32_t> &label, std::vector<uint32_t> &order) {
+  std::vector<uint32_t> first((size_t)n, 0xffffffffu);
+  for (int64_t i = 0; i < n; i++)
+    if (first[label[i]] == 0xffffffffu) first[label[i]] = (uint32_t)i;
+  order.resize((size_t)n);
+  std::iota(order.begin(), order.end(), 0u);
+  std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return first[label[x]] < first[label[y]]; });
+}
+
+}  // namespace
+
+extern "C" {
+
+int gcnb_reorder_communities(int64_t n, const uint32_t *indptr, const uint32_t *indices, int max_sweeps, uint64_t seed,
+                             uint32_t *new_of_old, int64_t *n_communities) {
+  if (n < 0 || n > 0xffffffffll || !indptr || (!indices && n && indptr[n]) || !new_of_old) return GCNB_E_BADARG;
+  std::vector<uint32_t> label;
+  propagate_labels(n, indptr, indices, max_sweeps, seed, label);
   std::vector<uint32_t> first((size_t)n, 0xffffffffu);
   for (int64_t i = 0; i < n; i++)
     if (first[label[i]] == 0xffffffffu) first[label[i]] = (uint32_t)i;
@@ -110,6 +129,92 @@ int gcnb_reorder_communities(int64_t n, const uint32_t *indptr, const uint32_t *
     if (k == 0 || label[order[k]] != label[order[k - 1]]) comms++;
   }
   if (n_communities) *n_communities = comms;
+  return 0;
+}
+
+// Balanced, community-aligned row partition for the multi-GPU engine (north_star: "METIS-style").  The
+// engine's ranks own contiguous row blocks and exchange the rows other ranks reference, so a good partition (i) gives every
+// rank the same amount of GraphSum work -- CSR entries, not rows: degrees are skewed -- and (ii) cuts few edges, i.e. puts
+// rank boundaries on community borders.  Communities come from the label propagation above; nodes are laid out community by
+// community and the stream is cut at the entry-count targets k * nnz / world, each cut snapped to the nearest community
+// border when one lies within `tolerance` (fraction of a rank's share, 0 = 0.1) of the target and placed inside the
+// community otherwise (a community larger than a rank's share has to be split).  Rank r receives the ids
+// [r * block, r * block + rows[r]) with block = the largest row count rounded up to a multiple of 4 (the engine's slab
+// size); the ids in between are padding (isolated dummy nodes when the caller materialises them).
+// stats: {communities, entries whose two ends lie on different ranks, the same count for the plain contiguous partition into
+// equal row blocks of the GIVEN numbering, largest entry count of a rank}.
+int gcnb_partition_communities(int64_t n, const uint32_t *indptr, const uint32_t *indices, int world, int max_sweeps,
+                               uint64_t seed, double tolerance, uint32_t *new_of_old, int64_t *block_out,
+                               int64_t *rows_out /* [world] */, int64_t stats[4]) {
+  if (n < 1 || n > 0xffffffffll || world < 1 || !indptr || (!indices && indptr[n]) || !new_of_old || !block_out || !rows_out)
+    return GCNB_E_BADARG;
+  if (tolerance <= 0) tolerance = 0.1;
+  std::vector<uint32_t> label, order;
+  propagate_labels(n, indptr, indices, max_sweeps, seed, label);
+  community_order(n, label, order);
+  const uint64_t nnz = indptr[n];
+  // prefix entry counts in the new order; community borders
+  std::vector<uint64_t> pre((size_t)n + 1, 0);
+  std::vector<int64_t> border;  // positions k where a community starts (k = 0 included), plus n
+  for (int64_t k = 0; k < n; k++) {
+    pre[k + 1] = pre[k] + (indptr[order[k] + 1] - indptr[order[k]]);
+    if (k == 0 || label[order[k]] != label[order[k - 1]]) border.push_back(k);
+  }
+  const int64_t comms = (int64_t)border.size();
+  border.push_back(n);
+  std::vector<int64_t> cut((size_t)world + 1, n);
+  cut[0] = 0;
+  const double share = (double)nnz / world;
+  for (int r = 1; r < world; r++) {
+    const uint64_t target = (uint64_t)((double)nnz * r / world);
+    int64_t k = std::lower_bound(pre.begin(), pre.end(), target) - pre.begin();  // first position with pre >= target
+    k = std::min<int64_t>(std::max<int64_t>(k, cut[r - 1]), n);
+    // nearest community border
+    auto it = std::lower_bound(border.begin(), border.end(), k);
+    int64_t best = -1;
+    double best_d = 0;
+    for (auto c : {it, it == border.begin() ? it : it - 1}) {
+      if (c == border.end()) continue;
+      const double d = std::fabs((double)pre[*c] - (double)target);
+      if (*c >= cut[r - 1] && (best < 0 || d < best_d)) best = *c, best_d = d;
+    }
+    cut[r] = (best >= 0 && best_d <= tolerance * share) ? best : k;
+  }
+  int64_t max_rows = 0;
+  uint64_t max_nnz = 0;
+  for (int r = 0; r < world; r++) {
+    rows_out[r] = cut[r + 1] - cut[r];
+    max_rows = std::max(max_rows, rows_out[r]);
+    max_nnz = std::max<uint64_t>(max_nnz, pre[cut[r + 1]] - pre[cut[r]]);
+  }
+  const int64_t block = (max_rows + 3) / 4 * 4;
+  if ((uint64_t)block * (uint64_t)world > 0xffffffffull) return GCNB_E_UNSUPPORTED;
+  std::vector<uint32_t> rank_of((size_t)n);
+  for (int r = 0; r < world; r++)
+    for (int64_t k = cut[r]; k < cut[r + 1]; k++) {
+      new_of_old[order[k]] = (uint32_t)(r * block + (k - cut[r]));
+      rank_of[order[k]] = (uint32_t)r;
+    }
+  *block_out = block;
+  if (stats) {
+    const int64_t eq = (n + world - 1) / world;  // the plain partition: equal contiguous row blocks of the given numbering
+    std::atomic<int64_t> cut_new(0), cut_old(0);
+    parallel_rows(n, indptr, [&](int64_t a, int64_t b) {
+      int64_t cn = 0, co = 0;
+      for (int64_t i = a; i < b; i++)
+        for (uint32_t e = indptr[i]; e < indptr[i + 1]; e++) {
+          const uint32_t j = indices[e];
+          cn += rank_of[i] != rank_of[j];
+          co += (i / eq) != (int64_t)(j / eq);
+        }
+      cut_new.fetch_add(cn);
+      cut_old.fetch_add(co);
+    });
+    stats[0] = comms;
+    stats[1] = cut_new.load();
+    stats[2] = cut_old.load();
+    stats[3] = (int64_t)max_nnz;
+  }
   return 0;
 }
 

@@ -209,8 +209,20 @@ int gcnb_synth_labels(int64_t n, int classes, double frac_train, double frac_val
 int gcnb_synth_sym_rows(int64_t n, int64_t row0, int64_t rows, int64_t block_size, double mean_intra, double mean_inter,
                         int n_reflect, double sigma, uint64_t seed, uint32_t **indptr_out, uint32_t **indices_out,
                         int64_t *nnz_out) {
+  return gcnb_synth_sym_rows_local(n, row0, rows, block_size, mean_intra, mean_inter, n_reflect, 0, sigma, seed, indptr_out,
+                                   indices_out, nnz_out);
+}
+
+// ... with inter_window > 0 the edges that leave a community stay NEAR it instead: the candidates of node i across
+// communities are i +- d_k for n_reflect / 2 fixed shifts d_k in [block_size, inter_window] (symmetric: i is the
+// candidate of i + d_k under -d_k), so a row block references only the rows within inter_window of its borders -- the
+// structure a METIS-style partition of a citation / co-purchase graph has, and the case the halo exchange is for.
+int gcnb_synth_sym_rows_local(int64_t n, int64_t row0, int64_t rows, int64_t block_size, double mean_intra, double mean_inter,
+                              int n_reflect, int64_t inter_window, double sigma, uint64_t seed, uint32_t **indptr_out,
+                              uint32_t **indices_out, int64_t *nnz_out) {
   if (n <= 1 || n > 0xffffffffll || row0 < 0 || rows < 0 || row0 + rows > n || block_size < 2 || n_reflect < 0 ||
-      mean_intra < 0 || mean_inter < 0 || !indptr_out || !indices_out || !nnz_out)
+      mean_intra < 0 || mean_inter < 0 || !indptr_out || !indices_out || !nnz_out ||
+      (inter_window != 0 && inter_window < block_size))
     return GCNB_E_BADARG;
   const double p_in = std::min(1.0, mean_intra / (double)block_size);
   const double p_out = n_reflect > 0 ? std::min(1.0, mean_inter / (double)n_reflect) : 0.0;
@@ -222,6 +234,13 @@ int gcnb_synth_sym_rows(int64_t n, int64_t row0, int64_t rows, int64_t block_siz
   });
   std::vector<int64_t> refl((size_t)n_reflect);
   for (int k = 0; k < n_reflect; k++) refl[k] = (int64_t)(rnd(seed, 12, (uint64_t)k) % (uint64_t)n);
+  std::vector<int64_t> shift;  // inter_window > 0: +-d for n_reflect / 2 distinct shifts d
+  if (inter_window > 0) {
+    const uint64_t span = (uint64_t)(inter_window - block_size + 1);
+    for (int k = 0; k < n_reflect / 2; k++) shift.push_back(block_size + (int64_t)(rnd(seed, 14, (uint64_t)k) % span));
+    std::sort(shift.begin(), shift.end());
+    shift.erase(std::unique(shift.begin(), shift.end()), shift.end());
+  }
   const uint64_t pair_seed = mix64(seed ^ 0x5eed5eedull);
   auto accept = [&](uint64_t i, uint64_t j, double p) {
     const uint64_t lo = std::min(i, j), hi = std::max(i, j);
@@ -242,11 +261,19 @@ int gcnb_synth_sym_rows(int64_t n, int64_t row0, int64_t rows, int64_t block_siz
         for (int64_t j = b0; j < b1; j++)
           if (j != i && accept((uint64_t)i, (uint64_t)j, p_in)) row.push_back((uint32_t)j);
         const size_t n_in = row.size();
-        for (int k = 0; k < n_reflect; k++) {
-          int64_t j = refl[k] - i;
-          if (j < 0) j += n;
-          if (j == i || (j >= b0 && j < b1)) continue;
-          if (accept((uint64_t)i, (uint64_t)j, p_out)) row.push_back((uint32_t)j);
+        if (inter_window > 0) {
+          for (const int64_t d : shift)
+            for (const int64_t j : {i - d, i + d}) {
+              if (j < 0 || j >= n || (j >= b0 && j < b1)) continue;
+              if (accept((uint64_t)i, (uint64_t)j, p_out)) row.push_back((uint32_t)j);
+            }
+        } else {
+          for (int k = 0; k < n_reflect; k++) {
+            int64_t j = refl[k] - i;
+            if (j < 0) j += n;
+            if (j == i || (j >= b0 && j < b1)) continue;
+            if (accept((uint64_t)i, (uint64_t)j, p_out)) row.push_back((uint32_t)j);
+          }
         }
         std::sort(row.begin() + n_in, row.end());
         row.erase(std::unique(row.begin() + n_in, row.end()), row.end());

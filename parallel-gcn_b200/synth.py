@@ -28,6 +28,7 @@ _sig("gcnb_host_free", None, [P])
 _sig("gcnb_synth_dense_features", I32, [I64, I32, C.c_uint64, P, P, P])
 _sig("gcnb_synth_labels", I32, [I64, I32, C.c_double, C.c_double, C.c_uint64, P, P])
 _sig("gcnb_synth_sym_rows", I32, [I64, I64, I64, I64, C.c_double, C.c_double, I32, C.c_double, C.c_uint64, P, P, P])
+_sig("gcnb_synth_sym_rows_local", I32, [I64, I64, I64, I64, C.c_double, C.c_double, I32, I64, C.c_double, C.c_uint64, P, P, P])
 _sig("gcnb_synth_graph_values", I32, [P, P, I64, I64, P, P])
 _sig("gcnb_synth_dense_features_uniform", I32, [I64, I32, C.c_uint64, C.c_uint64, P, P, P])
 
@@ -112,11 +113,12 @@ def _adopt(ptr_, ctype, n):
 
 
 def synth_sym_rows(n, row0, rows, block_size=4000, mean_intra=200.0, mean_inter=50.0, n_reflect=2048, sigma=1.0,
-                   seed=19990304):
-    """rows [row0, row0 + rows) of the row-local symmetric community graph (gcnb_synth_sym_rows); global column ids"""
+                   seed=19990304, inter_window=0):
+    """rows [row0, row0 + rows) of the row-local symmetric community graph (gcnb_synth_sym_rows); global column ids.
+    inter_window > 0: the edges that leave a community stay within that many rows of it (gcnb_synth_sym_rows_local)"""
     ip, ix, nnz = P(), P(), I64(0)
-    check(lib.gcnb_synth_sym_rows(n, row0, rows, block_size, mean_intra, mean_inter, n_reflect, sigma, seed, C.byref(ip),
-                                  C.byref(ix), C.byref(nnz)))
+    check(lib.gcnb_synth_sym_rows_local(n, row0, rows, block_size, mean_intra, mean_inter, n_reflect, int(inter_window), sigma,
+                                        seed, C.byref(ip), C.byref(ix), C.byref(nnz)))
     return _adopt(ip, C.c_uint32, rows + 1), _adopt(ix, C.c_uint32, nnz.value)
 
 

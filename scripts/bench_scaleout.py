@@ -36,6 +36,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--seed", type=int, default=20240229)
+    ap.add_argument("--inter-window", type=int, default=0, help="> 0: inter-community edges stay within this many rows (halo-exchange case)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -53,7 +54,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     line = dmod.scaleout_record(rank, world, local_rank, dist, n=args.n, block=args.block, intra=args.intra, inter=args.inter,
                                 reflect=args.reflect, sigma=args.sigma, features=args.features, classes=args.classes,
-                                hidden=args.hidden, steps=args.steps, warmup=args.warmup, seed=args.seed)
+                                hidden=args.hidden, steps=args.steps, warmup=args.warmup, seed=args.seed, inter_window=args.inter_window)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -64,3 +64,23 @@ def test_uniform_features_are_offset_consistent(eng):
     fp2, fi2, fv2 = eng.synth_dense_features_uniform(40, 12, 5, 60 * 12)
     assert np.array_equal(fv[60 * 12:], fv2) and np.array_equal(fi2[:12], np.arange(12, dtype=np.uint32))
     assert fp[-1] == 1200 and abs(float(fv.mean())) < 0.15 and 0.8 < float(fv.std()) < 1.2
+
+
+def test_local_inter_community_edges_stay_inside_the_window(eng):
+    """gcnb_synth_sym_rows_local: edges that leave a community reach at most inter_window rows -- the halo-exchange case"""
+    n, win = 12000, 1500
+    kw = dict(block_size=500, mean_intra=30, mean_inter=8, n_reflect=256, sigma=1.0, seed=7, inter_window=win)
+    ip, ix = eng.synth_sym_rows(n, 0, n, **kw)
+    ip64 = ip.astype(np.int64)
+    rows = np.repeat(np.arange(n), np.diff(ip64))
+    key, keyT = rows * n + ix.astype(np.int64), ix.astype(np.int64) * n + rows
+    assert np.array_equal(np.sort(key), np.sort(keyT))                      # symmetric
+    assert np.array_equal(ix[ip64[:-1]], np.arange(n, dtype=np.uint32))     # self entry first
+    leaves = (rows // 500) != (ix // 500)
+    assert 0.05 < leaves.mean() < 0.4 and np.abs(rows - ix.astype(np.int64))[leaves].max() <= win
+    for r0, r1 in ((0, 4000), (4000, n)):                                    # row blocks generated on their own
+        bp, bx = eng.synth_sym_rows(n, r0, r1 - r0, **kw)
+        assert np.array_equal(bx, ix[ip64[r0]:ip64[r1]])
+    # a row block references only the rows within the window of its borders
+    blk = ix[ip64[4000]:ip64[8000]].astype(np.int64)
+    assert blk.min() >= 4000 - win and blk.max() < 8000 + win
