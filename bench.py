@@ -291,6 +291,63 @@ def graphsum_worst_case(eng, ds, w, d, peak, steps=5):
             "create_plus_finish_setup_s": setup_s}
 
 
+def small_config_record(eng, name):
+    """BASELINE.json configs[0] / [1]: a shipped dataset with the reference's Part-1 defaults (2 layers, hidden 16, dropout
+    .5/.5, 100 epochs): device-timed epochs (train_epoch + eval(2)) and the reference-style GCN::run() average"""
+    from tests.util import pubmed_root
+    ds = eng.parse_dataset(pubmed_root(ROOT) if name == "pubmed" else ROOT, name)
+    g = eng.GCN(ds, epochs=100)
+    g.train_epoch(); g.eval(2)
+    r = g.timed_epochs(100, with_eval=True)
+    out = dict(config=name + (" (shipped graph/split, synthetic svmlight features)" if name == "pubmed" else ""),
+               model="L2 H16 dropout .5/.5", ms_per_epoch=r["ms"] / 100, launches_per_step=r["launches"] / 100)
+    g.close()
+    g = eng.GCN(ds, epochs=100)
+    t0 = time.perf_counter()
+    rr = g.run()
+    out.update(run_avg_epoch_ms_reference_style=rr["avg_epoch_ms"], run_wall_s=time.perf_counter() - t0, last_val_acc=rr["last_val_acc"])
+    g.close()
+    return out
+
+
+def wide_config_record(eng, ds, w, steps=5):
+    """BASELINE.json configs[3]: the Reddit-shape graph with parameters/parameters_reddit.txt's model (hidden 600, dropouts
+    0.0 / 0.1, weight decay 5e-5)"""
+    g = eng.GCN(ds, hidden_dims=(600,), dropouts=(0.0, 0.1), lr=0.01, weight_decay=5e-5, seed=w["seed"])
+    g.finish_setup()  # attach the background-built GraphSum representation before timing
+    for _ in range(2):
+        g.train_epoch(); g.eval(2)
+    r = g.timed_epochs(steps, with_eval=True, time_graphsum=True)
+    out = dict(config="reddit_shape H600 (parameters_reddit.txt model)", ms_per_epoch=r["ms"] / steps,
+               graphsum_ms_mean=r["graphsum_ms"] / max(1, r["graphsum_calls"]), graphsum_calls_per_step=r["graphsum_calls"] / steps,
+               launches_per_step=r["launches"] / steps, paths=g.path_info(), train=g.train_epoch(), val=g.eval(2),
+               note="input dropout 0: layer 0 runs on the propagated features A_hat X in both directions (no GraphSum at width 600); "
+                    "X W0 and X^T dH through the exact-split tcgen05 GEMM")
+    g.close()
+    return out
+
+
+def tuning_sweep_record(eng, dataset="cora", workers=8):
+    """The reference's tuning sweep (test/tuning_accuracy.cpp:56-196) as a throughput workload: the hidden-16 slice of its
+    2-layer grid (dropout {0,.2,.4,.6}^2 x weight decay {5e-5,5e-4,5e-3}, early stopping 10, <= 1000 epochs, one seed each)
+    through gcnb_sweep_run, one model at a time (the reference's loop) and `workers` at a time"""
+    import random
+    rnd = random.Random(5489)
+    trials = [dict(hidden_dims=(16,), dropouts=(d1, d2), epochs=1000, early_stopping=10, learning_rate=0.01, weight_decay=wd,
+                   seed=rnd.randrange(1 << 31))
+              for wd in (5e-5, 5e-4, 5e-3) for d1 in (0.0, 0.2, 0.4, 0.6) for d2 in (0.0, 0.2, 0.4, 0.6)]
+    eng.sweep_run((ROOT, dataset), trials[:4], workers=2)  # warm-up
+    one, wall1 = eng.sweep_run((ROOT, dataset), trials, workers=1)
+    many, wallw = eng.sweep_run((ROOT, dataset), trials, workers=workers)
+    epochs = sum(r["epochs_run"] for r in one)
+    same = all(a[k] == b[k] for a, b in zip(one, many) for k in ("epochs_run", "last_val_accuracy", "last_val_loss"))
+    return {"workload": "tuning sweep on %s: %d trials (2 layers, hidden 16, early stopping 10, <= 1000 epochs)" % (dataset, len(trials)),
+            "epochs_total": epochs, "one_at_a_time": {"wall_s": wall1, "epochs_per_s": epochs / wall1},
+            "concurrent": {"workers": workers, "wall_s": wallw, "epochs_per_s": epochs / wallw},
+            "speedup": wall1 / wallw, "results_identical": same,
+            "mean_val_acc": sum(r["last_val_accuracy"] for r in one) / len(one)}
+
+
 # ------------------------------------------------------------------------------------------------------------------
 def run_ours(args, rank, world, local_rank):
     import torch
@@ -393,6 +450,16 @@ def run_ours(args, rank, world, local_rank):
         line["ref_gpu_same_box_ms"] = rg.get("ms_per_epoch")
         line["ref_gpu_same_box"] = dict(rg, what="the reference's own CUDA code (src/*.cu, -arch=sm_100) on this GPU and dataset, "
                                                  "GCN::run() avg_epoch_time = train epoch + validation forward; separate process")
+        # the other BASELINE.json configs (parity-test cases, reported beside the bench line) and the tuning sweep
+        others = []
+        for name in ("cora", "citeseer", "pubmed"):
+            try:
+                others.append(small_config_record(eng, name))
+            except Exception as e:  # (pubmed needs a writable scratch directory for its synthetic svmlight)
+                others.append({"config": name, "unavailable": repr(e)[:200]})
+        others.append(wide_config_record(eng, ds, w))
+        line["other_configs"] = others
+        line["tuning_sweep"] = tuning_sweep_record(eng)
     if not args.no_scaleout:
         del ds
         dist_mod = importlib.import_module("parallel_gcn_b200.dist")

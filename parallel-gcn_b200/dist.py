@@ -569,7 +569,7 @@ def bench_main(args, rank, world, local_rank, bench):
                            "parallelism": "row-partitioned x%d (native engine): per GraphSum one exchange of the [N x 16] input "
                                           "slabs (%s), grouped NCCL all-reduce of the weight gradients per epoch and of the "
                                           "loss/count scalars per pass" % (world, gather_mode),
-                           "gather_mode": gather_mode, "paths": paths,
+                           "gather_mode": gather_mode, "paths": paths, "halo_exchange_rank0": g.halo_info(),
                            "switches": {k: os.environ[k] for k in sorted(os.environ) if k.startswith("GCNB_")},
                            "l2_policy": "inputs larger than L2", "dataset_gen_s": round(gen_s, 1), "scale": args.scale,
                            "final_train_loss": last[0][0], "final_val_acc": last[1][1]},
