@@ -369,6 +369,12 @@ GCNB_API int64_t gcnb_head_workspace(int64_t n, int in_dim, int num_classes);
 GCNB_API int gcnb_head_f32(const float *d_y, const float *d_w, const int32_t *d_truth, int64_t n, int in_dim, int num_classes,
                            uint32_t num_samples, int training, float *d_logits, float *d_grad, float *d_dy, float *d_result,
                            void *d_ws, int64_t ws_bytes, gcnb_stream_t stream);
+/* the same on the tensor cores (mma.sync TF32, x = hi + lo with all four piece products: fp32-level accuracy, other bits than
+ * the FMA chains); in_dim 16, classes <= 48; same workspace and gcnb_head_reduce_dw_f32 */
+GCNB_API int gcnb_head_tc_supported(int in_dim, int num_classes);
+GCNB_API int gcnb_head_tc_f32(const float *d_y, const float *d_w, const int32_t *d_truth, int64_t n, int in_dim, int num_classes,
+                              uint32_t num_samples, int training, float *d_logits, float *d_grad, float *d_dy, float *d_result,
+                              void *d_ws, int64_t ws_bytes, gcnb_stream_t stream);
 GCNB_API int gcnb_head_reduce_dw_f32(const void *d_ws, float *d_dw, int64_t n, int in_dim, int num_classes,
                                      gcnb_stream_t stream);
 

@@ -116,6 +116,8 @@ _sig("gcnb_softmax_ce_f32", I32, [P, P, P, I64, I32, U32, I32, P, P, P])
 _sig("gcnb_head_supported", I32, [I32, I32])
 _sig("gcnb_head_workspace", I64, [I64, I32, I32])
 _sig("gcnb_head_f32", I32, [P, P, P, I64, I32, I32, U32, I32, P, P, P, P, P, I64, P])
+_sig("gcnb_head_tc_supported", I32, [I32, I32])
+_sig("gcnb_head_tc_f32", I32, [P, P, P, I64, I32, I32, U32, I32, P, P, P, P, P, I64, P])
 _sig("gcnb_head_reduce_dw_f32", I32, [P, P, I64, I32, I32, P])
 _sig("gcnb_adam_step_f32", I32, [P, F32, F32, F32, F32, F32, P])
 _sig("gcnb_sumsq_workspace", I64, [I64])
@@ -588,9 +590,10 @@ def softmax_ce(logits, grad, truth, n, num_classes, num_samples, training, resul
                                   ptr(result), ptr(ws), stream()))
 
 
-def head(y, w, truth, n, in_dim, num_classes, num_samples, training, logits, grad, dy, dw, result, ws):
+def head(y, w, truth, n, in_dim, num_classes, num_samples, training, logits, grad, dy, dw, result, ws, tensor_cores=False):
     """Output head in one kernel (csrc/head.cu): logits = y W, softmax cross-entropy + counts, dy = dz W^T, dW = y^T dz."""
-    check(lib.gcnb_head_f32(ptr(y), ptr(w), ptr(truth), n, in_dim, num_classes, num_samples, int(training), ptr(logits),
+    fn = lib.gcnb_head_tc_f32 if tensor_cores else lib.gcnb_head_f32
+    check(fn(ptr(y), ptr(w), ptr(truth), n, in_dim, num_classes, num_samples, int(training), ptr(logits),
                             ptr(grad), ptr(dy), ptr(result), ptr(ws), ws.numel() * 4, stream()))
     if training:
         check(lib.gcnb_head_reduce_dw_f32(ptr(ws), ptr(dw), n, in_dim, num_classes, stream()))

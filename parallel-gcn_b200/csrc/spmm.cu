@@ -565,7 +565,9 @@ int gcnb_spmm_ld_f32(gcnb_spmm_plan *p, const float *d_values, const uint32_t *d
   if (p->bittile && d_values == p->bittile_values && !d_perm) {  // tensor-core bit tiles + remainder CSR, spmm_bittile.cu
     if (dim == 16 && ldb == 16 && ldc == 16 && (((uintptr_t)d_B | (uintptr_t)d_C) % 16 == 0))
       return gcnb_bittile_spmm16_f32(p->bittile, d_B, d_C, stream_);
-    if (dim >= 64) return gcnb_bittile_spmm_ld_f32(p->bittile, d_B, ldb, d_C, ldc, dim, stream_);  // 16-column slabs
+    // 16-column slabs for every wider operand (the last slab shifted left to end at dim): width 41 on the Reddit-shape graph
+    // = 3 slabs of ~0.25 ms against 2.0 ms for one pass of the generic kernel
+    if (dim > 16) return gcnb_bittile_spmm_ld_f32(p->bittile, d_B, ldb, d_C, ldc, dim, stream_);
   }
   if (p->staged) {  // window-staged fast path (static values, 16-column slabs), spmm_stage.cu
     int handled = 0;

@@ -345,6 +345,7 @@ struct GCNEngineState {
     // staged: per 16-column slab the staged kernel, the remainder kernel and the merge kernel (+ the slab packing kernel
     // when the operand is wider than a slab); a remainder combine kernel, if any, is not counted
     if (graph_bittile && dim == 16) return (size_t)gcnb_bittile_plan_launches(graph_bittile);  // pack, MMA kernel, remainder
+    if (graph_bittile && dim > 16 && !dist) return (size_t)((dim + 15) / 16) * 4;  // per slab: pack, MMA kernel, remainder, add
     const int slabs = graph_staged ? gcnb_spmm_plan_stage_slabs(graph_plan, (int)dim) : 0;
     if (slabs > 0) return (size_t)slabs * (dim == 16 ? 3 : 4);
     return (size_t)graph_spmm_kernels;
@@ -559,7 +560,7 @@ void GCN::init(bool quiet, const natural *h_graph_indptr, const natural *h_graph
     bool wanted = false, d16 = false;
     for (const GCNLayer &ly : st->layers) {
       const natural d = ly.reorder ? ly.in_dim : ly.out_dim;
-      wanted |= d == 16 || d >= 64;
+      wanted |= d >= 16;  // (bit tiles take any width >= 16 as 16-column slabs; window staging 16 and >= 64)
       d16 |= d == 16;
     }
     const char *bt_env = getenv("GCNB_BITTILE");
@@ -1120,9 +1121,14 @@ void GCN::forward_pass(bool training, natural split, cudaStream_t s) {
     // partials only feeds Adam: side stream, joined by the backward pass
     GCNLayer &ly = st->layers.back();
     if (live) {
-      GCNB_CALL(gcnb_head_f32(ly.pre->dev_data.get(), weights[L - 1]->dev_data.get(), dev_truth.get(), N, (int)ly.in_dim,
-                              (int)ly.out_dim, st->cur_num_samples, training, output->dev_data.get(), nullptr,
-                              ly.pre->dev_grad.get(), st->dev_result.get(), st->head_ws.get(), st->head_ws_bytes, s));
+      static const bool tc = [] {  // tuning probe: the tensor-core variant (other bits than the unfused kernels)
+        const char *e = getenv("GCNB_HEAD_TC");
+        return e && atoi(e) != 0;
+      }();
+      auto head_fn = tc && gcnb_head_tc_supported((int)ly.in_dim, (int)ly.out_dim) ? gcnb_head_tc_f32 : gcnb_head_f32;
+      GCNB_CALL(head_fn(ly.pre->dev_data.get(), weights[L - 1]->dev_data.get(), dev_truth.get(), N, (int)ly.in_dim,
+                        (int)ly.out_dim, st->cur_num_samples, training, output->dev_data.get(), nullptr,
+                        ly.pre->dev_grad.get(), st->dev_result.get(), st->head_ws.get(), st->head_ws_bytes, s));
       if (training) {
         CHECK_CUDA_ERROR(cudaEventRecord(st->ev_fork, s));
         CHECK_CUDA_ERROR(cudaStreamWaitEvent(st->side, st->ev_fork, 0));

@@ -420,10 +420,11 @@ def test_softmax_ce(O, gcnb, dev, n, C, training):
         assert_close(to_np(d_g), gw, rtol=1e-5, atol=1e-9, what="ce grad")
 
 
+@pytest.mark.parametrize("tensor_cores", [False, True])
 @pytest.mark.parametrize("n,K,C,training,with_grad", [(5000, 16, 41, 1, 0), (5000, 16, 41, 0, 0), (20011, 16, 41, 1, 1), (2708, 16, 64, 1, 0),
                                                      (1000, 8, 9, 1, 1), (333, 32, 40, 1, 0), (31, 16, 17, 1, 1), (1, 16, 41, 1, 0),
-                                                     (4096, 16, 20, 0, 0), (70000, 16, 41, 1, 0)])
-def test_output_head_in_one_kernel(O, gcnb, dev, n, K, C, training, with_grad):
+                                                     (4096, 16, 20, 0, 0), (70000, 16, 41, 1, 0), (900, 16, 7, 1, 1)])
+def test_output_head_in_one_kernel(O, gcnb, dev, n, K, C, training, with_grad, tensor_cores):
     """csrc/head.cu against the oracle's module chain: Matmul forward, cross-entropy + counts, Matmul backward."""
     import torch
     rng = np.random.default_rng(n * 7 + K + C)
@@ -442,6 +443,8 @@ def test_output_head_in_one_kernel(O, gcnb, dev, n, K, C, training, with_grad):
     if training:
         O.lib.orc_matmul_bwd(n, K, C, O._p(y), O._p(w), O._p(gw), O._p(dy_want), O._p(dw_want))
     assert gcnb.lib.gcnb_head_supported(K, C) == 1
+    if tensor_cores and not gcnb.lib.gcnb_head_tc_supported(K, C):
+        pytest.skip("the tensor-core variant covers in_dim 16, classes <= 48")
     d_y, d_w, d_t = to_dev(y, dev), to_dev(w, dev), to_dev(truth, dev)
     d_z = torch.full((n, C), float("nan"), device=dev)
     d_g = torch.full((n, C), float("nan"), device=dev) if with_grad else None
@@ -451,7 +454,7 @@ def test_output_head_in_one_kernel(O, gcnb, dev, n, K, C, training, with_grad):
     ws = gcnb.zeroed_workspace(gcnb.lib.gcnb_head_workspace(n, K, C), dev)
     outs = []
     for _ in range(2):  # second launch: self-resetting ticket, bit-repeatable sums
-        gcnb.head(d_y, d_w, d_t, n, K, C, ns, training, d_z, d_g, d_dy, d_dw, res, ws)
+        gcnb.head(d_y, d_w, d_t, n, K, C, ns, training, d_z, d_g, d_dy, d_dw, res, ws, tensor_cores=tensor_cores)
         torch.cuda.synchronize()
         outs.append((to_np(res).copy(), to_np(d_dw).copy()))
     r = outs[0][0]
@@ -473,14 +476,26 @@ def test_output_head_in_one_kernel(O, gcnb, dev, n, K, C, training, with_grad):
     res2 = torch.zeros(4, device=dev)
     ws2 = gcnb.zeroed_workspace(gcnb.lib.gcnb_ce_workspace(n), dev)
     gcnb.softmax_ce(z2, g2, d_t, n, C, ns, training, res2, ws2)
-    assert torch.equal(z2, d_z), "fused and unfused logits differ"
+    # head_tc_kernel: split-TF32 products (fp32-level accuracy, other bits); the FMA kernel's element arithmetic is that of the
+    # unfused kernels
+    if tensor_cores:
+        assert_close(to_np(d_z), to_np(z2), rtol=2e-6, atol=2e-6 * float(np.abs(z).max()), what="fused vs unfused logits")
+    else:
+        assert torch.equal(z2, d_z), "fused and unfused logits differ"
     if training:
         dy2 = torch.empty((n, K), device=dev)
         gcnb.matmul_nt(g2, d_w, dy2, n, K, C)
         lab = torch.from_numpy(truth >= 0).to(dev)
-        assert torch.equal(dy2[lab], d_dy[lab]), "fused and unfused dy differ"
+        if tensor_cores:
+            assert_close(to_np(d_dy[lab]), to_np(dy2[lab]), rtol=1e-5, what="fused vs unfused dy")
+            assert float(d_dy[~lab].abs().max()) == 0.0 if bool((~lab).any()) else True
+        else:
+            assert torch.equal(dy2[lab], d_dy[lab]), "fused and unfused dy differ"
         if with_grad:
-            assert torch.equal(g2, d_g)
+            if tensor_cores:
+                assert_close(to_np(d_g), to_np(g2), rtol=1e-5, what="fused vs unfused dz")
+            else:
+                assert torch.equal(g2, d_g)
 
 
 def test_adam_and_sumsq(O, gcnb, dev):

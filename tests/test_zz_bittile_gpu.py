@@ -132,16 +132,20 @@ def test_attached_plan_routes_only_matching_calls(O, gcnb, dev):
     indptr, indices, values = gcn_graph(rng, n, 6, 40, 3)
     d_ip, d_ix, d_v = (to_dev(a, dev) for a in (indptr, indices, values))
     plan = gcnb.SpmmPlan(d_ip, d_ix, n)
-    x16, x41 = torch.randn(n, 16, device=dev), torch.randn(n, 41, device=dev)
-    base16, base41 = torch.empty(n, 16, device=dev), torch.empty(n, 41, device=dev)
+    x16, x41, x7 = torch.randn(n, 16, device=dev), torch.randn(n, 41, device=dev), torch.randn(n, 7, device=dev)
+    base16, base41, base7 = torch.empty(n, 16, device=dev), torch.empty(n, 41, device=dev), torch.empty(n, 7, device=dev)
     plan.spmm(d_v, x16, base16, 16)
     plan.spmm(d_v, x41, base41, 41)
+    plan.spmm(d_v, x7, base7, 7)
     bt = gcnb.BitTilePlan(indptr, indices, values, n, min_tile_nnz=64)
     plan.attach_bittile(bt, d_v)
-    out16, out41 = torch.empty(n, 16, device=dev), torch.empty(n, 41, device=dev)
+    out16, out41, out7 = torch.empty(n, 16, device=dev), torch.full((n, 41), float("nan"), device=dev), torch.empty(n, 7, device=dev)
     plan.spmm(d_v, x16, out16, 16)
     plan.spmm(d_v, x41, out41, 41)
-    assert torch.equal(out41, base41), "other widths stay on the generic kernel"
+    plan.spmm(d_v, x7, out7, 7)
+    assert torch.equal(out7, base7), "widths below 16 stay on the generic kernel"
+    assert not torch.equal(out41, base41), "wider operands run as 16-column slabs through the bit tiles (41 = 3 slabs, the last shifted)"
+    assert_close(to_np(out41), to_np(base41), what="width 41 through bit-tile slabs")
     assert not torch.equal(out16, base16), "width 16 went through the bit tiles (different rounding)"
     assert_close(to_np(out16), to_np(base16), what="attached bit-tile plan")
     other = d_v.clone()
