@@ -216,7 +216,9 @@ TnShape tn_shape(int64_t m, int n, int p) {
   const int tiles = s.tiles_m * s.tiles_n;
   const int sm = std::max(1, device_info().sm_count);
   int slabs = std::max(1, (4 * sm + tiles - 1) / tiles);
-  const int64_t min_slab = 256;
+  // narrow shapes (tn_narrow_kernel) walk 64 rows per iteration with synchronous tile loads: on a small matrix one iteration
+  // per CTA keeps the kernel off the critical path of the epoch (cora, 2708 rows: 11 CTAs x 4 iterations took 22 us)
+  const int64_t min_slab = (n <= 32 && p <= 64) ? 64 : 256;
   slabs = (int)std::max<int64_t>(1, std::min<int64_t>(slabs, (m + min_slab - 1) / min_slab));
   s.k_slab = ((m + slabs - 1) / slabs + 15) / 16 * 16;
   s.slabs = (int)((m + s.k_slab - 1) / s.k_slab);
@@ -257,7 +259,7 @@ int gcnb_matmul_tn_f32(const float *d_A, const float *d_dC, float *d_dB, int64_t
   if (!d_ws || ws_bytes < (int64_t)sh.slabs * n * p * 4) return GCNB_E_BADARG;
   if (n <= 32 && p <= 64 && m >= 512) {  // (the 64 x 64 split-K tiles are 16 % full here: 73 us on cora's 2708 x 16 x 7)
     const int sm = std::max(1, device_info().sm_count);
-    const int ctas = (int)std::min<int64_t>(std::min<int64_t>(4 * sm, sh.slabs), (m + 255) / 256);  // 4 per SM: the tile loads are synchronous
+    const int ctas = (int)std::min<int64_t>(std::min<int64_t>(4 * sm, sh.slabs), (m + 63) / 64);  // 4 per SM: the tile loads are synchronous
     const int64_t rows_per_cta = ((m + ctas - 1) / ctas + 3) / 4 * 4;
     const int used = (int)((m + rows_per_cta - 1) / rows_per_cta);
     if (n <= 16) tn_narrow_kernel<16><<<used, 256, 0, stream>>>(d_A, d_dC, (float *)d_ws, m, n, p, rows_per_cta);

@@ -99,6 +99,8 @@ struct GCNEngineState {
   int64_t halo_info[4] = {0, 0, 0, 0};  // partitioned: {halo exchange active, rows sent, rows of a full push, rows needed}
   GCNRngContext rng;        // this model's Philox consumption history and seed (bound to the calling thread by RngScope)
   bool concurrent = false;  // other models may be running on other host threads: no process-wide timers
+  bool truth_ready[4] = {false, false, false, false};  // dev_truth + split * N holds set_truth(split) (computed on first use)
+  natural cur_split = 0;
   bool defer_sync = false;  // the caller of train_and_eval(sync = false) reads the results after its own synchronisation
   cudaStream_t stream = nullptr;
   gcnb_spmm_plan *graph_plan = nullptr, *feat_plan = nullptr, *feat_csc_plan = nullptr;
@@ -122,7 +124,8 @@ struct GCNEngineState {
   // side stream: work that is independent of the main chain (next epoch's dropout bits, weight gradients of the
   // upper layers) overlaps with the GraphSum / feature products on `stream`
   cudaStream_t side = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_bits = nullptr, ev_epoch = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_bits = nullptr, ev_epoch = nullptr, ev_sq_fork = nullptr, ev_sq_join = nullptr;
+  dev_shared_ptr<real> dev_l2;  // sum of squares of W0 (its own buffer: written on the side stream while the pass runs)
   cudaStream_t comm_stream = nullptr;  // slab exchange of the partitioned GraphSum, overlapped with own-slab windows
   cudaEvent_t ev_cfork = nullptr, ev_gather = nullptr;
   bool overlap_gather = false;
@@ -374,7 +377,7 @@ struct GCNEngineState {
     if (graph_plan) gcnb_spmm_plan_destroy(graph_plan);
     if (graph_bittile) gcnb_bittile_plan_destroy(graph_bittile);
     if (side && side != stream) cudaStreamDestroy(side);
-    for (cudaEvent_t e : {ev_fork, ev_join, ev_bits, ev_epoch, ev_cfork, ev_gather})
+    for (cudaEvent_t e : {ev_fork, ev_join, ev_bits, ev_epoch, ev_cfork, ev_gather, ev_sq_fork, ev_sq_join})
       if (e) cudaEventDestroy(e);
     if (comm_stream) cudaStreamDestroy(comm_stream);
     if (stream) cudaStreamDestroy(stream);
@@ -453,7 +456,7 @@ void GCN::init(bool quiet, const natural *h_graph_indptr, const natural *h_graph
   if (const char *e = getenv("GCNB_SIDE_STREAM")) st->use_side = atoi(e);  // tuning probe: 0 = single stream
   if (st->use_side & 1) CHECK_CUDA_ERROR(cudaStreamCreateWithFlags(&st->side, cudaStreamNonBlocking));
   else st->side = st->stream;
-  for (cudaEvent_t *e : {&st->ev_fork, &st->ev_join, &st->ev_bits, &st->ev_epoch, &st->ev_cfork, &st->ev_gather})
+  for (cudaEvent_t *e : {&st->ev_fork, &st->ev_join, &st->ev_bits, &st->ev_epoch, &st->ev_cfork, &st->ev_gather, &st->ev_sq_fork, &st->ev_sq_join})
     CHECK_CUDA_ERROR(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
   if (st->dist) {
     const char *e = getenv("GCNB_DIST_OVERLAP");  // tuning probe: 0 = exchange and product strictly in sequence
@@ -461,7 +464,7 @@ void GCN::init(bool quiet, const natural *h_graph_indptr, const natural *h_graph
     if (st->overlap_gather) CHECK_CUDA_ERROR(cudaStreamCreateWithFlags(&st->comm_stream, cudaStreamNonBlocking));
   }
   const natural N = params->num_nodes, F = params->input_dim;
-  dev_truth = dev_shared_ptr<integer>(N);
+  dev_truth = dev_shared_ptr<integer>((size_t)N * 4);  // one truth vector per split value 0..3: labels and splits never change
   decays.resize(L, false);  // only W0 is L2-regularised / decayed (src/gcn.cu:157-158)
   decays.front() = true;
 
@@ -477,7 +480,11 @@ void GCN::init(bool quiet, const natural *h_graph_indptr, const natural *h_graph
   if (!st->feat_dense) {
     GCNB_CALL(gcnb_spmm_plan_create(dev_data.dev_feature_index.dev_indptr.get(),
                                     dev_data.dev_feature_index.dev_indices.get(), N, F, 0, st->stream, &st->feat_plan));
-    GCNB_CALL(gcnb_spmm_plan_create(colptr, rowidx, F, N, 0, st->stream, &st->feat_csc_plan));
+    // the transposed feature matrix of a small dataset has a few very long rows (cora: words that occur in 1000+ documents);
+    // with segments of 1024 entries the longest row is one warp's serial chain (24 us of a 109 us cora epoch): short
+    // segments spread it over many warps, the per-segment partials are added in order by the combine kernel
+    const int csc_seg = dev_data.dev_feature_index.indices_size < (size_t(1) << 20) ? 128 : 0;
+    GCNB_CALL(gcnb_spmm_plan_create(colptr, rowidx, F, N, csc_seg, st->stream, &st->feat_csc_plan));
   }
 
   setup_lap("plans (graph, feature csc)");
@@ -824,6 +831,7 @@ void GCN::init(bool quiet, const natural *h_graph_indptr, const natural *h_graph
   st->sumsq_ws = dev_shared_ptr<natural>((gcnb_sumsq_workspace(weights[0]->size) + 3) / 4);
   CHECK_CUDA_ERROR(cudaMemsetAsync(st->ce_ws.get(), 0, st->ce_ws.get_n_elements() * 4, st->stream));
   CHECK_CUDA_ERROR(cudaMemsetAsync(st->sumsq_ws.get(), 0, st->sumsq_ws.get_n_elements() * 4, st->stream));
+  st->dev_l2 = dev_shared_ptr<real>(1);
   st->dev_result = dev_shared_ptr<real>(8);
   CHECK_CUDA_ERROR(cudaMemsetAsync(st->dev_result.get(), 0, 8 * sizeof(real), st->stream));
   st->host_result = pinned_host_ptr<real>(16);
@@ -910,6 +918,7 @@ float GCN::timed_epochs(natural n_epochs, bool with_eval) {
   CHECK_CUDA_ERROR(cudaEventCreate(&e1));
   CHECK_CUDA_ERROR(cudaStreamSynchronize(st->stream));
   CHECK_CUDA_ERROR(cudaEventRecord(e0, st->stream));
+  const auto host_t0 = std::chrono::steady_clock::now();
   for (natural i = 0; i < n_epochs; i++) {
     if (with_eval) {
       std::pair<real, real> tr, va;
@@ -919,7 +928,10 @@ float GCN::timed_epochs(natural n_epochs, bool with_eval) {
     }
   }
   CHECK_CUDA_ERROR(cudaEventRecord(e1, st->stream));
+  const double host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
   CHECK_CUDA_ERROR(cudaEventSynchronize(e1));
+  if (getenv("GCNB_SETUP_VERBOSE"))  // is the loop bound by the host (patch + launch of the replays) or by the device?
+    fprintf(stderr, "[timed] %u epochs: host enqueue %.3f ms (%.1f us per epoch)\n", n_epochs, host_ms, 1e3 * host_ms / std::max(1u, n_epochs));
   if (st->time_graphsum) st->collect_graphsum_times();  // (passes that were only enqueued left their event pairs behind)
   float ms = 0;
   CHECK_CUDA_ERROR(cudaEventElapsedTime(&ms, e0, e1));
@@ -949,9 +961,16 @@ void GCN::set_truth(const natural current_split, cudaStream_t stream) const {
   if (current_split == 1) st->cur_num_samples = params->train_dim;
   else if (current_split == 2) st->cur_num_samples = params->val_dim;
   else if (current_split == 3) st->cur_num_samples = params->test_dim;
-  if (st->live())
-    GCNB_CALL(gcnb_set_truth(dev_truth.get(), dev_data.dev_split.get(), dev_data.dev_label.get(), params->num_nodes,
-                             current_split, stream));
+  // the reference rebuilds the truth vector in every pass (src/gcn.cu:204-226); labels and splits are constants, so each
+  // split's vector is built once and kept (a cora epoch is ~26 dependent launches: two of them were this kernel)
+  const natural k = current_split < 4 ? current_split : 0;
+  st->cur_split = k;
+  if (k != 0 && st->truth_ready[k]) return;
+  if (st->live()) {
+    GCNB_CALL(gcnb_set_truth(dev_truth.get() + (size_t)k * params->num_nodes, dev_data.dev_split.get(), dev_data.dev_label.get(),
+                             params->num_nodes, current_split, stream));
+    if (k != 0) st->truth_ready[k] = true;
+  }
   st->launches++;
 }
 
@@ -969,6 +988,15 @@ void GCN::forward_pass(bool training, natural split, cudaStream_t s) {
   const size_t input_elems = st->dist ? st->f_nnz_global : (size_t)input->size;
   const size_t rows_global = st->dist ? st->n_global : (size_t)N;
   set_truth(split, s);
+  const integer *truth = dev_truth.get() + (size_t)st->cur_split * N;
+  // the L2 term of the decayed weights depends on W0 alone: side stream, off the chain of dependent launches
+  const bool sumsq_aside = st->side != s && !st->dist;
+  if (st->live() && sumsq_aside) {
+    CHECK_CUDA_ERROR(cudaEventRecord(st->ev_sq_fork, s));
+    CHECK_CUDA_ERROR(cudaStreamWaitEvent(st->side, st->ev_sq_fork, 0));
+    GCNB_CALL(gcnb_sumsq_f32(weights[0]->dev_data.get(), weights[0]->size, st->dev_l2.get(), st->sumsq_ws.get(), st->side));
+    CHECK_CUDA_ERROR(cudaEventRecord(st->ev_sq_join, st->side));
+  }
   // ---- layer 0: features never overwritten; training writes the dropped copy into `input`
   const real *xvals = dev_data.dev_feature_value.get();
   const natural *xbits = nullptr;
@@ -1128,7 +1156,7 @@ void GCN::forward_pass(bool training, natural split, cudaStream_t s) {
         return e && atoi(e) != 0;
       }();
       auto head_fn = tc && gcnb_head_tc_supported((int)ly.in_dim, (int)ly.out_dim) ? gcnb_head_tc_f32 : gcnb_head_f32;
-      GCNB_CALL(head_fn(ly.pre->dev_data.get(), weights[L - 1]->dev_data.get(), dev_truth.get(), N, (int)ly.in_dim,
+      GCNB_CALL(head_fn(ly.pre->dev_data.get(), weights[L - 1]->dev_data.get(), truth, N, (int)ly.in_dim,
                         (int)ly.out_dim, st->cur_num_samples, training, output->dev_data.get(), nullptr,
                         ly.pre->dev_grad.get(), st->dev_result.get(), st->head_ws.get(), st->head_ws_bytes, s));
       if (training) {
@@ -1141,7 +1169,7 @@ void GCN::forward_pass(bool training, natural split, cudaStream_t s) {
     }
     if (training) st->launches++;
   } else if (live) {
-    GCNB_CALL(gcnb_softmax_ce_f32(output->dev_data.get(), output->dev_grad.get(), dev_truth.get(), N, params->output_dim,
+    GCNB_CALL(gcnb_softmax_ce_f32(output->dev_data.get(), output->dev_grad.get(), truth, N, params->output_dim,
                                   st->cur_num_samples, training, st->dev_result.get(), st->ce_ws.get(), s));
   }
   if (st->dist) {  // loss sum (float) and wrong / labelled counts (uint32 bit patterns) over all row blocks
@@ -1151,9 +1179,17 @@ void GCN::forward_pass(bool training, natural split, cudaStream_t s) {
     GCNB_CALL(gcnb_comm_group_end(st->comm));
   }
   if (live) {
-    GCNB_CALL(gcnb_sumsq_f32(weights[0]->dev_data.get(), weights[0]->size, st->dev_result.get() + 4, st->sumsq_ws.get(), s));
-    CHECK_CUDA_ERROR(cudaMemcpyAsync(st->host_result.get() + (training ? 0 : 8), st->dev_result.get(), 8 * sizeof(real),
-                                     cudaMemcpyDeviceToHost, s));
+    if (sumsq_aside) {
+      CHECK_CUDA_ERROR(cudaStreamWaitEvent(s, st->ev_sq_join, 0));
+      CHECK_CUDA_ERROR(cudaMemcpyAsync(st->host_result.get() + (training ? 0 : 8) + 4, st->dev_l2.get(), sizeof(real),
+                                       cudaMemcpyDeviceToHost, s));
+      CHECK_CUDA_ERROR(cudaMemcpyAsync(st->host_result.get() + (training ? 0 : 8), st->dev_result.get(), 4 * sizeof(real),
+                                       cudaMemcpyDeviceToHost, s));
+    } else {
+      GCNB_CALL(gcnb_sumsq_f32(weights[0]->dev_data.get(), weights[0]->size, st->dev_result.get() + 4, st->sumsq_ws.get(), s));
+      CHECK_CUDA_ERROR(cudaMemcpyAsync(st->host_result.get() + (training ? 0 : 8), st->dev_result.get(), 8 * sizeof(real),
+                                       cudaMemcpyDeviceToHost, s));
+    }
   }
   st->result_total[training ? 0 : 1] = st->cur_num_samples;
   st->launches += 2;
