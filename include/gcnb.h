@@ -144,6 +144,20 @@ GCNB_API int gcnb_bittile_plan_create(const uint32_t *h_indptr, const uint32_t *
                                       int row_blocks /*0 = 1; 2 = items of 256 rows (chunk 64 only)*/, gcnb_stream_t stream,
                                       gcnb_bittile_plan **out);
 GCNB_API int gcnb_bittile_plan_destroy(gcnb_bittile_plan *plan);
+/* The same plan built ON THE DEVICE from device-resident arrays (parallel-gcn_b200/csrc/spmm_bittile_build.cu): the CSR never
+ * travels to the host; bit-identical to gcnb_bittile_plan_create on the same matrix.  GCNB_E_UNSUPPORTED when the matrix needs
+ * the host builder: entries that do not factor (they keep their values there), no tile at all, more column chunks than the
+ * shared-memory histogram holds (n_cols > ~3.2 M at 64 columns per chunk), scales to be derived from a non-square matrix. */
+GCNB_API int gcnb_bittile_plan_create_device(const uint32_t *d_indptr, const uint32_t *d_indices, const float *d_values,
+                                             int64_t n_rows, int64_t n_cols, const float *d_row_scale, const float *d_col_scale,
+                                             int min_tile_nnz, int chunk_cols, int row_blocks, gcnb_stream_t stream,
+                                             gcnb_bittile_plan **out);
+GCNB_API int gcnb_bittile_device_build_fits(int64_t n_cols, int chunk_cols /*64 or 128*/);
+/* test aid: element counts and contents of a plan's device arrays, whichever builder made them.  which: 0 tile_chunk (u32),
+ * 1 bits (u64), 2 cta_tile_ptr, 3 cta_item_ptr, 4 items (u32 x 2), 5 row_scale (f32), 6 col_scale, 7 ELL idx (u32), 8 ELL off,
+ * 9 ELL steps, 10 ELL rows, 11 ELL split_row, 12 ELL split_ptr; sizes[13] = ELL slots, [14] = entries in tiles, [15] = remainder */
+GCNB_API int gcnb_bittile_plan_sizes(const gcnb_bittile_plan *plan, int64_t sizes[16]);
+GCNB_API int gcnb_bittile_plan_copy(const gcnb_bittile_plan *plan, int which, void *h_dst, int64_t bytes);
 /* 1 when the current device can run the bit-tile kernels (tcgen05 / TMEM: compute capability 10.x) */
 GCNB_API int gcnb_bittile_supported(void);
 /* out = {tiles, entries in tiles, remainder entries, items' row blocks, columns per tile + 1000 * row_blocks

@@ -62,6 +62,9 @@ _sig("gcnb_stage_host_copy", I32, [P, I32, P, I64])
 _sig("gcnb_stage_host_destroy", I32, [P])
 _sig("gcnb_bittile_plan_create", I32, [P, P, P, I64, I64, P, P, I32, I32, I32, P, P])
 _sig("gcnb_bittile_plan_destroy", I32, [P])
+_sig("gcnb_bittile_plan_create_device", I32, [P, P, P, I64, I64, P, P, I32, I32, I32, P, P])
+_sig("gcnb_bittile_plan_sizes", I32, [P, P])
+_sig("gcnb_bittile_plan_copy", I32, [P, I32, P, I64])
 _sig("gcnb_bittile_plan_info", I32, [P, P])
 _sig("gcnb_bittile_spmm16_f32", I32, [P, P, P, P])
 _sig("gcnb_bittile_spmm_ld_f32", I32, [P, P, I64, P, I64, I32, P])
@@ -122,6 +125,9 @@ _sig("gcnb_head_reduce_dw_f32", I32, [P, P, I64, I32, I32, P])
 _sig("gcnb_adam_step_f32", I32, [P, F32, F32, F32, F32, F32, P])
 _sig("gcnb_sumsq_workspace", I64, [I64])
 _sig("gcnb_sumsq_f32", I32, [P, I64, P, P, P])
+
+
+E_BADARG, E_UNSUPPORTED = 10001, 10002  # GCNB_E_* of include/gcnb.h
 
 
 class GcnbError(RuntimeError):
@@ -398,6 +404,39 @@ class BitTilePlan:
         self.h = C.c_void_p()
         check(lib.gcnb_bittile_plan_create(_np_ptr(indptr), _np_ptr(indices), _np_ptr(values), len(indptr) - 1, int(n_cols),
                                            _np_ptr(rs), _np_ptr(cs), min_tile_nnz, chunk_cols, row_blocks, stream(), C.byref(self.h)))
+
+    @classmethod
+    def from_device(cls, d_indptr, d_indices, d_values, n_rows, n_cols, d_row_scale=None, d_col_scale=None, min_tile_nnz=0,
+                    chunk_cols=0, row_blocks=0):
+        """gcnb_bittile_plan_create_device: the same plan built on the GPU from device tensors (None when the matrix needs
+        the host builder, GCNB_E_UNSUPPORTED)"""
+        self = cls.__new__(cls)
+        self.h = C.c_void_p()
+        rc = lib.gcnb_bittile_plan_create_device(ptr(d_indptr), ptr(d_indices), ptr(d_values), int(n_rows), int(n_cols),
+                                                 ptr(d_row_scale), ptr(d_col_scale), min_tile_nnz, chunk_cols, row_blocks,
+                                                 stream(), C.byref(self.h))
+        if rc == E_UNSUPPORTED:
+            self.h = None
+            return None
+        check(rc)
+        return self
+
+    ARRAYS = ("tile_chunk", "bits", "cta_tile_ptr", "cta_item_ptr", "items", "row_scale", "col_scale", "ell_idx", "ell_off",
+              "ell_steps", "ell_rows", "ell_split_row", "ell_split_ptr")
+
+    def arrays(self):
+        """every device array of the plan as numpy (test aid: the host-built and the device-built plan must be identical)"""
+        import numpy as np
+        sz = (I64 * 16)()
+        check(lib.gcnb_bittile_plan_sizes(self.h, sz))
+        out = {"ell_slots": int(sz[13]), "tile_nnz": int(sz[14]), "rem_nnz": int(sz[15])}
+        for which, name in enumerate(self.ARRAYS):
+            dt = np.uint64 if which in (1, 4) else np.uint32  # scales compared as bit patterns
+            a = np.zeros(int(sz[which]), dt)
+            if a.size:
+                check(lib.gcnb_bittile_plan_copy(self.h, which, a.ctypes.data_as(C.c_void_p), a.nbytes))
+            out[name] = a
+        return out
 
     def info(self):
         out = (I64 * 8)()

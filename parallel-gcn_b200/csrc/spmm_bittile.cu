@@ -50,18 +50,13 @@
 #include "bulk.cuh"
 #include "common.cuh"
 #include "spmm_plan.cuh"
+#include "spmm_bittile.cuh"
 #include "tcgen05.cuh"
 
 using namespace gcnb;
 
 namespace gcnb {
 
-constexpr int kBtRows = 128;                 // rows per block = MMA M = TMEM lanes
-constexpr int kBtChunk = 64;                 // columns per tile = 4 MMA k-steps of 16
-constexpr int kBtN = 48;                     // MMA N: 3 bf16 pieces x 16 columns
-constexpr int kBtKStepBytes = kBtN * 16 * 2; // 1536: one 48 x 16 bf16 operand
-constexpr int kBtChunkBytes = 4 * kBtKStepBytes;  // 6144 bytes of packed B' per chunk
-constexpr int kBtThreads = 14 * 32;
 
 // Host-side plan (pure CPU; unit-tested without a GPU through gcnb_bittile_host_*).
 //   CTA q processes tiles [cta_tile_ptr[q], cta_tile_ptr[q+1]) in order; they belong to its items
@@ -111,6 +106,48 @@ struct BlockOut {
 };
 
 }  // namespace
+
+int64_t bittile_schedule(const uint32_t *tiles_of_block, int64_t n_blk, int n_cta, int chunk_cols, int row_blocks,
+                         std::vector<uint32_t> &cta_tile_ptr, std::vector<uint32_t> &cta_item_ptr, std::vector<uint2> &items,
+                         std::vector<uint64_t> &tile_base) {
+  std::vector<uint32_t> order;
+  for (int64_t b = 0; b < n_blk; b++)
+    if (tiles_of_block[b]) order.push_back((uint32_t)b);
+  std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return tiles_of_block[a] > tiles_of_block[b]; });
+  std::vector<std::vector<uint32_t>> per_cta((size_t)n_cta);
+  {
+    typedef std::pair<uint64_t, int> Load;  // (load, cta): smallest load first, ties by CTA index
+    std::priority_queue<Load, std::vector<Load>, std::greater<Load>> pq;
+    for (int q = 0; q < n_cta; q++) pq.push(Load(0, q));
+    for (uint32_t b : order) {
+      Load l = pq.top();
+      pq.pop();
+      per_cta[(size_t)l.second].push_back(b);
+      l.first += ((size_t)tiles_of_block[b] + (size_t)(chunk_cols == 128 ? 3 : 6)) * (size_t)row_blocks;
+      pq.push(l);
+    }
+  }
+  cta_tile_ptr.assign((size_t)n_cta + 1, 0u);
+  cta_item_ptr.assign((size_t)n_cta + 1, 0u);
+  items.clear();
+  tile_base.assign((size_t)n_blk, 0ull);
+  uint64_t tiles = 0;
+  for (int q = 0; q < n_cta; q++) {
+    cta_tile_ptr[(size_t)q] = (uint32_t)tiles;
+    cta_item_ptr[(size_t)q] = (uint32_t)items.size();
+    uint32_t pos = 0;
+    for (uint32_t b : per_cta[(size_t)q]) {
+      tile_base[b] = tiles + pos;
+      pos += tiles_of_block[b];
+      items.push_back(make_uint2(b, pos));
+    }
+    tiles += pos;
+    if (tiles > 0xfffffff0ull) return -1;
+  }
+  cta_tile_ptr[(size_t)n_cta] = (uint32_t)tiles;
+  cta_item_ptr[(size_t)n_cta] = (uint32_t)items.size();
+  return (int64_t)tiles;
+}
 
 int bittile_build_host(const uint32_t *indptr, const uint32_t *indices, const float *values, int64_t n_rows, int64_t n_cols,
                        const float *row_scale, const float *col_scale, int min_tile_nnz, int chunk_cols, int row_blocks,
@@ -250,46 +287,13 @@ int bittile_build_host(const uint32_t *indptr, const uint32_t *indices, const fl
   });
 
   lap("tiles + remainder per block");
-  // CTA schedule: longest-processing-time greedy over the row blocks that own tiles (cost = tiles + a per-block
-  // constant for the epilogue and the pipeline drain); deterministic
-  std::vector<uint32_t> order;
-  for (int64_t b = 0; b < H.n_blk; b++)
-    if (!blocks[(size_t)b].chunks.empty()) order.push_back((uint32_t)b);
-  std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
-    return blocks[a].chunks.size() > blocks[b].chunks.size();
-  });
-  std::vector<std::vector<uint32_t>> per_cta((size_t)H.n_cta);
-  {
-    typedef std::pair<uint64_t, int> Load;  // (load, cta): smallest load first, ties by CTA index
-    std::priority_queue<Load, std::vector<Load>, std::greater<Load>> pq;
-    for (int q = 0; q < H.n_cta; q++) pq.push(Load(0, q));
-    for (uint32_t b : order) {
-      Load l = pq.top();
-      pq.pop();
-      per_cta[(size_t)l.second].push_back(b);
-      l.first += (blocks[b].chunks.size() + (size_t)(chunk_cols == 128 ? 3 : 6)) * (size_t)row_blocks;
-      pq.push(l);
-    }
-  }
-  H.cta_tile_ptr.assign((size_t)H.n_cta + 1, 0u);
-  H.cta_item_ptr.assign((size_t)H.n_cta + 1, 0u);
-  H.items.clear();
-  std::vector<uint64_t> tile_base((size_t)H.n_blk, 0ull);
-  uint64_t tiles = 0;
-  for (int q = 0; q < H.n_cta; q++) {
-    H.cta_tile_ptr[(size_t)q] = (uint32_t)tiles;
-    H.cta_item_ptr[(size_t)q] = (uint32_t)H.items.size();
-    uint32_t pos = 0;
-    for (uint32_t b : per_cta[(size_t)q]) {
-      tile_base[b] = tiles + pos;
-      pos += (uint32_t)blocks[b].chunks.size();
-      H.items.push_back(make_uint2(b, pos));
-    }
-    tiles += pos;
-    if (tiles > 0xfffffff0ull) return GCNB_E_BADARG;
-  }
-  H.cta_tile_ptr[(size_t)H.n_cta] = (uint32_t)tiles;
-  H.cta_item_ptr[(size_t)H.n_cta] = (uint32_t)H.items.size();
+  // CTA schedule (bittile_schedule: shared with the device builder)
+  std::vector<uint32_t> tiles_of_block((size_t)H.n_blk);
+  for (int64_t b = 0; b < H.n_blk; b++) tiles_of_block[(size_t)b] = (uint32_t)blocks[(size_t)b].chunks.size();
+  std::vector<uint64_t> tile_base;
+  const int64_t tiles = bittile_schedule(tiles_of_block.data(), H.n_blk, H.n_cta, chunk_cols, row_blocks, H.cta_tile_ptr,
+                                         H.cta_item_ptr, H.items, tile_base);
+  if (tiles < 0) return GCNB_E_BADARG;
   H.n_tiles = (int64_t)tiles;
   H.tile_chunk.assign((size_t)tiles, 0u);
   H.bits.alloc((size_t)tiles * BH * wpr);
@@ -744,29 +748,6 @@ struct gcnb_bittile_host {
   BitTileHost H;
 };
 
-struct gcnb_bittile_plan {
-  int64_t n_rows = 0, n_cols = 0, nnz = 0, n_blk = 0, n_tiles = 0, tile_nnz = 0, rem_nnz = 0, n_chunks = 0;
-  int n_cta = 0;
-  int chunk = kBtChunk;  // columns per tile (64: bt_mma_wide_kernel<1, 1> / <2, 1>; 128: <1, 2>)
-  int rb = 1;            // 128-row blocks per item (2: bt_mma_wide_kernel<2, 1>)
-  int parts = 15;  // debugging: bit 0 pack, 1 MMA kernel, 2 remainder, 3 final add
-  uint32_t *d_tile_chunk = nullptr, *d_cta_tile_ptr = nullptr, *d_cta_item_ptr = nullptr;
-  uint2 *d_items = nullptr;
-  uint64_t *d_bits = nullptr;
-  uint32_t *d_r_indptr = nullptr, *d_r_indices = nullptr;
-  float *d_r_values = nullptr, *d_row_scale = nullptr, *d_col_scale = nullptr;
-  uint8_t *d_packed = nullptr;
-  float *d_P = nullptr, *d_R = nullptr;
-  gcnb_spmm_plan *rem = nullptr;  // valued remainder CSR on the generic kernel (entries that do not factor exist, or GCNB_BT_ELL=0)
-  gcnb::EllDev *ell = nullptr;    // pattern-only remainder (spmm_ell.cu): every remainder entry factors
-  float *d_B2 = nullptr;          // [n_cols + 1][16]: diag(col_scale) * B of the current launch, last row zero
-  int rem_ctas = 0;               // CTAs per SM of the remainder kernel (0 = its default)
-  int64_t n_unfactored = 0;       // entries whose value is not row_scale * col_scale (0: the matrix is a scaled pattern)
-  uint32_t *d_perm = nullptr;     // gcnb_bittile_plan_set_permutation: plan index k = caller's row perm[k] (needs the merge path)
-  int merge_by_reduction = 1;     // GCNB_BT_MERGE=0 (tuning probe): partial buffers + bt_add_kernel even with the ELL remainder
-  cudaStream_t aux = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-};
 
 namespace {
 template <class T>
@@ -777,6 +758,42 @@ int bt_upload(T **dst, const T *src, size_t n, cudaStream_t stream) {
   return 0;
 }
 }  // namespace
+
+namespace gcnb {
+int bittile_finish_plan(gcnb_bittile_plan *p, cudaStream_t stream) {
+  const bool verbose = getenv("GCNB_SETUP_VERBOSE") != nullptr;
+  auto tp = std::chrono::steady_clock::now();
+  auto lap = [&](const char *what) {
+    if (!verbose) return;
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[bittile finish] %-28s %7.2f ms\n", what, std::chrono::duration<double, std::milli>(now - tp).count());
+    tp = now;
+  };
+  const size_t packed_bytes = std::max<size_t>((size_t)p->n_chunks * kBtChunkBytes, 16);
+  const size_t p_bytes = std::max<size_t>((size_t)p->n_blk * p->rb * kBtRows * 16 * sizeof(float), 16);
+  GCNB_CHECK(cudaMalloc((void **)&p->d_packed, packed_bytes));
+  GCNB_CHECK(cudaMalloc((void **)&p->d_P, p_bytes));
+  GCNB_CHECK(cudaMalloc((void **)&p->d_R, std::max<size_t>((size_t)p->n_rows * 16 * sizeof(float), 16)));
+  lap("operand / partial buffers");
+  GCNB_CHECK(cudaMemsetAsync(p->d_P, 0, p_bytes, stream));  // blocks without tiles stay 0 for ever
+  GCNB_CHECK(cudaStreamSynchronize(stream));
+  lap("synchronise");
+  // tuning probe: cap the remainder kernel's CTAs per SM so that, whichever kernel the block scheduler sees first, the MMA
+  // kernel's CTA (448 threads x 68 registers) still fits on every SM (first measurements: launched at the same instant the
+  // two kernels took 772 us instead of 502)
+  if (const char *e = getenv("GCNB_BT_MERGE")) p->merge_by_reduction = atoi(e) != 0;
+  if (const char *e = getenv("GCNB_BT_REM_CTAS")) p->rem_ctas = std::max(0, atoi(e));
+  GCNB_CHECK(cudaStreamCreateWithFlags(&p->aux, cudaStreamNonBlocking));
+  GCNB_CHECK(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+  GCNB_CHECK(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
+  lap("stream + events");
+  GCNB_CHECK(cudaFuncSetAttribute(bt_mma_wide_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BtWide<1, 1>::kSmemBytes));
+  GCNB_CHECK(cudaFuncSetAttribute(bt_mma_wide_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BtWide<1, 2>::kSmemBytes));
+  GCNB_CHECK(cudaFuncSetAttribute(bt_mma_wide_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BtWide<2, 1>::kSmemBytes));
+  lap("kernel attributes");
+  return 0;
+}
+}  // namespace gcnb
 
 extern "C" {
 
@@ -911,34 +928,11 @@ int gcnb_bittile_plan_create(const uint32_t *h_indptr, const uint32_t *h_indices
   }
   if ((rc = bt_upload(&p->d_row_scale, H.row_scale.data(), H.row_scale.size(), stream))) return fail(rc);
   if ((rc = bt_upload(&p->d_col_scale, H.col_scale.data(), H.col_scale.size(), stream))) return fail(rc);
-  const size_t packed_bytes = std::max<size_t>((size_t)p->n_chunks * kBtChunkBytes, 16);
-  const size_t p_bytes = std::max<size_t>((size_t)p->n_blk * p->rb * kBtRows * 16 * sizeof(float), 16);
-  if ((rc = (int)cudaMalloc((void **)&p->d_packed, packed_bytes))) return fail(rc);
-  if ((rc = (int)cudaMalloc((void **)&p->d_P, p_bytes))) return fail(rc);
-  if ((rc = (int)cudaMalloc((void **)&p->d_R, std::max<size_t>((size_t)n_rows * 16 * sizeof(float), 16)))) return fail(rc);
-  if ((rc = (int)cudaMemsetAsync(p->d_P, 0, p_bytes, stream))) return fail(rc);  // blocks without tiles stay 0 for ever
-  if ((rc = (int)cudaStreamSynchronize(stream))) return fail(rc);                // host arrays go out of scope
-  if (!p->ell && (rc = gcnb_spmm_plan_create(p->d_r_indptr, p->d_r_indices, n_rows, n_cols, 0, stream_, &p->rem))) return fail(rc);
-  // tuning probe: cap the remainder kernel's CTAs per SM so that, whichever kernel the block scheduler sees first, the MMA
-  // kernel's CTA (448 threads x 68 registers) still fits on every SM (first measurements: launched at the same instant the
-  // two kernels took 772 us instead of 502)
-  if (const char *e = getenv("GCNB_BT_MERGE")) p->merge_by_reduction = atoi(e) != 0;
-  if (const char *e = getenv("GCNB_BT_REM_CTAS")) {
-    p->rem_ctas = std::max(0, atoi(e));
-    if (p->rem) p->rem->max_cta_per_sm = p->rem_ctas;
+  if ((rc = bittile_finish_plan(p, stream))) return fail(rc);  // (synchronises: the host arrays go out of scope)
+  if (!p->ell) {
+    if ((rc = gcnb_spmm_plan_create(p->d_r_indptr, p->d_r_indices, n_rows, n_cols, 0, stream_, &p->rem))) return fail(rc);
+    p->rem->max_cta_per_sm = p->rem_ctas;
   }
-  if ((rc = (int)cudaStreamCreateWithFlags(&p->aux, cudaStreamNonBlocking))) return fail(rc);
-  if ((rc = (int)cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming))) return fail(rc);
-  if ((rc = (int)cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming))) return fail(rc);
-  if ((rc = (int)cudaFuncSetAttribute(bt_mma_wide_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)BtWide<1, 1>::kSmemBytes)))
-    return fail(rc);
-  if ((rc = (int)cudaFuncSetAttribute(bt_mma_wide_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)BtWide<1, 2>::kSmemBytes)))
-    return fail(rc);
-  if ((rc = (int)cudaFuncSetAttribute(bt_mma_wide_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)BtWide<2, 1>::kSmemBytes)))
-    return fail(rc);
   *out = p;
   return 0;
 }

@@ -36,41 +36,47 @@ namespace gcnb {
 
 constexpr uint32_t kEllNone = 0xffffffffu;
 
-int ell_build_host(const uint32_t *indptr, const uint32_t *indices, int64_t n_rows, int64_t n_cols, int n_threads,
-                   EllHost &H) {
-  if (!indptr || n_rows < 0 || n_cols < 0 || n_rows > 0xfffffff0ll || n_cols > 0xfffffff0ll) return GCNB_E_BADARG;
-  H.n_rows = n_rows;
-  H.n_cols = n_cols;
-  H.nnz = indptr[n_rows];
-  if (H.nnz > 0 && !indices) return GCNB_E_BADARG;
-  // ---- bundles: wide parts first (longest first), then the short rows sorted by length, 8 per bundle
-  struct Wide { uint32_t row, beg, len, slot; };
-  std::vector<Wide> wide;
-  std::vector<uint32_t> narrow;
+// One wide bundle (a row of more than kEllWideMin entries, or one part of a row of more than kEllWideMax): `beg` is the
+// part's first entry RELATIVE to the row's first entry
+struct EllWide {
+  uint32_t row, beg, len, slot;
+};
+
+// Bundle layout from the rows' lengths alone: wide parts first (longest first), then the short rows sorted by length (longest
+// first, ties by row id), 8 per bundle.  Fills H.off / steps / rows / split_* / n_slots / n_bundles; returns the number of
+// uint4-rows of H.idx in *n_idx_rows.  Shared by the host builder and the device builder (ell_build_device).
+static int ell_layout(const uint32_t *len_of_row, int64_t n_rows, EllHost &H, std::vector<EllWide> &wide,
+                      std::vector<uint32_t> &narrow, uint64_t *n_idx_rows) {
+  wide.clear();
   H.split_row.clear();
   H.split_ptr.assign(1, 0u);
   uint32_t n_slots = 0;
+  // narrow rows by counting sort (descending length, ascending row id inside a length == a stable sort by length)
+  std::vector<uint32_t> bucket((size_t)kEllWideMin + 2, 0u);
   for (int64_t i = 0; i < n_rows; i++) {
-    const uint32_t len = indptr[i + 1] - indptr[i];
+    const uint32_t len = len_of_row[i];
     if (len <= (uint32_t)kEllWideMin) {
-      narrow.push_back((uint32_t)i);
+      bucket[(size_t)kEllWideMin - len + 1]++;
     } else if (len <= (uint32_t)kEllWideMax) {
-      wide.push_back(Wide{(uint32_t)i, indptr[i], len, kEllNone});
+      wide.push_back(EllWide{(uint32_t)i, 0u, len, kEllNone});
     } else {
       const uint32_t parts = (len + kEllWideMax - 1) / kEllWideMax;
       for (uint32_t p = 0; p < parts; p++) {
         const uint32_t b = (uint32_t)((uint64_t)len * p / parts), e = (uint32_t)((uint64_t)len * (p + 1) / parts);
-        wide.push_back(Wide{(uint32_t)i, indptr[i] + b, e - b, n_slots++});
+        wide.push_back(EllWide{(uint32_t)i, b, e - b, n_slots++});
       }
       H.split_row.push_back((uint32_t)i);
       H.split_ptr.push_back(n_slots);
     }
   }
+  for (size_t k = 1; k < bucket.size(); k++) bucket[k] += bucket[k - 1];
+  narrow.assign((size_t)bucket.back(), 0u);
+  for (int64_t i = 0; i < n_rows; i++) {
+    const uint32_t len = len_of_row[i];
+    if (len <= (uint32_t)kEllWideMin) narrow[bucket[(size_t)kEllWideMin - len]++] = (uint32_t)i;
+  }
   H.n_slots = n_slots;
-  std::stable_sort(wide.begin(), wide.end(), [](const Wide &a, const Wide &b) { return a.len > b.len; });
-  std::stable_sort(narrow.begin(), narrow.end(), [&](uint32_t a, uint32_t b) {
-    return indptr[a + 1] - indptr[a] > indptr[b + 1] - indptr[b];
-  });
+  std::stable_sort(wide.begin(), wide.end(), [](const EllWide &a, const EllWide &b) { return a.len > b.len; });
   const size_t n_narrow_b = (narrow.size() + 7) / 8;
   const size_t n_b = wide.size() + n_narrow_b;
   if (n_b > 0x7ffffff0ull) return GCNB_E_BADARG;
@@ -81,15 +87,14 @@ int ell_build_host(const uint32_t *indptr, const uint32_t *indices, int64_t n_ro
   for (size_t b = 0; b < n_b; b++) {
     uint32_t s4;
     if (b < wide.size()) {
-      const Wide &w = wide[b];
+      const EllWide &w = wide[b];
       s4 = ((w.len + 7) / 8 + 3) / 4;
       H.steps[b] = s4 | 0x80000000u;
       H.rows[b * 8 + 0] = w.row;
       H.rows[b * 8 + 1] = w.slot;
     } else {
       const size_t k0 = (b - wide.size()) * 8;
-      const uint32_t r0 = narrow[k0];
-      s4 = (indptr[r0 + 1] - indptr[r0] + 3) / 4;  // the bundle's first row is its longest
+      s4 = (len_of_row[narrow[k0]] + 3) / 4;  // the bundle's first row is its longest
       H.steps[b] = s4;
       for (size_t g = 0; g < 8 && k0 + g < narrow.size(); g++) H.rows[b * 8 + g] = narrow[k0 + g];
     }
@@ -99,6 +104,25 @@ int ell_build_host(const uint32_t *indptr, const uint32_t *indices, int64_t n_ro
   }
   H.off[n_b] = (uint32_t)acc;
   H.n_bundles = (int64_t)n_b;
+  *n_idx_rows = acc;
+  return 0;
+}
+
+int ell_build_host(const uint32_t *indptr, const uint32_t *indices, int64_t n_rows, int64_t n_cols, int n_threads,
+                   EllHost &H) {
+  if (!indptr || n_rows < 0 || n_cols < 0 || n_rows > 0xfffffff0ll || n_cols > 0xfffffff0ll) return GCNB_E_BADARG;
+  H.n_rows = n_rows;
+  H.n_cols = n_cols;
+  H.nnz = indptr[n_rows];
+  if (H.nnz > 0 && !indices) return GCNB_E_BADARG;
+  std::vector<uint32_t> len_of_row((size_t)n_rows);
+  for (int64_t i = 0; i < n_rows; i++) len_of_row[(size_t)i] = indptr[i + 1] - indptr[i];
+  std::vector<EllWide> wide;
+  std::vector<uint32_t> narrow;
+  uint64_t acc = 0;
+  const int lrc = ell_layout(len_of_row.data(), n_rows, H, wide, narrow, &acc);
+  if (lrc) return lrc;
+  const size_t n_b = (size_t)H.n_bundles;
   H.idx.alloc((size_t)acc * 32);
   // ---- fill: idx[((off + k / 4) * 8 + g) * 4 + k % 4] = column of entry k of group g, n_cols (the zero row) as padding
   int T = n_threads > 0 ? n_threads : host_threads();
@@ -110,11 +134,11 @@ int ell_build_host(const uint32_t *indptr, const uint32_t *indices, int64_t n_ro
       const uint32_t s4 = H.steps[b] & 0x7fffffffu;
       uint32_t *base = out + (size_t)H.off[b] * 32;
       if (H.steps[b] & 0x80000000u) {
-        const Wide &w = wide[b];
-        const uint32_t cap = s4 * 32;
+        const EllWide &w = wide[b];
+        const uint32_t cap = s4 * 32, beg = indptr[w.row] + w.beg;
         for (uint32_t e = 0; e < cap; e++) {
           const uint32_t g = e & 7u, k = e >> 3;
-          base[((size_t)(k >> 2) * 8 + g) * 4 + (k & 3u)] = e < w.len ? indices[w.beg + e] : pad;
+          base[((size_t)(k >> 2) * 8 + g) * 4 + (k & 3u)] = e < w.len ? indices[beg + e] : pad;
         }
       } else {
         for (uint32_t g = 0; g < 8; g++) {
@@ -275,6 +299,38 @@ __global__ void __launch_bounds__(256) ell_combine_kernel(const uint32_t *__rest
   ell_out(R + ro * ldr + l * 4, make_float4(acc.x * sc, acc.y * sc, acc.z * sc, acc.w * sc), accumulate != 0);
 }
 
+// Device-side fill of the index array (ell_build_device): one warp per bundle writes its uint4-rows; output word o of a
+// bundle holds step k = (o / 32) * 4 + o % 4 of lane group g = (o % 32) / 4 -- a lane keeps its group for the whole bundle.
+// src[row_beg[r] + k] = k-th entry of row r (k < row_len[r]); wide[b] = (first entry relative to the row, entries) of wide
+// bundle b < n_wide (its row is rows[b * 8])
+__global__ void __launch_bounds__(256) ell_fill_kernel(const uint32_t *__restrict__ off, const uint32_t *__restrict__ steps,
+                                                       const uint32_t *__restrict__ rows, const uint2 *__restrict__ wide,
+                                                       const uint32_t *__restrict__ row_beg, const uint32_t *__restrict__ row_len,
+                                                       const uint32_t *__restrict__ src, uint32_t pad, uint32_t *__restrict__ idx,
+                                                       uint32_t n_bundles) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, kk = lane & 3;
+  const uint32_t n_warps = gridDim.x * (blockDim.x >> 5);
+  for (uint32_t b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); b < n_bundles; b += n_warps) {
+    const uint32_t st = steps[b], s4 = st & 0x7fffffffu;
+    uint32_t *base = idx + (size_t)off[b] * 32;
+    if (st & 0x80000000u) {
+      const uint2 w = wide[b];
+      const uint32_t beg = row_beg[rows[(size_t)b * 8]] + w.x;
+      for (uint32_t k4 = 0; k4 < s4; k4++) {
+        const uint32_t e = (k4 * 4 + kk) * 8 + g;
+        base[k4 * 32 + lane] = e < w.y ? src[beg + e] : pad;
+      }
+    } else {
+      const uint32_t r = rows[(size_t)b * 8 + g];
+      const uint32_t beg = r == kEllNone ? 0u : row_beg[r], len = r == kEllNone ? 0u : row_len[r];
+      for (uint32_t k4 = 0; k4 < s4; k4++) {
+        const uint32_t k = k4 * 4 + kk;
+        base[k4 * 32 + lane] = k < len ? src[beg + k] : pad;
+      }
+    }
+  }
+}
+
 template <class T>
 int ell_upload(T **dst, const T *src, size_t n, cudaStream_t stream) {
   *dst = nullptr;
@@ -308,6 +364,63 @@ int ell_upload_plan(const EllHost &H, cudaStream_t stream, EllDev **out) {
   if (!rc) rc = (int)cudaMalloc((void **)&e->d_counter, 2 * sizeof(uint32_t));
   if (!rc) rc = (int)cudaMemsetAsync(e->d_counter, 0, 2 * sizeof(uint32_t), stream);
   if (!rc) rc = (int)cudaStreamSynchronize(stream);  // the host arrays may go out of scope
+  if (rc) {
+    ell_destroy(e);
+    return rc;
+  }
+  *out = e;
+  return 0;
+}
+
+// The same plan built where the entries already are: d_src[d_row_beg[i] + k] = column of the k-th entry of row i,
+// k < d_row_len[i] (device arrays; the bit-tile device builder leaves its remainder like this).  Only the row lengths travel to
+// the host (4 bytes per row) for the bundle layout; the index array is filled by ell_fill_kernel.  Bit-identical to
+// ell_build_host + ell_upload_plan on the compacted CSR.
+int ell_build_device(const uint32_t *d_row_beg, const uint32_t *d_row_len, const uint32_t *d_src, int64_t n_rows, int64_t n_cols,
+                     cudaStream_t stream, EllDev **out) {
+  *out = nullptr;
+  if (n_rows < 0 || n_cols < 0 || n_rows > 0xfffffff0ll || n_cols > 0xfffffff0ll) return GCNB_E_BADARG;
+  std::vector<uint32_t> len_of_row((size_t)n_rows);
+  if (n_rows) GCNB_CHECK(cudaMemcpyAsync(len_of_row.data(), d_row_len, (size_t)n_rows * 4, cudaMemcpyDeviceToHost, stream));
+  GCNB_CHECK(cudaStreamSynchronize(stream));
+  EllHost H;
+  H.n_rows = n_rows;
+  H.n_cols = n_cols;
+  uint64_t nnz = 0;
+  for (uint32_t l : len_of_row) nnz += l;
+  if (nnz > 0xfffffff0ull) return GCNB_E_BADARG;
+  H.nnz = (int64_t)nnz;
+  std::vector<EllWide> wide;
+  std::vector<uint32_t> narrow;
+  uint64_t acc = 0;
+  const int lrc = ell_layout(len_of_row.data(), n_rows, H, wide, narrow, &acc);
+  if (lrc) return lrc;
+  std::vector<uint2> wide_part(wide.size());
+  for (size_t b = 0; b < wide.size(); b++) wide_part[b] = make_uint2(wide[b].beg, wide[b].len);
+  auto *e = new EllDev();
+  e->n_rows = H.n_rows; e->n_cols = H.n_cols; e->nnz = H.nnz; e->n_bundles = H.n_bundles;
+  e->n_split = (int64_t)H.split_row.size(); e->n_slots = H.n_slots;
+  uint2 *d_wide = nullptr;
+  int rc = 0;
+  if (!rc) rc = (int)cudaMalloc((void **)&e->d_idx, std::max<size_t>((size_t)acc * 32, 1) * 4);
+  if (!rc) rc = ell_upload(&e->d_off, H.off.data(), H.off.size(), stream);
+  if (!rc) rc = ell_upload(&e->d_steps, H.steps.data(), H.steps.size(), stream);
+  if (!rc) rc = ell_upload(&e->d_rows, H.rows.data(), H.rows.size(), stream);
+  if (!rc) rc = ell_upload(&e->d_split_row, H.split_row.data(), H.split_row.size(), stream);
+  if (!rc) rc = ell_upload(&e->d_split_ptr, H.split_ptr.data(), H.split_ptr.size(), stream);
+  if (!rc) rc = ell_upload(&d_wide, wide_part.data(), wide_part.size(), stream);
+  if (!rc) rc = (int)cudaMalloc((void **)&e->d_slots, std::max<size_t>((size_t)H.n_slots * 16 * sizeof(float), 16));
+  if (!rc) rc = (int)cudaMalloc((void **)&e->d_counter, 2 * sizeof(uint32_t));
+  if (!rc) rc = (int)cudaMemsetAsync(e->d_counter, 0, 2 * sizeof(uint32_t), stream);
+  if (!rc && H.n_bundles > 0) {
+    const int64_t want = (H.n_bundles + 7) / 8;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)std::max(1, device_info().sm_count) * 16));
+    ell_fill_kernel<<<grid, 256, 0, stream>>>(e->d_off, e->d_steps, e->d_rows, d_wide, d_row_beg, d_row_len, d_src, (uint32_t)n_cols,
+                                              e->d_idx, (uint32_t)H.n_bundles);
+    rc = (int)cudaPeekAtLastError();
+  }
+  if (!rc) rc = (int)cudaStreamSynchronize(stream);  // the host arrays may go out of scope
+  cudaFree(d_wide);
   if (rc) {
     ell_destroy(e);
     return rc;

@@ -115,6 +115,9 @@ struct EllDev {
 int ell_build_host(const uint32_t *indptr, const uint32_t *indices, int64_t n_rows, int64_t n_cols, int n_threads, EllHost &out);
 int ell_upload_plan(const EllHost &H, cudaStream_t stream, EllDev **out);
 void ell_destroy(EllDev *e);
+// the same plan from device arrays (spmm_ell.cu): d_src[d_row_beg[i] + k] = column of entry k of row i, k < d_row_len[i]
+int ell_build_device(const uint32_t *d_row_beg, const uint32_t *d_row_len, const uint32_t *d_src, int64_t n_rows, int64_t n_cols,
+                     cudaStream_t stream, EllDev **out);
 // R[n_rows x 16] (row stride ldr floats, 16-byte aligned rows) = or += diag(row_scale) * pattern * B2 (B2: n_cols + 1 rows,
 // the last one zero); accumulate: vector reductions into R instead of stores; d_row_map (optional): plan row k is written
 // to row d_row_map[k] of R; ctas_per_sm 0 = default

@@ -625,9 +625,33 @@ void GCN::init(bool quiet, const natural *h_graph_indptr, const natural *h_graph
         for (real &x : s_all) x = x > 0.f ? sqrtf(x) : std::nanf("");  // no usable diagonal: that row / column stays in the remainder
       }
       const size_t row0 = st->row0, n_global = st->n_global;
-      auto make_dist = [N, nnz, d_ip, d_ix, d_gv, row0, n_global, s_all, bt_min_nnz, bt_chunk, bt_rb](cudaStream_t stream, gcnb_bittile_plan **out) -> int {
+      // device builder (csrc/spmm_bittile_build.cu) on this rank's row block x all columns: milliseconds instead of a
+      // read-back + host build + upload, so it runs synchronously (no background thread, no switch epoch)
+      const char *dev_env = getenv("GCNB_BT_DEVICE_BUILD");
+      const bool dev_build = bt_on && d16 && !(dev_env && atoi(dev_env) == 0) && !s_all.empty() &&
+                             gcnb_bittile_device_build_fits((int64_t)n_global, bt_chunk ? bt_chunk : 64) != 0;
+      dev_shared_ptr<real> d_s_all;
+      if (dev_build) {
+        d_s_all = dev_shared_ptr<real>(s_all.size());
+        CHECK_CUDA_ERROR(cudaMemcpy(d_s_all.get(), s_all.data(), s_all.size() * sizeof(real), cudaMemcpyHostToDevice));
+      }
+      const real *d_s = dev_build ? d_s_all.get() : nullptr;
+      auto make_dist = [N, nnz, d_ip, d_ix, d_gv, row0, n_global, s_all, bt_min_nnz, bt_chunk, bt_rb, d_s](cudaStream_t stream, gcnb_bittile_plan **out) -> int {
         *out = nullptr;
         if (nnz < bt_min_nnz) return 0;
+        if (d_s) {
+          gcnb_bittile_plan *bt = nullptr;
+          const int rc = gcnb_bittile_plan_create_device(d_ip, d_ix, d_gv, (int64_t)N, (int64_t)n_global, d_s + row0, d_s, 0, bt_chunk,
+                                                         bt_rb, (gcnb_stream_t)stream, &bt);
+          if (rc == 0) {
+            int64_t binfo[8];
+            gcnb_bittile_plan_info(bt, binfo);
+            if (binfo[0] > 0 && binfo[1] * 4 >= (int64_t)nnz) *out = bt;
+            else gcnb_bittile_plan_destroy(bt);
+            return 0;
+          }
+          if (rc != GCNB_E_UNSUPPORTED) return rc;  // (unsupported: entries that do not factor -> the host builder below)
+        }
         std::vector<natural> hp((size_t)N + 1), hi(nnz);
         std::vector<real> hv(nnz);
         int rc = (int)cudaMemcpyAsync(hp.data(), d_ip, hp.size() * sizeof(natural), cudaMemcpyDeviceToHost, stream);
@@ -651,7 +675,7 @@ void GCN::init(bool quiet, const natural *h_graph_indptr, const natural *h_graph
       // So: bit tiles while the exchanged matrix stays L2-resident (GCNB_BITTILE=1 forces them).
       const bool bt_small_matrix = (double)st->n_global * 16 * sizeof(real) <= 96e6;
       st->bt_collective = bt_on && d16 && (bt_small_matrix || (bt_env && atoi(bt_env) != 0));
-      if (dist_background) {
+      if (dist_background && !(dev_build && st->bt_collective)) {
         st->setup_pending = true;
         int device = 0;
         CHECK_CUDA_ERROR(cudaGetDevice(&device));
@@ -759,7 +783,36 @@ void GCN::init(bool quiet, const natural *h_graph_indptr, const natural *h_graph
         return 0;
       };
       CHECK_CUDA_ERROR(cudaStreamSynchronize(st->stream));  // graph_value may have been computed on this stream
-      if (background) {
+      // Device builder first (csrc/spmm_bittile_build.cu): the CSR is already in HBM, the plan is there a few milliseconds
+      // later and bit-identical to the host builder's, so the FIRST epoch already runs on the tensor cores -- nothing to
+      // build in the background, no switch epoch.  The host path below stays for what it cannot do: matrices with entries
+      // that do not factor, graphs that need the locality renumbering (label propagation on the host), very wide column
+      // ranges, and GCNB_BT_DEVICE_BUILD=0.
+      bool dev_built = false;
+      {
+        const char *e = getenv("GCNB_BT_DEVICE_BUILD");
+        if (bt_on && nnz >= bt_min_nnz && !(e && atoi(e) == 0)) {
+          gcnb_bittile_plan *bt = nullptr;
+          const int rc = gcnb_bittile_plan_create_device(d_ip, d_ix, d_gv, (int64_t)N, (int64_t)N, nullptr, nullptr, 0, bt_chunk,
+                                                         bt_rb, (gcnb_stream_t)st->stream, &bt);
+          if (rc != 0 && rc != GCNB_E_UNSUPPORTED) GCNB_CALL(rc);
+          if (bt) {
+            int64_t binfo[8];
+            gcnb_bittile_plan_info(bt, binfo);
+            const int64_t cover = nnz ? binfo[1] * 100 / (int64_t)nnz : 0;
+            if (cover >= min_cover && cover > 0 && !(renumber && cover < 50 && N > 1)) {
+              st->graph_bittile = bt;
+              GCNB_CALL(gcnb_spmm_plan_attach_bittile(st->graph_plan, st->graph_bittile, d_gv));
+              dev_built = true;
+            } else {
+              gcnb_bittile_plan_destroy(bt);
+            }
+          }
+        }
+      }
+      if (dev_built) {
+        setup_lap("bit tiles built on the device");  // nothing pending
+      } else if (background) {
         st->setup_pending = true;
         if (bt_on) {
           int device = 0;

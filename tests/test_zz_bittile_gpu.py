@@ -87,6 +87,97 @@ def test_duplicates_missing_diagonals_unfactored_values_and_sparse_graphs(O, gcn
     assert info["n_tiles"] == 0
 
 
+def _same_plans(host, devp, what):
+    a, b = host.arrays(), devp.arrays()
+    for k in a:
+        if isinstance(a[k], int):
+            assert a[k] == b[k], (what, k, a[k], b[k])
+        else:
+            assert a[k].shape == b[k].shape, (what, k, a[k].shape, b[k].shape)
+            bad = np.nonzero(a[k] != b[k])[0]
+            assert bad.size == 0, (what, k, int(bad.size), int(bad[0]), a[k][bad[:4]], b[k][bad[:4]])
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("cfg", [dict(n=3000, comm=6, intra=40, inter=3, thr=64, dup=0), dict(n=777, comm=2, intra=60, inter=2, thr=32, dup=60),
+                                 dict(n=20000, comm=5, intra=120, inter=10, thr=0, dup=500), dict(n=5000, comm=2, intra=300, inter=400, thr=1500, dup=0)])
+def test_device_built_plan_is_the_host_built_plan(O, gcnb, dev, cfg, shape):
+    """csrc/spmm_bittile_build.cu: the plan built on the GPU from the device CSR (bit maps by atomicOr, remainder compacted in
+    row order, ELL bundles filled on the device) equals the host builder's array by array -- duplicate entries (the first
+    occurrence owns the bit), ragged last blocks, rows above 256 remainder entries (wide ELL bundles)"""
+    import torch
+    rng = np.random.default_rng(cfg["n"] + 5)
+    indptr, indices, values = gcn_graph(rng, cfg["n"], cfg["comm"], cfg["intra"], cfg["inter"], dup=cfg["dup"])
+    n = cfg["n"]
+    thr = cfg["thr"] * (1 if shape == (64, 1) else 2)
+    host = gcnb.BitTilePlan(indptr, indices, values, n, min_tile_nnz=thr, chunk_cols=shape[0], row_blocks=shape[1])
+    d_ip, d_ix, d_v = to_dev(indptr, dev), to_dev(indices, dev), to_dev(values, dev)
+    devp = gcnb.BitTilePlan.from_device(d_ip, d_ix, d_v, n, n, min_tile_nnz=thr, chunk_cols=shape[0], row_blocks=shape[1])
+    assert devp is not None, "a GraphSum matrix factors: the device builder must take it"
+    assert host.info() == devp.info()
+    assert host.info()["n_tiles"] > 0 and host.info()["ell"] == 1
+    _same_plans(host, devp, cfg)
+    x = to_dev(rng.standard_normal((n, 16)).astype(f32), dev)
+    out_h = torch.full((n, 16), float("nan"), device=dev)
+    out_d = torch.full((n, 16), float("nan"), device=dev)
+    host.spmm16(x, out_h)
+    devp.spmm16(x, out_d)
+    assert torch.equal(out_h, out_d)
+    # explicit scales + a rectangular row block of the same matrix (what a rank of the partitioned engine builds)
+    a = host.arrays()
+    s = a["col_scale"].view(f32)
+    r0, r1 = n // 3, n // 3 + min(n // 2, 2000)
+    ip_blk = (indptr[r0:r1 + 1] - indptr[r0]).astype(np.uint32)
+    ix_blk, v_blk = indices[indptr[r0]:indptr[r1]], values[indptr[r0]:indptr[r1]]
+    host_blk = gcnb.BitTilePlan(ip_blk, ix_blk, v_blk, n, s[r0:r1].copy(), s, min_tile_nnz=thr, chunk_cols=shape[0], row_blocks=shape[1])
+    if host_blk.info()["n_tiles"] > 0:
+        dev_blk = gcnb.BitTilePlan.from_device(to_dev(ip_blk, dev), to_dev(ix_blk, dev), to_dev(v_blk, dev), r1 - r0, n,
+                                               to_dev(s[r0:r1].copy(), dev), to_dev(s, dev), min_tile_nnz=thr, chunk_cols=shape[0],
+                                               row_blocks=shape[1])
+        assert dev_blk is not None
+        _same_plans(host_blk, dev_blk, (cfg, "row block"))
+        dev_blk.close()
+    host_blk.close()
+    host.close()
+    devp.close()
+
+
+def test_device_built_plan_with_hub_rows_and_explicit_scales(gcnb, dev):
+    """rows of 9000 and 20000 remainder entries (ELL parts with partial slots) and a pattern given with explicit scales"""
+    rng = np.random.default_rng(17)
+    n = 12000
+    rows = []
+    for i in range(n):
+        if i in (7, 5000):
+            cols = rng.choice(n, 9000 if i == 7 else 11999, replace=False)
+        else:
+            b0 = (i // 512) * 512
+            cols = np.concatenate([b0 + rng.choice(min(512, n - b0), 40, replace=False), rng.integers(0, n, 3)])
+        rows.append(cols.astype(np.uint32))
+    indptr = np.zeros(n + 1, np.uint32)
+    indptr[1:] = np.cumsum([len(r) for r in rows])
+    indices = np.concatenate(rows)
+    rs, cs = (0.5 + rng.random(n)).astype(f32), (0.5 + rng.random(n)).astype(f32)
+    values = rs[np.repeat(np.arange(n), np.diff(indptr.astype(np.int64)))] * cs[indices]
+    host = gcnb.BitTilePlan(indptr, indices, values, n, rs, cs)
+    assert host.info()["ell"] == 1 and host.arrays()["ell_slots"] > 0
+    for d_v in (to_dev(values, dev), None):  # valued, and the pattern alone
+        devp = gcnb.BitTilePlan.from_device(to_dev(indptr, dev), to_dev(indices, dev), d_v, n, n, to_dev(rs, dev), to_dev(cs, dev))
+        assert devp is not None
+        _same_plans(host, devp, "hub rows")
+        devp.close()
+    host.close()
+
+
+def test_device_builder_hands_unfactored_matrices_to_the_host_builder(gcnb, dev):
+    rng = np.random.default_rng(3)
+    indptr, indices, values = gcn_graph(rng, 777, 3, 30, 2, dup=10, drop_diag=(5, 300))  # rows without a diagonal: no scale
+    assert gcnb.BitTilePlan.from_device(to_dev(indptr, dev), to_dev(indices, dev), to_dev(values, dev), 777, 777, min_tile_nnz=64) is None
+    indptr, indices, values = gcn_graph(rng, 777, 3, 30, 2)
+    values[::7] *= 1.5
+    assert gcnb.BitTilePlan.from_device(to_dev(indptr, dev), to_dev(indices, dev), to_dev(values, dev), 777, 777, min_tile_nnz=64) is None
+
+
 @pytest.mark.parametrize("case", ["short", "mixed", "long"])
 def test_pattern_only_ell_gather_matches_float64(gcnb, dev, case):
     """csrc/spmm_ell.cu on its own: R = diag(row_scale) * pattern * B2 (the remainder kernel of the bit-tile plans)"""
@@ -272,7 +363,10 @@ def test_engine_background_setup_switches_at_a_fixed_epoch(gcnb, dev):
 
     sw = {"GCNB_STAGE_SWITCH_EPOCH": "2"}
     curves = []
-    for extra, kind in (({}, "graph_bittile"), ({"GCNB_BT_MIN_COVERAGE": "101"}, "graph_staged"), ({"GCNB_BITTILE": "0"}, "graph_staged")):
+    # (bit tiles come from the device builder by default -- nothing pending, see the end of this test; GCNB_BT_DEVICE_BUILD=0
+    # keeps the host builder on its helper thread)
+    for extra, kind in (({"GCNB_BT_DEVICE_BUILD": "0"}, "graph_bittile"), ({"GCNB_BT_MIN_COVERAGE": "101"}, "graph_staged"),
+                        ({"GCNB_BITTILE": "0"}, "graph_staged")):
         other = "graph_staged" if kind == "graph_bittile" else "graph_bittile"
         sync = run(ds, dict(extra, GCNB_ASYNC_STAGE="0"))
         assert sync[2][kind] and sync[3][kind] and not sync[2][other] and not sync[2]["setup_pending"], (extra, sync[2], sync[3])
@@ -284,6 +378,11 @@ def test_engine_background_setup_switches_at_a_fixed_epoch(gcnb, dev):
         curves.append(sync)
     same_curve(curves[0], curves[1])
     same_curve(curves[1], curves[2])
+    # default: the plan is built on the device inside the constructor -- bit tiles from the first epoch, the host builder's bits
+    dflt = run(ds, {})
+    assert dflt[2]["graph_bittile"] and not dflt[2]["setup_pending"] and dflt[3]["graph_bittile"], (dflt[2], dflt[3])
+    assert dflt[0] == curves[0][0] and all(np.array_equal(x, y) for x, y in zip(dflt[1], curves[0][1])), \
+        "device-built and host-built plans must give the same bits"
 
 
 # ---- exact-split tcgen05 GEMM for the wide first layer (csrc/dense_tc.cu)
