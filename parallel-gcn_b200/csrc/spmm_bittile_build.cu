@@ -202,8 +202,10 @@ int btb_upload(T **dst, const T *src, size_t n, cudaStream_t stream) {
 
 struct Scratch {  // freed on every exit path
   std::vector<void *> ptrs;
-  ~Scratch() {
+  ~Scratch() { release(); }
+  void release() {
     for (void *p : ptrs) cudaFree(p);
+    ptrs.clear();
   }
   template <class T>
   int alloc(T **dst, size_t n) {
@@ -357,6 +359,8 @@ int gcnb_bittile_plan_create_device(const uint32_t *d_indptr, const uint32_t *d_
   lap("B2 + scale clean-up");
   if ((rc = bittile_finish_plan(p, stream))) return fail(rc);
   lap("buffers");
+  scratch.release();
+  lap("scratch freed");
   *out = p;
   return 0;
 }

@@ -15,7 +15,7 @@
 // broadcasts and a 12-shuffle tree per row on the same pipe as the gathers.  Indices are stored [bundle][step / 4][group]
 // as uint4: the four lanes of a group load the same 16 bytes (one LDG.128 per warp = 128 contiguous bytes = the next four
 // gather steps of all 8 rows).  Rows are padded to the bundle's length with the index of an all-zero row (n_cols).
-// Rows longer than kEllWideMin entries become WIDE bundles: the 8 groups share the row (entry e -> group e % 8) and
+// Rows longer than kEllWideMin entries (64 when the plan has few rows, see ell_layout) become WIDE bundles: the 8 groups share the row (entry e -> group e % 8) and
 // finish with a 3-step shuffle tree; rows longer than kEllWideMax are cut into parts whose partial sums go to slots
 // that ell_combine_kernel adds in ascending order.  Bundles are claimed longest first through one atomic ticket
 // (two tickets and one header ahead).  Fixed summation order => bit-reproducible.
@@ -52,11 +52,16 @@ static int ell_layout(const uint32_t *len_of_row, int64_t n_rows, EllHost &H, st
   H.split_ptr.assign(1, 0u);
   uint32_t n_slots = 0;
   // narrow rows by counting sort (descending length, ascending row id inside a length == a stable sort by length)
-  std::vector<uint32_t> bucket((size_t)kEllWideMin + 2, 0u);
+  // Few rows (a rank's block of a partitioned graph, a small graph): 8 rows per warp leave most of the machine idle and the
+  // longest row of a bundle is one lane group's serial chain (B200, one of 8 row blocks of the bench graph: 75 us for
+  // 3.8 M entries, 4x the full-size rate).  There the 8 groups share every row of more than 64 entries.
+  const uint32_t wide_min = (uint32_t)(n_rows < kEllFewRows ? kEllWideMinFewRows : kEllWideMin);
+  H.wide_min = (int)wide_min;
+  std::vector<uint32_t> bucket((size_t)wide_min + 2, 0u);
   for (int64_t i = 0; i < n_rows; i++) {
     const uint32_t len = len_of_row[i];
-    if (len <= (uint32_t)kEllWideMin) {
-      bucket[(size_t)kEllWideMin - len + 1]++;
+    if (len <= wide_min) {
+      bucket[(size_t)wide_min - len + 1]++;
     } else if (len <= (uint32_t)kEllWideMax) {
       wide.push_back(EllWide{(uint32_t)i, 0u, len, kEllNone});
     } else {
@@ -73,7 +78,7 @@ static int ell_layout(const uint32_t *len_of_row, int64_t n_rows, EllHost &H, st
   narrow.assign((size_t)bucket.back(), 0u);
   for (int64_t i = 0; i < n_rows; i++) {
     const uint32_t len = len_of_row[i];
-    if (len <= (uint32_t)kEllWideMin) narrow[bucket[(size_t)kEllWideMin - len]++] = (uint32_t)i;
+    if (len <= wide_min) narrow[bucket[(size_t)wide_min - len]++] = (uint32_t)i;
   }
   H.n_slots = n_slots;
   std::stable_sort(wide.begin(), wide.end(), [](const EllWide &a, const EllWide &b) { return a.len > b.len; });
@@ -481,7 +486,7 @@ int gcnb_ell_host_sizes(const gcnb_ell_host *h, int64_t out[8]) {
   if (!h || !out) return GCNB_E_BADARG;
   const EllHost &H = h->H;
   out[0] = H.n_rows; out[1] = H.n_cols; out[2] = H.nnz; out[3] = H.n_bundles; out[4] = (int64_t)H.idx.size();
-  out[5] = (int64_t)H.split_row.size(); out[6] = H.n_slots; out[7] = kEllWideMin;
+  out[5] = (int64_t)H.split_row.size(); out[6] = H.n_slots; out[7] = H.wide_min;
   return 0;
 }
 

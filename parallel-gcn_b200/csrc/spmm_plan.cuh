@@ -96,6 +96,8 @@ int stage_build_host(const uint32_t *indptr, const uint32_t *indices, int64_t n_
 
 // ---- pattern-only row gather at width 16 (spmm_ell.cu): the remainder of a bit-tile plan whose entries all factor --------
 constexpr int kEllWideMin = 256;   // rows with more entries are shared by the 8 lane groups of a warp (wide bundle)
+constexpr int kEllFewRows = 65536;          // plans with fewer rows cannot fill the machine with 8 rows per warp:
+constexpr int kEllWideMinFewRows = 64;      // there rows of more than 64 entries are shared already
 constexpr int kEllWideMax = 8192;  // longer rows are cut into parts with partial slots
 // bundles in ticket order; off[b] = first uint4-row of bundle b (a uint4-row = 8 groups x 4 indices = 128 bytes);
 // steps[b] = uint4-rows of the bundle | 0x80000000 for a wide bundle; rows[b*8 + g] = row owned by lane group g
@@ -103,6 +105,7 @@ constexpr int kEllWideMax = 8192;  // longer rows are cut into parts with partia
 // split_row[k] = k-th row assembled from the slots [split_ptr[k], split_ptr[k+1])
 struct EllHost {
   int64_t n_rows = 0, n_cols = 0, nnz = 0, n_bundles = 0, n_slots = 0;
+  int wide_min = kEllWideMin;  // rows with more entries are wide bundles (chosen by the layout)
   HostArray<uint32_t> idx;
   std::vector<uint32_t> off, steps, rows, split_row, split_ptr;
 };

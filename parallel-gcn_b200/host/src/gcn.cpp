@@ -505,8 +505,13 @@ void GCN::init(bool quiet, const natural *h_graph_indptr, const natural *h_graph
   dims.push_back(F);
   for (natural h : params->hidden_dims) dims.push_back(h);
   dims.push_back(params->output_dim);
-  variables.push_back(std::make_shared<Variable>(dev_data.dev_feature_index.indices_size, false, true));
+  // `input` receives the dropped copy of the feature values (src/gcn.cu:50-52).  Its buffer is as large as the feature
+  // matrix (561 MB at Reddit shape) and the dense path never writes it (dropout is a bit mask inside the product kernel):
+  // allocated on first use (forward_pass), never during a captured epoch (the first epoch runs eagerly)
+  variables.push_back(std::make_shared<Variable>(0, false, true));
   input = variables.back();
+  input->size = dev_data.dev_feature_index.indices_size;
+  input->dev_data = dev_shared_ptr<real>();
   variables_info += "input:         " + std::to_string(input->size) + "\n";
   st->layers.resize(L);
   int64_t tn_need = 0;
@@ -789,6 +794,7 @@ void GCN::init(bool quiet, const natural *h_graph_indptr, const natural *h_graph
       // that do not factor, graphs that need the locality renumbering (label propagation on the host), very wide column
       // ranges, and GCNB_BT_DEVICE_BUILD=0.
       bool dev_built = false;
+      setup_lap("variables");
       {
         const char *e = getenv("GCNB_BT_DEVICE_BUILD");
         if (bt_on && nnz >= bt_min_nnz && !(e && atoi(e) == 0)) {
@@ -1081,6 +1087,7 @@ void GCN::forward_pass(bool training, natural split, cudaStream_t s) {
     st->x_train_p = 0.f;
     if (p0 > 0.f || ext) {
       const gcnb_rng_t rng = rng_at(st->f_elem_off);
+      if (!input->dev_data.get()) input->dev_data = dev_shared_ptr<real>(input->size);
       st->rng_site(rng, [&] {
         GCNB_CALL(gcnb_dropout_fwd_oop_f32(xvals, input->dev_data.get(), nullptr, ext, input->size, p0, &rng, s));
       });

@@ -68,18 +68,18 @@ def test_ell_plan_reproduces_the_pattern_product(gcnb, case):
         lens = rng.integers(0, 40, n_rows)
     elif case == "mixed":
         n_rows, n_cols = 97, 3000
-        lens = rng.integers(0, 600, n_rows)     # rows above 256 entries become wide bundles
+        lens = rng.integers(0, 600, n_rows)     # rows above 64 entries become wide bundles (plans with few rows)
         lens[5] = 0
     elif case == "long":
-        n_rows, n_cols = 12, 500
-        lens = np.array([20000, 3, 9000, 0, 257, 256, 8192, 8193, 1, 300, 17000, 5])  # cut rows: parts + slots
+        n_rows, n_cols = 14, 500
+        lens = np.array([20000, 3, 9000, 0, 257, 256, 8192, 8193, 1, 300, 17000, 5, 64, 65])  # cut rows: parts + slots
     else:
         n_rows, n_cols, lens = 9, 4, np.zeros(9, np.int64)
     indptr = np.zeros(n_rows + 1, np.uint32)
     indptr[1:] = np.cumsum(lens)
     indices = rng.integers(0, n_cols, int(indptr[-1])).astype(np.uint32)  # duplicates allowed
     plan = gcnb.ell_host_build(indptr, indices, n_cols)
-    assert plan["nnz"] == indptr[-1] and plan["wide_min"] == 256
+    assert plan["nnz"] == indptr[-1] and plan["wide_min"] == 64  # few rows: the 8 lane groups share rows above 64 entries
     B2 = np.zeros((n_cols + 1, 16), np.float32)
     B2[:n_cols] = rng.standard_normal((n_cols, 16)).astype(np.float32)
     rs = (0.5 + rng.random(n_rows)).astype(np.float32)
@@ -104,6 +104,21 @@ def test_ell_plan_reproduces_the_pattern_product(gcnb, case):
     for kind in (0, 1):
         s = (st[wide == kind] & 0x7fffffff).astype(np.int64)
         assert (np.diff(s) <= 0).all()
+
+
+def test_ell_plans_with_many_rows_keep_eight_rows_per_warp(gcnb):
+    """from 65536 rows on the narrow bundles alone fill the machine: only rows above 256 entries are shared by the lane groups"""
+    rng = np.random.default_rng(8)
+    n_rows, n_cols = 70000, 5000
+    lens = rng.integers(0, 12, n_rows)
+    lens[[3, 500, 69999]] = [256, 257, 100]
+    indptr = np.zeros(n_rows + 1, np.uint32)
+    indptr[1:] = np.cumsum(lens)
+    indices = rng.integers(0, n_cols, int(indptr[-1])).astype(np.uint32)
+    plan = gcnb.ell_host_build(indptr, indices, n_cols)
+    assert plan["wide_min"] == 256
+    wide = plan["steps"] >> 31
+    assert int(wide.sum()) == 1 and plan["rows"][0] == 500  # the one row above 256 entries, first in ticket order
 
 
 def test_bittile_plan_counts_unfactored_entries(gcnb):
