@@ -205,21 +205,28 @@ __global__ void __launch_bounds__(256, 4)
 ell_gather16_kernel(const uint4 *__restrict__ idx4, const uint32_t *__restrict__ off, const uint32_t *__restrict__ steps,
                     const uint32_t *__restrict__ rows, const float *__restrict__ B2, const float *__restrict__ row_scale,
                     float *__restrict__ R, int64_t ldr, int accumulate, const uint32_t *__restrict__ row_map,
-                    float *__restrict__ slots, uint32_t *__restrict__ counter, uint32_t n_bundles) {
+                    float *__restrict__ slots, uint32_t *__restrict__ counter, uint32_t n_bundles, uint32_t static_stride) {
   const int lane = threadIdx.x & 31, g = lane >> 2, l = lane & 3;
   const float *B2l = B2 + l * 4;
+  // static_stride > 0 (plans with few rows: many short bundles): warp w takes bundles w, w + stride, ... -- the ticket
+  // counter is ONE address, and tens of thousands of atomics on it cost more than the short bundles they hand out
   uint32_t t = 0, tn = 0;
-  if (lane == 0) {
-    t = atomicAdd(counter, 1u);
-    tn = atomicAdd(counter, 1u);
+  if (static_stride) {
+    t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    tn = t + static_stride;
+  } else {
+    if (lane == 0) {
+      t = atomicAdd(counter, 1u);
+      tn = atomicAdd(counter, 1u);
+    }
+    t = __shfl_sync(0xffffffffu, t, 0);
+    tn = __shfl_sync(0xffffffffu, tn, 0);
   }
-  t = __shfl_sync(0xffffffffu, t, 0);
-  tn = __shfl_sync(0xffffffffu, tn, 0);
   EllHeader h{0, 0, kEllNone, kEllNone}, hn{0, 0, kEllNone, kEllNone};
   if (t < n_bundles) h = ell_header(off, steps, rows, t, g);
   while (t < n_bundles) {
-    uint32_t tnn = 0;
-    if (lane == 0) tnn = atomicAdd(counter, 1u);                       // two tickets ahead
+    uint32_t tnn = tn + static_stride;
+    if (!static_stride && lane == 0) tnn = atomicAdd(counter, 1u);     // two tickets ahead
     if (tn < n_bundles) hn = ell_header(off, steps, rows, tn, g);      // one header ahead
     const uint32_t n4 = h.steps & 0x7fffffffu;
     const bool wide = (h.steps & 0x80000000u) != 0u;
@@ -274,7 +281,7 @@ ell_gather16_kernel(const uint4 *__restrict__ idx4, const uint32_t *__restrict__
     }
     t = tn;
     h = hn;
-    tn = __shfl_sync(0xffffffffu, tnn, 0);
+    tn = static_stride ? tnn : __shfl_sync(0xffffffffu, tnn, 0);
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -358,6 +365,7 @@ int ell_upload_plan(const EllHost &H, cudaStream_t stream, EllDev **out) {
   auto *e = new EllDev();
   e->n_rows = H.n_rows; e->n_cols = H.n_cols; e->nnz = H.nnz; e->n_bundles = H.n_bundles;
   e->n_split = (int64_t)H.split_row.size(); e->n_slots = H.n_slots;
+  e->static_schedule = H.wide_min != kEllWideMin;
   int rc = 0;
   if (!rc) rc = ell_upload(&e->d_idx, H.idx.data(), H.idx.size(), stream);
   if (!rc) rc = ell_upload(&e->d_off, H.off.data(), H.off.size(), stream);
@@ -405,6 +413,7 @@ int ell_build_device(const uint32_t *d_row_beg, const uint32_t *d_row_len, const
   auto *e = new EllDev();
   e->n_rows = H.n_rows; e->n_cols = H.n_cols; e->nnz = H.nnz; e->n_bundles = H.n_bundles;
   e->n_split = (int64_t)H.split_row.size(); e->n_slots = H.n_slots;
+  e->static_schedule = H.wide_min != kEllWideMin;
   uint2 *d_wide = nullptr;
   int rc = 0;
   if (!rc) rc = (int)cudaMalloc((void **)&e->d_idx, std::max<size_t>((size_t)acc * 32, 1) * 4);
@@ -443,7 +452,7 @@ int ell_launch(EllDev *e, const float *d_B2, const float *d_row_scale, float *d_
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)std::max(1, di.sm_count) * per_sm));
   ell_gather16_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const uint4 *>(e->d_idx), e->d_off, e->d_steps, e->d_rows,
                                                 d_B2, d_row_scale, d_R, ldr, accumulate, d_row_map, e->d_slots, e->d_counter,
-                                                (uint32_t)e->n_bundles);
+                                                (uint32_t)e->n_bundles, e->static_schedule ? (uint32_t)grid * 8u : 0u);
   GCNB_LAUNCH_CHECK();
   if (e->n_split > 0) {
     ell_combine_kernel<<<(unsigned)((e->n_split * 4 + 255) / 256), 256, 0, stream>>>(e->d_split_row, e->d_split_ptr, e->d_slots,

@@ -114,6 +114,7 @@ struct EllDev {
   uint32_t *d_idx = nullptr, *d_off = nullptr, *d_steps = nullptr, *d_rows = nullptr, *d_split_row = nullptr,
            *d_split_ptr = nullptr, *d_counter = nullptr;
   float *d_slots = nullptr;
+  bool static_schedule = false;  // few-rows plans: bundles dealt round-robin to the warps instead of through the ticket counter
 };
 int ell_build_host(const uint32_t *indptr, const uint32_t *indices, int64_t n_rows, int64_t n_cols, int n_threads, EllHost &out);
 int ell_upload_plan(const EllHost &H, cudaStream_t stream, EllDev **out);
