@@ -273,6 +273,10 @@ int gcnb_bittile_plan_create_device(const uint32_t *d_indptr, const uint32_t *d_
   auto *p = new gcnb_bittile_plan();
   auto fail = [&](int code) {
     gcnb_bittile_plan_destroy(p);
+    if (code == (int)cudaErrorMemoryAllocation) {  // no room for the scratch (4 bytes per entry): the host builder's business
+      cudaGetLastError();
+      return GCNB_E_UNSUPPORTED;
+    }
     return code;
   };
   Scratch scratch;
