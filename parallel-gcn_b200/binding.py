@@ -398,7 +398,7 @@ class BitTilePlan:
         import numpy as np
         indptr = np.ascontiguousarray(indptr, np.uint32)
         indices = np.ascontiguousarray(indices, np.uint32)
-        values = np.ascontiguousarray(values, np.float32)
+        values = None if values is None else np.ascontiguousarray(values, np.float32)  # None: a pattern scaled by rs x cs
         rs = None if row_scale is None else np.ascontiguousarray(row_scale, np.float32)
         cs = None if col_scale is None else np.ascontiguousarray(col_scale, np.float32)
         self.h = C.c_void_p()

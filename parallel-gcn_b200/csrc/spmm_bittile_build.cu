@@ -17,7 +17,8 @@
 //                       others are compacted in order into the row's remainder
 //   ell_build_device    remainder -> ELL bundles (spmm_ell.cu)
 // Restrictions (the caller falls back to the host builder on GCNB_E_UNSUPPORTED): the chunk histogram must fit shared memory
-// (n_cols <= ~3.2 M at 64 columns per chunk) and every entry must factor as row_scale * col_scale (GraphSum's always do).
+// (32-bit counters up to ~3.2 M columns at 64 columns per chunk, saturating 16-bit counters up to 4.19 M) and every entry must
+// factor as row_scale * col_scale (GraphSum's always do).
 //
 // Reference being replaced: none (set-up of the kernels that replace graphsum_kernel, src/module.cu:172-186).
 #include <algorithm>
@@ -35,8 +36,8 @@ using namespace gcnb;
 namespace {
 
 constexpr int kBtbThreads = 512;
-constexpr uint32_t kBtbNoTile = 0xffffffffu;
-constexpr size_t kBtbSmemMax = 200 * 1024;  // dynamic shared memory of the two block kernels: 4 bytes per column chunk
+constexpr size_t kBtbSmemMax = 200 * 1024;  // dynamic shared memory of the two block kernels: 4 bytes per column chunk ...
+constexpr int64_t kBtbMaxChunks16 = 65534;   // ... or 2 (saturating 16-bit counters; a tile slot must fit 16 bits too)
 
 __device__ __forceinline__ int btb_bit_of_col(uint32_t c) {  // = bt_bit_of_col (spmm_bittile.cu), c in [0, 64)
   const uint32_t cc = c & 31u;
@@ -89,19 +90,44 @@ struct BtbArgs {
   unsigned long long *counters;  // [0] entries in tiles, [1] entries that do not factor
 };
 
-__device__ __forceinline__ void btb_histogram(const BtbArgs &a, uint32_t *cnt, int64_t r0, int64_t r1) {
-  for (uint32_t c = threadIdx.x; c < a.n_chunks; c += blockDim.x) cnt[c] = 0u;
+// Counters: 32-bit, or -- for column ranges whose 32-bit histogram would not fit shared memory -- 16-bit halves of 32-bit
+// words that SATURATE: a count is only ever compared with the threshold (<= 0x7fff), and an increment is skipped once the
+// half reads 0x7fff or more; the at most 512 threads that pass that test together leave it below 0x8200, so a half never
+// carries into its neighbour.
+template <class CT>
+struct BtbCounter;
+template <>
+struct BtbCounter<uint32_t> {
+  static constexpr uint32_t kNoTile = 0xffffffffu;
+  static __device__ __forceinline__ void inc(uint32_t *cnt, uint32_t c) { atomicAdd(&cnt[c], 1u); }
+};
+template <>
+struct BtbCounter<uint16_t> {
+  static constexpr uint32_t kNoTile = 0xffffu;
+  static __device__ __forceinline__ void inc(uint16_t *cnt, uint32_t c) {
+    uint32_t *w = reinterpret_cast<uint32_t *>(cnt) + (c >> 1);
+    const uint32_t sh = (c & 1u) * 16u;
+    if (((*reinterpret_cast<volatile uint32_t *>(w) >> sh) & 0xffffu) < 0x7fffu) atomicAdd(w, 1u << sh);
+  }
+};
+
+template <class CT>
+__device__ __forceinline__ void btb_histogram(const BtbArgs &a, CT *cnt, int64_t r0, int64_t r1) {
+  const uint32_t n_zero = sizeof(CT) == 2 ? a.n_chunks + (a.n_chunks & 1u) : a.n_chunks;  // whole 32-bit words
+  for (uint32_t c = threadIdx.x; c < n_zero; c += blockDim.x) cnt[c] = (CT)0;
   __syncthreads();
   const uint32_t e1 = a.indptr[r1];
   for (uint32_t e = a.indptr[r0] + threadIdx.x; e < e1; e += blockDim.x) {
     const uint32_t c = a.indices[e] >> a.shift;
-    if (c < a.n_chunks) atomicAdd(&cnt[c], 1u);
+    if (c < a.n_chunks) BtbCounter<CT>::inc(cnt, c);
   }
   __syncthreads();
 }
 
+template <class CT>
 __global__ void __launch_bounds__(kBtbThreads) btb_count_kernel(BtbArgs a) {
-  extern __shared__ uint32_t cnt[];
+  extern __shared__ uint32_t btb_smem[];
+  CT *cnt = reinterpret_cast<CT *>(btb_smem);
   __shared__ uint32_t total;
   const int64_t r0 = (int64_t)blockIdx.x * a.bh, r1 = min(a.n_rows, r0 + a.bh);
   if (threadIdx.x == 0) total = 0u;
@@ -114,8 +140,11 @@ __global__ void __launch_bounds__(kBtbThreads) btb_count_kernel(BtbArgs a) {
   if (threadIdx.x == 0) a.tiles_of_block[blockIdx.x] = total;
 }
 
+template <class CT>
 __global__ void __launch_bounds__(kBtbThreads) btb_fill_kernel(BtbArgs a) {
-  extern __shared__ uint32_t cnt[];  // histogram, then chunk -> tile slot of this block (kBtbNoTile: not a tile)
+  extern __shared__ uint32_t btb_smem[];
+  CT *cnt = reinterpret_cast<CT *>(btb_smem);  // histogram, then chunk -> tile slot of this block (kNoTile: not a tile)
+  constexpr uint32_t kBtbNoTile = BtbCounter<CT>::kNoTile;
   __shared__ uint32_t warp_tot[kBtbThreads / 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t r0 = (int64_t)blockIdx.x * a.bh, r1 = min(a.n_rows, r0 + a.bh);
@@ -138,9 +167,9 @@ __global__ void __launch_bounds__(kBtbThreads) btb_fill_kernel(BtbArgs a) {
   for (uint32_t c = c0; c < c1; c++) {
     if (cnt[c] >= a.thr) {
       a.tile_chunk[tb + slot] = c;
-      cnt[c] = slot++;
+      cnt[c] = (CT)slot++;
     } else {
-      cnt[c] = kBtbNoTile;
+      cnt[c] = (CT)kBtbNoTile;
     }
   }
   __syncthreads();
@@ -223,7 +252,8 @@ extern "C" {
 // 1 when a matrix of n_cols columns fits the device builder's shared-memory histogram (one counter per column chunk)
 int gcnb_bittile_device_build_fits(int64_t n_cols, int chunk_cols) {
   if (chunk_cols != 64 && chunk_cols != 128) chunk_cols = 64;
-  return n_cols > 0 && (size_t)((n_cols + chunk_cols - 1) / chunk_cols) * 4 <= kBtbSmemMax;
+  const int64_t n_chunks = (n_cols + chunk_cols - 1) / chunk_cols;
+  return n_cols > 0 && ((size_t)n_chunks * 4 <= kBtbSmemMax || n_chunks <= kBtbMaxChunks16);
 }
 
 // gcnb_bittile_plan_create with every input array ON THE DEVICE (d_values / the two scale arrays may be NULL as there: scales
@@ -258,8 +288,12 @@ int gcnb_bittile_plan_create_device(const uint32_t *d_indptr, const uint32_t *d_
   const int64_t BH = (int64_t)kBtRows * row_blocks;
   const int64_t n_blk = (n_rows + BH - 1) / BH;
   const int64_t n_chunks = (n_cols + chunk_cols - 1) / chunk_cols;
-  const size_t smem = (size_t)n_chunks * 4;
-  if (smem > kBtbSmemMax) return GCNB_E_UNSUPPORTED;
+  // 32-bit counters while they fit shared memory, else saturating 16-bit ones (GCNB_BTB_COUNTER16=1: test probe, always 16)
+  bool counter16 = (size_t)n_chunks * 4 > kBtbSmemMax;
+  if (const char *e = getenv("GCNB_BTB_COUNTER16")) counter16 = counter16 || atoi(e) != 0;
+  const uint32_t thr_arg = (uint32_t)(min_tile_nnz > 0 ? min_tile_nnz : 2 * chunk_cols * row_blocks);
+  if (counter16 && (n_chunks > kBtbMaxChunks16 || thr_arg > 0x7fffu)) return GCNB_E_UNSUPPORTED;
+  const size_t smem = counter16 ? ((size_t)n_chunks * 2 + 3) / 4 * 4 : (size_t)n_chunks * 4;
   const bool verbose = getenv("GCNB_SETUP_VERBOSE") != nullptr;
   auto tp = std::chrono::steady_clock::now();
   auto lap = [&](const char *what) {
@@ -301,12 +335,14 @@ int gcnb_bittile_plan_create_device(const uint32_t *d_indptr, const uint32_t *d_
   BtbArgs a{};
   a.indptr = d_indptr; a.indices = d_indices; a.values = d_values; a.row_scale = p->d_row_scale; a.col_scale = p->d_col_scale;
   a.n_rows = n_rows; a.n_chunks = (uint32_t)n_chunks;
-  a.thr = (uint32_t)(min_tile_nnz > 0 ? min_tile_nnz : 2 * chunk_cols * row_blocks);
+  a.thr = thr_arg;
   a.bh = (int)BH; a.shift = chunk_cols == 128 ? 7 : 6; a.chunk_cols = chunk_cols; a.wpr = chunk_cols / 64;
   if ((rc = scratch.alloc(&a.tiles_of_block, (size_t)n_blk))) return fail(rc);
-  if ((rc = (int)cudaFuncSetAttribute(btb_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return fail(rc);
-  if ((rc = (int)cudaFuncSetAttribute(btb_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return fail(rc);
-  btb_count_kernel<<<(unsigned)n_blk, kBtbThreads, smem, stream>>>(a);
+  auto count_fn = counter16 ? btb_count_kernel<uint16_t> : btb_count_kernel<uint32_t>;
+  auto fill_fn = counter16 ? btb_fill_kernel<uint16_t> : btb_fill_kernel<uint32_t>;
+  if ((rc = (int)cudaFuncSetAttribute(count_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return fail(rc);
+  if ((rc = (int)cudaFuncSetAttribute(fill_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return fail(rc);
+  count_fn<<<(unsigned)n_blk, kBtbThreads, smem, stream>>>(a);
   if ((rc = (int)cudaPeekAtLastError())) return fail(rc);
   std::vector<uint32_t> tiles_of_block((size_t)n_blk);
   if ((rc = (int)cudaMemcpyAsync(tiles_of_block.data(), a.tiles_of_block, (size_t)n_blk * 4, cudaMemcpyDeviceToHost, stream))) return fail(rc);
@@ -339,7 +375,7 @@ int gcnb_bittile_plan_create_device(const uint32_t *d_indptr, const uint32_t *d_
   if ((rc = scratch.alloc(&a.counters, 2))) return fail(rc);
   if ((rc = (int)cudaMemsetAsync(a.counters, 0, 16, stream))) return fail(rc);
   a.tile_base = d_tile_base; a.tile_chunk = p->d_tile_chunk; a.bits = reinterpret_cast<unsigned long long *>(p->d_bits);
-  btb_fill_kernel<<<(unsigned)n_blk, kBtbThreads, smem, stream>>>(a);
+  fill_fn<<<(unsigned)n_blk, kBtbThreads, smem, stream>>>(a);
   if ((rc = (int)cudaPeekAtLastError())) return fail(rc);
   unsigned long long counters[2] = {0, 0};
   if ((rc = (int)cudaMemcpyAsync(counters, a.counters, 16, cudaMemcpyDeviceToHost, stream))) return fail(rc);

@@ -169,6 +169,43 @@ def test_device_built_plan_with_hub_rows_and_explicit_scales(gcnb, dev):
     host.close()
 
 
+def test_device_builder_with_saturating_16_bit_counters(gcnb, dev):
+    """column ranges whose 32-bit chunk histogram would not fit shared memory (> 3.2 M columns) count in saturating 16-bit
+    halves; forced here on small graphs (GCNB_BTB_COUNTER16=1), odd and even chunk counts, a chunk that saturates"""
+    rng = np.random.default_rng(23)
+    cases = [gcn_graph(rng, 3000, 6, 40, 3, dup=30) + (64,), gcn_graph(rng, 4100, 3, 200, 10) + (0,)]
+    # one row block x one chunk with > 0x7fff entries: 256 rows x 64 columns full of duplicates
+    n = 600
+    rows = np.repeat(np.arange(256), 64 * 3)
+    cols = np.tile(np.tile(np.arange(64), 3), 256)
+    extra_r, extra_c = np.arange(n), np.arange(n)  # a diagonal, so every row and column has a scale
+    rr, cc = np.concatenate([extra_r, rows]), np.concatenate([extra_c, cols])
+    order = np.argsort(rr, kind="stable")
+    rr, cc = rr[order], cc[order]
+    ip = np.zeros(n + 1, np.uint32)
+    ip[1:] = np.cumsum(np.bincount(rr, minlength=n))
+    sc = (0.5 + rng.random(n)).astype(f32)
+    os.environ["GCNB_BTB_COUNTER16"] = "1"
+    try:
+        for indptr, indices, values, thr in cases:
+            nn = len(indptr) - 1
+            host = gcnb.BitTilePlan(indptr, indices, values, nn, min_tile_nnz=thr)
+            devp = gcnb.BitTilePlan.from_device(to_dev(indptr, dev), to_dev(indices, dev), to_dev(values, dev), nn, nn, min_tile_nnz=thr)
+            assert devp is not None
+            _same_plans(host, devp, "16-bit counters")
+            host.close()
+            devp.close()
+        host = gcnb.BitTilePlan(ip, cc.astype(np.uint32), None, n, sc, sc)
+        assert host.info()["n_tiles"] >= 1 and host.info()["ell"] == 1
+        devp = gcnb.BitTilePlan.from_device(to_dev(ip, dev), to_dev(cc.astype(np.uint32), dev), None, n, n, to_dev(sc, dev), to_dev(sc, dev))
+        assert devp is not None
+        _same_plans(host, devp, "saturated chunk")
+        host.close()
+        devp.close()
+    finally:
+        os.environ.pop("GCNB_BTB_COUNTER16", None)
+
+
 def test_device_builder_hands_unfactored_matrices_to_the_host_builder(gcnb, dev):
     rng = np.random.default_rng(3)
     indptr, indices, values = gcn_graph(rng, 777, 3, 30, 2, dup=10, drop_diag=(5, 300))  # rows without a diagonal: no scale
