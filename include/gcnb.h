@@ -147,7 +147,7 @@ GCNB_API int gcnb_bittile_plan_destroy(gcnb_bittile_plan *plan);
 /* The same plan built ON THE DEVICE from device-resident arrays (parallel-gcn_b200/csrc/spmm_bittile_build.cu): the CSR never
  * travels to the host; bit-identical to gcnb_bittile_plan_create on the same matrix.  GCNB_E_UNSUPPORTED when the matrix needs
  * the host builder: entries that do not factor (they keep their values there), no tile at all, more column chunks than the
- * shared-memory histogram holds (n_cols > ~3.2 M at 64 columns per chunk), scales to be derived from a non-square matrix. */
+ * shared-memory histogram holds (n_cols > 4.19 M at 64 columns per chunk), scales to be derived from a non-square matrix. */
 GCNB_API int gcnb_bittile_plan_create_device(const uint32_t *d_indptr, const uint32_t *d_indices, const float *d_values,
                                              int64_t n_rows, int64_t n_cols, const float *d_row_scale, const float *d_col_scale,
                                              int min_tile_nnz, int chunk_cols, int row_blocks, gcnb_stream_t stream,
