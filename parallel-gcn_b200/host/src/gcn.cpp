@@ -512,6 +512,7 @@ void GCN::init(bool quiet, const natural *h_graph_indptr, const natural *h_graph
   input = variables.back();
   input->size = dev_data.dev_feature_index.indices_size;
   input->dev_data = dev_shared_ptr<real>();
+  if (!Variable::sizes.empty() && Variable::sizes.back() == 0) Variable::sizes.back() = input->size;  // (the reference's bookkeeping)
   variables_info += "input:         " + std::to_string(input->size) + "\n";
   st->layers.resize(L);
   int64_t tn_need = 0;
