@@ -453,7 +453,12 @@ void GCN::init(bool quiet, const natural *h_graph_indptr, const natural *h_graph
       gcnb_set_host_threads((int)std::max<size_t>(2, std::thread::hardware_concurrency() / world));
   }
   CHECK_CUDA_ERROR(cudaStreamCreateWithFlags(&st->stream, cudaStreamNonBlocking));
-  if (const char *e = getenv("GCNB_SIDE_STREAM")) st->use_side = atoi(e);  // tuning probe: 0 = single stream
+  // wide hidden layers (parameters_reddit.txt: 600): the weight-gradient GEMMs are milliseconds of full-machine work, and
+  // running them beside the main chain's persistent tcgen05 kernels costs more than it hides (B200, hidden 600: 12.7 ms per
+  // epoch with the side stream, 11.5 without) -- one stream there
+  for (natural h : params->hidden_dims)
+    if (h >= 64) st->use_side = 0;
+  if (const char *e = getenv("GCNB_SIDE_STREAM")) st->use_side = atoi(e);  // tuning probe: 0 = single stream, 3 = both uses
   if (st->use_side & 1) CHECK_CUDA_ERROR(cudaStreamCreateWithFlags(&st->side, cudaStreamNonBlocking));
   else st->side = st->stream;
   for (cudaEvent_t *e : {&st->ev_fork, &st->ev_join, &st->ev_bits, &st->ev_epoch, &st->ev_cfork, &st->ev_gather, &st->ev_sq_fork, &st->ev_sq_join})
