@@ -1319,6 +1319,23 @@ void GCN::backward_pass(cudaStream_t s) {
   };
   if (!st->dense_fast && st->feat_dense) join_side();  // that branch re-uses the split-K workspace
   if (st->dense_fast) {
+    if (st->phase == GCNEngineState::Eager && (st->use_side & 2) && !st->ext_masks[0].get() && params->dropouts.front() > 0.f &&
+        !st->graphs_usable()) {
+      // Keep bits of the NEXT epoch's input dropout, on the side stream, into the other buffer (its last reader was the
+      // previous epoch's weight-gradient product, long done on `s`).  167 us of Philox arithmetic: started HERE it runs
+      // beside the HBM-bound weight-gradient product and the evaluation's feature product, which leave the ALUs idle;
+      // started at the top of the epoch (until r2) it spilled into the first GraphSum (216 -> 246 us per call on one box).
+      join_side();  // the upper layers' weight gradients are long done: join them now, not behind the keep bits
+      st->next_bits_rng = rng_at(st->f_elem_off);
+      st->next_bits_p = params->dropouts.front();
+      CHECK_CUDA_ERROR(cudaEventRecord(st->ev_epoch, s));
+      CHECK_CUDA_ERROR(cudaStreamWaitEvent(st->side, st->ev_epoch, 0));
+      GCNB_CALL(gcnb_dropout_maskbits(st->x_bits_next.get(), params->num_nodes, (int)params->input_dim, st->next_bits_p,
+                                      &st->next_bits_rng, st->side));
+      CHECK_CUDA_ERROR(cudaEventRecord(st->ev_bits, st->side));
+      st->launches++;
+      st->next_bits_valid = true;
+    }
     GCNB_CALL(gcnb_dense_feat_tn_f32(x_tn, st->x_train_ax ? nullptr : st->x_train_bits, st->x_train_ax ? 0.f : st->x_train_p, g0,
                                      weights[0]->dev_grad.get(), N, (int)F, (int)l0.out_dim, st->dense_tn_ws.get(),
                                      st->dense_tn_ws_bytes, s));
@@ -1379,20 +1396,7 @@ std::pair<real, real> GCN::read_result(int slot) const {
 // host bookkeeping plus the patches of the per-epoch kernel arguments)
 void GCN::train_body(cudaStream_t s) {
   forward_pass(true, 1, s);
-  if (st->phase == GCNEngineState::Eager && (st->use_side & 2) && st->dense_fast && !st->ext_masks[0].get() &&
-      params->dropouts.front() > 0.f && !st->graphs_usable()) {
-    // keep bits of the next epoch's input dropout, on the side stream, into the other buffer (its last reader was
-    // the previous epoch's weight-gradient product, ordered by ev_epoch)
-    st->next_bits_rng = rng_at(st->f_elem_off);
-    st->next_bits_p = params->dropouts.front();
-    CHECK_CUDA_ERROR(cudaStreamWaitEvent(st->side, st->ev_epoch, 0));
-    GCNB_CALL(gcnb_dropout_maskbits(st->x_bits_next.get(), params->num_nodes, (int)params->input_dim, st->next_bits_p,
-                                    &st->next_bits_rng, st->side));
-    CHECK_CUDA_ERROR(cudaEventRecord(st->ev_bits, st->side));
-    st->launches++;
-    st->next_bits_valid = true;
-  }
-  backward_pass(s);
+  backward_pass(s);  // (the dense path forks the next epoch's keep bits off just before its weight-gradient product)
   const real step_size = optimizer.advance();
   if (st->phase == GCNEngineState::Replay) {
     GCNB_CALL(gcnb_graph_patch_node(st->train_exec, st->train_sites[st->site_cursor++], nullptr, &step_size));
