@@ -119,6 +119,7 @@ struct GCNEngineState {
   // stream is a pure function of the consumption history, so the descriptor is known as soon as this epoch's
   // forward has been enqueued); used only if the descriptor still matches when the next epoch starts
   bool next_bits_valid = false;
+  bool bits_fork_late = true;  // keep bits of the next epoch: forked off before the weight-gradient product (GCNB_BITS_FORK_LATE=0: at the top of the epoch)
   gcnb_rng_t next_bits_rng{};
   real next_bits_p = 0.f;
   // side stream: work that is independent of the main chain (next epoch's dropout bits, weight gradients of the
@@ -459,6 +460,7 @@ void GCN::init(bool quiet, const natural *h_graph_indptr, const natural *h_graph
   for (natural h : params->hidden_dims)
     if (h >= 64) st->use_side = 0;
   if (const char *e = getenv("GCNB_SIDE_STREAM")) st->use_side = atoi(e);  // tuning probe: 0 = single stream, 3 = both uses
+  if (const char *e = getenv("GCNB_BITS_FORK_LATE")) st->bits_fork_late = atoi(e) != 0;
   if (st->use_side & 1) CHECK_CUDA_ERROR(cudaStreamCreateWithFlags(&st->side, cudaStreamNonBlocking));
   else st->side = st->stream;
   for (cudaEvent_t *e : {&st->ev_fork, &st->ev_join, &st->ev_bits, &st->ev_epoch, &st->ev_cfork, &st->ev_gather, &st->ev_sq_fork, &st->ev_sq_join})
@@ -1319,8 +1321,8 @@ void GCN::backward_pass(cudaStream_t s) {
   };
   if (!st->dense_fast && st->feat_dense) join_side();  // that branch re-uses the split-K workspace
   if (st->dense_fast) {
-    if (st->phase == GCNEngineState::Eager && (st->use_side & 2) && !st->ext_masks[0].get() && params->dropouts.front() > 0.f &&
-        !st->graphs_usable()) {
+    if (st->bits_fork_late && st->phase == GCNEngineState::Eager && (st->use_side & 2) && !st->ext_masks[0].get() &&
+        params->dropouts.front() > 0.f && !st->graphs_usable()) {
       // Keep bits of the NEXT epoch's input dropout, on the side stream, into the other buffer (its last reader was the
       // previous epoch's weight-gradient product, long done on `s`).  167 us of Philox arithmetic: started HERE it runs
       // beside the HBM-bound weight-gradient product and the evaluation's feature product, which leave the ALUs idle;
@@ -1396,6 +1398,18 @@ std::pair<real, real> GCN::read_result(int slot) const {
 // host bookkeeping plus the patches of the per-epoch kernel arguments)
 void GCN::train_body(cudaStream_t s) {
   forward_pass(true, 1, s);
+  if (!st->bits_fork_late && st->phase == GCNEngineState::Eager && (st->use_side & 2) && st->dense_fast && !st->ext_masks[0].get() &&
+      params->dropouts.front() > 0.f && !st->graphs_usable()) {
+    // tuning probe (the placement until r2): the next epoch's keep bits start with this epoch, ordered by ev_epoch
+    st->next_bits_rng = rng_at(st->f_elem_off);
+    st->next_bits_p = params->dropouts.front();
+    CHECK_CUDA_ERROR(cudaStreamWaitEvent(st->side, st->ev_epoch, 0));
+    GCNB_CALL(gcnb_dropout_maskbits(st->x_bits_next.get(), params->num_nodes, (int)params->input_dim, st->next_bits_p,
+                                    &st->next_bits_rng, st->side));
+    CHECK_CUDA_ERROR(cudaEventRecord(st->ev_bits, st->side));
+    st->launches++;
+    st->next_bits_valid = true;
+  }
   backward_pass(s);  // (the dense path forks the next epoch's keep bits off just before its weight-gradient product)
   const real step_size = optimizer.advance();
   if (st->phase == GCNEngineState::Replay) {
